@@ -1,0 +1,115 @@
+// Shared helpers for libdesire_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/desire_abi.h"
+
+namespace desire {
+
+void set_error(const char* fmt, ...);
+
+#define DESIRE_CHECK_ARG(cond, ...)            \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::desire::set_error(__VA_ARGS__);        \
+      return DESIRE_ERR_INVALID;               \
+    }                                          \
+  } while (0)
+
+#define DESIRE_CUDA(call)                                                              \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      ::desire::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                 \
+                          cudaGetErrorString(e_));                                     \
+      return DESIRE_ERR_CUDA;                                                          \
+    }                                                                                  \
+  } while (0)
+
+#define DESIRE_LAUNCH_CHECK() DESIRE_CUDA(cudaGetLastError())
+
+#define DESIRE_TRY(call)          \
+  do {                            \
+    int rc_ = (call);             \
+    if (rc_ != DESIRE_OK) return rc_; \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Workspace {
+  char* base;
+  size_t cap, off;
+  Workspace(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T));
+    if (off + bytes > cap) return nullptr;
+    T* r = (T*)(base + off);
+    off += bytes;
+    return r;
+  }
+};
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case DESIRE_ACT_RELU: return fmaxf(x, 0.f);
+    case DESIRE_ACT_ELU: return x > 0.f ? x : (expf(x) - 1.f);
+    case DESIRE_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    default: return x;
+  }
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- internal cross-file entry points (all asynchronous on `st`)
+// C[M,N] (ldc) = act(A @ B + bias) (+C if accumulate).  A via loader (see gemm_f32.cu), B [K,N] ldb,
+// or, when trans_b, B stored [N,K] (ldb = K stride).
+struct Im2col {
+  // A(m,k): m = (img, oy, ox), k = (ky, kx, ci) over an NHWC input, zero outside
+  int Hi, Wi, Ci, Ho, Wo, kh, kw, stride, pad_t, pad_l;
+};
+int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const float* bias, float* C,
+          int ldc, int M, int N, int K, int act, bool accumulate, cudaStream_t st);
+int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const float* bias, float* C,
+                 int ldc, int M, int N, int K, int act, cudaStream_t st);
+
+// GRU recurrence (gru.cu).  xp: hoisted input projection incl. biases, [.., 3H] = (r|u|c) per row.
+struct GruSeqArgs {
+  int R, H, T;
+  const float* xp;          // may be null when traj != null
+  long xp_row_stride;       // floats
+  long xp_step_stride;      // 0 => constant input
+  const float* traj;        // [R,T,3] (id,x,y): input width 2 projected inline with wx_g/wx_c rows 0,1
+  const float *wx_g, *wx_c, *bg, *bc;
+  const float* ex;          // extra per-step operand [R,Ka] (only with T==1), or null
+  int Ka, ld_ex;
+  const float* w_g;         // [(Ka+H), 2H]: rows 0..Ka-1 multiply ex, the rest multiply h
+  const float* w_c;         // [(Ka+H), H]
+  const float* h0;          // null => zeros; row = r / h0_div, stride ld_h0
+  int h0_div, ld_h0;
+  float* hs;                // all states: hs + r*hs_row_stride + t*hs_step_stride, or null
+  long hs_row_stride, hs_step_stride;
+  float* h_final;           // [R] rows, stride ld_hf, or null
+  int ld_hf;
+};
+int gru_seq(const GruSeqArgs& a, cudaStream_t st);
+
+// col2im + bias + per-row BN + activation (cvae.cu): col [R*Hin*Hin, k*k*Cout] -> out [R,Hout,Hout,Cout]
+int colbn_act(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int Cout,
+              const float* bias, const float* gamma, const float* beta, int act, float* out,
+              cudaStream_t st);
+
+}  // namespace desire

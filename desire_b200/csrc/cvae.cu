@@ -1,0 +1,197 @@
+// Conv-CVAE of the sample-generation stage (model/model.py:453-492, utils/convolutional_vae_util.py).
+//
+// Every conv / deconv layer is a GEMM plus one fused "col2im + bias + per-row BN + activation"
+// kernel.  Forward convs gather (im2col loader inside the GEMM, k=1 identity col2im);
+// transposed convs run in SCATTER form: col = X[R*Pin, Cin] @ W^T[Cin, k*k*Cout] does exactly the
+// algorithmic MACs (no stride-2 zero taps), and the col2im kernel gathers each col element once.
+// BN is the reference's batch-of-one statistics: per row and channel over the H*W positions
+// (DESIGN.md D5), two-pass variance, eps = 1e-3.
+#include "common.cuh"
+
+namespace desire {
+namespace {
+
+constexpr float BN_EPS = 1e-3f;
+
+// one CTA per row; out tile [Hout*Hout*Cout] lives in shared memory between the passes
+__global__ void __launch_bounds__(256) colbn_act_kernel(const float* __restrict__ col, int Hin, int Hout, int k,
+                                                        int stride, int pad, int Cout,
+                                                        const float* __restrict__ bias,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int act,
+                                                        float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  const int Pout = Hout * Hout, n = Pout * Cout;
+  float* tile = sm;            // [n]
+  float* red = sm + n;         // [256]
+  float* stat = red + 256;     // [2*Cout] mean, rstd
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const size_t r = blockIdx.x;
+  const int kk = k * k;
+  const float* colr = col + r * (size_t)Hin * Hin * kk * Cout;
+
+  for (int e = tid; e < n; e += nthr) {
+    int o = e % Cout, p = e / Cout;
+    int oy = p / Hout, ox = p % Hout;
+    float acc = bias ? __ldg(bias + o) : 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      int ty = oy + pad - ky;
+      if (ty < 0 || ty % stride) continue;
+      int iy = ty / stride;
+      if (iy >= Hin) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        int tx = ox + pad - kx;
+        if (tx < 0 || tx % stride) continue;
+        int ix = tx / stride;
+        if (ix >= Hin) continue;
+        acc += __ldg(colr + ((size_t)(iy * Hin + ix) * kk + ky * k + kx) * Cout + o);
+      }
+    }
+    tile[e] = acc;
+  }
+  __syncthreads();
+
+  // per-channel moments over the Pout positions: thread (o, part) strides positions by `parts`
+  const int parts = nthr / Cout;          // Cout in {1,32,64,128} <= nthr
+  const int o = tid % Cout, part = tid / Cout;
+  const bool on = part < parts;
+  float s = 0.f;
+  if (on)
+    for (int p = part; p < Pout; p += parts) s += tile[p * Cout + o];
+  red[tid] = on ? s : 0.f;
+  __syncthreads();
+  if (tid < Cout) {
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += red[q * Cout + tid];
+    stat[tid] = t / (float)Pout;
+  }
+  __syncthreads();
+  const float mean = stat[o];
+  s = 0.f;
+  if (on)
+    for (int p = part; p < Pout; p += parts) {
+      float d = tile[p * Cout + o] - mean;
+      s += d * d;
+    }
+  __syncthreads();
+  red[tid] = on ? s : 0.f;
+  __syncthreads();
+  if (tid < Cout) {
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += red[q * Cout + tid];
+    stat[Cout + tid] = 1.f / sqrtf(t / (float)Pout + BN_EPS);
+  }
+  __syncthreads();
+  float* outr = out + r * (size_t)n;
+  for (int e = tid; e < n; e += nthr) {
+    int oc = e % Cout;
+    float v = __ldg(gamma + oc) * ((tile[e] - stat[oc]) * stat[Cout + oc]) + __ldg(beta + oc);
+    outr[e] = act_apply(v, act);
+  }
+}
+
+}  // namespace
+
+int colbn_act(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int Cout, const float* bias,
+              const float* gamma, const float* beta, int act, float* out, cudaStream_t st) {
+  if (R == 0) return DESIRE_OK;
+  DESIRE_CHECK_ARG(Cout >= 1 && Cout <= 256 && 256 % Cout == 0, "colbn_act: Cout=%d unsupported", Cout);
+  size_t smem = ((size_t)Hout * Hout * Cout + 256 + 2 * Cout) * sizeof(float);
+  DESIRE_CHECK_ARG(smem <= 227 * 1024, "colbn_act: tile too large");
+  DESIRE_CUDA(cudaFuncSetAttribute(colbn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  colbn_act_kernel<<<R, 256, smem, st>>>(col, Hin, Hout, k, stride, pad, Cout, bias, gamma, beta, act, out);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}
+
+}  // namespace desire
+
+using namespace desire;
+
+// ------------------------------------------------------------------------------------------ encoder
+static const int ENC_CHUNK = 8192;
+
+extern "C" size_t desire_cvae_encode_workspace_bytes(int M, int Z) {
+  (void)Z;
+  size_t mc = M < ENC_CHUNK ? M : ENC_CHUNK;
+  // col (<= mc*256*32) + a1 (mc*8192) + a2 (mc*4096) + a3 (mc*2048)
+  return align_up(mc * 8192 * 4) + align_up(mc * 8192 * 4) + align_up(mc * 4096 * 4) + align_up(mc * 2048 * 4);
+}
+
+extern "C" int desire_cvae_encode_fwd(const float* v, int M, int Z, const desire_cvae_enc_t* w, float* mu_logvar,
+                                      void* ws, size_t ws_bytes, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(v && w && mu_logvar && M >= 0 && Z > 0, "desire_cvae_encode_fwd: bad arguments");
+  if (!ws || ws_bytes < desire_cvae_encode_workspace_bytes(M, Z)) {
+    set_error("desire_cvae_encode_fwd: workspace too small");
+    return DESIRE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int m0 = 0; m0 < M; m0 += ENC_CHUNK) {
+    const int mc = (M - m0) < ENC_CHUNK ? (M - m0) : ENC_CHUNK;
+    Workspace W(ws, ws_bytes);
+    float* col = W.take<float>((size_t)mc * 8192);
+    float* a1 = W.take<float>((size_t)mc * 8192);
+    float* a2 = W.take<float>((size_t)mc * 4096);
+    float* a3 = W.take<float>((size_t)mc * 2048);
+    const float* x = v + (size_t)m0 * 1024;
+    // conv5/2 SAME 32x32x1 -> 16x16x32 : pad_before = 1 (TF: total 3 -> 1 | 2)
+    Im2col g1{32, 32, 1, 16, 16, 5, 5, 2, 1, 1};
+    DESIRE_TRY(sgemm_im2col(x, g1, w->c1.w, 32, nullptr, col, 32, mc * 256, 32, 25, DESIRE_ACT_NONE, st));
+    DESIRE_TRY(colbn_act(col, mc, 16, 16, 1, 1, 0, 32, w->c1.b, w->c1.gamma, w->c1.beta, DESIRE_ACT_ELU, a1, st));
+    // conv5/2 SAME 16x16x32 -> 8x8x64
+    Im2col g2{16, 16, 32, 8, 8, 5, 5, 2, 1, 1};
+    DESIRE_TRY(sgemm_im2col(a1, g2, w->c2.w, 64, nullptr, col, 64, mc * 64, 64, 800, DESIRE_ACT_NONE, st));
+    DESIRE_TRY(colbn_act(col, mc, 8, 8, 1, 1, 0, 64, w->c2.b, w->c2.gamma, w->c2.beta, DESIRE_ACT_ELU, a2, st));
+    // conv5 VALID 8x8x64 -> 4x4x128
+    Im2col g3{8, 8, 64, 4, 4, 5, 5, 1, 0, 0};
+    DESIRE_TRY(sgemm_im2col(a2, g3, w->c3.w, 128, nullptr, col, 128, mc * 16, 128, 1600, DESIRE_ACT_NONE, st));
+    DESIRE_TRY(colbn_act(col, mc, 4, 4, 1, 1, 0, 128, w->c3.b, w->c3.gamma, w->c3.beta, DESIRE_ACT_ELU, a3, st));
+    // flatten (h,w,c) -> fc 2048 -> 2Z, no BN, no activation
+    DESIRE_TRY(sgemm(a3, 2048, w->fc_w, 2 * Z, false, w->fc_b, mu_logvar + (size_t)m0 * 2 * Z, 2 * Z, mc, 2 * Z, 2048,
+                     DESIRE_ACT_NONE, false, st));
+  }
+  return DESIRE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ decoder
+static const int DEC_CHUNK = 4096;
+
+extern "C" size_t desire_cvae_decode_workspace_bytes(int R, int Z) {
+  (void)Z;
+  size_t rc = R < DEC_CHUNK ? R : DEC_CHUNK;
+  // col (<= rc*64*800) + a1 (rc*2048) + a2 (rc*4096) + a3 (rc*8192)
+  return align_up(rc * 51200 * 4) + align_up(rc * 2048 * 4) + align_up(rc * 4096 * 4) + align_up(rc * 8192 * 4);
+}
+
+extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire_cvae_dec_t* w, float* xr, void* ws,
+                                      size_t ws_bytes, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(z && w && xr && R >= 0 && Z > 0, "desire_cvae_decode_fwd: bad arguments");
+  if (!ws || ws_bytes < desire_cvae_decode_workspace_bytes(R, Z)) {
+    set_error("desire_cvae_decode_fwd: workspace too small");
+    return DESIRE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int r0 = 0; r0 < R; r0 += DEC_CHUNK) {
+    const int rc = (R - r0) < DEC_CHUNK ? (R - r0) : DEC_CHUNK;
+    Workspace W(ws, ws_bytes);
+    float* col = W.take<float>((size_t)rc * 51200);
+    float* a1 = W.take<float>((size_t)rc * 2048);
+    float* a2 = W.take<float>((size_t)rc * 4096);
+    float* a3 = W.take<float>((size_t)rc * 8192);
+    const float* zc = z + (size_t)r0 * Z;
+    // deconv4 VALID 1x1xZ -> 4x4x128: col[r, (y,x,o)] = z[r,:] . W[y,x,o,:]
+    DESIRE_TRY(sgemm(zc, Z, w->d1.w, Z, true, nullptr, col, 2048, rc, 2048, Z, DESIRE_ACT_NONE, false, st));
+    DESIRE_TRY(colbn_act(col, rc, 1, 4, 4, 1, 0, 128, w->d1.b, w->d1.gamma, w->d1.beta, DESIRE_ACT_ELU, a1, st));
+    // deconv5 VALID 4x4x128 -> 8x8x64
+    DESIRE_TRY(sgemm(a1, 128, w->d2.w, 128, true, nullptr, col, 1600, rc * 16, 1600, 128, DESIRE_ACT_NONE, false, st));
+    DESIRE_TRY(colbn_act(col, rc, 4, 8, 5, 1, 0, 64, w->d2.b, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, a2, st));
+    // deconv5/2 SAME 8x8x64 -> 16x16x32 (full 19x19, keep [1,17))
+    DESIRE_TRY(sgemm(a2, 64, w->d3.w, 64, true, nullptr, col, 800, rc * 64, 800, 64, DESIRE_ACT_NONE, false, st));
+    DESIRE_TRY(colbn_act(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st));
+    // deconv5/2 SAME 16x16x32 -> 32x32x1, BN + sigmoid
+    DESIRE_TRY(sgemm(a3, 32, w->d4.w, 32, true, nullptr, col, 25, rc * 256, 25, 32, DESIRE_ACT_NONE, false, st));
+    DESIRE_TRY(colbn_act(col, rc, 16, 32, 5, 2, 1, 1, w->d4.b, w->d4.gamma, w->d4.beta, DESIRE_ACT_SIGMOID,
+                         xr + (size_t)r0 * 1024, st));
+  }
+  return DESIRE_OK;
+}

@@ -1,0 +1,161 @@
+// FP32 CUDA-core GEMM with fused bias/activation epilogue and pluggable A-operand loaders
+// (dense rows, or im2col gather over an NHWC image for the forward convolutions).
+// This is the exact-arithmetic baseline path; the tcgen05 path (gemm_tc.cu) takes over the
+// large GEMMs, this one stays for odd shapes and as the in-library cross-check.
+#include "common.cuh"
+
+namespace desire {
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
+constexpr int AS_LD = BM + 4;
+
+struct DenseA {
+  const float* A;
+  int lda, M, K;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    return (m < M && k < K) ? __ldg(A + (size_t)m * lda + k) : 0.f;
+  }
+};
+
+struct Im2colA {
+  const float* X;
+  Im2col g;
+  int M, K;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    if (m >= M || k >= K) return 0.f;
+    int ox = m % g.Wo;
+    int t = m / g.Wo;
+    int oy = t % g.Ho;
+    int img = t / g.Ho;
+    int ci = k % g.Ci;
+    int t2 = k / g.Ci;
+    int kx = t2 % g.kw;
+    int ky = t2 / g.kw;
+    int iy = oy * g.stride + ky - g.pad_t;
+    int ix = ox * g.stride + kx - g.pad_l;
+    if (iy < 0 || iy >= g.Hi || ix < 0 || ix >= g.Wi) return 0.f;
+    return __ldg(X + (((size_t)img * g.Hi + iy) * g.Wi + ix) * g.Ci + ci);
+  }
+};
+
+template <class ALoader, bool TRANS_B>
+__global__ void __launch_bounds__(NT) sgemm_kernel(ALoader A, const float* __restrict__ B, int ldb,
+                                                   const float* __restrict__ bias, float* __restrict__ C,
+                                                   int ldc, int M, int N, int K, int act, int accumulate) {
+  __shared__ __align__(16) float As[BK][AS_LD];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int m_blk = blockIdx.y * BM, n_blk = blockIdx.x * BN;
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    {
+      const int k = tid % BK, m0 = tid / BK;
+#pragma unroll
+      for (int i = 0; i < BM / (NT / BK); ++i) {
+        int m = m0 + i * (NT / BK);
+        As[k][m] = A(m_blk + m, k0 + k);
+      }
+    }
+    if (TRANS_B) {
+      const int k = tid % BK, n0 = tid / BK;
+#pragma unroll
+      for (int i = 0; i < BN / (NT / BK); ++i) {
+        int n = n0 + i * (NT / BK);
+        int gn = n_blk + n, gk = k0 + k;
+        Bs[k][n] = (gn < N && gk < K) ? __ldg(B + (size_t)gn * ldb + gk) : 0.f;
+      }
+    } else {
+      const int n = tid % BN, kk0 = tid / BN;
+#pragma unroll
+      for (int i = 0; i < BK / (NT / BN); ++i) {
+        int k = kk0 + i * (NT / BN);
+        int gn = n_blk + n, gk = k0 + k;
+        Bs[k][n] = (gn < N && gk < K) ? __ldg(B + (size_t)gk * ldb + gn) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m_blk + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n_blk + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += __ldg(bias + n);
+      float* c = C + (size_t)m * ldc + n;
+      if (accumulate) v += *c;
+      *c = act_apply(v, act);
+    }
+  }
+}
+
+template <class L>
+int launch(const L& a, const float* B, int ldb, bool trans_b, const float* bias, float* C, int ldc, int M,
+           int N, int K, int act, bool accumulate, cudaStream_t st) {
+  if (M == 0 || N == 0) return DESIRE_OK;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  if (grid.y > 65535) {
+    set_error("sgemm: M=%d too large for one launch", M);
+    return DESIRE_ERR_INVALID;
+  }
+  if (trans_b)
+    sgemm_kernel<L, true><<<grid, NT, 0, st>>>(a, B, ldb, bias, C, ldc, M, N, K, act, accumulate ? 1 : 0);
+  else
+    sgemm_kernel<L, false><<<grid, NT, 0, st>>>(a, B, ldb, bias, C, ldc, M, N, K, act, accumulate ? 1 : 0);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}
+
+}  // namespace
+
+int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const float* bias, float* C, int ldc,
+          int M, int N, int K, int act, bool accumulate, cudaStream_t st) {
+  // split very tall problems so gridDim.y stays legal
+  const int MAXM = 65535 * BM;
+  for (long m0 = 0; m0 < M; m0 += MAXM) {
+    int mm = (int)((M - m0) < MAXM ? (M - m0) : MAXM);
+    DenseA a{A + (size_t)m0 * lda, lda, mm, K};
+    DESIRE_TRY(launch(a, B, ldb, trans_b, bias, C + (size_t)m0 * ldc, ldc, mm, N, K, act, accumulate, st));
+  }
+  return DESIRE_OK;
+}
+
+int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const float* bias, float* C, int ldc,
+                 int M, int N, int K, int act, cudaStream_t st) {
+  DESIRE_CHECK_ARG((M + BM - 1) / BM <= 65535, "sgemm_im2col: M=%d too large", M);
+  Im2colA a{X, g, M, K};
+  return launch(a, B, ldb, false, bias, C, ldc, M, N, K, act, false, st);
+}
+
+}  // namespace desire
+
+extern "C" int desire_fc_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
+                             int ldc, int M, int N, int K, int act, int accumulate, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(A && W && C && M >= 0 && N > 0 && K > 0, "desire_fc_fwd: bad arguments");
+  DESIRE_CHECK_ARG(lda >= K && ldw >= N && ldc >= N, "desire_fc_fwd: leading dimensions too small");
+  return desire::sgemm(A, lda, W, ldw, false, bias, C, ldc, M, N, K, act, accumulate != 0, (cudaStream_t)stream);
+}

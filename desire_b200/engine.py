@@ -1,0 +1,124 @@
+"""Host-side driver of the hot path: owns the device buffers and issues the C-ABI calls in order.
+
+PyTorch is plumbing here (device memory, streams, CUDA graphs); every arithmetic op of the path
+runs inside libdesire_b200.so.  All buffers are allocated once per (config, batch) so a step can
+be captured into a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .config import DesireConfig, logpolar_tables
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class HotPath:
+    """Sample generation (a2-a13) + IOC ranking/refinement (a14) for a fixed batch of B scenes."""
+
+    def __init__(self, cfg: DesireConfig, params: dict, B: int, device="cuda:0"):
+        cfg.validate()
+        self.cfg, self.B, self.device = cfg, B, torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.DesireError("the DESIRE hot path only runs on a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.P = {k: v.to(self.device, torch.float32).contiguous() for k, v in params.items()}
+        r2, dirs = logpolar_tables(cfg)
+        self.r2_edges, self.dirs = r2.to(self.device), dirs.to(self.device)
+        N, K, H, Zl, Tp, Tf, Cm = cfg.max_num_obj, cfg.K, cfg.H, cfg.Z, cfg.seq_length, cfg.pred_length, cfg.channel_multiplier
+        M, R = B * N, B * N * K
+        self.M, self.R = M, R
+        Hm = (cfg.scene_size + 1) // 2
+        self.Hm = Hm
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        self.buf = dict(
+            rho_i=f(M, 2 * Cm), HxHy=f(M, 2 * H), vae_inputs=f(M, cfg.S * cfg.S), mu_logvar=f(M, 2 * Zl),
+            zval=f(R, Zl), x_reconstr_mean=f(R, cfg.S * cfg.S), x_z=f(R, H), output_states=f(R, Tf, H),
+            Yhat=f(R, Tf, 2), feature_pooling=f(R, Tf, 2 * Cm), kld_rows=f(M), recon_rows=f(M), cost=f(2),
+            scene_features=f(B, Hm, Hm, cfg.scene_channels), Y_refined=f(R, Tf, 2),
+            ioc_scores=f(max(cfg.ioc_iters, 1), R),
+        )
+        self._structs()
+        lib = self.lib
+        self.ioc_dims = _lib.IocDims(B, N, K, H, Tf, Cm, cfg.vel_dim, cfg.scene_channels, cfg.n_rad, cfg.n_ang,
+                                     Hm, Hm, cfg.ioc_iters)
+        ws = max(
+            lib.desire_cvae_encode_workspace_bytes(M, Zl), lib.desire_cvae_decode_workspace_bytes(R, Zl),
+            lib.desire_mask_softmax_workspace_bytes(R, H), lib.desire_gru_decode_workspace_bytes(R, H),
+            lib.desire_scene_cnn_workspace_bytes(B, cfg.scene_size, cfg.scene_size),
+            lib.desire_ioc_workspace_bytes(C.byref(self.ioc_dims)), 256)
+        self.ws_bytes = ws
+        self.ws = torch.empty(ws, dtype=torch.uint8, device=self.device)
+        self.launches = None
+
+    def _structs(self):
+        P = self.P
+        gru = lambda n: _lib.GruW(*[P[n + s].data_ptr() for s in ("_wg", "_bg", "_wc", "_bc")])
+        cbn = lambda n: _lib.ConvBnW(*[P[n + s].data_ptr() for s in ("_w", "_b", "_g", "_be")])
+        self.w_encx, self.w_ency, self.w_dec1 = gru("encx"), gru("ency"), gru("dec1")
+        self.w_venc = _lib.CvaeEncW(cbn("venc_c1"), cbn("venc_c2"), cbn("venc_c3"),
+                                    P["venc_fc_w"].data_ptr(), P["venc_fc_b"].data_ptr())
+        self.w_vdec = _lib.CvaeDecW(cbn("vdec_d1"), cbn("vdec_d2"), cbn("vdec_d3"), cbn("vdec_d4"))
+        self.w_scene = _lib.SceneCnnW(*[P["scene_" + n].data_ptr() for n in ("c1_w", "c1_b", "c2_w", "c2_b", "c3_w", "c3_b")])
+        self.w_ioc = _lib.IocW(P["ioc_vel_w"].data_ptr(), P["ioc_vel_b"].data_ptr(), P["ioc_sp_w"].data_ptr(),
+                               P["ioc_sp_b"].data_ptr(), gru("dec2"), P["ioc_score_w"].data_ptr(),
+                               P["ioc_score_b"].data_ptr(), P["ioc_reg_w"].data_ptr(), P["ioc_reg_b"].data_ptr(),
+                               self.r2_edges.data_ptr(), self.dirs.data_ptr())
+
+    # ------------------------------------------------------------------ one pass of the hot path
+    def run(self, obs, tgt, eps, scene, stages=("generate", "rank")):
+        """obs [B,N,Tp,3], tgt [B,N,Tf,3], eps [M,K,Z], scene [B,Hi,Wi,3] — contiguous fp32 CUDA tensors.
+        Enqueues everything on the current stream; returns the dict of output buffers (views)."""
+        cfg, lib, b, P = self.cfg, self.lib, self.buf, self.P
+        N, K, H, Zl, Tp, Tf, Cm = cfg.max_num_obj, cfg.K, cfg.H, cfg.Z, cfg.seq_length, cfg.pred_length, cfg.channel_multiplier
+        M, R, S2 = self.M, self.R, cfg.S * cfg.S
+        for t, shp in ((obs, (self.B, N, Tp, 3)), (tgt, (self.B, N, Tf, 3)), (eps, (M, K, Zl))):
+            if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("expected contiguous float32 %s on %s, got %s %s" % (shp, self.device, tuple(t.shape), t.dtype))
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        ws, wsb = _p(self.ws), self.ws_bytes
+        ck = _lib.check
+        if "generate" in stages:
+            ck(lib.desire_tconv_fwd(_p(obs), M, Tp, Cm, _p(P["temporal_w"]), _p(P["temporal_b"]), _p(b["rho_i"]), st), "tconv")
+            ck(lib.desire_gru_encode_fwd(_p(obs), M, Tp, H, C.byref(self.w_encx), _p(b["HxHy"]), 2 * H, st), "gru_encode_x")
+            ck(lib.desire_gru_encode_fwd(_p(tgt), M, Tf, H, C.byref(self.w_ency),
+                                         C.c_void_p(b["HxHy"].data_ptr() + 4 * H), 2 * H, st), "gru_encode_y")
+            ck(lib.desire_fc_fwd(_p(b["HxHy"]), 2 * H, _p(P["w_hidden_enc1"]), S2, _p(P["b_hidden_enc1"]),
+                                 _p(b["vae_inputs"]), S2, M, S2, 2 * H, 1, 0, st), "fc_c")
+            ck(lib.desire_cvae_encode_fwd(_p(b["vae_inputs"]), M, Zl, C.byref(self.w_venc), _p(b["mu_logvar"]), ws, wsb, st), "cvae_encode")
+            ck(lib.desire_reparam_fwd(_p(b["mu_logvar"]), _p(eps), M, K, Zl, _p(b["zval"]), st), "reparam")
+            ck(lib.desire_cvae_decode_fwd(_p(b["zval"]), R, Zl, C.byref(self.w_vdec), _p(b["x_reconstr_mean"]), ws, wsb, st), "cvae_decode")
+            ck(lib.desire_mask_softmax_fwd(_p(b["x_reconstr_mean"]), R, S2, H, K, _p(P["w_post_vae"]), _p(P["b_post_vae"]),
+                                           _p(b["HxHy"]), 2 * H, _p(b["x_z"]), ws, wsb, st), "mask_softmax")
+            ck(lib.desire_gru_decode_fwd(_p(b["x_z"]), _p(b["HxHy"]), 2 * H, R, K, H, Tf, C.byref(self.w_dec1),
+                                         _p(b["output_states"]), ws, wsb, st), "gru_decode")
+            ck(lib.desire_readout_pool_fwd(_p(b["output_states"]), R, K, Tf, H, 0, 1, _p(P["output_w"]), _p(P["output_b"]),
+                                           _p(obs), Tp, _p(b["rho_i"]), Cm, _p(b["Yhat"]), _p(b["feature_pooling"]), st), "readout_pool")
+            ck(lib.desire_kld_rows_fwd(_p(b["mu_logvar"]), M, Zl, _p(b["kld_rows"]), st), "kld_rows")
+            ck(lib.desire_recon_rows_fwd(_p(b["Yhat"]), _p(tgt), M, K, Tf, _p(b["recon_rows"]), st), "recon_rows")
+            ck(lib.desire_masked_cost_fwd(_p(b["recon_rows"]), _p(b["kld_rows"]), _p(obs), M, Tp, _p(b["cost"]), st), "masked_cost")
+        if "rank" in stages:
+            if tuple(scene.shape) != (self.B, cfg.scene_size, cfg.scene_size, 3) or not scene.is_contiguous():
+                raise ValueError("scene must be contiguous [B,%d,%d,3]" % (cfg.scene_size, cfg.scene_size))
+            ck(lib.desire_scene_cnn_fwd(_p(scene), self.B, cfg.scene_size, cfg.scene_size, cfg.scene_channels,
+                                        C.byref(self.w_scene), _p(b["scene_features"]), ws, wsb, st), "scene_cnn")
+            b["Y_refined"].copy_(b["Yhat"])
+            ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs), Tp,
+                                  _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["Y_refined"]), _p(b["ioc_scores"]),
+                                  ws, wsb, st), "ioc")
+        return self.outputs()
+
+    def outputs(self):
+        b, cfg = self.buf, self.cfg
+        H, Zl = cfg.H, cfg.Z
+        out = dict(b)
+        out["H_x"], out["H_y"] = b["HxHy"][:, :H], b["HxHy"][:, H:]
+        out["z_mean"], out["z_log_sigma_sq"] = b["mu_logvar"][:, :Zl], b["mu_logvar"][:, Zl:]
+        out["cost"] = b["cost"][0]
+        out["ioc_scores"] = b["ioc_scores"][:cfg.ioc_iters]
+        return out

@@ -1,0 +1,182 @@
+/* desire_abi.h — C-ABI of libdesire_b200.so, the sm_100a kernel library behind the DESIRE hot path.
+ *
+ * The reference (tdavchev/DESIRE) has no FFI: its hot path is TensorFlow-1 graph code inside
+ * model/model.py, entered through sess.run (train.py:181).  Each entry point below replaces the
+ * TF/prettytensor ops of one stage of that graph (cited per function) — the binding a maintainer
+ * would add is the ctypes stub in INTEGRATION.md (desire_b200/_lib.py is that stub, in use).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to row-major contiguous float32 unless a ld_/stride
+ *     argument says otherwise; images are NHWC; nothing is allocated inside the library:
+ *     scratch comes from the caller through (ws, ws_bytes) and *_workspace_bytes() queries;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - returns 0 on success, <0 on error (desire_last_error() gives the text, thread-local);
+ *   - rows: M = B*N agents (row = b*N+n), R = M*K agent-samples (row = m*K+k);
+ *   - trajectories keep the reference's [agents, time, (id,x,y)] layout (model/model.py:91-105).
+ *   - GRU weights follow TF-1.x GRUCell: wg [(I+H), 2H] (r|u), bg [2H], wc [(I+H), H], bc [H];
+ *     rows 0..I-1 multiply the input, rows I.. multiply the state.
+ */
+#ifndef DESIRE_ABI_H_
+#define DESIRE_ABI_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DESIRE_ABI_VERSION 1
+
+#define DESIRE_OK 0
+#define DESIRE_ERR_INVALID (-1)     /* bad argument / unsupported size            */
+#define DESIRE_ERR_CUDA (-2)        /* a CUDA runtime call or launch failed       */
+#define DESIRE_ERR_WORKSPACE (-3)   /* ws_bytes smaller than *_workspace_bytes()  */
+
+#define DESIRE_ACT_NONE 0
+#define DESIRE_ACT_RELU 1
+#define DESIRE_ACT_ELU 2
+#define DESIRE_ACT_SIGMOID 3
+
+typedef void* desire_stream_t;
+
+/* GRU parameters (TF-1.x GRUCell layout, see header comment). */
+typedef struct {
+  const float* wg;
+  const float* bg;
+  const float* wc;
+  const float* bc;
+} desire_gru_t;
+
+/* One conv / deconv layer of the CVAE: kernel, bias, BN gamma, BN beta. */
+typedef struct {
+  const float* w;
+  const float* b;
+  const float* gamma;
+  const float* beta;
+} desire_convbn_t;
+
+/* vae_encoder, model/model.py:471-492: conv5/2x32, conv5/2x64, conv5 VALIDx128 [kh,kw,in,out], fc 2048->2Z */
+typedef struct {
+  desire_convbn_t c1, c2, c3;
+  const float* fc_w;
+  const float* fc_b;
+} desire_cvae_enc_t;
+
+/* vae_decoder, model/model.py:453-469: deconv4 VALIDx128, deconv5 VALIDx64, deconv5/2x32, deconv5/2x1
+ * filters [kh,kw,out,in] (utils/convolutional_vae_util.py:83) */
+typedef struct {
+  desire_convbn_t d1, d2, d3, d4;
+} desire_cvae_dec_t;
+
+/* stage-2 parameters (absent in the reference, marker model/model.py:312-313) */
+typedef struct {
+  const float *c1_w, *c1_b, *c2_w, *c2_b, *c3_w, *c3_b; /* scene CNN 5x5: 3->16 s2, 16->32, 32->Cs */
+} desire_scene_cnn_t;
+
+typedef struct {
+  const float *vel_w, *vel_b;     /* [2,Fv], [Fv]        */
+  const float *sp_w, *sp_b;       /* [G*H, H], [H]       */
+  desire_gru_t dec2;              /* I = Fv+Cs+2C+H      */
+  const float *score_w, *score_b; /* [H], [1]            */
+  const float *reg_w, *reg_b;     /* [H, 2*Tf], [2*Tf]   */
+  const float* r2_edges;          /* [n_rad+1] squared radial bin edges */
+  const float* dirs;              /* [n_ang,2] sector boundary directions (cos,sin) */
+} desire_ioc_t;
+
+typedef struct {
+  int B, N, K, H, Tf;
+  int C;            /* channel multiplier (feature_pooling width is 2C) */
+  int Fv, Cs;       /* velocity-fc width, scene channels */
+  int n_rad, n_ang; /* log-polar grid */
+  int Hm, Wm;       /* scene feature-map size */
+  int iters;
+} desire_ioc_dims_t;
+
+int desire_version(void);
+const char* desire_last_error(void);
+
+/* ---- generic dense layer: C = act(A[M,K] @ W[K,N] + bias), replaces tf.nn.xw_plus_b / tf.matmul
+ * call sites model/model.py:249-251 (fc_c) and :272-275.  accumulate!=0 adds into C. */
+int desire_fc_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                  int M, int N, int K, int act, int accumulate, desire_stream_t stream);
+
+/* ---- a2  rho_i = relu(depthwise_conv2d(VALID) + b), model/model.py:116-133.
+ * obs [M,Tp,3] (id,x,y); w [Tp,2,C]; b [2C]; rho [M,2C] */
+int desire_tconv_fwd(const float* obs, int M, int Tp, int C, const float* w, const float* b, float* rho,
+                     desire_stream_t stream);
+
+/* ---- a3/a4  static_rnn(GRUCell) from a zero state over the (x,y) columns of traj [M,T,3],
+ * model/model.py:233-241.  h_out row stride ld_out (so H_x|H_y can share one [M,2H] buffer). */
+int desire_gru_encode_fwd(const float* traj, int M, int T, int H, const desire_gru_t* w, float* h_out,
+                          int ld_out, desire_stream_t stream);
+
+/* ---- a6  vae_encoder, model/model.py:471-492.  v [M,1024] -> mu_logvar [M,2Z] (mean | logvar). */
+size_t desire_cvae_encode_workspace_bytes(int M, int Z);
+int desire_cvae_encode_fwd(const float* v, int M, int Z, const desire_cvae_enc_t* w, float* mu_logvar,
+                           void* ws, size_t ws_bytes, desire_stream_t stream);
+
+/* ---- a7  z = mean + sqrt(exp(logvar))*eps, model/model.py:260-264.  eps [M,K,Z] -> z [M*K,Z]. */
+int desire_reparam_fwd(const float* mu_logvar, const float* eps, int M, int K, int Z, float* z,
+                       desire_stream_t stream);
+
+/* ---- a8  vae_decoder + deconv2d, model/model.py:453-469, utils/convolutional_vae_util.py:31-135.
+ * z [R,Z] -> xr [R,1024].  Rows are processed in chunks so the scratch stays bounded. */
+size_t desire_cvae_decode_workspace_bytes(int R, int Z);
+int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire_cvae_dec_t* w, float* xr, void* ws,
+                           size_t ws_bytes, desire_stream_t stream);
+
+/* ---- a9  x_z = softmax(relu(xr@W2+b2)) * H_x, model/model.py:271-280.
+ * xr [R,S2]; w [S2,H]; Hx row m = r/K with row stride ld_hx; x_z [R,H]; ws holds R*H floats. */
+size_t desire_mask_softmax_workspace_bytes(int R, int H);
+int desire_mask_softmax_fwd(const float* xr, int R, int S2, int H, int K, const float* w, const float* b,
+                            const float* Hx, int ld_hx, float* x_z, void* ws, size_t ws_bytes,
+                            desire_stream_t stream);
+
+/* ---- a10  Decoder-1: rnn_decoder with a constant input, model/model.py:279-285.
+ * x_z [R,H]; h0 row = r/K of Hx (stride ld_hx); hs [R,T,H] (output_states). */
+size_t desire_gru_decode_workspace_bytes(int R, int H);
+int desire_gru_decode_fwd(const float* x_z, const float* Hx, int ld_hx, int R, int K, int H, int T,
+                          const desire_gru_t* w, float* hs, void* ws, size_t ws_bytes,
+                          desire_stream_t stream);
+
+/* ---- a11  read-out + feature pooling, model/model.py:286-311.
+ * mode 0 (D3): Yhat[r,t,:] = hs[r,t,:]@out_w + out_b + obs[r/K, Tp-1, 1:3]
+ * mode 1 (reference split read-out): T2 = n_chunks, Yhat[r,t,c,:] = hs[r,t, c*(H/n_chunks) + {0,1}]
+ * fpool [R, T(*n_chunks), 2C] = [y_x*rho[:C], y_y*rho[C:]]  (may be NULL). */
+int desire_readout_pool_fwd(const float* hs, int R, int K, int T, int H, int mode, int n_chunks,
+                            const float* out_w, const float* out_b, const float* obs, int Tp,
+                            const float* rho, int C, float* Yhat, float* fpool, desire_stream_t stream);
+
+/* ---- a12/a13  losses: kld rows (model/model.py:587-589), reconstruction rows (D7) and the masked
+ * mean cost = sum_{id!=0}(rows)/count (model/model.py:351-376).  cost[0] = cost, cost[1] = count. */
+int desire_kld_rows_fwd(const float* mu_logvar, int M, int Z, float* kld_rows, desire_stream_t stream);
+int desire_recon_rows_fwd(const float* Yhat, const float* target, int M, int K, int T, float* recon_rows,
+                          desire_stream_t stream);
+int desire_masked_cost_fwd(const float* rows_a, const float* rows_b, const float* obs, int M, int Tp,
+                           float* cost, desire_stream_t stream);
+
+/* ---- a14  stage 2 pieces (D11) */
+size_t desire_scene_cnn_workspace_bytes(int B, int Hi, int Wi);
+int desire_scene_cnn_fwd(const float* img, int B, int Hi, int Wi, int Cs, const desire_scene_cnn_t* w,
+                         float* fmap, void* ws, size_t ws_bytes, desire_stream_t stream);
+/* bilinear gather: fmap [B,Hm,Wm,Cs]; pos = base + row*pos_stride (x,y), rows_per_scene rows per b;
+ * out row stride ld_out. */
+int desire_scene_gather_fwd(const float* fmap, int B, int Hm, int Wm, int Cs, const float* pos,
+                            long pos_stride, int rows_per_scene, float* out, int ld_out,
+                            desire_stream_t stream);
+/* log-polar social pooling: pos/h rows ordered (b,n,k); mask from obs ids ([B*N,Tp,3], id!=0);
+ * pooled [R, G*H]. */
+int desire_social_pool_fwd(const float* pos, long pos_stride, const float* h, int ld_h, const float* obs,
+                           int Tp, int B, int N, int K, int H, int n_rad, int n_ang,
+                           const float* r2_edges, const float* dirs, float* pooled,
+                           desire_stream_t stream);
+/* full ranking & refinement loop.  Y [R,Tf,2] is refined IN PLACE; scores [iters, R]. */
+size_t desire_ioc_workspace_bytes(const desire_ioc_dims_t* d);
+int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
+                   int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores,
+                   void* ws, size_t ws_bytes, desire_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESIRE_ABI_H_ */
