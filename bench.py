@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — agent-samples/sec of the DESIRE hot path (sample-generate + rank-refine) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
+    python bench.py --impl reference --steps K --warmup W     # the reference's algorithm on host cores
+
+A "step" is one pass of the hot path (a2-a14: CVAE sample generation, then `ioc_iters` iterations of
+IOC ranking/refinement) over one synthetic minibatch of BASELINE.json configs[1]'s shape
+(B=32 scenes x N=60 agents x K=20 samples, H=128, Z=128, T_p=8, T_f=12).  One JSON line on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent-samples/sec (NxK, T_fut=12), sample-generate + rank-refine"
+UNIT = "agent-samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    # workload = BASELINE.json configs[1] shape
+    ap.add_argument("--scenes", type=int, default=32, help="B, scenes per GPU per step")
+    ap.add_argument("--agents", type=int, default=60)
+    ap.add_argument("--samples", type=int, default=20)
+    ap.add_argument("--hidden", type=int, default=128)
+    ap.add_argument("--latent", type=int, default=128)
+    ap.add_argument("--pred-length", type=int, default=12)
+    ap.add_argument("--ioc-iters", type=int, default=2)
+    ap.add_argument("--scene-size", type=int, default=256)
+    ap.add_argument("--cpu-sample-scenes", type=int, default=1, help="scenes per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default="", help="write the per-kernel timing table to this file")
+    return ap.parse_args()
+
+
+def make_cfg(a):
+    from desire_b200.config import DesireConfig
+    cfg = DesireConfig(d_dim=a.hidden, latent_size=a.latent, max_num_obj=a.agents, num_samples=a.samples,
+                       pred_length=a.pred_length, ioc_iters=a.ioc_iters, scene_size=a.scene_size)
+    cfg.validate()
+    return cfg
+
+
+def workload_config(a, cfg, extra):
+    d = {
+        "workload": "BASELINE configs[1] shape, synthetic: B=%d scenes x N=%d agents x K=%d samples, H=%d, Z=%d, "
+                    "T_p=%d, T_f=%d, scene %dx%dx3, ioc_iters=%d; one step = CVAE sample generation + IOC "
+                    "rank/refine (forward pass of the path)" % (a.scenes, a.agents, a.samples, a.hidden, a.latent,
+                                                                cfg.seq_length, cfg.pred_length, a.scene_size,
+                                                                a.scene_size, a.ioc_iters),
+        "scenes_per_gpu": a.scenes, "agents": a.agents, "samples": a.samples, "hidden": a.hidden,
+        "latent": a.latent, "T_past": cfg.seq_length, "T_fut": cfg.pred_length, "ioc_iters": a.ioc_iters,
+        "scene_size": a.scene_size, "log_polar_bins": cfg.G,
+    }
+    d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def oracle_step_fn(a, cfg, n_scenes, seed=0):
+    """One bounded sample of the workload through the CPU oracle (numpy fp32, all BLAS threads)."""
+    import numpy as np
+    from desire_b200.config import init_params, logpolar_tables
+    from desire_b200.synthetic import make_batch
+    from oracle import desire_oracle as O
+    P = {k: v.numpy() for k, v in init_params(cfg, 1).items()}
+    batch = [t.numpy() for t in make_batch(cfg, n_scenes, seed)]
+    r2, dirs = [t.numpy() for t in logpolar_tables(cfg)]
+    ocfg = dict(K=cfg.K, Z=cfg.Z, ioc_iters=cfg.ioc_iters)
+
+    def step():
+        out = O.forward(P, ocfg, batch[0], batch[1], batch[2], batch[3], r2, dirs)
+        return float(np.asarray(out["ioc_scores"]).sum())
+
+    return step, n_scenes * cfg.max_num_obj * cfg.K
+
+
+def run_cpu(a, cfg, steps, warmup):
+    step, units = oracle_step_fn(a, cfg, a.cpu_sample_scenes)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return units * steps / dt, dt / steps, units
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = make_cfg(a)
+    steps, warmup = max(a.steps, 1), max(a.warmup, 0)
+    # keep the whole run within a few minutes: one scene per step, warm-up capped
+    warmup = min(warmup, 2)
+    steps = min(steps, 20)
+    cores = os.cpu_count()
+    val, s_per_step, units = run_cpu(a, cfg, steps, warmup)
+    sample = "%d scene(s) x N=%d x K=%d = %d agent-samples per step, full path, numpy fp32 oracle" % (
+        a.cpu_sample_scenes, a.agents, a.samples, units)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, cfg, {"note": "reference TF1 graph cannot run (SURVEY.md 0.4); this is the "
+                                                   "oracle port of its algorithm on the host cores"}),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor": d["bf16_tflops_sustained"], "src": "measured (MEASURED_PEAKS.json; "
+                "HBM copy GB/s, bf16 sustained TFLOP/s)"}
+    return {"hbm": 6650.0, "tensor": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def slot_table(a, cfg, world_local_R):
+    """Algorithmic work per STEP of each timed kernel (DESIGN.md 'Kernels'): (name, bound, amount) with
+    amount in FLOP (tensor) or bytes (hbm)."""
+    R, T, H, G = world_local_R, cfg.pred_length, cfg.H, cfg.G
+    it = cfg.ioc_iters
+    Dst = cfg.vel_dim + cfg.scene_channels + 2 * cfg.channel_multiplier
+    return {
+        0: ("gru_decoder1_recurrence", "tensor", R * 6.0 * H * H * T),
+        1: ("gru_decoder2_step", "tensor", it * T * R * 12.0 * H * H),
+        2: ("gru_encoders", "tensor", (R / cfg.K) * 6.0 * H * H * (cfg.seq_length + T)),
+        3: ("social_pool", "hbm", it * T * R * (8.0 + 4 * H + 4.0 * G * H)),
+        4: ("social_fc_gemm", "tensor", it * T * R * 2.0 * G * H * H),
+        5: ("scene_gather", "hbm", it * R * T * (20.0 * cfg.scene_channels + 8)),
+        6: ("cvae_deconv2_gemm", "tensor", R * 2.0 * 16 * 128 * 1600),
+        7: ("cvae_deconv3_gemm", "tensor", R * 2.0 * 64 * 64 * 800),
+        8: ("cvae_col2im_bn_act", "hbm", R * 4.0 * (2048 + 16 * 1600 + 64 * 800 + 256 * 25 + 2048 + 4096 + 8192 + 1024)),
+        9: ("decoder2_input_projection_gemm", "tensor", it * R * T * 2.0 * Dst * 3 * H),
+        10: ("scene_cnn", "tensor", 0.0),
+        11: ("readout_feature_pool", "hbm", R * T * 4.0 * (H + 2 + 2 * cfg.channel_multiplier)),
+    }
+
+
+def ours_arm(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from desire_b200 import _lib
+    from desire_b200.model.model import DESIREModel
+    from desire_b200.synthetic import make_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = make_cfg(a)
+    lib = _lib.load()
+    model = DESIREModel(cfg, device=dev, seed=1)
+    B = a.scenes
+    host = make_batch(cfg, B, seed=100 + rank)              # every rank owns its own scenes (weak scaling)
+    dev_in = [t.to(dev) for t in host]
+    hp = model._path(B)
+    R_local = B * cfg.max_num_obj * cfg.K
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(max(a.warmup, 3)):
+        hp.run(*dev_in)
+    torch.cuda.synchronize()
+    steps = max(a.steps, 1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    clocks = ClockSampler(local)
+    lib.desire_prof_enable(1)
+    barrier()
+    clocks.start()
+    l0 = lib.desire_launch_count()
+    t_wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.zero_()                                        # L2 flush, outside the timed events
+        s.record()
+        hp.run(*dev_in)
+        e.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.desire_launch_count() - l0
+    clk = clocks.stop()
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    prof = {}
+    for slot in range(16):
+        n, ms = C.c_long(0), C.c_double(0)
+        lib.desire_prof_read(slot, C.byref(n), C.byref(ms))
+        if n.value:
+            prof[slot] = (n.value, ms.value)
+    lib.desire_prof_enable(0)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = R_local * world * steps / (dev_ms_max / 1e3)
+
+    # ---- end to end through the public API with host buffers (pinned staging inside the model)
+    host_np = [x.numpy() for x in host]
+    for _ in range(2):
+        model.sample_and_rank(*host_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y, sc, cost = model.sample_and_rank(*host_np)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = R_local * world * steps / float(te.item())
+    h2d = sum(x.nbytes for x in host_np)
+    d2h = y.nbytes + sc.nbytes + 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event timing of the tagged launches)
+    pk = peaks()
+    table = slot_table(a, cfg, R_local)
+    rows = []
+    for slot, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        name, bound, amount = table.get(slot, ("slot%d" % slot, "hbm", 0.0))
+        per_step_ms = ms / steps
+        ach = (amount / (per_step_ms / 1e3)) / (1e12 if bound == "tensor" else 1e9) if per_step_ms > 0 else 0.0
+        rows.append({"kernel": name, "bound": bound, "launches_per_step": n / steps, "ms_per_step": per_step_ms,
+                     "share_of_step": per_step_ms / (dev_ms / steps), "achieved": ach,
+                     "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "peak": pk[bound], "frac": ach / pk[bound]})
+    top = rows[0] if rows else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if top and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top["kernel"])
+    roofline = None
+    if top:
+        roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+                    "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "peak_source": pk["src"],
+                    "share_of_step": top["share_of_step"]}
+    if a.breakdown:
+        os.makedirs(os.path.dirname(os.path.abspath(a.breakdown)), exist_ok=True)
+        json.dump({"ms_per_step": dev_ms / steps, "kernels": rows}, open(a.breakdown, "w"), indent=1)
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        v, s_per, units = run_cpu(a, cfg, steps=2, warmup=1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d scene(s) x N=%d x K=%d = %d agent-samples per step x 2 steps, full path, numpy fp32 "
+                         "oracle (%.1f s/step)" % (a.cpu_sample_scenes, a.agents, a.samples, units, s_per)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, cfg, {"parallelism": "scenes sharded over %d GPU(s), no data-path collective" % world,
+                                           "l2": "flushed (256 MiB memset) before every timed step; timed with CUDA "
+                                                 "events per step, max over ranks",
+                                           "wall_s_timed_region": t_wall}),
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": rows[:8],
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        ours_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,9 @@ P, I, L, Z = C.c_void_p, C.c_int, C.c_long, C.c_size_t
 SIGNATURES = {
     "desire_version": (I, []),
     "desire_last_error": (C.c_char_p, []),
+    "desire_launch_count": (L, []),
+    "desire_prof_enable": (I, [I]),
+    "desire_prof_read": (I, [I, C.POINTER(C.c_long), C.POINTER(C.c_double)]),
     "desire_fc_fwd": (I, [P, I, P, I, P, P, I, I, I, I, I, I, P]),
     "desire_tconv_fwd": (I, [P, I, I, I, P, P, P, P]),
     "desire_gru_encode_fwd": (I, [P, I, I, I, C.POINTER(GruW), P, I, P]),

@@ -9,6 +9,18 @@
 namespace desire {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+
+// Optional per-kernel timing (desire_prof_enable): a ProfScope brackets ONE launch with CUDA events on
+// the launching stream; desire_prof_read sums them per slot.  Off by default (zero overhead but a branch).
+void prof_begin(int slot, cudaStream_t st);
+void prof_end(int slot, cudaStream_t st);
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(int s, cudaStream_t st_) : slot(s), st(st_) { prof_begin(slot, st); }
+  ~ProfScope() { prof_end(slot, st); }
+};
 
 #define DESIRE_CHECK_ARG(cond, ...)            \
   do {                                         \
@@ -28,7 +40,12 @@ void set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-#define DESIRE_LAUNCH_CHECK() DESIRE_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro, so the counter is the number of OUR kernels
+#define DESIRE_LAUNCH_CHECK()                 \
+  do {                                        \
+    ::desire::count_launch();                 \
+    DESIRE_CUDA(cudaGetLastError());          \
+  } while (0)
 
 #define DESIRE_TRY(call)          \
   do {                            \

@@ -181,17 +181,35 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
     const float* zc = z + (size_t)r0 * Z;
     // deconv4 VALID 1x1xZ -> 4x4x128: col[r, (y,x,o)] = z[r,:] . W[y,x,o,:]
     DESIRE_TRY(sgemm(zc, Z, w->d1.w, Z, true, nullptr, col, 2048, rc, 2048, Z, DESIRE_ACT_NONE, false, st));
-    DESIRE_TRY(colbn_act(col, rc, 1, 4, 4, 1, 0, 128, w->d1.b, w->d1.gamma, w->d1.beta, DESIRE_ACT_ELU, a1, st));
+    {
+      ProfScope ps_(DESIRE_PROF_COL2IM, st);
+      DESIRE_TRY(colbn_act(col, rc, 1, 4, 4, 1, 0, 128, w->d1.b, w->d1.gamma, w->d1.beta, DESIRE_ACT_ELU, a1, st));
+    }
     // deconv5 VALID 4x4x128 -> 8x8x64
-    DESIRE_TRY(sgemm(a1, 128, w->d2.w, 128, true, nullptr, col, 1600, rc * 16, 1600, 128, DESIRE_ACT_NONE, false, st));
-    DESIRE_TRY(colbn_act(col, rc, 4, 8, 5, 1, 0, 64, w->d2.b, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, a2, st));
+    {
+      ProfScope ps_(DESIRE_PROF_DECONV2, st);
+      DESIRE_TRY(sgemm(a1, 128, w->d2.w, 128, true, nullptr, col, 1600, rc * 16, 1600, 128, DESIRE_ACT_NONE, false, st));
+    }
+    {
+      ProfScope ps_(DESIRE_PROF_COL2IM, st);
+      DESIRE_TRY(colbn_act(col, rc, 4, 8, 5, 1, 0, 64, w->d2.b, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, a2, st));
+    }
     // deconv5/2 SAME 8x8x64 -> 16x16x32 (full 19x19, keep [1,17))
-    DESIRE_TRY(sgemm(a2, 64, w->d3.w, 64, true, nullptr, col, 800, rc * 64, 800, 64, DESIRE_ACT_NONE, false, st));
-    DESIRE_TRY(colbn_act(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st));
+    {
+      ProfScope ps_(DESIRE_PROF_DECONV3, st);
+      DESIRE_TRY(sgemm(a2, 64, w->d3.w, 64, true, nullptr, col, 800, rc * 64, 800, 64, DESIRE_ACT_NONE, false, st));
+    }
+    {
+      ProfScope ps_(DESIRE_PROF_COL2IM, st);
+      DESIRE_TRY(colbn_act(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st));
+    }
     // deconv5/2 SAME 16x16x32 -> 32x32x1, BN + sigmoid
     DESIRE_TRY(sgemm(a3, 32, w->d4.w, 32, true, nullptr, col, 25, rc * 256, 25, 32, DESIRE_ACT_NONE, false, st));
-    DESIRE_TRY(colbn_act(col, rc, 16, 32, 5, 2, 1, 1, w->d4.b, w->d4.gamma, w->d4.beta, DESIRE_ACT_SIGMOID,
-                         xr + (size_t)r0 * 1024, st));
+    {
+      ProfScope ps_(DESIRE_PROF_COL2IM, st);
+      DESIRE_TRY(colbn_act(col, rc, 16, 32, 5, 2, 1, 1, w->d4.b, w->d4.gamma, w->d4.beta, DESIRE_ACT_SIGMOID,
+                           xr + (size_t)r0 * 1024, st));
+    }
   }
   return DESIRE_OK;
 }

@@ -238,6 +238,7 @@ extern "C" int desire_gru_encode_fwd(const float* traj, int M, int T, int H, con
   a.Ka = 0;
   a.h0 = nullptr; a.h0_div = 1;
   a.h_final = h_out; a.ld_hf = ld_out;
+  ProfScope ps_(DESIRE_PROF_GRU_ENC, (cudaStream_t)stream);
   return gru_seq(a, (cudaStream_t)stream);
 }
 
@@ -263,5 +264,6 @@ extern "C" int desire_gru_decode_fwd(const float* x_z, const float* Hx, int ld_h
   a.Ka = 0;
   a.h0 = Hx; a.h0_div = K; a.ld_h0 = ld_hx;
   a.hs = hs; a.hs_row_stride = (long)T * H; a.hs_step_stride = H;
+  ProfScope ps_(DESIRE_PROF_GRU_DEC1, st);
   return gru_seq(a, st);
 }

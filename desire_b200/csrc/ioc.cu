@@ -293,18 +293,33 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
     float* score = scores + (size_t)it * R;
     vel_fc_kernel<<<blocks(R * T * Fv, 256), 256, 0, st>>>(Y, obs, Tp, R, K, T, Fv, w->vel_w, w->vel_b, Xs, Dst);
     DESIRE_LAUNCH_CHECK();
-    scene_gather_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(fmap, d->Hm, d->Wm, Cs, Y, 2, R * T, d->N * K * T,
-                                                                  Xs + Fv, Dst);
+    {
+      ProfScope ps_(DESIRE_PROF_GATHER, st);
+      scene_gather_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(fmap, d->Hm, d->Wm, Cs, Y, 2, R * T, d->N * K * T,
+                                                                    Xs + Fv, Dst);
+    }
     DESIRE_LAUNCH_CHECK();
     // hoisted input projection of the static features for all T steps: XP[(r,t), r|u|c]
-    DESIRE_TRY(sgemm(Xs, Dst, g.wg, 2 * H, false, g.bg, XP, 3 * H, (int)(R * T), 2 * H, Dst, DESIRE_ACT_NONE, false, st));
-    DESIRE_TRY(sgemm(Xs, Dst, g.wc, H, false, g.bc, XP + 2 * H, 3 * H, (int)(R * T), H, Dst, DESIRE_ACT_NONE, false, st));
+    {
+      ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
+      DESIRE_TRY(sgemm(Xs, Dst, g.wg, 2 * H, false, g.bg, XP, 3 * H, (int)(R * T), 2 * H, Dst, DESIRE_ACT_NONE, false, st));
+    }
+    {
+      ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
+      DESIRE_TRY(sgemm(Xs, Dst, g.wc, H, false, g.bc, XP + 2 * H, 3 * H, (int)(R * T), H, Dst, DESIRE_ACT_NONE, false, st));
+    }
     expand_rows_kernel<<<blocks(R * H, 256), 256, 0, st>>>(Hx, ld_hx, K, H, R, h2);
     DESIRE_LAUNCH_CHECK();
     for (int t = 0; t < T; ++t) {
-      DESIRE_TRY(social_pool_launch(Y + 2 * t, 2L * T, h2, H, obs, Tp, d->B, d->N, K, H, d->n_rad, d->n_ang,
-                                    w->r2_edges, w->dirs, pooled, st));
-      DESIRE_TRY(sgemm(pooled, G * H, w->sp_w, H, false, w->sp_b, fsp, H, (int)R, H, G * H, DESIRE_ACT_RELU, false, st));
+      {
+        ProfScope ps_(DESIRE_PROF_SOCIAL_POOL, st);
+        DESIRE_TRY(social_pool_launch(Y + 2 * t, 2L * T, h2, H, obs, Tp, d->B, d->N, K, H, d->n_rad, d->n_ang,
+                                      w->r2_edges, w->dirs, pooled, st));
+      }
+      {
+        ProfScope ps_(DESIRE_PROF_SOCIAL_FC, st);
+        DESIRE_TRY(sgemm(pooled, G * H, w->sp_w, H, false, w->sp_b, fsp, H, (int)R, H, G * H, DESIRE_ACT_RELU, false, st));
+      }
       GruSeqArgs a{};
       a.R = (int)R; a.H = H; a.T = 1;
       a.xp = XP + (size_t)t * 3 * H; a.xp_row_stride = (long)T * 3 * H; a.xp_step_stride = 0;
@@ -313,7 +328,10 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
       a.w_c = g.wc + (size_t)Dst * H;
       a.h0 = h2; a.h0_div = 1; a.ld_h0 = H;
       a.h_final = h2; a.ld_hf = H;
-      DESIRE_TRY(gru_seq(a, st));
+      {
+        ProfScope ps_(DESIRE_PROF_GRU_DEC2, st);
+        DESIRE_TRY(gru_seq(a, st));
+      }
       score_kernel<<<blocks(R * 32, 256), 256, 0, st>>>(h2, R, H, w->score_w, w->score_b, score, t == 0 ? 1 : 0);
       DESIRE_LAUNCH_CHECK();
     }

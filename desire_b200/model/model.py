@@ -1,0 +1,192 @@
+"""DESIREModel — host-side mirror of the reference's model/model.py:29-688 on the B200 kernel library.
+
+Same constructor (`DESIREModel(args)` with the train.py flags), same attribute names
+(`input_data`, `target_data`, `temporal_data`, `learning_rate`, `cost`, `final_states`,
+`final_output`, `rho_i`, `output_states`, `feature_pooling`) and the same `[agents, time, (id,x,y)]`
+layouts (model/model.py:86-105).  Where the reference builds a TF graph and evaluates it one
+sequence per `sess.run` (train.py:146-181), this class owns device buffers for a whole minibatch
+of scenes and runs the fused path through the C-ABI (engine.HotPath): attributes are filled by
+`forward()` instead of being graph nodes.  There is no CPU path: constructing the model without a
+CUDA device or without libdesire_b200.so raises.
+"""
+from __future__ import annotations
+
+import argparse
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from ..config import DesireConfig, init_params
+from ..engine import HotPath
+
+
+def config_from_args(args) -> DesireConfig:
+    """Map the reference's argparse namespace (train.py:28-88) + the added flags onto DesireConfig."""
+    g = lambda n, d: getattr(args, n, d)
+    return DesireConfig(
+        rnn_size=g("rnn_size", 512), d_dim=g("d_dim", 16), latent_size=g("latent_size", 128),
+        seq_length=g("seq_length", 8), max_num_obj=g("max_num_obj", 60), stride=g("stride", 1),
+        pred_length=g("pred_length", 12), num_samples=g("num_samples", 20), ioc_iters=g("ioc_iters", 2),
+        scene_size=g("scene_size", 256), scene_channels=g("scene_channels", 32), vel_dim=g("vel_dim", 16),
+        n_rad=g("n_rad", 6), n_ang=g("n_ang", 6), r_min=g("r_min", 0.01), r_max=g("r_max", 0.5))
+
+
+class DESIREModel(object):
+    """Stochastic IOC RNN encoder-decoder (sample generation + ranking/refinement) on one GPU."""
+
+    def __init__(self, args, device="cuda:0", seed=1, params=None):
+        self.args = args
+        cfg = args if isinstance(args, DesireConfig) else config_from_args(args)
+        cfg.validate()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        # names kept from model/model.py:43-60
+        self.filter_height, self.filter_width = 1, cfg.seq_length
+        self.in_channels, self.channel_multiplier = 2, cfg.channel_multiplier
+        self.input_size = 3
+        self.decoder_output = cfg.d_dim
+        self.rnn_size = cfg.rnn_size
+        self.seq_length = cfg.seq_length
+        self.batch_size = getattr(args, "batch_size", 1)
+        self.latent_size = cfg.latent_size
+        self.input_shape = [cfg.S, cfg.S]
+        self.vae_input_size = cfg.S * cfg.S
+        self.max_num_obj = cfg.max_num_obj
+        self.learning_rate = float(getattr(args, "learning_rate", 0.005))
+        self.weights = params if params is not None else self.define_weights(seed)
+        self._paths = {}
+        self._pinned = {}
+        # filled by forward(); same names as the reference's graph nodes
+        self.input_data = self.target_data = self.target_data_enc = self.temporal_data = None
+        self.rho_i = self.output_states = self.feature_pooling = None
+        self.cost = self.final_states = self.final_output = self.gradients = None
+        self.build_model()
+
+    # ------------------------------------------------------------------ reference API
+    def define_weights(self, seed=1):
+        """model/model.py:420-451 (+ library-default initialisers, D10)."""
+        return init_params(self.cfg, seed, self.device)
+
+    def build_model(self):
+        """model/model.py:79-403 built a graph for ONE sequence; here it sizes the buffers for
+        `batch_size` scenes and loads the kernel library (raises if it is missing)."""
+        self._path(max(int(self.batch_size), 1))
+
+    def get_name(self):
+        """model/model.py:405-412."""
+        return "cvae_input_%dx%d_latent%d_edim%d_ddim%d" % (
+            self.input_shape[0], self.input_shape[1], self.latent_size,
+            getattr(self.args, "e_dim", 256), self.cfg.d_dim)
+
+    # ------------------------------------------------------------------ the hot path
+    def _path(self, B) -> HotPath:
+        if B not in self._paths:
+            self._paths[B] = HotPath(self.cfg, self.weights, B, self.device)
+        return self._paths[B]
+
+    def _stage(self, name, arr):
+        """numpy -> pinned host staging buffer (reused) -> device, async on the current stream."""
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+        key = (name, tuple(t.shape))
+        if key not in self._pinned:
+            self._pinned[key] = (torch.empty(t.shape, dtype=torch.float32).pin_memory(),
+                                 torch.empty(t.shape, dtype=torch.float32, device=self.device))
+        pin, dev = self._pinned[key]
+        pin.copy_(t)
+        dev.copy_(pin, non_blocking=True)
+        return dev
+
+    def forward(self, input_data, target_data, eps=None, scene=None, stages=("generate", "rank"), seed=None):
+        """input_data [B,N,Tp,3], target_data [B,N,Tf,3] (id,x,y), agent-major as the reference's
+        placeholders (model/model.py:91-105) with a leading scene axis; eps [B*N,K,Z] (drawn with
+        `seed` if None, D1); scene [B,Hi,Wi,3].  CUDA tensors are used in place, numpy/CPU inputs
+        are staged through pinned memory.  Returns the dict of device outputs."""
+        cfg = self.cfg
+        to_dev = lambda n, x: x if (torch.is_tensor(x) and x.is_cuda) else self._stage(n, x.numpy() if torch.is_tensor(x) else x)
+        obs = to_dev("obs", input_data)
+        tgt = to_dev("tgt", target_data)
+        B = obs.shape[0]
+        if eps is None:
+            g = torch.Generator(device=self.device)
+            g.manual_seed(2 if seed is None else seed)
+            eps = torch.randn(B * cfg.max_num_obj, cfg.K, cfg.Z, generator=g, device=self.device)
+        else:
+            eps = to_dev("eps", eps)
+        if scene is None:
+            scene = torch.zeros(B, cfg.scene_size, cfg.scene_size, 3, device=self.device)
+        else:
+            scene = to_dev("scene", scene)
+        out = self._path(B).run(obs, tgt, eps, scene, stages)
+        self.input_data, self.target_data, self.target_data_enc = obs, tgt, tgt
+        self.temporal_data = obs
+        self.rho_i, self.output_states, self.feature_pooling = out["rho_i"], out["output_states"], out["feature_pooling"]
+        self.cost, self.final_states, self.final_output = out["cost"], out["H_x"], out["Y_refined"]
+        return out
+
+    def sample_and_rank(self, input_data, target_data, eps=None, scene=None):
+        """End-to-end public call with HOST buffers: stage inputs, run sample generation + IOC
+        ranking/refinement, copy the ranked result back.  Returns (Y_refined [B,N,K,Tf,2],
+        scores [iters,B,N,K], cost) as numpy."""
+        cfg = self.cfg
+        out = self.forward(input_data, target_data, eps, scene)
+        B = out["Y_refined"].shape[0] // (cfg.max_num_obj * cfg.K)
+        key = ("res", B)
+        if key not in self._pinned:
+            self._pinned[key] = (torch.empty_like(out["Y_refined"], device="cpu").pin_memory(),
+                                 torch.empty_like(out["ioc_scores"], device="cpu").pin_memory(),
+                                 torch.empty(2, dtype=torch.float32).pin_memory())
+        y, s, c = self._pinned[key]
+        y.copy_(out["Y_refined"], non_blocking=True)
+        s.copy_(out["ioc_scores"], non_blocking=True)
+        c.copy_(self._path(B).buf["cost"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        N, K, Tf = cfg.max_num_obj, cfg.K, cfg.pred_length
+        return (y.numpy().reshape(B, N, K, Tf, 2), s.numpy().reshape(-1, B, N, K), float(c[0]))
+
+    def sample(self, sess, traj, grid, dimensions, true_traj, num=10):
+        """Signature of model/model.py:613 kept as an entry point (the reference body is a broken
+        Social-LSTM leftover).  traj [obs_len, N, 3] -> [obs_len+num, N, 3]: the
+        top-ranked of the K refined samples per agent is appended.  `sess`, `grid`, `dimensions`
+        are accepted and ignored; `true_traj` ([obs_len+num, N, 3]) feeds the future encoder."""
+        cfg = self.cfg
+        traj = np.asarray(traj, np.float32)
+        true_traj = np.asarray(true_traj, np.float32)
+        obs_len = traj.shape[0]
+        if obs_len != cfg.seq_length or num != cfg.pred_length:
+            raise ValueError("sample(): traj must hold seq_length=%d frames and num must equal pred_length=%d"
+                             % (cfg.seq_length, cfg.pred_length))
+        inp = np.ascontiguousarray(traj.transpose(1, 0, 2))[None]                       # [1,N,Tp,3]
+        tgt = np.ascontiguousarray(true_traj[obs_len:obs_len + num].transpose(1, 0, 2))[None]
+        y, s, _ = self.sample_and_rank(inp, tgt)
+        best = s[-1, 0].argmax(-1)                                                      # [N]
+        pred = y[0, np.arange(cfg.max_num_obj), best]                                   # [N,Tf,2]
+        ids = traj[-1, :, 0]
+        new = np.concatenate([np.broadcast_to(ids[None, :, None], (num, cfg.max_num_obj, 1)),
+                              pred.transpose(1, 0, 2)], -1)
+        return np.vstack((traj, new.astype(np.float32)))
+
+    # closed-form helpers kept for API parity (model/model.py:494-611); torch, any device
+    def kld_loss(self, inputs, x_reconstr_mean, z_log_sigma_sq, z_mean):
+        latent = -0.5 * torch.sum(1.0 + z_log_sigma_sq - z_mean ** 2 - torch.exp(z_log_sigma_sq), 1)
+        return latent.mean()
+
+    def get_coef(self, output):
+        z_mux, z_muy, z_sx, z_sy, z_corr = torch.split(output, output.shape[1] // 5, 1)
+        return [z_mux, z_muy, torch.exp(z_sx), torch.exp(z_sy), torch.tanh(z_corr)]
+
+    def tf_2d_normal(self, x_val, y_val, mux, muy, sx_val, sy_val, rho):
+        normx, normy = x_val - mux, y_val - muy
+        sxsy = sx_val * sy_val
+        z_val = (normx / sx_val) ** 2 + (normy / sy_val) ** 2 - 2 * (rho * normx * normy) / sxsy
+        neg_rho = 1 - rho ** 2
+        return torch.exp(-z_val / (2 * neg_rho)) / (2 * np.pi * sxsy * torch.sqrt(neg_rho))
+
+    def get_reconstr_loss(self, z_mux, z_muy, z_sx, z_sy, z_corr, x_data, y_data):
+        result0 = self.tf_2d_normal(x_data, y_data, z_mux, z_muy, z_sx, z_sy, z_corr)
+        return torch.sum(-torch.log(torch.clamp(result0, min=1e-20)))
+
+    def sample_gaussian_2d(self, mux, muy, sx_val, sy_val, rho):
+        cov = [[sx_val * sx_val, rho * sx_val * sy_val], [rho * sx_val * sy_val, sy_val * sy_val]]
+        x_val = np.random.multivariate_normal([mux, muy], cov, 1)
+        return x_val[0][0], x_val[0][1]

@@ -95,6 +95,26 @@ typedef struct {
 int desire_version(void);
 const char* desire_last_error(void);
 
+/* ---- measurement hooks (bench.py): number of kernels launched by this library so far, and optional
+ * per-kernel CUDA-event timing of the tagged launches below. */
+long desire_launch_count(void);
+#define DESIRE_PROF_GRU_DEC1 0      /* Decoder-1 recurrence (a10)                       */
+#define DESIRE_PROF_GRU_DEC2 1      /* one Decoder-2 step (a14)                         */
+#define DESIRE_PROF_GRU_ENC 2       /* encoder recurrences (a3/a4)                      */
+#define DESIRE_PROF_SOCIAL_POOL 3   /* log-polar social pooling, one step               */
+#define DESIRE_PROF_SOCIAL_FC 4     /* pooled[R,G*H] @ sp_w GEMM, one step              */
+#define DESIRE_PROF_GATHER 5        /* bilinear scene gather, all steps of an iteration */
+#define DESIRE_PROF_DECONV2 6       /* CVAE decoder 4x4x128->8x8x64 GEMM, one chunk     */
+#define DESIRE_PROF_DECONV3 7       /* CVAE decoder 8x8x64->16x16x32 GEMM, one chunk    */
+#define DESIRE_PROF_COL2IM 8        /* col2im+BN+act kernels of the decoder             */
+#define DESIRE_PROF_DEC2_XPROJ 9    /* hoisted Decoder-2 input projection GEMMs         */
+#define DESIRE_PROF_SCENE_CNN 10    /* scene CNN convs                                  */
+#define DESIRE_PROF_READOUT 11      /* read-out + feature pooling (a11)                 */
+#define DESIRE_PROF_OTHER 12
+#define DESIRE_PROF_SLOTS 16
+int desire_prof_enable(int on);                                  /* resets the slots */
+int desire_prof_read(int slot, long* launches, double* total_ms); /* synchronises the recorded events */
+
 /* ---- generic dense layer: C = act(A[M,K] @ W[K,N] + bias), replaces tf.nn.xw_plus_b / tf.matmul
  * call sites model/model.py:249-251 (fc_c) and :272-275.  accumulate!=0 adds into C. */
 int desire_fc_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
