@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
         res = list(ex.map(lambda s: _compile(s, force, verbose), srcs))
     objs = [o for o, _ in res]
     if any(changed for _, changed in res) or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -1,0 +1,58 @@
+"""Golden fixtures (tests/golden/*.npz, made by tools/gen_golden.py from the oracle with fixed seeds).
+CPU: the oracle still reproduces them (freezes the restatement + initialisers + synthetic generator).
+GPU: the CUDA path through the C-ABI reproduces them within 1e-4 rel-L2."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import TOL, np_batch, np_params, np_tables, oracle_forward, rel_l2, small_cfg
+
+FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+SAMPLED = {"output_states_s": ("output_states", (slice(None), slice(None, None, 3), slice(None, None, 5))),
+           "feature_pooling_s": ("feature_pooling", (slice(None), slice(None, None, 4), slice(None, None, 17))),
+           "x_reconstr_mean_s": ("x_reconstr_mean", (slice(None), slice(None, None, 37))),
+           "scene_features_s": ("scene_features", (slice(None), slice(None, None, 3), slice(None, None, 3), slice(None, None, 5)))}
+
+
+def load(path):
+    g = dict(np.load(path))
+    B, miss, H, N, K, S, it = [int(x) for x in g.pop("meta")]
+    return g, small_cfg(d_dim=H, max_num_obj=N, num_samples=K, scene_size=S, ioc_iters=it), B, miss
+
+
+def compare(got, gold, tol):
+    bad = {}
+    for k, ref in gold.items():
+        v = got[SAMPLED[k][0]][SAMPLED[k][1]] if k in SAMPLED else got[k]
+        e = rel_l2(np.asarray(v).reshape(-1), ref.reshape(-1))
+        if not e <= tol:
+            bad[k] = e
+    return bad
+
+
+def test_fixtures_exist():
+    assert len(FILES) >= 2
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_oracle_reproduces_golden(path):
+    gold, cfg, B, miss = load(path)
+    out = oracle_forward(cfg, np_params(cfg), np_batch(cfg, B, 0, miss), np_tables(cfg))
+    assert not compare(out, gold, 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_cuda_reproduces_golden(path):
+    import torch
+    from desire_b200.config import init_params
+    from desire_b200.engine import HotPath
+    from desire_b200.synthetic import make_batch
+    gold, cfg, B, miss = load(path)
+    hp = HotPath(cfg, init_params(cfg, 1), B)
+    out = hp.run(*[t.cuda() for t in make_batch(cfg, B, 0, miss)])
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    assert not compare(got, gold, TOL)
