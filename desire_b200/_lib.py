@@ -51,9 +51,13 @@ SIGNATURES = {
     "desire_version": (I, []),
     "desire_last_error": (C.c_char_p, []),
     "desire_launch_count": (L, []),
+    "desire_set_gemm_mode": (I, [I]),
+    "desire_get_gemm_mode": (I, []),
     "desire_prof_enable": (I, [I]),
     "desire_prof_read": (I, [I, C.POINTER(C.c_long), C.POINTER(C.c_double)]),
     "desire_fc_fwd": (I, [P, I, P, I, P, P, I, I, I, I, I, I, P]),
+    "desire_gemm_tc_workspace_bytes": (Z, [I, I]),
+    "desire_gemm_tc_fwd": (I, [P, I, P, I, I, P, P, I, I, I, I, I, I, P, Z, P]),
     "desire_tconv_fwd": (I, [P, I, I, I, P, P, P, P]),
     "desire_gru_encode_fwd": (I, [P, I, I, I, C.POINTER(GruW), P, I, P]),
     "desire_cvae_encode_workspace_bytes": (Z, [I, I]),

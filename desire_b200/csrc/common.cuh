@@ -98,10 +98,24 @@ struct Im2col {
   // A(m,k): m = (img, oy, ox), k = (ky, kx, ci) over an NHWC input, zero outside
   int Hi, Wi, Ci, Ho, Wo, kh, kw, stride, pad_t, pad_l;
 };
+// pw: scratch for the packed BF16 weight image of the tcgen05 path (gemm_tc.cu); without it (or in
+// gemm mode 0) the FP32 CUDA-core kernel runs.
+struct PackWs {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+constexpr size_t PACK_WS_BYTES = 8u << 20;   // >= the largest packed weight of the path (venc fc / social fc)
 int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const float* bias, float* C,
-          int ldc, int M, int N, int K, int act, bool accumulate, cudaStream_t st);
+          int ldc, int M, int N, int K, int act, bool accumulate, cudaStream_t st, PackWs pw = PackWs());
 int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const float* bias, float* C,
-                 int ldc, int M, int N, int K, int act, cudaStream_t st);
+                 int ldc, int M, int N, int K, int act, cudaStream_t st, PackWs pw = PackWs());
+int gemm_mode();
+size_t gemm_tc_pack_bytes(int N, int K);
+bool gemm_tc_eligible(int M, int N, int K, const void* pack_ws, size_t pack_bytes);
+int gemm_tc(const float* A, int lda, const float* W, int ldw, bool trans_b, const float* bias, float* C, int ldc,
+            int M, int N, int K, int act, bool accumulate, void* pack_ws, cudaStream_t st);
+int gemm_tc_im2col(const float* X, const Im2col& g, const float* W, int ldw, const float* bias, float* C, int ldc,
+                   int M, int N, int K, int act, void* pack_ws, cudaStream_t st);
 
 // GRU recurrence (gru.cu).  xp: hoisted input projection incl. biases, [.., 3H] = (r|u|c) per row.
 struct GruSeqArgs {

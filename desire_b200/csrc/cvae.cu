@@ -115,7 +115,7 @@ extern "C" size_t desire_cvae_encode_workspace_bytes(int M, int Z) {
   (void)Z;
   size_t mc = M < ENC_CHUNK ? M : ENC_CHUNK;
   // col (<= mc*256*32) + a1 (mc*8192) + a2 (mc*4096) + a3 (mc*2048)
-  return align_up(mc * 8192 * 4) + align_up(mc * 8192 * 4) + align_up(mc * 4096 * 4) + align_up(mc * 2048 * 4);
+  return align_up(mc * 8192 * 4) + align_up(mc * 8192 * 4) + align_up(mc * 4096 * 4) + align_up(mc * 2048 * 4) + PACK_WS_BYTES;
 }
 
 extern "C" int desire_cvae_encode_fwd(const float* v, int M, int Z, const desire_cvae_enc_t* w, float* mu_logvar,
@@ -133,22 +133,23 @@ extern "C" int desire_cvae_encode_fwd(const float* v, int M, int Z, const desire
     float* a1 = W.take<float>((size_t)mc * 8192);
     float* a2 = W.take<float>((size_t)mc * 4096);
     float* a3 = W.take<float>((size_t)mc * 2048);
+    PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
     const float* x = v + (size_t)m0 * 1024;
     // conv5/2 SAME 32x32x1 -> 16x16x32 : pad_before = 1 (TF: total 3 -> 1 | 2)
     Im2col g1{32, 32, 1, 16, 16, 5, 5, 2, 1, 1};
-    DESIRE_TRY(sgemm_im2col(x, g1, w->c1.w, 32, nullptr, col, 32, mc * 256, 32, 25, DESIRE_ACT_NONE, st));
+    DESIRE_TRY(sgemm_im2col(x, g1, w->c1.w, 32, nullptr, col, 32, mc * 256, 32, 25, DESIRE_ACT_NONE, st, pw));
     DESIRE_TRY(colbn_act(col, mc, 16, 16, 1, 1, 0, 32, w->c1.b, w->c1.gamma, w->c1.beta, DESIRE_ACT_ELU, a1, st));
     // conv5/2 SAME 16x16x32 -> 8x8x64
     Im2col g2{16, 16, 32, 8, 8, 5, 5, 2, 1, 1};
-    DESIRE_TRY(sgemm_im2col(a1, g2, w->c2.w, 64, nullptr, col, 64, mc * 64, 64, 800, DESIRE_ACT_NONE, st));
+    DESIRE_TRY(sgemm_im2col(a1, g2, w->c2.w, 64, nullptr, col, 64, mc * 64, 64, 800, DESIRE_ACT_NONE, st, pw));
     DESIRE_TRY(colbn_act(col, mc, 8, 8, 1, 1, 0, 64, w->c2.b, w->c2.gamma, w->c2.beta, DESIRE_ACT_ELU, a2, st));
     // conv5 VALID 8x8x64 -> 4x4x128
     Im2col g3{8, 8, 64, 4, 4, 5, 5, 1, 0, 0};
-    DESIRE_TRY(sgemm_im2col(a2, g3, w->c3.w, 128, nullptr, col, 128, mc * 16, 128, 1600, DESIRE_ACT_NONE, st));
+    DESIRE_TRY(sgemm_im2col(a2, g3, w->c3.w, 128, nullptr, col, 128, mc * 16, 128, 1600, DESIRE_ACT_NONE, st, pw));
     DESIRE_TRY(colbn_act(col, mc, 4, 4, 1, 1, 0, 128, w->c3.b, w->c3.gamma, w->c3.beta, DESIRE_ACT_ELU, a3, st));
     // flatten (h,w,c) -> fc 2048 -> 2Z, no BN, no activation
     DESIRE_TRY(sgemm(a3, 2048, w->fc_w, 2 * Z, false, w->fc_b, mu_logvar + (size_t)m0 * 2 * Z, 2 * Z, mc, 2 * Z, 2048,
-                     DESIRE_ACT_NONE, false, st));
+                     DESIRE_ACT_NONE, false, st, pw));
   }
   return DESIRE_OK;
 }
@@ -160,7 +161,7 @@ extern "C" size_t desire_cvae_decode_workspace_bytes(int R, int Z) {
   (void)Z;
   size_t rc = R < DEC_CHUNK ? R : DEC_CHUNK;
   // col (<= rc*64*800) + a1 (rc*2048) + a2 (rc*4096) + a3 (rc*8192)
-  return align_up(rc * 51200 * 4) + align_up(rc * 2048 * 4) + align_up(rc * 4096 * 4) + align_up(rc * 8192 * 4);
+  return align_up(rc * 51200 * 4) + align_up(rc * 2048 * 4) + align_up(rc * 4096 * 4) + align_up(rc * 8192 * 4) + PACK_WS_BYTES;
 }
 
 extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire_cvae_dec_t* w, float* xr, void* ws,
@@ -178,9 +179,10 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
     float* a1 = W.take<float>((size_t)rc * 2048);
     float* a2 = W.take<float>((size_t)rc * 4096);
     float* a3 = W.take<float>((size_t)rc * 8192);
+    PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
     const float* zc = z + (size_t)r0 * Z;
     // deconv4 VALID 1x1xZ -> 4x4x128: col[r, (y,x,o)] = z[r,:] . W[y,x,o,:]
-    DESIRE_TRY(sgemm(zc, Z, w->d1.w, Z, true, nullptr, col, 2048, rc, 2048, Z, DESIRE_ACT_NONE, false, st));
+    DESIRE_TRY(sgemm(zc, Z, w->d1.w, Z, true, nullptr, col, 2048, rc, 2048, Z, DESIRE_ACT_NONE, false, st, pw));
     {
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
       DESIRE_TRY(colbn_act(col, rc, 1, 4, 4, 1, 0, 128, w->d1.b, w->d1.gamma, w->d1.beta, DESIRE_ACT_ELU, a1, st));
@@ -188,7 +190,7 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
     // deconv5 VALID 4x4x128 -> 8x8x64
     {
       ProfScope ps_(DESIRE_PROF_DECONV2, st);
-      DESIRE_TRY(sgemm(a1, 128, w->d2.w, 128, true, nullptr, col, 1600, rc * 16, 1600, 128, DESIRE_ACT_NONE, false, st));
+      DESIRE_TRY(sgemm(a1, 128, w->d2.w, 128, true, nullptr, col, 1600, rc * 16, 1600, 128, DESIRE_ACT_NONE, false, st, pw));
     }
     {
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
@@ -197,14 +199,14 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
     // deconv5/2 SAME 8x8x64 -> 16x16x32 (full 19x19, keep [1,17))
     {
       ProfScope ps_(DESIRE_PROF_DECONV3, st);
-      DESIRE_TRY(sgemm(a2, 64, w->d3.w, 64, true, nullptr, col, 800, rc * 64, 800, 64, DESIRE_ACT_NONE, false, st));
+      DESIRE_TRY(sgemm(a2, 64, w->d3.w, 64, true, nullptr, col, 800, rc * 64, 800, 64, DESIRE_ACT_NONE, false, st, pw));
     }
     {
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
       DESIRE_TRY(colbn_act(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st));
     }
     // deconv5/2 SAME 16x16x32 -> 32x32x1, BN + sigmoid
-    DESIRE_TRY(sgemm(a3, 32, w->d4.w, 32, true, nullptr, col, 25, rc * 256, 25, 32, DESIRE_ACT_NONE, false, st));
+    DESIRE_TRY(sgemm(a3, 32, w->d4.w, 32, true, nullptr, col, 25, rc * 256, 25, 32, DESIRE_ACT_NONE, false, st, pw));
     {
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
       DESIRE_TRY(colbn_act(col, rc, 16, 32, 5, 2, 1, 1, w->d4.b, w->d4.gamma, w->d4.beta, DESIRE_ACT_SIGMOID,

@@ -1,0 +1,362 @@
+// tcgen05 GEMM with FP32 interface: C[M,N] = act(A[M,K] @ W[K,N] + bias) (+C).
+//
+// sm_100a design (one 128 x BN output tile per CTA, up to two CTAs resident per SM so one tile's
+// epilogue overlaps the other's main loop):
+//   warps 0-3  A producers: FP32 rows (dense, or im2col-gathered from an NHWC image) are loaded with
+//              128-bit loads one K stage ahead, split into BF16 hi/lo and written to shared memory in the
+//              canonical UMMA K-major layout (tc.cuh); afterwards the same warps run the epilogue
+//              (tcgen05.ld of their 32 TMEM lanes -> bias/activation -> 128-byte row segments to HBM).
+//   warp 4     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM
+//              accumulator, 3 MMAs per K step in 3xBF16 mode (hi*hi + lo*hi + hi*lo), and frees each
+//              shared-memory stage with tcgen05.commit.
+//   warp 5     B loader: weights are pre-packed (pack_b_kernel) into per-(n-tile, k-stage) shared-memory
+//              images, so a stage is ONE 1-D bulk TMA copy (cp.async.bulk) completing on the stage's
+//              mbarrier.
+// Full/empty mbarrier ring of `stages` stages; accumulator handed to the epilogue by tcgen05.commit.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace desire {
+
+static int g_gemm_mode = 3;  // 0: FP32 CUDA cores, 1: single BF16 pass, 3: 3xBF16 (parity mode)
+int gemm_mode() { return g_gemm_mode; }
+
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128;       // rows per tile == TMEM lanes
+constexpr int BK = 32;        // K elements per stage (4 chunks of 8)
+constexpr int KC = BK / 8;
+constexpr int NTHR = 192;
+
+struct DenseA8 {
+  const float* A;
+  int lda, M, K;
+  bool vec;
+  __device__ __forceinline__ void load(int m, int k, float* v) const {
+    if (m >= M) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      return;
+    }
+    const float* p = A + (size_t)m * lda + k;
+    if (vec && k + 8 <= K) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(p));
+      float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldg(p + i) : 0.f;
+    }
+  }
+};
+
+struct Im2colA8 {
+  const float* X;
+  Im2col g;
+  int M, K;
+  __device__ __forceinline__ void load(int m, int k, float* v) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (m >= M || k >= K) return;
+    const int ox = m % g.Wo;
+    const int t = m / g.Wo;
+    const int oy = t % g.Ho;
+    const int img = t / g.Ho;
+    if (g.Ci % 8 == 0) {   // 8 consecutive k share (ky,kx): one contiguous 32-byte read
+      const int ci = k % g.Ci, t2 = k / g.Ci, kx = t2 % g.kw, ky = t2 / g.kw;
+      const int iy = oy * g.stride + ky - g.pad_t, ix = ox * g.stride + kx - g.pad_l;
+      if (iy < 0 || iy >= g.Hi || ix < 0 || ix >= g.Wi) return;
+      const float4* p = reinterpret_cast<const float4*>(X + (((size_t)img * g.Hi + iy) * g.Wi + ix) * g.Ci + ci);
+      float4 a = __ldg(p), b = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kk = k + i;
+        if (kk >= K) break;
+        const int ci = kk % g.Ci, t2 = kk / g.Ci, kx = t2 % g.kw, ky = t2 / g.kw;
+        const int iy = oy * g.stride + ky - g.pad_t, ix = ox * g.stride + kx - g.pad_l;
+        if (iy < 0 || iy >= g.Hi || ix < 0 || ix >= g.Wi) continue;
+        v[i] = __ldg(X + (((size_t)img * g.Hi + iy) * g.Wi + ix) * g.Ci + ci);
+      }
+    }
+  }
+};
+
+// W [K,N] (or [N,K] when trans) FP32 -> packed[(jn*nks + ks)] = { hi: [KC][BN][8] bf16, lo: same }
+__global__ void pack_b_kernel(const float* __restrict__ W, int ldw, int trans, int K, int N, int BN, int nks,
+                              int ntn, uint4* __restrict__ out) {
+  const long total = (long)ntn * nks * KC * BN;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx % BN);
+  long t = idx / BN;
+  const int c = (int)(t % KC);
+  t /= KC;
+  const int ks = (int)(t % nks);
+  const int jn = (int)(t / nks);
+  const int gn = jn * BN + n, k0 = ks * BK + c * 8;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + i;
+    v[i] = (gn < N && k < K) ? (trans ? __ldg(W + (size_t)gn * ldw + k) : __ldg(W + (size_t)k * ldw + gn)) : 0.f;
+  }
+  Split8 s = split8(v);
+  uint4* stage = out + ((size_t)jn * nks + ks) * (2 * KC * BN);
+  stage[c * BN + n] = s.hi;
+  stage[KC * BN + c * BN + n] = s.lo;
+}
+
+template <class ALoad>
+__global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A, const uint4* __restrict__ Bp,
+                                                       const float* __restrict__ bias, float* __restrict__ C, int ldc,
+                                                       int M, int N, int BN, int nks, int stages, int act,
+                                                       int accumulate, int passes, uint32_t tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int a_half = KC * TM * 16;              // bytes of A_hi (== A_lo) per stage
+  const int b_half = KC * BN * 16;
+  const int stage_bytes = 2 * a_half + 2 * b_half;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tfull = empty + stages;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int jn = blockIdx.x, m0 = blockIdx.y * TM;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 5);    // 4 producer warps + the B loader's expect_tx arrive
+      mbar_init(&empty[s], 1);   // one tcgen05.commit
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc_dyn(tslot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  if (warp < 4) {
+    // ===================== A producers (thread <-> row), one stage of loads in flight
+    const int m = m0 + tid;
+    float v[KC][8];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) A.load(m, c * 8, v[c]);
+    for (int ks = 0; ks < nks; ++ks) {
+      const int slot = ks % stages;
+      const uint32_t ph = (ks / stages) & 1;
+      mbar_wait(&empty[slot], ph ^ 1);
+      uint8_t* sa = smem + (size_t)slot * stage_bytes;
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        Split8 s = split8(v[c]);
+        *reinterpret_cast<uint4*>(sa + c * TM * 16 + tid * 16) = s.hi;
+        *reinterpret_cast<uint4*>(sa + a_half + c * TM * 16 + tid * 16) = s.lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[slot]);
+      if (ks + 1 < nks) {
+#pragma unroll
+        for (int c = 0; c < KC; ++c) A.load(m, (ks + 1) * BK + c * 8, v[c]);
+      }
+    }
+    // ===================== epilogue: TMEM lanes 32*warp .. +31 == rows m0 + tid
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const int n0 = jn * BN;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float acc[32];
+      const int ncol = min(32, BN - c0);          // BN is a multiple of 16
+      if (ncol == 32) tmem_ld32(trow + c0, acc);
+      else tmem_ld16(trow + c0, acc);
+      tmem_ld_wait();
+      if (m < M) {
+        float* crow = C + (size_t)m * ldc + n0 + c0;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + ncol <= N);
+        if (vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j >= ncol) break;
+            float4 o;
+            float* po = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = acc[j + e];
+              if (bias) x += __ldg(bias + n0 + c0 + j + e);
+              po[e] = x;
+            }
+            if (accumulate) {
+              float4 old = *reinterpret_cast<const float4*>(crow + j);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            o.x = act_apply(o.x, act); o.y = act_apply(o.y, act); o.z = act_apply(o.z, act); o.w = act_apply(o.w, act);
+            *reinterpret_cast<float4*>(crow + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (j >= ncol || n >= N) break;
+            float x = acc[j];
+            if (bias) x += __ldg(bias + n);
+            if (accumulate) x += crow[j];
+            crow[j] = act_apply(x, act);
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(TM, BN);
+      const uint32_t lbo_a = TM * 16, lbo_b = BN * 16;
+      uint32_t acc_flag = 0;
+      for (int ks = 0; ks < nks; ++ks) {
+        const int slot = ks % stages;
+        const uint32_t ph = (ks / stages) & 1;
+        mbar_wait(&full[slot], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)slot * stage_bytes);
+        const uint32_t sb = sa + 2 * a_half;
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j) {
+          const uint64_t ahi = smem_desc(sa + j * 2 * lbo_a, lbo_a, 128);
+          const uint64_t alo = smem_desc(sa + a_half + j * 2 * lbo_a, lbo_a, 128);
+          const uint64_t bhi = smem_desc(sb + j * 2 * lbo_b, lbo_b, 128);
+          const uint64_t blo = smem_desc(sb + b_half + j * 2 * lbo_b, lbo_b, 128);
+          mma_bf16(tmem, ahi, bhi, idesc, acc_flag);
+          acc_flag = 1;
+          if (passes == 3) {
+            mma_bf16(tmem, alo, bhi, idesc, 1);
+            mma_bf16(tmem, ahi, blo, idesc, 1);
+          }
+        }
+        mma_commit(&empty[slot]);     // frees the stage when these MMAs have read it
+      }
+      mma_commit(tfull);              // accumulator complete
+    }
+  } else {
+    // ===================== B loader: one bulk TMA copy per stage
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(Bp) + (size_t)jn * nks * (2 * b_half);
+      for (int ks = 0; ks < nks; ++ks) {
+        const int slot = ks % stages;
+        const uint32_t ph = (ks / stages) & 1;
+        mbar_wait(&empty[slot], ph ^ 1);
+        mbar_arrive_expect_tx(&full[slot], 2 * b_half);
+        bulk_g2s(smem + (size_t)slot * stage_bytes + 2 * a_half, src + (size_t)ks * (2 * b_half), 2 * b_half, &full[slot]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+}
+
+int pick_bn(int N) {
+  if (N <= 256) return (N + 15) / 16 * 16;
+  int best = 256, best_waste = 1 << 30;
+  const int cands[] = {256, 224, 192, 160, 128};
+  for (int bn : cands) {
+    int waste = (N + bn - 1) / bn * bn - N;
+    if (waste < best_waste) {
+      best_waste = waste;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+struct Plan {
+  int BN, ntn, nks, stages;
+  uint32_t tmem_cols;
+  size_t smem, pack_bytes;
+};
+Plan make_plan(int N, int K) {
+  Plan p;
+  p.BN = pick_bn(N);
+  p.ntn = (N + p.BN - 1) / p.BN;
+  p.nks = (K + BK - 1) / BK;
+  const size_t stage = 2 * (size_t)KC * TM * 16 + 2 * (size_t)KC * p.BN * 16;
+  int st = (int)((110 * 1024) / stage);      // two CTAs per SM
+  p.stages = st < 2 ? 2 : (st > 6 ? 6 : st);
+  if (p.stages > p.nks) p.stages = p.nks < 2 ? 2 : p.nks;
+  p.smem = p.stages * stage + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
+  uint32_t c = 32;
+  while ((int)c < p.BN) c <<= 1;
+  p.tmem_cols = c;
+  p.pack_bytes = (size_t)p.ntn * p.nks * 2 * KC * p.BN * 16;
+  return p;
+}
+
+template <class ALoad>
+int launch_tc(const ALoad& A, const float* W, int ldw, bool trans_b, const float* bias, float* C, int ldc, int M, int N,
+              int K, int act, bool accumulate, void* pack_ws, cudaStream_t st) {
+  const Plan p = make_plan(N, K);
+  {
+    const long total = (long)p.ntn * p.nks * KC * p.BN;
+    pack_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, ldw, trans_b ? 1 : 0, K, N, p.BN, p.nks, p.ntn,
+                                                                   (uint4*)pack_ws);
+    DESIRE_LAUNCH_CHECK();
+  }
+  DESIRE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<ALoad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  dim3 grid(p.ntn, (M + TM - 1) / TM);
+  gemm_tc_kernel<ALoad><<<grid, NTHR, p.smem, st>>>(A, (const uint4*)pack_ws, bias, C, ldc, M, N, p.BN, p.nks, p.stages,
+                                                    act, accumulate ? 1 : 0, g_gemm_mode == 1 ? 1 : 3, p.tmem_cols);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}
+
+}  // namespace
+
+size_t gemm_tc_pack_bytes(int N, int K) { return align_up(make_plan(N, K).pack_bytes); }
+
+// Returns true when the tensor-core path took the problem.
+bool gemm_tc_eligible(int M, int N, int K, const void* pack_ws, size_t pack_bytes) {
+  return g_gemm_mode != 0 && M >= 64 && N >= 16 && K >= 8 && pack_ws && pack_bytes >= make_plan(N, K).pack_bytes &&
+         (M + TM - 1) / TM <= 65535;
+}
+
+int gemm_tc(const float* A, int lda, const float* W, int ldw, bool trans_b, const float* bias, float* C, int ldc, int M,
+            int N, int K, int act, bool accumulate, void* pack_ws, cudaStream_t st) {
+  DenseA8 a{A, lda, M, K, (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0)};
+  return launch_tc(a, W, ldw, trans_b, bias, C, ldc, M, N, K, act, accumulate, pack_ws, st);
+}
+
+int gemm_tc_im2col(const float* X, const Im2col& g, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
+                   int N, int K, int act, void* pack_ws, cudaStream_t st) {
+  Im2colA8 a{X, g, M, K};
+  return launch_tc(a, W, ldw, false, bias, C, ldc, M, N, K, act, false, pack_ws, st);
+}
+
+}  // namespace desire
+
+extern "C" int desire_set_gemm_mode(int mode) {
+  DESIRE_CHECK_ARG(mode == 0 || mode == 1 || mode == 3, "desire_set_gemm_mode: mode must be 0 (fp32), 1 (bf16) or 3 (3xbf16)");
+  desire::g_gemm_mode = mode;
+  return DESIRE_OK;
+}
+extern "C" int desire_get_gemm_mode(void) { return desire::g_gemm_mode; }
+
+extern "C" size_t desire_gemm_tc_workspace_bytes(int N, int K) { return desire::gemm_tc_pack_bytes(N, K); }
+
+extern "C" int desire_gemm_tc_fwd(const float* A, int lda, const float* W, int ldw, int trans_w, const float* bias,
+                                  float* C, int ldc, int M, int N, int K, int act, int accumulate, void* ws,
+                                  size_t ws_bytes, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(A && W && C && M > 0 && N > 0 && K > 0, "desire_gemm_tc_fwd: bad arguments");
+  DESIRE_CHECK_ARG(lda >= K && ldc >= N && ldw >= (trans_w ? K : N), "desire_gemm_tc_fwd: leading dimensions too small");
+  if (!ws || ws_bytes < desire::gemm_tc_pack_bytes(N, K)) {
+    desire::set_error("desire_gemm_tc_fwd: workspace too small");
+    return DESIRE_ERR_WORKSPACE;
+  }
+  DESIRE_CHECK_ARG((M + 127) / 128 <= 65535, "desire_gemm_tc_fwd: M too large");
+  return desire::gemm_tc(A, lda, W, ldw, trans_w != 0, bias, C, ldc, M, N, K, act, accumulate != 0, ws,
+                         (cudaStream_t)stream);
+}

@@ -242,7 +242,9 @@ extern "C" int desire_gru_encode_fwd(const float* traj, int M, int T, int H, con
   return gru_seq(a, (cudaStream_t)stream);
 }
 
-extern "C" size_t desire_gru_decode_workspace_bytes(int R, int H) { return align_up((size_t)R * 3 * H * sizeof(float)); }
+extern "C" size_t desire_gru_decode_workspace_bytes(int R, int H) {
+  return align_up((size_t)R * 3 * H * sizeof(float)) + PACK_WS_BYTES;
+}
 
 extern "C" int desire_gru_decode_fwd(const float* x_z, const float* Hx, int ld_hx, int R, int K, int H, int T,
                                      const desire_gru_t* w, float* hs, void* ws, size_t ws_bytes,
@@ -254,8 +256,9 @@ extern "C" int desire_gru_decode_fwd(const float* x_z, const float* Hx, int ld_h
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* xp = (float*)ws;  // [R,3H] hoisted input projection (the input is the same every step)
-  DESIRE_TRY(sgemm(x_z, H, w->wg, 2 * H, false, w->bg, xp, 3 * H, R, 2 * H, H, DESIRE_ACT_NONE, false, st));
-  DESIRE_TRY(sgemm(x_z, H, w->wc, H, false, w->bc, xp + 2 * H, 3 * H, R, H, H, DESIRE_ACT_NONE, false, st));
+  PackWs pw{(char*)ws + align_up((size_t)R * 3 * H * sizeof(float)), PACK_WS_BYTES};
+  DESIRE_TRY(sgemm(x_z, H, w->wg, 2 * H, false, w->bg, xp, 3 * H, R, 2 * H, H, DESIRE_ACT_NONE, false, st, pw));
+  DESIRE_TRY(sgemm(x_z, H, w->wc, H, false, w->bc, xp + 2 * H, 3 * H, R, H, H, DESIRE_ACT_NONE, false, st, pw));
   GruSeqArgs a{};
   a.R = R; a.H = H; a.T = T;
   a.xp = xp; a.xp_row_stride = 3 * H; a.xp_step_stride = 0;

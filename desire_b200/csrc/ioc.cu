@@ -182,7 +182,7 @@ int social_pool_launch(const float* pos, long pos_stride, const float* h, int ld
 // ------------------------------------------------------------------------------------------ scene CNN
 extern "C" size_t desire_scene_cnn_workspace_bytes(int B, int Hi, int Wi) {
   size_t Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
-  return align_up((size_t)B * Ho * Wo * 16 * 4) + align_up((size_t)B * Ho * Wo * 32 * 4);
+  return align_up((size_t)B * Ho * Wo * 16 * 4) + align_up((size_t)B * Ho * Wo * 32 * 4) + PACK_WS_BYTES;
 }
 
 extern "C" int desire_scene_cnn_fwd(const float* img, int B, int Hi, int Wi, int Cs, const desire_scene_cnn_t* w,
@@ -197,6 +197,7 @@ extern "C" int desire_scene_cnn_fwd(const float* img, int B, int Hi, int Wi, int
   Workspace W(ws, ws_bytes);
   float* f1 = W.take<float>((size_t)B * Ho * Wo * 16);
   float* f2 = W.take<float>((size_t)B * Ho * Wo * 32);
+  PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
   // TF SAME: total pad = max((out-1)*s + k - in, 0), before = total/2
   const int pt1 = max((Ho - 1) * 2 + 5 - Hi, 0) / 2, pl1 = max((Wo - 1) * 2 + 5 - Wi, 0) / 2;
   // one image at a time keeps gridDim.y legal for any map size
@@ -204,13 +205,13 @@ extern "C" int desire_scene_cnn_fwd(const float* img, int B, int Hi, int Wi, int
     const size_t px = (size_t)Ho * Wo;
     Im2col g1{Hi, Wi, 3, Ho, Wo, 5, 5, 2, pt1, pl1};
     DESIRE_TRY(sgemm_im2col(img + (size_t)b * Hi * Wi * 3, g1, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, (int)px, 16,
-                            75, DESIRE_ACT_RELU, st));
+                            75, DESIRE_ACT_RELU, st, pw));
     Im2col g2{Ho, Wo, 16, Ho, Wo, 5, 5, 1, 2, 2};
     DESIRE_TRY(sgemm_im2col(f1 + b * px * 16, g2, w->c2_w, 32, w->c2_b, f2 + b * px * 32, 32, (int)px, 32, 400,
-                            DESIRE_ACT_RELU, st));
+                            DESIRE_ACT_RELU, st, pw));
     Im2col g3{Ho, Wo, 32, Ho, Wo, 5, 5, 1, 2, 2};
     DESIRE_TRY(sgemm_im2col(f2 + b * px * 32, g3, w->c3_w, Cs, w->c3_b, fmap + b * px * Cs, Cs, (int)px, Cs, 800,
-                            DESIRE_ACT_RELU, st));
+                            DESIRE_ACT_RELU, st, pw));
   }
   return DESIRE_OK;
 }
@@ -241,7 +242,7 @@ extern "C" int desire_social_pool_fwd(const float* pos, long pos_stride, const f
 // ------------------------------------------------------------------------------------------ IOC loop
 namespace {
 struct IocLayout {
-  size_t Xs, XP, pooled, fsp, h2, total;
+  size_t Xs, XP, pooled, fsp, h2, pack, total;
 };
 IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   const size_t R = (size_t)d->B * d->N * d->K, T = d->Tf, H = d->H;
@@ -253,6 +254,7 @@ IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   L.pooled = off; off += align_up(R * G * H * 4);
   L.fsp = off; off += align_up(R * H * 4);
   L.h2 = off; off += align_up(R * H * 4);
+  L.pack = off; off += PACK_WS_BYTES;
   L.total = off;
   return L;
 }
@@ -283,6 +285,7 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
   float* pooled = (float*)(base + L.pooled);
   float* fsp = (float*)(base + L.fsp);
   float* h2 = (float*)(base + L.h2);
+  PackWs pw{base + L.pack, PACK_WS_BYTES};
   const desire_gru_t& g = w->dec2;
 
   // feature_pooling columns of the static input are iteration-invariant
@@ -302,11 +305,11 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
     // hoisted input projection of the static features for all T steps: XP[(r,t), r|u|c]
     {
       ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
-      DESIRE_TRY(sgemm(Xs, Dst, g.wg, 2 * H, false, g.bg, XP, 3 * H, (int)(R * T), 2 * H, Dst, DESIRE_ACT_NONE, false, st));
+      DESIRE_TRY(sgemm(Xs, Dst, g.wg, 2 * H, false, g.bg, XP, 3 * H, (int)(R * T), 2 * H, Dst, DESIRE_ACT_NONE, false, st, pw));
     }
     {
       ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
-      DESIRE_TRY(sgemm(Xs, Dst, g.wc, H, false, g.bc, XP + 2 * H, 3 * H, (int)(R * T), H, Dst, DESIRE_ACT_NONE, false, st));
+      DESIRE_TRY(sgemm(Xs, Dst, g.wc, H, false, g.bc, XP + 2 * H, 3 * H, (int)(R * T), H, Dst, DESIRE_ACT_NONE, false, st, pw));
     }
     expand_rows_kernel<<<blocks(R * H, 256), 256, 0, st>>>(Hx, ld_hx, K, H, R, h2);
     DESIRE_LAUNCH_CHECK();
@@ -318,7 +321,7 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
       }
       {
         ProfScope ps_(DESIRE_PROF_SOCIAL_FC, st);
-        DESIRE_TRY(sgemm(pooled, G * H, w->sp_w, H, false, w->sp_b, fsp, H, (int)R, H, G * H, DESIRE_ACT_RELU, false, st));
+        DESIRE_TRY(sgemm(pooled, G * H, w->sp_w, H, false, w->sp_b, fsp, H, (int)R, H, G * H, DESIRE_ACT_RELU, false, st, pw));
       }
       GruSeqArgs a{};
       a.R = (int)R; a.H = H; a.T = 1;
@@ -336,7 +339,7 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
       DESIRE_LAUNCH_CHECK();
     }
     // regression refinement: Y[R, 2T] += h2 @ reg_w + reg_b
-    DESIRE_TRY(sgemm(h2, H, w->reg_w, 2 * T, false, w->reg_b, Y, 2 * T, (int)R, 2 * T, H, DESIRE_ACT_NONE, true, st));
+    DESIRE_TRY(sgemm(h2, H, w->reg_w, 2 * T, false, w->reg_b, Y, 2 * T, (int)R, 2 * T, H, DESIRE_ACT_NONE, true, st, pw));
   }
   return DESIRE_OK;
 }

@@ -189,7 +189,9 @@ extern "C" int desire_reparam_fwd(const float* mu_logvar, const float* eps, int 
   return DESIRE_OK;
 }
 
-extern "C" size_t desire_mask_softmax_workspace_bytes(int R, int H) { return align_up((size_t)R * H * sizeof(float)); }
+extern "C" size_t desire_mask_softmax_workspace_bytes(int R, int H) {
+  return align_up((size_t)R * H * sizeof(float)) + PACK_WS_BYTES;
+}
 
 extern "C" int desire_mask_softmax_fwd(const float* xr, int R, int S2, int H, int K, const float* w, const float* b,
                                        const float* Hx, int ld_hx, float* x_z, void* ws, size_t ws_bytes,
@@ -202,7 +204,8 @@ extern "C" int desire_mask_softmax_fwd(const float* xr, int R, int S2, int H, in
   if (R == 0) return DESIRE_OK;
   cudaStream_t st = (cudaStream_t)stream;
   float* logits = (float*)ws;
-  DESIRE_TRY(sgemm(xr, S2, w, H, false, b, logits, H, R, H, S2, DESIRE_ACT_RELU, false, st));
+  PackWs pw{(char*)ws + align_up((size_t)R * H * sizeof(float)), PACK_WS_BYTES};
+  DESIRE_TRY(sgemm(xr, S2, w, H, false, b, logits, H, R, H, S2, DESIRE_ACT_RELU, false, st, pw));
   softmax_gate_kernel<<<warps_grid(R, 256), 256, 0, st>>>(logits, R, H, K, Hx, ld_hx, x_z);
   DESIRE_LAUNCH_CHECK();
   return DESIRE_OK;

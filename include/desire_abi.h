@@ -112,6 +112,10 @@ long desire_launch_count(void);
 #define DESIRE_PROF_READOUT 11      /* read-out + feature pooling (a11)                 */
 #define DESIRE_PROF_OTHER 12
 #define DESIRE_PROF_SLOTS 16
+/* GEMM arithmetic of the dense layers: 3 = tcgen05 3xBF16 split with FP32 accumulation (default; meets the
+ * 1e-4 parity bar), 1 = tcgen05 single BF16 pass (fast mode), 0 = FP32 CUDA cores. */
+int desire_set_gemm_mode(int mode);
+int desire_get_gemm_mode(void);
 int desire_prof_enable(int on);                                  /* resets the slots */
 int desire_prof_read(int slot, long* launches, double* total_ms); /* synchronises the recorded events */
 
@@ -119,6 +123,13 @@ int desire_prof_read(int slot, long* launches, double* total_ms); /* synchronise
  * call sites model/model.py:249-251 (fc_c) and :272-275.  accumulate!=0 adds into C. */
 int desire_fc_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                   int M, int N, int K, int act, int accumulate, desire_stream_t stream);
+
+/* same contract on the tcgen05 path (3xBF16 or BF16 per desire_set_gemm_mode); trans_w: W stored [N,K].
+ * ws holds the packed BF16 image of W (desire_gemm_tc_workspace_bytes). */
+size_t desire_gemm_tc_workspace_bytes(int N, int K);
+int desire_gemm_tc_fwd(const float* A, int lda, const float* W, int ldw, int trans_w, const float* bias, float* C,
+                       int ldc, int M, int N, int K, int act, int accumulate, void* ws, size_t ws_bytes,
+                       desire_stream_t stream);
 
 /* ---- a2  rho_i = relu(depthwise_conv2d(VALID) + b), model/model.py:116-133.
  * obs [M,Tp,3] (id,x,y); w [Tp,2,C]; b [2C]; rho [M,2C] */
