@@ -136,7 +136,14 @@ struct GruSeqArgs {
   float* h_final;           // [R] rows, stride ld_hf, or null
   int ld_hf;
 };
-int gru_seq(const GruSeqArgs& a, cudaStream_t st);
+int gru_seq(const GruSeqArgs& a, cudaStream_t st, PackWs pw = PackWs());
+// tcgen05 recurrence (gru_tc.cu): taken when H % 32 == 0, H <= 256, the input projection is hoisted (xp)
+// and scratch for the packed weights is available
+size_t tc_pack_bytes(int K, int N, int BN);
+int tc_pack_b(const float* W, int ldw, bool trans, int K, int N, int BN, void* out, cudaStream_t st);
+size_t gru_tc_pack_bytes(int H);
+bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes);
+int gru_seq_tc(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
 
 // col2im + bias + per-row BN + activation (cvae.cu): col [R*Hin*Hin, k*k*Cout] -> out [R,Hout,Hout,Cout]
 int colbn_act(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int Cout,

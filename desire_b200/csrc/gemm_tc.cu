@@ -318,6 +318,19 @@ int launch_tc(const ALoad& A, const float* W, int ldw, bool trans_b, const float
 
 size_t gemm_tc_pack_bytes(int N, int K) { return align_up(make_plan(N, K).pack_bytes); }
 
+// Packed BF16 hi/lo image of W for an explicit n-tile width BN (used by the GRU kernel): per
+// (n-tile, 32-wide k stage) one contiguous block { hi [4][BN][8], lo [4][BN][8] }.
+size_t tc_pack_bytes(int K, int N, int BN) {
+  return (size_t)((N + BN - 1) / BN) * ((K + BK - 1) / BK) * 2 * KC * BN * 16;
+}
+int tc_pack_b(const float* W, int ldw, bool trans, int K, int N, int BN, void* out, cudaStream_t st) {
+  const int ntn = (N + BN - 1) / BN, nks = (K + BK - 1) / BK;
+  const long total = (long)ntn * nks * KC * BN;
+  pack_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, ldw, trans ? 1 : 0, K, N, BN, nks, ntn, (uint4*)out);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}
+
 // Returns true when the tensor-core path took the problem.
 bool gemm_tc_eligible(int M, int N, int K, const void* pack_ws, size_t pack_bytes) {
   return g_gemm_mode != 0 && M >= 64 && N >= 16 && K >= 8 && pack_ws && pack_bytes >= make_plan(N, K).pack_bytes &&

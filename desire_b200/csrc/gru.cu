@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(256) gru_seq_kernel(GruSeqArgs a, int cgn, int
 
 }  // namespace
 
-int gru_seq(const GruSeqArgs& a, cudaStream_t st) {
+int gru_seq(const GruSeqArgs& a, cudaStream_t st, PackWs pw) {
+  if (gru_tc_eligible(a, pw.p, pw.bytes)) return gru_seq_tc(a, pw.p, st);
   DESIRE_CHECK_ARG(a.H % 4 == 0 && a.H >= 4 && a.H <= 1024, "gru: H=%d must be a multiple of 4 in [4,1024]", a.H);
   DESIRE_CHECK_ARG(a.Ka % 4 == 0, "gru: extra operand width %d must be a multiple of 4", a.Ka);
   DESIRE_CHECK_ARG(!a.ex || a.T == 1, "gru: the extra operand is per-step (T must be 1)");
@@ -268,5 +269,5 @@ extern "C" int desire_gru_decode_fwd(const float* x_z, const float* Hx, int ld_h
   a.h0 = Hx; a.h0_div = K; a.ld_h0 = ld_hx;
   a.hs = hs; a.hs_row_stride = (long)T * H; a.hs_step_stride = H;
   ProfScope ps_(DESIRE_PROF_GRU_DEC1, st);
-  return gru_seq(a, st);
+  return gru_seq(a, st, pw);
 }

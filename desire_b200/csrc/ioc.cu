@@ -242,7 +242,7 @@ extern "C" int desire_social_pool_fwd(const float* pos, long pos_stride, const f
 // ------------------------------------------------------------------------------------------ IOC loop
 namespace {
 struct IocLayout {
-  size_t Xs, XP, pooled, fsp, h2, pack, total;
+  size_t Xs, XP, pooled, fsp, h2, wsp3, pack, total;
 };
 IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   const size_t R = (size_t)d->B * d->N * d->K, T = d->Tf, H = d->H;
@@ -254,6 +254,7 @@ IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   L.pooled = off; off += align_up(R * G * H * 4);
   L.fsp = off; off += align_up(R * H * 4);
   L.h2 = off; off += align_up(R * H * 4);
+  L.wsp3 = off; off += align_up(H * 3 * H * 4);
   L.pack = off; off += PACK_WS_BYTES;
   L.total = off;
   return L;
@@ -285,8 +286,15 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
   float* pooled = (float*)(base + L.pooled);
   float* fsp = (float*)(base + L.fsp);
   float* h2 = (float*)(base + L.h2);
+  float* wsp3 = (float*)(base + L.wsp3);
   PackWs pw{base + L.pack, PACK_WS_BYTES};
   const desire_gru_t& g = w->dec2;
+  // [H,3H] = dec2 rows [Dst,Dst+H) of (wg | wc): projection of the social feature fsp, applied per step on
+  // top of the hoisted projection of the static features
+  DESIRE_CUDA(cudaMemcpy2DAsync(wsp3, 3 * H * sizeof(float), g.wg + (size_t)Dst * 2 * H, 2 * H * sizeof(float),
+                                2 * H * sizeof(float), H, cudaMemcpyDeviceToDevice, st));
+  DESIRE_CUDA(cudaMemcpy2DAsync(wsp3 + 2 * H, 3 * H * sizeof(float), g.wc + (size_t)Dst * H, H * sizeof(float),
+                                H * sizeof(float), H, cudaMemcpyDeviceToDevice, st));
 
   // feature_pooling columns of the static input are iteration-invariant
   copy_cols_kernel<<<blocks(R * T * C2, 256), 256, 0, st>>>(fpool, C2, R * T, Xs + Fv + Cs, Dst);
@@ -323,17 +331,23 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
         ProfScope ps_(DESIRE_PROF_SOCIAL_FC, st);
         DESIRE_TRY(sgemm(pooled, G * H, w->sp_w, H, false, w->sp_b, fsp, H, (int)R, H, G * H, DESIRE_ACT_RELU, false, st, pw));
       }
+      {
+        // XP[:, t, :] += fsp @ wsp3  (completes the step's input projection)
+        ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
+        DESIRE_TRY(sgemm(fsp, H, wsp3, 3 * H, false, nullptr, XP + (size_t)t * 3 * H, T * 3 * H, (int)R, 3 * H, H,
+                         DESIRE_ACT_NONE, true, st, pw));
+      }
       GruSeqArgs a{};
       a.R = (int)R; a.H = H; a.T = 1;
       a.xp = XP + (size_t)t * 3 * H; a.xp_row_stride = (long)T * 3 * H; a.xp_step_stride = 0;
-      a.ex = fsp; a.Ka = H; a.ld_ex = H;
-      a.w_g = g.wg + (size_t)Dst * 2 * H;       // rows [Dst, Dst+H): fsp, rows [Dst+H, Dst+2H): state
-      a.w_c = g.wc + (size_t)Dst * H;
+      a.Ka = 0;
+      a.w_g = g.wg + (size_t)(Dst + H) * 2 * H;   // state rows
+      a.w_c = g.wc + (size_t)(Dst + H) * H;
       a.h0 = h2; a.h0_div = 1; a.ld_h0 = H;
       a.h_final = h2; a.ld_hf = H;
       {
         ProfScope ps_(DESIRE_PROF_GRU_DEC2, st);
-        DESIRE_TRY(gru_seq(a, st));
+        DESIRE_TRY(gru_seq(a, st, pw));
       }
       score_kernel<<<blocks(R * 32, 256), 256, 0, st>>>(h2, R, H, w->score_w, w->score_b, score, t == 0 ? 1 : 0);
       DESIRE_LAUNCH_CHECK();

@@ -24,7 +24,8 @@ def run_gpu(cfg, B, seed=0, n_missing=0):
     return {k: v.detach().cpu().numpy() for k, v in out.items()}
 
 
-@pytest.mark.parametrize("H,N,K,B,missing", [(48, 8, 1, 2, 0), (48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (16, 5, 2, 1, 0)])
+@pytest.mark.parametrize("H,N,K,B,missing", [(48, 8, 1, 2, 0), (48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (16, 5, 2, 1, 0),
+                                                (64, 10, 5, 2, 1), (256, 6, 6, 2, 0), (32, 40, 2, 2, 0)])
 def test_full_path_matches_oracle(H, N, K, B, missing):
     cfg = small_cfg(d_dim=H, max_num_obj=N, num_samples=K)
     got = run_gpu(cfg, B, n_missing=missing)
