@@ -1,4 +1,5 @@
-// Library identity and the thread-local error string of the C-ABI.
+// Library identity, the thread-local error string, the launch counter and the optional per-kernel
+// CUDA-event timers of the C-ABI.
 #include <stdarg.h>
 
 #include <atomic>
@@ -20,67 +21,71 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct ProfSlot {
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
-  cudaEvent_t open = nullptr;
-};
+// ---- per-kernel timing: ProfScope names the slot, DESIRE_LAUNCH brackets the launch itself with two
+// events taken from a pool (no event creation on the hot path), so host-side preparation between
+// launches never lands inside a bracket.
 static bool g_prof = false;
-static ProfSlot g_slots[DESIRE_PROF_SLOTS];
 static std::mutex g_prof_mu;
+static std::vector<cudaEvent_t> g_pool;
+static size_t g_pool_next = 0;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_slots[DESIRE_PROF_SLOTS];
+static thread_local int t_slot = -1;
+static thread_local cudaEvent_t t_open = nullptr;
 
-void prof_begin(int slot, cudaStream_t st) {
-  if (!g_prof || slot < 0 || slot >= DESIRE_PROF_SLOTS) return;
-  std::lock_guard<std::mutex> lk(g_prof_mu);
-  cudaEvent_t e;
-  if (cudaEventCreate(&e) != cudaSuccess) return;
-  cudaEventRecord(e, st);
-  g_slots[slot].open = e;
+int prof_set_slot(int slot) {
+  int old = t_slot;
+  t_slot = slot;
+  return old;
 }
-void prof_end(int slot, cudaStream_t st) {
-  if (!g_prof || slot < 0 || slot >= DESIRE_PROF_SLOTS) return;
-  std::lock_guard<std::mutex> lk(g_prof_mu);
-  ProfSlot& s = g_slots[slot];
-  if (!s.open) return;
-  cudaEvent_t e;
-  if (cudaEventCreate(&e) != cudaSuccess) return;
-  cudaEventRecord(e, st);
-  s.ev.emplace_back(s.open, e);
-  s.open = nullptr;
-}
-static void prof_reset() {
-  for (auto& s : g_slots) {
-    for (auto& p : s.ev) {
-      cudaEventDestroy(p.first);
-      cudaEventDestroy(p.second);
-    }
-    s.ev.clear();
-    if (s.open) cudaEventDestroy(s.open);
-    s.open = nullptr;
+static cudaEvent_t pool_take() {
+  if (g_pool_next == g_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    g_pool.push_back(e);
   }
+  return g_pool[g_pool_next++];
+}
+void prof_kernel_begin(cudaStream_t st) {
+  if (!g_prof || t_slot < 0 || t_slot >= DESIRE_PROF_SLOTS) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  t_open = pool_take();
+  if (t_open) cudaEventRecord(t_open, st);
+}
+void prof_kernel_end(cudaStream_t st) {
+  if (!g_prof || !t_open) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t e = pool_take();
+  if (e) {
+    cudaEventRecord(e, st);
+    g_slots[t_slot].emplace_back(t_open, e);
+  }
+  t_open = nullptr;
 }
 }  // namespace desire
 
+extern "C" int desire_version(void) { return DESIRE_ABI_VERSION; }
+extern "C" const char* desire_last_error(void) { return desire::g_err; }
 extern "C" long desire_launch_count(void) { return desire::g_launches.load(); }
+
 extern "C" int desire_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(desire::g_prof_mu);
-  desire::prof_reset();
+  for (auto& s : desire::g_slots) s.clear();
+  desire::g_pool_next = 0;           // events are reused; earlier readings are discarded
   desire::g_prof = on != 0;
   return DESIRE_OK;
 }
+
 extern "C" int desire_prof_read(int slot, long* launches, double* total_ms) {
   DESIRE_CHECK_ARG(slot >= 0 && slot < DESIRE_PROF_SLOTS && launches && total_ms, "desire_prof_read: bad arguments");
   std::lock_guard<std::mutex> lk(desire::g_prof_mu);
   double tot = 0;
-  for (auto& p : desire::g_slots[slot].ev) {
+  for (auto& p : desire::g_slots[slot]) {
     DESIRE_CUDA(cudaEventSynchronize(p.second));
     float ms = 0;
     DESIRE_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
     tot += ms;
   }
-  *launches = (long)desire::g_slots[slot].ev.size();
+  *launches = (long)desire::g_slots[slot].size();
   *total_ms = tot;
   return DESIRE_OK;
 }
-
-extern "C" int desire_version(void) { return DESIRE_ABI_VERSION; }
-extern "C" const char* desire_last_error(void) { return desire::g_err; }

@@ -13,13 +13,13 @@ void count_launch();
 
 // Optional per-kernel timing (desire_prof_enable): a ProfScope brackets ONE launch with CUDA events on
 // the launching stream; desire_prof_read sums them per slot.  Off by default (zero overhead but a branch).
-void prof_begin(int slot, cudaStream_t st);
-void prof_end(int slot, cudaStream_t st);
-struct ProfScope {
-  int slot;
-  cudaStream_t st;
-  ProfScope(int s, cudaStream_t st_) : slot(s), st(st_) { prof_begin(slot, st); }
-  ~ProfScope() { prof_end(slot, st); }
+int prof_set_slot(int slot);
+void prof_kernel_begin(cudaStream_t st);
+void prof_kernel_end(cudaStream_t st);
+struct ProfScope {   // names the slot that DESIRE_LAUNCH-bracketed kernels inside it are charged to
+  int old;
+  ProfScope(int s, cudaStream_t) : old(prof_set_slot(s)) {}
+  ~ProfScope() { prof_set_slot(old); }
 };
 
 #define DESIRE_CHECK_ARG(cond, ...)            \
@@ -45,6 +45,25 @@ struct ProfScope {
   do {                                        \
     ::desire::count_launch();                 \
     DESIRE_CUDA(cudaGetLastError());          \
+  } while (0)
+
+// launch + (optional) tight event bracket + launch counter/error check
+#define DESIRE_LAUNCH(st, ...)            \
+  do {                                    \
+    ::desire::prof_kernel_begin(st);      \
+    __VA_ARGS__;                          \
+    ::desire::prof_kernel_end(st);        \
+    DESIRE_LAUNCH_CHECK();                \
+  } while (0)
+
+// raise a kernel's dynamic shared-memory limit once per process (cached per call site)
+#define DESIRE_ENSURE_SMEM(kernel, bytes)                                                              \
+  do {                                                                                                 \
+    static size_t cached_ = 0;                                                                         \
+    if ((size_t)(bytes) > cached_) {                                                                   \
+      DESIRE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      cached_ = (size_t)(bytes);                                                                       \
+    }                                                                                                  \
   } while (0)
 
 #define DESIRE_TRY(call)          \
@@ -91,6 +110,28 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- log-polar bin of d = pos_j - pos_i; exact arithmetic on the shared tables (oracle: logpolar_bin)
+__device__ __forceinline__ int logpolar_bin(float dx, float dy, const float* r2e, int n_rad, const float* dirs,
+                                            int n_ang) {
+  const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  int rb = -1;
+  for (int e = 0; e <= n_rad; ++e) rb += (r2 >= r2e[e]) ? 1 : 0;
+  if (rb < 0 || rb >= n_rad) return -1;
+  int ab = n_ang - 1;
+  bool ge0 = __fsub_rn(__fmul_rn(dirs[0], dy), __fmul_rn(dirs[1], dx)) >= 0.f;
+  bool ge = ge0;
+  for (int s = 0; s < n_ang; ++s) {
+    bool gn = (s + 1 < n_ang) ? (__fsub_rn(__fmul_rn(dirs[2 * (s + 1)], dy), __fmul_rn(dirs[2 * (s + 1) + 1], dx)) >= 0.f)
+                              : ge0;
+    if (ge && !gn) {
+      ab = s;
+      break;
+    }
+    ge = gn;
+  }
+  return rb * n_ang + ab;
+}
+
 // ---- internal cross-file entry points (all asynchronous on `st`)
 // C[M,N] (ldc) = act(A @ B + bias) (+C if accumulate).  A via loader (see gemm_f32.cu), B [K,N] ldb,
 // or, when trans_b, B stored [N,K] (ldb = K stride).
@@ -110,6 +151,34 @@ int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const 
 int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const float* bias, float* C,
                  int ldc, int M, int N, int K, int act, cudaStream_t st, PackWs pw = PackWs());
 int gemm_mode();
+// A weight packed ONCE for many GEMM calls (IOC loop): pack_weight() fills `packed` when the tensor-core
+// path will be used; gemm_packed() then skips the per-call packing.
+struct PackedW {
+  const float* W = nullptr;
+  int ldw = 0;
+  bool trans = false;
+  int K = 0, N = 0;
+  const void* packed = nullptr;
+};
+int pack_weight(PackedW& w, void* ws, size_t ws_bytes, cudaStream_t st);
+int gemm_packed(const float* A, int lda, const PackedW& w, const float* bias, float* C, int ldc, int M, int act,
+                bool accumulate, cudaStream_t st);
+// fully fused social pooling + fc on tensor cores (social_tc.cu): fsp = relu(pool(h) @ sp_w + b)
+struct SocialFcArgs {
+  const float* pos;      // position of row r at pos + r*pos_stride (x,y)
+  long pos_stride;
+  const float* h;        // [R,H] hidden vectors (row stride ld_h)
+  int ld_h;
+  const float* obs;      // [B*N,Tp,3] ids for the existence mask
+  int Tp, B, N, K, H, n_rad, n_ang;
+  const float* r2_edges;
+  const float* dirs;
+  const void* packed;    // sp_w [G*H, H] packed for N-tile H (tc_pack_b / pack_weight)
+  const float* bias;
+  float* out;            // fsp [R,H]
+};
+bool social_fc_tc_eligible(const SocialFcArgs& a);
+int social_fc_tc(const SocialFcArgs& a, cudaStream_t st);
 size_t gemm_tc_pack_bytes(int N, int K);
 bool gemm_tc_eligible(int M, int N, int K, const void* pack_ws, size_t pack_bytes);
 int gemm_tc(const float* A, int lda, const float* W, int ldw, bool trans_b, const float* bias, float* C, int ldc,
@@ -135,7 +204,9 @@ struct GruSeqArgs {
   long hs_row_stride, hs_step_stride;
   float* h_final;           // [R] rows, stride ld_hf, or null
   int ld_hf;
+  const void* packed = nullptr;   // optional: weights already packed by gru_tc_pack (skips per-call packing)
 };
+int gru_tc_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st);
 int gru_seq(const GruSeqArgs& a, cudaStream_t st, PackWs pw = PackWs());
 // tcgen05 recurrence (gru_tc.cu): taken when H % 32 == 0, H <= 256, the input projection is hoisted (xp)
 // and scratch for the packed weights is available

