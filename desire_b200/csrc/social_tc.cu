@@ -8,10 +8,11 @@
 //   prologue   the groups' hidden vectors ([128][H+4] FP32, padded rows) and positions are staged in shared
 //              memory once; each producer thread (one row) bins its N-1 neighbours with the oracle's exact
 //              arithmetic and counting-sorts them into a private per-bin list (ascending j);
-//   warps 0-15 four threads per row, one 8-column chunk each (16 warps so every SM sub-partition has four warps
-//              to hide shared-memory latency): per 32-wide K stage (= a 32-column slice of one bin) sum the listed
-//              neighbours' slices from shared memory in list order, divide by the count, split to BF16 hi/lo,
-//              store as the UMMA A operand; afterwards: epilogue (bias + ReLU) of a 32x32 accumulator block each;
+//   warps 0-15 producers (16 warps so every SM sub-partition has four to hide shared-memory latency).  Warp w owns
+//              tile rows 8w..8w+7 and 8 lanes cooperate on a row (one 16-byte chunk of a 64-column K stage each):
+//              sum the listed neighbours' slices from shared memory in list order, scale by 1/count, split to
+//              BF16 hi/lo, store as the UMMA A operand.  Neighbour loops diverge over 4 rows, not 32.
+//              Afterwards: epilogue (bias + ReLU) of a 32x32 accumulator block each;
 //   warp 16    tcgen05.mma issuer (M=128, N=H, 3xBF16), accumulator in TMEM;
 //   warp 17    streams the packed sp_w stages with 1-D bulk TMA copies.
 #include "common.cuh"
@@ -22,14 +23,14 @@ namespace {
 
 using namespace tc;
 
-constexpr int TM = 128, BK = 32, KC = 4, STAGES = 3;
+constexpr int TM = 128, BK = 64, KC = 8, STAGES = 2;   // a stage = 64 columns of one bin = two packed 32-col blocks
 constexpr int NPW = 16;                 // producer/epilogue warps: 4 threads per row, one 8-column chunk each
 constexpr int NTHR = (NPW + 2) * 32;
 constexpr int MAXG = 64;
 
 struct Layout {
   int hs_ld;            // floats per staged hidden row
-  size_t hs, px, py, tab, lists, list_stride, stages, stage_bytes, bars, total;
+  size_t hs, px, py, tab, lists, list_stride, bins, stages, stage_bytes, bars, total;
 };
 __host__ __device__ inline Layout make_layout(int H, int Npad, int G, int n_rad, int n_ang) {
   Layout L;
@@ -41,6 +42,7 @@ __host__ __device__ inline Layout make_layout(int H, int Npad, int G, int n_rad,
   L.tab = off; off += (size_t)((n_rad + 1 + 2 * n_ang + 3) / 4 * 4) * 4;
   L.list_stride = (size_t)((G + 1 + Npad + 3) / 4 * 4);          // bytes per row: off[G+1] then list[Npad]
   L.lists = off; off += TM * L.list_stride;
+  L.bins = off; off += (size_t)TM * Npad;                       // bin of every (row, neighbour) pair, 255 = none
   off = (off + 1023) / 1024 * 1024;
   L.stage_bytes = 2 * (size_t)KC * TM * 16 + 2 * (size_t)KC * H * 16;
   L.stages = off; off += STAGES * L.stage_bytes;
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
   float* py = reinterpret_cast<float*>(smem + L.py);
   float* tab = reinterpret_cast<float*>(smem + L.tab);
   uint8_t* lists = smem + L.lists;
+  uint8_t* bins = smem + L.bins;
   uint8_t* stages = smem + L.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + STAGES;
@@ -69,7 +72,9 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
   const long ngroups = (long)a.B * K;
   const long grp0 = (long)blockIdx.x * gpt;
   const int nks = (G * H) / BK;
-  const int a_half = KC * TM * 16, b_half = KC * H * 16;
+  const int a_half = KC * TM * 16;          // bytes of A_hi per stage (8 chunk planes)
+  const int b_blk = 4 * H * 16;             // bytes of one packed hi (or lo) block of 32 columns
+  const int b_half = 2 * b_blk;             // per stage: two blocks, each hi+lo => 2*b_half bytes in total
 
   // global row of tile lane l (or -1): group grp0 + l/Npad = (b, k), agent i = l % Npad
   auto row_of = [&](int l) -> long {
@@ -123,83 +128,95 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
   const uint32_t tmem = *tslot;
 
   if (warp < NPW) {
-    // ===================== 16 producer warps: thread = (row = tid % 128, chunk = tid / 128)
-    const int rl = tid & (TM - 1), ch = tid >> 7;              // tile lane (row), 8-column chunk of the stage
-    const long myrow = row_of(rl);
-    uint8_t* off = lists + (size_t)rl * L.list_stride;         // [G+1]
-    uint8_t* lst = off + G + 1;                                 // [Npad]
-    const int gbase = (rl / Npad) * Npad;                       // first lane of my group
-    if (ch == 0) {
-      // ---- binning: counting sort of this row's neighbours into per-bin lists (ascending j)
-      const int me = rl % Npad;
+    // ===================== binning, all 512 threads: thread (row rl, quarter q) bins neighbours j = q, q+4, ...
+    {
+      const int rl = tid & (TM - 1), q = tid >> 7;
+      const long r = row_of(rl);
+      const int gbase = (rl / Npad) * Npad, me = rl % Npad;
+      uint8_t* brow = bins + (size_t)rl * Npad;
       // a masked row still pools its existing neighbours: its own position comes from global memory
       float xi = 0.f, yi = 0.f;
-      if (myrow >= 0) {
-        xi = __ldg(a.pos + myrow * a.pos_stride);
-        yi = __ldg(a.pos + myrow * a.pos_stride + 1);
+      if (r >= 0) {
+        xi = __ldg(a.pos + r * a.pos_stride);
+        yi = __ldg(a.pos + r * a.pos_stride + 1);
       }
-      for (int g = 0; g <= G; ++g) off[g] = 0;
-      if (myrow >= 0) {
-        for (int j = 0; j < N; ++j) {                           // pass 1: counts (stored at off[g+1])
-          if (j == me) continue;
+      for (int j = q; j < N; j += 4) {
+        int g = -1;
+        if (r >= 0 && j != me) {
           const float dx = px[gbase + j] - xi, dy = py[gbase + j] - yi;
-          if (dx == dx) {
-            const int g = logpolar_bin(dx, dy, tab, a.n_rad, tab + a.n_rad + 1, a.n_ang);
-            if (g >= 0) off[g + 1]++;
-          }
+          if (dx == dx) g = logpolar_bin(dx, dy, tab, a.n_rad, tab + a.n_rad + 1, a.n_ang);
         }
-        for (int g = 0; g < G; ++g) off[g + 1] += off[g];       // prefix: off[g] = start of bin g
-        for (int j = 0; j < N; ++j) {                           // pass 2: fill (off[g] is the cursor)
-          if (j == me) continue;
-          const float dx = px[gbase + j] - xi, dy = py[gbase + j] - yi;
-          if (dx == dx) {
-            const int g = logpolar_bin(dx, dy, tab, a.n_rad, tab + a.n_rad + 1, a.n_ang);
-            if (g >= 0) lst[off[g]++] = (uint8_t)j;
-          }
-        }
-        for (int g = G; g > 0; --g) off[g] = off[g - 1];        // cursors ended at the next bin's start: shift back
-        off[0] = 0;
+        brow[j] = (uint8_t)g;                                   // 255 = no bin
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");    // lists visible to the other chunk threads
+    asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
+    // ===================== per-row counting sort into per-bin lists (ascending j), one thread per row
+    if (tid < TM) {
+      uint8_t* off = lists + (size_t)tid * L.list_stride;       // [G+1]
+      uint8_t* lst = off + G + 1;                                // [Npad]
+      const uint8_t* brow = bins + (size_t)tid * Npad;
+      for (int g = 0; g <= G; ++g) off[g] = 0;
+      for (int j = 0; j < N; ++j) {                              // counts, stored at off[g+1]
+        const int g = brow[j];
+        if (g < G) off[g + 1]++;
+      }
+      for (int g = 0; g < G; ++g) off[g + 1] += off[g];          // prefix: off[g] = start of bin g
+      for (int j = 0; j < N; ++j) {                              // fill (off[g] is the cursor)
+        const int g = brow[j];
+        if (g < G) lst[off[g]++] = (uint8_t)j;
+      }
+      for (int g = G; g > 0; --g) off[g] = off[g - 1];           // cursors ended at the next bin's start: shift back
+      off[0] = 0;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
 
-    // ===================== A producer: this thread's 8 columns of a 32-column slice of one bin per stage
-    const float* hgrp = hs + (size_t)gbase * L.hs_ld + ch * 8;
-    const uint32_t a_off = ch * TM * 16 + rl * 16;
+    // ===================== A producer.  Warp w owns tile rows 8w..8w+7: lane -> (row 8w + lane%8, chunk pair
+    // lane/8 and 4 + lane/8 of the 64-column stage).  A quarter-warp therefore stores 8 consecutive rows of one
+    // chunk plane = 128 contiguous bytes (conflict-free), and every lane converts exactly the 16 values it stores.
+    const int prow = warp * 8 + (lane & 7);
+    const int kq = lane >> 3;
+    const uint8_t* off = lists + (size_t)prow * L.list_stride;
+    const uint8_t* lst = off + G + 1;
+    const float* hrow = hs + (size_t)((prow / Npad) * Npad) * L.hs_ld + kq * 8;
+    const uint32_t aoff = kq * TM * 16 + prow * 16;
     for (int ks = 0; ks < nks; ++ks) {
       const int slot = ks % STAGES;
       const uint32_t ph = (ks / STAGES) & 1;
       const int k0 = ks * BK;
       const int g = k0 / H, col = k0 - g * H;
       const int o0 = off[g], o1 = off[g + 1];
-      uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+      uint4 hi0 = make_uint4(0, 0, 0, 0), lo0 = hi0, hi1 = hi0, lo1 = hi0;
       if (o1 > o0) {
-        float v[8];
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
         for (int o = o0; o < o1; ++o) {
-          const float4* p = reinterpret_cast<const float4*>(hgrp + (size_t)lst[o] * L.hs_ld + col);
-          const float4 x = p[0], y = p[1];
-          v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w;
-          v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+          const float4* p = reinterpret_cast<const float4*>(hrow + (size_t)lst[o] * L.hs_ld + col);
+          const float4 x0 = p[0], y0 = p[1], x1 = p[8], y1 = p[9];      // chunks kq and kq+4 (32 floats apart)
+          v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
+          v[4] += y0.x; v[5] += y0.y; v[6] += y0.z; v[7] += y0.w;
+          v[8] += x1.x; v[9] += x1.y; v[10] += x1.z; v[11] += x1.w;
+          v[12] += y1.x; v[13] += y1.y; v[14] += y1.z; v[15] += y1.w;
         }
         if (o1 - o0 > 1) {
-          const float cnt = (float)(o1 - o0);
+          const float inv = __frcp_rn((float)(o1 - o0));       // mean = sum * (1/count)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = v[i] / cnt;
+          for (int i = 0; i < 16; ++i) v[i] *= inv;
         }
-        const Split8 sp = split8(v);
-        hi = sp.hi;
-        lo = sp.lo;
+        const Split8 s0 = split8(v), s1 = split8(v + 8);
+        hi0 = s0.hi; lo0 = s0.lo; hi1 = s1.hi; lo1 = s1.lo;
       }
       mbar_wait(&empty[slot], ph ^ 1);
-      uint8_t* sa = stages + (size_t)slot * L.stage_bytes + a_off;
-      *reinterpret_cast<uint4*>(sa) = hi;
-      *reinterpret_cast<uint4*>(sa + a_half) = lo;
+      uint8_t* sa = stages + (size_t)slot * L.stage_bytes + aoff;
+      *reinterpret_cast<uint4*>(sa) = hi0;
+      *reinterpret_cast<uint4*>(sa + 4 * TM * 16) = hi1;
+      *reinterpret_cast<uint4*>(sa + a_half) = lo0;
+      *reinterpret_cast<uint4*>(sa + a_half + 4 * TM * 16) = lo1;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[slot]);
     }
+    const long myrow = row_of(tid & (TM - 1));
 
     // ===================== epilogue: warp w -> TMEM lanes 32*(w%4).., columns 32*(w/4)..
     mbar_wait(tfull, 0);
@@ -236,10 +253,12 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
         const uint32_t sb = sa + 2 * a_half;
 #pragma unroll
         for (int j = 0; j < BK / 16; ++j) {
+          // A: chunk planes 2j, 2j+1 of the stage; B: packed block j/2 = { hi [4][H][16B], lo [4][H][16B] }
+          const uint32_t sbb = sb + (j >> 1) * (2 * b_blk) + (j & 1) * 2 * lbo_b;
           const uint64_t ahi = smem_desc(sa + j * 2 * lbo_a, lbo_a, 128);
           const uint64_t alo = smem_desc(sa + a_half + j * 2 * lbo_a, lbo_a, 128);
-          const uint64_t bhi = smem_desc(sb + j * 2 * lbo_b, lbo_b, 128);
-          const uint64_t blo = smem_desc(sb + b_half + j * 2 * lbo_b, lbo_b, 128);
+          const uint64_t bhi = smem_desc(sbb, lbo_b, 128);
+          const uint64_t blo = smem_desc(sbb + b_blk, lbo_b, 128);
           mma_bf16(tmem, ahi, bhi, idesc, accf);
           accf = 1;
           if (passes == 3) {
@@ -279,7 +298,7 @@ int npad_of(int N) {
 bool social_fc_tc_eligible(const SocialFcArgs& a) {
   const int G = a.n_rad * a.n_ang;
   if (gemm_mode() == 0 || !a.packed) return false;
-  if (a.H % 32 != 0 || a.H < 32 || a.H > 128 || a.ld_h % 4 != 0) return false;
+  if (a.H % 64 != 0 || a.H < 64 || a.H > 128 || a.ld_h % 4 != 0) return false;   // a 64-column stage never straddles bins
   if (a.N > 128 || a.N < 1 || G > MAXG || G < 1) return false;
   const Layout L = make_layout(a.H, npad_of(a.N), G, a.n_rad, a.n_ang);
   return L.total <= 227 * 1024;
