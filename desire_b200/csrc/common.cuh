@@ -216,6 +216,14 @@ size_t gru_tc_pack_bytes(int H);
 bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes);
 int gru_seq_tc(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
 
+// fused transposed conv + bias + per-row BN + activation on tcgen05 (deconv_tc.cu)
+size_t deconv_tc_pack_bytes(int Cin, int Cout, int ks);
+bool deconv_tc_eligible(int R, int Hin, int Hout, int Cin, int Cout, int ks, int stride, const void* pack_ws,
+                        size_t pack_bytes);
+int deconv_tc(const float* X, int R, int Hin, int Hout, int Cin, int Cout, int ks, int stride, int pad, const float* W,
+              const float* bias, const float* gamma, const float* beta, int act, float* Y, void* pack_ws,
+              cudaStream_t st);
+
 // col2im + bias + per-row BN + activation (cvae.cu): col [R*Hin*Hin, k*k*Cout] -> out [R,Hout,Hout,Cout]
 int colbn_act(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int Cout,
               const float* bias, const float* gamma, const float* beta, int act, float* out,

@@ -289,20 +289,28 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
       DESIRE_TRY(colbn_act(col, rc, 1, 4, 4, 1, 0, 128, w->d1.b, w->d1.gamma, w->d1.beta, DESIRE_ACT_ELU, a1, st));
     }
     // deconv5 VALID 4x4x128 -> 8x8x64
-    {
+    if (deconv_tc_eligible(rc, 4, 8, 128, 64, 5, 1, pw.p, pw.bytes)) {
       ProfScope ps_(DESIRE_PROF_DECONV2, st);
-      DESIRE_TRY(sgemm(a1, 128, w->d2.w, 128, true, nullptr, col, 1600, rc * 16, 1600, 128, DESIRE_ACT_NONE, false, st, pw));
-    }
-    {
+      DESIRE_TRY(deconv_tc(a1, rc, 4, 8, 128, 64, 5, 1, 0, w->d2.w, w->d2.b, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, a2,
+                           pw.p, st));
+    } else {
+      {
+        ProfScope ps_(DESIRE_PROF_DECONV2, st);
+        DESIRE_TRY(sgemm(a1, 128, w->d2.w, 128, true, nullptr, col, 1600, rc * 16, 1600, 128, DESIRE_ACT_NONE, false, st, pw));
+      }
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
       DESIRE_TRY(colbn_act(col, rc, 4, 8, 5, 1, 0, 64, w->d2.b, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, a2, st));
     }
     // deconv5/2 SAME 8x8x64 -> 16x16x32 (full 19x19, keep [1,17))
-    {
+    if (deconv_tc_eligible(rc, 8, 16, 64, 32, 5, 2, pw.p, pw.bytes)) {
       ProfScope ps_(DESIRE_PROF_DECONV3, st);
-      DESIRE_TRY(sgemm(a2, 64, w->d3.w, 64, true, nullptr, col, 800, rc * 64, 800, 64, DESIRE_ACT_NONE, false, st, pw));
-    }
-    {
+      DESIRE_TRY(deconv_tc(a2, rc, 8, 16, 64, 32, 5, 2, 1, w->d3.w, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3,
+                           pw.p, st));
+    } else {
+      {
+        ProfScope ps_(DESIRE_PROF_DECONV3, st);
+        DESIRE_TRY(sgemm(a2, 64, w->d3.w, 64, true, nullptr, col, 800, rc * 64, 800, 64, DESIRE_ACT_NONE, false, st, pw));
+      }
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
       DESIRE_TRY(colbn_act(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st));
     }

@@ -1,0 +1,353 @@
+// Fused transposed convolution for the CVAE decoder (model/model.py:465-468, deconv2d of
+// utils/convolutional_vae_util.py:31-135):   Y = act( BN_row( conv2d_transpose(X, W) + b ) )
+// in ONE kernel on tcgen05 — the scatter-form GEMM col = X[R*Pin, Cin] @ W^T[Cin, 25*Cout], the col2im
+// accumulation, the bias, the per-row batch-norm (batch-of-one statistics) and the activation.
+// The col matrix (4*25*Cout bytes per input position; 12 GB written + read per step at the bench workload)
+// never leaves the SM.
+//
+// One CTA = 128 GEMM rows = SPT = 128/Pin whole samples, so every output position of those samples is produced
+// inside the CTA.  Channels are processed in groups of 32 (out tile [SPT][Pout][32] FP32 = 64 KB of smem):
+//   warps 0-7  (a) convert the X tile once to BF16 hi/lo in the UMMA K-major layout (A stays resident);
+//              (b) epilogue: accumulators arrive per n-tile of 8 taps x 32 channels; tap by tap (named barrier
+//                  between taps => deterministic, race-free) each thread adds its 16 channels of its input
+//                  position into the output position (iy*s+ky-pad, ix*s+kx-pad) of the smem tile (XOR-rotated
+//                  channel quads => conflict-free);
+//              (c) two-pass BN statistics per (sample, channel) over the tile, normalise, activate, store.
+//   warp 8     tcgen05.mma issuer, M=128, N=256 (last n-tile: one tap, N=32), two TMEM accumulators so the MMAs
+//              of n-tile t+1 overlap the scatter of n-tile t.
+//   warp 9     streams the packed weights (one 32-wide K stage of one n-tile per 1-D bulk TMA copy).
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace desire {
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128, CG = 32, TPT = 8, NTHR = 320;
+constexpr int SLOT = 32 * 1024;   // 2 (hi,lo) x 4 chunks x 256 rows x 16 B
+
+struct DcArgs {
+  const float* X;
+  int R, Hin, Hout, Cin, Cout, ks, stride, pad;
+  const uint8_t* wpack;
+  const float *bias, *gamma, *beta;
+  int act;
+  float* Y;
+  int passes, nstg;
+};
+
+struct DcLayout {
+  size_t a_hi, a_lo, ring, out, red, stat, bars, total;
+};
+__host__ __device__ inline DcLayout dc_layout(int Cin, int nstg, int spt) {
+  DcLayout L;
+  size_t off = 0;
+  const size_t a_half = (size_t)(Cin / 8) * TM * 16;
+  L.a_hi = off; off += a_half;
+  L.a_lo = off; off += a_half;
+  L.ring = off; off += (size_t)nstg * SLOT;
+  L.out = off; off += 64 * 1024;
+  L.red = off; off += 256 * 4;
+  L.stat = off; off += (size_t)2 * spt * CG * 4;
+  L.bars = off; off += (2 * 4 + 4 + 1) * 8 + 16;
+  L.total = off;
+  return L;
+}
+
+// packed weights: for cg, nt, ks: { hi [4][BNt][8 bf16], lo [4][BNt][8 bf16] } with n = tap_local*32 + c
+__global__ void pack_deconv_kernel(const float* __restrict__ W, int Cin, int Cout, int ntaps, uint4* __restrict__ out) {
+  const int nks = Cin / 32, ncg = Cout / CG, nnt = (ntaps + TPT - 1) / TPT;
+  // chunk-granular work items: (cg, nt, ks, c, n)
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  // enumerate by walking the tiles (few of them)
+  long base_u4 = 0;
+  for (int cg = 0; cg < ncg; ++cg)
+    for (int nt = 0; nt < nnt; ++nt) {
+      const int taps = min(TPT, ntaps - nt * TPT), BNt = taps * CG;
+      const long items = (long)nks * 4 * BNt;
+      if (idx < items) {
+        const int n = (int)(idx % BNt);
+        long t = idx / BNt;
+        const int c = (int)(t % 4);
+        const int ks = (int)(t / 4);
+        const int tap = nt * TPT + n / CG, o = cg * CG + n % CG;
+        const float* src = W + ((size_t)tap * Cout + o) * Cin + ks * 32 + c * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(src + i);
+        const Split8 s = split8(v);
+        uint4* blk = out + base_u4 + (size_t)ks * (2 * 4 * BNt);
+        blk[c * BNt + n] = s.hi;
+        blk[4 * BNt + c * BNt + n] = s.lo;
+        return;
+      }
+      idx -= items;
+      base_u4 += (long)nks * 2 * 4 * BNt;
+    }
+}
+
+__device__ __forceinline__ int swz(int oy, int ox, int sh) { return ((ox >> sh) + 4 * ((oy >> sh) & 1)) & 7; }
+
+__global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int Pin = a.Hin * a.Hin, Pout = a.Hout * a.Hout, spt = TM / Pin;
+  const DcLayout L = dc_layout(a.Cin, a.nstg, spt);
+  uint8_t* A_hi = smem + L.a_hi;
+  uint8_t* A_lo = smem + L.a_lo;
+  uint8_t* ring = smem + L.ring;
+  float* outt = reinterpret_cast<float*>(smem + L.out);
+  float* red = reinterpret_cast<float*>(smem + L.red);
+  float* stat = reinterpret_cast<float*>(smem + L.stat);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* empty = full + 4;
+  uint64_t* acc_full = empty + 4;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* a_ready = acc_empty + 2;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(a_ready + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntaps = a.ks * a.ks, nnt = (ntaps + TPT - 1) / TPT, ncg = a.Cout / CG, nks = a.Cin / 32;
+  const long samp0 = (long)blockIdx.x * spt;
+  const int sh = a.stride - 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.nstg; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);
+    }
+    mbar_init(a_ready, 8);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc_dyn(tslot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  if (warp < 8) {
+    const int rl = tid & (TM - 1), half = tid >> 7;           // GEMM row (TMEM lane), column half
+    const int s_loc = rl / Pin, p = rl % Pin;
+    const long samp = samp0 + s_loc;
+    const bool ok = samp < a.R;
+    // ---- (a) X tile -> BF16 hi/lo A operand; this thread converts half of the K chunks of its row
+    {
+      const float* xr = a.X + ((size_t)samp * Pin + p) * a.Cin;
+      const int nch = a.Cin / 8;
+      for (int c = half * (nch / 2); c < (half + 1) * (nch / 2); ++c) {
+        float v[8];
+        if (ok) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(xr + c * 8));
+          const float4 y = __ldg(reinterpret_cast<const float4*>(xr + c * 8) + 1);
+          v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        const Split8 sp = split8(v);
+        *reinterpret_cast<uint4*>(A_hi + (size_t)c * TM * 16 + rl * 16) = sp.hi;
+        *reinterpret_cast<uint4*>(A_lo + (size_t)c * TM * 16 + rl * 16) = sp.lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    const int iy = p / a.Hin, ix = p % a.Hin;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* osamp = outt + (size_t)s_loc * Pout * CG;
+    const int ntile_el = spt * Pout * CG;                      // 16384 floats = 64 KB
+    uint32_t use = 0;
+    for (int cg = 0; cg < ncg; ++cg) {
+      // zero the output tile of this channel group
+      for (int e = tid; e < ntile_el / 4; e += 256) reinterpret_cast<float4*>(outt)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // ---- (b) scatter the accumulators, n-tile by n-tile, tap by tap
+      for (int nt = 0; nt < nnt; ++nt, ++use) {
+        const int ab = use & 1;
+        const int taps = min(TPT, ntaps - nt * TPT);
+        mbar_wait(&acc_full[ab], (use >> 1) & 1);
+        tc_fence_after();
+        for (int tl = 0; tl < taps; ++tl) {
+          const int t = nt * TPT + tl;
+          const int ky = t / a.ks, kx = t - ky * a.ks;
+          const int oy = iy * a.stride + ky - a.pad, ox = ix * a.stride + kx - a.pad;
+          float v[16];
+          tmem_ld16(trow + ab * 256 + tl * CG + half * 16, v);
+          tmem_ld_wait();
+          if (oy >= 0 && oy < a.Hout && ox >= 0 && ox < a.Hout) {
+            float* o = osamp + (size_t)(oy * a.Hout + ox) * CG;
+            const int rot = swz(oy, ox, sh);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4* dst = reinterpret_cast<float4*>(o) + ((half * 4 + q + rot) & 7);
+              float4 cur = *dst;
+              cur.x += v[4 * q]; cur.y += v[4 * q + 1]; cur.z += v[4 * q + 2]; cur.w += v[4 * q + 3];
+              *dst = cur;
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");     // taps in lockstep: no two taps touch a cell at once
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      }
+      // ---- (c) bias + per-(sample, channel) BN over the Pout positions + activation + store
+      const int npair = spt * CG, parts = 256 / npair;         // npair in {64, 256}
+      const int pair = tid % npair, part = tid / npair;
+      const int ps = pair / CG, pc = pair % CG;
+      const float b = __ldg(a.bias + cg * CG + pc);
+      const float* tsamp = outt + (size_t)ps * Pout * CG;
+      float sum = 0.f;
+      for (int q = part; q < Pout; q += parts) {
+        const int oy = q / a.Hout, ox = q - oy * a.Hout;
+        sum += tsamp[q * CG + (((pc >> 2) + swz(oy, ox, sh)) & 7) * 4 + (pc & 3)] + b;
+      }
+      red[tid] = sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < npair) {
+        float t = 0.f;
+        for (int q = 0; q < parts; ++q) t += red[q * npair + tid];
+        stat[tid] = t / (float)Pout;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mean = stat[pair];
+      sum = 0.f;
+      for (int q = part; q < Pout; q += parts) {
+        const int oy = q / a.Hout, ox = q - oy * a.Hout;
+        const float d = tsamp[q * CG + (((pc >> 2) + swz(oy, ox, sh)) & 7) * 4 + (pc & 3)] + b - mean;
+        sum += d * d;
+      }
+      red[tid] = sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < npair) {
+        float t = 0.f;
+        for (int q = 0; q < parts; ++q) t += red[q * npair + tid];
+        stat[npair + tid] = 1.f / sqrtf(t / (float)Pout + 1e-3f);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int e = tid; e < ntile_el; e += 256) {
+        const int c = e % CG, q = (e / CG) % Pout, s2 = e / (CG * Pout);
+        const long smp = samp0 + s2;
+        if (smp >= a.R) continue;
+        const int oy = q / a.Hout, ox = q - oy * a.Hout;
+        const float x = outt[((size_t)s2 * Pout + q) * CG + (((c >> 2) + swz(oy, ox, sh)) & 7) * 4 + (c & 3)] +
+                        __ldg(a.bias + cg * CG + c);
+        const int pr = s2 * CG + c;
+        const float y = __ldg(a.gamma + cg * CG + c) * ((x - stat[pr]) * stat[npair + pr]) + __ldg(a.beta + cg * CG + c);
+        a.Y[((size_t)smp * Pout + q) * a.Cout + cg * CG + c] = act_apply(y, a.act);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
+      mbar_wait(a_ready, 0);
+      tc_fence_after();
+      uint32_t it = 0, use = 0;
+      for (int cg = 0; cg < ncg; ++cg) {
+        for (int nt = 0; nt < nnt; ++nt, ++use) {
+          const int ab = use & 1;
+          const int BNt = min(TPT, ntaps - nt * TPT) * CG;
+          const uint32_t idesc = idesc_bf16(TM, BNt);
+          const uint32_t lbo_b = BNt * 16, b_half = 4 * BNt * 16;
+          mbar_wait(&acc_empty[ab], ((use >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int ks = 0; ks < nks; ++ks, ++it) {
+            const int slot = it % a.nstg;
+            mbar_wait(&full[slot], (it / a.nstg) & 1);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(ring + (size_t)slot * SLOT);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t ao = (ks * 4 + j * 2) * 2048;
+              const uint64_t ahi = smem_desc(a_hi + ao, 2048, 128), alo = smem_desc(a_lo + ao, 2048, 128);
+              const uint64_t bhi = smem_desc(sb + j * 2 * lbo_b, lbo_b, 128);
+              const uint64_t blo = smem_desc(sb + b_half + j * 2 * lbo_b, lbo_b, 128);
+              const uint32_t d = tmem + ab * 256;
+              const uint32_t accf = (ks > 0 || j > 0) ? 1u : 0u;
+              mma_bf16(d, ahi, bhi, idesc, accf);
+              if (a.passes == 3) {
+                mma_bf16(d, alo, bhi, idesc, 1);
+                mma_bf16(d, ahi, blo, idesc, 1);
+              }
+            }
+            mma_commit(&empty[slot]);
+          }
+          mma_commit(&acc_full[ab]);
+        }
+      }
+    }
+  } else {
+    // ===================== weight streamer
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint8_t* src = a.wpack;
+      for (int cg = 0; cg < ncg; ++cg) {
+        for (int nt = 0; nt < nnt; ++nt) {
+          const int BNt = min(TPT, ntaps - nt * TPT) * CG;
+          const uint32_t bytes = 2 * 4 * BNt * 16;
+          for (int ks = 0; ks < nks; ++ks, ++it) {
+            const int slot = it % a.nstg;
+            mbar_wait(&empty[slot], ((it / a.nstg) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[slot], bytes);
+            bulk_g2s(ring + (size_t)slot * SLOT, src, bytes, &full[slot]);
+            src += bytes;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+size_t deconv_tc_pack_bytes(int Cin, int Cout, int ks) { return align_up((size_t)ks * ks * Cout * Cin * 4); }
+
+bool deconv_tc_eligible(int R, int Hin, int Hout, int Cin, int Cout, int ks, int stride, const void* pack_ws,
+                        size_t pack_bytes) {
+  const int Pin = Hin * Hin, Pout = Hout * Hout;
+  if (gemm_mode() == 0 || R < 1) return false;
+  if (Pin < 1 || Pin > TM || TM % Pin != 0) return false;
+  if (Cin % 32 != 0 || Cin > 128 || Cout % CG != 0) return false;
+  if ((size_t)(TM / Pin) * Pout * CG * 4 != 64 * 1024) return false;        // out tile exactly 64 KB
+  if (256 % ((TM / Pin) * CG) != 0 && ((TM / Pin) * CG) % 256 != 0) return false;
+  if ((TM / Pin) * CG > 256) return false;
+  if (stride < 1 || stride > 2 || ks * ks > 32) return false;
+  return pack_ws && pack_bytes >= deconv_tc_pack_bytes(Cin, Cout, ks);
+}
+
+int deconv_tc(const float* X, int R, int Hin, int Hout, int Cin, int Cout, int ks, int stride, int pad, const float* W,
+              const float* bias, const float* gamma, const float* beta, int act, float* Y, void* pack_ws,
+              cudaStream_t st) {
+  const int nks = Cin / 32, ncg = Cout / CG, ntaps = ks * ks;
+  long items = 0;
+  for (int nt = 0; nt * TPT < ntaps; ++nt) items += (long)nks * 4 * std::min(TPT, ntaps - nt * TPT) * CG;
+  items *= ncg;
+  // the pack kernel walks the (cg, nt) tiles per thread; give every tile's items a thread
+  pack_deconv_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(W, Cin, Cout, ntaps, (uint4*)pack_ws);
+  DESIRE_LAUNCH_CHECK();
+  DcArgs a{};
+  a.X = X; a.R = R; a.Hin = Hin; a.Hout = Hout; a.Cin = Cin; a.Cout = Cout; a.ks = ks; a.stride = stride; a.pad = pad;
+  a.wpack = (const uint8_t*)pack_ws; a.bias = bias; a.gamma = gamma; a.beta = beta; a.act = act; a.Y = Y;
+  a.passes = gemm_mode() == 1 ? 1 : 3;
+  const int spt = TM / (Hin * Hin);
+  a.nstg = Cin > 64 ? 2 : 3;
+  const DcLayout L = dc_layout(Cin, a.nstg, spt);
+  DESIRE_CHECK_ARG(L.total <= 227 * 1024, "deconv_tc: shared memory layout too large");
+  DESIRE_ENSURE_SMEM(deconv_tc_kernel, L.total);
+  const unsigned grid = (unsigned)((R + spt - 1) / spt);
+  DESIRE_LAUNCH(st, (deconv_tc_kernel<<<grid, NTHR, L.total, st>>>(a)));
+  return DESIRE_OK;
+}
+
+}  // namespace desire

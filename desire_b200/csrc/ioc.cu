@@ -1,6 +1,8 @@
 // Stage 2 — IOC ranking & refinement (absent in the reference, marker
 // model/model.py:312-313): scene CNN, bilinear scene-feature gather, log-polar social pooling,
 // Decoder-2 GRU with per-step scoring, regression refinement.
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace desire;
@@ -282,18 +284,23 @@ extern "C" int desire_scene_cnn_fwd(const float* img, int B, int Hi, int Wi, int
   PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
   // TF SAME: total pad = max((out-1)*s + k - in, 0), before = total/2
   const int pt1 = max((Ho - 1) * 2 + 5 - Hi, 0) / 2, pl1 = max((Wo - 1) * 2 + 5 - Wi, 0) / 2;
-  // one image at a time keeps gridDim.y legal for any map size
-  for (int b = 0; b < B; ++b) {
-    const size_t px = (size_t)Ho * Wo;
+  // all images of a chunk in one launch (a single 128x128 map is only 128 tiles — less than one wave);
+  // chunks keep gridDim.y <= 65535 for any map size
+  const size_t px = (size_t)Ho * Wo;
+  const int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (size_t)65535 * 128 / px));
+  for (int b = 0; b < B; b += per) {
+    const int nb = std::min(per, B - b);
+    const int M = (int)(nb * px);
+    ProfScope ps_(DESIRE_PROF_SCENE_CNN, st);
     Im2col g1{Hi, Wi, 3, Ho, Wo, 5, 5, 2, pt1, pl1};
-    DESIRE_TRY(sgemm_im2col(img + (size_t)b * Hi * Wi * 3, g1, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, (int)px, 16,
-                            75, DESIRE_ACT_RELU, st, pw));
+    DESIRE_TRY(sgemm_im2col(img + (size_t)b * Hi * Wi * 3, g1, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, M, 16, 75,
+                            DESIRE_ACT_RELU, st, pw));
     Im2col g2{Ho, Wo, 16, Ho, Wo, 5, 5, 1, 2, 2};
-    DESIRE_TRY(sgemm_im2col(f1 + b * px * 16, g2, w->c2_w, 32, w->c2_b, f2 + b * px * 32, 32, (int)px, 32, 400,
-                            DESIRE_ACT_RELU, st, pw));
+    DESIRE_TRY(sgemm_im2col(f1 + b * px * 16, g2, w->c2_w, 32, w->c2_b, f2 + b * px * 32, 32, M, 32, 400, DESIRE_ACT_RELU,
+                            st, pw));
     Im2col g3{Ho, Wo, 32, Ho, Wo, 5, 5, 1, 2, 2};
-    DESIRE_TRY(sgemm_im2col(f2 + b * px * 32, g3, w->c3_w, Cs, w->c3_b, fmap + b * px * Cs, Cs, (int)px, Cs, 800,
-                            DESIRE_ACT_RELU, st, pw));
+    DESIRE_TRY(sgemm_im2col(f2 + b * px * 32, g3, w->c3_w, Cs, w->c3_b, fmap + b * px * Cs, Cs, M, Cs, 800, DESIRE_ACT_RELU,
+                            st, pw));
   }
   return DESIRE_OK;
 }
