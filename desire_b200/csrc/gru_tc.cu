@@ -1,20 +1,24 @@
 // Persistent tcgen05 GRU recurrence (TF-1.x GRUCell semantics) — the dense contraction of the path.
 //
-//   gates = sigmoid(xp_ru + h @ Wg_h)      [128 x 2H]  accumulated in TMEM columns [0,2H)
+//   gates = sigmoid(xp_ru + h @ Wg_h)      [128 x 2H]  TMEM columns [0,2H) of the tile
 //   cand  = tanh   (xp_c  + (r*h) @ Wc_h)  [128 x  H]  accumulated OVER the consumed r columns [0,H)
-//   h'    = u*h + (1-u)*cand                           u is read from TMEM columns [H,2H) only now
+//   h'    = u*h + (1-u)*cand                           u is read from columns [H,2H) only now
 //
-// One CTA owns a 128-row tile (rows are independent) for all T steps.  Warp roles:
-//   warps 0-7  epilogue: warp w serves TMEM lanes 32*(w%4).. and column half w/4.  After the gates MMA they
-//              turn r into the next A operand r*h (BF16 hi/lo, UMMA K-major layout, in place of h), after
-//              the candidate MMA they finish the state update, store h_t (FP32) to HBM and write h_t back
-//              as the A operand of the next step.  FP32 state never lives in BF16: h_{t-1} is re-read
-//              from the FP32 output of the previous step (L2-resident, written by the same thread).
-//   warp 8     MMA issuer: tcgen05.mma M=128, N<=256, K=16, 3 MMAs per K step in 3xBF16 mode.
-//   warp 9     weight streamer: the recurrent weights are pre-packed into shared-memory images and
-//              streamed every step through a 3-stage ring with 1-D bulk TMA copies (they do not fit
-//              next to the state tile in 3xBF16 form: 12*H^2 bytes).
-// mbarriers: ring full/empty, gates-done, cand-done (tcgen05.commit), rh-ready, h-ready (epilogue).
+// Design (v2, after the ncu capture of v1 showed 12 % tensor-pipe: serial phases, epilogues stalled on
+// dependent global loads):
+//   * one CTA owns NT (=2 for H<=128) independent 128-row tiles for all T steps and ONE MMA warp serves both:
+//     gates(0) gates(1) cand(0) cand(1) ...  While a tile's epilogue warps work, the tensor core runs the
+//     other tile's MMAs (ping-pong inside the CTA; TMEM = NT * 2H columns).
+//   * the hoisted input projection xp is never added in an epilogue: it is PRE-LOADED into the TMEM accumulator
+//     with tcgen05.st (xp_r|xp_u by the previous step's epilogue right after it consumed those columns, xp_c by
+//     the gate epilogue right after it consumed r) and every MMA accumulates on top of it.  The epilogues'
+//     global loads are therefore independent prefetches issued at the top of each 16-column chunk.
+//   * epilogue warps: 4 lane quadrants x (H/HC) column splits per tile, HC = 64 columns per thread.  E1 turns r
+//     into the next A operand r*h (BF16 hi/lo, UMMA K-major layout, in place of h); E2 finishes the state
+//     update, stores h_t (FP32) and writes h_t back as the A operand.  FP32 state never lives in BF16: h_{t-1}
+//     is re-read from the FP32 output of the previous step (written by the same thread, L1/L2 resident).
+//   * recurrent weights: pre-packed shared-memory images streamed through a 3-stage ring with 1-D bulk TMA
+//     copies (12*H^2 bytes per tile-step in 3xBF16 form — they do not fit next to the state tiles).
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -25,7 +29,7 @@ using namespace tc;
 
 constexpr int NS = 3;                 // weight ring stages
 constexpr int SLOT_BYTES = 32 * 1024; // 2 (hi,lo) x 4 chunks x 256 rows x 16 B
-constexpr int NTHR = 320;
+constexpr int MAXNT = 2;
 
 struct GruTcArgs {
   int R, H, T;
@@ -41,32 +45,55 @@ struct GruTcArgs {
   const uint8_t* wc;   // packed [H/32] blocks of 128*H bytes
   int BNg, ntg;
   int passes;
+  int NT, HC, EW;      // tiles per CTA, columns per epilogue thread, epilogue warps per tile
   uint32_t tmem_cols;
 };
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) {
-  // 1 - 2/(1+e^{2x}); saturates correctly for |x| large (e^{2x} -> inf or 0)
-  return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ld16(const float* p, float* v) {   // plain loads (state written by this kernel)
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(p + i);
+    v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+  }
+}
+__device__ __forceinline__ void ld16g(const float* p, float* v) {  // read-only data (xp)
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p + i));
+    v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+  }
+}
+__device__ __forceinline__ void zero16(float* v) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
 }
 
-__global__ void __launch_bounds__(NTHR, 1) gru_tc_kernel(GruTcArgs a) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) gru_tc_kernel(GruTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int H = a.H;
-  const int a_half = (H / 8) * 2048;                 // [H/8 chunks][128 rows][16 B]
-  uint8_t* A_hi = smem;
-  uint8_t* A_lo = smem + a_half;
-  uint8_t* ring = smem + 2 * a_half;
+  const int H = a.H, NT = a.NT;
+  const int a_half = (H / 8) * 2048;                 // [H/8 chunks][128 rows][16 B] per tile
+  uint8_t* ring = smem + (size_t)NT * 2 * a_half;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + NS * SLOT_BYTES);
   uint64_t* empty = full + NS;
-  uint64_t* g_done = empty + NS;
-  uint64_t* c_done = g_done + 1;
-  uint64_t* rh_ready = c_done + 1;
-  uint64_t* h_ready = rh_ready + 1;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(h_ready + 1);
+  uint64_t* g_done = empty + NS;        // [MAXNT]
+  uint64_t* c_done = g_done + MAXNT;
+  uint64_t* rh_ready = c_done + MAXNT;
+  uint64_t* h_ready = rh_ready + MAXNT;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(h_ready + MAXNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long row_blk = (long)blockIdx.x * 128;
+  const int n_epi = NT * a.EW;                       // epilogue warps; then MMA warp, loader warp
   const int nks = H / 32;
 
   if (tid == 0) {
@@ -74,143 +101,171 @@ __global__ void __launch_bounds__(NTHR, 1) gru_tc_kernel(GruTcArgs a) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(g_done, 1);
-    mbar_init(c_done, 1);
-    mbar_init(rh_ready, 8);
-    mbar_init(h_ready, 8);
+    for (int ti = 0; ti < MAXNT; ++ti) {
+      mbar_init(&g_done[ti], 1);
+      mbar_init(&c_done[ti], 1);
+      mbar_init(&rh_ready[ti], a.EW);
+      mbar_init(&h_ready[ti], a.EW);
+    }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc_dyn(tslot, a.tmem_cols);
+  if (warp == n_epi) tmem_alloc_dyn(tslot, a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
 
-  if (warp < 8) {
+  if (warp < n_epi) {
     // ======================================================================== epilogue warps
-    const int q = warp & 3, hf = warp >> 2;
+    const int ti = warp / a.EW, w8 = warp % a.EW;
+    const int q = w8 & 3, cs = w8 >> 2;             // TMEM lane quadrant (== warp % 4), column split
     const int rloc = q * 32 + lane;                 // TMEM lane == row in tile
-    const long row = row_blk + rloc;
-    const bool ok = row < a.R;
-    const int HC = H / 2, cbeg = hf * HC;           // this thread's columns [cbeg, cbeg+HC)
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    uint8_t* my_hi = A_hi + rloc * 16;
-    uint8_t* my_lo = A_lo + rloc * 16;
+    const long row_true = ((long)blockIdx.x * NT + ti) * 128 + rloc;
+    const bool ok = row_true < a.R;
+    const long row = ok ? row_true : (long)a.R - 1;   // rows past the end recompute the last row (loads stay
+                                                      // branch-free and in bounds); they never store
+    const int HC = a.HC, cbeg = cs * HC;            // this thread's columns [cbeg, cbeg+HC)
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + ti * 2 * H;
+    uint8_t* my_hi = smem + (size_t)ti * 2 * a_half + rloc * 16;
+    uint8_t* my_lo = my_hi + a_half;
+    const float* xp0 = a.xp + row * a.xp_row_stride;
+    const float* h0r = a.h0 ? a.h0 + (row / a.h0_div) * (long)a.ld_h0 : nullptr;
 
-    // ---- initial state -> A operand
-    {
-      const float* h0r = (a.h0 && ok) ? a.h0 + (row / a.h0_div) * (long)a.ld_h0 : nullptr;
-      for (int c = cbeg; c < cbeg + HC; c += 8) {
-        float v[8];
-        if (h0r) {
-          float4 x = *reinterpret_cast<const float4*>(h0r + c);   // plain loads: h0 may alias h_final
-          float4 y = *(reinterpret_cast<const float4*>(h0r + c) + 1);
-          v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        }
-        Split8 s = split8(v);
-        *reinterpret_cast<uint4*>(my_hi + (c / 8) * 2048) = s.hi;
-        *reinterpret_cast<uint4*>(my_lo + (c / 8) * 2048) = s.lo;
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(h_ready);
+    // ---- initial state -> A operand, xp_r|xp_u of step 0 -> TMEM accumulator
+    for (int c = cbeg; c < cbeg + HC; c += 16) {
+      float hv[16], xr[16], xu[16];
+      if (h0r) ld16(h0r + c, hv);
+      else zero16(hv);
+      ld16g(xp0 + c, xr);
+      ld16g(xp0 + H + c, xu);
+      const Split8 s0 = split8(hv), s1 = split8(hv + 8);
+      *reinterpret_cast<uint4*>(my_hi + (c / 8) * 2048) = s0.hi;
+      *reinterpret_cast<uint4*>(my_lo + (c / 8) * 2048) = s0.lo;
+      *reinterpret_cast<uint4*>(my_hi + (c / 8 + 1) * 2048) = s1.hi;
+      *reinterpret_cast<uint4*>(my_lo + (c / 8 + 1) * 2048) = s1.lo;
+      tmem_st16(trow + c, xr);
+      tmem_st16(trow + H + c, xu);
     }
+    tmem_st_wait();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&h_ready[ti]);
 
     for (int t = 0; t < a.T; ++t) {
       const uint32_t par = t & 1;
-      const float* xpr = ok ? a.xp + row * a.xp_row_stride + (long)t * a.xp_step_stride : nullptr;
-      const float* hprev = nullptr;
-      if (ok) {
-        if (t == 0) hprev = a.h0 ? a.h0 + (row / a.h0_div) * (long)a.ld_h0 : nullptr;
-        else hprev = a.hs + row * a.hs_row_stride + (long)(t - 1) * a.hs_step_stride;
-      }
-      // ---------------- E1: r = sigmoid(.), stage r*h as the candidate's A operand
-      mbar_wait(g_done, par);
+      const float* xpt = xp0 + (long)t * a.xp_step_stride;
+      const float* xpn = xp0 + (long)(t + 1 < a.T ? t + 1 : t) * a.xp_step_stride;
+      const float* hprev = (t == 0) ? h0r : a.hs + row * a.hs_row_stride + (long)(t - 1) * a.hs_step_stride;
+      // ---------------- E1: r = sigmoid(.), stage r*h as the candidate's A operand, pre-load xp_c
+      mbar_wait(&g_done[ti], par);
       tc_fence_after();
       for (int c = cbeg; c < cbeg + HC; c += 16) {
-        float acc[16];
+        float hv[16], xc[16], acc[16];
+        if (hprev) ld16(hprev + c, hv);
+        else zero16(hv);
+        ld16g(xpt + 2 * H + c, xc);
         tmem_ld16(trow + c, acc);
         tmem_ld_wait();
-        float xv[16], hv[16];
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float4 x = xpr ? __ldg(reinterpret_cast<const float4*>(xpr + c + i)) : make_float4(0, 0, 0, 0);
-          float4 h = hprev ? *reinterpret_cast<const float4*>(hprev + c + i) : make_float4(0, 0, 0, 0);
-          xv[i] = x.x; xv[i + 1] = x.y; xv[i + 2] = x.z; xv[i + 3] = x.w;
-          hv[i] = h.x; hv[i + 1] = h.y; hv[i + 2] = h.z; hv[i + 3] = h.w;
-        }
-        float rh[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) rh[i] = fast_sigmoid(acc[i] + xv[i]) * hv[i];
-        Split8 s0 = split8(rh), s1 = split8(rh + 8);
+        for (int i = 0; i < 16; ++i) acc[i] = sigmoid_a(acc[i]) * hv[i];
+        const Split8 s0 = split8(acc), s1 = split8(acc + 8);
         *reinterpret_cast<uint4*>(my_hi + (c / 8) * 2048) = s0.hi;
         *reinterpret_cast<uint4*>(my_lo + (c / 8) * 2048) = s0.lo;
         *reinterpret_cast<uint4*>(my_hi + (c / 8 + 1) * 2048) = s1.hi;
         *reinterpret_cast<uint4*>(my_lo + (c / 8 + 1) * 2048) = s1.lo;
+        tmem_st16(trow + c, xc);                     // the candidate MMA accumulates on top of xp_c
       }
+      tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(rh_ready);
+      if (lane == 0) mbar_arrive(&rh_ready[ti]);
 
-      // ---------------- E2: u, candidate, state update
-      mbar_wait(c_done, par);
+      // ---------------- E2: u, candidate, state update; pre-load xp_r|xp_u of the next step
+      mbar_wait(&c_done[ti], par);
       tc_fence_after();
-      float* hout = ok ? a.hs ? a.hs + row * a.hs_row_stride + (long)t * a.hs_step_stride : nullptr : nullptr;
+      float* hout = (ok && a.hs) ? a.hs + row * a.hs_row_stride + (long)t * a.hs_step_stride : nullptr;
       float* hfin = (ok && a.h_final && t == a.T - 1) ? a.h_final + row * (long)a.ld_hf : nullptr;
       for (int c = cbeg; c < cbeg + HC; c += 16) {
-        float accc[16], accu[16];
+        float hv[16], xr[16], xu[16], accc[16], accu[16];
+        if (hprev) ld16(hprev + c, hv);
+        else zero16(hv);
+        ld16g(xpn + c, xr);
+        ld16g(xpn + H + c, xu);
         tmem_ld16(trow + c, accc);
         tmem_ld16(trow + H + c, accu);
         tmem_ld_wait();
-        float hn[16];
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float4 xu = xpr ? __ldg(reinterpret_cast<const float4*>(xpr + H + c + i)) : make_float4(0, 0, 0, 0);
-          float4 xc = xpr ? __ldg(reinterpret_cast<const float4*>(xpr + 2 * H + c + i)) : make_float4(0, 0, 0, 0);
-          float4 h = hprev ? *reinterpret_cast<const float4*>(hprev + c + i) : make_float4(0, 0, 0, 0);
-          const float xu_[4] = {xu.x, xu.y, xu.z, xu.w}, xc_[4] = {xc.x, xc.y, xc.z, xc.w}, h_[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float u = fast_sigmoid(accu[i + e] + xu_[e]);
-            const float cd = fast_tanh(accc[i + e] + xc_[e]);
-            hn[i + e] = u * h_[e] + (1.f - u) * cd;
-          }
+        for (int i = 0; i < 16; ++i) {
+          const float u = sigmoid_a(accu[i]);
+          const float cd = tanh_a(accc[i]);
+          accc[i] = fmaf(u, hv[i] - cd, cd);          // u*h + (1-u)*cd
         }
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 o = make_float4(hn[i], hn[i + 1], hn[i + 2], hn[i + 3]);
+          const float4 o = make_float4(accc[i], accc[i + 1], accc[i + 2], accc[i + 3]);
           if (hout) *reinterpret_cast<float4*>(hout + c + i) = o;
           if (hfin) *reinterpret_cast<float4*>(hfin + c + i) = o;
         }
-        Split8 s0 = split8(hn), s1 = split8(hn + 8);
+        const Split8 s0 = split8(accc), s1 = split8(accc + 8);
         *reinterpret_cast<uint4*>(my_hi + (c / 8) * 2048) = s0.hi;
         *reinterpret_cast<uint4*>(my_lo + (c / 8) * 2048) = s0.lo;
         *reinterpret_cast<uint4*>(my_hi + (c / 8 + 1) * 2048) = s1.hi;
         *reinterpret_cast<uint4*>(my_lo + (c / 8 + 1) * 2048) = s1.lo;
+        if (t + 1 < a.T) {
+          tmem_st16(trow + c, xr);
+          tmem_st16(trow + H + c, xu);
+        }
       }
+      tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(h_ready);
+      if (lane == 0) mbar_arrive(&h_ready[ti]);
     }
-  } else if (warp == 8) {
-    // ======================================================================== MMA issuer
+  } else if (warp == n_epi) {
+    // ======================================================================== MMA issuer (serves all tiles)
     if (lane == 0) {
       const uint32_t idesc_g = idesc_bf16(128, a.BNg), idesc_c = idesc_bf16(128, H);
-      const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
       const uint32_t lbo_g = a.BNg * 16, lbo_c = H * 16;
       const uint32_t g_half = 4 * a.BNg * 16, c_half = 4 * H * 16;
       uint32_t it = 0;
       for (int t = 0; t < a.T; ++t) {
         const uint32_t par = t & 1;
-        mbar_wait(h_ready, par);
-        tc_fence_after();
-        for (int ks = 0; ks < nks; ++ks) {
-          for (int jn = 0; jn < a.ntg; ++jn, ++it) {
+        for (int ti = 0; ti < NT; ++ti) {           // gates of every tile
+          const uint32_t a_hi = smem_u32(smem + (size_t)ti * 2 * a_half), a_lo = a_hi + a_half;
+          mbar_wait(&h_ready[ti], par);
+          tc_fence_after();
+          for (int ks = 0; ks < nks; ++ks) {
+            for (int jn = 0; jn < a.ntg; ++jn, ++it) {
+              const int slot = it % NS;
+              mbar_wait(&full[slot], (it / NS) & 1);
+              tc_fence_after();
+              const uint32_t sb = smem_u32(ring + slot * SLOT_BYTES);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t ao = (ks * 4 + j * 2) * 2048;
+                const uint64_t ahi = smem_desc(a_hi + ao, 2048, 128), alo = smem_desc(a_lo + ao, 2048, 128);
+                const uint64_t bhi = smem_desc(sb + j * 2 * lbo_g, lbo_g, 128);
+                const uint64_t blo = smem_desc(sb + g_half + j * 2 * lbo_g, lbo_g, 128);
+                const uint32_t d = tmem + ti * 2 * H + jn * a.BNg;
+                mma_bf16(d, ahi, bhi, idesc_g, 1);   // accumulates on the pre-loaded xp_r|xp_u
+                if (a.passes == 3) {
+                  mma_bf16(d, alo, bhi, idesc_g, 1);
+                  mma_bf16(d, ahi, blo, idesc_g, 1);
+                }
+              }
+              mma_commit(&empty[slot]);
+            }
+          }
+          mma_commit(&g_done[ti]);
+        }
+        for (int ti = 0; ti < NT; ++ti) {           // candidates of every tile
+          const uint32_t a_hi = smem_u32(smem + (size_t)ti * 2 * a_half), a_lo = a_hi + a_half;
+          mbar_wait(&rh_ready[ti], par);
+          tc_fence_after();
+          for (int ks = 0; ks < nks; ++ks, ++it) {
             const int slot = it % NS;
             mbar_wait(&full[slot], (it / NS) & 1);
             tc_fence_after();
@@ -219,71 +274,68 @@ __global__ void __launch_bounds__(NTHR, 1) gru_tc_kernel(GruTcArgs a) {
             for (int j = 0; j < 2; ++j) {
               const uint32_t ao = (ks * 4 + j * 2) * 2048;
               const uint64_t ahi = smem_desc(a_hi + ao, 2048, 128), alo = smem_desc(a_lo + ao, 2048, 128);
-              const uint64_t bhi = smem_desc(sb + j * 2 * lbo_g, lbo_g, 128);
-              const uint64_t blo = smem_desc(sb + g_half + j * 2 * lbo_g, lbo_g, 128);
-              const uint32_t d = tmem + jn * a.BNg;
-              const uint32_t accf = (ks > 0 || j > 0) ? 1u : 0u;
-              mma_bf16(d, ahi, bhi, idesc_g, accf);
+              const uint64_t bhi = smem_desc(sb + j * 2 * lbo_c, lbo_c, 128);
+              const uint64_t blo = smem_desc(sb + c_half + j * 2 * lbo_c, lbo_c, 128);
+              const uint32_t d = tmem + ti * 2 * H;
+              mma_bf16(d, ahi, bhi, idesc_c, 1);     // accumulates on the pre-loaded xp_c
               if (a.passes == 3) {
-                mma_bf16(d, alo, bhi, idesc_g, 1);
-                mma_bf16(d, ahi, blo, idesc_g, 1);
+                mma_bf16(d, alo, bhi, idesc_c, 1);
+                mma_bf16(d, ahi, blo, idesc_c, 1);
               }
             }
             mma_commit(&empty[slot]);
           }
+          mma_commit(&c_done[ti]);
         }
-        mma_commit(g_done);
-        mbar_wait(rh_ready, par);
-        tc_fence_after();
-        for (int ks = 0; ks < nks; ++ks, ++it) {
-          const int slot = it % NS;
-          mbar_wait(&full[slot], (it / NS) & 1);
-          tc_fence_after();
-          const uint32_t sb = smem_u32(ring + slot * SLOT_BYTES);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t ao = (ks * 4 + j * 2) * 2048;
-            const uint64_t ahi = smem_desc(a_hi + ao, 2048, 128), alo = smem_desc(a_lo + ao, 2048, 128);
-            const uint64_t bhi = smem_desc(sb + j * 2 * lbo_c, lbo_c, 128);
-            const uint64_t blo = smem_desc(sb + c_half + j * 2 * lbo_c, lbo_c, 128);
-            const uint32_t accf = (ks > 0 || j > 0) ? 1u : 0u;
-            mma_bf16(tmem, ahi, bhi, idesc_c, accf);
-            if (a.passes == 3) {
-              mma_bf16(tmem, alo, bhi, idesc_c, 1);
-              mma_bf16(tmem, ahi, blo, idesc_c, 1);
-            }
-          }
-          mma_commit(&empty[slot]);
-        }
-        mma_commit(c_done);
       }
     }
-  } else {
+  } else if (warp == n_epi + 1) {
     // ======================================================================== weight streamer
     if (lane == 0) {
       const uint32_t g_bytes = 2 * 4 * a.BNg * 16, c_bytes = 2 * 4 * H * 16;
       uint32_t it = 0;
       for (int t = 0; t < a.T; ++t) {
-        for (int ks = 0; ks < nks; ++ks) {
-          for (int jn = 0; jn < a.ntg; ++jn, ++it) {
+        for (int ti = 0; ti < NT; ++ti)
+          for (int ks = 0; ks < nks; ++ks)
+            for (int jn = 0; jn < a.ntg; ++jn, ++it) {
+              const int slot = it % NS;
+              mbar_wait(&empty[slot], ((it / NS) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full[slot], g_bytes);
+              bulk_g2s(ring + slot * SLOT_BYTES, a.wg + ((size_t)jn * nks + ks) * g_bytes, g_bytes, &full[slot]);
+            }
+        for (int ti = 0; ti < NT; ++ti)
+          for (int ks = 0; ks < nks; ++ks, ++it) {
             const int slot = it % NS;
             mbar_wait(&empty[slot], ((it / NS) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full[slot], g_bytes);
-            bulk_g2s(ring + slot * SLOT_BYTES, a.wg + ((size_t)jn * nks + ks) * g_bytes, g_bytes, &full[slot]);
+            mbar_arrive_expect_tx(&full[slot], c_bytes);
+            bulk_g2s(ring + slot * SLOT_BYTES, a.wc + (size_t)ks * c_bytes, c_bytes, &full[slot]);
           }
-        }
-        for (int ks = 0; ks < nks; ++ks, ++it) {
-          const int slot = it % NS;
-          mbar_wait(&empty[slot], ((it / NS) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full[slot], c_bytes);
-          bulk_g2s(ring + slot * SLOT_BYTES, a.wc + (size_t)ks * c_bytes, c_bytes, &full[slot]);
-        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, a.tmem_cols);
+  if (warp == n_epi) tmem_dealloc(tmem, a.tmem_cols);
+}
+
+struct Shape {
+  int NT, HC, EW, nthr;
+  uint32_t cols;
+  size_t smem;
+};
+Shape shape_of(int H) {
+  Shape s;
+  s.HC = (H % 64 == 0) ? 64 : 32;
+  s.EW = 4 * (H / s.HC);
+  s.NT = 1;   // two tiles per CTA (ping-pong) measured no faster: the epilogue, not the MMA, is the critical path
+  auto bytes = [&](int nt) { return (size_t)nt * 2 * (H / 8) * 2048 + NS * SLOT_BYTES + 256; };
+  if (s.NT == 2 && bytes(2) > 227 * 1024) s.NT = 1;
+  s.smem = bytes(s.NT);
+  s.nthr = (s.NT * s.EW + 2) * 32;
+  uint32_t c = 32;
+  while ((int)c < s.NT * 2 * H) c <<= 1;
+  s.cols = c;
+  return s;
 }
 
 }  // namespace
@@ -298,33 +350,8 @@ bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes
   if (a.H % 32 != 0 || a.H < 32 || a.H > 256) return false;
   if (a.T > 1 && !a.hs) return false;
   if (!a.packed && (!pack_ws || pack_bytes < gru_tc_pack_bytes(a.H))) return false;
-  const size_t smem = 2 * (size_t)(a.H / 8) * 2048 + NS * SLOT_BYTES + 128;
-  return smem <= 227 * 1024 && a.R >= 64;
-}
-
-int gru_seq_tc(const GruSeqArgs& s, void* pack_ws, cudaStream_t st) {
-  const int H = s.H;
-  GruTcArgs a{};
-  a.R = s.R; a.H = H; a.T = s.T;
-  a.xp = s.xp; a.xp_row_stride = s.xp_row_stride; a.xp_step_stride = s.xp_step_stride;
-  a.h0 = s.h0; a.h0_div = s.h0_div > 0 ? s.h0_div : 1; a.ld_h0 = s.ld_h0;
-  a.hs = s.hs; a.hs_row_stride = s.hs_row_stride; a.hs_step_stride = s.hs_step_stride;
-  a.h_final = s.h_final; a.ld_hf = s.ld_hf;
-  a.BNg = 2 * H <= 256 ? 2 * H : 256;
-  a.ntg = (2 * H) / a.BNg;
-  a.passes = gemm_mode() == 1 ? 1 : 3;
-  uint32_t cols = 32;
-  while ((int)cols < 2 * H) cols <<= 1;
-  a.tmem_cols = cols;
-  const uint8_t* pg = (const uint8_t*)(s.packed ? s.packed : pack_ws);
-  if (!s.packed) DESIRE_TRY(gru_tc_pack(s.w_g, s.w_c, H, pack_ws, gru_tc_pack_bytes(H), st));
-  a.wg = pg;
-  a.wc = pg + align_up(tc_pack_bytes(H, 2 * H, a.BNg));
-  const size_t smem = 2 * (size_t)(H / 8) * 2048 + NS * SLOT_BYTES + 128;
-  DESIRE_ENSURE_SMEM(gru_tc_kernel, smem);
-  const unsigned grid = (unsigned)(((long)s.R + 127) / 128);
-  DESIRE_LAUNCH(st, (gru_tc_kernel<<<grid, NTHR, smem, st>>>(a)));
-  return DESIRE_OK;
+  const Shape s = shape_of(a.H);
+  return s.smem <= 227 * 1024 && s.nthr <= 1024 && a.R >= 64;
 }
 
 int gru_tc_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -334,6 +361,35 @@ int gru_tc_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_b
   uint8_t* pc = pg + align_up(tc_pack_bytes(H, 2 * H, BNg));
   DESIRE_TRY(tc_pack_b(w_g, 2 * H, false, H, 2 * H, BNg, pg, st));
   DESIRE_TRY(tc_pack_b(w_c, H, false, H, H, H, pc, st));
+  return DESIRE_OK;
+}
+
+int gru_seq_tc(const GruSeqArgs& s, void* pack_ws, cudaStream_t st) {
+  const int H = s.H;
+  const Shape sh = shape_of(H);
+  GruTcArgs a{};
+  a.R = s.R; a.H = H; a.T = s.T;
+  a.xp = s.xp; a.xp_row_stride = s.xp_row_stride; a.xp_step_stride = s.xp_step_stride;
+  a.h0 = s.h0; a.h0_div = s.h0_div > 0 ? s.h0_div : 1; a.ld_h0 = s.ld_h0;
+  a.hs = s.hs; a.hs_row_stride = s.hs_row_stride; a.hs_step_stride = s.hs_step_stride;
+  a.h_final = s.h_final; a.ld_hf = s.ld_hf;
+  a.BNg = 2 * H <= 256 ? 2 * H : 256;
+  a.ntg = (2 * H) / a.BNg;
+  a.passes = gemm_mode() == 1 ? 1 : 3;
+  a.NT = sh.NT; a.HC = sh.HC; a.EW = sh.EW; a.tmem_cols = sh.cols;
+  const uint8_t* pg = (const uint8_t*)(s.packed ? s.packed : pack_ws);
+  if (!s.packed) DESIRE_TRY(gru_tc_pack(s.w_g, s.w_c, H, pack_ws, gru_tc_pack_bytes(H), st));
+  a.wg = pg;
+  a.wc = pg + align_up(tc_pack_bytes(H, 2 * H, a.BNg));
+  const long tiles = ((long)s.R + 127) / 128;
+  const unsigned grid = (unsigned)((tiles + sh.NT - 1) / sh.NT);
+  if (sh.nthr <= 576) {            // H in {32, 64, 128, 192, 256}: up to 113 registers per thread
+    DESIRE_ENSURE_SMEM(gru_tc_kernel<576>, sh.smem);
+    DESIRE_LAUNCH(st, (gru_tc_kernel<576><<<grid, sh.nthr, sh.smem, st>>>(a)));
+  } else {
+    DESIRE_ENSURE_SMEM(gru_tc_kernel<1024>, sh.smem);
+    DESIRE_LAUNCH(st, (gru_tc_kernel<1024><<<grid, sh.nthr, sh.smem, st>>>(a)));
+  }
   return DESIRE_OK;
 }
 

@@ -129,20 +129,36 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
 struct Split8 {
   uint4 hi, lo;
 };
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+// 2 elements per cvt (cvt.rn.bf16x2.f32), ~3 instructions per element:
+// hi = bf16x2(x1,x0); hi as floats = bits<<16 / bits&0xffff0000; lo = bf16x2(x1-hi1, x0-hi0).
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
 __device__ __forceinline__ Split8 split8(const float* x) {
-  __nv_bfloat16 h[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = __float2bfloat16_rn(x[i]);
-    l[i] = __float2bfloat16_rn(x[i] - __bfloat162float(h[i]));
-  }
   Split8 s;
-  s.hi = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-  s.lo = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+  split2(x[0], x[1], s.hi.x, s.lo.x);
+  split2(x[2], x[3], s.hi.y, s.lo.y);
+  split2(x[4], x[5], s.hi.z, s.lo.z);
+  split2(x[6], x[7], s.hi.w, s.lo.w);
   return s;
+}
+
+// fast activations: ex2.approx (2 ulp) + rcp.approx (1 ulp); 4-5 instructions each
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpa(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_a(float x) { return rcpa(1.f + ex2a(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_a(float x) {     // 1 - 2/(1+e^{2x}); saturates to +-1 for large |x|
+  return fmaf(-2.f, rcpa(1.f + ex2a(2.8853900817779268f * x)), 1.f);
 }
 
 }  // namespace tc
