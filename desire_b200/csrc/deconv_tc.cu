@@ -91,9 +91,10 @@ __global__ void pack_deconv_kernel(const float* __restrict__ W, int Cin, int Cou
 
 __device__ __forceinline__ int swz(int oy, int ox, int sh) { return ((ox >> sh) + 4 * ((oy >> sh) & 1)) & 7; }
 
+template <int HIN, int HOUT, int STRIDE, int KS>
 __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int Pin = a.Hin * a.Hin, Pout = a.Hout * a.Hout, spt = TM / Pin;
+  constexpr int Pin = HIN * HIN, Pout = HOUT * HOUT, spt = TM / Pin;
   const DcLayout L = dc_layout(a.Cin, a.nstg, spt);
   uint8_t* A_hi = smem + L.a_hi;
   uint8_t* A_lo = smem + L.a_lo;
@@ -109,9 +110,10 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
   uint32_t* tslot = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntaps = a.ks * a.ks, nnt = (ntaps + TPT - 1) / TPT, ncg = a.Cout / CG, nks = a.Cin / 32;
+  constexpr int ntaps = KS * KS, nnt = (ntaps + TPT - 1) / TPT;
+  const int ncg = a.Cout / CG, nks = a.Cin / 32;
   const long samp0 = (long)blockIdx.x * spt;
-  const int sh = a.stride - 1;
+  constexpr int sh = STRIDE - 1;
 
   if (tid == 0) {
     for (int s = 0; s < a.nstg; ++s) {
@@ -158,10 +160,10 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
     }
-    const int iy = p / a.Hin, ix = p % a.Hin;
+    const int iy = p / HIN, ix = p % HIN;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* osamp = outt + (size_t)s_loc * Pout * CG;
-    const int ntile_el = spt * Pout * CG;                      // 16384 floats = 64 KB
+    constexpr int ntile_el = spt * Pout * CG;                  // 16384 floats = 64 KB
     uint32_t use = 0;
     for (int cg = 0; cg < ncg; ++cg) {
       // zero the output tile of this channel group
@@ -175,13 +177,13 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
         tc_fence_after();
         for (int tl = 0; tl < taps; ++tl) {
           const int t = nt * TPT + tl;
-          const int ky = t / a.ks, kx = t - ky * a.ks;
-          const int oy = iy * a.stride + ky - a.pad, ox = ix * a.stride + kx - a.pad;
+          const int ky = t / KS, kx = t - ky * KS;
+          const int oy = iy * STRIDE + ky - a.pad, ox = ix * STRIDE + kx - a.pad;
           float v[16];
           tmem_ld16(trow + ab * 256 + tl * CG + half * 16, v);
           tmem_ld_wait();
-          if (oy >= 0 && oy < a.Hout && ox >= 0 && ox < a.Hout) {
-            float* o = osamp + (size_t)(oy * a.Hout + ox) * CG;
+          if (oy >= 0 && oy < HOUT && ox >= 0 && ox < HOUT) {
+            float* o = osamp + (size_t)(oy * HOUT + ox) * CG;
             const int rot = swz(oy, ox, sh);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -198,14 +200,14 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
         if (lane == 0) mbar_arrive(&acc_empty[ab]);
       }
       // ---- (c) bias + per-(sample, channel) BN over the Pout positions + activation + store
-      const int npair = spt * CG, parts = 256 / npair;         // npair in {64, 256}
+      constexpr int npair = spt * CG, parts = 256 / npair;     // npair in {64, 256}
       const int pair = tid % npair, part = tid / npair;
       const int ps = pair / CG, pc = pair % CG;
       const float b = __ldg(a.bias + cg * CG + pc);
       const float* tsamp = outt + (size_t)ps * Pout * CG;
       float sum = 0.f;
       for (int q = part; q < Pout; q += parts) {
-        const int oy = q / a.Hout, ox = q - oy * a.Hout;
+        const int oy = q / HOUT, ox = q - oy * HOUT;
         sum += tsamp[q * CG + (((pc >> 2) + swz(oy, ox, sh)) & 7) * 4 + (pc & 3)] + b;
       }
       red[tid] = sum;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
       const float mean = stat[pair];
       sum = 0.f;
       for (int q = part; q < Pout; q += parts) {
-        const int oy = q / a.Hout, ox = q - oy * a.Hout;
+        const int oy = q / HOUT, ox = q - oy * HOUT;
         const float d = tsamp[q * CG + (((pc >> 2) + swz(oy, ox, sh)) & 7) * 4 + (pc & 3)] + b - mean;
         sum += d * d;
       }
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
         const int c = e % CG, q = (e / CG) % Pout, s2 = e / (CG * Pout);
         const long smp = samp0 + s2;
         if (smp >= a.R) continue;
-        const int oy = q / a.Hout, ox = q - oy * a.Hout;
+        const int oy = q / HOUT, ox = q - oy * HOUT;
         const float x = outt[((size_t)s2 * Pout + q) * CG + (((c >> 2) + swz(oy, ox, sh)) & 7) * 4 + (c & 3)] +
                         __ldg(a.bias + cg * CG + c);
         const int pr = s2 * CG + c;
@@ -322,7 +324,8 @@ bool deconv_tc_eligible(int R, int Hin, int Hout, int Cin, int Cout, int ks, int
   if ((size_t)(TM / Pin) * Pout * CG * 4 != 64 * 1024) return false;        // out tile exactly 64 KB
   if (256 % ((TM / Pin) * CG) != 0 && ((TM / Pin) * CG) % 256 != 0) return false;
   if ((TM / Pin) * CG > 256) return false;
-  if (stride < 1 || stride > 2 || ks * ks > 32) return false;
+  if (!((Hin == 4 && Hout == 8 && stride == 1 && ks == 5) || (Hin == 8 && Hout == 16 && stride == 2 && ks == 5)))
+    return false;   // the two instantiated geometries of model/model.py:466-467
   return pack_ws && pack_bytes >= deconv_tc_pack_bytes(Cin, Cout, ks);
 }
 
@@ -344,9 +347,17 @@ int deconv_tc(const float* X, int R, int Hin, int Hout, int Cin, int Cout, int k
   a.nstg = Cin > 64 ? 2 : 3;
   const DcLayout L = dc_layout(Cin, a.nstg, spt);
   DESIRE_CHECK_ARG(L.total <= 227 * 1024, "deconv_tc: shared memory layout too large");
-  DESIRE_ENSURE_SMEM(deconv_tc_kernel, L.total);
   const unsigned grid = (unsigned)((R + spt - 1) / spt);
-  DESIRE_LAUNCH(st, (deconv_tc_kernel<<<grid, NTHR, L.total, st>>>(a)));
+  if (Hin == 4 && Hout == 8 && stride == 1 && ks == 5) {
+    DESIRE_ENSURE_SMEM((deconv_tc_kernel<4, 8, 1, 5>), L.total);
+    DESIRE_LAUNCH(st, (deconv_tc_kernel<4, 8, 1, 5><<<grid, NTHR, L.total, st>>>(a)));
+  } else if (Hin == 8 && Hout == 16 && stride == 2 && ks == 5) {
+    DESIRE_ENSURE_SMEM((deconv_tc_kernel<8, 16, 2, 5>), L.total);
+    DESIRE_LAUNCH(st, (deconv_tc_kernel<8, 16, 2, 5><<<grid, NTHR, L.total, st>>>(a)));
+  } else {
+    set_error("deconv_tc: geometry %dx%d -> %dx%d k%d s%d has no instantiation", Hin, Hin, Hout, Hout, ks, stride);
+    return DESIRE_ERR_INVALID;
+  }
   return DESIRE_OK;
 }
 

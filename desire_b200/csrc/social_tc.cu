@@ -30,7 +30,7 @@ constexpr int MAXG = 64;
 
 struct Layout {
   int hs_ld;            // floats per staged hidden row
-  size_t hs, px, py, tab, lists, list_stride, bins, stages, stage_bytes, bars, total;
+  size_t hs, px, py, rowmap, tab, lists, list_stride, bins, stages, stage_bytes, bars, total;
 };
 __host__ __device__ inline Layout make_layout(int H, int Npad, int G, int n_rad, int n_ang) {
   Layout L;
@@ -39,6 +39,7 @@ __host__ __device__ inline Layout make_layout(int H, int Npad, int G, int n_rad,
   L.hs = off; off += (size_t)TM * L.hs_ld * 4;
   L.px = off; off += TM * 4;
   L.py = off; off += TM * 4;
+  L.rowmap = off; off += TM * 8;                                 // global row of every tile lane (-1 = none)
   L.tab = off; off += (size_t)((n_rad + 1 + 2 * n_ang + 3) / 4 * 4) * 4;
   L.list_stride = (size_t)((G + 1 + Npad + 3) / 4 * 4);          // bytes per row: off[G+1] then list[Npad]
   L.lists = off; off += TM * L.list_stride;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
   float* px = reinterpret_cast<float*>(smem + L.px);
   float* py = reinterpret_cast<float*>(smem + L.py);
   float* tab = reinterpret_cast<float*>(smem + L.tab);
+  long* rowmap = reinterpret_cast<long*>(smem + L.rowmap);
   uint8_t* lists = smem + L.lists;
   uint8_t* bins = smem + L.bins;
   uint8_t* stages = smem + L.stages;
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
     return (b * N + i) * K + k;
   };
 
+  if (tid < TM) rowmap[tid] = row_of(tid);     // the 64-bit divisions happen once per lane, not per element
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], NPW + 1);
@@ -95,12 +98,13 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
     fence_barrier_init();
   }
   if (warp == NPW) tmem_alloc_dyn(tslot, tmem_cols);
+  __syncthreads();
 
   // ---- prologue: stage tables, positions (NaN = non-existent / padding) and hidden vectors
   for (int e = tid; e < a.n_rad + 1; e += NTHR) tab[e] = __ldg(a.r2_edges + e);
   for (int e = tid; e < 2 * a.n_ang; e += NTHR) tab[a.n_rad + 1 + e] = __ldg(a.dirs + e);
   for (int l = tid; l < TM; l += NTHR) {
-    const long r = row_of(l);
+    const long r = rowmap[l];
     float x = __int_as_float(0x7fc00000), y = x;
     if (r >= 0) {
       const long bn = r / K;                         // b*N + i
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
     const int H4 = H / 4;
     for (int e = tid; e < TM * H4; e += NTHR) {
       const int l = e / H4, c4 = e - l * H4;
-      const long r = row_of(l);
+      const long r = rowmap[l];
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r >= 0) v = __ldg(reinterpret_cast<const float4*>(a.h + r * (long)a.ld_h) + c4);
       *reinterpret_cast<float4*>(hs + (size_t)l * L.hs_ld + c4 * 4) = v;
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
     // ===================== binning, all 512 threads: thread (row rl, quarter q) bins neighbours j = q, q+4, ...
     {
       const int rl = tid & (TM - 1), q = tid >> 7;
-      const long r = row_of(rl);
+      const long r = rowmap[rl];
       const int gbase = (rl / Npad) * Npad, me = rl % Npad;
       uint8_t* brow = bins + (size_t)rl * Npad;
       // a masked row still pools its existing neighbours: its own position comes from global memory
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[slot]);
     }
-    const long myrow = row_of(tid & (TM - 1));
+    const long myrow = rowmap[tid & (TM - 1)];
 
     // ===================== epilogue: warp w -> TMEM lanes 32*(w%4).., columns 32*(w/4)..
     mbar_wait(tfull, 0);
