@@ -206,13 +206,13 @@ struct GruSeqArgs {
   int ld_hf;
   const void* packed = nullptr;   // optional: weights already packed by gru_tc_pack (skips per-call packing)
 };
-int gru_tc_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st);
+int gru_tc_pack(const float* w_g, const float* w_c, int H, int Ka, void* ws, size_t ws_bytes, cudaStream_t st);
 int gru_seq(const GruSeqArgs& a, cudaStream_t st, PackWs pw = PackWs());
 // tcgen05 recurrence (gru_tc.cu): taken when H % 32 == 0, H <= 256, the input projection is hoisted (xp)
 // and scratch for the packed weights is available
 size_t tc_pack_bytes(int K, int N, int BN);
 int tc_pack_b(const float* W, int ldw, bool trans, int K, int N, int BN, void* out, cudaStream_t st);
-size_t gru_tc_pack_bytes(int H);
+size_t gru_tc_pack_bytes(int H, int Ka = 0);
 bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes);
 int gru_seq_tc(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
 

@@ -175,6 +175,95 @@ __global__ void __launch_bounds__(256) colbn_act_v4_kernel(const float* __restri
   }
 }
 
+// Direct single-output-channel transposed conv (the decoder's last layer, model/model.py:468:
+// 16x16x32 -> 32x32x1, k5 s2 SAME, BN + sigmoid).  Its GEMM form is degenerate (N = 25 columns, a col matrix
+// 8x larger than the input), so: one CTA per sample, input tile [Pin][Cin+4] and the filter in shared memory
+// (row stride Cin+4 floats keeps the 128-bit reads of a quarter-warp conflict-free), each thread gathers its
+// output pixels over the valid taps with float4 FMAs, then block-wide two-pass BN and the activation.
+template <int CIN, int KS, int STRIDE>
+__global__ void __launch_bounds__(256) deconv1ch_bn_act_kernel(const float* __restrict__ X, int Hin, int Hout,
+                                                               int pad, const float* __restrict__ W,
+                                                               const float* __restrict__ bias,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int act,
+                                                               float* __restrict__ Y) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int LD = CIN + 4;
+  const int Pin = Hin * Hin, Pout = Hout * Hout;
+  constexpr int kk = KS * KS;
+  float* xin = sm;                       // [Pin][LD]
+  float* wf = xin + (size_t)Pin * LD;    // [kk][CIN]
+  float* red = wf + kk * CIN;            // [32]
+  const int tid = threadIdx.x;
+  const size_t r = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(X + r * (size_t)Pin * CIN);
+  for (int e = tid; e < Pin * (CIN / 4); e += 256) {
+    const int p = e / (CIN / 4), c4 = e % (CIN / 4);
+    *reinterpret_cast<float4*>(xin + (size_t)p * LD + c4 * 4) = __ldg(src + e);
+  }
+  for (int e = tid; e < kk * CIN; e += 256) wf[e] = __ldg(W + e);      // [ky,kx,o=0,ci] == [tap][ci]
+  __syncthreads();
+
+  float vals[4];                          // Pout <= 1024 => <= 4 pixels per thread (pixel = tid + 256*i, coalesced)
+  const float b0 = __ldg(bias);
+  float lsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = tid + 256 * i;
+    float acc = 0.f;
+    if (q < Pout) {
+      const int oy = q / Hout, ox = q - oy * Hout;
+      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      // only the taps of this pixel's parity class exist: ky = (oy+pad) mod S, +S, ... (no div/mod per tap)
+      for (int ky = (oy + pad) % STRIDE; ky < KS; ky += STRIDE) {
+        const int iy = (oy + pad - ky) / STRIDE;
+        if (iy < 0 || iy >= Hin) continue;
+        for (int kx = (ox + pad) % STRIDE; kx < KS; kx += STRIDE) {
+          const int ix = (ox + pad - kx) / STRIDE;
+          if (ix < 0 || ix >= Hin) continue;
+          const float4* xp = reinterpret_cast<const float4*>(xin + (size_t)(iy * Hin + ix) * LD);
+          const float4* wp = reinterpret_cast<const float4*>(wf + (ky * KS + kx) * CIN);
+#pragma unroll
+          for (int c = 0; c < CIN / 4; ++c) {
+            const float4 xv = xp[c], wv = wp[c];
+            a4.x = fmaf(xv.x, wv.x, a4.x); a4.y = fmaf(xv.y, wv.y, a4.y);
+            a4.z = fmaf(xv.z, wv.z, a4.z); a4.w = fmaf(xv.w, wv.w, a4.w);
+          }
+        }
+      }
+      acc = (a4.x + a4.y) + (a4.z + a4.w) + b0;
+      lsum += acc;
+    }
+    vals[i] = acc;
+  }
+  // block reductions (deterministic): warp shuffle, then 8 partials
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
+  };
+  const float mean = block_sum(lsum) / (float)Pout;
+  float lvar = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (tid + 256 * i < Pout) {
+      const float d = vals[i] - mean;
+      lvar += d * d;
+    }
+  const float rstd = 1.f / sqrtf(block_sum(lvar) / (float)Pout + BN_EPS);
+  const float g = __ldg(gamma), be = __ldg(beta);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = tid + 256 * i;
+    if (q < Pout) Y[r * (size_t)Pout + q] = act_apply(g * ((vals[i] - mean) * rstd) + be, act);
+  }
+}
+
 template <int KS, int S>
 int launch_v4(const float* col, int R, int Hin, int Hout, int pad, int Cout, const float* bias, const float* gamma,
               const float* beta, int act, float* out, size_t smem, cudaStream_t st) {
@@ -314,12 +403,14 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
       DESIRE_TRY(colbn_act(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st));
     }
-    // deconv5/2 SAME 16x16x32 -> 32x32x1, BN + sigmoid
-    DESIRE_TRY(sgemm(a3, 32, w->d4.w, 32, true, nullptr, col, 25, rc * 256, 25, 32, DESIRE_ACT_NONE, false, st, pw));
+    // deconv5/2 SAME 16x16x32 -> 32x32x1, BN + sigmoid: direct kernel (no GEMM, no col matrix)
     {
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
-      DESIRE_TRY(colbn_act(col, rc, 16, 32, 5, 2, 1, 1, w->d4.b, w->d4.gamma, w->d4.beta, DESIRE_ACT_SIGMOID,
-                           xr + (size_t)r0 * 1024, st));
+      const size_t smem4 = ((size_t)256 * 36 + 25 * 32 + 32) * sizeof(float);
+      DESIRE_ENSURE_SMEM((deconv1ch_bn_act_kernel<32, 5, 2>), smem4);
+      DESIRE_LAUNCH(st, (deconv1ch_bn_act_kernel<32, 5, 2><<<rc, 256, smem4, st>>>(a3, 16, 32, 1, w->d4.w, w->d4.b, w->d4.gamma,
+                                                                                w->d4.beta, DESIRE_ACT_SIGMOID,
+                                                                                xr + (size_t)r0 * 1024)));
     }
   }
   return DESIRE_OK;

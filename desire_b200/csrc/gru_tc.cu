@@ -41,8 +41,10 @@ struct GruTcArgs {
   long hs_row_stride, hs_step_stride;
   float* h_final;
   int ld_hf;
-  const uint8_t* wg;   // packed [ntg][H/32] blocks of 128*BNg bytes
-  const uint8_t* wc;   // packed [H/32] blocks of 128*H bytes
+  const float* ex;     // optional extra per-step operand [R,Ka] (Decoder-2: the social feature), Ka in {0, H}
+  int Ka, ld_ex;
+  const uint8_t* wg;   // packed [ntg][(Ka+H)/32] blocks of 128*BNg bytes (rows 0..Ka-1 multiply ex, then h)
+  const uint8_t* wc;   // packed [(Ka+H)/32] blocks of 128*H bytes
   int BNg, ntg;
   int passes;
   int NT, HC, EW;      // tiles per CTA, columns per epilogue thread, epilogue warps per tile
@@ -82,7 +84,8 @@ template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) gru_tc_kernel(GruTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, NT = a.NT;
-  const int a_half = (H / 8) * 2048;                 // [H/8 chunks][128 rows][16 B] per tile
+  const int KA = a.Ka + H;                           // A operand width: [ex | h]
+  const int a_half = (KA / 8) * 2048;                // [KA/8 chunks][128 rows][16 B] per tile
   uint8_t* ring = smem + (size_t)NT * 2 * a_half;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + NS * SLOT_BYTES);
   uint64_t* empty = full + NS;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(MAXT, 1) gru_tc_kernel(GruTcArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_epi = NT * a.EW;                       // epilogue warps; then MMA warp, loader warp
-  const int nks = H / 32;
+  const int nks = KA / 32;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -126,11 +129,25 @@ __global__ void __launch_bounds__(MAXT, 1) gru_tc_kernel(GruTcArgs a) {
                                                       // branch-free and in bounds); they never store
     const int HC = a.HC, cbeg = cs * HC;            // this thread's columns [cbeg, cbeg+HC)
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + ti * 2 * H;
-    uint8_t* my_hi = smem + (size_t)ti * 2 * a_half + rloc * 16;
+    uint8_t* my_hi = smem + (size_t)ti * 2 * a_half + (a.Ka / 8) * 2048 + rloc * 16;   // h / r*h chunks (after ex)
     uint8_t* my_lo = my_hi + a_half;
     const float* xp0 = a.xp + row * a.xp_row_stride;
     const float* h0r = a.h0 ? a.h0 + (row / a.h0_div) * (long)a.ld_h0 : nullptr;
 
+    // ---- extra operand (constant over the launch) -> first Ka/8 chunks of the A operand
+    if (a.ex) {
+      const float* exr = a.ex + row * (long)a.ld_ex;
+      uint8_t* e_hi = smem + (size_t)ti * 2 * a_half + rloc * 16;
+      for (int c = cbeg; c < cbeg + HC; c += 16) {
+        float ev[16];
+        ld16g(exr + c, ev);
+        const Split8 s0 = split8(ev), s1 = split8(ev + 8);
+        *reinterpret_cast<uint4*>(e_hi + (c / 8) * 2048) = s0.hi;
+        *reinterpret_cast<uint4*>(e_hi + a_half + (c / 8) * 2048) = s0.lo;
+        *reinterpret_cast<uint4*>(e_hi + (c / 8 + 1) * 2048) = s1.hi;
+        *reinterpret_cast<uint4*>(e_hi + a_half + (c / 8 + 1) * 2048) = s1.lo;
+      }
+    }
     // ---- initial state -> A operand, xp_r|xp_u of step 0 -> TMEM accumulator
     for (int c = cbeg; c < cbeg + HC; c += 16) {
       float hv[16], xr[16], xu[16];
@@ -323,12 +340,12 @@ struct Shape {
   uint32_t cols;
   size_t smem;
 };
-Shape shape_of(int H) {
+Shape shape_of(int H, int Ka) {
   Shape s;
   s.HC = (H % 64 == 0) ? 64 : 32;
   s.EW = 4 * (H / s.HC);
   s.NT = 1;   // two tiles per CTA (ping-pong) measured no faster: the epilogue, not the MMA, is the critical path
-  auto bytes = [&](int nt) { return (size_t)nt * 2 * (H / 8) * 2048 + NS * SLOT_BYTES + 256; };
+  auto bytes = [&](int nt) { return (size_t)nt * 2 * ((Ka + H) / 8) * 2048 + NS * SLOT_BYTES + 256; };
   if (s.NT == 2 && bytes(2) > 227 * 1024) s.NT = 1;
   s.smem = bytes(s.NT);
   s.nthr = (s.NT * s.EW + 2) * 32;
@@ -340,47 +357,49 @@ Shape shape_of(int H) {
 
 }  // namespace
 
-size_t gru_tc_pack_bytes(int H) {
+size_t gru_tc_pack_bytes(int H, int Ka) {
   const int BNg = 2 * H <= 256 ? 2 * H : 256;
-  return align_up(tc_pack_bytes(H, 2 * H, BNg)) + align_up(tc_pack_bytes(H, H, H));
+  return align_up(tc_pack_bytes(Ka + H, 2 * H, BNg)) + align_up(tc_pack_bytes(Ka + H, H, H));
 }
 
 bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes) {
-  if (gemm_mode() == 0 || !a.xp || a.traj || a.ex || a.Ka != 0) return false;
+  if (gemm_mode() == 0 || !a.xp || a.traj) return false;
   if (a.H % 32 != 0 || a.H < 32 || a.H > 256) return false;
+  if (a.ex ? (a.Ka != a.H || a.T != 1 || a.ld_ex % 4 != 0) : a.Ka != 0) return false;
   if (a.T > 1 && !a.hs) return false;
-  if (!a.packed && (!pack_ws || pack_bytes < gru_tc_pack_bytes(a.H))) return false;
-  const Shape s = shape_of(a.H);
+  if (!a.packed && (!pack_ws || pack_bytes < gru_tc_pack_bytes(a.H, a.Ka))) return false;
+  const Shape s = shape_of(a.H, a.Ka);
   return s.smem <= 227 * 1024 && s.nthr <= 1024 && a.R >= 64;
 }
 
-int gru_tc_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st) {
-  DESIRE_CHECK_ARG(ws && ws_bytes >= gru_tc_pack_bytes(H), "gru_tc_pack: workspace too small");
+int gru_tc_pack(const float* w_g, const float* w_c, int H, int Ka, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DESIRE_CHECK_ARG(ws && ws_bytes >= gru_tc_pack_bytes(H, Ka), "gru_tc_pack: workspace too small");
   const int BNg = 2 * H <= 256 ? 2 * H : 256;
   uint8_t* pg = (uint8_t*)ws;
-  uint8_t* pc = pg + align_up(tc_pack_bytes(H, 2 * H, BNg));
-  DESIRE_TRY(tc_pack_b(w_g, 2 * H, false, H, 2 * H, BNg, pg, st));
-  DESIRE_TRY(tc_pack_b(w_c, H, false, H, H, H, pc, st));
+  uint8_t* pc = pg + align_up(tc_pack_bytes(Ka + H, 2 * H, BNg));
+  DESIRE_TRY(tc_pack_b(w_g, 2 * H, false, Ka + H, 2 * H, BNg, pg, st));
+  DESIRE_TRY(tc_pack_b(w_c, H, false, Ka + H, H, H, pc, st));
   return DESIRE_OK;
 }
 
 int gru_seq_tc(const GruSeqArgs& s, void* pack_ws, cudaStream_t st) {
   const int H = s.H;
-  const Shape sh = shape_of(H);
+  const Shape sh = shape_of(H, s.Ka);
   GruTcArgs a{};
   a.R = s.R; a.H = H; a.T = s.T;
   a.xp = s.xp; a.xp_row_stride = s.xp_row_stride; a.xp_step_stride = s.xp_step_stride;
   a.h0 = s.h0; a.h0_div = s.h0_div > 0 ? s.h0_div : 1; a.ld_h0 = s.ld_h0;
   a.hs = s.hs; a.hs_row_stride = s.hs_row_stride; a.hs_step_stride = s.hs_step_stride;
   a.h_final = s.h_final; a.ld_hf = s.ld_hf;
+  a.ex = s.ex; a.Ka = s.Ka; a.ld_ex = s.ld_ex;
   a.BNg = 2 * H <= 256 ? 2 * H : 256;
   a.ntg = (2 * H) / a.BNg;
   a.passes = gemm_mode() == 1 ? 1 : 3;
   a.NT = sh.NT; a.HC = sh.HC; a.EW = sh.EW; a.tmem_cols = sh.cols;
   const uint8_t* pg = (const uint8_t*)(s.packed ? s.packed : pack_ws);
-  if (!s.packed) DESIRE_TRY(gru_tc_pack(s.w_g, s.w_c, H, pack_ws, gru_tc_pack_bytes(H), st));
+  if (!s.packed) DESIRE_TRY(gru_tc_pack(s.w_g, s.w_c, H, s.Ka, pack_ws, gru_tc_pack_bytes(H, s.Ka), st));
   a.wg = pg;
-  a.wc = pg + align_up(tc_pack_bytes(H, 2 * H, a.BNg));
+  a.wc = pg + align_up(tc_pack_bytes(s.Ka + H, 2 * H, a.BNg));
   const long tiles = ((long)s.R + 127) / 128;
   const unsigned grid = (unsigned)((tiles + sh.NT - 1) / sh.NT);
   if (sh.nthr <= 576) {            // H in {32, 64, 128, 192, 256}: up to 113 registers per thread

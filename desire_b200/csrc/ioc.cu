@@ -356,7 +356,7 @@ IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   L.pk_sp = take(gemm_tc_pack_bytes((int)H, (int)(G * H)));
   L.pk_sp3 = take(gemm_tc_pack_bytes(3 * (int)H, (int)H));
   L.pk_reg = take(gemm_tc_pack_bytes(2 * (int)T, (int)H));
-  L.pk_gru = take(H % 32 == 0 && H <= 256 ? gru_tc_pack_bytes((int)H) : 256);
+  L.pk_gru = take(H % 32 == 0 && H <= 256 ? gru_tc_pack_bytes((int)H, (int)H) : 256);
   L.total = off;
   return L;
 }
@@ -414,15 +414,27 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
   DESIRE_TRY(pack_weight(pw_sp, base + L.pk_sp, L.pk_sp3 - L.pk_sp, st));
   DESIRE_TRY(pack_weight(pw_sp3, base + L.pk_sp3, L.pk_reg - L.pk_sp3, st));
   DESIRE_TRY(pack_weight(pw_reg, base + L.pk_reg, L.pk_gru - L.pk_reg, st));
-  const float* wg_h = g.wg + (size_t)(Dst + H) * 2 * H;   // state rows
+  // Decoder-2 step, preferred form: the social feature enters the GRU kernel as an extra A operand
+  // ([fsp | h] @ rows [Dst, Dst+2H) of the weights), so no per-step projection GEMM and no XP read-modify-write
+  const float* wg_sh = g.wg + (size_t)Dst * 2 * H;        // rows: fsp (H) then state (H)
+  const float* wc_sh = g.wc + (size_t)Dst * H;
+  const float* wg_h = g.wg + (size_t)(Dst + H) * 2 * H;   // state rows only (fallback form)
   const float* wc_h = g.wc + (size_t)(Dst + H) * H;
   const void* gru_packed = nullptr;
+  bool gru_ex = false;
   {
     GruSeqArgs probe{};
-    probe.R = (int)R; probe.H = H; probe.T = 1; probe.xp = XP;
+    probe.R = (int)R; probe.H = H; probe.T = 1; probe.xp = XP; probe.ex = fsp; probe.Ka = H; probe.ld_ex = H;
     if (gru_tc_eligible(probe, base + L.pk_gru, L.total - L.pk_gru)) {
-      DESIRE_TRY(gru_tc_pack(wg_h, wc_h, H, base + L.pk_gru, L.total - L.pk_gru, st));
+      DESIRE_TRY(gru_tc_pack(wg_sh, wc_sh, H, H, base + L.pk_gru, L.total - L.pk_gru, st));
       gru_packed = base + L.pk_gru;
+      gru_ex = true;
+    } else {
+      probe.ex = nullptr; probe.Ka = 0;
+      if (gru_tc_eligible(probe, base + L.pk_gru, L.total - L.pk_gru)) {
+        DESIRE_TRY(gru_tc_pack(wg_h, wc_h, H, 0, base + L.pk_gru, L.total - L.pk_gru, st));
+        gru_packed = base + L.pk_gru;
+      }
     }
   }
 
@@ -468,7 +480,7 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
         ProfScope ps_(DESIRE_PROF_SOCIAL_FC, st);
         DESIRE_TRY(gemm_packed(pooled, G * H, pw_sp, w->sp_b, fsp, H, (int)R, DESIRE_ACT_RELU, false, st));
       }
-      {
+      if (!gru_ex) {
         // XP[:, t, :] += fsp @ wsp3  (completes the step's input projection)
         ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
         DESIRE_TRY(gemm_packed(fsp, H, pw_sp3, nullptr, XP + (size_t)t * 3 * H, T * 3 * H, (int)R, DESIRE_ACT_NONE, true, st));
@@ -476,9 +488,15 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
       GruSeqArgs a{};
       a.R = (int)R; a.H = H; a.T = 1;
       a.xp = XP + (size_t)t * 3 * H; a.xp_row_stride = (long)T * 3 * H; a.xp_step_stride = 0;
-      a.Ka = 0;
-      a.w_g = wg_h;
-      a.w_c = wc_h;
+      if (gru_ex) {
+        a.ex = fsp; a.Ka = H; a.ld_ex = H;
+        a.w_g = wg_sh;
+        a.w_c = wc_sh;
+      } else {
+        a.Ka = 0;
+        a.w_g = wg_h;
+        a.w_c = wc_h;
+      }
       a.h0 = h2; a.h0_div = 1; a.ld_h0 = H;
       a.h_final = h2; a.ld_hf = H;
       a.packed = gru_packed;
