@@ -90,6 +90,12 @@ def oracle_step_fn(a, cfg, n_scenes, seed=0):
 
 
 def run_cpu(a, cfg, steps, warmup):
+    # torchrun exports OMP_NUM_THREADS=1; the CPU legs must use every host core the BLAS can get
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     step, units = oracle_step_fn(a, cfg, a.cpu_sample_scenes)
     for _ in range(warmup):
         step()

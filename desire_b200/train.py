@@ -1,0 +1,110 @@
+"""Train-script entry point with the reference's flags and loop shape (train.py:24-207).
+
+    python -m desire_b200.train --d_dim 128 --batch_size 32 --num_samples 20 ...
+
+Same 19 argparse flags with the same names and defaults (train.py:28-88) plus the knobs the build adds
+(DESIGN.md D1/D2/D11).  Like the reference — whose loop only ever evaluates `model.cost` (train.py:181; the
+optimiser op of model/model.py:394 is never run) — round 1 evaluates the hot path per minibatch:
+sample generation + IOC ranking/refinement on the GPU, the masked cost, the reference's log line, the per-epoch
+learning-rate schedule value, and a checkpoint of the weights every `save_every` steps.  The optimiser step (D9)
+arrives with the backward kernels.  Where the reference ran one sess.run per SEQUENCE
+(train.py:146-181), a whole minibatch of scenes is one pass here.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import pickle
+import sys
+import time
+
+import numpy as np
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    # ---- the reference's flags, verbatim (train.py:30-88)
+    p.add_argument('--rnn_size', type=int, default=512, help='size of RNN hidden state')
+    p.add_argument('--num_layers', type=int, default=1, help='number of layers in the RNN')
+    p.add_argument('--model', type=str, default='gru', help='rnn, gru, or lstm')
+    p.add_argument('--batch_size', type=int, default=10, help='minibatch size')
+    p.add_argument('--seq_length', type=int, default=8, help='RNN sequence length')
+    p.add_argument('--num_epochs', type=int, default=100, help='number of epochs')
+    p.add_argument('--save_every', type=int, default=400, help='save frequency')
+    p.add_argument('--grad_clip', type=float, default=10., help='clip gradients at this value')
+    p.add_argument('--learning_rate', type=float, default=0.005, help='learning rate')
+    p.add_argument('--decay_rate', type=float, default=0.95, help='decay rate for rmsprop')
+    p.add_argument('--keep_prob', type=float, default=0.8, help='dropout keep probability')
+    p.add_argument('--embedding_size', type=int, default=64, help='Embedding dimension for the spatial coordinates')
+    p.add_argument('--neighborhood_size', type=int, default=32, help='Neighborhood size to be considered for social grid')
+    p.add_argument('--grid_size', type=int, default=4, help='Grid size of the social grid')
+    p.add_argument('--max_num_obj', type=int, default=60, help='Maximum Number of Moving objects')
+    p.add_argument('--leave_dataset', type=int, default=5, help='The dataset index to be left out in training')
+    p.add_argument('--latent_size', type=int, default=128, help='The latent size for CVAE')
+    p.add_argument('--e_dim', type=int, default=256, help="The encoder's output dimension")
+    p.add_argument('--d_dim', type=int, default=16, help="The decoder's output dimension")
+    p.add_argument('--stride', type=int, default=1, help='Stride size for the Temporal Convolution')
+    # ---- added
+    p.add_argument('--pred_length', type=int, default=12, help='T_f, future frames to predict (D2)')
+    p.add_argument('--num_samples', type=int, default=20, help='K, CVAE samples per agent (D1)')
+    p.add_argument('--ioc_iters', type=int, default=2, help='IOC ranking/refinement iterations (D11)')
+    p.add_argument('--scene_size', type=int, default=256, help='scene image side fed to the scene CNN (D11)')
+    p.add_argument('--data_dir', type=str, default='data/', help='directory holding <scene>/<video>/annotations_processed.csv')
+    p.add_argument('--save_dir', type=str, default='save', help='checkpoint / config directory (reference: save/)')
+    p.add_argument('--clip_objects', action='store_true', help='keep the first max_num_obj objects of crowded frames instead of raising')
+    p.add_argument('--norm_w', type=float, default=0.0, help='divide x by this (0 = raw pixels as in the reference)')
+    p.add_argument('--norm_h', type=float, default=0.0, help='divide y by this')
+    p.add_argument('--max_batches', type=int, default=0, help='stop an epoch after this many batches (0 = all)')
+    p.add_argument('--seed', type=int, default=1)
+    p.add_argument('--device', type=str, default='cuda:0')
+    return p
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    train(args)
+
+
+def train(args):
+    from desire_b200.model.model import DESIREModel
+    from desire_b200.utils.data_loader import DataLoader
+    import torch
+
+    norm = (args.norm_w, args.norm_h) if args.norm_w > 0 and args.norm_h > 0 else None
+    data_loader = DataLoader(args.batch_size, args.seq_length, args.max_num_obj, args.leave_dataset, preprocess=False,
+                             data_dir=args.data_dir, pred_length=args.pred_length, clip=args.clip_objects,
+                             normalize=norm)
+    os.makedirs(args.save_dir, exist_ok=True)
+    with open(os.path.join(args.save_dir, 'config.pkl'), 'wb') as fh:     # train.py:102-103
+        pickle.dump(args, fh)
+
+    model = DESIREModel(args, device=args.device, seed=args.seed)
+    losses = []
+    for epoch in range(args.num_epochs):
+        model.learning_rate = args.learning_rate * (args.decay_rate ** epoch)   # train.py:122-126
+        data_loader.reset_batch_pointer()
+        nb = data_loader.num_batches if not args.max_batches else min(args.max_batches, data_loader.num_batches)
+        for batch in range(nb):
+            start = time.time()
+            xval, yval, dval = data_loader.next_batch()
+            x = DataLoader.to_model_layout(xval)         # [B,N,Tp,3] agent-major (the transpose train.py:158-173 forgot)
+            y = DataLoader.to_model_layout(yval)
+            out = model.forward(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch)
+            loss_batch = float(out["cost"])              # masked mean over existing agents (model.py:351-376)
+            torch.cuda.synchronize()
+            end = time.time()
+            losses.append(loss_batch)
+            step = epoch * data_loader.num_batches + batch
+            print("{}/{} (epoch {}), train_loss = {:.3f}, time/batch = {:.3f}"
+                  .format(step, args.num_epochs * data_loader.num_batches, epoch, loss_batch, end - start))
+            sys.stdout.flush()
+            if step % args.save_every == 0 and step > 0:                  # train.py:197-207
+                checkpoint_path = os.path.join(args.save_dir, 'social_model.ckpt')
+                torch.save({k: v.cpu() for k, v in model.weights.items()}, "%s-%d" % (checkpoint_path, step))
+                print("model saved to {}".format(checkpoint_path))
+                sys.stdout.flush()
+    return losses
+
+
+if __name__ == '__main__':
+    main()
