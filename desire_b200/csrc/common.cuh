@@ -224,6 +224,10 @@ int deconv_tc(const float* X, int R, int Hin, int Hout, int Cin, int Cout, int k
               const float* bias, const float* gamma, const float* beta, int act, float* Y, void* pack_ws,
               cudaStream_t st);
 
+bool deconv1c_tc_eligible();
+int deconv1c_tc(const float* X, int R, const float* W, const float* bias, const float* gamma, const float* beta, int act,
+                float* Y, void* pack_ws, cudaStream_t st);
+
 // col2im + bias + per-row BN + activation (cvae.cu): col [R*Hin*Hin, k*k*Cout] -> out [R,Hout,Hout,Cout]
 int colbn_act(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int Cout,
               const float* bias, const float* gamma, const float* beta, int act, float* out,

@@ -345,13 +345,20 @@ extern "C" int desire_cvae_encode_fwd(const float* v, int M, int Z, const desire
 }
 
 // ------------------------------------------------------------------------------------------ decoder
-static const int DEC_CHUNK = 4096;
+// Rows per pass.  With the fused deconv kernels the only col matrix left is deconv1's [rows, 2048], so the whole
+// batch goes through in one pass (fewer launches, no per-chunk tails); the unfused fallback (gemm mode 0) keeps
+// 4096-row chunks because its deconv3 col matrix is 205 KB per row.
+static const int DEC_CHUNK_FUSED = 65536, DEC_CHUNK_COL = 4096;
+static size_t dec_ws_bytes(size_t rc, size_t col_per_row) {
+  return align_up(rc * col_per_row * 4) + align_up(rc * 2048 * 4) + align_up(rc * 4096 * 4) + align_up(rc * 8192 * 4) +
+         PACK_WS_BYTES;
+}
 
 extern "C" size_t desire_cvae_decode_workspace_bytes(int R, int Z) {
   (void)Z;
-  size_t rc = R < DEC_CHUNK ? R : DEC_CHUNK;
-  // col (<= rc*64*800) + a1 (rc*2048) + a2 (rc*4096) + a3 (rc*8192)
-  return align_up(rc * 51200 * 4) + align_up(rc * 2048 * 4) + align_up(rc * 4096 * 4) + align_up(rc * 8192 * 4) + PACK_WS_BYTES;
+  const size_t a = dec_ws_bytes(R < DEC_CHUNK_FUSED ? R : DEC_CHUNK_FUSED, 2048);
+  const size_t b = dec_ws_bytes(R < DEC_CHUNK_COL ? R : DEC_CHUNK_COL, 51200);
+  return a > b ? a : b;
 }
 
 extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire_cvae_dec_t* w, float* xr, void* ws,
@@ -362,10 +369,12 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
     return DESIRE_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const bool fused = gemm_mode() != 0;     // deconv2/3 run fused (their eligibility only depends on the mode here)
+  const int DEC_CHUNK = fused ? DEC_CHUNK_FUSED : DEC_CHUNK_COL;
   for (int r0 = 0; r0 < R; r0 += DEC_CHUNK) {
     const int rc = (R - r0) < DEC_CHUNK ? (R - r0) : DEC_CHUNK;
     Workspace W(ws, ws_bytes);
-    float* col = W.take<float>((size_t)rc * 51200);
+    float* col = W.take<float>((size_t)rc * (fused ? 2048 : 51200));
     float* a1 = W.take<float>((size_t)rc * 2048);
     float* a2 = W.take<float>((size_t)rc * 4096);
     float* a3 = W.take<float>((size_t)rc * 8192);
@@ -403,14 +412,21 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
       DESIRE_TRY(colbn_act(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st));
     }
-    // deconv5/2 SAME 16x16x32 -> 32x32x1, BN + sigmoid: direct kernel (no GEMM, no col matrix)
+    // deconv5/2 SAME 16x16x32 -> 32x32x1, BN + sigmoid: tiny-N tcgen05 kernel with in-kernel col2im + BN
+    // (CUDA-core direct kernel when tensor cores are off)
     {
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
-      const size_t smem4 = ((size_t)256 * 36 + 25 * 32 + 32) * sizeof(float);
-      DESIRE_ENSURE_SMEM((deconv1ch_bn_act_kernel<32, 5, 2>), smem4);
-      DESIRE_LAUNCH(st, (deconv1ch_bn_act_kernel<32, 5, 2><<<rc, 256, smem4, st>>>(a3, 16, 32, 1, w->d4.w, w->d4.b, w->d4.gamma,
-                                                                                w->d4.beta, DESIRE_ACT_SIGMOID,
-                                                                                xr + (size_t)r0 * 1024)));
+      if (deconv1c_tc_eligible()) {
+        DESIRE_TRY(deconv1c_tc(a3, rc, w->d4.w, w->d4.b, w->d4.gamma, w->d4.beta, DESIRE_ACT_SIGMOID,
+                               xr + (size_t)r0 * 1024, pw.p, st));
+      } else {
+        const size_t smem4 = ((size_t)256 * 36 + 25 * 32 + 32) * sizeof(float);
+        DESIRE_ENSURE_SMEM((deconv1ch_bn_act_kernel<32, 5, 2>), smem4);
+        DESIRE_LAUNCH(st, (deconv1ch_bn_act_kernel<32, 5, 2><<<rc, 256, smem4, st>>>(a3, 16, 32, 1, w->d4.w, w->d4.b,
+                                                                                  w->d4.gamma, w->d4.beta,
+                                                                                  DESIRE_ACT_SIGMOID,
+                                                                                  xr + (size_t)r0 * 1024)));
+      }
     }
   }
   return DESIRE_OK;

@@ -16,7 +16,7 @@
 namespace desire {
 namespace {
 
-constexpr int RM = 4;    // rows per thread
+constexpr int RM = 4;    // rows per thread (the vector width of the k-major state tile)
 constexpr int BKW = 16;  // weight rows per smem chunk
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -210,7 +210,8 @@ int gru_seq(const GruSeqArgs& a, cudaStream_t st, PackWs pw) {
   DESIRE_CHECK_ARG((a.xp != nullptr) != (a.traj != nullptr), "gru: exactly one of xp / traj");
   if (a.R == 0 || a.T == 0) return DESIRE_OK;
   const int cgn = a.H / 4;
-  const int rgn = cgn >= 256 ? 1 : 256 / cgn;
+  const int rgn = cgn >= 256 ? 1 : 256 / cgn;   // (smaller row tiles for the few-row encoders measured 3x slower:
+                                               //  fewer threads per CTA stream the same weights)
   const int BMt = rgn * RM, LD = BMt + 4;
   const int nthr = ((cgn * rgn + 31) / 32) * 32;
   size_t smem = ((size_t)(a.Ka + 2 * a.H) * LD + (size_t)BKW * 2 * a.H) * sizeof(float);
