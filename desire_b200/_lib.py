@@ -40,11 +40,27 @@ class IocW(C.Structure):
                 ("reg_w", C.c_void_p), ("reg_b", C.c_void_p), ("r2_edges", C.c_void_p), ("dirs", C.c_void_p)]
 
 
+class GruG(C.Structure):
+    _fields_ = [("wg", C.c_void_p), ("bg", C.c_void_p), ("wc", C.c_void_p), ("bc", C.c_void_p)]
+
+
+class ConvBnG(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p)]
+
+
+class CvaeEncG(C.Structure):
+    _fields_ = [("c1", ConvBnG), ("c2", ConvBnG), ("c3", ConvBnG), ("fc_w", C.c_void_p), ("fc_b", C.c_void_p)]
+
+
+class CvaeDecG(C.Structure):
+    _fields_ = [("d1", ConvBnG), ("d2", ConvBnG), ("d3", ConvBnG), ("d4", ConvBnG)]
+
+
 class IocDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "N", "K", "H", "Tf", "C", "Fv", "Cs", "n_rad", "n_ang", "Hm", "Wm", "iters")]
 
 
-P, I, L, Z = C.c_void_p, C.c_int, C.c_long, C.c_size_t
+P, I, L, Z, F = C.c_void_p, C.c_int, C.c_long, C.c_size_t, C.c_float
 
 # name -> (restype, argtypes); the single source of truth the ABI test checks against the header
 SIGNATURES = {
@@ -79,6 +95,23 @@ SIGNATURES = {
     "desire_social_pool_fwd": (I, [P, L, P, I, P, I, I, I, I, I, I, I, P, P, P, P]),
     "desire_ioc_workspace_bytes": (Z, [C.POINTER(IocDims)]),
     "desire_ioc_fwd": (I, [C.POINTER(IocDims), C.POINTER(IocW), P, P, I, P, I, P, P, P, P, Z, P]),
+    # ---- train step
+    "desire_cost_bwd": (I, [P, P, P, P, P, I, I, I, I, I, P, P, P]),
+    "desire_readout_bwd": (I, [P, P, I, I, I, P, P, P, P, P]),
+    "desire_gru_decode_bwd_workspace_bytes": (Z, [I, I]),
+    "desire_gru_decode_bwd": (I, [P, P, I, I, I, I, I, C.POINTER(GruW), P, P, P, P, I, C.POINTER(GruG), P, Z, P]),
+    "desire_mask_softmax_bwd_workspace_bytes": (Z, [I, I]),
+    "desire_mask_softmax_bwd": (I, [P, I, I, I, I, P, P, P, I, P, P, P, I, P, P, P, Z, P]),
+    "desire_cvae_decode_bwd_workspace_bytes": (Z, [I, I]),
+    "desire_cvae_decode_bwd": (I, [P, I, I, C.POINTER(CvaeDecW), P, P, C.POINTER(CvaeDecG), P, Z, P]),
+    "desire_reparam_bwd": (I, [P, P, P, I, I, I, P, P]),
+    "desire_cvae_encode_bwd_workspace_bytes": (Z, [I, I]),
+    "desire_cvae_encode_bwd": (I, [P, I, I, C.POINTER(CvaeEncW), P, P, C.POINTER(CvaeEncG), P, Z, P]),
+    "desire_fc_bwd": (I, [P, I, P, I, P, I, P, I, I, I, I, I, P, I, I, P, I, P, P]),
+    "desire_gru_encode_bwd_workspace_bytes": (Z, [I, I, I]),
+    "desire_gru_encode_bwd": (I, [P, I, I, I, C.POINTER(GruW), P, I, C.POINTER(GruG), P, Z, P]),
+    "desire_sumsq_fwd": (I, [P, L, P, I, P]),
+    "desire_adam_step": (I, [P, P, P, P, L, P, F, F, F, F, I, F, F, P]),
 }
 
 _lib = None

@@ -150,6 +150,12 @@ int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const 
           int ldc, int M, int N, int K, int act, bool accumulate, cudaStream_t st, PackWs pw = PackWs());
 int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const float* bias, float* C,
                  int ldc, int M, int N, int K, int act, cudaStream_t st, PackWs pw = PackWs());
+// train step (gemm_f32.cu): dW[Kd,N] (ldw) += A^T @ B over M rows, A dense or implicit im2col; column sums
+int wgrad_tn(const float* A, int lda, const float* B, int ldb, float* dW, int ldw, int M, int Kd, int N,
+             cudaStream_t st);
+int wgrad_tn_im2col(const float* X, const Im2col& g, const float* B, int ldb, float* dW, int ldw, int M, int Kd,
+                    int N, cudaStream_t st);
+int colsum_acc(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
 int gemm_mode();
 // A weight packed ONCE for many GEMM calls (IOC loop): pack_weight() fills `packed` when the tensor-core
 // path will be used; gemm_packed() then skips the per-call packing.

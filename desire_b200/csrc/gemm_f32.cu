@@ -129,6 +129,105 @@ int launch(const L& a, const float* B, int ldb, bool trans_b, const float* bias,
   return DESIRE_OK;
 }
 
+
+// ---- weight-gradient GEMM (train step): dW[Kd,N] += sum_m A(m,kd) * B[m,n], FP32 CUDA cores.
+// The reduction runs over the ROWS (up to millions), so the grid splits them (blockIdx.z) and the
+// partial tiles are added with atomicAdd (the caller zeroes dW once per step).  Loads are coalesced
+// along kd / n; A comes through the same loaders as the forward GEMM (dense rows or implicit im2col).
+constexpr int WBM = 128, WBN = 64, WBK = 16;
+template <class ALoader>
+__global__ void __launch_bounds__(NT) wgrad_tn_kernel(ALoader A, const float* __restrict__ B, int ldb,
+                                                      float* __restrict__ dW, int ldw, int M, int Kd, int N,
+                                                      int rows_per_split) {
+  __shared__ __align__(16) float As[WBK][WBM + 4];
+  __shared__ __align__(16) float Bs[WBK][WBN];
+  const int tid = threadIdx.x;
+  const int k_blk = blockIdx.y * WBM, n_blk = blockIdx.x * WBN;
+  const int ty = tid / 16, tx = tid % 16;
+  const long m_begin = (long)blockIdx.z * rows_per_split;
+  const long m_end = (m_begin + rows_per_split < M) ? m_begin + rows_per_split : M;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long m0 = m_begin; m0 < m_end; m0 += WBK) {
+    {
+      const int kd = tid % WBM, r0 = tid / WBM;          // 2 rows per pass
+#pragma unroll
+      for (int i = 0; i < WBK / (NT / WBM); ++i) {
+        const int r = r0 + i * (NT / WBM);
+        const long m = m0 + r;
+        As[r][kd] = (m < m_end) ? A((int)m, k_blk + kd) : 0.f;
+      }
+    }
+    {
+      const int n = tid % WBN, r0 = tid / WBN;           // 4 rows per pass
+#pragma unroll
+      for (int i = 0; i < WBK / (NT / WBN); ++i) {
+        const int r = r0 + i * (NT / WBN);
+        const long m = m0 + r;
+        const int gn = n_blk + n;
+        Bs[r][n] = (m < m_end && gn < N) ? __ldg(B + (size_t)m * ldb + gn) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WBK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int kd = k_blk + ty * 8 + i;
+    if (kd >= Kd) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n_blk + tx * 4 + j;
+      if (n < N) atomicAdd(dW + (size_t)kd * ldw + n, acc[i][j]);
+    }
+  }
+}
+
+template <class L>
+int launch_wgrad(const L& a, const float* B, int ldb, float* dW, int ldw, int M, int Kd, int N, cudaStream_t st) {
+  if (M == 0 || N == 0 || Kd == 0) return DESIRE_OK;
+  const int gx = (N + WBN - 1) / WBN, gy = (Kd + WBM - 1) / WBM;
+  // ~4 CTAs per SM in flight; every split at least 256 rows
+  int splits = (148 * 4 + gx * gy - 1) / (gx * gy);
+  const int max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  int rows = (M + splits - 1) / splits;
+  rows = (rows + WBK - 1) / WBK * WBK;
+  splits = (M + rows - 1) / rows;
+  dim3 grid(gx, gy, splits);
+  DESIRE_LAUNCH(st, (wgrad_tn_kernel<L><<<grid, NT, 0, st>>>(a, B, ldb, dW, ldw, M, Kd, N, rows)));
+  return DESIRE_OK;
+}
+
+// out[n] += sum_m A[m, n]
+__global__ void colsum_kernel(const float* __restrict__ A, int lda, int M, int N, int rows_per_block,
+                              float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long m0 = (long)blockIdx.y * rows_per_block;
+  const long m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  float s = 0.f;
+  for (long m = m0; m < m1; ++m) s += __ldg(A + (size_t)m * lda + n);
+  atomicAdd(out + n, s);
+}
+
 }  // namespace
 
 int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const float* bias, float* C, int ldc,
@@ -152,6 +251,34 @@ int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const
   DESIRE_CHECK_ARG((M + BM - 1) / BM <= 65535, "sgemm_im2col: M=%d too large", M);
   Im2colA a{X, g, M, K};
   return launch(a, B, ldb, false, bias, C, ldc, M, N, K, act, false, st);
+}
+
+
+int wgrad_tn(const float* A, int lda, const float* B, int ldb, float* dW, int ldw, int M, int Kd, int N,
+             cudaStream_t st) {
+  DenseA a{A, lda, M, Kd};
+  return launch_wgrad(a, B, ldb, dW, ldw, M, Kd, N, st);
+}
+
+int wgrad_tn_im2col(const float* X, const Im2col& g, const float* B, int ldb, float* dW, int ldw, int M, int Kd,
+                    int N, cudaStream_t st) {
+  Im2colA a{X, g, M, Kd};
+  return launch_wgrad(a, B, ldb, dW, ldw, M, Kd, N, st);
+}
+
+int colsum_acc(const float* A, int lda, int M, int N, float* out, cudaStream_t st) {
+  if (M == 0 || N == 0) return DESIRE_OK;
+  const int threads = N >= 128 ? 128 : 32;
+  const int gx = (N + threads - 1) / threads;
+  int gy = (148 * 8 + gx - 1) / gx;
+  const int max_gy = (M + 63) / 64;
+  if (gy > max_gy) gy = max_gy;
+  if (gy < 1) gy = 1;
+  if (gy > 65535) gy = 65535;
+  const int rows = (M + gy - 1) / gy;
+  gy = (M + rows - 1) / rows;
+  DESIRE_LAUNCH(st, (colsum_kernel<<<dim3(gx, gy), threads, 0, st>>>(A, lda, M, N, rows, out)));
+  return DESIRE_OK;
 }
 
 }  // namespace desire

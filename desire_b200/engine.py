@@ -18,6 +18,24 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+FLAT_ALIGN = 64   # floats (256 B): the kernels read weights with 128-bit loads
+
+
+def flatten_params(params: dict, device):
+    """One flat fp32 device buffer holding every tensor (each start 256-byte aligned, padding zero) and the
+    dict of views into it.  The train step all-reduces / clips / updates the flat buffer in one go."""
+    offs, n = {}, 0
+    for k, v in params.items():
+        offs[k] = (n, v.numel(), tuple(v.shape))
+        n += (v.numel() + FLAT_ALIGN - 1) // FLAT_ALIGN * FLAT_ALIGN
+    flat = torch.zeros(n, dtype=torch.float32, device=device)
+    views = {}
+    for k, (o, cnt, shp) in offs.items():
+        views[k] = flat[o:o + cnt].view(shp)
+        views[k].copy_(params[k])
+    return flat, views, offs
+
+
 class HotPath:
     """Sample generation (a2-a13) + IOC ranking/refinement (a14) for a fixed batch of B scenes."""
 
@@ -27,6 +45,7 @@ class HotPath:
         if self.device.type != "cuda":
             raise _lib.DesireError("the DESIRE hot path only runs on a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
+        # tensors already on the device (e.g. views of DESIREModel's flat buffer) are used in place
         self.P = {k: v.to(self.device, torch.float32).contiguous() for k, v in params.items()}
         r2, dirs = logpolar_tables(cfg)
         self.r2_edges, self.dirs = r2.to(self.device), dirs.to(self.device)
@@ -151,3 +170,137 @@ class HotPath:
         out["cost"] = b["cost"][0]
         out["ioc_scores"] = b["ioc_scores"][:cfg.ioc_iters]
         return out
+
+
+class TrainPath(HotPath):
+    """Forward (sample generation) + backward of `cost` + clip_by_global_norm + Adam for a fixed batch of B
+    scenes (model/model.py:388-394).  `flat` is the flat parameter buffer `params` are views of
+    (flatten_params); gradients and the Adam moments live in flat buffers of the same layout, so the
+    multi-GPU step is ONE all-reduce of `grad_flat`."""
+
+    def __init__(self, cfg: DesireConfig, flat: torch.Tensor, params: dict, offsets: dict, B: int, device="cuda:0"):
+        super().__init__(cfg, params, B, device)
+        for k, (o, cnt, shp) in offsets.items():
+            if self.P[k].data_ptr() != flat.data_ptr() + 4 * o:
+                raise ValueError("parameter %s is not a view of the flat buffer" % k)
+        self.flat, self.offsets = flat, offsets
+        self.grad_flat = torch.zeros_like(flat)
+        self.G = {k: self.grad_flat[o:o + cnt].view(shp) for k, (o, cnt, shp) in offsets.items()}
+        self.adam_m, self.adam_v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.count = torch.ones(1, dtype=torch.float32, device=self.device)
+        self.step_no = 0
+        N, K, H, Zl, Tf = cfg.max_num_obj, cfg.K, cfg.H, cfg.Z, cfg.pred_length
+        M, R, S2 = self.M, self.R, cfg.S * cfg.S
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+        self.dbuf = dict(dYhat=f(R, Tf, 2), dhs=f(R, Tf, H), dx_z=f(R, H), dxr=f(R, S2), dz=f(R, Zl),
+                         d_mu_logvar=f(M, 2 * Zl), dv=f(M, S2), dHxHy=f(M, 2 * H))
+        G = self.G
+        gru = lambda n: _lib.GruG(*[G[n + s].data_ptr() for s in ("_wg", "_bg", "_wc", "_bc")])
+        cbn = lambda n: _lib.ConvBnG(*[G[n + s].data_ptr() for s in ("_w", "_b", "_g", "_be")])
+        self.g_encx, self.g_ency, self.g_dec1 = gru("encx"), gru("ency"), gru("dec1")
+        self.g_venc = _lib.CvaeEncG(cbn("venc_c1"), cbn("venc_c2"), cbn("venc_c3"),
+                                    G["venc_fc_w"].data_ptr(), G["venc_fc_b"].data_ptr())
+        self.g_vdec = _lib.CvaeDecG(cbn("vdec_d1"), cbn("vdec_d2"), cbn("vdec_d3"), cbn("vdec_d4"))
+        lib = self.lib
+        bws = max(lib.desire_gru_decode_bwd_workspace_bytes(R, H), lib.desire_mask_softmax_bwd_workspace_bytes(R, H),
+                  lib.desire_cvae_decode_bwd_workspace_bytes(R, Zl), lib.desire_cvae_encode_bwd_workspace_bytes(M, Zl),
+                  lib.desire_gru_encode_bwd_workspace_bytes(M, max(cfg.seq_length, Tf), H))
+        if bws > self.ws_bytes:
+            self.ws_bytes = bws
+            self.ws = torch.empty(bws, dtype=torch.uint8, device=self.device)
+        self.train_graph = None
+
+    def set_count(self, obs):
+        """Number of existing agents (id != 0, D8) of this rank's scenes, summed over ranks: the normaliser of
+        `cost` (model/model.py:376) every rank must share."""
+        import torch.distributed as dist
+        self.count.copy_((obs[:, :, 0, 0] != 0).sum().to(torch.float32).reshape(1))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.count, op=dist.ReduceOp.SUM)
+        return self.count
+
+    def backward(self, obs, tgt, eps):
+        """Gradients of `cost` w.r.t. every parameter into grad_flat (zeroed here).  Call after run(); uses
+        self.count as the normaliser."""
+        cfg, lib, b, d, P, G = self.cfg, self.lib, self.buf, self.dbuf, self.P, self.G
+        N, K, H, Zl, Tp, Tf = cfg.max_num_obj, cfg.K, cfg.H, cfg.Z, cfg.seq_length, cfg.pred_length
+        M, R, S2 = self.M, self.R, cfg.S * cfg.S
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        ws, wsb = _p(self.ws), self.ws_bytes
+        ck = _lib.check
+        self.grad_flat.zero_()
+        d["dHxHy"].zero_()
+        ck(lib.desire_cost_bwd(_p(b["Yhat"]), _p(tgt), _p(b["mu_logvar"]), _p(obs), _p(self.count), M, K, Tf, Tp, Zl,
+                               _p(d["dYhat"]), _p(d["d_mu_logvar"]), st), "cost_bwd")
+        ck(lib.desire_readout_bwd(_p(b["output_states"]), _p(d["dYhat"]), R, Tf, H, _p(P["output_w"]), _p(d["dhs"]),
+                                  _p(G["output_w"]), _p(G["output_b"]), st), "readout_bwd")
+        ck(lib.desire_gru_decode_bwd(_p(b["x_z"]), _p(b["HxHy"]), 2 * H, R, K, H, Tf, C.byref(self.w_dec1),
+                                     _p(b["output_states"]), _p(d["dhs"]), _p(d["dx_z"]), _p(d["dHxHy"]), 2 * H,
+                                     C.byref(self.g_dec1), ws, wsb, st), "gru_decode_bwd")
+        ck(lib.desire_mask_softmax_bwd(_p(b["x_reconstr_mean"]), R, S2, H, K, _p(P["w_post_vae"]), _p(P["b_post_vae"]),
+                                       _p(b["HxHy"]), 2 * H, _p(d["dx_z"]), _p(d["dxr"]), _p(d["dHxHy"]), 2 * H,
+                                       _p(G["w_post_vae"]), _p(G["b_post_vae"]), ws, wsb, st), "mask_softmax_bwd")
+        ck(lib.desire_cvae_decode_bwd(_p(b["zval"]), R, Zl, C.byref(self.w_vdec), _p(d["dxr"]), _p(d["dz"]),
+                                      C.byref(self.g_vdec), ws, wsb, st), "cvae_decode_bwd")
+        ck(lib.desire_reparam_bwd(_p(b["mu_logvar"]), _p(eps), _p(d["dz"]), M, K, Zl, _p(d["d_mu_logvar"]), st), "reparam_bwd")
+        ck(lib.desire_cvae_encode_bwd(_p(b["vae_inputs"]), M, Zl, C.byref(self.w_venc), _p(d["d_mu_logvar"]), _p(d["dv"]),
+                                      C.byref(self.g_venc), ws, wsb, st), "cvae_encode_bwd")
+        ck(lib.desire_fc_bwd(_p(b["HxHy"]), 2 * H, _p(P["w_hidden_enc1"]), S2, _p(b["vae_inputs"]), S2, _p(d["dv"]), S2,
+                             M, S2, 2 * H, 1, _p(d["dHxHy"]), 2 * H, 1, _p(G["w_hidden_enc1"]), S2,
+                             _p(G["b_hidden_enc1"]), st), "fc_c_bwd")
+        ck(lib.desire_gru_encode_bwd(_p(obs), M, Tp, H, C.byref(self.w_encx), _p(d["dHxHy"]), 2 * H,
+                                     C.byref(self.g_encx), ws, wsb, st), "gru_encode_x_bwd")
+        ck(lib.desire_gru_encode_bwd(_p(tgt), M, Tf, H, C.byref(self.w_ency),
+                                     C.c_void_p(d["dHxHy"].data_ptr() + 4 * H), 2 * H,
+                                     C.byref(self.g_ency), ws, wsb, st), "gru_encode_y_bwd")
+        return self.G
+
+    def apply(self, lr, clip=10.0, beta1=0.9, beta2=0.999, eps=1e-8):
+        """All-reduce (sum) of the flat gradient over ranks, clip_by_global_norm, Adam."""
+        import torch.distributed as dist
+        lib = self.lib
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM)
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        n = self.flat.numel()
+        self.step_no += 1
+        _lib.check(lib.desire_sumsq_fwd(_p(self.grad_flat), n, _p(self.sumsq), 0, st), "sumsq")
+        _lib.check(lib.desire_adam_step(_p(self.flat), _p(self.grad_flat), _p(self.adam_m), _p(self.adam_v), n,
+                                        _p(self.sumsq), lr, beta1, beta2, eps, self.step_no, clip, 1.0, st), "adam")
+
+    def capture_train(self, obs, tgt, eps, scene):
+        """Capture forward (generate stage) + backward into one CUDA graph over static inputs."""
+        self.static_in = [t.clone() for t in (obs, tgt, eps, scene)]
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.run(*self.static_in, stages=("generate",))
+                self.backward(*self.static_in[:3])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(*self.static_in, stages=("generate",))
+            self.backward(*self.static_in[:3])
+        self.train_graph = g
+        return g
+
+    def train_step(self, obs, tgt, eps, scene, lr, clip=10.0, use_graph=True):
+        """One optimiser step on this rank's scenes.  Returns the (local) cost tensor [cost, count]."""
+        if use_graph:
+            if self.train_graph is None:
+                self.set_count(obs)
+                self.capture_train(obs, tgt, eps, scene)
+            for dst, src in zip(self.static_in, (obs, tgt, eps, scene)):
+                if src is not None and src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            self.set_count(self.static_in[0])
+            self.train_graph.replay()
+        else:
+            self.set_count(obs)
+            self.run(obs, tgt, eps, scene, stages=("generate",))
+            self.backward(obs, tgt, eps)
+        self.apply(lr, clip)
+        return self.buf["cost"]

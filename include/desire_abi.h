@@ -207,6 +207,77 @@ int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w, const floa
                    int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores,
                    void* ws, size_t ws_bytes, desire_stream_t stream);
 
+/* ======================================================================================================
+ * Train step (SURVEY 8.0 D9, 8.b "*_bwd twins"): gradients of `cost` (model/model.py:374-376) with respect
+ * to every trainable variable — what tf.gradients(self.cost, tvars) at model/model.py:388-391 would return —
+ * then clip_by_global_norm (:391) and Adam (:394).  Conventions:
+ *   - d<name> arguments mirror the forward tensors; PARAMETER gradients are ACCUMULATED (+=, atomics) so the
+ *     caller zeroes its flat gradient buffer once per step; activation gradients are overwritten unless the
+ *     comment says "+=";
+ *   - every backward recomputes the forward intermediates it needs (pre-BN activations, gates) into the
+ *     workspace; nothing is cached between the forward and backward calls;
+ *   - conv/deconv biases that sit in front of a batch-norm have an identically zero gradient (BN removes
+ *     any per-channel constant), so those bias gradients are left untouched (= 0).
+ */
+typedef struct { float *wg, *bg, *wc, *bc; } desire_gru_grad_t;
+typedef struct { float *w, *b, *gamma, *beta; } desire_convbn_grad_t;
+typedef struct { desire_convbn_grad_t c1, c2, c3; float *fc_w, *fc_b; } desire_cvae_enc_grad_t;
+typedef struct { desire_convbn_grad_t d1, d2, d3, d4; } desire_cvae_dec_grad_t;
+
+/* a12/a13/D7 backward.  count = device pointer to the (global) number of existing agents (cost[1] of
+ * desire_masked_cost_fwd, all-reduced by the caller when scenes are sharded over ranks).
+ * dYhat [R,T,2] = d cost / d Yhat;  d_mu_logvar [M,2Z] = KLD part (overwritten). */
+int desire_cost_bwd(const float* Yhat, const float* target, const float* mu_logvar, const float* obs,
+                    const float* count, int M, int K, int T, int Tp, int Z, float* dYhat, float* d_mu_logvar,
+                    desire_stream_t stream);
+/* a11 (linear read-out) backward: dhs [R,T,H] = dYhat @ out_w^T (overwritten); d_out_w [H,2], d_out_b [2] += */
+int desire_readout_bwd(const float* hs, const float* dYhat, int R, int T, int H, const float* out_w, float* dhs,
+                       float* d_out_w, float* d_out_b, desire_stream_t stream);
+/* a10 backward through time.  dhs [R,T,H]: in = gradient reaching every state from the read-out, clobbered.
+ * dx_z [R,H] overwritten; dHx (row m, stride ld_dhx) += sum_k d h0. */
+size_t desire_gru_decode_bwd_workspace_bytes(int R, int H);
+int desire_gru_decode_bwd(const float* x_z, const float* Hx, int ld_hx, int R, int K, int H, int T,
+                          const desire_gru_t* w, const float* hs, float* dhs, float* dx_z, float* dHx,
+                          int ld_dhx, const desire_gru_grad_t* g, void* ws, size_t ws_bytes,
+                          desire_stream_t stream);
+/* a9 backward: dxr [R,S2] overwritten; dHx += ; dw [S2,H], db [H] += */
+size_t desire_mask_softmax_bwd_workspace_bytes(int R, int H);
+int desire_mask_softmax_bwd(const float* xr, int R, int S2, int H, int K, const float* w, const float* b,
+                            const float* Hx, int ld_hx, const float* dx_z, float* dxr, float* dHx, int ld_dhx,
+                            float* dw, float* db, void* ws, size_t ws_bytes, desire_stream_t stream);
+/* a8 backward: dz [R,Z] overwritten */
+size_t desire_cvae_decode_bwd_workspace_bytes(int R, int Z);
+int desire_cvae_decode_bwd(const float* z, int R, int Z, const desire_cvae_dec_t* w, const float* dxr, float* dz,
+                           const desire_cvae_dec_grad_t* g, void* ws, size_t ws_bytes, desire_stream_t stream);
+/* a7 backward: d_mu_logvar [M,2Z] += (sum_k dz, sum_k dz*eps*0.5*sqrt(exp(logvar))) */
+int desire_reparam_bwd(const float* mu_logvar, const float* eps, const float* dz, int M, int K, int Z,
+                       float* d_mu_logvar, desire_stream_t stream);
+/* a6 backward: dv [M,1024] overwritten */
+size_t desire_cvae_encode_bwd_workspace_bytes(int M, int Z);
+int desire_cvae_encode_bwd(const float* v, int M, int Z, const desire_cvae_enc_t* w, const float* d_mu_logvar,
+                           float* dv, const desire_cvae_enc_grad_t* g, void* ws, size_t ws_bytes,
+                           desire_stream_t stream);
+/* dense layer backward (a5 fc_c and friends): Cout = act(A@W+b) as produced by desire_fc_fwd; dC is
+ * clobbered (becomes the pre-activation gradient).  dA (ldda) is overwritten, or += when accumulate_dA;
+ * dA may be NULL.  dW [K,N] (lddw), db [N] +=. */
+int desire_fc_bwd(const float* A, int lda, const float* W, int ldw, const float* Cout, int ldc, float* dC,
+                  int lddc, int M, int N, int K, int act, float* dA, int ldda, int accumulate_dA, float* dW,
+                  int lddw, float* db, desire_stream_t stream);
+/* a3/a4 backward through time from the gradient of the final state dh (row stride ld_dh). */
+size_t desire_gru_encode_bwd_workspace_bytes(int M, int T, int H);
+int desire_gru_encode_bwd(const float* traj, int M, int T, int H, const desire_gru_t* w, const float* dh,
+                          int ld_dh, const desire_gru_grad_t* g, void* ws, size_t ws_bytes,
+                          desire_stream_t stream);
+/* clip_by_global_norm + Adam on flat buffers (model/model.py:391-394; TF-1.x AdamOptimizer update rule):
+ *   scale = clip / max(||g||, clip);  m = b1 m + (1-b1) g s;  v = b2 v + (1-b2) (g s)^2;
+ *   p -= lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps).
+ * desire_sumsq_fwd: out[0] (+)= sum g^2 (out is zeroed first unless accumulate). grad_scale multiplies g
+ * before everything else (1/world for an averaged all-reduce, 1 otherwise).  clip <= 0 disables clipping. */
+int desire_sumsq_fwd(const float* g, long n, float* out, int accumulate, desire_stream_t stream);
+int desire_adam_step(float* p, const float* g, float* m, float* v, long n, const float* sumsq, float lr,
+                     float beta1, float beta2, float eps, int step, float clip, float grad_scale,
+                     desire_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,167 @@
+"""-m gpu: the train step (backward of `cost` + clip + Adam) through the C-ABI vs float64 autograd of the
+differentiable oracle twin (oracle/desire_oracle_torch.py) on identical seeded inputs.
+
+Tolerances (stated here): every parameter gradient and every activation gradient within 2e-3 rel-L2 of
+the float64 reference (the forward they are taken at is itself only within 1e-4 of it; measured values are
+printed and are typically 1e-5..1e-4); tensors whose true gradient is identically zero (biases in front of a
+batch-norm, the temporal conv that never reaches `cost`, stage-2 weights) must stay below 1e-6 of the largest
+gradient norm."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import np_batch, np_params, rel_l2, small_cfg
+
+pytestmark = pytest.mark.gpu
+GTOL = 2e-3
+
+SHAPES = [(48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (16, 5, 2, 1, 0), (64, 10, 5, 2, 1), (32, 40, 2, 2, 0)]
+ACT = {"dYhat": "Yhat", "dx_z": "x_z", "dxr": "x_reconstr_mean", "dz": "zval", "dv": "vae_inputs"}
+
+
+def make_train_path(cfg, B):
+    from desire_b200.config import init_params
+    from desire_b200.engine import TrainPath, flatten_params
+    flat, views, offs = flatten_params(init_params(cfg, 1), "cuda:0")
+    return TrainPath(cfg, flat, views, offs, B)
+
+
+def oracle_grads(cfg, B, missing, P=None):
+    from oracle import desire_oracle_torch as OT
+    P = np_params(cfg, dtype=np.float64) if P is None else P
+    batch = np_batch(cfg, B, n_missing=missing, dtype=np.float64)
+    Pt = OT.to_torch(P)
+    out = OT.generate_forward(Pt, dict(K=cfg.K, Z=cfg.Z), batch[0], batch[1], batch[2])
+    for k in list(ACT.values()) + ["z_mean", "z_log_sigma_sq", "H_x", "H_y"]:
+        out[k].retain_grad()
+    out["cost"].backward()
+    g = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in Pt.items()}
+    a = {k: out[k].grad.numpy() for k in list(ACT.values()) + ["z_mean", "z_log_sigma_sq", "H_x", "H_y"]}
+    # desire_fc_bwd turns dv into the PRE-activation gradient in place (dC is clobbered by contract)
+    a["vae_inputs"] = a["vae_inputs"] * (out["vae_inputs"].detach().numpy() > 0)
+    return g, a, float(out["cost"].detach())
+
+
+@pytest.mark.parametrize("H,N,K,B,missing", SHAPES)
+def test_backward_matches_autograd(H, N, K, B, missing):
+    from desire_b200.synthetic import make_batch
+    cfg = small_cfg(d_dim=H, max_num_obj=N, num_samples=K)
+    tp = make_train_path(cfg, B)
+    obs, tgt, eps, scene = [t.cuda() for t in make_batch(cfg, B, 0, missing)]
+    tp.set_count(obs)
+    tp.run(obs, tgt, eps, scene, stages=("generate",))
+    G = tp.backward(obs, tgt, eps)
+    torch.cuda.synchronize()
+    ref_g, ref_a, ref_cost = oracle_grads(cfg, B, missing)
+    assert abs(float(tp.buf["cost"][0]) - ref_cost) <= 1e-4 * abs(ref_cost)
+    bad = {}
+    # activation gradients (localise a failure to one op)
+    d = tp.dbuf
+    got_a = {ACT[k]: d[k].cpu().numpy() for k in ACT}
+    got_a["z_mean"], got_a["z_log_sigma_sq"] = d["d_mu_logvar"][:, :cfg.Z].cpu().numpy(), d["d_mu_logvar"][:, cfg.Z:].cpu().numpy()
+    got_a["H_x"], got_a["H_y"] = d["dHxHy"][:, :H].cpu().numpy(), d["dHxHy"][:, H:].cpu().numpy()
+    for k, v in got_a.items():
+        e = rel_l2(v.reshape(-1), ref_a[k].reshape(-1))
+        print("act  %-18s rel-L2 %.3e" % (k, e))
+        if not e <= GTOL:
+            bad["act:" + k] = e
+    gmax = max(float(np.linalg.norm(v)) for v in ref_g.values())
+    for k, v in G.items():
+        got, ref = v.cpu().numpy().astype(np.float64), ref_g[k]
+        nr = float(np.linalg.norm(ref))
+        if nr <= 1e-9 * gmax:
+            e = float(np.linalg.norm(got)) / gmax
+            print("grad %-18s zero-gradient tensor, |got|/gmax %.3e" % (k, e))
+            if not e <= 1e-6:
+                bad[k] = e
+            continue
+        e = rel_l2(got.reshape(-1), ref.reshape(-1))
+        print("grad %-18s rel-L2 %.3e  (|ref| %.3e)" % (k, e, nr))
+        # a one-element BN beta gradient is a sum of ~1e5 mixed-sign terms: allow an absolute floor of 1e-6 of
+        # the largest gradient norm next to the relative bound
+        if not (e <= GTOL or e * nr <= 1e-6 * gmax):
+            bad[k] = e
+    assert not bad, bad
+
+
+def test_backward_fp32_gemm_mode_agrees(lib):
+    """Same gradients with the tcgen05 GEMMs switched off (mode 0 = FP32 CUDA cores) — the in-library cross-check."""
+    from desire_b200.synthetic import make_batch
+    cfg = small_cfg(d_dim=64, max_num_obj=12, num_samples=4)
+    outs = []
+    for mode in (3, 0):
+        lib.desire_set_gemm_mode(mode)
+        try:
+            tp = make_train_path(cfg, 3)
+            batch = [t.cuda() for t in make_batch(cfg, 3, 0, 1)]
+            tp.set_count(batch[0])
+            tp.run(*batch, stages=("generate",))
+            tp.backward(*batch[:3])
+            torch.cuda.synchronize()
+            outs.append(tp.grad_flat.cpu().numpy().copy())
+        finally:
+            lib.desire_set_gemm_mode(3)
+    assert rel_l2(outs[0], outs[1]) <= 1e-3
+
+
+def test_adam_step_matches_reference(lib):
+    import ctypes as C
+    from oracle import desire_oracle_torch as OT
+    rng = np.random.default_rng(0)
+    n = 100003
+    p = rng.standard_normal(n).astype(np.float32)
+    m = np.zeros(n)
+    v = np.zeros(n)
+    dp, dm, dv = torch.tensor(p).cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    ss = torch.zeros(1, device="cuda")
+    pr = {"p": p.astype(np.float64)}
+    mr, vr = {"p": m}, {"p": v}
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for step in range(1, 5):
+        g = (rng.standard_normal(n) * (10.0 if step == 2 else 0.01)).astype(np.float32)   # step 2 is clipped
+        dg = torch.tensor(g).cuda()
+        assert lib.desire_sumsq_fwd(C.c_void_p(dg.data_ptr()), n, C.c_void_p(ss.data_ptr()), 0, st) == 0
+        assert lib.desire_adam_step(C.c_void_p(dp.data_ptr()), C.c_void_p(dg.data_ptr()), C.c_void_p(dm.data_ptr()),
+                                    C.c_void_p(dv.data_ptr()), n, C.c_void_p(ss.data_ptr()), 5e-3, 0.9, 0.999, 1e-8,
+                                    step, 10.0, 1.0, st) == 0
+        pr, mr, vr = OT.adam_reference(pr, {"p": g}, mr, vr, step, 5e-3, clip=10.0)
+        assert abs(float(ss[0]) - float((g.astype(np.float64) ** 2).sum())) <= 1e-4 * float((g.astype(np.float64) ** 2).sum())
+    torch.cuda.synchronize()
+    assert rel_l2(dp.cpu().numpy(), pr["p"]) <= 1e-6
+    assert rel_l2(dm.cpu().numpy(), mr["p"]) <= 1e-5
+    assert rel_l2(dv.cpu().numpy(), vr["p"]) <= 5e-5   # fp32 moments
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_steps_follow_the_reference_trajectory_and_reduce_cost(use_graph):
+    """Three optimiser steps on a fixed batch: the parameter update of step 1 matches autograd + the Adam
+    reference, and the cost goes down."""
+    from oracle import desire_oracle_torch as OT
+    from desire_b200.synthetic import make_batch
+    cfg = small_cfg(d_dim=32, max_num_obj=10, num_samples=4)
+    B, missing, lr = 2, 1, 1e-3
+    tp = make_train_path(cfg, B)
+    batch = [t.cuda() for t in make_batch(cfg, B, 0, missing)]
+    p0 = tp.flat.cpu().numpy().astype(np.float64).copy()
+    costs = []
+    for it in range(3):
+        c = tp.train_step(*batch, lr=lr, clip=10.0, use_graph=use_graph)
+        costs.append(float(c[0]))
+        if it == 0:
+            p1 = tp.flat.cpu().numpy().astype(np.float64).copy()
+    torch.cuda.synchronize()
+    assert costs[2] < costs[0], costs
+    ref_g, _, _ = oracle_grads(cfg, B, missing)
+    P = np_params(cfg, dtype=np.float64)
+    z = {k: np.zeros_like(v) for k, v in P.items()}
+    P1, _, _ = OT.adam_reference(P, ref_g, z, {k: np.zeros_like(v) for k, v in P.items()}, 1, lr, clip=10.0)
+    num = den = 0.0
+    for k, (o, cnt, shp) in tp.offsets.items():
+        got = (p1[o:o + cnt] - p0[o:o + cnt])
+        ref = (P1[k] - P[k]).reshape(-1)
+        big = np.abs(ref_g[k].reshape(-1)) > 1e-6          # Adam turns ANY gradient into a +-lr step; skip ~zero ones
+        num += float(((got - ref)[big] ** 2).sum())
+        den += float((ref[big] ** 2).sum())
+    e = (num / den) ** 0.5
+    print("step-1 parameter update rel-L2 vs reference: %.3e" % e)
+    assert e <= 2e-2
