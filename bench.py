@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--scene-size", type=int, default=256)
     ap.add_argument("--cpu-sample-scenes", type=int, default=1, help="scenes per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step timing block")
     ap.add_argument("--breakdown", default="", help="write the per-kernel timing table to this file")
     return ap.parse_args()
 
@@ -196,9 +197,12 @@ def slot_table(a, cfg, world_local_R):
         5: ("scene_gather", "hbm", it * R * T * (20.0 * cfg.scene_channels + 8)),
         6: ("cvae_deconv2_gemm", "tensor", R * 2.0 * 16 * 128 * 1600),
         7: ("cvae_deconv3_gemm", "tensor", R * 2.0 * 64 * 64 * 800),
-        8: ("cvae_col2im_bn_act", "hbm", R * 4.0 * (2048 + 16 * 1600 + 64 * 800 + 256 * 25 + 2048 + 4096 + 8192 + 1024)),
+        # slot 8 today = deconv1's identity col2im+BN+ELU ([R,2048] read + write) and the fused tiny-N deconv4
+        # kernel ([R,8192] read, [R,1024] write); deconv2/3 are fused into their tensor-core kernels (slots 6/7)
+        8: ("cvae_deconv1_bn_act+deconv4_fused", "hbm", R * 4.0 * (2048 + 2048 + 8192 + 1024)),
         9: ("decoder2_input_projection_gemm", "tensor", it * R * T * 2.0 * Dst * 3 * H),
-        10: ("scene_cnn", "tensor", 0.0),
+        10: ("scene_cnn", "tensor", (R / (cfg.max_num_obj * cfg.K)) * ((a.scene_size + 1) // 2) ** 2 * 2.0 *
+             (75 * 16 + 400 * 32 + 800 * cfg.scene_channels)),
         11: ("readout_feature_pool", "hbm", R * T * 4.0 * (H + 2 + 2 * cfg.channel_multiplier)),
     }
 
@@ -293,6 +297,31 @@ def ours_arm(a):
     h2d = sum(x.nbytes for x in host_np)
     d2h = y.nbytes + sc.nbytes + 8
 
+    # ---- train step (D9): forward of the sample-generation stage + backward of `cost` + all-reduce + clip + Adam,
+    # device-resident inputs, one CUDA-graph replay for forward+backward; reported next to the headline metric
+    train = None
+    if not a.no_train:
+        tp = model._train_path(B)
+        for _ in range(3):
+            tp.train_step(*dev_in, lr=1e-4, clip=10.0)
+        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        l0 = lib.desire_launch_count()
+        for s_, e_ in tev:
+            flush.zero_()
+            s_.record()
+            tp.train_step(*dev_in, lr=1e-4, clip=10.0)
+            e_.record()
+        barrier()
+        tms = torch.tensor([sum(s_.elapsed_time(e_) for s_, e_ in tev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        train = {"ms_per_step": float(tms.item()) / steps,
+                 "agent_samples_per_s": R_local * world * steps / (float(tms.item()) / 1e3),
+                 "what": "sample-generation forward + backward of cost + %sclip_by_global_norm + Adam over %d parameters"
+                         % ("NCCL all-reduce of the flat gradient + " if world > 1 else "", tp.flat.numel()),
+                 "cost_after": float(tp.buf["cost"][0])}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -347,6 +376,7 @@ def ours_arm(a):
         "roofline": roofline,
         "kernels": rows[:8],
         "cpu_baseline": cpu,
+        "train_step": train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

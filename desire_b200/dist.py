@@ -25,3 +25,24 @@ def global_masked_cost(local_sum: torch.Tensor, local_count: torch.Tensor) -> to
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return (t[0] / t[1]).float()
+
+
+def _active():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def global_count_(count: torch.Tensor) -> torch.Tensor:
+    """In-place sum over ranks of the number of existing agents — the shared normaliser of `cost`
+    (model/model.py:376) that every rank's backward divides by, so that the SUM of the per-rank gradients
+    equals the gradient of the single-GPU cost over the union of the scenes."""
+    if _active():
+        dist.all_reduce(count, op=dist.ReduceOp.SUM)
+    return count
+
+
+def all_reduce_gradients_(grad_flat: torch.Tensor) -> torch.Tensor:
+    """The train step's one collective: in-place SUM of the flat fp32 gradient buffer over ranks
+    (NCCL over NVLink on GPUs; gloo in the CPU tests).  Every rank then applies the identical clip + Adam."""
+    if _active():
+        dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM)
+    return grad_flat

@@ -214,11 +214,9 @@ class TrainPath(HotPath):
     def set_count(self, obs):
         """Number of existing agents (id != 0, D8) of this rank's scenes, summed over ranks: the normaliser of
         `cost` (model/model.py:376) every rank must share."""
-        import torch.distributed as dist
+        from .dist import global_count_
         self.count.copy_((obs[:, :, 0, 0] != 0).sum().to(torch.float32).reshape(1))
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.count, op=dist.ReduceOp.SUM)
-        return self.count
+        return global_count_(self.count)
 
     def backward(self, obs, tgt, eps):
         """Gradients of `cost` w.r.t. every parameter into grad_flat (zeroed here).  Call after run(); uses
@@ -258,10 +256,9 @@ class TrainPath(HotPath):
 
     def apply(self, lr, clip=10.0, beta1=0.9, beta2=0.999, eps=1e-8):
         """All-reduce (sum) of the flat gradient over ranks, clip_by_global_norm, Adam."""
-        import torch.distributed as dist
+        from .dist import all_reduce_gradients_
         lib = self.lib
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM)
+        all_reduce_gradients_(self.grad_flat)
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         n = self.flat.numel()
         self.step_no += 1

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from ..config import DesireConfig, init_params
-from ..engine import HotPath
+from ..engine import HotPath, TrainPath, flatten_params
 
 
 def config_from_args(args) -> DesireConfig:
@@ -55,8 +55,13 @@ class DESIREModel(object):
         self.vae_input_size = cfg.S * cfg.S
         self.max_num_obj = cfg.max_num_obj
         self.learning_rate = float(getattr(args, "learning_rate", 0.005))
-        self.weights = params if params is not None else self.define_weights(seed)
+        # every trainable tensor is a view into ONE flat device buffer (the train step clips / all-reduces /
+        # updates that buffer in one go); `weights` keeps the reference's name -> tensor dict
+        init = params if params is not None else self.define_weights(seed)
+        self.flat_weights, self.weights, self._offsets = flatten_params(init, self.device)
+        self.grad_clip = float(getattr(args, "grad_clip", 10.0))
         self._paths = {}
+        self._train_paths = {}
         self._pinned = {}
         # filled by forward(); same names as the reference's graph nodes
         self.input_data = self.target_data = self.target_data_enc = self.temporal_data = None
@@ -85,6 +90,37 @@ class DESIREModel(object):
         if B not in self._paths:
             self._paths[B] = HotPath(self.cfg, self.weights, B, self.device)
         return self._paths[B]
+
+    def _train_path(self, B) -> TrainPath:
+        if B not in self._train_paths:
+            self._train_paths[B] = TrainPath(self.cfg, self.flat_weights, self.weights, self._offsets, B, self.device)
+        return self._train_paths[B]
+
+    def train_step(self, input_data, target_data, eps=None, scene=None, seed=None):
+        """One optimiser step on a minibatch (D9): forward of the sample-generation stage, gradients of `cost`
+        (what `tf.gradients(self.cost, tvars)` builds at model/model.py:388-391), clip_by_global_norm(grad_clip)
+        and Adam(self.learning_rate) (:391-394) — the op the reference creates and never runs.  Under
+        torch.distributed the flat gradient is all-reduced (sum) and `cost` is normalised by the global number
+        of existing agents.  Returns the device tensor [cost, count] of this rank's scenes."""
+        cfg = self.cfg
+        to_dev = lambda n, x: x if (torch.is_tensor(x) and x.is_cuda) else self._stage(n, x.numpy() if torch.is_tensor(x) else x)
+        obs, tgt = to_dev("obs", input_data), to_dev("tgt", target_data)
+        B = obs.shape[0]
+        if eps is None:
+            g = torch.Generator(device=self.device)
+            g.manual_seed(2 if seed is None else seed)
+            eps = torch.randn(B * cfg.max_num_obj, cfg.K, cfg.Z, generator=g, device=self.device)
+        else:
+            eps = to_dev("eps", eps)
+        if scene is None:
+            scene = torch.zeros(B, cfg.scene_size, cfg.scene_size, 3, device=self.device)
+        else:
+            scene = to_dev("scene", scene)
+        tp = self._train_path(B)
+        cost = tp.train_step(obs, tgt, eps, scene, lr=self.learning_rate, clip=self.grad_clip, use_graph=self.use_graph)
+        self.input_data, self.target_data, self.target_data_enc, self.temporal_data = obs, tgt, tgt, obs
+        self.cost, self.final_states, self.gradients = cost[0], tp.buf["HxHy"][:, :cfg.H], tp.G
+        return cost
 
     def _stage(self, name, arr):
         """numpy -> pinned host staging buffer (reused) -> device, async on the current stream."""

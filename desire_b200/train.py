@@ -3,11 +3,12 @@
     python -m desire_b200.train --d_dim 128 --batch_size 32 --num_samples 20 ...
 
 Same 19 argparse flags with the same names and defaults (train.py:28-88) plus the knobs the build adds
-(DESIGN.md D1/D2/D11).  Like the reference — whose loop only ever evaluates `model.cost` (train.py:181; the
-optimiser op of model/model.py:394 is never run) — round 1 evaluates the hot path per minibatch:
-sample generation + IOC ranking/refinement on the GPU, the masked cost, the reference's log line, the per-epoch
-learning-rate schedule value, and a checkpoint of the weights every `save_every` steps.  The optimiser step (D9)
-arrives with the backward kernels.  Where the reference ran one sess.run per SEQUENCE
+(DESIGN.md D1/D2/D11).  The reference's loop only ever evaluates `model.cost` (train.py:181; the optimiser op of
+model/model.py:394 is created and never run).  Here every minibatch is one optimiser step (D9):
+forward + backward of `cost` + clip_by_global_norm(grad_clip) + Adam(learning_rate * decay_rate**epoch) on the GPU
+(`--optimize 0` restores the reference's evaluate-only loop, which then also runs IOC ranking/refinement), the
+reference's log line, and a checkpoint every `save_every` steps that `--resume` restores (weights + Adam moments +
+step; the restore path the reference lacks, train.py:197-207).  Where the reference ran one sess.run per SEQUENCE
 (train.py:146-181), a whole minibatch of scenes is one pass here.
 """
 from __future__ import annotations
@@ -55,6 +56,8 @@ def build_parser():
     p.add_argument('--norm_w', type=float, default=0.0, help='divide x by this (0 = raw pixels as in the reference)')
     p.add_argument('--norm_h', type=float, default=0.0, help='divide y by this')
     p.add_argument('--max_batches', type=int, default=0, help='stop an epoch after this many batches (0 = all)')
+    p.add_argument('--optimize', type=int, default=1, help='1: run the Adam step per minibatch (D9); 0: evaluate cost only, as the reference loop does')
+    p.add_argument('--resume', type=str, default='', help='checkpoint file written by a previous run to continue from')
     p.add_argument('--seed', type=int, default=1)
     p.add_argument('--device', type=str, default='cuda:0')
     return p
@@ -63,6 +66,30 @@ def build_parser():
 def main(argv=None):
     args = build_parser().parse_args(argv)
     train(args)
+
+
+def save_checkpoint(model, path, next_step):
+    """Weights by name (the reference's tf.train.Saver keeps variables by name, train.py:114,200-205) plus the
+    optimiser state of every TrainPath-independent buffer so a resumed run continues the same trajectory."""
+    import torch
+    state = {"weights": {k: v.detach().cpu() for k, v in model.weights.items()}, "next_step": int(next_step)}
+    tps = list(model._train_paths.values())
+    if tps:
+        state["adam_m"], state["adam_v"], state["adam_t"] = tps[0].adam_m.cpu(), tps[0].adam_v.cpu(), tps[0].step_no
+    torch.save(state, path)
+
+
+def load_checkpoint(model, path):
+    import torch
+    state = torch.load(path, map_location="cpu")
+    for k, v in state["weights"].items():
+        model.weights[k].copy_(v)
+    if "adam_m" in state:
+        tp = model._train_path(max(int(model.batch_size), 1))
+        tp.adam_m.copy_(state["adam_m"])
+        tp.adam_v.copy_(state["adam_v"])
+        tp.step_no = int(state["adam_t"])
+    return int(state.get("next_step", 0))
 
 
 def train(args):
@@ -79,6 +106,10 @@ def train(args):
         pickle.dump(args, fh)
 
     model = DESIREModel(args, device=args.device, seed=args.seed)
+    start_step = 0
+    if args.resume:
+        start_step = load_checkpoint(model, args.resume)
+        print("resumed from {} at step {}".format(args.resume, start_step))
     losses = []
     for epoch in range(args.num_epochs):
         model.learning_rate = args.learning_rate * (args.decay_rate ** epoch)   # train.py:122-126
@@ -89,18 +120,23 @@ def train(args):
             xval, yval, dval = data_loader.next_batch()
             x = DataLoader.to_model_layout(xval)         # [B,N,Tp,3] agent-major (the transpose train.py:158-173 forgot)
             y = DataLoader.to_model_layout(yval)
-            out = model.forward(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch)
-            loss_batch = float(out["cost"])              # masked mean over existing agents (model.py:351-376)
+            step = epoch * data_loader.num_batches + batch
+            if step < start_step:
+                continue
+            if args.optimize:
+                loss_batch = float(model.train_step(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch)[0])
+            else:
+                out = model.forward(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch)
+                loss_batch = float(out["cost"])          # masked mean over existing agents (model.py:351-376)
             torch.cuda.synchronize()
             end = time.time()
             losses.append(loss_batch)
-            step = epoch * data_loader.num_batches + batch
             print("{}/{} (epoch {}), train_loss = {:.3f}, time/batch = {:.3f}"
                   .format(step, args.num_epochs * data_loader.num_batches, epoch, loss_batch, end - start))
             sys.stdout.flush()
             if step % args.save_every == 0 and step > 0:                  # train.py:197-207
                 checkpoint_path = os.path.join(args.save_dir, 'social_model.ckpt')
-                torch.save({k: v.cpu() for k, v in model.weights.items()}, "%s-%d" % (checkpoint_path, step))
+                save_checkpoint(model, "%s-%d" % (checkpoint_path, step), step + 1)
                 print("model saved to {}".format(checkpoint_path))
                 sys.stdout.flush()
     return losses
