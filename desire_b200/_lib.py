@@ -56,6 +56,16 @@ class CvaeDecG(C.Structure):
     _fields_ = [("d1", ConvBnG), ("d2", ConvBnG), ("d3", ConvBnG), ("d4", ConvBnG)]
 
 
+class IocG(C.Structure):
+    _fields_ = [("vel_w", C.c_void_p), ("vel_b", C.c_void_p), ("sp_w", C.c_void_p), ("sp_b", C.c_void_p),
+                ("dec2", GruG), ("score_w", C.c_void_p), ("score_b", C.c_void_p),
+                ("reg_w", C.c_void_p), ("reg_b", C.c_void_p)]
+
+
+class SceneCnnG(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("c1_w", "c1_b", "c2_w", "c2_b", "c3_w", "c3_b")]
+
+
 class IocDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "N", "K", "H", "Tf", "C", "Fv", "Cs", "n_rad", "n_ang", "Hm", "Wm", "iters")]
 
@@ -110,6 +120,11 @@ SIGNATURES = {
     "desire_fc_bwd": (I, [P, I, P, I, P, I, P, I, I, I, I, I, P, I, I, P, I, P, P]),
     "desire_gru_encode_bwd_workspace_bytes": (Z, [I, I, I]),
     "desire_gru_encode_bwd": (I, [P, I, I, I, C.POINTER(GruW), P, I, C.POINTER(GruG), P, Z, P]),
+    "desire_ioc_train_workspace_bytes": (Z, [C.POINTER(IocDims)]),
+    "desire_ioc_train": (I, [C.POINTER(IocDims), C.POINTER(IocW), P, P, I, P, P, I, P, P, P, P, P, P, C.POINTER(IocG), P,
+                             P, Z, P]),
+    "desire_scene_cnn_bwd_workspace_bytes": (Z, [I, I, I]),
+    "desire_scene_cnn_bwd": (I, [P, I, I, I, I, C.POINTER(SceneCnnW), P, C.POINTER(SceneCnnG), P, Z, P]),
     "desire_sumsq_fwd": (I, [P, L, P, I, P]),
     "desire_adam_step": (I, [P, P, P, P, L, P, F, F, F, F, I, F, F, P]),
 }

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <functional>
+
 #include "../../include/desire_abi.h"
 
 namespace desire {
@@ -156,6 +158,27 @@ int wgrad_tn(const float* A, int lda, const float* B, int ldb, float* dW, int ld
 int wgrad_tn_im2col(const float* X, const Im2col& g, const float* B, int ldb, float* dW, int ldw, int M, int Kd,
                     int N, cudaStream_t st);
 int colsum_acc(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
+// train.cu: GRU backward through time over recomputed gates (shared by the encoders, Decoder-1 and Decoder-2)
+struct GruBptt {
+  int R, H, T, I;
+  const float *wg, *wc;                 // full TF-layout kernels [(I+H),2H], [(I+H),H]
+  const float* xp; long xp_rs, xp_ss;   // hoisted input projection incl. biases, [.., 3H] = (r|u|c)
+  const float* hs; long hs_rs, hs_ss;   // forward states h_t
+  const float* h0e;                     // [R,H] dense initial state
+  float* dhs; long dhs_rs, dhs_ss;      // gradient reaching h_t (in), accumulated in place
+  float* dxp; long dxp_rs, dxp_ss;      // += (zeroed by the caller)
+  float* dh0;                           // [R,H], zeroed by the caller, receives d h_{-1}
+  float *dwg, *dwc;                     // full-layout gradients (+=); only the state rows are touched here
+};
+size_t gru_bptt_ws_bytes(size_t R, int H);
+// after_step(t) runs on the host right after step t's kernels are enqueued (t = T-1 .. 0): Decoder-2 uses it to
+// push the social-pooling gradient of step t into dhs[t-1] before step t-1 consumes it.
+int gru_bptt(const GruBptt& a, void* ws, size_t ws_bytes, cudaStream_t st,
+             const std::function<int(int)>* after_step = nullptr);
+int col2im_gather(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int C, const float* bias,
+                  float* out, cudaStream_t st);
+// d <- d * act'(computed from the post-activation output `out`)
+int act_bwd_post(const float* out, int ldo, float* d, int ldd, size_t M, int N, int act, cudaStream_t st);
 int gemm_mode();
 // A weight packed ONCE for many GEMM calls (IOC loop): pack_weight() fills `packed` when the tensor-core
 // path will be used; gemm_packed() then skips the per-call packing.

@@ -364,9 +364,20 @@ IocLayout ioc_layout(const desire_ioc_dims_t* d) {
 
 extern "C" size_t desire_ioc_workspace_bytes(const desire_ioc_dims_t* d) { return d ? ioc_layout(d).total : 0; }
 
+static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
+                        int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores, void* ws,
+                        size_t ws_bytes, desire_stream_t stream, float* snaps);
+
 extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
                               int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores, void* ws,
                               size_t ws_bytes, desire_stream_t stream) {
+  return ioc_fwd_impl(d, w, fmap, obs, Tp, Hx, ld_hx, fpool, Y, scores, ws, ws_bytes, stream, nullptr);
+}
+
+// snaps (train step only): [iters+1, R, T, 2] — the trajectories entering every iteration, then the final ones
+static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
+                        int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores, void* ws,
+                        size_t ws_bytes, desire_stream_t stream, float* snaps) {
   DESIRE_CHECK_ARG(d && w && fmap && obs && Hx && fpool && Y && scores, "desire_ioc_fwd: null argument");
   DESIRE_CHECK_ARG(d->B >= 0 && d->N > 0 && d->K > 0 && d->H > 0 && d->Tf > 0 && d->iters >= 0 && d->Fv % 4 == 0 &&
                        d->Cs % 4 == 0 && (2 * d->C) % 4 == 0,
@@ -450,6 +461,8 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
 
   for (int it = 0; it < d->iters; ++it) {
     float* score = scores + (size_t)it * R;
+    if (snaps)
+      DESIRE_CUDA(cudaMemcpyAsync(snaps + (size_t)it * R * T * 2, Y, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
     vel_fc_kernel<<<blocks(R * T * Fv, 256), 256, 0, st>>>(Y, obs, Tp, R, K, T, Fv, w->vel_w, w->vel_b, Xs, Dst);
     DESIRE_LAUNCH_CHECK();
     {
@@ -509,6 +522,488 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
     }
     // regression refinement: Y[R, 2T] += h2 @ reg_w + reg_b
     DESIRE_TRY(gemm_packed(h2, H, pw_reg, w->reg_b, Y, 2 * T, (int)R, DESIRE_ACT_NONE, true, st));
+  }
+  if (snaps)
+    DESIRE_CUDA(cudaMemcpyAsync(snaps + (size_t)d->iters * R * T * 2, Y, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
+  return DESIRE_OK;
+}
+
+// =========================================================================================== train step (D13)
+// Loss of the ranking & refinement module and its gradients.  Per iteration `it` and agent m:
+//   CE_it  = -sum_k q log p,  p = softmax_k(score_it),  q = softmax_k(-max_t ||Y - Y_it(k)||)       (q constant)
+//   REG_it = mean_k sum_t ||Y - Y_{it+1}(k)||^2,        Y_{it+1} = Y_it + dY_it
+//   ioc_cost = masked mean over existing agents of sum_it (CE_it + REG_it)
+// Stage-wise training: the module's inputs from stage 1 (Yhat, feature_pooling, H_x) are constants, and inside an
+// iteration every feature is computed from stop_gradient(Y_it) — only the chain Y_{it+1} = Y_it + dY_it carries
+// gradient, so d ioc_cost / d dY_j = sum_{it>=j} dREG_it/dY_{it+1} and the iterations differentiate independently.
+namespace {
+
+// one warp per agent m: loss rows, d score [iters,R], d dY [iters,R,T,2]
+__global__ void ioc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ snaps,
+                                const float* __restrict__ tgt, const float* __restrict__ obs,
+                                const float* __restrict__ count, int M, int K, int T, int Tp, int iters,
+                                float* __restrict__ rows, float* __restrict__ dscore, float* __restrict__ dDY) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const long R = (long)M * K;
+  const float g = (__ldg(obs + (size_t)m * Tp * 3) != 0.f) ? 1.f / __ldg(count) : 0.f;
+  const float* y = tgt + (size_t)m * T * 3;
+  float total = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    const float* Yi = snaps + ((size_t)it * R + (size_t)m * K) * T * 2;
+    const float* sc = scores + (size_t)it * R + (size_t)m * K;
+    auto dist = [&](int k) {
+      float d2max = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const float dx = __ldg(y + t * 3 + 1) - Yi[((size_t)k * T + t) * 2];
+        const float dy = __ldg(y + t * 3 + 2) - Yi[((size_t)k * T + t) * 2 + 1];
+        d2max = fmaxf(d2max, dx * dx + dy * dy);
+      }
+      return sqrtf(d2max);
+    };
+    float dmin = INFINITY, smax = -INFINITY;
+    for (int k = lane; k < K; k += 32) {
+      dmin = fminf(dmin, dist(k));
+      smax = fmaxf(smax, sc[k]);
+    }
+    dmin = -warp_max(-dmin);
+    smax = warp_max(smax);
+    float zq = 0.f, zp = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      zq += expf(dmin - dist(k));
+      zp += expf(sc[k] - smax);
+    }
+    zq = warp_sum(zq);
+    zp = warp_sum(zp);
+    const float lzp = logf(zp);
+    float ce = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float q = expf(dmin - dist(k)) / zq;
+      const float logp = sc[k] - smax - lzp;
+      ce -= q * logp;
+      dscore[(size_t)it * R + (size_t)m * K + k] = g * (expf(logp) - q);
+    }
+    total += warp_sum(ce);
+  }
+  // regression rows and the running sum of dREG over later iterations
+  float reg = 0.f;
+  for (int e = lane; e < K * T * 2; e += 32) {
+    const int c = e & 1, t = (e >> 1) % T;
+    const float yt = __ldg(y + t * 3 + 1 + c);
+    float acc = 0.f;
+    for (int it = iters - 1; it >= 0; --it) {
+      const float d = snaps[((size_t)(it + 1) * R + (size_t)m * K) * T * 2 + e] - yt;
+      reg = fmaf(d, d, reg);
+      acc += 2.f * d / (float)K * g;
+      dDY[((size_t)it * R + (size_t)m * K) * T * 2 + e] = acc;
+    }
+  }
+  total += warp_sum(reg) / (float)K;
+  if (lane == 0) rows[m] = total;
+}
+
+// cost[0] = sum_{existing} rows / count, cost[1] = local number of existing agents
+__global__ void ioc_cost_kernel(const float* __restrict__ rows, const float* __restrict__ obs,
+                                const float* __restrict__ count, int M, int Tp, float* __restrict__ cost) {
+  __shared__ float ssum[32], scnt[32];
+  float s = 0.f, n = 0.f;
+  for (int m = threadIdx.x; m < M; m += blockDim.x)
+    if (__ldg(obs + (size_t)m * Tp * 3) != 0.f) {
+      s += rows[m];
+      n += 1.f;
+    }
+  s = warp_sum(s);
+  n = warp_sum(n);
+  if ((threadIdx.x & 31) == 0) {
+    ssum[threadIdx.x >> 5] = s;
+    scnt[threadIdx.x >> 5] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    s = threadIdx.x < nw ? ssum[threadIdx.x] : 0.f;
+    n = threadIdx.x < nw ? scnt[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    n = warp_sum(n);
+    if (threadIdx.x == 0) {
+      cost[0] = s / __ldg(count);
+      cost[1] = n;
+    }
+  }
+}
+
+// dhs[r,t,:] = ds[r] * w_s ; dsT[r*T+t] = ds[r]
+__global__ void ioc_dhs_init_kernel(const float* __restrict__ ds, const float* __restrict__ ws, long R, int T, int H,
+                                    float* __restrict__ dhs, float* __restrict__ dsT) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * T * H) return;
+  const int h = (int)(i % H);
+  const long rt = i / H;
+  const float d = ds[rt / T];
+  dhs[i] = d * __ldg(ws + h);
+  if (h == 0) dsT[rt] = d;
+}
+
+// velocity inputs v[(r,t),:] = Y_t - Y_{t-1}
+__global__ void vel_kernel(const float* __restrict__ Y, const float* __restrict__ obs, int Tp, long R, int K, int T,
+                           float* __restrict__ v) {
+  const long rt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rt >= R * T) return;
+  const int t = (int)(rt % T);
+  const long r = rt / T;
+  float px, py;
+  if (t == 0) {
+    const float* last = obs + ((r / K) * Tp + (Tp - 1)) * 3;
+    px = __ldg(last + 1);
+    py = __ldg(last + 2);
+  } else {
+    px = Y[(rt - 1) * 2];
+    py = Y[(rt - 1) * 2 + 1];
+  }
+  v[rt * 2] = Y[rt * 2] - px;
+  v[rt * 2 + 1] = Y[rt * 2 + 1] - py;
+}
+
+// number of pooled neighbours per (row, bin): one warp per row, same binning arithmetic as the forward kernels
+__global__ void social_count_kernel(const float* __restrict__ pos, long pos_stride, const float* __restrict__ obs,
+                                    int Tp, long R, int N, int K, int n_rad, int n_ang,
+                                    const float* __restrict__ r2_edges, const float* __restrict__ dirs,
+                                    float* __restrict__ cnt) {
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const int G = n_rad * n_ang;
+  const int k = (int)(row % K);
+  const long bi = row / K;
+  const int i = (int)(bi % N);
+  const long b = bi / N;
+  const float xi = __ldg(pos + row * pos_stride), yi = __ldg(pos + row * pos_stride + 1);
+  for (int g0 = 0; g0 < G; g0 += 32) {          // lanes own bins g0+lane; every lane scans all neighbours
+    float c = 0.f;
+    for (int j = 0; j < N; ++j) {
+      if (j == i || __ldg(obs + ((size_t)(b * N + j) * Tp) * 3) == 0.f) continue;
+      const long rj = (b * N + j) * K + k;
+      const float dx = __ldg(pos + rj * pos_stride) - xi, dy = __ldg(pos + rj * pos_stride + 1) - yi;
+      const int g = logpolar_bin(dx, dy, r2_edges, n_rad, dirs, n_ang);
+      c += (g == g0 + lane) ? 1.f : 0.f;
+    }
+    if (g0 + lane < G) cnt[row * G + g0 + lane] = c;
+  }
+}
+
+// transpose of the pooling: dh[j,:] += sum_{i != j, bin(pos_j - pos_i) = g >= 0} dpooled[i, g, :] / cnt[i, g]
+// one warp per row j (lanes over H)
+__global__ void social_pool_bwd_kernel(const float* __restrict__ pos, long pos_stride, const float* __restrict__ obs,
+                                       int Tp, long R, int N, int K, int H, int n_rad, int n_ang,
+                                       const float* __restrict__ r2_edges, const float* __restrict__ dirs,
+                                       const float* __restrict__ dpooled, const float* __restrict__ cnt,
+                                       float* __restrict__ dh, long dh_rs) {
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const int G = n_rad * n_ang;
+  const int k = (int)(row % K);
+  const long bj = row / K;
+  const int j = (int)(bj % N);
+  const long b = bj / N;
+  if (__ldg(obs + ((size_t)(b * N + j) * Tp) * 3) == 0.f) return;    // a non-existent agent is never pooled
+  const float xj = __ldg(pos + row * pos_stride), yj = __ldg(pos + row * pos_stride + 1);
+  for (int c0 = 0; c0 < H; c0 += 32) {
+    const int c = c0 + lane;
+    float acc = 0.f;
+    for (int i = 0; i < N; ++i) {
+      if (i == j) continue;
+      const long ri = (b * N + i) * K + k;
+      const float dx = xj - __ldg(pos + ri * pos_stride), dy = yj - __ldg(pos + ri * pos_stride + 1);
+      const int g = logpolar_bin(dx, dy, r2_edges, n_rad, dirs, n_ang);
+      if (g < 0) continue;
+      if (c < H) acc += dpooled[(ri * G + g) * (long)H + c] / fmaxf(cnt[ri * G + g], 1.f);
+    }
+    if (c < H) dh[row * dh_rs + c] += acc;
+  }
+}
+
+// transpose of the bilinear gather: dfmap[b, taps, :] += weights * dfs[pt, :]   (atomics; one warp per point)
+__global__ void scene_gather_bwd_kernel(const float* __restrict__ dfs, int ld, int Hm, int Wm, int Cs,
+                                        const float* __restrict__ pos, long pos_stride, long npts, int rows_per_scene,
+                                        float* __restrict__ dfmap) {
+  const long pt = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pt >= npts) return;
+  const long b = pt / rows_per_scene;
+  const float x = __ldg(pos + pt * pos_stride), y = __ldg(pos + pt * pos_stride + 1);
+  const float wm1 = (float)(Wm - 1), hm1 = (float)(Hm - 1);
+  const float px = fminf(fmaxf(__fmul_rn(x, wm1), 0.f), wm1);
+  const float py = fminf(fmaxf(__fmul_rn(y, hm1), 0.f), hm1);
+  const int x0 = (int)floorf(px), y0 = (int)floorf(py);
+  const int x1 = min(x0 + 1, Wm - 1), y1 = min(y0 + 1, Hm - 1);
+  const float fx = px - (float)x0, fy = py - (float)y0;
+  float* base = dfmap + (size_t)b * Hm * Wm * Cs;
+  float* p00 = base + ((size_t)y0 * Wm + x0) * Cs;
+  float* p01 = base + ((size_t)y0 * Wm + x1) * Cs;
+  float* p10 = base + ((size_t)y1 * Wm + x0) * Cs;
+  float* p11 = base + ((size_t)y1 * Wm + x1) * Cs;
+  for (int c = lane; c < Cs; c += 32) {
+    const float d = dfs[pt * (long)ld + c];
+    // out = (1-fy)*((1-fx) v00 + fx v01) + fy*((1-fx) v10 + fx v11)
+    atomicAdd(p00 + c, d * (1.f - fy) * (1.f - fx));
+    atomicAdd(p01 + c, d * (1.f - fy) * fx);
+    atomicAdd(p10 + c, d * fy * (1.f - fx));
+    atomicAdd(p11 + c, d * fy * fx);
+  }
+}
+
+struct IocTrainLayout {
+  size_t snaps, dscore, dDY, rows, Xs, XP, dXP, fsp, hs2, dhs, pooled, h0e, dh0, dpre, cnt, dX48, vel, dsT, bptt, pack,
+      fwd, total;
+};
+IocTrainLayout ioc_train_layout(const desire_ioc_dims_t* d) {
+  const size_t R = (size_t)d->B * d->N * d->K, T = d->Tf, H = d->H, M = (size_t)d->B * d->N;
+  const size_t Dst = d->Fv + d->Cs + 2 * d->C, G = (size_t)d->n_rad * d->n_ang;
+  const size_t it = d->iters > 0 ? d->iters : 1;
+  IocTrainLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  L.snaps = take((it + 1) * R * T * 2 * 4);
+  L.dscore = take(it * R * 4);
+  L.dDY = take(it * R * T * 2 * 4);
+  L.rows = take(M * 4);
+  L.Xs = take(R * T * Dst * 4);
+  L.XP = take(R * T * 3 * H * 4);
+  L.dXP = take(R * T * 3 * H * 4);
+  L.fsp = take(R * T * H * 4);
+  L.hs2 = take(R * T * H * 4);
+  L.dhs = take(R * T * H * 4);
+  L.pooled = take(R * G * H * 4);
+  L.h0e = take(R * H * 4);
+  L.dh0 = take(R * H * 4);
+  L.dpre = take(R * H * 4);
+  L.cnt = take(R * G * 4);
+  L.dX48 = take(R * T * (d->Fv + d->Cs) * 4);
+  L.vel = take(R * T * 2 * 4);
+  L.dsT = take(R * T * 4);
+  L.bptt = take(gru_bptt_ws_bytes(R, (int)H));
+  L.pack = take(PACK_WS_BYTES);
+  L.fwd = take(ioc_layout(d).total);
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+extern "C" size_t desire_ioc_train_workspace_bytes(const desire_ioc_dims_t* d) { return d ? ioc_train_layout(d).total : 0; }
+
+extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
+                                int Tp, const float* target, const float* Hx, int ld_hx, const float* fpool,
+                                const float* Yhat, const float* count, float* Y, float* scores, float* ioc_cost,
+                                const desire_ioc_grad_t* g, float* dfmap, void* ws, size_t ws_bytes,
+                                desire_stream_t stream) {
+  DESIRE_CHECK_ARG(d && w && fmap && obs && target && Hx && fpool && Yhat && count && Y && scores && ioc_cost && g && dfmap,
+                   "desire_ioc_train: null argument");
+  DESIRE_CHECK_ARG(d->iters >= 1 && d->H % 4 == 0, "desire_ioc_train: needs iters >= 1 and H %% 4 == 0");
+  const IocTrainLayout L = ioc_train_layout(d);
+  if (!ws || ws_bytes < L.total) {
+    set_error("desire_ioc_train: workspace too small (%zu < %zu)", ws_bytes, L.total);
+    return DESIRE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long R = (long)d->B * d->N * d->K;
+  if (R == 0) return DESIRE_OK;
+  const int T = d->Tf, H = d->H, K = d->K, N = d->N, Fv = d->Fv, Cs = d->Cs, C2 = 2 * d->C, iters = d->iters;
+  const int Dst = Fv + Cs + C2, G = d->n_rad * d->n_ang, M = d->B * d->N, F48 = Fv + Cs;
+  DESIRE_CHECK_ARG(R * T < (1L << 31) / 4, "desire_ioc_train: R*T too large");
+  char* base = (char*)ws;
+  auto fp = [&](size_t o) { return (float*)(base + o); };
+  float *snaps = fp(L.snaps), *dscore = fp(L.dscore), *dDY = fp(L.dDY), *rows = fp(L.rows), *Xs = fp(L.Xs), *XP = fp(L.XP),
+        *dXP = fp(L.dXP), *fsp = fp(L.fsp), *hs2 = fp(L.hs2), *dhs = fp(L.dhs), *pooled = fp(L.pooled), *h0e = fp(L.h0e),
+        *dh0 = fp(L.dh0), *dpre = fp(L.dpre), *cnt = fp(L.cnt), *dX48 = fp(L.dX48), *vel = fp(L.vel), *dsT = fp(L.dsT);
+  PackWs pw{base + L.pack, PACK_WS_BYTES};
+  const size_t f4 = sizeof(float);
+  const desire_gru_t& gw = w->dec2;
+  const desire_gru_grad_t& gg = g->dec2;
+  const int I = Dst + H;                                   // input rows of the Decoder-2 kernels
+
+  // ---- phase A: the forward of every iteration (fast fused path) with snapshots of the trajectories
+  DESIRE_CUDA(cudaMemcpyAsync(Y, Yhat, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
+  DESIRE_TRY(ioc_fwd_impl(d, w, fmap, obs, Tp, Hx, ld_hx, fpool, Y, scores, base + L.fwd, ws_bytes - L.fwd, stream, snaps));
+  DESIRE_LAUNCH(st, (ioc_loss_kernel<<<blocks((long)M * 32, 256), 256, 0, st>>>(scores, snaps, target, obs, count, M, K, T, Tp,
+                                                                                iters, rows, dscore, dDY)));
+  DESIRE_LAUNCH(st, (ioc_cost_kernel<<<1, 1024, 0, st>>>(rows, obs, count, M, Tp, ioc_cost)));
+
+  // ---- phase B: per iteration, recompute with every intermediate kept, then backward
+  DESIRE_LAUNCH(st, (copy_cols_kernel<<<blocks(R * T * C2, 256), 256, 0, st>>>(fpool, C2, R * T, Xs + Fv + Cs, Dst)));
+  DESIRE_LAUNCH(st, (expand_rows_kernel<<<blocks(R * H, 256), 256, 0, st>>>(Hx, ld_hx, K, H, R, h0e)));
+  const float* wg_sp = gw.wg + (size_t)Dst * 2 * H;        // rows multiplying the social feature
+  const float* wc_sp = gw.wc + (size_t)Dst * H;
+  const float* wg_h = gw.wg + (size_t)I * 2 * H;           // rows multiplying the state
+  const float* wc_h = gw.wc + (size_t)I * H;
+  for (int it = 0; it < iters; ++it) {
+    const float* Yi = snaps + (size_t)it * R * T * 2;
+    // static features and their hoisted projection (biases included)
+    DESIRE_LAUNCH(st, (vel_fc_kernel<<<blocks(R * T * Fv, 256), 256, 0, st>>>(Yi, obs, Tp, R, K, T, Fv, w->vel_w, w->vel_b, Xs, Dst)));
+    DESIRE_LAUNCH(st, (scene_gather_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(fmap, d->Hm, d->Wm, Cs, Yi, 2, R * T,
+                                                                                    N * K * T, Xs + Fv, Dst)));
+    DESIRE_TRY(sgemm(Xs, Dst, gw.wg, 2 * H, false, gw.bg, XP, 3 * H, (int)(R * T), 2 * H, Dst, DESIRE_ACT_NONE, false, st, pw));
+    DESIRE_TRY(sgemm(Xs, Dst, gw.wc, H, false, gw.bc, XP + 2 * H, 3 * H, (int)(R * T), H, Dst, DESIRE_ACT_NONE, false, st, pw));
+    for (int t = 0; t < T; ++t) {
+      const float* hp = t > 0 ? hs2 + (size_t)(t - 1) * H : h0e;
+      const int hp_ld = t > 0 ? T * H : H;
+      DESIRE_TRY(social_pool_launch(Yi + 2 * t, 2L * T, hp, hp_ld, obs, Tp, d->B, N, K, H, d->n_rad, d->n_ang, w->r2_edges,
+                                    w->dirs, pooled, st));
+      float* fsp_t = fsp + (size_t)t * H;
+      DESIRE_TRY(sgemm(pooled, G * H, w->sp_w, H, false, w->sp_b, fsp_t, T * H, (int)R, H, G * H, DESIRE_ACT_RELU, false, st, pw));
+      float* xp_t = XP + (size_t)t * 3 * H;
+      DESIRE_TRY(sgemm(fsp_t, T * H, wg_sp, 2 * H, false, nullptr, xp_t, T * 3 * H, (int)R, 2 * H, H, DESIRE_ACT_NONE, true, st, pw));
+      DESIRE_TRY(sgemm(fsp_t, T * H, wc_sp, H, false, nullptr, xp_t + 2 * H, T * 3 * H, (int)R, H, H, DESIRE_ACT_NONE, true, st, pw));
+      GruSeqArgs a{};
+      a.R = (int)R; a.H = H; a.T = 1;
+      a.xp = xp_t; a.xp_row_stride = (long)T * 3 * H; a.xp_step_stride = 0;
+      a.Ka = 0; a.w_g = wg_h; a.w_c = wc_h;
+      a.h0 = hp; a.h0_div = 1; a.ld_h0 = hp_ld;
+      a.h_final = hs2 + (size_t)t * H; a.ld_hf = T * H;
+      DESIRE_TRY(gru_seq(a, st, pw));
+    }
+    // ---- gradients reaching the states: score head on every step, regression head on the last
+    const float* ds = dscore + (size_t)it * R;
+    const float* dDYi = dDY + (size_t)it * R * T * 2;
+    DESIRE_LAUNCH(st, (ioc_dhs_init_kernel<<<blocks(R * T * H, 256), 256, 0, st>>>(ds, w->score_w, R, T, H, dhs, dsT)));
+    DESIRE_TRY(wgrad_tn(hs2, H, dsT, 1, g->score_w, 1, (int)(R * T), H, 1, st));
+    DESIRE_TRY(colsum_acc(dsT, 1, (int)(R * T), 1, g->score_b, st));
+    const float* hT = hs2 + (size_t)(T - 1) * H;
+    DESIRE_TRY(wgrad_tn(hT, T * H, dDYi, 2 * T, g->reg_w, 2 * T, (int)R, H, 2 * T, st));
+    DESIRE_TRY(colsum_acc(dDYi, 2 * T, (int)R, 2 * T, g->reg_b, st));
+    DESIRE_TRY(sgemm(dDYi, 2 * T, w->reg_w, 2 * T, true, nullptr, dhs + (size_t)(T - 1) * H, T * H, (int)R, H, 2 * T,
+                     DESIRE_ACT_NONE, true, st, pw));
+    // ---- backward through time; after each step the social path feeds the previous step's state gradient
+    DESIRE_CUDA(cudaMemsetAsync(dXP, 0, (size_t)R * T * 3 * H * f4, st));
+    DESIRE_CUDA(cudaMemsetAsync(dh0, 0, (size_t)R * H * f4, st));
+    GruBptt a{};
+    a.R = (int)R; a.H = H; a.T = T; a.I = I;
+    a.wg = gw.wg; a.wc = gw.wc;
+    a.xp = XP; a.xp_rs = (long)T * 3 * H; a.xp_ss = 3 * H;
+    a.hs = hs2; a.hs_rs = (long)T * H; a.hs_ss = H;
+    a.h0e = h0e;
+    a.dhs = dhs; a.dhs_rs = (long)T * H; a.dhs_ss = H;
+    a.dxp = dXP; a.dxp_rs = (long)T * 3 * H; a.dxp_ss = 3 * H;
+    a.dh0 = dh0;
+    a.dwg = gg.wg; a.dwc = gg.wc;
+    std::function<int(int)> social_bwd = [&](int t) -> int {
+      const float* hp = t > 0 ? hs2 + (size_t)(t - 1) * H : h0e;
+      const int hp_ld = t > 0 ? T * H : H;
+      const float* dxp_t = dXP + (size_t)t * 3 * H;
+      // d fsp_t = dxp_t @ W[social rows]^T, through the ReLU
+      DESIRE_TRY(sgemm(dxp_t, T * 3 * H, wg_sp, 2 * H, true, nullptr, dpre, H, (int)R, H, 2 * H, DESIRE_ACT_NONE, false, st, pw));
+      DESIRE_TRY(sgemm(dxp_t + 2 * H, T * 3 * H, wc_sp, H, true, nullptr, dpre, H, (int)R, H, H, DESIRE_ACT_NONE, true, st, pw));
+      DESIRE_TRY(act_bwd_post(fsp + (size_t)t * H, T * H, dpre, H, (size_t)R, H, DESIRE_ACT_RELU, st));
+      DESIRE_TRY(social_pool_launch(Yi + 2 * t, 2L * T, hp, hp_ld, obs, Tp, d->B, N, K, H, d->n_rad, d->n_ang, w->r2_edges,
+                                    w->dirs, pooled, st));
+      DESIRE_TRY(wgrad_tn(pooled, G * H, dpre, H, g->sp_w, H, (int)R, G * H, H, st));
+      DESIRE_TRY(colsum_acc(dpre, H, (int)R, H, g->sp_b, st));
+      if (t == 0) return DESIRE_OK;                         // h2_{-1} = H_x is a constant of this module
+      DESIRE_TRY(sgemm(dpre, H, w->sp_w, H, true, nullptr, pooled, G * H, (int)R, G * H, H, DESIRE_ACT_NONE, false, st, pw));
+      DESIRE_LAUNCH(st, (social_count_kernel<<<blocks(R * 32, 256), 256, 0, st>>>(Yi + 2 * t, 2L * T, obs, Tp, R, N, K, d->n_rad,
+                                                                                  d->n_ang, w->r2_edges, w->dirs, cnt)));
+      DESIRE_LAUNCH(st, (social_pool_bwd_kernel<<<blocks(R * 32, 256), 256, 0, st>>>(
+                            Yi + 2 * t, 2L * T, obs, Tp, R, N, K, H, d->n_rad, d->n_ang, w->r2_edges, w->dirs, pooled, cnt,
+                            dhs + (size_t)(t - 1) * H, (long)T * H)));
+      return DESIRE_OK;
+    };
+    DESIRE_TRY(gru_bptt(a, base + L.bptt, L.pack - L.bptt, st, &social_bwd));
+    // ---- input rows of Decoder-2: static features, social feature, biases
+    const int RT = (int)(R * T);
+    DESIRE_TRY(wgrad_tn(Xs, Dst, dXP, 3 * H, gg.wg, 2 * H, RT, Dst, 2 * H, st));
+    DESIRE_TRY(wgrad_tn(Xs, Dst, dXP + 2 * H, 3 * H, gg.wc, H, RT, Dst, H, st));
+    DESIRE_TRY(wgrad_tn(fsp, H, dXP, 3 * H, gg.wg + (size_t)Dst * 2 * H, 2 * H, RT, H, 2 * H, st));
+    DESIRE_TRY(wgrad_tn(fsp, H, dXP + 2 * H, 3 * H, gg.wc + (size_t)Dst * H, H, RT, H, H, st));
+    DESIRE_TRY(colsum_acc(dXP, 3 * H, RT, 2 * H, gg.bg, st));
+    DESIRE_TRY(colsum_acc(dXP + 2 * H, 3 * H, RT, H, gg.bc, st));
+    // d [fv | fs] = dXP @ W[rows 0..Fv+Cs)^T
+    DESIRE_TRY(sgemm(dXP, 3 * H, gw.wg, 2 * H, true, nullptr, dX48, F48, RT, F48, 2 * H, DESIRE_ACT_NONE, false, st, pw));
+    DESIRE_TRY(sgemm(dXP + 2 * H, 3 * H, gw.wc, H, true, nullptr, dX48, F48, RT, F48, H, DESIRE_ACT_NONE, true, st, pw));
+    // velocity fc
+    DESIRE_TRY(act_bwd_post(Xs, Dst, dX48, F48, (size_t)RT, Fv, DESIRE_ACT_RELU, st));
+    DESIRE_LAUNCH(st, (vel_kernel<<<blocks(R * T, 256), 256, 0, st>>>(Yi, obs, Tp, R, K, T, vel)));
+    DESIRE_TRY(wgrad_tn(vel, 2, dX48, F48, g->vel_w, Fv, RT, 2, Fv, st));
+    DESIRE_TRY(colsum_acc(dX48, F48, RT, Fv, g->vel_b, st));
+    // scene features: scatter the gather's gradient into the feature-map gradient
+    DESIRE_LAUNCH(st, (scene_gather_bwd_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(dX48 + Fv, F48, d->Hm, d->Wm, Cs, Yi, 2,
+                                                                                        R * T, N * K * T, dfmap)));
+  }
+  return DESIRE_OK;
+}
+
+// ---- scene CNN backward: fmap = relu(conv3(relu(conv2(relu(conv1(img)))))), SAME 5x5, strides 2/1/1
+namespace {
+const size_t SCENE_COL_BUDGET = 256u << 20;   // bytes of the dy @ W^T column matrix per chunk of images
+}
+extern "C" size_t desire_scene_cnn_bwd_workspace_bytes(int B, int Hi, int Wi) {
+  const size_t Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2, px = Ho * Wo;
+  size_t per = SCENE_COL_BUDGET / (px * 800 * 4);
+  if (per < 1) per = 1;
+  if (per > (size_t)B) per = B > 0 ? B : 1;
+  return align_up((size_t)B * px * 16 * 4) * 2 + align_up((size_t)B * px * 32 * 4) * 2 + align_up((size_t)B * px * 64 * 4) +
+         align_up(per * px * 800 * 4) + PACK_WS_BYTES;
+}
+
+extern "C" int desire_scene_cnn_bwd(const float* img, int B, int Hi, int Wi, int Cs, const desire_scene_cnn_t* w,
+                                    float* dfmap, const desire_scene_cnn_grad_t* g, void* ws, size_t ws_bytes,
+                                    desire_stream_t stream) {
+  DESIRE_CHECK_ARG(img && w && dfmap && g && B >= 0 && Hi > 0 && Wi == Hi && Cs > 0 && Cs <= 64,
+                   "desire_scene_cnn_bwd: bad arguments (square images, Cs <= 64)");
+  if (!ws || ws_bytes < desire_scene_cnn_bwd_workspace_bytes(B, Hi, Wi)) {
+    set_error("desire_scene_cnn_bwd: workspace too small");
+    return DESIRE_ERR_WORKSPACE;
+  }
+  if (B == 0) return DESIRE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
+  const size_t px = (size_t)Ho * Wo;
+  Workspace W(ws, ws_bytes);
+  float* f1 = W.take<float>((size_t)B * px * 16);
+  float* df1 = W.take<float>((size_t)B * px * 16);
+  float* f2 = W.take<float>((size_t)B * px * 32);
+  float* df2 = W.take<float>((size_t)B * px * 32);
+  float* f3 = W.take<float>((size_t)B * px * 64);
+  size_t per = SCENE_COL_BUDGET / (px * 800 * 4);
+  if (per < 1) per = 1;
+  if (per > (size_t)B) per = B;
+  float* col = W.take<float>(per * px * 800);
+  PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
+  const int pt1 = max((Ho - 1) * 2 + 5 - Hi, 0) / 2;
+  DESIRE_CHECK_ARG(per * px <= (size_t)65535 * 128, "desire_scene_cnn_bwd: map too large");
+  for (int b0 = 0; b0 < B; b0 += (int)per) {
+    const int nb = std::min((int)per, B - b0);
+    const int Mr = (int)(nb * px);
+    const float* im = img + (size_t)b0 * Hi * Wi * 3;
+    float *F1 = f1 + b0 * px * 16, *DF1 = df1 + b0 * px * 16, *F2 = f2 + b0 * px * 32, *DF2 = df2 + b0 * px * 32,
+          *F3 = f3 + b0 * px * Cs, *DF3 = dfmap + b0 * px * Cs;
+    Im2col g1{Hi, Wi, 3, Ho, Wo, 5, 5, 2, pt1, pt1};
+    Im2col g2{Ho, Wo, 16, Ho, Wo, 5, 5, 1, 2, 2};
+    Im2col g3{Ho, Wo, 32, Ho, Wo, 5, 5, 1, 2, 2};
+    // forward recompute (the forward keeps only the final map)
+    DESIRE_TRY(sgemm_im2col(im, g1, w->c1_w, 16, w->c1_b, F1, 16, Mr, 16, 75, DESIRE_ACT_RELU, st, pw));
+    DESIRE_TRY(sgemm_im2col(F1, g2, w->c2_w, 32, w->c2_b, F2, 32, Mr, 32, 400, DESIRE_ACT_RELU, st, pw));
+    DESIRE_TRY(sgemm_im2col(F2, g3, w->c3_w, Cs, w->c3_b, F3, Cs, Mr, Cs, 800, DESIRE_ACT_RELU, st, pw));
+    // conv3
+    DESIRE_TRY(act_bwd_post(F3, Cs, DF3, Cs, (size_t)Mr, Cs, DESIRE_ACT_RELU, st));
+    DESIRE_TRY(wgrad_tn_im2col(F2, g3, DF3, Cs, g->c3_w, Cs, Mr, 800, Cs, st));
+    DESIRE_TRY(colsum_acc(DF3, Cs, Mr, Cs, g->c3_b, st));
+    DESIRE_TRY(sgemm(DF3, Cs, w->c3_w, Cs, true, nullptr, col, 800, Mr, 800, Cs, DESIRE_ACT_NONE, false, st, pw));
+    DESIRE_TRY(col2im_gather(col, nb, Ho, Ho, 5, 1, 2, 32, nullptr, DF2, st));
+    // conv2
+    DESIRE_TRY(act_bwd_post(F2, 32, DF2, 32, (size_t)Mr, 32, DESIRE_ACT_RELU, st));
+    DESIRE_TRY(wgrad_tn_im2col(F1, g2, DF2, 32, g->c2_w, 32, Mr, 400, 32, st));
+    DESIRE_TRY(colsum_acc(DF2, 32, Mr, 32, g->c2_b, st));
+    DESIRE_TRY(sgemm(DF2, 32, w->c2_w, 32, true, nullptr, col, 400, Mr, 400, 32, DESIRE_ACT_NONE, false, st, pw));
+    DESIRE_TRY(col2im_gather(col, nb, Ho, Ho, 5, 1, 2, 16, nullptr, DF1, st));
+    // conv1 (the image needs no gradient)
+    DESIRE_TRY(act_bwd_post(F1, 16, DF1, 16, (size_t)Mr, 16, DESIRE_ACT_RELU, st));
+    DESIRE_TRY(wgrad_tn_im2col(im, g1, DF1, 16, g->c1_w, 16, Mr, 75, 16, st));
+    DESIRE_TRY(colsum_acc(DF1, 16, Mr, 16, g->c1_b, st));
   }
   return DESIRE_OK;
 }

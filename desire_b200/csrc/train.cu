@@ -151,24 +151,15 @@ __global__ void gru_bwd_reset_kernel(const float* __restrict__ drh, const float*
   dxp[r * dxp_rs + c] += drp;
 }
 
-struct GruBptt {
-  int R, H, T, I;
-  const float *wg, *wc;                 // full TF-layout kernels [(I+H),2H], [(I+H),H]
-  const float* xp; long xp_rs, xp_ss;   // hoisted input projection incl. biases
-  const float* hs; long hs_rs, hs_ss;   // forward states h_t
-  const float* h0e;                     // [R,H] dense initial state
-  float* dhs; long dhs_rs, dhs_ss;      // gradient reaching h_t (in), accumulated in place
-  float* dxp; long dxp_rs, dxp_ss;      // += (zeroed by the caller)
-  float* dh0;                           // [R,H], zeroed by the caller, receives d h_{-1}
-  float *dwg, *dwc;                     // full-layout gradients (+=); only the state rows are touched here
-};
+}  // namespace
 
+namespace desire {
 size_t gru_bptt_ws_bytes(size_t R, int H) {
   // gh[2H] ru[2H] dg[2H] + rh ch dcpre drh tmp [H each]
   return 3 * align_up(R * 2 * H * 4) + 5 * align_up(R * H * 4) + PACK_WS_BYTES;
 }
 
-int gru_bptt(const GruBptt& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+int gru_bptt(const GruBptt& a, void* ws, size_t ws_bytes, cudaStream_t st, const std::function<int(int)>* after_step) {
   const size_t R = a.R;
   const int H = a.H;
   Workspace W(ws, ws_bytes);
@@ -212,9 +203,13 @@ int gru_bptt(const GruBptt& a, void* ws, size_t ws_bytes, cudaStream_t st) {
     DESIRE_TRY(sgemm(dg, 2 * H, wg_h, 2 * H, true, nullptr, target, (int)tg_rs, a.R, H, 2 * H, DESIRE_ACT_NONE, true, st, pw));
     DESIRE_TRY(wgrad_tn(hp, (int)hp_rs, dg, 2 * H, dwg_h, 2 * H, a.R, H, 2 * H, st));
     DESIRE_TRY(wgrad_tn(rh, H, dcpre, H, dwc_h, H, a.R, H, H, st));
+    if (after_step) DESIRE_TRY((*after_step)(t));
   }
   return DESIRE_OK;
 }
+}  // namespace desire
+
+namespace {
 
 // ------------------------------------------------------------------------------------------ softmax gate
 // one warp per row: beta = softmax(l); dl = relu'(l) * beta * (dbeta - sum beta dbeta), dbeta = dxz*Hx;
@@ -405,6 +400,8 @@ int bn_row_bwd(const float* y, int R, int P, int C, const float* gamma, const fl
   return DESIRE_OK;
 }
 
+}  // namespace
+namespace desire {
 int col2im_gather(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int C, const float* bias,
                   float* out, cudaStream_t st) {
   const size_t total = (size_t)R * Hout * Hout * C;
@@ -412,6 +409,8 @@ int col2im_gather(const float* col, int R, int Hin, int Hout, int k, int stride,
   DESIRE_LAUNCH(st, (col2im_gather_kernel<<<grid1d(total), 256, 0, st>>>(col, total, Hin, Hout, k, stride, pad, C, bias, out)));
   return DESIRE_OK;
 }
+}  // namespace desire
+namespace {
 
 // dC <- dC * act'(from the post-activation output)
 __global__ void act_bwd_post_kernel(const float* __restrict__ out, int ldo, float* __restrict__ d, int ldd, size_t M,
@@ -428,6 +427,15 @@ __global__ void act_bwd_post_kernel(const float* __restrict__ out, int ldo, floa
   d[m * ldd + n] *= f;
 }
 
+}  // namespace
+namespace desire {
+int act_bwd_post(const float* out, int ldo, float* d, int ldd, size_t M, int N, int act, cudaStream_t st) {
+  if (M == 0 || N == 0 || act == DESIRE_ACT_NONE) return DESIRE_OK;
+  DESIRE_LAUNCH(st, (act_bwd_post_kernel<<<grid1d(M * N), 256, 0, st>>>(out, ldo, d, ldd, M, N, act)));
+  return DESIRE_OK;
+}
+}  // namespace desire
+namespace {
 // ------------------------------------------------------------------------------------------ Adam
 __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
   __shared__ float sm[32];

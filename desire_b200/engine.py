@@ -178,8 +178,10 @@ class TrainPath(HotPath):
     (flatten_params); gradients and the Adam moments live in flat buffers of the same layout, so the
     multi-GPU step is ONE all-reduce of `grad_flat`."""
 
-    def __init__(self, cfg: DesireConfig, flat: torch.Tensor, params: dict, offsets: dict, B: int, device="cuda:0"):
+    def __init__(self, cfg: DesireConfig, flat: torch.Tensor, params: dict, offsets: dict, B: int, device="cuda:0",
+                 train_ioc=True):
         super().__init__(cfg, params, B, device)
+        self.train_ioc = bool(train_ioc) and cfg.ioc_iters > 0
         for k, (o, cnt, shp) in offsets.items():
             if self.P[k].data_ptr() != flat.data_ptr() + 4 * o:
                 raise ValueError("parameter %s is not a view of the flat buffer" % k)
@@ -202,10 +204,19 @@ class TrainPath(HotPath):
         self.g_venc = _lib.CvaeEncG(cbn("venc_c1"), cbn("venc_c2"), cbn("venc_c3"),
                                     G["venc_fc_w"].data_ptr(), G["venc_fc_b"].data_ptr())
         self.g_vdec = _lib.CvaeDecG(cbn("vdec_d1"), cbn("vdec_d2"), cbn("vdec_d3"), cbn("vdec_d4"))
+        self.g_scene = _lib.SceneCnnG(*[G["scene_" + n].data_ptr() for n in ("c1_w", "c1_b", "c2_w", "c2_b", "c3_w", "c3_b")])
+        self.g_ioc = _lib.IocG(G["ioc_vel_w"].data_ptr(), G["ioc_vel_b"].data_ptr(), G["ioc_sp_w"].data_ptr(),
+                               G["ioc_sp_b"].data_ptr(), gru("dec2"), G["ioc_score_w"].data_ptr(),
+                               G["ioc_score_b"].data_ptr(), G["ioc_reg_w"].data_ptr(), G["ioc_reg_b"].data_ptr())
+        self.dbuf["dfmap"] = torch.empty_like(self.buf["scene_features"])
+        self.buf["ioc_cost"] = f(2)
         lib = self.lib
         bws = max(lib.desire_gru_decode_bwd_workspace_bytes(R, H), lib.desire_mask_softmax_bwd_workspace_bytes(R, H),
                   lib.desire_cvae_decode_bwd_workspace_bytes(R, Zl), lib.desire_cvae_encode_bwd_workspace_bytes(M, Zl),
                   lib.desire_gru_encode_bwd_workspace_bytes(M, max(cfg.seq_length, Tf), H))
+        if self.train_ioc:
+            bws = max(bws, lib.desire_ioc_train_workspace_bytes(C.byref(self.ioc_dims)),
+                      lib.desire_scene_cnn_bwd_workspace_bytes(B, cfg.scene_size, cfg.scene_size))
         if bws > self.ws_bytes:
             self.ws_bytes = bws
             self.ws = torch.empty(bws, dtype=torch.uint8, device=self.device)
@@ -218,9 +229,10 @@ class TrainPath(HotPath):
         self.count.copy_((obs[:, :, 0, 0] != 0).sum().to(torch.float32).reshape(1))
         return global_count_(self.count)
 
-    def backward(self, obs, tgt, eps):
-        """Gradients of `cost` w.r.t. every parameter into grad_flat (zeroed here).  Call after run(); uses
-        self.count as the normaliser."""
+    def backward(self, obs, tgt, eps, scene=None):
+        """Gradients of `cost` (+ `ioc_cost` when train_ioc, D13) w.r.t. every parameter into grad_flat (zeroed
+        here).  Call after run(stages=("generate",)); uses self.count as the normaliser.  With train_ioc the IOC
+        forward runs inside (Y_refined, ioc_scores, ioc_cost are outputs of this call)."""
         cfg, lib, b, d, P, G = self.cfg, self.lib, self.buf, self.dbuf, self.P, self.G
         N, K, H, Zl, Tp, Tf = cfg.max_num_obj, cfg.K, cfg.H, cfg.Z, cfg.seq_length, cfg.pred_length
         M, R, S2 = self.M, self.R, cfg.S * cfg.S
@@ -252,6 +264,19 @@ class TrainPath(HotPath):
         ck(lib.desire_gru_encode_bwd(_p(tgt), M, Tf, H, C.byref(self.w_ency),
                                      C.c_void_p(d["dHxHy"].data_ptr() + 4 * H), 2 * H,
                                      C.byref(self.g_ency), ws, wsb, st), "gru_encode_y_bwd")
+        if self.train_ioc:
+            if scene is None:
+                raise ValueError("train_ioc needs the scene images")
+            ck(lib.desire_scene_cnn_fwd(_p(scene), self.B, cfg.scene_size, cfg.scene_size, cfg.scene_channels,
+                                        C.byref(self.w_scene), _p(b["scene_features"]), ws, wsb, st), "scene_cnn")
+            d["dfmap"].zero_()
+            ck(lib.desire_ioc_train(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs), Tp,
+                                    _p(tgt), _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["Yhat"]),
+                                    _p(self.count), _p(b["Y_refined"]), _p(b["ioc_scores"]), _p(b["ioc_cost"]),
+                                    C.byref(self.g_ioc), _p(d["dfmap"]), ws, wsb, st), "ioc_train")
+            ck(lib.desire_scene_cnn_bwd(_p(scene), self.B, cfg.scene_size, cfg.scene_size, cfg.scene_channels,
+                                        C.byref(self.w_scene), _p(d["dfmap"]), C.byref(self.g_scene), ws, wsb, st),
+               "scene_cnn_bwd")
         return self.G
 
     def apply(self, lr, clip=10.0, beta1=0.9, beta2=0.999, eps=1e-8):
@@ -274,13 +299,13 @@ class TrainPath(HotPath):
         with torch.cuda.stream(side):
             for _ in range(2):
                 self.run(*self.static_in, stages=("generate",))
-                self.backward(*self.static_in[:3])
+                self.backward(*self.static_in)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.run(*self.static_in, stages=("generate",))
-            self.backward(*self.static_in[:3])
+            self.backward(*self.static_in)
         self.train_graph = g
         return g
 
@@ -298,6 +323,6 @@ class TrainPath(HotPath):
         else:
             self.set_count(obs)
             self.run(obs, tgt, eps, scene, stages=("generate",))
-            self.backward(obs, tgt, eps)
+            self.backward(obs, tgt, eps, scene)
         self.apply(lr, clip)
         return self.buf["cost"]

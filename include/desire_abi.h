@@ -278,6 +278,30 @@ int desire_adam_step(float* p, const float* g, float* m, float* v, long n, const
                      float beta1, float beta2, float eps, int step, float clip, float grad_scale,
                      desire_stream_t stream);
 
+/* ---- a14 train step (stage 2 is absent in the reference, so is its loss).  Per iteration it:
+ *   CE_it = -sum_k q log p, p = softmax_k(score_it), q = softmax_k(-max_t ||Y - Y_it(k)||) (constant);
+ *   REG_it = mean_k sum_t ||Y - Y_{it+1}(k)||^2;  ioc_cost = sum_{existing}(sum_it CE+REG) / count.
+ * Stage-wise: Yhat, feature_pooling, H_x are constants of this module and features are taken at
+ * stop_gradient(Y_it).  desire_ioc_train runs the forward of all iterations (Y [R,Tf,2] = refined output, scores
+ * [iters,R] as desire_ioc_fwd), writes ioc_cost[0] (normalised by *count) and ioc_cost[1] (local agent count), and
+ * accumulates the gradients of ioc_cost into g (+=) and into dfmap [B,Hm,Wm,Cs] (+=, zeroed by the caller), which
+ * desire_scene_cnn_bwd then carries into the scene CNN weights (dfmap is clobbered). */
+typedef struct {
+  float *vel_w, *vel_b, *sp_w, *sp_b;
+  desire_gru_grad_t dec2;
+  float *score_w, *score_b, *reg_w, *reg_b;
+} desire_ioc_grad_t;
+typedef struct { float *c1_w, *c1_b, *c2_w, *c2_b, *c3_w, *c3_b; } desire_scene_cnn_grad_t;
+size_t desire_ioc_train_workspace_bytes(const desire_ioc_dims_t* d);
+int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
+                     int Tp, const float* target, const float* Hx, int ld_hx, const float* fpool,
+                     const float* Yhat, const float* count, float* Y, float* scores, float* ioc_cost,
+                     const desire_ioc_grad_t* g, float* dfmap, void* ws, size_t ws_bytes, desire_stream_t stream);
+size_t desire_scene_cnn_bwd_workspace_bytes(int B, int Hi, int Wi);
+int desire_scene_cnn_bwd(const float* img, int B, int Hi, int Wi, int Cs, const desire_scene_cnn_t* w,
+                         float* dfmap, const desire_scene_cnn_grad_t* g, void* ws, size_t ws_bytes,
+                         desire_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

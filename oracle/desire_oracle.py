@@ -367,7 +367,7 @@ def social_pool_loops(pos, h, mask, r2_edges, dirs):
     return out
 
 
-def ioc_refine(Yhat, x_last, Hx, fpool, fmap, mask, P, dims, iters, r2_edges, dirs):
+def ioc_refine(Yhat, x_last, Hx, fpool, fmap, mask, P, dims, iters, r2_edges, dirs, snapshots=None):
     """D11 ranking & refinement (absent in the reference, marker model/model.py:312-313).
 
     Per iteration, per step t and row (b,n,k):
@@ -399,9 +399,33 @@ def ioc_refine(Yhat, x_last, Hx, fpool, fmap, mask, P, dims, iters, r2_edges, di
             s = s + h2 @ P["ioc_score_w"] + P["ioc_score_b"]
             prev = Y[:, t]
         dY = (h2 @ P["ioc_reg_w"] + P["ioc_reg_b"]).reshape(MK, T, 2)
+        if snapshots is not None:
+            snapshots.append(Y)          # the trajectories this iteration scored (Y_it)
         Y = Y + dY
         scores.append(s)
+    if snapshots is not None:
+        snapshots.append(Y)
     return np.stack(scores, 0), Y
+
+
+def ioc_loss_rows(scores, snaps, Y_true, K):
+    """D13 (paper sec. 3.3-3.4; absent in the reference): per agent m, summed over the IOC iterations,
+      CE_it  = - sum_k q log p,   p = softmax_k(score_it),  q = softmax_k(-max_t ||Y - Y_it(k)||_2)
+      REG_it = mean_k sum_t ||Y - Y_{it+1}(k)||^2
+    scores [iters, M*K]; snaps = [Y_0 .. Y_iters] each [M*K,T,2]; Y_true [M,T,2] -> [M]."""
+    M = Y_true.shape[0]
+    rows = np.zeros(M, Y_true.dtype)
+    for it in range(scores.shape[0]):
+        d = np.sqrt(((snaps[it].reshape(M, K, -1, 2) - Y_true[:, None]) ** 2).sum(-1)).max(-1)     # [M,K]
+        q = softmax(-d)
+        s = scores[it].reshape(M, K)
+        logp = s - s.max(axis=1, keepdims=True)
+        logp = logp - np.log(np.exp(logp).sum(axis=1, keepdims=True))
+        ce = -(q * logp).sum(axis=1)
+        e = snaps[it + 1].reshape(M, K, -1, 2) - Y_true[:, None]
+        reg = (e * e).sum(axis=(2, 3)).mean(axis=1)
+        rows = rows + ce + reg
+    return rows
 
 
 # --------------------------------------------------------------------------- whole path
@@ -444,7 +468,10 @@ def forward(P, cfg, input_data, target_data, eps, scene_img, r2_edges, dirs):
     out["cost"] = masked_cost(out["recon_rows"] + out["kld_rows"], mask.reshape(M))
     fmap = scene_cnn(scene_img, P)
     out["scene_features"] = fmap
+    snaps = []
     scores, Yref = ioc_refine(Yhat, x_last, Hx, fpool, fmap, mask, P, (B, N, K),
-                              cfg["ioc_iters"], r2_edges, dirs)
+                              cfg["ioc_iters"], r2_edges, dirs, snaps)
     out["ioc_scores"], out["Y_refined"] = scores, Yref
+    out["ioc_rows"] = ioc_loss_rows(scores, snaps, Y, K)
+    out["ioc_cost"] = masked_cost(out["ioc_rows"], mask.reshape(M)) if cfg["ioc_iters"] > 0 else np.zeros((), Y.dtype)
     return out

@@ -187,6 +187,102 @@ def generate_forward(P, cfg, input_data, target_data, eps):
     return out
 
 
+# --------------------------------------------------------------------------- stage 2 (D11 forward, D13 loss)
+def scene_cnn(img, P):
+    x = torch.relu(conv2d_tf(img, P["scene_c1_w"], P["scene_c1_b"], 2, "SAME"))
+    x = torch.relu(conv2d_tf(x, P["scene_c2_w"], P["scene_c2_b"], 1, "SAME"))
+    return torch.relu(conv2d_tf(x, P["scene_c3_w"], P["scene_c3_b"], 1, "SAME"))
+
+
+def _bilinear_const(fmap, pos_np):
+    """Bilinear gather with CONSTANT positions (numpy): linear in fmap.  pos [B,R,2] -> [B,R,Cs]."""
+    B, Hm, Wm, Cs = fmap.shape
+    px = np.clip(pos_np[..., 0] * (Wm - 1), 0, Wm - 1)
+    py = np.clip(pos_np[..., 1] * (Hm - 1), 0, Hm - 1)
+    x0, y0 = np.floor(px).astype(np.int64), np.floor(py).astype(np.int64)
+    x1, y1 = np.minimum(x0 + 1, Wm - 1), np.minimum(y0 + 1, Hm - 1)
+    fx = torch.as_tensor(px - x0).to(fmap.dtype)[..., None]
+    fy = torch.as_tensor(py - y0).to(fmap.dtype)[..., None]
+    bi = np.arange(B)[:, None]
+    v00, v01, v10, v11 = fmap[bi, y0, x0], fmap[bi, y0, x1], fmap[bi, y1, x0], fmap[bi, y1, x1]
+    top = v00 + fx * (v01 - v00)
+    bot = v10 + fx * (v11 - v10)
+    return top + fy * (bot - top)
+
+
+def _pool_const(pos_np, h, mask_np, r2_edges, dirs, bin_dtype=None):
+    """Log-polar social pooling with CONSTANT bins (numpy, same binning code as the NumPy oracle): linear in h.
+    pos [B,N,K,2], h [B,N,K,H] torch -> [B,N,K,G,H].  bin_dtype=np.float32 bins in the kernels' arithmetic."""
+    from oracle import desire_oracle as O
+    if bin_dtype is not None:
+        pos_np, r2_edges, dirs = pos_np.astype(bin_dtype), r2_edges.astype(bin_dtype), dirs.astype(bin_dtype)
+    B, N, K, H = h.shape
+    G = (r2_edges.shape[0] - 1) * dirs.shape[0]
+    outs = []
+    eye = np.eye(N, dtype=bool)[:, :, None]
+    for b in range(B):
+        dx = pos_np[b, None, :, :, 0] - pos_np[b, :, None, :, 0]
+        dy = pos_np[b, None, :, :, 1] - pos_np[b, :, None, :, 1]
+        bins = O.logpolar_bin(dx, dy, r2_edges, dirs)
+        ok = (bins >= 0) & (mask_np[b][None, :, None] > 0) & ~eye
+        onehot = ((bins[..., None] == np.arange(G)) & ok[..., None]).astype(np.float64)     # [i,j,K,G]
+        cnt = np.maximum(onehot.sum(1), 1)                                                   # [i,K,G]
+        A = torch.as_tensor(onehot / cnt[:, None]).to(h.dtype)
+        outs.append(torch.einsum("ijkg,jkh->ikgh", A, h[b]))
+    return torch.stack(outs, 0)
+
+
+def ioc_train_forward(P, cfg, gen, input_data, target_data, scene_img, r2_edges, dirs, bin_dtype=None):
+    """Stage 2 with the D13 training loss.  `gen` = the (detached) outputs of stage 1 as numpy: Yhat, H_x,
+    feature_pooling — the IOC module treats them as constants (stage-wise training), and inside an iteration
+    every feature is computed from stop_gradient(Y_it); only Y_{it+1} = Y_it + dY_it carries gradient.
+    Returns dict(ioc_scores [iters,MK], Y_refined, ioc_rows [M], ioc_cost)."""
+    dt = next(iter(P.values())).dtype
+    inp = np.asarray(input_data, np.float64)
+    B, N, Tp, _ = inp.shape
+    K, iters = cfg["K"], cfg["ioc_iters"]
+    M, MK = B * N, B * N * K
+    mask_np = (inp[:, :, 0, 0] != 0)
+    Y_true = torch.as_tensor(np.asarray(target_data, np.float64).reshape(M, -1, 3)[..., 1:3]).to(dt)
+    T = Y_true.shape[1]
+    x_last = np.repeat(inp.reshape(M, Tp, 3)[:, -1, 1:3], K, 0)
+    Hx = torch.as_tensor(np.asarray(gen["H_x"], np.float64)).to(dt)
+    H = Hx.shape[1]
+    fpool = torch.as_tensor(np.asarray(gen["feature_pooling"], np.float64)).to(dt)
+    fmap = scene_cnn(torch.as_tensor(np.asarray(scene_img, np.float64)).to(dt), P)
+    Y = torch.as_tensor(np.asarray(gen["Yhat"], np.float64)).to(dt)
+    r2_edges, dirs = np.asarray(r2_edges), np.asarray(dirs)
+    rows = torch.zeros(M, dtype=dt)
+    scores = []
+    for _ in range(iters):
+        Yd = Y.detach().numpy()
+        h2 = Hx.repeat_interleave(K, dim=0)
+        s = torch.zeros(MK, dtype=dt)
+        prev = x_last
+        for t in range(T):
+            v = torch.as_tensor(Yd[:, t] - prev).to(dt)
+            fv = torch.relu(v @ P["ioc_vel_w"] + P["ioc_vel_b"])
+            fs = _bilinear_const(fmap, Yd[:, t].reshape(B, N * K, 2)).reshape(MK, -1)
+            pooled = _pool_const(Yd[:, t].reshape(B, N, K, 2), h2.reshape(B, N, K, H), mask_np, r2_edges, dirs, bin_dtype)
+            fsp = torch.relu(pooled.reshape(MK, -1) @ P["ioc_sp_w"] + P["ioc_sp_b"])
+            x_t = torch.cat([fv, fs, fpool[:, t], fsp], 1)
+            h2 = gru_cell(x_t, h2, P["dec2_wg"], P["dec2_bg"], P["dec2_wc"], P["dec2_bc"])
+            s = s + h2 @ P["ioc_score_w"] + P["ioc_score_b"]
+            prev = Yd[:, t]
+        dY = (h2 @ P["ioc_reg_w"] + P["ioc_reg_b"]).reshape(MK, T, 2)
+        d = torch.as_tensor(np.sqrt(((Yd.reshape(M, K, T, 2) - Y_true.numpy()[:, None]) ** 2).sum(-1)).max(-1)).to(dt)
+        q = torch.softmax(-d, dim=1)
+        ce = -(q * torch.log_softmax(s.reshape(M, K), dim=1)).sum(dim=1)
+        Y = Y + dY
+        e = Y.reshape(M, K, T, 2) - Y_true[:, None]
+        rows = rows + ce + (e * e).sum(dim=(2, 3)).mean(dim=1)
+        scores.append(s)
+    out = {"ioc_scores": torch.stack(scores, 0) if scores else torch.zeros(0, MK, dtype=dt), "Y_refined": Y,
+           "ioc_rows": rows, "scene_features": fmap}
+    out["ioc_cost"] = masked_cost(rows, torch.as_tensor(mask_np.reshape(M)))
+    return out
+
+
 def adam_reference(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, clip=0.0):
     """clip_by_global_norm over the whole list + TF-1.x AdamOptimizer update, on dicts of numpy arrays
     (float64).  Returns (p', m', v')."""

@@ -19,11 +19,11 @@ SHAPES = [(48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (16, 5, 2, 1, 0), (64, 10, 5, 2,
 ACT = {"dYhat": "Yhat", "dx_z": "x_z", "dxr": "x_reconstr_mean", "dz": "zval", "dv": "vae_inputs"}
 
 
-def make_train_path(cfg, B):
+def make_train_path(cfg, B, train_ioc=False):
     from desire_b200.config import init_params
     from desire_b200.engine import TrainPath, flatten_params
     flat, views, offs = flatten_params(init_params(cfg, 1), "cuda:0")
-    return TrainPath(cfg, flat, views, offs, B)
+    return TrainPath(cfg, flat, views, offs, B, train_ioc=train_ioc)
 
 
 def oracle_grads(cfg, B, missing, P=None):
@@ -165,3 +165,95 @@ def test_train_steps_follow_the_reference_trajectory_and_reduce_cost(use_graph):
     e = (num / den) ** 0.5
     print("step-1 parameter update rel-L2 vs reference: %.3e" % e)
     assert e <= 2e-2
+
+
+# ------------------------------------------------------------------------------------------ stage 2 (D13)
+IOC_PARAMS = ["scene_c1_w", "scene_c1_b", "scene_c2_w", "scene_c2_b", "scene_c3_w", "scene_c3_b", "ioc_vel_w", "ioc_vel_b",
+              "ioc_sp_w", "ioc_sp_b", "dec2_wg", "dec2_bg", "dec2_wc", "dec2_bc", "ioc_score_w", "ioc_score_b", "ioc_reg_w",
+              "ioc_reg_b"]
+ONE_BIN = dict(n_rad=1, n_ang=1, r_min=1e-6, r_max=1e3)
+
+
+def run_ioc_train(cfg, B, missing):
+    from desire_b200.synthetic import make_batch
+    tp = make_train_path(cfg, B, train_ioc=True)
+    batch = [t.cuda() for t in make_batch(cfg, B, 0, missing)]
+    tp.set_count(batch[0])
+    tp.run(*batch, stages=("generate",))
+    G = tp.backward(*batch)
+    torch.cuda.synchronize()
+    return tp, G
+
+
+def ioc_reference(cfg, B, missing, gen, bin_dtype=None):
+    from oracle import desire_oracle_torch as OT
+    from helpers import np_tables
+    P = np_params(cfg, dtype=np.float64)
+    batch = np_batch(cfg, B, n_missing=missing, dtype=np.float64)
+    Pt = OT.to_torch(P)
+    r2, dirs = np_tables(cfg, np.float64)
+    out = OT.ioc_train_forward(Pt, dict(K=cfg.K, Z=cfg.Z, ioc_iters=cfg.ioc_iters), gen, batch[0], batch[1], batch[3], r2, dirs,
+                               bin_dtype=bin_dtype)
+    out["ioc_cost"].backward()
+    g = {k: (Pt[k].grad.numpy() if Pt[k].grad is not None else np.zeros(Pt[k].shape)) for k in IOC_PARAMS}
+    return out, g
+
+
+def compare_ioc(tp, G, out, ref_g, tol):
+    bad = {}
+    for k, ref in (("ioc_scores", out["ioc_scores"]), ("Y_refined", out["Y_refined"]), ("ioc_cost", out["ioc_cost"])):
+        got = tp.buf[k].cpu().numpy() if k != "ioc_cost" else tp.buf[k][:1].cpu().numpy()
+        e = rel_l2(got.reshape(-1), ref.detach().numpy().reshape(-1))
+        print("fwd  %-18s rel-L2 %.3e" % (k, e))
+        if not e <= max(tol, 1e-4):
+            bad["fwd:" + k] = e
+    gmax = max(float(np.linalg.norm(v)) for v in ref_g.values())
+    for k in IOC_PARAMS:
+        got, ref = G[k].cpu().numpy().astype(np.float64), ref_g[k]
+        nr = float(np.linalg.norm(ref))
+        e = rel_l2(got.reshape(-1), ref.reshape(-1)) if nr > 1e-9 * gmax else float(np.linalg.norm(got)) / gmax
+        print("grad %-18s rel-L2 %.3e  (|ref| %.3e)" % (k, e, nr))
+        if not (e <= tol or e * nr <= 1e-6 * gmax):
+            bad[k] = e
+    return bad
+
+
+@pytest.mark.parametrize("H,N,K,B,missing,iters", [(48, 8, 3, 2, 3, 2), (128, 12, 4, 3, 2, 2), (16, 5, 2, 1, 0, 1),
+                                                   (64, 10, 5, 2, 1, 3)])
+def test_ioc_backward_single_bin_strict(H, N, K, B, missing, iters):
+    """One social bin (no bin edges, everything smooth): strict comparison against float64 autograd of the twin fed
+    with the float64 oracle's stage-1 outputs."""
+    from helpers import np_tables, oracle_forward
+    cfg = small_cfg(d_dim=H, max_num_obj=N, num_samples=K, ioc_iters=iters, **ONE_BIN)
+    tp, G = run_ioc_train(cfg, B, missing)
+    gen = oracle_forward(cfg, np_params(cfg, dtype=np.float64), np_batch(cfg, B, n_missing=missing, dtype=np.float64),
+                         np_tables(cfg, np.float64))
+    out, ref_g = ioc_reference(cfg, B, missing, gen)
+    bad = compare_ioc(tp, G, out, ref_g, GTOL)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("H,N,K,B,missing", [(48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (32, 40, 2, 2, 0)])
+def test_ioc_backward_logpolar(H, N, K, B, missing):
+    """Real 6x6 log-polar grid, one iteration: the twin is fed with the GPU's own stage-1 outputs (constants of the
+    IOC module, D13) and bins in fp32 with the kernels' arithmetic, so both sides pool identical neighbour sets."""
+    cfg = small_cfg(d_dim=H, max_num_obj=N, num_samples=K, ioc_iters=1)
+    tp, G = run_ioc_train(cfg, B, missing)
+    gen = {"Yhat": tp.buf["Yhat"].cpu().numpy(), "H_x": tp.buf["HxHy"][:, :H].cpu().numpy(),
+           "feature_pooling": tp.buf["feature_pooling"].cpu().numpy()}
+    out, ref_g = ioc_reference(cfg, B, missing, gen, bin_dtype=np.float32)
+    bad = compare_ioc(tp, G, out, ref_g, GTOL)
+    assert not bad, bad
+
+
+def test_full_train_step_with_ioc_reduces_both_costs():
+    from desire_b200.synthetic import make_batch
+    cfg = small_cfg(d_dim=32, max_num_obj=10, num_samples=4)
+    tp = make_train_path(cfg, 2, train_ioc=True)
+    batch = [t.cuda() for t in make_batch(cfg, 2, 0, 1)]
+    hist = []
+    for _ in range(6):
+        tp.train_step(*batch, lr=2e-3, clip=10.0, use_graph=True)
+        hist.append((float(tp.buf["cost"][0]), float(tp.buf["ioc_cost"][0])))
+    print(hist)
+    assert hist[-1][0] < hist[0][0] and hist[-1][1] < hist[0][1], hist
