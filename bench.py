@@ -223,6 +223,11 @@ def ours_arm(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the ONE JSON line (NCCL_DEBUG=VERSION prints its banner there), and give each rank its share
+        # of the host cores for the pinned-staging memcpy of the e2e leg (torchrun exports OMP_NUM_THREADS=1)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
         dist.init_process_group("nccl", device_id=dev)
     cfg = make_cfg(a)
     lib = _lib.load()
@@ -318,9 +323,10 @@ def ours_arm(a):
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         train = {"ms_per_step": float(tms.item()) / steps,
                  "agent_samples_per_s": R_local * world * steps / (float(tms.item()) / 1e3),
-                 "what": "sample-generation forward + backward of cost + %sclip_by_global_norm + Adam over %d parameters"
-                         % ("NCCL all-reduce of the flat gradient + " if world > 1 else "", tp.flat.numel()),
-                 "cost_after": float(tp.buf["cost"][0])}
+                 "what": "full CVAE+IOC train step: sample-generation forward, backward of cost, IOC forward + D13 loss + "
+                         "backward (ioc_iters=%d), scene-CNN backward, %sclip_by_global_norm + Adam over %d parameters"
+                         % (cfg.ioc_iters, "NCCL all-reduce of the flat gradient, " if world > 1 else "", tp.flat.numel()),
+                 "cost_after": float(tp.buf["cost"][0]), "ioc_cost_after": float(tp.buf["ioc_cost"][0])}
 
     if rank != 0:
         if world > 1:
