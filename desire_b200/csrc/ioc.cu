@@ -236,6 +236,199 @@ __global__ void __launch_bounds__(SP_WARPS * 32) social_pool_tile_kernel(
   }
 }
 
+// ---- social pooling, large scenes (the N hidden vectors of a group no longer fit shared memory: N=256 at H=256,
+// N=1024 at H=128).  One CTA = I consecutive agents i of one (scene, sample) group.  The CTA bins its I x N pairs once
+// and counting-sorts every row's neighbours by bin (ascending j, as the other kernels); it then walks the hidden
+// dimension in slices of W = 32*V columns: the slice of ALL N neighbours is staged in shared memory once and reused
+// by the I rows (L2 traffic N*H*4/I bytes per row instead of N*H*4), each warp sums a row's bin members in
+// registers (one LDS.32V per member) and streams the averaged slice out as one coalesced 128*V-byte store.  HBM
+// traffic is the algorithmic 4*G*H-byte write per row.
+constexpr int SPB_WARPS = 32, SPB_ROWS = 32;   // one row per warp; 1024 threads hide the shared-memory latency
+
+struct SpbLayout {
+  size_t hs, lst, off, cur, binrow, px, py, tab, total;
+  int Np, offs_ld;
+};
+__host__ __device__ inline SpbLayout spb_layout(int N, int W, int G, int n_rad, int n_ang) {
+  SpbLayout L;
+  L.Np = (N + 31) / 32 * 32;
+  L.offs_ld = (G + 1 + 7) / 8 * 8;
+  size_t o = 0;
+  L.hs = o;
+  L.binrow = o;                                   // the per-warp bin rows of the sort phase alias the staging area
+  {
+    const size_t a = (size_t)N * W * 4, b2 = (size_t)SPB_WARPS * L.Np;
+    o += a > b2 ? a : b2;
+  }
+  o = (o + 15) / 16 * 16;
+  L.lst = o; o += (size_t)SPB_ROWS * L.Np * 2;
+  L.off = o; o += (size_t)SPB_ROWS * L.offs_ld * 2;
+  L.cur = o; o += (size_t)SPB_WARPS * 64 * 2;
+  o = (o + 15) / 16 * 16;
+  L.px = o; o += (size_t)L.Np * 4;
+  L.py = o; o += (size_t)L.Np * 4;
+  L.tab = o; o += (size_t)(n_rad + 1 + 2 * n_ang) * 4;
+  L.total = (o + 15) / 16 * 16;
+  return L;
+}
+
+template <int V>
+__global__ void __launch_bounds__(SPB_WARPS * 32) social_pool_rows_kernel(
+    const float* __restrict__ pos, long pos_stride, const float* __restrict__ h, int ld_h,
+    const float* __restrict__ obs, int Tp, int N, int K, int H, int n_rad, int n_ang,
+    const float* __restrict__ r2_edges, const float* __restrict__ dirs, float* __restrict__ pooled, int nblk) {
+  extern __shared__ __align__(16) uint8_t spb_smem[];
+  constexpr int W = 32 * V;
+  const int G = n_rad * n_ang;
+  const SpbLayout L = spb_layout(N, W, G, n_rad, n_ang);
+  float* hs = reinterpret_cast<float*>(spb_smem + L.hs);
+  unsigned short* lst = reinterpret_cast<unsigned short*>(spb_smem + L.lst);
+  unsigned short* offs = reinterpret_cast<unsigned short*>(spb_smem + L.off);
+  uint8_t* binrow = spb_smem + L.binrow;
+  float* px = reinterpret_cast<float*>(spb_smem + L.px);
+  float* py = reinterpret_cast<float*>(spb_smem + L.py);
+  float* tab = reinterpret_cast<float*>(spb_smem + L.tab);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long grp = blockIdx.x / nblk;
+  const int i0 = (int)(blockIdx.x % nblk) * SPB_ROWS;
+  const long b = grp / K;
+  const int k = (int)(grp % K);
+
+  for (int e = tid; e < n_rad + 1; e += blockDim.x) tab[e] = __ldg(r2_edges + e);
+  for (int e = tid; e < 2 * n_ang; e += blockDim.x) tab[n_rad + 1 + e] = __ldg(dirs + e);
+  for (int j = tid; j < L.Np; j += blockDim.x) {
+    float x = __int_as_float(0x7fc00000), y = x;          // NaN = non-existent / padding: fails every comparison
+    if (j < N && __ldg(obs + ((size_t)(b * N + j) * Tp) * 3) != 0.f) {
+      const long rj = (b * N + j) * K + k;
+      x = __ldg(pos + rj * pos_stride);
+      y = __ldg(pos + rj * pos_stride + 1);
+    }
+    px[j] = x;
+    py[j] = y;
+  }
+  __syncthreads();
+
+  // ---- bins of the I x N pairs, then a per-row counting sort (ascending j inside a bin).  The sort is warp-wide:
+  // 32 neighbours per step, __match_any groups the lanes of equal bin, the group leader bumps the bin's counter.
+  uint8_t* mybin = binrow + (size_t)warp * L.Np;
+  unsigned short* cur = reinterpret_cast<unsigned short*>(spb_smem + L.cur) + warp * 64;
+  for (int il = warp; il < SPB_ROWS; il += SPB_WARPS) {
+    const int i = i0 + il;
+    unsigned short* off = offs + (size_t)il * L.offs_ld;
+    unsigned short* ml = lst + (size_t)il * L.Np;
+    if (i >= N) continue;
+    const long ri = (b * N + i) * K + k;
+    const float xi = __ldg(pos + ri * pos_stride), yi = __ldg(pos + ri * pos_stride + 1);   // a masked row still pools
+    for (int g = lane; g <= G; g += 32) off[g] = 0;
+    __syncwarp();
+    for (int j0 = 0; j0 < L.Np; j0 += 32) {                   // pass 1: bins + histogram (count of bin g at off[g+1])
+      const int j = j0 + lane;
+      int g = 255;                                            // 255 = no bin
+      if (j < N && j != i) {
+        const float dx = px[j] - xi, dy = py[j] - yi;
+        if (dx == dx) {
+          const int bb = logpolar_bin(dx, dy, tab, n_rad, tab + n_rad + 1, n_ang);
+          if (bb >= 0) g = bb;
+        }
+      }
+      mybin[j] = (uint8_t)g;
+      const unsigned m = __match_any_sync(0xffffffffu, g);
+      if (g != 255 && (__ffs(m) - 1) == lane) off[g + 1] += (unsigned short)__popc(m);
+      __syncwarp();
+    }
+    {                                                         // inclusive scan over the bins (G <= 64): off[g+1] = end of bin g
+      int c0 = lane < G ? off[lane + 1] : 0, c1 = lane + 32 < G ? off[lane + 33] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v0 = __shfl_up_sync(0xffffffffu, c0, o), v1 = __shfl_up_sync(0xffffffffu, c1, o);
+        if (lane >= o) {
+          c0 += v0;
+          c1 += v1;
+        }
+      }
+      c1 += __shfl_sync(0xffffffffu, c0, 31);
+      __syncwarp();
+      if (lane < G) off[lane + 1] = (unsigned short)c0;
+      if (lane + 32 < G) off[lane + 33] = (unsigned short)c1;
+      __syncwarp();
+      for (int g = lane; g < G; g += 32) cur[g] = off[g];
+      __syncwarp();
+    }
+    for (int j0 = 0; j0 < L.Np; j0 += 32) {                   // pass 2: stable fill
+      const int j = j0 + lane;
+      const int g = mybin[j];
+      const unsigned m = __match_any_sync(0xffffffffu, g);
+      if (g != 255) ml[cur[g] + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+      __syncwarp();
+      if (g != 255 && (__ffs(m) - 1) == lane) cur[g] += (unsigned short)__popc(m);
+      __syncwarp();
+    }
+  }
+
+  // ---- walk the hidden dimension in slices of W columns
+  constexpr int W4 = W / 4;
+  for (int c0 = 0; c0 < H; c0 += W) {
+    __syncthreads();                                          // lists ready / previous slice fully consumed
+    for (int e = tid; e < N * W4; e += blockDim.x) {
+      const int j = e / W4, c4 = e - j * W4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(h + ((b * N + j) * K + k) * (long)ld_h + c0) + c4);
+      *reinterpret_cast<float4*>(hs + (size_t)j * W + c4 * 4) = v;
+    }
+    __syncthreads();
+    for (int il = warp; il < SPB_ROWS; il += SPB_WARPS) {
+      const int i = i0 + il;
+      if (i >= N) continue;
+      const unsigned short* off = offs + (size_t)il * L.offs_ld;
+      const unsigned short* ml = lst + (size_t)il * L.Np;
+      float* orow = pooled + ((b * N + i) * K + k) * (long)G * H + c0 + lane * V;
+      const float* hs_lane = hs + lane * V;
+      for (int g = 0; g < G; ++g) {
+        const int o0 = off[g], o1 = off[g + 1];
+        float acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = 0.f;
+        for (int base = o0; base < o1; base += 32) {
+          // lanes fetch 32 member indices at once; the shuffles make the hidden-vector loads independent of them
+          const int n = min(32, o1 - base);
+          const int myj = lane < n ? (int)ml[base + lane] : 0;
+#pragma unroll 8
+          for (int q = 0; q < n; ++q) {
+            const int j = __shfl_sync(0xffffffffu, myj, q);
+            const float* src = hs_lane + j * W;
+            if (V == 4) {
+              const float4 x = *reinterpret_cast<const float4*>(src);
+              acc[0] += x.x; acc[V > 1 ? 1 : 0] += x.y; acc[V > 2 ? 2 : 0] += x.z; acc[V > 3 ? 3 : 0] += x.w;
+            } else if (V == 2) {
+              const float2 x = *reinterpret_cast<const float2*>(src);
+              acc[0] += x.x; acc[V > 1 ? 1 : 0] += x.y;
+            } else {
+              acc[0] += src[0];
+            }
+          }
+        }
+        const float inv = (float)max(o1 - o0, 1);
+        float* dst = orow + (size_t)g * H;
+        if (V == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0] / inv, acc[V > 1 ? 1 : 0] / inv, acc[V > 2 ? 2 : 0] / inv, acc[V > 3 ? 3 : 0] / inv));
+        else if (V == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(acc[0] / inv, acc[V > 1 ? 1 : 0] / inv));
+        else __stcs(dst, acc[0] / inv);
+      }
+    }
+  }
+}
+
+template <int V>
+int social_pool_rows_launch(const float* pos, long pos_stride, const float* h, int ld_h, const float* obs, int Tp, int B,
+                            int N, int K, int H, int n_rad, int n_ang, const float* r2_edges, const float* dirs,
+                            float* pooled, size_t smem, cudaStream_t st) {
+  const int nblk = (N + SPB_ROWS - 1) / SPB_ROWS;
+  const long grid = (long)B * K * nblk;
+  DESIRE_CHECK_ARG(grid < (1L << 31), "social_pool: grid too large");
+  DESIRE_ENSURE_SMEM(social_pool_rows_kernel<V>, smem);
+  DESIRE_LAUNCH(st, (social_pool_rows_kernel<V><<<(unsigned)grid, SPB_WARPS * 32, smem, st>>>(
+                        pos, pos_stride, h, ld_h, obs, Tp, N, K, H, n_rad, n_ang, r2_edges, dirs, pooled, nblk)));
+  return DESIRE_OK;
+}
+
 int social_pool_launch(const float* pos, long pos_stride, const float* h, int ld_h, const float* obs, int Tp, int B,
                        int N, int K, int H, int n_rad, int n_ang, const float* r2_edges, const float* dirs,
                        float* pooled, cudaStream_t st) {
@@ -248,6 +441,19 @@ int social_pool_launch(const float* pos, long pos_stride, const float* h, int ld
       DESIRE_LAUNCH(st, (social_pool_tile_kernel<<<(unsigned)((long)B * K), SP_WARPS * 32, tile, st>>>(
                             pos, pos_stride, h, ld_h, obs, Tp, N, K, H, n_rad, n_ang, r2_edges, dirs, pooled)));
       return DESIRE_OK;
+    }
+  }
+  if (H % 32 == 0 && G <= 64 && ld_h % 4 == 0 && N < 65535 && (long)B * K > 0) {
+    // large scenes: row-block kernel, widest column slice whose staging fits shared memory
+    for (int W = 128; W >= 32; W >>= 1) {
+      if (H % W) continue;
+      const size_t need = spb_layout(N, W, G, n_rad, n_ang).total;
+      if (need > 220 * 1024) continue;
+      if (W == 128)
+        return social_pool_rows_launch<4>(pos, pos_stride, h, ld_h, obs, Tp, B, N, K, H, n_rad, n_ang, r2_edges, dirs, pooled, need, st);
+      if (W == 64)
+        return social_pool_rows_launch<2>(pos, pos_stride, h, ld_h, obs, Tp, B, N, K, H, n_rad, n_ang, r2_edges, dirs, pooled, need, st);
+      return social_pool_rows_launch<1>(pos, pos_stride, h, ld_h, obs, Tp, B, N, K, H, n_rad, n_ang, r2_edges, dirs, pooled, need, st);
     }
   }
   size_t smem = ((size_t)G * H + G + n_rad + 1 + 2 * n_ang) * sizeof(float) + (size_t)N * sizeof(int);

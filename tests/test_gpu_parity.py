@@ -81,7 +81,10 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-@pytest.mark.parametrize("B,N,K,H,missing", [(2, 7, 3, 8, 2), (3, 60, 4, 128, 5), (1, 33, 2, 256, 0), (2, 100, 2, 48, 3)])
+@pytest.mark.parametrize("B,N,K,H,missing", [(2, 7, 3, 8, 2), (3, 60, 4, 128, 5), (1, 33, 2, 256, 0), (2, 100, 2, 48, 3),
+                                             # large scenes -> row-block kernel (128-, 64- and 32-column slices)
+                                             (1, 300, 2, 256, 5), (1, 400, 2, 192, 0), (1, 1024, 1, 128, 7),
+                                             (2, 256, 3, 256, 1)])
 def test_social_pool_exact_bins(lib, B, N, K, H, missing):
     """Identical inputs -> identical bin membership (the binning arithmetic is shared exactly)."""
     from oracle import desire_oracle as O
