@@ -153,10 +153,18 @@ int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const 
 int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const float* bias, float* C,
                  int ldc, int M, int N, int K, int act, cudaStream_t st, PackWs pw = PackWs());
 // train step (gemm_f32.cu): dW[Kd,N] (ldw) += A^T @ B over M rows, A dense or implicit im2col; column sums
+// wp: scratch for the packed BF16 image of B (wgrad_tc_pack_bytes(M, N)); with it (and gemm mode != 0, Kd >= 64,
+// N >= 16, M >= 2048) the product runs on tcgen05 (gemm_tc.cu, split-K + atomics), otherwise on FP32 CUDA cores.
 int wgrad_tn(const float* A, int lda, const float* B, int ldb, float* dW, int ldw, int M, int Kd, int N,
-             cudaStream_t st);
+             cudaStream_t st, PackWs wp = PackWs());
 int wgrad_tn_im2col(const float* X, const Im2col& g, const float* B, int ldb, float* dW, int ldw, int M, int Kd,
-                    int N, cudaStream_t st);
+                    int N, cudaStream_t st, PackWs wp = PackWs());
+size_t wgrad_tc_pack_bytes(int rows, int N);
+bool wgrad_tc_eligible(int rows, int Kd, int N, const void* pack_ws, size_t pack_bytes);
+int wgrad_tc(const float* A, int lda, const float* B, int ldb, float* dW, int ldw, int rows, int Kd, int N, void* pack_ws,
+             cudaStream_t st);
+int wgrad_tc_im2col(const float* X, const Im2col& g, const float* B, int ldb, float* dW, int ldw, int rows, int Kd, int N,
+                    void* pack_ws, cudaStream_t st);
 int colsum_acc(const float* A, int lda, int M, int N, float* out, cudaStream_t st);
 // train.cu: GRU backward through time over recomputed gates (shared by the encoders, Decoder-1 and Decoder-2)
 struct GruBptt {

@@ -255,13 +255,15 @@ int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const
 
 
 int wgrad_tn(const float* A, int lda, const float* B, int ldb, float* dW, int ldw, int M, int Kd, int N,
-             cudaStream_t st) {
+             cudaStream_t st, PackWs wp) {
+  if (wgrad_tc_eligible(M, Kd, N, wp.p, wp.bytes)) return wgrad_tc(A, lda, B, ldb, dW, ldw, M, Kd, N, wp.p, st);
   DenseA a{A, lda, M, Kd};
   return launch_wgrad(a, B, ldb, dW, ldw, M, Kd, N, st);
 }
 
 int wgrad_tn_im2col(const float* X, const Im2col& g, const float* B, int ldb, float* dW, int ldw, int M, int Kd,
-                    int N, cudaStream_t st) {
+                    int N, cudaStream_t st, PackWs wp) {
+  if (wgrad_tc_eligible(M, Kd, N, wp.p, wp.bytes)) return wgrad_tc_im2col(X, g, B, ldb, dW, ldw, M, Kd, N, wp.p, st);
   Im2colA a{X, g, M, Kd};
   return launch_wgrad(a, B, ldb, dW, ldw, M, Kd, N, st);
 }

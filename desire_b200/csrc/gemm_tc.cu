@@ -122,6 +122,67 @@ struct Im2colA8 {
   }
 };
 
+// ---- transposed loaders for the weight-gradient GEMM dW[Kd,N] = A^T[Kd,rows] @ B[rows,N]: the GEMM's "row" is kd
+// (one thread each) and its K dimension runs over the sample rows, so a warp's 32 threads read 32 consecutive kd of
+// one sample row = one coalesced 128-byte request, and the values land directly in the K-major UMMA layout.
+struct TransDenseA8 {
+  const float* A;      // [rows, Kd] row-major, lda
+  int lda, M /*= Kd*/, K /*= rows*/;
+  const float* col;    // A + kd, null past Kd
+  __device__ __forceinline__ void init(int m) { col = m < M ? A + m : nullptr; }
+  __device__ __forceinline__ void load_stage(int ks, float (*v)[8]) const {
+    const long r0 = (long)ks * BK;
+#pragma unroll
+    for (int c = 0; c < KC; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long r = r0 + c * 8 + i;
+        v[c][i] = (col && r < K) ? __ldg(col + r * lda) : 0.f;
+      }
+  }
+};
+
+struct TransIm2colA8 {
+  const float* X;      // NHWC image the patches are cut from
+  Im2col g;
+  int M /*= Kd = kh*kw*Ci*/, K /*= rows = imgs*Ho*Wo*/;
+  int ky, kx, ci;      // this thread's (tap, channel); ci < 0 past Kd
+  __device__ __forceinline__ void init(int m) {
+    ci = -1;
+    if (m >= M) return;
+    ci = m % g.Ci;
+    const int t2 = m / g.Ci;
+    kx = t2 % g.kw;
+    ky = t2 / g.kw;
+  }
+  __device__ __forceinline__ void load_stage(int ks, float (*v)[8]) const {
+    const long r0 = (long)ks * BK;
+    int ox = (int)(r0 % g.Wo);
+    long t = r0 / g.Wo;
+    int oy = (int)(t % g.Ho);
+    long img = t / g.Ho;
+#pragma unroll
+    for (int c = 0; c < KC; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x = 0.f;
+        if (ci >= 0 && r0 + c * 8 + i < K) {
+          const int iy = oy * g.stride + ky - g.pad_t, ix = ox * g.stride + kx - g.pad_l;
+          if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+            x = __ldg(X + (((size_t)img * g.Hi + iy) * g.Wi + ix) * g.Ci + ci);
+        }
+        v[c][i] = x;
+        if (++ox == g.Wo) {
+          ox = 0;
+          if (++oy == g.Ho) {
+            oy = 0;
+            ++img;
+          }
+        }
+      }
+  }
+};
+
 // W [K,N] (or [N,K] when trans) FP32 -> packed[(jn*nks + ks)] = { hi: [KC][BN][8] bf16, lo: same }
 __global__ void pack_b_kernel(const float* __restrict__ W, int ldw, int trans, int K, int N, int BN, int nks,
                               int ntn, uint4* __restrict__ out) {
@@ -150,8 +211,8 @@ __global__ void pack_b_kernel(const float* __restrict__ W, int ldw, int trans, i
 template <class ALoad>
 __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __restrict__ Bp,
                                                        const float* __restrict__ bias, float* __restrict__ C, int ldc,
-                                                       int M, int N, int BN, int nks, int stages, int act,
-                                                       int accumulate, int passes, uint32_t tmem_cols) {
+                                                       int M, int N, int BN, int nks_total, int stages, int act,
+                                                       int accumulate, int passes, uint32_t tmem_cols, int ks_split) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int a_half = KC * TM * 16;              // bytes of A_hi (== A_lo) per stage
   const int b_half = KC * BN * 16;
@@ -164,6 +225,10 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int jn = blockIdx.x, m0 = blockIdx.y * TM;
   ALoad A = A_;
+  // split-K (weight gradients): slice blockIdx.z runs K stages [ks_begin, ks_begin + nks) and adds its partial tile
+  // with atomics (accumulate == 2)
+  const int ks_begin = ks_split > 0 ? (int)blockIdx.z * ks_split : 0;
+  const int nks = ks_split > 0 ? min(ks_split, nks_total - ks_begin) : nks_total;
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -185,8 +250,8 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
     const int m = m0 + tid;
     A.init(m);
     float v0[KC][8], v1[KC][8];
-    A.load_stage(0, v0);
-    if (nks > 1) A.load_stage(1, v1);
+    A.load_stage(ks_begin, v0);
+    if (nks > 1) A.load_stage(ks_begin + 1, v1);
     auto emit = [&](int ks, float (*v)[8]) {
       const int slot = ks % stages;
       const uint32_t ph = (ks / stages) & 1;
@@ -205,10 +270,10 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
     // manually unrolled by two so each register buffer is addressed statically (loads stay asynchronous)
     for (int ks = 0; ks < nks; ks += 2) {
       emit(ks, v0);
-      if (ks + 2 < nks) A.load_stage(ks + 2, v0);
+      if (ks + 2 < nks) A.load_stage(ks_begin + ks + 2, v0);
       if (ks + 1 < nks) {
         emit(ks + 1, v1);
-        if (ks + 3 < nks) A.load_stage(ks + 3, v1);
+        if (ks + 3 < nks) A.load_stage(ks_begin + ks + 3, v1);
       }
     }
     // ===================== epilogue: TMEM lanes 32*warp .. +31 == rows m0 + tid
@@ -225,7 +290,13 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
       if (m < M) {
         float* crow = C + (size_t)m * ldc + n0 + c0;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + ncol <= N);
-        if (vec_ok) {
+        if (accumulate == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j >= ncol || n0 + c0 + j >= N) break;
+            atomicAdd(crow + j, acc[j]);
+          }
+        } else if (vec_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (j >= ncol) break;
@@ -290,7 +361,7 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
   } else {
     // ===================== B loader: one bulk TMA copy per stage
     if (lane == 0) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(Bp) + (size_t)jn * nks * (2 * b_half);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(Bp) + ((size_t)jn * nks_total + ks_begin) * (2 * b_half);
       for (int ks = 0; ks < nks; ++ks) {
         const int slot = ks % stages;
         const uint32_t ph = (ks / stages) & 1;
@@ -377,7 +448,7 @@ int run_tc(const ALoad& A, const void* packed, const float* bias, float* C, int 
   dim3 grid(p.ntn, (M + TM - 1) / TM);
   DESIRE_LAUNCH(st, (gemm_tc_kernel<ALoad><<<grid, NTHR, p.smem, st>>>(A, (const uint4*)packed, bias, C, ldc, M, N, p.BN,
                                                                        p.nks, p.stages, act, accumulate ? 1 : 0,
-                                                                       g_gemm_mode == 1 ? 1 : 3, p.tmem_cols)));
+                                                                       g_gemm_mode == 1 ? 1 : 3, p.tmem_cols, 0)));
   return DESIRE_OK;
 }
 
@@ -388,9 +459,54 @@ int launch_tc(const ALoad& A, const float* W, int ldw, bool trans_b, const float
   return run_tc(A, pack_ws, bias, C, ldc, M, N, K, act, accumulate, st);
 }
 
+
+template <class ALoad>
+int run_wgrad_tc(const ALoad& A, const float* B, int ldb, float* dW, int ldw, int rows, int Kd, int N, void* pack_ws,
+                 cudaStream_t st) {
+  // GEMM view: M = Kd, K = rows; B [rows,N] is packed like a weight matrix (its K dimension is the sample rows)
+  const Plan p = make_plan(N, rows, Kd);
+  DESIRE_TRY(pack_for_plan(p, B, ldb, false, rows, N, pack_ws, st));
+  const int gy = (Kd + TM - 1) / TM;
+  const int tiles = p.ntn * gy;
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  const int max_splits = p.nks / 8 > 0 ? p.nks / 8 : 1;       // at least 8 K stages (256 rows) per slice
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int ks_split = (p.nks + splits - 1) / splits;
+  splits = (p.nks + ks_split - 1) / ks_split;
+  int stages = p.stages;
+  if (stages > ks_split) stages = ks_split < 2 ? 2 : ks_split;
+  const size_t stage = 2 * (size_t)KC * TM * 16 + 2 * (size_t)KC * p.BN * 16;
+  const size_t smem = stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  DESIRE_ENSURE_SMEM(gemm_tc_kernel<ALoad>, smem);
+  dim3 grid(p.ntn, gy, splits);
+  DESIRE_LAUNCH(st, (gemm_tc_kernel<ALoad><<<grid, NTHR, smem, st>>>(A, (const uint4*)pack_ws, nullptr, dW, ldw, Kd, N, p.BN,
+                                                                     p.nks, stages, DESIRE_ACT_NONE, 2,
+                                                                     g_gemm_mode == 1 ? 1 : 3, p.tmem_cols, ks_split)));
+  return DESIRE_OK;
+}
+
 }  // namespace
 
 size_t gemm_tc_pack_bytes(int N, int K) { return align_up(make_plan(N, K).pack_bytes); }
+
+// ---- weight gradients on tcgen05: dW[Kd,N] += A^T @ B over `rows` sample rows (A dense or implicit im2col)
+size_t wgrad_tc_pack_bytes(int rows, int N) { return align_up(make_plan(N, rows).pack_bytes); }
+bool wgrad_tc_eligible(int rows, int Kd, int N, const void* pack_ws, size_t pack_bytes) {
+  return g_gemm_mode != 0 && Kd >= 64 && N >= 16 && rows >= 2048 && pack_ws &&
+         pack_bytes >= make_plan(N, rows).pack_bytes && (Kd + TM - 1) / TM <= 65535;
+}
+int wgrad_tc(const float* A, int lda, const float* B, int ldb, float* dW, int ldw, int rows, int Kd, int N, void* pack_ws,
+             cudaStream_t st) {
+  TransDenseA8 a{A, lda, Kd, rows, nullptr};
+  return run_wgrad_tc(a, B, ldb, dW, ldw, rows, Kd, N, pack_ws, st);
+}
+int wgrad_tc_im2col(const float* X, const Im2col& g, const float* B, int ldb, float* dW, int ldw, int rows, int Kd, int N,
+                    void* pack_ws, cudaStream_t st) {
+  TransIm2colA8 a{X, g, Kd, rows, 0, 0, -1};
+  return run_wgrad_tc(a, B, ldb, dW, ldw, rows, Kd, N, pack_ws, st);
+}
+
 
 // Packed BF16 hi/lo image of W for an explicit n-tile width BN (used by the GRU kernel): per
 // (n-tile, 32-wide k stage) one contiguous block { hi [4][BN][8], lo [4][BN][8] }.

@@ -961,7 +961,7 @@ __global__ void scene_gather_bwd_kernel(const float* __restrict__ dfs, int ld, i
 
 struct IocTrainLayout {
   size_t snaps, dscore, dDY, rows, Xs, XP, dXP, fsp, hs2, dhs, pooled, h0e, dh0, dpre, cnt, dX48, vel, dsT, bptt, pack,
-      fwd, total;
+      wpack, wpack_bytes, fwd, total;
 };
 IocTrainLayout ioc_train_layout(const desire_ioc_dims_t* d) {
   const size_t R = (size_t)d->B * d->N * d->K, T = d->Tf, H = d->H, M = (size_t)d->B * d->N;
@@ -994,6 +994,12 @@ IocTrainLayout ioc_train_layout(const desire_ioc_dims_t* d) {
   L.dsT = take(R * T * 4);
   L.bptt = take(gru_bptt_ws_bytes(R, (int)H));
   L.pack = take(PACK_WS_BYTES);
+  {
+    // packed B operands of the tcgen05 weight gradients: dpre [R,H] (social fc) and dXP [R*T, 2H] (Decoder-2 inputs)
+    const size_t a = wgrad_tc_pack_bytes((int)R, (int)H), b = wgrad_tc_pack_bytes((int)(R * T), 2 * (int)H);
+    L.wpack_bytes = a > b ? a : b;
+    L.wpack = take(L.wpack_bytes);
+  }
   L.fwd = take(ioc_layout(d).total);
   L.total = off;
   return L;
@@ -1028,6 +1034,7 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
         *dXP = fp(L.dXP), *fsp = fp(L.fsp), *hs2 = fp(L.hs2), *dhs = fp(L.dhs), *pooled = fp(L.pooled), *h0e = fp(L.h0e),
         *dh0 = fp(L.dh0), *dpre = fp(L.dpre), *cnt = fp(L.cnt), *dX48 = fp(L.dX48), *vel = fp(L.vel), *dsT = fp(L.dsT);
   PackWs pw{base + L.pack, PACK_WS_BYTES};
+  PackWs wp{base + L.wpack, L.wpack_bytes};
   const size_t f4 = sizeof(float);
   const desire_gru_t& gw = w->dec2;
   const desire_gru_grad_t& gg = g->dec2;
@@ -1107,7 +1114,7 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
       DESIRE_TRY(act_bwd_post(fsp + (size_t)t * H, T * H, dpre, H, (size_t)R, H, DESIRE_ACT_RELU, st));
       DESIRE_TRY(social_pool_launch(Yi + 2 * t, 2L * T, hp, hp_ld, obs, Tp, d->B, N, K, H, d->n_rad, d->n_ang, w->r2_edges,
                                     w->dirs, pooled, st));
-      DESIRE_TRY(wgrad_tn(pooled, G * H, dpre, H, g->sp_w, H, (int)R, G * H, H, st));
+      DESIRE_TRY(wgrad_tn(pooled, G * H, dpre, H, g->sp_w, H, (int)R, G * H, H, st, wp));
       DESIRE_TRY(colsum_acc(dpre, H, (int)R, H, g->sp_b, st));
       if (t == 0) return DESIRE_OK;                         // h2_{-1} = H_x is a constant of this module
       DESIRE_TRY(sgemm(dpre, H, w->sp_w, H, true, nullptr, pooled, G * H, (int)R, G * H, H, DESIRE_ACT_NONE, false, st, pw));
@@ -1121,10 +1128,10 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
     DESIRE_TRY(gru_bptt(a, base + L.bptt, L.pack - L.bptt, st, &social_bwd));
     // ---- input rows of Decoder-2: static features, social feature, biases
     const int RT = (int)(R * T);
-    DESIRE_TRY(wgrad_tn(Xs, Dst, dXP, 3 * H, gg.wg, 2 * H, RT, Dst, 2 * H, st));
-    DESIRE_TRY(wgrad_tn(Xs, Dst, dXP + 2 * H, 3 * H, gg.wc, H, RT, Dst, H, st));
-    DESIRE_TRY(wgrad_tn(fsp, H, dXP, 3 * H, gg.wg + (size_t)Dst * 2 * H, 2 * H, RT, H, 2 * H, st));
-    DESIRE_TRY(wgrad_tn(fsp, H, dXP + 2 * H, 3 * H, gg.wc + (size_t)Dst * H, H, RT, H, H, st));
+    DESIRE_TRY(wgrad_tn(Xs, Dst, dXP, 3 * H, gg.wg, 2 * H, RT, Dst, 2 * H, st, wp));
+    DESIRE_TRY(wgrad_tn(Xs, Dst, dXP + 2 * H, 3 * H, gg.wc, H, RT, Dst, H, st, wp));
+    DESIRE_TRY(wgrad_tn(fsp, H, dXP, 3 * H, gg.wg + (size_t)Dst * 2 * H, 2 * H, RT, H, 2 * H, st, wp));
+    DESIRE_TRY(wgrad_tn(fsp, H, dXP + 2 * H, 3 * H, gg.wc + (size_t)Dst * H, H, RT, H, H, st, wp));
     DESIRE_TRY(colsum_acc(dXP, 3 * H, RT, 2 * H, gg.bg, st));
     DESIRE_TRY(colsum_acc(dXP + 2 * H, 3 * H, RT, H, gg.bc, st));
     // d [fv | fs] = dXP @ W[rows 0..Fv+Cs)^T

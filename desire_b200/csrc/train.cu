@@ -663,10 +663,14 @@ static size_t dec_bwd_row_floats() {
   // col 51200 | y1 2048 a1 2048 | y2 4096 a2 4096 | y3 8192 a3 8192 | y4 1024 | g3 8192 g2 4096 g1 2048 g4 1024
   return 51200 + 2 * 2048 + 2 * 4096 + 2 * 8192 + 1024 + 8192 + 4096 + 2048 + 1024;
 }
+static size_t dec_bwd_wpack_bytes(int rc, int Z) {
+  // packed B operands of the tcgen05 weight gradients: a2 [rc*64,64], a1 [rc*16,128], z [rc,Z]
+  size_t a = wgrad_tc_pack_bytes(rc * 64, 64), b = wgrad_tc_pack_bytes(rc * 16, 128), c = wgrad_tc_pack_bytes(rc, Z);
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
+}
 extern "C" size_t desire_cvae_decode_bwd_workspace_bytes(int R, int Z) {
-  (void)Z;
   const size_t rc = R < DEC_BWD_CHUNK ? R : DEC_BWD_CHUNK;
-  return align_up(rc * dec_bwd_row_floats() * 4) + 16 * 256 + PACK_WS_BYTES;
+  return align_up(rc * dec_bwd_row_floats() * 4) + 16 * 256 + PACK_WS_BYTES + dec_bwd_wpack_bytes((int)rc, Z);
 }
 
 extern "C" int desire_cvae_decode_bwd(const float* z, int R, int Z, const desire_cvae_dec_t* w, const float* dxr,
@@ -695,7 +699,9 @@ extern "C" int desire_cvae_decode_bwd(const float* z, int R, int Z, const desire
     float* g1 = W.take<float>(n * 2048);
     float* g4 = W.take<float>(n * 1024);
     PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
-    if (!pw.p) {
+    const size_t wpb = dec_bwd_wpack_bytes(rc, Z);
+    PackWs wp{W.take<char>(wpb), wpb};
+    if (!pw.p || !wp.p) {
       set_error("desire_cvae_decode_bwd: workspace too small");
       return DESIRE_ERR_WORKSPACE;
     }
@@ -722,16 +728,16 @@ extern "C" int desire_cvae_decode_bwd(const float* z, int R, int Z, const desire
     // layer 3: 8x8x64 -> 16x16x32
     DESIRE_TRY(bn_row_bwd(y3, rc, 256, 32, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, g3, g->d3.gamma, g->d3.beta, st));
     Im2col i3{16, 16, 32, 8, 8, 5, 5, 2, 1, 1};
-    DESIRE_TRY(wgrad_tn_im2col(g3, i3, a2, 64, g->d3.w, 64, rc * 64, 800, 64, st));
+    DESIRE_TRY(wgrad_tn_im2col(g3, i3, a2, 64, g->d3.w, 64, rc * 64, 800, 64, st, wp));
     DESIRE_TRY(sgemm_im2col(g3, i3, w->d3.w, 64, nullptr, g2, 64, rc * 64, 64, 800, DESIRE_ACT_NONE, st, pw));
     // layer 2: 4x4x128 -> 8x8x64 (VALID)
     DESIRE_TRY(bn_row_bwd(y2, rc, 64, 64, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, g2, g->d2.gamma, g->d2.beta, st));
     Im2col i2{8, 8, 64, 4, 4, 5, 5, 1, 0, 0};
-    DESIRE_TRY(wgrad_tn_im2col(g2, i2, a1, 128, g->d2.w, 128, rc * 16, 1600, 128, st));
+    DESIRE_TRY(wgrad_tn_im2col(g2, i2, a1, 128, g->d2.w, 128, rc * 16, 1600, 128, st, wp));
     DESIRE_TRY(sgemm_im2col(g2, i2, w->d2.w, 128, nullptr, g1, 128, rc * 16, 128, 1600, DESIRE_ACT_NONE, st, pw));
     // layer 1: 1x1xZ -> 4x4x128 (a plain GEMM: y1[r,(y,x,o)] = z[r,:] . W[(y,x,o),:])
     DESIRE_TRY(bn_row_bwd(y1, rc, 16, 128, w->d1.gamma, w->d1.beta, DESIRE_ACT_ELU, g1, g->d1.gamma, g->d1.beta, st));
-    DESIRE_TRY(wgrad_tn(g1, 2048, zc, Z, g->d1.w, Z, rc, 2048, Z, st));
+    DESIRE_TRY(wgrad_tn(g1, 2048, zc, Z, g->d1.w, Z, rc, 2048, Z, st, wp));
     DESIRE_TRY(sgemm(g1, 2048, w->d1.w, Z, false, nullptr, dz + (size_t)r0 * Z, Z, rc, Z, 2048, DESIRE_ACT_NONE, false, st, pw));
   }
   return DESIRE_OK;
@@ -850,4 +856,13 @@ extern "C" int desire_adam_step(float* p, const float* g, float* m, float* v, lo
   DESIRE_LAUNCH(st, (adam_kernel<<<grid1d((size_t)n), 256, 0, st>>>(p, g, m, v, (size_t)n, sumsq, (float)lr_t, beta1, beta2,
                                                                    eps, clip, grad_scale)));
   return DESIRE_OK;
+}
+
+// generic weight-gradient product (the backward twin of desire_fc_fwd's W): dW[K,N] (lddw) += A[M,K]^T @ dC[M,N]
+extern "C" size_t desire_wgrad_workspace_bytes(int M, int N) { return wgrad_tc_pack_bytes(M, N); }
+extern "C" int desire_wgrad_tn(const float* A, int lda, const float* dC, int lddc, float* dW, int lddw, int M, int N, int K,
+                               void* ws, size_t ws_bytes, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(A && dC && dW && M >= 0 && N > 0 && K > 0 && lda >= K && lddc >= N && lddw >= N,
+                   "desire_wgrad_tn: bad arguments");
+  return wgrad_tn(A, lda, dC, lddc, dW, lddw, M, K, N, (cudaStream_t)stream, PackWs{ws, ws_bytes});
 }

@@ -302,6 +302,13 @@ int desire_scene_cnn_bwd(const float* img, int B, int Hi, int Wi, int Cs, const 
                          float* dfmap, const desire_scene_cnn_grad_t* g, void* ws, size_t ws_bytes,
                          desire_stream_t stream);
 
+/* generic weight-gradient product, the backward twin of desire_fc_fwd's W: dW[K,N] (lddw) += A[M,K]^T @ dC[M,N].
+ * With ws >= desire_wgrad_workspace_bytes(M,N) (the packed BF16 image of dC) and K >= 64, N >= 16, M >= 2048 it runs
+ * on tcgen05 (3xBF16, split over the rows, atomics); otherwise on FP32 CUDA cores (ws may be NULL). */
+size_t desire_wgrad_workspace_bytes(int M, int N);
+int desire_wgrad_tn(const float* A, int lda, const float* dC, int lddc, float* dW, int lddw, int M, int N, int K,
+                    void* ws, size_t ws_bytes, desire_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -257,3 +257,31 @@ def test_full_train_step_with_ioc_reduces_both_costs():
         hist.append((float(tp.buf["cost"][0]), float(tp.buf["ioc_cost"][0])))
     print(hist)
     assert hist[-1][0] < hist[0][0] and hist[-1][1] < hist[0][1], hist
+
+
+@pytest.mark.parametrize("M,K,N,lda,ldc", [(50000, 300, 96, 300, 96), (4096, 4608, 128, 4608, 128), (38400, 248, 256, 248, 384),
+                                          (2500, 64, 16, 70, 20), (1000, 128, 128, 128, 128), (9000, 25, 32, 25, 32)])
+def test_wgrad_tn_matches_float64(lib, M, K, N, lda, ldc):
+    """dW += A^T @ dC on the tcgen05 split-K path (large shapes) and the FP32 fallback (small ones), vs float64."""
+    import ctypes as C
+    rng = np.random.default_rng(M + K)
+    A = rng.standard_normal((M, lda)).astype(np.float32)
+    dC = rng.standard_normal((M, ldc)).astype(np.float32)
+    ref = A[:, :K].astype(np.float64).T @ dC[:, :N].astype(np.float64)
+    dA, dD = torch.from_numpy(A).cuda(), torch.from_numpy(dC).cuda()
+    dW = torch.ones(K, N, device="cuda")                  # += semantics: starts at 1
+    wsb = lib.desire_wgrad_workspace_bytes(M, N)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device="cuda")
+    for mode in (3, 0):
+        dW.fill_(1.0)
+        lib.desire_set_gemm_mode(mode)
+        try:
+            rc = lib.desire_wgrad_tn(C.c_void_p(dA.data_ptr()), lda, C.c_void_p(dD.data_ptr()), ldc, C.c_void_p(dW.data_ptr()), N,
+                                     M, N, K, C.c_void_p(ws.data_ptr()), wsb, None)
+        finally:
+            lib.desire_set_gemm_mode(3)
+        assert rc == 0
+        torch.cuda.synchronize()
+        e = rel_l2((dW.cpu().numpy().astype(np.float64) - 1.0).reshape(-1), ref.reshape(-1))
+        print("wgrad M=%d K=%d N=%d mode %d rel-L2 %.3e" % (M, K, N, mode, e))
+        assert e <= 2e-5
