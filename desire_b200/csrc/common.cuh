@@ -266,8 +266,9 @@ int deconv1c_tc(const float* X, int R, const float* W, const float* bias, const 
                 float* Y, void* pack_ws, cudaStream_t st);
 
 // col2im + bias + per-row BN + activation (cvae.cu): col [R*Hin*Hin, k*k*Cout] -> out [R,Hout,Hout,Cout]
+// ypre (optional, train step): also stores the pre-BN values (col2im + bias) [R,Hout,Hout,Cout]
 int colbn_act(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int Cout,
               const float* bias, const float* gamma, const float* beta, int act, float* out,
-              cudaStream_t st);
+              cudaStream_t st, float* ypre = nullptr);
 
 }  // namespace desire

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) colbn_act_v4_kernel(const float* __restri
                                                            int Cout, const float* __restrict__ bias,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, int act,
-                                                           float* __restrict__ out) {
+                                                           float* __restrict__ out, float* __restrict__ ypre) {
   extern __shared__ __align__(16) float sm[];
   const int Pout = Hout * Hout, n = Pout * Cout, C4 = Cout / 4;
   float* tile = sm;
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256) colbn_act_v4_kernel(const float* __restri
       }
     }
     reinterpret_cast<float4*>(tile)[e] = acc;
+    if (ypre) reinterpret_cast<float4*>(ypre + r * (size_t)n)[e] = acc;   // train step: pre-BN values for the backward
   }
   __syncthreads();
 
@@ -266,26 +267,27 @@ __global__ void __launch_bounds__(256) deconv1ch_bn_act_kernel(const float* __re
 
 template <int KS, int S>
 int launch_v4(const float* col, int R, int Hin, int Hout, int pad, int Cout, const float* bias, const float* gamma,
-              const float* beta, int act, float* out, size_t smem, cudaStream_t st) {
+              const float* beta, int act, float* out, size_t smem, cudaStream_t st, float* ypre) {
   DESIRE_ENSURE_SMEM((colbn_act_v4_kernel<KS, S>), 227 * 1024);
-  DESIRE_LAUNCH(st, (colbn_act_v4_kernel<KS, S><<<R, 256, smem, st>>>(col, Hin, Hout, pad, Cout, bias, gamma, beta, act, out)));
+  DESIRE_LAUNCH(st, (colbn_act_v4_kernel<KS, S><<<R, 256, smem, st>>>(col, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, ypre)));
   return DESIRE_OK;
 }
 
 }  // namespace
 
 int colbn_act(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int Cout, const float* bias,
-              const float* gamma, const float* beta, int act, float* out, cudaStream_t st) {
+              const float* gamma, const float* beta, int act, float* out, cudaStream_t st, float* ypre) {
   if (R == 0) return DESIRE_OK;
   if (Cout % 4 == 0 && Cout <= 256 && 256 % Cout == 0) {
     const size_t smem4 = ((size_t)Hout * Hout * Cout + 256 + 2 * Cout) * sizeof(float);
     if (smem4 <= 227 * 1024) {
-      if (k == 1 && stride == 1) return launch_v4<1, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st);
-      if (k == 4 && stride == 1) return launch_v4<4, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st);
-      if (k == 5 && stride == 1) return launch_v4<5, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st);
-      if (k == 5 && stride == 2) return launch_v4<5, 2>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st);
+      if (k == 1 && stride == 1) return launch_v4<1, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st, ypre);
+      if (k == 4 && stride == 1) return launch_v4<4, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st, ypre);
+      if (k == 5 && stride == 1) return launch_v4<5, 1>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st, ypre);
+      if (k == 5 && stride == 2) return launch_v4<5, 2>(col, R, Hin, Hout, pad, Cout, bias, gamma, beta, act, out, smem4, st, ypre);
     }
   }
+  DESIRE_CHECK_ARG(!ypre, "colbn_act: pre-BN output needs the vectorised kernel (Cout %% 4 == 0, known k/stride)");
   DESIRE_CHECK_ARG(Cout >= 1 && Cout <= 256 && 256 % Cout == 0, "colbn_act: Cout=%d unsupported", Cout);
   size_t smem = ((size_t)Hout * Hout * Cout + 256 + 2 * Cout) * sizeof(float);
   DESIRE_CHECK_ARG(smem <= 227 * 1024, "colbn_act: tile too large");

@@ -134,8 +134,8 @@ int launch(const L& a, const float* B, int ldb, bool trans_b, const float* bias,
 // The reduction runs over the ROWS (up to millions), so the grid splits them (blockIdx.z) and the
 // partial tiles are added with atomicAdd (the caller zeroes dW once per step).  Loads are coalesced
 // along kd / n; A comes through the same loaders as the forward GEMM (dense rows or implicit im2col).
-constexpr int WBM = 128, WBN = 64, WBK = 16;
-template <class ALoader>
+constexpr int WBN = 64, WBK = 16;
+template <class ALoader, int WBM>      // WBM = kd rows per tile: 128, or 32 for the narrow filters (Kd <= 32)
 __global__ void __launch_bounds__(NT) wgrad_tn_kernel(ALoader A, const float* __restrict__ B, int ldb,
                                                       float* __restrict__ dW, int ldw, int M, int Kd, int N,
                                                       int rows_per_split) {
@@ -146,9 +146,10 @@ __global__ void __launch_bounds__(NT) wgrad_tn_kernel(ALoader A, const float* __
   const int ty = tid / 16, tx = tid % 16;
   const long m_begin = (long)blockIdx.z * rows_per_split;
   const long m_end = (m_begin + rows_per_split < M) ? m_begin + rows_per_split : M;
-  float acc[8][4];
+  constexpr int RI = WBM / 16;           // kd rows per thread
+  float acc[RI][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (long m0 = m_begin; m0 < m_end; m0 += WBK) {
@@ -174,21 +175,21 @@ __global__ void __launch_bounds__(NT) wgrad_tn_kernel(ALoader A, const float* __
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < WBK; ++k) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      float av[RI];
+#pragma unroll
+      for (int i = 0; i < RI; ++i) av[i] = As[k][ty * RI + i];
       float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < RI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int kd = k_blk + ty * 8 + i;
+  for (int i = 0; i < RI; ++i) {
+    const int kd = k_blk + ty * RI + i;
     if (kd >= Kd) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(NT) wgrad_tn_kernel(ALoader A, const float* __
 template <class L>
 int launch_wgrad(const L& a, const float* B, int ldb, float* dW, int ldw, int M, int Kd, int N, cudaStream_t st) {
   if (M == 0 || N == 0 || Kd == 0) return DESIRE_OK;
+  const int WBM = Kd <= 32 ? 32 : 128;
   const int gx = (N + WBN - 1) / WBN, gy = (Kd + WBM - 1) / WBM;
   // ~4 CTAs per SM in flight; every split at least 256 rows
   int splits = (148 * 4 + gx * gy - 1) / (gx * gy);
@@ -212,7 +214,10 @@ int launch_wgrad(const L& a, const float* B, int ldb, float* dW, int ldw, int M,
   rows = (rows + WBK - 1) / WBK * WBK;
   splits = (M + rows - 1) / rows;
   dim3 grid(gx, gy, splits);
-  DESIRE_LAUNCH(st, (wgrad_tn_kernel<L><<<grid, NT, 0, st>>>(a, B, ldb, dW, ldw, M, Kd, N, rows)));
+  if (WBM == 32)
+    DESIRE_LAUNCH(st, (wgrad_tn_kernel<L, 32><<<grid, NT, 0, st>>>(a, B, ldb, dW, ldw, M, Kd, N, rows)));
+  else
+    DESIRE_LAUNCH(st, (wgrad_tn_kernel<L, 128><<<grid, NT, 0, st>>>(a, B, ldb, dW, ldw, M, Kd, N, rows)));
   return DESIRE_OK;
 }
 

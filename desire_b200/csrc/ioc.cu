@@ -870,42 +870,53 @@ __global__ void vel_kernel(const float* __restrict__ Y, const float* __restrict_
   v[rt * 2 + 1] = Y[rt * 2 + 1] - py;
 }
 
-// number of pooled neighbours per (row, bin): one warp per row, same binning arithmetic as the forward kernels
-__global__ void social_count_kernel(const float* __restrict__ pos, long pos_stride, const float* __restrict__ obs,
-                                    int Tp, long R, int N, int K, int n_rad, int n_ang,
-                                    const float* __restrict__ r2_edges, const float* __restrict__ dirs,
-                                    float* __restrict__ cnt) {
-  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// number of pooled neighbours per (row, bin): one warp per row i, lanes over the neighbours j (same binning
+// arithmetic as the forward kernels); __match_any groups the lanes of equal bin and the group leader bumps the
+// warp's shared-memory histogram.
+constexpr int SB_WARPS = 8;
+__global__ void __launch_bounds__(SB_WARPS * 32) social_count_kernel(
+    const float* __restrict__ pos, long pos_stride, const float* __restrict__ obs, int Tp, long R, int N, int K, int n_rad,
+    int n_ang, const float* __restrict__ r2_edges, const float* __restrict__ dirs, float* __restrict__ cnt) {
+  __shared__ int hist[SB_WARPS][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * SB_WARPS + warp;
   if (row >= R) return;
-  const int G = n_rad * n_ang;
+  const int G = n_rad * n_ang;            // <= 64
   const int k = (int)(row % K);
   const long bi = row / K;
   const int i = (int)(bi % N);
   const long b = bi / N;
+  hist[warp][lane] = 0;
+  hist[warp][lane + 32] = 0;
+  __syncwarp();
   const float xi = __ldg(pos + row * pos_stride), yi = __ldg(pos + row * pos_stride + 1);
-  for (int g0 = 0; g0 < G; g0 += 32) {          // lanes own bins g0+lane; every lane scans all neighbours
-    float c = 0.f;
-    for (int j = 0; j < N; ++j) {
-      if (j == i || __ldg(obs + ((size_t)(b * N + j) * Tp) * 3) == 0.f) continue;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    const int j = j0 + lane;
+    int g = -1;
+    if (j < N && j != i && __ldg(obs + ((size_t)(b * N + j) * Tp) * 3) != 0.f) {
       const long rj = (b * N + j) * K + k;
       const float dx = __ldg(pos + rj * pos_stride) - xi, dy = __ldg(pos + rj * pos_stride + 1) - yi;
-      const int g = logpolar_bin(dx, dy, r2_edges, n_rad, dirs, n_ang);
-      c += (g == g0 + lane) ? 1.f : 0.f;
+      g = logpolar_bin(dx, dy, r2_edges, n_rad, dirs, n_ang);
     }
-    if (g0 + lane < G) cnt[row * G + g0 + lane] = c;
+    const unsigned m = __match_any_sync(0xffffffffu, g);
+    if (g >= 0 && (__ffs(m) - 1) == lane) hist[warp][g] += __popc(m);
+    __syncwarp();
   }
+  for (int g = lane; g < G; g += 32) cnt[row * G + g] = (float)hist[warp][g];
 }
 
 // transpose of the pooling: dh[j,:] += sum_{i != j, bin(pos_j - pos_i) = g >= 0} dpooled[i, g, :] / cnt[i, g]
-// one warp per row j (lanes over H)
-__global__ void social_pool_bwd_kernel(const float* __restrict__ pos, long pos_stride, const float* __restrict__ obs,
-                                       int Tp, long R, int N, int K, int H, int n_rad, int n_ang,
-                                       const float* __restrict__ r2_edges, const float* __restrict__ dirs,
-                                       const float* __restrict__ dpooled, const float* __restrict__ cnt,
-                                       float* __restrict__ dh, long dh_rs) {
-  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// One warp per row j.  Phase 1: lanes over the rows i that pooled j — bin of (pos_j - pos_i) and the weight
+// 1/cnt[i,g], kept in shared memory; phase 2: lanes over the hidden columns (float4 each) walk the valid pairs.
+__global__ void __launch_bounds__(SB_WARPS * 32) social_pool_bwd_kernel(
+    const float* __restrict__ pos, long pos_stride, const float* __restrict__ obs, int Tp, long R, int N, int K, int H,
+    int n_rad, int n_ang, const float* __restrict__ r2_edges, const float* __restrict__ dirs,
+    const float* __restrict__ dpooled, const float* __restrict__ cnt, float* __restrict__ dh, long dh_rs, int Np) {
+  extern __shared__ __align__(16) uint8_t spw_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* src = reinterpret_cast<int*>(spw_smem) + (size_t)warp * 2 * Np;       // [Np] source offset ri*G+g (or -1)
+  float* wgt = reinterpret_cast<float*>(src + Np);                          // [Np]
+  const long row = (long)blockIdx.x * SB_WARPS + warp;
   if (row >= R) return;
   const int G = n_rad * n_ang;
   const int k = (int)(row % K);
@@ -914,18 +925,40 @@ __global__ void social_pool_bwd_kernel(const float* __restrict__ pos, long pos_s
   const long b = bj / N;
   if (__ldg(obs + ((size_t)(b * N + j) * Tp) * 3) == 0.f) return;    // a non-existent agent is never pooled
   const float xj = __ldg(pos + row * pos_stride), yj = __ldg(pos + row * pos_stride + 1);
-  for (int c0 = 0; c0 < H; c0 += 32) {
-    const int c = c0 + lane;
-    float acc = 0.f;
-    for (int i = 0; i < N; ++i) {
-      if (i == j) continue;
-      const long ri = (b * N + i) * K + k;
+  int nvalid = 0;
+  for (int i0 = 0; i0 < N; i0 += 32) {
+    const int i = i0 + lane;
+    int g = -1;
+    long ri = 0;
+    if (i < N && i != j) {
+      ri = (b * N + i) * K + k;
       const float dx = xj - __ldg(pos + ri * pos_stride), dy = yj - __ldg(pos + ri * pos_stride + 1);
-      const int g = logpolar_bin(dx, dy, r2_edges, n_rad, dirs, n_ang);
-      if (g < 0) continue;
-      if (c < H) acc += dpooled[(ri * G + g) * (long)H + c] / fmaxf(cnt[ri * G + g], 1.f);
+      g = logpolar_bin(dx, dy, r2_edges, n_rad, dirs, n_ang);
     }
-    if (c < H) dh[row * dh_rs + c] += acc;
+    // compact the valid pairs of this chunk (ascending i)
+    const unsigned m = __ballot_sync(0xffffffffu, g >= 0);
+    if (g >= 0) {
+      const int slot = nvalid + __popc(m & ((1u << lane) - 1u));
+      src[slot] = (int)(ri * G + g);
+      wgt[slot] = 1.f / fmaxf(cnt[ri * G + g], 1.f);
+    }
+    nvalid += __popc(m);
+  }
+  __syncwarp();
+  for (int c0 = 0; c0 < H; c0 += 128) {
+    const int c = c0 + lane * 4;
+    if (c >= H) break;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int q = 0; q < nvalid; ++q) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dpooled + (size_t)src[q] * H + c));
+      const float w = wgt[q];
+      acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+    }
+    float4* d = reinterpret_cast<float4*>(dh + row * dh_rs + c);
+    float4 o = *d;
+    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    *d = o;
   }
 }
 
@@ -1017,6 +1050,11 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
   DESIRE_CHECK_ARG(d && w && fmap && obs && target && Hx && fpool && Yhat && count && Y && scores && ioc_cost && g && dfmap,
                    "desire_ioc_train: null argument");
   DESIRE_CHECK_ARG(d->iters >= 1 && d->H % 4 == 0, "desire_ioc_train: needs iters >= 1 and H %% 4 == 0");
+  DESIRE_CHECK_ARG(d->n_rad * d->n_ang <= 64, "desire_ioc_train: at most 64 social bins");
+  const int Np_bwd = (d->N + 31) / 32 * 32;
+  const size_t spb_bwd_smem = (size_t)SB_WARPS * 2 * Np_bwd * 4;
+  DESIRE_CHECK_ARG(spb_bwd_smem <= 200 * 1024, "desire_ioc_train: too many agents per scene for the pooling transpose");
+  DESIRE_ENSURE_SMEM(social_pool_bwd_kernel, spb_bwd_smem);
   const IocTrainLayout L = ioc_train_layout(d);
   if (!ws || ws_bytes < L.total) {
     set_error("desire_ioc_train: workspace too small (%zu < %zu)", ws_bytes, L.total);
@@ -1118,11 +1156,11 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
       DESIRE_TRY(colsum_acc(dpre, H, (int)R, H, g->sp_b, st));
       if (t == 0) return DESIRE_OK;                         // h2_{-1} = H_x is a constant of this module
       DESIRE_TRY(sgemm(dpre, H, w->sp_w, H, true, nullptr, pooled, G * H, (int)R, G * H, H, DESIRE_ACT_NONE, false, st, pw));
-      DESIRE_LAUNCH(st, (social_count_kernel<<<blocks(R * 32, 256), 256, 0, st>>>(Yi + 2 * t, 2L * T, obs, Tp, R, N, K, d->n_rad,
-                                                                                  d->n_ang, w->r2_edges, w->dirs, cnt)));
-      DESIRE_LAUNCH(st, (social_pool_bwd_kernel<<<blocks(R * 32, 256), 256, 0, st>>>(
+      DESIRE_LAUNCH(st, (social_count_kernel<<<blocks(R, SB_WARPS), SB_WARPS * 32, 0, st>>>(
+                            Yi + 2 * t, 2L * T, obs, Tp, R, N, K, d->n_rad, d->n_ang, w->r2_edges, w->dirs, cnt)));
+      DESIRE_LAUNCH(st, (social_pool_bwd_kernel<<<blocks(R, SB_WARPS), SB_WARPS * 32, spb_bwd_smem, st>>>(
                             Yi + 2 * t, 2L * T, obs, Tp, R, N, K, H, d->n_rad, d->n_ang, w->r2_edges, w->dirs, pooled, cnt,
-                            dhs + (size_t)(t - 1) * H, (long)T * H)));
+                            dhs + (size_t)(t - 1) * H, (long)T * H, Np_bwd)));
       return DESIRE_OK;
     };
     DESIRE_TRY(gru_bptt(a, base + L.bptt, L.pack - L.bptt, st, &social_bwd));

@@ -706,16 +706,14 @@ extern "C" int desire_cvae_decode_bwd(const float* z, int R, int Z, const desire
       return DESIRE_ERR_WORKSPACE;
     }
     const float* zc = z + (size_t)r0 * Z;
-    // ---------------- forward recompute (GEMM -> col2im + bias -> per-row BN + activation), pre-BN values kept
+    // ---------------- forward recompute (GEMM -> the forward's fused col2im + bias + per-row BN + activation kernel,
+    // which here also stores the pre-BN values the backward needs)
     DESIRE_TRY(sgemm(zc, Z, w->d1.w, Z, true, nullptr, col, 2048, rc, 2048, Z, DESIRE_ACT_NONE, false, st, pw));
-    DESIRE_TRY(col2im_gather(col, rc, 1, 4, 4, 1, 0, 128, w->d1.b, y1, st));
-    DESIRE_TRY(bn_row_fwd(y1, rc, 16, 128, w->d1.gamma, w->d1.beta, DESIRE_ACT_ELU, a1, st));
+    DESIRE_TRY(colbn_act(col, rc, 1, 4, 4, 1, 0, 128, w->d1.b, w->d1.gamma, w->d1.beta, DESIRE_ACT_ELU, a1, st, y1));
     DESIRE_TRY(sgemm(a1, 128, w->d2.w, 128, true, nullptr, col, 1600, rc * 16, 1600, 128, DESIRE_ACT_NONE, false, st, pw));
-    DESIRE_TRY(col2im_gather(col, rc, 4, 8, 5, 1, 0, 64, w->d2.b, y2, st));
-    DESIRE_TRY(bn_row_fwd(y2, rc, 64, 64, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, a2, st));
+    DESIRE_TRY(colbn_act(col, rc, 4, 8, 5, 1, 0, 64, w->d2.b, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, a2, st, y2));
     DESIRE_TRY(sgemm(a2, 64, w->d3.w, 64, true, nullptr, col, 800, rc * 64, 800, 64, DESIRE_ACT_NONE, false, st, pw));
-    DESIRE_TRY(col2im_gather(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, y3, st));
-    DESIRE_TRY(bn_row_fwd(y3, rc, 256, 32, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st));
+    DESIRE_TRY(colbn_act(col, rc, 8, 16, 5, 2, 1, 32, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3, st, y3));
     DESIRE_TRY(sgemm(a3, 32, w->d4.w, 32, true, nullptr, col, 25, rc * 256, 25, 32, DESIRE_ACT_NONE, false, st, pw));
     DESIRE_TRY(col2im_gather(col, rc, 16, 32, 5, 2, 1, 1, w->d4.b, y4, st));
     // ---------------- backward
