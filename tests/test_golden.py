@@ -9,7 +9,9 @@ import pytest
 
 from helpers import TOL, np_batch, np_params, np_tables, oracle_forward, rel_l2, small_cfg
 
-FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+FILES = sorted(f for f in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+               if not os.path.basename(f).startswith("grads_"))
+GRAD_FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "grads_*.npz")))
 SAMPLED = {"output_states_s": ("output_states", (slice(None), slice(None, None, 3), slice(None, None, 5))),
            "feature_pooling_s": ("feature_pooling", (slice(None), slice(None, None, 4), slice(None, None, 17))),
            "x_reconstr_mean_s": ("x_reconstr_mean", (slice(None), slice(None, None, 37))),
@@ -65,3 +67,53 @@ def test_cuda_reproduces_golden(path):
         r = ref.reshape(-1, B, N, K) if k == "ioc_scores" else ref.reshape(1, B, N, K, -1)
         errs = [rel_l2(a[:, b, :, kk], r[:, b, :, kk]) for b in range(B) for kk in range(K)]
         assert np.median(errs) <= TOL and np.mean(np.array(errs) <= TOL) >= 0.75, (k, errs)
+
+
+# ------------------------------------------------------------------------------------------ gradients (train step)
+def _load_grads(path):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gen_golden_grads as GG
+    g = dict(np.load(path))
+    B, miss, H, N, K, S, it = [int(x) for x in g.pop("meta")]
+    cfg = small_cfg(d_dim=H, max_num_obj=N, num_samples=K, scene_size=S, ioc_iters=it, **GG.ONE_BIN)
+    return g, cfg, B, miss, GG
+
+
+@pytest.mark.parametrize("path", GRAD_FILES, ids=[os.path.basename(f) for f in GRAD_FILES])
+def test_twin_reproduces_golden_gradients(path):
+    gold, cfg, B, miss, GG = _load_grads(path)
+    g, c1, c2 = GG.reference_grads(cfg, B, miss)
+    assert np.allclose([c1, c2], gold["cost"], rtol=1e-9)
+    gmax = max(float(np.abs(v).max()) for k, v in gold.items() if k.startswith("g_"))
+    for k, v in g.items():
+        assert np.allclose(GG.sample(v), gold["g_" + k], rtol=1e-5, atol=1e-7 * gmax), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GRAD_FILES, ids=[os.path.basename(f) for f in GRAD_FILES])
+def test_cuda_reproduces_golden_gradients(path):
+    import torch
+    from desire_b200.config import init_params
+    from desire_b200.engine import TrainPath, flatten_params
+    from desire_b200.synthetic import make_batch
+    gold, cfg, B, miss, GG = _load_grads(path)
+    flat, views, offs = flatten_params(init_params(cfg, 1), "cuda:0")
+    tp = TrainPath(cfg, flat, views, offs, B, train_ioc=True)
+    batch = [t.cuda() for t in make_batch(cfg, B, 0, miss)]
+    tp.set_count(batch[0])
+    tp.run(*batch, stages=("generate",))
+    G = tp.backward(*batch)
+    torch.cuda.synchronize()
+    assert abs(float(tp.buf["cost"][0]) - gold["cost"][0]) <= 1e-4 * abs(gold["cost"][0])
+    assert abs(float(tp.buf["ioc_cost"][0]) - gold["cost"][1]) <= 1e-4 * abs(gold["cost"][1])
+    gmax = max(float(np.linalg.norm(v)) for k, v in gold.items() if k.startswith("g_"))
+    bad = {}
+    for k, v in G.items():
+        ref = gold["g_" + k].astype(np.float64)
+        got = GG.sample(v.cpu().numpy()).astype(np.float64)
+        nr = float(np.linalg.norm(ref))
+        e = rel_l2(got, ref) if nr > 1e-9 * gmax else float(np.linalg.norm(got)) / gmax
+        if not (e <= 2e-3 or e * nr <= 1e-6 * gmax):
+            bad[k] = e
+    assert not bad, bad
