@@ -179,10 +179,12 @@ class DESIREModel(object):
             # graph path: host -> pinned -> static device buffers -> one graph replay
             B = int(np.shape(input_data)[0])
             hp = self._path(B)
-            pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data), ("eps", eps), ("scene", scene))]
-            if hp.graph is None:
-                hp.capture(*[p.to(self.device) for p in pins])
-            out = hp.replay(*pins)
+            if hp.graph_gen is None:
+                pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data), ("eps", eps), ("scene", scene))]
+                hp.capture_split(*[p.to(self.device) for p in pins])
+            pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data), ("eps", eps))]
+            # the scene images (the largest input) are staged while the generation graph is already running
+            out = hp.replay_split(*pins, stage_scene=lambda: self._pin("scene", scene))
         else:
             out = self.forward(input_data, target_data, eps, scene)
         B = out["Y_refined"].shape[0] // (cfg.max_num_obj * cfg.K)
