@@ -1,6 +1,8 @@
 // Stage 2 — IOC ranking & refinement (absent in the reference, marker
 // model/model.py:312-313): scene CNN, bilinear scene-feature gather, log-polar social pooling,
 // Decoder-2 GRU with per-step scoring, regression refinement.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -993,8 +995,9 @@ __global__ void scene_gather_bwd_kernel(const float* __restrict__ dfs, int ld, i
 }
 
 struct IocTrainLayout {
-  size_t snaps, dscore, dDY, rows, Xs, XP, dXP, fsp, hs2, dhs, pooled, h0e, dh0, dpre, cnt, dX48, vel, dsT, bptt, pack,
+  size_t snaps, dscore, dDY, rows, Xs, XP, dXP, fsp, hs2, dhs, pooled, dpool, h0e, dh0, dpre, cnt, dX48, vel, dsT, bptt, pack,
       wpack, wpack_bytes, fwd, total;
+  bool keep;   // every step's pooled tensor is kept for the sp_w gradient (one GEMM over all steps) when it fits
 };
 IocTrainLayout ioc_train_layout(const desire_ioc_dims_t* d) {
   const size_t R = (size_t)d->B * d->N * d->K, T = d->Tf, H = d->H, M = (size_t)d->B * d->N;
@@ -1017,10 +1020,16 @@ IocTrainLayout ioc_train_layout(const desire_ioc_dims_t* d) {
   L.fsp = take(R * T * H * 4);
   L.hs2 = take(R * T * H * 4);
   L.dhs = take(R * T * H * 4);
-  L.pooled = take(R * G * H * 4);
+  // budget for keeping every step's pooled tensor (default 12 GiB; DESIRE_IOC_KEEP_POOLED_BYTES overrides it — the
+  // tests use 0 to exercise the rebuild-per-step path that large scenes take)
+  size_t keep_budget = (size_t)12 << 30;
+  if (const char* e = getenv("DESIRE_IOC_KEEP_POOLED_BYTES")) keep_budget = (size_t)strtoull(e, nullptr, 10);
+  L.keep = R * G * H * 4 * T <= keep_budget;
+  L.pooled = take((L.keep ? T : 1) * R * G * H * 4);
+  L.dpool = L.keep ? take(R * G * H * 4) : L.pooled;
   L.h0e = take(R * H * 4);
   L.dh0 = take(R * H * 4);
-  L.dpre = take(R * H * 4);
+  L.dpre = take((L.keep ? T : 1) * R * H * 4);
   L.cnt = take(R * G * 4);
   L.dX48 = take(R * T * (d->Fv + d->Cs) * 4);
   L.vel = take(R * T * 2 * 4);
@@ -1069,8 +1078,11 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
   char* base = (char*)ws;
   auto fp = [&](size_t o) { return (float*)(base + o); };
   float *snaps = fp(L.snaps), *dscore = fp(L.dscore), *dDY = fp(L.dDY), *rows = fp(L.rows), *Xs = fp(L.Xs), *XP = fp(L.XP),
-        *dXP = fp(L.dXP), *fsp = fp(L.fsp), *hs2 = fp(L.hs2), *dhs = fp(L.dhs), *pooled = fp(L.pooled), *h0e = fp(L.h0e),
-        *dh0 = fp(L.dh0), *dpre = fp(L.dpre), *cnt = fp(L.cnt), *dX48 = fp(L.dX48), *vel = fp(L.vel), *dsT = fp(L.dsT);
+        *dXP = fp(L.dXP), *fsp = fp(L.fsp), *hs2 = fp(L.hs2), *dhs = fp(L.dhs), *pooled0 = fp(L.pooled), *dpool = fp(L.dpool),
+        *h0e = fp(L.h0e), *dh0 = fp(L.dh0), *dpre0 = fp(L.dpre), *cnt = fp(L.cnt), *dX48 = fp(L.dX48), *vel = fp(L.vel),
+        *dsT = fp(L.dsT);
+  const bool keep = L.keep;
+  const size_t pooled_step = keep ? (size_t)R * G * H : 0, dpre_step = keep ? (size_t)R * H : 0;
   PackWs pw{base + L.pack, PACK_WS_BYTES};
   PackWs wp{base + L.wpack, L.wpack_bytes};
   const size_t f4 = sizeof(float);
@@ -1103,6 +1115,7 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
     for (int t = 0; t < T; ++t) {
       const float* hp = t > 0 ? hs2 + (size_t)(t - 1) * H : h0e;
       const int hp_ld = t > 0 ? T * H : H;
+      float* pooled = pooled0 + (size_t)t * pooled_step;
       DESIRE_TRY(social_pool_launch(Yi + 2 * t, 2L * T, hp, hp_ld, obs, Tp, d->B, N, K, H, d->n_rad, d->n_ang, w->r2_edges,
                                     w->dirs, pooled, st));
       float* fsp_t = fsp + (size_t)t * H;
@@ -1147,23 +1160,33 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
       const int hp_ld = t > 0 ? T * H : H;
       const float* dxp_t = dXP + (size_t)t * 3 * H;
       // d fsp_t = dxp_t @ W[social rows]^T, through the ReLU
+      float* dpre = dpre0 + (size_t)t * dpre_step;
+      float* pooled = pooled0 + (size_t)t * pooled_step;
       DESIRE_TRY(sgemm(dxp_t, T * 3 * H, wg_sp, 2 * H, true, nullptr, dpre, H, (int)R, H, 2 * H, DESIRE_ACT_NONE, false, st, pw));
       DESIRE_TRY(sgemm(dxp_t + 2 * H, T * 3 * H, wc_sp, H, true, nullptr, dpre, H, (int)R, H, H, DESIRE_ACT_NONE, true, st, pw));
       DESIRE_TRY(act_bwd_post(fsp + (size_t)t * H, T * H, dpre, H, (size_t)R, H, DESIRE_ACT_RELU, st));
-      DESIRE_TRY(social_pool_launch(Yi + 2 * t, 2L * T, hp, hp_ld, obs, Tp, d->B, N, K, H, d->n_rad, d->n_ang, w->r2_edges,
-                                    w->dirs, pooled, st));
-      DESIRE_TRY(wgrad_tn(pooled, G * H, dpre, H, g->sp_w, H, (int)R, G * H, H, st, wp));
-      DESIRE_TRY(colsum_acc(dpre, H, (int)R, H, g->sp_b, st));
+      if (!keep) {
+        // the pooled tensor of this step is rebuilt for the sp_w gradient (too large to keep for every step)
+        DESIRE_TRY(social_pool_launch(Yi + 2 * t, 2L * T, hp, hp_ld, obs, Tp, d->B, N, K, H, d->n_rad, d->n_ang, w->r2_edges,
+                                      w->dirs, pooled, st));
+        DESIRE_TRY(wgrad_tn(pooled, G * H, dpre, H, g->sp_w, H, (int)R, G * H, H, st, wp));
+        DESIRE_TRY(colsum_acc(dpre, H, (int)R, H, g->sp_b, st));
+      }
       if (t == 0) return DESIRE_OK;                         // h2_{-1} = H_x is a constant of this module
-      DESIRE_TRY(sgemm(dpre, H, w->sp_w, H, true, nullptr, pooled, G * H, (int)R, G * H, H, DESIRE_ACT_NONE, false, st, pw));
+      DESIRE_TRY(sgemm(dpre, H, w->sp_w, H, true, nullptr, dpool, G * H, (int)R, G * H, H, DESIRE_ACT_NONE, false, st, pw));
       DESIRE_LAUNCH(st, (social_count_kernel<<<blocks(R, SB_WARPS), SB_WARPS * 32, 0, st>>>(
                             Yi + 2 * t, 2L * T, obs, Tp, R, N, K, d->n_rad, d->n_ang, w->r2_edges, w->dirs, cnt)));
       DESIRE_LAUNCH(st, (social_pool_bwd_kernel<<<blocks(R, SB_WARPS), SB_WARPS * 32, spb_bwd_smem, st>>>(
-                            Yi + 2 * t, 2L * T, obs, Tp, R, N, K, H, d->n_rad, d->n_ang, w->r2_edges, w->dirs, pooled, cnt,
+                            Yi + 2 * t, 2L * T, obs, Tp, R, N, K, H, d->n_rad, d->n_ang, w->r2_edges, w->dirs, dpool, cnt,
                             dhs + (size_t)(t - 1) * H, (long)T * H, Np_bwd)));
       return DESIRE_OK;
     };
     DESIRE_TRY(gru_bptt(a, base + L.bptt, L.pack - L.bptt, st, &social_bwd));
+    if (keep) {
+      // social fc weights: ONE product over all T steps (pooled [T*R, G*H]^T @ dpre [T*R, H])
+      DESIRE_TRY(wgrad_tn(pooled0, G * H, dpre0, H, g->sp_w, H, (int)(R * T), G * H, H, st, wp));
+      DESIRE_TRY(colsum_acc(dpre0, H, (int)(R * T), H, g->sp_b, st));
+    }
     // ---- input rows of Decoder-2: static features, social feature, biases
     const int RT = (int)(R * T);
     DESIRE_TRY(wgrad_tn(Xs, Dst, dXP, 3 * H, gg.wg, 2 * H, RT, Dst, 2 * H, st, wp));

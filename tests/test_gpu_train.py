@@ -246,6 +246,20 @@ def test_ioc_backward_logpolar(H, N, K, B, missing):
     assert not bad, bad
 
 
+def test_ioc_backward_rebuild_pooled_path_agrees(monkeypatch):
+    """Large scenes rebuild each step's pooled tensor for the sp_w gradient instead of keeping all of them; force that
+    path and compare with the default one."""
+    cfg = small_cfg(d_dim=64, max_num_obj=12, num_samples=4, ioc_iters=2)
+    grads = []
+    for budget in (None, "0"):
+        if budget is not None:
+            monkeypatch.setenv("DESIRE_IOC_KEEP_POOLED_BYTES", budget)
+        tp, G = run_ioc_train(cfg, 3, 1)
+        grads.append(tp.grad_flat.cpu().numpy().copy())
+    monkeypatch.delenv("DESIRE_IOC_KEEP_POOLED_BYTES")
+    assert rel_l2(grads[1], grads[0]) <= 1e-5
+
+
 def test_full_train_step_with_ioc_reduces_both_costs():
     from desire_b200.synthetic import make_batch
     cfg = small_cfg(d_dim=32, max_num_obj=10, num_samples=4)
