@@ -223,12 +223,20 @@ def ours_arm(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the ONE JSON line (NCCL_DEBUG=VERSION prints its banner there), and give each rank its share
-        # of the host cores for the pinned-staging memcpy of the e2e leg (torchrun exports OMP_NUM_THREADS=1)
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the ONE JSON line, and give each rank its share of the host cores for the pinned-staging
+        # memcpy of the e2e leg (torchrun exports OMP_NUM_THREADS=1)
         torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)                     # NCCL's "NCCL version ..." banner goes to stderr, not next to the JSON line
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()                # forces communicator creation while stdout is redirected
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = make_cfg(a)
     lib = _lib.load()
     model = DESIREModel(cfg, device=dev, seed=1)
