@@ -73,6 +73,11 @@ class HotPath:
             lib.desire_ioc_workspace_bytes(C.byref(self.ioc_dims)), 256)
         self.ws_bytes = ws
         self.ws = torch.empty(ws, dtype=torch.uint8, device=self.device)
+        # the scene CNN only depends on the images: it gets its own scratch and runs on a side stream, concurrently
+        # with the (small-M, SM-underfilling) encoder / CVAE-encoder kernels of the generation stage
+        self.ws_scene_bytes = max(lib.desire_scene_cnn_workspace_bytes(B, cfg.scene_size, cfg.scene_size), 256)
+        self.ws_scene = torch.empty(self.ws_scene_bytes, dtype=torch.uint8, device=self.device)
+        self.side = torch.cuda.Stream(self.device)
         self.graph = None
         self.graph_gen = self.graph_rank = None
         self.static_in = None
@@ -101,9 +106,22 @@ class HotPath:
         for t, shp in ((obs, (self.B, N, Tp, 3)), (tgt, (self.B, N, Tf, 3)), (eps, (M, K, Zl))):
             if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
                 raise ValueError("expected contiguous float32 %s on %s, got %s %s" % (shp, self.device, tuple(t.shape), t.dtype))
-        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        cur = torch.cuda.current_stream(self.device)
+        st = C.c_void_p(cur.cuda_stream)
         ws, wsb = _p(self.ws), self.ws_bytes
         ck = _lib.check
+        if "rank" in stages:
+            stages = tuple(x for x in stages if x != "rank") + ("scene", "ioc")
+        if "scene" in stages:
+            if tuple(scene.shape) != (self.B, cfg.scene_size, cfg.scene_size, 3) or not scene.is_contiguous():
+                raise ValueError("scene must be contiguous [B,%d,%d,3]" % (cfg.scene_size, cfg.scene_size))
+            fork = "generate" in stages            # overlap with the generation stage when both run in this call
+            s_str = self.side if fork else cur
+            if fork:
+                self.side.wait_stream(cur)
+            ck(lib.desire_scene_cnn_fwd(_p(scene), self.B, cfg.scene_size, cfg.scene_size, cfg.scene_channels,
+                                        C.byref(self.w_scene), _p(b["scene_features"]), _p(self.ws_scene),
+                                        self.ws_scene_bytes, C.c_void_p(s_str.cuda_stream)), "scene_cnn")
         if "generate" in stages:
             ck(lib.desire_tconv_fwd(_p(obs), M, Tp, Cm, _p(P["temporal_w"]), _p(P["temporal_b"]), _p(b["rho_i"]), st), "tconv")
             ck(lib.desire_gru_encode_fwd(_p(obs), M, Tp, H, C.byref(self.w_encx), _p(b["HxHy"]), 2 * H, st), "gru_encode_x")
@@ -123,11 +141,9 @@ class HotPath:
             ck(lib.desire_kld_rows_fwd(_p(b["mu_logvar"]), M, Zl, _p(b["kld_rows"]), st), "kld_rows")
             ck(lib.desire_recon_rows_fwd(_p(b["Yhat"]), _p(tgt), M, K, Tf, _p(b["recon_rows"]), st), "recon_rows")
             ck(lib.desire_masked_cost_fwd(_p(b["recon_rows"]), _p(b["kld_rows"]), _p(obs), M, Tp, _p(b["cost"]), st), "masked_cost")
-        if "rank" in stages:
-            if tuple(scene.shape) != (self.B, cfg.scene_size, cfg.scene_size, 3) or not scene.is_contiguous():
-                raise ValueError("scene must be contiguous [B,%d,%d,3]" % (cfg.scene_size, cfg.scene_size))
-            ck(lib.desire_scene_cnn_fwd(_p(scene), self.B, cfg.scene_size, cfg.scene_size, cfg.scene_channels,
-                                        C.byref(self.w_scene), _p(b["scene_features"]), ws, wsb, st), "scene_cnn")
+        if "ioc" in stages:
+            if "scene" in stages and "generate" in stages:
+                cur.wait_stream(self.side)         # join the scene-CNN branch
             b["Y_refined"].copy_(b["Yhat"])
             ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs), Tp,
                                   _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["Y_refined"]), _p(b["ioc_scores"]),
@@ -164,19 +180,21 @@ class HotPath:
                 self.run(*self.static_in)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
-        self.graph_gen, self.graph_rank = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.graph_gen, self.graph_scene, self.graph_rank = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_gen):
             self.run(*self.static_in, stages=("generate",))
-        with torch.cuda.graph(self.graph_rank, pool=self.graph_gen.pool()):
-            self.run(*self.static_in, stages=("rank",))
+        with torch.cuda.graph(self.graph_scene):
+            self.run(*self.static_in, stages=("scene",))
+        with torch.cuda.graph(self.graph_rank):
+            self.run(*self.static_in, stages=("ioc",))
         self.copy_stream = torch.cuda.Stream(self.device)
         self.copy_done = torch.cuda.Event()
         return self.graph_gen, self.graph_rank
 
     def replay_split(self, obs, tgt, eps, stage_scene):
         """obs/tgt/eps: pinned host (or device) tensors; stage_scene(): returns the pinned scene tensor — called
-        AFTER the generation graph has been launched, so its host-side memcpy and its H2D copy (on a second
-        stream) overlap the generation kernels.  The ranking graph waits on the copy."""
+        AFTER the generation graph has been launched, so its host-side memcpy, its H2D copy and the scene CNN (on a
+        second stream) overlap the generation kernels.  The ranking graph waits on that stream."""
         for dst, src in zip(self.static_in[:3], (obs, tgt, eps)):
             dst.copy_(src, non_blocking=True)
         self.graph_gen.replay()
@@ -184,6 +202,7 @@ class HotPath:
         cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.copy_stream):
             self.static_in[3].copy_(scene, non_blocking=True)
+            self.graph_scene.replay()              # the scene CNN runs next to the rest of the generation graph
             self.copy_done.record(self.copy_stream)
         cur.wait_event(self.copy_done)
         self.graph_rank.replay()
