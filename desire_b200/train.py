@@ -92,11 +92,47 @@ def load_checkpoint(model, path):
     return int(state.get("next_step", 0))
 
 
+def _init_distributed(args):
+    """Under torchrun (WORLD_SIZE > 1): one process per GPU, NCCL; every minibatch of `batch_size` scenes is sharded
+    round-robin over the ranks, gradients are all-reduced inside DESIREModel.train_step.
+    Returns (rank, world)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    args.device = "cuda:%d" % local
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.batch_size % world:
+        raise ValueError("batch_size %d must be divisible by the number of ranks %d" % (args.batch_size, world))
+    return rank, world
+
+
+def _check_replicas_in_sync(model, world):
+    """Data-parallel invariant: every rank applied the identical all-reduced gradient, so the flat weight buffers
+    are bit-identical.  One 16-byte all-reduce per epoch; raises if a replica drifted."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    cs = model.flat_weights.double().sum().reshape(1)
+    lo, hi = cs.clone(), cs.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if float(lo) != float(hi):
+        raise RuntimeError("replicas out of sync: weight checksum min %.17g max %.17g" % (float(lo), float(hi)))
+
+
 def train(args):
+    from desire_b200.dist import global_masked_cost, shard_scenes
     from desire_b200.model.model import DESIREModel
     from desire_b200.utils.data_loader import DataLoader
     import torch
 
+    rank, world = _init_distributed(args)
     norm = (args.norm_w, args.norm_h) if args.norm_w > 0 and args.norm_h > 0 else None
     data_loader = DataLoader(args.batch_size, args.seq_length, args.max_num_obj, args.leave_dataset, preprocess=False,
                              data_dir=args.data_dir, pred_length=args.pred_length, clip=args.clip_objects,
@@ -105,7 +141,8 @@ def train(args):
     with open(os.path.join(args.save_dir, 'config.pkl'), 'wb') as fh:     # train.py:102-103
         pickle.dump(args, fh)
 
-    model = DESIREModel(args, device=args.device, seed=args.seed)
+    model = DESIREModel(args, device=args.device, seed=args.seed)      # same seed => identical weights on every rank
+    model.batch_size = args.batch_size // world
     start_step = 0
     if args.resume:
         start_step = load_checkpoint(model, args.resume)
@@ -120,25 +157,32 @@ def train(args):
             xval, yval, dval = data_loader.next_batch()
             x = DataLoader.to_model_layout(xval)         # [B,N,Tp,3] agent-major (the transpose train.py:158-173 forgot)
             y = DataLoader.to_model_layout(yval)
+            if world > 1:                                # this rank's scenes of the minibatch
+                mine = shard_scenes(x.shape[0], rank, world)
+                x, y = np.ascontiguousarray(x[mine]), np.ascontiguousarray(y[mine])
             step = epoch * data_loader.num_batches + batch
             if step < start_step:
                 continue
             if args.optimize:
-                loss_batch = float(model.train_step(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch)[0])
+                c = model.train_step(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch + 7919 * rank)
+                # cost over the whole minibatch: sum_ranks(cost_r * n_r) / sum_ranks(n_r)   (model/model.py:376)
+                loss_batch = float(global_masked_cost(c[0] * c[1], c[1]))
             else:
                 out = model.forward(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch)
                 loss_batch = float(out["cost"])          # masked mean over existing agents (model.py:351-376)
             torch.cuda.synchronize()
             end = time.time()
             losses.append(loss_batch)
-            print("{}/{} (epoch {}), train_loss = {:.3f}, time/batch = {:.3f}"
-                  .format(step, args.num_epochs * data_loader.num_batches, epoch, loss_batch, end - start))
-            sys.stdout.flush()
-            if step % args.save_every == 0 and step > 0:                  # train.py:197-207
+            if rank == 0:
+                print("{}/{} (epoch {}), train_loss = {:.3f}, time/batch = {:.3f}"
+                      .format(step, args.num_epochs * data_loader.num_batches, epoch, loss_batch, end - start))
+                sys.stdout.flush()
+            if rank == 0 and step % args.save_every == 0 and step > 0:    # train.py:197-207
                 checkpoint_path = os.path.join(args.save_dir, 'social_model.ckpt')
                 save_checkpoint(model, "%s-%d" % (checkpoint_path, step), step + 1)
                 print("model saved to {}".format(checkpoint_path))
                 sys.stdout.flush()
+        _check_replicas_in_sync(model, world)
     return losses
 
 
