@@ -437,18 +437,21 @@ int act_bwd_post(const float* out, int ldo, float* d, int ldd, size_t M, int N, 
 }  // namespace desire
 namespace {
 // ------------------------------------------------------------------------------------------ Adam
-__global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+// Deterministic sum of squares: ONE block, fixed per-thread strides and a fixed reduction tree, so every rank gets the
+// bit-identical norm from the bit-identical all-reduced gradient (an atomics-based reduction made the clip factor —
+// and then the replicas' weights — differ in the last bit).  ~10 us for the 2.7 M parameters of the path.
+__global__ void __launch_bounds__(1024) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out,
+                                                     int accumulate) {
   __shared__ float sm[32];
   float s = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    s = fmaf(g[i], g[i], s);
+  for (size_t i = threadIdx.x; i < n; i += 1024) s = fmaf(g[i], g[i], s);
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x < 32) {
-    s = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+    s = sm[threadIdx.x];
     s = warp_sum(s);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + s;
   }
 }
 
@@ -835,11 +838,7 @@ extern "C" int desire_fc_bwd(const float* A, int lda, const float* W, int ldw, c
 extern "C" int desire_sumsq_fwd(const float* g, long n, float* out, int accumulate, desire_stream_t stream) {
   DESIRE_CHECK_ARG(g && out && n >= 0, "desire_sumsq_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (!accumulate) DESIRE_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
-  if (n == 0) return DESIRE_OK;
-  unsigned blocks = grid1d((size_t)n, 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  DESIRE_LAUNCH(st, (sumsq_kernel<<<blocks, 256, 0, st>>>(g, (size_t)n, out)));
+  DESIRE_LAUNCH(st, (sumsq_kernel<<<1, 1024, 0, st>>>(g, (size_t)n, out, accumulate ? 1 : 0)));
   return DESIRE_OK;
 }
 
