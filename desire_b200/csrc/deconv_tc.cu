@@ -50,7 +50,7 @@ __host__ __device__ inline DcLayout dc_layout(int Cin, int nstg, int spt) {
   L.a_lo = off; off += a_half;
   L.ring = off; off += (size_t)nstg * SLOT;
   L.out = off; off += 64 * 1024;
-  L.red = off; off += 256 * 4;
+  L.red = off; off += 256 * 16;     // float4 partial sums of the vectorised BN phase
   L.stat = off; off += (size_t)2 * spt * CG * 4;
   L.bars = off; off += (2 * 4 + 4 + 1) * 8 + 16;
   L.total = off;
@@ -199,50 +199,78 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[ab]);
       }
-      // ---- (c) bias + per-(sample, channel) BN over the Pout positions + activation + store
-      constexpr int npair = spt * CG, parts = 256 / npair;     // npair in {64, 256}
-      const int pair = tid % npair, part = tid / npair;
-      const int ps = pair / CG, pc = pair % CG;
-      const float b = __ldg(a.bias + cg * CG + pc);
-      const float* tsamp = outt + (size_t)ps * Pout * CG;
-      float sum = 0.f;
-      for (int q = part; q < Pout; q += parts) {
-        const int oy = q / HOUT, ox = q - oy * HOUT;
-        sum += tsamp[q * CG + (((pc >> 2) + swz(oy, ox, sh)) & 7) * 4 + (pc & 3)] + b;
+      // ---- (c) bias + per-(sample, channel) BN over the Pout positions + activation + store, four channels per
+      // thread: a thread owns one channel quad (its bias / gamma / beta live in registers), every tile access is one
+      // LDS.128 of the XOR-rotated quad and every store one 16-byte STG (the scalar form of this phase was 47 % of
+      // the kernel's instructions).
+      constexpr int units = spt * 8, parts = 256 / units;      // (sample, quad) units: 16 or 64; position slices per unit
+      float4* red4 = reinterpret_cast<float4*>(red);
+      float4* stat4 = reinterpret_cast<float4*>(stat);         // [units] mean, then [units] rstd
+      {
+        const int unit = tid % units, part = tid / units;
+        const int us = unit >> 3, uq = unit & 7;
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + cg * CG) + uq);
+        const float* tsamp = outt + (size_t)us * Pout * CG;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = part; q < Pout; q += parts) {
+          const int oy = q / HOUT, ox = q - oy * HOUT;
+          const float4 x = *reinterpret_cast<const float4*>(tsamp + q * CG + ((uq + swz(oy, ox, sh)) & 7) * 4);
+          sum.x += x.x + b4.x; sum.y += x.y + b4.y; sum.z += x.z + b4.z; sum.w += x.w + b4.w;
+        }
+        red4[tid] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid < units) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < parts; ++q) {
+            const float4 r = red4[q * units + tid];
+            t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+          }
+          const float inv = 1.f / (float)Pout;
+          stat4[tid] = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float4 mean = stat4[unit];
+        sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = part; q < Pout; q += parts) {
+          const int oy = q / HOUT, ox = q - oy * HOUT;
+          const float4 x = *reinterpret_cast<const float4*>(tsamp + q * CG + ((uq + swz(oy, ox, sh)) & 7) * 4);
+          const float dx = x.x + b4.x - mean.x, dy = x.y + b4.y - mean.y, dz = x.z + b4.z - mean.z, dw = x.w + b4.w - mean.w;
+          sum.x += dx * dx; sum.y += dy * dy; sum.z += dz * dz; sum.w += dw * dw;
+        }
+        red4[tid] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid < units) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < parts; ++q) {
+            const float4 r = red4[q * units + tid];
+            t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+          }
+          const float inv = 1.f / (float)Pout;
+          stat4[units + tid] = make_float4(1.f / sqrtf(t.x * inv + 1e-3f), 1.f / sqrtf(t.y * inv + 1e-3f),
+                                           1.f / sqrtf(t.z * inv + 1e-3f), 1.f / sqrtf(t.w * inv + 1e-3f));
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      red[tid] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid < npair) {
-        float t = 0.f;
-        for (int q = 0; q < parts; ++q) t += red[q * npair + tid];
-        stat[tid] = t / (float)Pout;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mean = stat[pair];
-      sum = 0.f;
-      for (int q = part; q < Pout; q += parts) {
-        const int oy = q / HOUT, ox = q - oy * HOUT;
-        const float d = tsamp[q * CG + (((pc >> 2) + swz(oy, ox, sh)) & 7) * 4 + (pc & 3)] + b - mean;
-        sum += d * d;
-      }
-      red[tid] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid < npair) {
-        float t = 0.f;
-        for (int q = 0; q < parts; ++q) t += red[q * npair + tid];
-        stat[npair + tid] = 1.f / sqrtf(t / (float)Pout + 1e-3f);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int e = tid; e < ntile_el; e += 256) {
-        const int c = e % CG, q = (e / CG) % Pout, s2 = e / (CG * Pout);
-        const long smp = samp0 + s2;
-        if (smp >= a.R) continue;
-        const int oy = q / HOUT, ox = q - oy * HOUT;
-        const float x = outt[((size_t)s2 * Pout + q) * CG + (((c >> 2) + swz(oy, ox, sh)) & 7) * 4 + (c & 3)] +
-                        __ldg(a.bias + cg * CG + c);
-        const int pr = s2 * CG + c;
-        const float y = __ldg(a.gamma + cg * CG + c) * ((x - stat[pr]) * stat[npair + pr]) + __ldg(a.beta + cg * CG + c);
-        a.Y[((size_t)smp * Pout + q) * a.Cout + cg * CG + c] = act_apply(y, a.act);
+      {
+        const int qd = tid & 7;                                // 256 % 8 == 0: the quad of a thread never changes
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + cg * CG) + qd);
+        const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + cg * CG) + qd);
+        const float4 bb4 = __ldg(reinterpret_cast<const float4*>(a.bias + cg * CG) + qd);
+        for (int e4 = tid; e4 < ntile_el / 4; e4 += 256) {
+          const int pq = e4 >> 3;
+          const int q = pq % Pout, s2 = pq / Pout;
+          const long smp = samp0 + s2;
+          if (smp >= a.R) continue;
+          const int oy = q / HOUT, ox = q - oy * HOUT;
+          const float4 x = *reinterpret_cast<const float4*>(outt + ((size_t)s2 * Pout + q) * CG + ((qd + swz(oy, ox, sh)) & 7) * 4);
+          const float4 m4 = stat4[s2 * 8 + qd], r4 = stat4[units + s2 * 8 + qd];
+          float4 y;
+          y.x = act_apply(g4.x * ((x.x + bb4.x - m4.x) * r4.x) + be4.x, a.act);
+          y.y = act_apply(g4.y * ((x.y + bb4.y - m4.y) * r4.y) + be4.y, a.act);
+          y.z = act_apply(g4.z * ((x.z + bb4.z - m4.z) * r4.z) + be4.z, a.act);
+          y.w = act_apply(g4.w * ((x.w + bb4.w - m4.w) * r4.w) + be4.w, a.act);
+          *reinterpret_cast<float4*>(a.Y + ((size_t)smp * Pout + q) * a.Cout + cg * CG + qd * 4) = y;
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
