@@ -183,19 +183,24 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
     const uint8_t* lst = off + G + 1;
     const float* hrow = hs + (size_t)((prow / Npad) * Npad) * L.hs_ld + kq * 8;
     const uint32_t aoff = kq * TM * 16 + prow * 16;
+    // list metadata is prefetched one bin ahead (off[] is a prefix array: the next bin starts where this one ends), so a
+    // stage never starts with a chain of dependent shared-memory loads
+    const int spb = H / BK;                       // K stages per bin
+    int g = 0, half = 0;
+    int o0 = 0, o1 = off[1], o1n = G > 1 ? off[2] : 0;
+    int jf = lst[0], jfn = lst[o1];              // first member of this / the next bin (unused when the bin is empty)
     for (int ks = 0; ks < nks; ++ks) {
       const int slot = ks % STAGES;
       const uint32_t ph = (ks / STAGES) & 1;
-      const int k0 = ks * BK;
-      const int g = k0 / H, col = k0 - g * H;
-      const int o0 = off[g], o1 = off[g + 1];
+      const int col = half * BK;
       uint4 hi0 = make_uint4(0, 0, 0, 0), lo0 = hi0, hi1 = hi0, lo1 = hi0;
       if (o1 > o0) {
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
         for (int o = o0; o < o1; ++o) {
-          const float4* p = reinterpret_cast<const float4*>(hrow + (size_t)lst[o] * L.hs_ld + col);
+          const int jm = (o == o0) ? jf : (int)lst[o];
+          const float4* p = reinterpret_cast<const float4*>(hrow + (size_t)jm * L.hs_ld + col);
           const float4 x0 = p[0], y0 = p[1], x1 = p[8], y1 = p[9];      // chunks kq and kq+4 (32 floats apart)
           v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
           v[4] += y0.x; v[5] += y0.y; v[6] += y0.z; v[7] += y0.w;
@@ -219,6 +224,15 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[slot]);
+      if (++half == spb) {                        // next bin: shift the prefetched metadata, fetch the bin after it
+        half = 0;
+        ++g;
+        o0 = o1;
+        o1 = o1n;
+        jf = jfn;
+        o1n = g + 1 < G ? off[g + 2] : 0;
+        jfn = lst[o1];
+      }
     }
     const long myrow = rowmap[tid & (TM - 1)];
 
