@@ -86,6 +86,8 @@ SIGNATURES = {
     "desire_gemm_tc_fwd": (I, [P, I, P, I, I, P, P, I, I, I, I, I, I, P, Z, P]),
     "desire_tconv_fwd": (I, [P, I, I, I, P, P, P, P]),
     "desire_gru_encode_fwd": (I, [P, I, I, I, C.POINTER(GruW), P, I, P]),
+    "desire_gru_encode_workspace_bytes": (Z, [I, I, I]),
+    "desire_gru_encode_ws_fwd": (I, [P, I, I, I, C.POINTER(GruW), P, I, P, Z, P]),
     "desire_cvae_encode_workspace_bytes": (Z, [I, I]),
     "desire_cvae_encode_fwd": (I, [P, I, I, C.POINTER(CvaeEncW), P, P, Z, P]),
     "desire_reparam_fwd": (I, [P, P, I, I, I, P, P]),

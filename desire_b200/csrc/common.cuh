@@ -185,6 +185,8 @@ int gru_bptt(const GruBptt& a, void* ws, size_t ws_bytes, cudaStream_t st,
              const std::function<int(int)>* after_step = nullptr);
 int col2im_gather(const float* col, int R, int Hin, int Hout, int k, int stride, int pad, int C, const float* bias,
                   float* out, cudaStream_t st);
+// hoisted input projection of an encoder: xp[(m,t), :] = [x,y] @ W_x + b   ([rows, 3H] = r|u|c), traj [rows,3]
+int xproj_traj(const float* traj, size_t rows, int H, const desire_gru_t* w, float* xp, cudaStream_t st);
 // d <- d * act'(computed from the post-activation output `out`)
 int act_bwd_post(const float* out, int ldo, float* d, int ldd, size_t M, int N, int act, cudaStream_t st);
 int gemm_mode();

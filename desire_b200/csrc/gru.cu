@@ -243,6 +243,42 @@ extern "C" int desire_gru_encode_fwd(const float* traj, int M, int T, int H, con
   return gru_seq(a, (cudaStream_t)stream);
 }
 
+// Encoder on the tensor-core recurrence: the width-2 input projection is hoisted for all T steps (one tiny kernel),
+// then the same persistent tcgen05 GRU as Decoder-1 runs the T steps (FP32 CUDA-core recurrence when not eligible).
+extern "C" size_t desire_gru_encode_workspace_bytes(int M, int T, int H) {
+  const size_t m = (size_t)M;
+  return align_up(m * T * 3 * H * sizeof(float)) + align_up(m * T * H * sizeof(float)) + PACK_WS_BYTES;
+}
+
+extern "C" int desire_gru_encode_ws_fwd(const float* traj, int M, int T, int H, const desire_gru_t* w, float* h_out,
+                                        int ld_out, void* ws, size_t ws_bytes, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(traj && w && h_out && M >= 0 && T > 0, "desire_gru_encode_ws_fwd: bad arguments");
+  DESIRE_CHECK_ARG(ld_out >= H && ld_out % 4 == 0, "desire_gru_encode_ws_fwd: ld_out must be >= H and a multiple of 4");
+  if (!ws || ws_bytes < desire_gru_encode_workspace_bytes(M, T, H)) {
+    set_error("desire_gru_encode_ws_fwd: workspace too small");
+    return DESIRE_ERR_WORKSPACE;
+  }
+  if (M == 0) return DESIRE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t m = (size_t)M;
+  Workspace W(ws, ws_bytes);
+  float* xp = W.take<float>(m * T * 3 * H);
+  float* hs = W.take<float>(m * T * H);
+  PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
+  ProfScope ps_(DESIRE_PROF_GRU_ENC, st);
+  DESIRE_TRY(xproj_traj(traj, m * T, H, w, xp, st));
+  GruSeqArgs a{};
+  a.R = M; a.H = H; a.T = T;
+  a.xp = xp; a.xp_row_stride = (long)T * 3 * H; a.xp_step_stride = 3 * H;
+  a.w_g = w->wg + 2 * 2 * H;                                    // rows 2.. = state rows
+  a.w_c = w->wc + 2 * H;
+  a.Ka = 0;
+  a.h0 = nullptr; a.h0_div = 1;
+  a.hs = hs; a.hs_row_stride = (long)T * H; a.hs_step_stride = H;
+  a.h_final = h_out; a.ld_hf = ld_out;
+  return gru_seq(a, st, pw);
+}
+
 extern "C" size_t desire_gru_decode_workspace_bytes(int R, int H) {
   return align_up((size_t)R * 3 * H * sizeof(float)) + PACK_WS_BYTES;
 }

@@ -74,6 +74,15 @@ __global__ void xproj_traj_kernel(const float* __restrict__ traj, size_t rows, i
   xp[i] = v;
 }
 
+}  // namespace
+namespace desire {
+int xproj_traj(const float* traj, size_t rows, int H, const desire_gru_t* w, float* xp, cudaStream_t st) {
+  if (rows == 0) return DESIRE_OK;
+  DESIRE_LAUNCH(st, (xproj_traj_kernel<<<grid1d(rows * 3 * H), 256, 0, st>>>(traj, rows, H, w->wg, w->bg, w->wc, w->bc, xp)));
+  return DESIRE_OK;
+}
+}  // namespace desire
+namespace {
 // rows [R,H] <- src[(r / div) * ld + c]   (src may be null: zeros)
 __global__ void expand_rows_bwd_kernel(const float* __restrict__ src, int div, int ld, size_t R, int H,
                                        float* __restrict__ dst) {

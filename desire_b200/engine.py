@@ -78,6 +78,11 @@ class HotPath:
         self.ws_scene_bytes = max(lib.desire_scene_cnn_workspace_bytes(B, cfg.scene_size, cfg.scene_size), 256)
         self.ws_scene = torch.empty(self.ws_scene_bytes, dtype=torch.uint8, device=self.device)
         self.side = torch.cuda.Stream(self.device)
+        # the two encoders run side by side on the tensor-core recurrence, each with its own scratch
+        self.side2 = torch.cuda.Stream(self.device)
+        self.ws_enc_bytes = max(lib.desire_gru_encode_workspace_bytes(M, max(Tp, Tf), H), 256)
+        self.ws_encx = torch.empty(self.ws_enc_bytes, dtype=torch.uint8, device=self.device)
+        self.ws_ency = torch.empty(self.ws_enc_bytes, dtype=torch.uint8, device=self.device)
         self.graph = None
         self.graph_gen = self.graph_rank = None
         self.static_in = None
@@ -124,9 +129,13 @@ class HotPath:
                                         self.ws_scene_bytes, C.c_void_p(s_str.cuda_stream)), "scene_cnn")
         if "generate" in stages:
             ck(lib.desire_tconv_fwd(_p(obs), M, Tp, Cm, _p(P["temporal_w"]), _p(P["temporal_b"]), _p(b["rho_i"]), st), "tconv")
-            ck(lib.desire_gru_encode_fwd(_p(obs), M, Tp, H, C.byref(self.w_encx), _p(b["HxHy"]), 2 * H, st), "gru_encode_x")
-            ck(lib.desire_gru_encode_fwd(_p(tgt), M, Tf, H, C.byref(self.w_ency),
-                                         C.c_void_p(b["HxHy"].data_ptr() + 4 * H), 2 * H, st), "gru_encode_y")
+            self.side2.wait_stream(cur)
+            ck(lib.desire_gru_encode_ws_fwd(_p(tgt), M, Tf, H, C.byref(self.w_ency), C.c_void_p(b["HxHy"].data_ptr() + 4 * H),
+                                            2 * H, _p(self.ws_ency), self.ws_enc_bytes,
+                                            C.c_void_p(self.side2.cuda_stream)), "gru_encode_y")
+            ck(lib.desire_gru_encode_ws_fwd(_p(obs), M, Tp, H, C.byref(self.w_encx), _p(b["HxHy"]), 2 * H,
+                                            _p(self.ws_encx), self.ws_enc_bytes, st), "gru_encode_x")
+            cur.wait_stream(self.side2)
             ck(lib.desire_fc_fwd(_p(b["HxHy"]), 2 * H, _p(P["w_hidden_enc1"]), S2, _p(P["b_hidden_enc1"]),
                                  _p(b["vae_inputs"]), S2, M, S2, 2 * H, 1, 0, st), "fc_c")
             ck(lib.desire_cvae_encode_fwd(_p(b["vae_inputs"]), M, Zl, C.byref(self.w_venc), _p(b["mu_logvar"]), ws, wsb, st), "cvae_encode")

@@ -141,6 +141,12 @@ int desire_tconv_fwd(const float* obs, int M, int Tp, int C, const float* w, con
 int desire_gru_encode_fwd(const float* traj, int M, int T, int H, const desire_gru_t* w, float* h_out,
                           int ld_out, desire_stream_t stream);
 
+/* same result through the tcgen05 recurrence: the width-2 input projection is hoisted for all T steps into ws
+ * (desire_gru_encode_workspace_bytes), then the persistent tensor-core GRU of a10 runs them. */
+size_t desire_gru_encode_workspace_bytes(int M, int T, int H);
+int desire_gru_encode_ws_fwd(const float* traj, int M, int T, int H, const desire_gru_t* w, float* h_out,
+                             int ld_out, void* ws, size_t ws_bytes, desire_stream_t stream);
+
 /* ---- a6  vae_encoder, model/model.py:471-492.  v [M,1024] -> mu_logvar [M,2Z] (mean | logvar). */
 size_t desire_cvae_encode_workspace_bytes(int M, int Z);
 int desire_cvae_encode_fwd(const float* v, int M, int Z, const desire_cvae_enc_t* w, float* mu_logvar,
