@@ -157,18 +157,19 @@ def train(args):
             xval, yval, dval = data_loader.next_batch()
             x = DataLoader.to_model_layout(xval)         # [B,N,Tp,3] agent-major (the transpose train.py:158-173 forgot)
             y = DataLoader.to_model_layout(yval)
+            scene = data_loader.scene_images(dval, args.scene_size)   # reference.jpg next to the CSV, blank if absent
             if world > 1:                                # this rank's scenes of the minibatch
                 mine = shard_scenes(x.shape[0], rank, world)
-                x, y = np.ascontiguousarray(x[mine]), np.ascontiguousarray(y[mine])
+                x, y, scene = np.ascontiguousarray(x[mine]), np.ascontiguousarray(y[mine]), np.ascontiguousarray(scene[mine])
             step = epoch * data_loader.num_batches + batch
             if step < start_step:
                 continue
             if args.optimize:
-                c = model.train_step(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch + 7919 * rank)
+                c = model.train_step(x, y, eps=None, scene=scene, seed=args.seed + epoch * 100003 + batch + 7919 * rank)
                 # cost over the whole minibatch: sum_ranks(cost_r * n_r) / sum_ranks(n_r)   (model/model.py:376)
                 loss_batch = float(global_masked_cost(c[0] * c[1], c[1]))
             else:
-                out = model.forward(x, y, eps=None, scene=None, seed=args.seed + epoch * 100003 + batch)
+                out = model.forward(x, y, eps=None, scene=scene, seed=args.seed + epoch * 100003 + batch)
                 loss_batch = float(out["cost"])          # masked mean over existing agents (model.py:351-376)
             torch.cuda.synchronize()
             end = time.time()

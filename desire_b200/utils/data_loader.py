@@ -174,6 +174,38 @@ class DataLoader(object):
         self.dataset_pointer = 0
         self.frame_pointer = 0
 
+    # ------------------------------------------------------------------ scene context
+    SCENE_IMAGE_NAMES = ("reference.jpg", "reference.png", "reference.jpeg")
+
+    def scene_images(self, dval, size):
+        """Scene images for the sequences of a batch: for every dataset index in `dval` (third value of next_batch)
+        the `reference.jpg` that the Stanford Drone Dataset ships next to each video's annotations, resized to
+        size x size, RGB float32 in [0,1] -> [B,size,size,3] (the scene CNN's input layout).  The reference repository
+        ships only the CSVs (its data/ holds no images), so a missing file yields a blank (zero) scene — the same
+        input the training loop used before.  Decoded images are cached per dataset."""
+        if not hasattr(self, "_scene_cache"):
+            self._scene_cache = {}
+        files = self._csv_files()
+        out = np.zeros((len(dval), size, size, 3), np.float32)
+        for i, d in enumerate(dval):
+            key = (int(d), int(size))
+            if key not in self._scene_cache:
+                img = None
+                folder = os.path.dirname(files[int(d)]) if int(d) < len(files) else None
+                if folder:
+                    for name in self.SCENE_IMAGE_NAMES:
+                        path = os.path.join(folder, name)
+                        if os.path.exists(path):
+                            from PIL import Image      # only needed when an image is actually present
+                            with Image.open(path) as im:
+                                im = im.convert("RGB").resize((size, size), Image.BILINEAR)
+                                img = np.asarray(im, np.float32) / 255.0
+                            break
+                self._scene_cache[key] = img
+            if self._scene_cache[key] is not None:
+                out[i] = self._scene_cache[key]
+        return out
+
     # ------------------------------------------------------------------ model-side layout
     @staticmethod
     def to_model_layout(batch):

@@ -116,3 +116,26 @@ def test_dataset_walk_wrap_and_leave_dataset(tmp_path):
         _, _, dv = two.next_batch(random_update=False)
         seen |= set(dv)
     assert seen == {0, 1}                           # pointer ticks to the next dataset and wraps (data_loader.py:249-258)
+
+
+def test_scene_images_loaded_resized_and_blank_when_absent(tmp_path):
+    """SURVEY 8f #4: reference.jpg next to a video's CSV becomes the scene CNN input; datasets without one get zeros."""
+    from PIL import Image
+    from desire_b200.utils.data_loader import DataLoader
+    rows = np.array([[0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9],
+                     [1, 2] * 10, np.arange(20) * 1.0, np.arange(20) * 2.0])
+    for name, with_img in (("a", True), ("b", False)):
+        d = tmp_path / name / "video0"
+        d.mkdir(parents=True)
+        np.savetxt(d / "annotations_processed.csv", rows, delimiter=",")
+        if with_img:
+            img = np.zeros((10, 20, 3), np.uint8)
+            img[:, :10, 0] = 255                                   # left half red
+            Image.fromarray(img).save(d / "reference.png")
+    dl = DataLoader(1, 2, 4, 2, preprocess=True, data_dir=str(tmp_path) + "/", cache=False, pred_length=3)
+    files = dl._csv_files()
+    idx_with = [i for i, f in enumerate(files) if "/a/" in f][0]
+    sc = dl.scene_images([idx_with, 1 - idx_with], 8)
+    assert sc.shape == (2, 8, 8, 3) and sc.dtype == np.float32
+    assert sc[0, :, :3, 0].min() > 0.9 and sc[0, :, 5:, 0].max() < 0.1 and sc[0, ..., 1:].max() == 0
+    assert sc[1].max() == 0
