@@ -110,7 +110,7 @@ SIGNATURES = {
     # ---- train step
     "desire_cost_bwd": (I, [P, P, P, P, P, I, I, I, I, I, P, P, P]),
     "desire_readout_bwd": (I, [P, P, I, I, I, P, P, P, P, P]),
-    "desire_gru_decode_bwd_workspace_bytes": (Z, [I, I]),
+    "desire_gru_decode_bwd_workspace_bytes": (Z, [I, I, I]),
     "desire_gru_decode_bwd": (I, [P, P, I, I, I, I, I, C.POINTER(GruW), P, P, P, P, I, C.POINTER(GruG), P, Z, P]),
     "desire_mask_softmax_bwd_workspace_bytes": (Z, [I, I]),
     "desire_mask_softmax_bwd": (I, [P, I, I, I, I, P, P, P, I, P, P, P, I, P, P, P, Z, P]),

@@ -178,7 +178,7 @@ struct GruBptt {
   float* dh0;                           // [R,H], zeroed by the caller, receives d h_{-1}
   float *dwg, *dwc;                     // full-layout gradients (+=); only the state rows are touched here
 };
-size_t gru_bptt_ws_bytes(size_t R, int H);
+size_t gru_bptt_ws_bytes(size_t R, int H, int T);
 // after_step(t) runs on the host right after step t's kernels are enqueued (t = T-1 .. 0): Decoder-2 uses it to
 // push the social-pooling gradient of step t into dhs[t-1] before step t-1 consumes it.
 int gru_bptt(const GruBptt& a, void* ws, size_t ws_bytes, cudaStream_t st,

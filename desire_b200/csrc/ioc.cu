@@ -1034,7 +1034,7 @@ IocTrainLayout ioc_train_layout(const desire_ioc_dims_t* d) {
   L.dX48 = take(R * T * (d->Fv + d->Cs) * 4);
   L.vel = take(R * T * 2 * 4);
   L.dsT = take(R * T * 4);
-  L.bptt = take(gru_bptt_ws_bytes(R, (int)H));
+  L.bptt = take(gru_bptt_ws_bytes(R, (int)H, (int)T));
   L.pack = take(PACK_WS_BYTES);
   {
     // packed B operands of the tcgen05 weight gradients: dpre [R,H] (social fc) and dXP [R*T, 2H] (Decoder-2 inputs)

@@ -105,19 +105,34 @@ __global__ void reduce_k_rows_kernel(const float* __restrict__ src, size_t M, in
   dst[m * ld + c] += s;
 }
 
-// r,u = sigmoid(gh + xp_ru);  rh = r * h_prev
-__global__ void gru_bwd_gates_kernel(const float* __restrict__ gh, const float* __restrict__ xp, long xp_rs,
-                                     const float* __restrict__ hp, long hp_rs, size_t R, int H,
-                                     float* __restrict__ ru, float* __restrict__ rh) {
+// step-major copy of the previous states: hp_all[t][r][:] = h_{t-1}(r)  (h0e for t == 0)
+__global__ void gru_hprev_gather_kernel(const float* __restrict__ hs, long hs_rs, long hs_ss, const float* __restrict__ h0e,
+                                        size_t R, int T, int H, float* __restrict__ hp_all) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * H) return;
-  const size_t r = i / H;
+  if (i >= R * T * H) return;
   const int c = (int)(i % H);
-  const float rr = sigmoidf_(gh[r * 2 * H + c] + xp[r * xp_rs + c]);
-  const float uu = sigmoidf_(gh[r * 2 * H + H + c] + xp[r * xp_rs + H + c]);
-  ru[r * 2 * H + c] = rr;
-  ru[r * 2 * H + H + c] = uu;
-  rh[i] = rr * hp[r * hp_rs + c];
+  const size_t tr = i / H;
+  const size_t r = tr % R;
+  const int t = (int)(tr / R);
+  hp_all[i] = t > 0 ? hs[r * hs_rs + (size_t)(t - 1) * hs_ss + c] : h0e[r * H + c];
+}
+
+// gates of every step: r,u = sigmoid(gh + xp_ru(r,t));  rh = r * h_prev       (all buffers step-major [T][R][.])
+__global__ void gru_bwd_gates_all_kernel(const float* __restrict__ gh, const float* __restrict__ xp, long xp_rs, long xp_ss,
+                                         const float* __restrict__ hp, size_t R, int T, int H, float* __restrict__ ru,
+                                         float* __restrict__ rh) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * T * H) return;
+  const int c = (int)(i % H);
+  const size_t tr = i / H;
+  const size_t r = tr % R;
+  const int t = (int)(tr / R);
+  const float* x = xp + r * xp_rs + (size_t)t * xp_ss;
+  const float rr = sigmoidf_(gh[tr * 2 * H + c] + x[c]);
+  const float uu = sigmoidf_(gh[tr * 2 * H + H + c] + x[H + c]);
+  ru[tr * 2 * H + c] = rr;
+  ru[tr * 2 * H + H + c] = uu;
+  rh[i] = rr * hp[i];
 }
 
 // c = tanh(ch + xp_c); from dh: dcpre, dupre (-> dg[:,H:]), tmp = dh*u; dxp[c], dxp[u] +=
@@ -163,57 +178,74 @@ __global__ void gru_bwd_reset_kernel(const float* __restrict__ drh, const float*
 }  // namespace
 
 namespace desire {
-size_t gru_bptt_ws_bytes(size_t R, int H) {
-  // gh[2H] ru[2H] dg[2H] + rh ch dcpre drh tmp [H each]
-  return 3 * align_up(R * 2 * H * 4) + 5 * align_up(R * H * 4) + PACK_WS_BYTES;
+size_t gru_bptt_ws_bytes(size_t R, int H, int T) {
+  // step-major [T][R][.] buffers: gh/dg[2H] ru[2H] hp rh ch dcpre [H each]; per-step drh tmp [H]; GEMM + wgrad packs
+  const size_t RT = R * (size_t)T;
+  return 2 * align_up(RT * 2 * H * 4) + 4 * align_up(RT * H * 4) + 2 * align_up(R * H * 4) + PACK_WS_BYTES +
+         wgrad_tc_pack_bytes((int)RT, 2 * H);
 }
 
+// The forward quantities the backward needs (gates r,u and the candidate pre-activation) only depend on the SAVED
+// states h_{t-1}, so they are recomputed for ALL T steps at once — two large GEMMs and one element-wise kernel over
+// [T*R] rows instead of two small GEMMs per step — and the two recurrent weight gradients become one tcgen05 product
+// each over T*R rows after the loop.  The serial part is what is inherently serial: per step two element-wise kernels
+// and the two input-gradient GEMMs that carry d h_{t-1}.
 int gru_bptt(const GruBptt& a, void* ws, size_t ws_bytes, cudaStream_t st, const std::function<int(int)>* after_step) {
-  const size_t R = a.R;
-  const int H = a.H;
+  const size_t R = a.R, RT = R * (size_t)a.T;
+  const int H = a.H, T = a.T;
+  DESIRE_CHECK_ARG(RT < ((size_t)1 << 31), "gru_bptt: R*T too large");
   Workspace W(ws, ws_bytes);
-  float* gh = W.take<float>(R * 2 * H);
-  float* ru = W.take<float>(R * 2 * H);
-  float* dg = W.take<float>(R * 2 * H);
-  float* rh = W.take<float>(R * H);
-  float* ch = W.take<float>(R * H);
-  float* dcpre = W.take<float>(R * H);
+  float* gh_all = W.take<float>(RT * 2 * H);      // h_prev @ Wg_h for every step; reused as d(gate pre-activations)
+  float* ru_all = W.take<float>(RT * 2 * H);
+  float* hp_all = W.take<float>(RT * H);
+  float* rh_all = W.take<float>(RT * H);
+  float* ch_all = W.take<float>(RT * H);
+  float* dcpre_all = W.take<float>(RT * H);
   float* drh = W.take<float>(R * H);
   float* tmp = W.take<float>(R * H);
   char* pk = W.take<char>(PACK_WS_BYTES);
-  if (!pk) {
+  const size_t wpb = wgrad_tc_pack_bytes((int)RT, 2 * H);
+  char* wpk = W.take<char>(wpb);
+  if (!pk || !wpk) {
     set_error("gru_bptt: workspace too small");
     return DESIRE_ERR_WORKSPACE;
   }
-  PackWs pw{pk, PACK_WS_BYTES};
+  PackWs pw{pk, PACK_WS_BYTES}, wp{wpk, wpb};
+  float* dg_all = gh_all;
   const float* wg_h = a.wg + (size_t)a.I * 2 * H;
   const float* wc_h = a.wc + (size_t)a.I * H;
   float* dwg_h = a.dwg + (size_t)a.I * 2 * H;
   float* dwc_h = a.dwc + (size_t)a.I * H;
+  // ---- forward recompute, all steps at once
+  DESIRE_LAUNCH(st, (gru_hprev_gather_kernel<<<grid1d(RT * H), 256, 0, st>>>(a.hs, a.hs_rs, a.hs_ss, a.h0e, R, T, H, hp_all)));
+  DESIRE_TRY(sgemm(hp_all, H, wg_h, 2 * H, false, nullptr, gh_all, 2 * H, (int)RT, 2 * H, H, DESIRE_ACT_NONE, false, st, pw));
+  DESIRE_LAUNCH(st, (gru_bwd_gates_all_kernel<<<grid1d(RT * H), 256, 0, st>>>(gh_all, a.xp, a.xp_rs, a.xp_ss, hp_all, R, T, H,
+                                                                             ru_all, rh_all)));
+  DESIRE_TRY(sgemm(rh_all, H, wc_h, H, false, nullptr, ch_all, H, (int)RT, H, H, DESIRE_ACT_NONE, false, st, pw));
+  // ---- backward through time
   const unsigned g = grid1d(R * H);
-  for (int t = a.T - 1; t >= 0; --t) {
-    const float* hp = t > 0 ? a.hs + (size_t)(t - 1) * a.hs_ss : a.h0e;
-    const long hp_rs = t > 0 ? a.hs_rs : H;
+  for (int t = T - 1; t >= 0; --t) {
+    const float* hp = hp_all + (size_t)t * R * H;
+    const float* ru = ru_all + (size_t)t * R * 2 * H;
+    float* dg = dg_all + (size_t)t * R * 2 * H;
+    float* dcpre = dcpre_all + (size_t)t * R * H;
     const float* xp = a.xp + (size_t)t * a.xp_ss;
     float* dxp = a.dxp + (size_t)t * a.dxp_ss;
     float* target = t > 0 ? a.dhs + (size_t)(t - 1) * a.dhs_ss : a.dh0;
     const long tg_rs = t > 0 ? a.dhs_rs : H;
-    DESIRE_TRY(sgemm(hp, (int)hp_rs, wg_h, 2 * H, false, nullptr, gh, 2 * H, a.R, 2 * H, H, DESIRE_ACT_NONE, false, st, pw));
-    DESIRE_LAUNCH(st, (gru_bwd_gates_kernel<<<g, 256, 0, st>>>(gh, xp, a.xp_rs, hp, hp_rs, R, H, ru, rh)));
-    DESIRE_TRY(sgemm(rh, H, wc_h, H, false, nullptr, ch, H, a.R, H, H, DESIRE_ACT_NONE, false, st, pw));
-    DESIRE_LAUNCH(st, (gru_bwd_cand_kernel<<<g, 256, 0, st>>>(ch, xp, a.xp_rs, hp, hp_rs, ru,
+    DESIRE_LAUNCH(st, (gru_bwd_cand_kernel<<<g, 256, 0, st>>>(ch_all + (size_t)t * R * H, xp, a.xp_rs, hp, H, ru,
                                                               a.dhs + (size_t)t * a.dhs_ss, a.dhs_rs, R, H, dcpre, dg,
                                                               tmp, dxp, a.dxp_rs)));
     // d(r*h) = dcpre @ Wc_h^T
     DESIRE_TRY(sgemm(dcpre, H, wc_h, H, true, nullptr, drh, H, a.R, H, H, DESIRE_ACT_NONE, false, st, pw));
-    DESIRE_LAUNCH(st, (gru_bwd_reset_kernel<<<g, 256, 0, st>>>(drh, hp, hp_rs, ru, tmp, R, H, dg, target, tg_rs, dxp,
-                                                               a.dxp_rs)));
+    DESIRE_LAUNCH(st, (gru_bwd_reset_kernel<<<g, 256, 0, st>>>(drh, hp, H, ru, tmp, R, H, dg, target, tg_rs, dxp, a.dxp_rs)));
     // d h_prev += dg @ Wg_h^T
     DESIRE_TRY(sgemm(dg, 2 * H, wg_h, 2 * H, true, nullptr, target, (int)tg_rs, a.R, H, 2 * H, DESIRE_ACT_NONE, true, st, pw));
-    DESIRE_TRY(wgrad_tn(hp, (int)hp_rs, dg, 2 * H, dwg_h, 2 * H, a.R, H, 2 * H, st));
-    DESIRE_TRY(wgrad_tn(rh, H, dcpre, H, dwc_h, H, a.R, H, H, st));
     if (after_step) DESIRE_TRY((*after_step)(t));
   }
+  // ---- recurrent weight gradients over all T*R rows
+  DESIRE_TRY(wgrad_tn(hp_all, H, dg_all, 2 * H, dwg_h, 2 * H, (int)RT, H, 2 * H, st, wp));
+  DESIRE_TRY(wgrad_tn(rh_all, H, dcpre_all, H, dwc_h, H, (int)RT, H, H, st, wp));
   return DESIRE_OK;
 }
 }  // namespace desire
@@ -512,10 +544,10 @@ extern "C" int desire_readout_bwd(const float* hs, const float* dYhat, int R, in
   return DESIRE_OK;
 }
 
-extern "C" size_t desire_gru_decode_bwd_workspace_bytes(int R, int H) {
+extern "C" size_t desire_gru_decode_bwd_workspace_bytes(int R, int H, int T) {
   const size_t r = (size_t)R;
   // xp[3H] dxp[3H] h0e[H] dh0[H] + bptt scratch
-  return 2 * align_up(r * 3 * H * 4) + 2 * align_up(r * H * 4) + gru_bptt_ws_bytes(r, H);
+  return 2 * align_up(r * 3 * H * 4) + 2 * align_up(r * H * 4) + gru_bptt_ws_bytes(r, H, T);
 }
 
 extern "C" int desire_gru_decode_bwd(const float* x_z, const float* Hx, int ld_hx, int R, int K, int H, int T,
@@ -524,7 +556,7 @@ extern "C" int desire_gru_decode_bwd(const float* x_z, const float* Hx, int ld_h
                                      desire_stream_t stream) {
   DESIRE_CHECK_ARG(x_z && Hx && w && hs && dhs && dx_z && dHx && g && R >= 0 && K > 0 && T > 0 && H > 0 && R % K == 0,
                    "desire_gru_decode_bwd: bad arguments");
-  if (!ws || ws_bytes < desire_gru_decode_bwd_workspace_bytes(R, H)) {
+  if (!ws || ws_bytes < desire_gru_decode_bwd_workspace_bytes(R, H, T)) {
     set_error("desire_gru_decode_bwd: workspace too small");
     return DESIRE_ERR_WORKSPACE;
   }
@@ -570,7 +602,7 @@ extern "C" int desire_gru_decode_bwd(const float* x_z, const float* Hx, int ld_h
 extern "C" size_t desire_gru_encode_bwd_workspace_bytes(int M, int T, int H) {
   const size_t m = (size_t)M;
   // xp, dxp [M,T,3H]; hs, dhs [M,T,H]; h0e, dh0 [M,H]
-  return 2 * align_up(m * T * 3 * H * 4) + 2 * align_up(m * T * H * 4) + 2 * align_up(m * H * 4) + gru_bptt_ws_bytes(m, H);
+  return 2 * align_up(m * T * 3 * H * 4) + 2 * align_up(m * T * H * 4) + 2 * align_up(m * H * 4) + gru_bptt_ws_bytes(m, H, T);
 }
 
 extern "C" int desire_gru_encode_bwd(const float* traj, int M, int T, int H, const desire_gru_t* w, const float* dh,

@@ -277,7 +277,7 @@ class TrainPath(HotPath):
         self.dbuf["dfmap"] = torch.empty_like(self.buf["scene_features"])
         self.buf["ioc_cost"] = f(2)
         lib = self.lib
-        bws = max(lib.desire_gru_decode_bwd_workspace_bytes(R, H), lib.desire_mask_softmax_bwd_workspace_bytes(R, H),
+        bws = max(lib.desire_gru_decode_bwd_workspace_bytes(R, H, Tf), lib.desire_mask_softmax_bwd_workspace_bytes(R, H),
                   lib.desire_cvae_decode_bwd_workspace_bytes(R, Zl), lib.desire_cvae_encode_bwd_workspace_bytes(M, Zl),
                   lib.desire_gru_encode_bwd_workspace_bytes(M, max(cfg.seq_length, Tf), H))
         if self.train_ioc:

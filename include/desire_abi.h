@@ -241,7 +241,7 @@ int desire_readout_bwd(const float* hs, const float* dYhat, int R, int T, int H,
                        float* d_out_w, float* d_out_b, desire_stream_t stream);
 /* a10 backward through time.  dhs [R,T,H]: in = gradient reaching every state from the read-out, clobbered.
  * dx_z [R,H] overwritten; dHx (row m, stride ld_dhx) += sum_k d h0. */
-size_t desire_gru_decode_bwd_workspace_bytes(int R, int H);
+size_t desire_gru_decode_bwd_workspace_bytes(int R, int H, int T);
 int desire_gru_decode_bwd(const float* x_z, const float* Hx, int ld_hx, int R, int K, int H, int T,
                           const desire_gru_t* w, const float* hs, float* dhs, float* dx_z, float* dHx,
                           int ld_dhx, const desire_gru_grad_t* g, void* ws, size_t ws_bytes,
