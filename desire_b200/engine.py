@@ -117,6 +117,8 @@ class HotPath:
         ck = _lib.check
         if "rank" in stages:
             stages = tuple(x for x in stages if x != "rank") + ("scene", "ioc")
+        if "generate" in stages:
+            stages = stages + ("encode", "decode")      # the two halves of the generation stage (eps enters the second)
         if "scene" in stages:
             if tuple(scene.shape) != (self.B, cfg.scene_size, cfg.scene_size, 3) or not scene.is_contiguous():
                 raise ValueError("scene must be contiguous [B,%d,%d,3]" % (cfg.scene_size, cfg.scene_size))
@@ -127,7 +129,7 @@ class HotPath:
             ck(lib.desire_scene_cnn_fwd(_p(scene), self.B, cfg.scene_size, cfg.scene_size, cfg.scene_channels,
                                         C.byref(self.w_scene), _p(b["scene_features"]), _p(self.ws_scene),
                                         self.ws_scene_bytes, C.c_void_p(s_str.cuda_stream)), "scene_cnn")
-        if "generate" in stages:
+        if "encode" in stages:
             ck(lib.desire_tconv_fwd(_p(obs), M, Tp, Cm, _p(P["temporal_w"]), _p(P["temporal_b"]), _p(b["rho_i"]), st), "tconv")
             self.side2.wait_stream(cur)
             ck(lib.desire_gru_encode_ws_fwd(_p(tgt), M, Tf, H, C.byref(self.w_ency), C.c_void_p(b["HxHy"].data_ptr() + 4 * H),
@@ -139,6 +141,7 @@ class HotPath:
             ck(lib.desire_fc_fwd(_p(b["HxHy"]), 2 * H, _p(P["w_hidden_enc1"]), S2, _p(P["b_hidden_enc1"]),
                                  _p(b["vae_inputs"]), S2, M, S2, 2 * H, 1, 0, st), "fc_c")
             ck(lib.desire_cvae_encode_fwd(_p(b["vae_inputs"]), M, Zl, C.byref(self.w_venc), _p(b["mu_logvar"]), ws, wsb, st), "cvae_encode")
+        if "decode" in stages:
             ck(lib.desire_reparam_fwd(_p(b["mu_logvar"]), _p(eps), M, K, Zl, _p(b["zval"]), st), "reparam")
             ck(lib.desire_cvae_decode_fwd(_p(b["zval"]), R, Zl, C.byref(self.w_vdec), _p(b["x_reconstr_mean"]), ws, wsb, st), "cvae_decode")
             ck(lib.desire_mask_softmax_fwd(_p(b["x_reconstr_mean"]), R, S2, H, K, _p(P["w_post_vae"]), _p(P["b_post_vae"]),
@@ -189,29 +192,43 @@ class HotPath:
                 self.run(*self.static_in)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
-        self.graph_gen, self.graph_scene, self.graph_rank = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.graph_enc, self.graph_gen, self.graph_scene, self.graph_rank = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(),
+                                                                              torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
+        with torch.cuda.graph(self.graph_enc):
+            self.run(*self.static_in, stages=("encode",))
         with torch.cuda.graph(self.graph_gen):
-            self.run(*self.static_in, stages=("generate",))
+            self.run(*self.static_in, stages=("decode",))
         with torch.cuda.graph(self.graph_scene):
             self.run(*self.static_in, stages=("scene",))
         with torch.cuda.graph(self.graph_rank):
             self.run(*self.static_in, stages=("ioc",))
         self.copy_stream = torch.cuda.Stream(self.device)
         self.copy_done = torch.cuda.Event()
+        self.eps_done = torch.cuda.Event()
         return self.graph_gen, self.graph_rank
 
-    def replay_split(self, obs, tgt, eps, stage_scene):
-        """obs/tgt/eps: pinned host (or device) tensors; stage_scene(): returns the pinned scene tensor — called
-        AFTER the generation graph has been launched, so its host-side memcpy, its H2D copy and the scene CNN (on a
-        second stream) overlap the generation kernels.  The ranking graph waits on that stream."""
-        for dst, src in zip(self.static_in[:3], (obs, tgt, eps)):
-            dst.copy_(src, non_blocking=True)
+    def replay_split(self, obs, tgt, stage_eps, stage_scene):
+        """Host-buffer replay.  obs/tgt: pinned host tensors (small); stage_eps() / stage_scene() return the pinned eps
+        and scene tensors and are called only AFTER GPU work that does not need them has been launched, so their
+        host-side memcpy, their H2D copies (second stream) and the scene CNN overlap the encoder graph and the
+        decoder graph respectively:
+            main:  H2D obs,tgt | encode graph ............ | wait eps | decode graph ............... | wait scene | IOC graph
+            host:              | memcpy eps -> pinned      |          | memcpy scene -> pinned       |
+            copy:                          | H2D eps       |                       | H2D scene, scene CNN |"""
+        cur = torch.cuda.current_stream(self.device)
+        self.static_in[0].copy_(obs, non_blocking=True)
+        self.static_in[1].copy_(tgt, non_blocking=True)
+        self.graph_enc.replay()
+        eps = stage_eps()
+        with torch.cuda.stream(self.copy_stream):
+            self.static_in[2].copy_(eps, non_blocking=True)
+            self.eps_done.record(self.copy_stream)
+        cur.wait_event(self.eps_done)
         self.graph_gen.replay()
         scene = stage_scene()
-        cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.copy_stream):
             self.static_in[3].copy_(scene, non_blocking=True)
-            self.graph_scene.replay()              # the scene CNN runs next to the rest of the generation graph
+            self.graph_scene.replay()              # the scene CNN runs next to the rest of the decoder graph
             self.copy_done.record(self.copy_stream)
         cur.wait_event(self.copy_done)
         self.graph_rank.replay()

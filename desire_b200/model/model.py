@@ -182,9 +182,10 @@ class DESIREModel(object):
             if hp.graph_gen is None:
                 pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data), ("eps", eps), ("scene", scene))]
                 hp.capture_split(*[p.to(self.device) for p in pins])
-            pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data), ("eps", eps))]
-            # the scene images (the largest input) are staged while the generation graph is already running
-            out = hp.replay_split(*pins, stage_scene=lambda: self._pin("scene", scene))
+            pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data))]
+            # eps and the scene images (the two large inputs) are staged while graphs that do not need them run
+            out = hp.replay_split(*pins, stage_eps=lambda: self._pin("eps", eps),
+                                  stage_scene=lambda: self._pin("scene", scene))
         else:
             out = self.forward(input_data, target_data, eps, scene)
         B = out["Y_refined"].shape[0] // (cfg.max_num_obj * cfg.K)
