@@ -43,7 +43,8 @@ __host__ __device__ inline Layout make_layout(int H, int Npad, int G, int n_rad,
   L.tab = off; off += (size_t)((n_rad + 1 + 2 * n_ang + 3) / 4 * 4) * 4;
   L.list_stride = (size_t)((G + 1 + Npad + 3) / 4 * 4);          // bytes per row: off[G+1] then list[Npad]
   L.lists = off; off += TM * L.list_stride;
-  L.bins = off; off += (size_t)TM * Npad;                       // bin of every (row, neighbour) pair, 255 = none
+  L.bins = off; off += (size_t)TM * (Npad + 4);                 // bin of every (row, neighbour) pair, 255 = none; the row
+                                                                // stride Npad+4 bytes keeps the 32 rows a warp writes on 32 banks
   off = (off + 1023) / 1024 * 1024;
   L.stage_bytes = 2 * (size_t)KC * TM * 16 + 2 * (size_t)KC * H * 16;
   L.stages = off; off += STAGES * L.stage_bytes;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
       const int rl = tid & (TM - 1), q = tid >> 7;
       const long r = rowmap[rl];
       const int gbase = (rl / Npad) * Npad, me = rl % Npad;
-      uint8_t* brow = bins + (size_t)rl * Npad;
+      uint8_t* brow = bins + (size_t)rl * (Npad + 4);
       // a masked row still pools its existing neighbours: its own position comes from global memory
       float xi = 0.f, yi = 0.f;
       if (r >= 0) {
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
     if (tid < TM) {
       uint8_t* off = lists + (size_t)tid * L.list_stride;       // [G+1]
       uint8_t* lst = off + G + 1;                                // [Npad]
-      const uint8_t* brow = bins + (size_t)tid * Npad;
+      const uint8_t* brow = bins + (size_t)tid * (Npad + 4);
       for (int g = 0; g <= G; ++g) off[g] = 0;
       for (int j = 0; j < N; ++j) {                              // counts, stored at off[g+1]
         const int g = brow[j];
