@@ -78,6 +78,37 @@ class HotPath:
         self.ws_scene_bytes = max(lib.desire_scene_cnn_workspace_bytes(B, cfg.scene_size, cfg.scene_size), 256)
         self.ws_scene = torch.empty(self.ws_scene_bytes, dtype=torch.uint8, device=self.device)
         self.side = torch.cuda.Stream(self.device)
+        # IOC ranking/refinement is a chain of ~50 dependent launches per iteration whose tile counts do not divide the
+        # SM count (320 / 300 tiles on 148 SMs: every launch ends in a mostly idle round).  Scenes are independent,
+        # so the batch is cut into `ioc_chains` groups of scenes, each an independent chain on its own stream / graph
+        # branch with its own scratch: the idle tail of one chain's launch is filled by the other chains' CTAs.
+        import os
+        self.ioc_chains = 1
+        want = int(os.environ.get("DESIRE_IOC_CHAINS", "0"))        # 0 = automatic
+        if want > 1:
+            if B % want == 0 and B >= 2 * want:
+                self.ioc_chains = want
+        elif want == 0 and B >= 8 and N <= 128:
+            # automatic: the fewest chains whose launches fit one round of the machine (measured at B=32: 1 chain
+            # 19.3 ms/step, 2 chains 22.5 — two 160-tile launches fight over 148 SMs —, 4 chains 18.7, 8 chains 19.6)
+            npad = 8
+            while npad < N:
+                npad *= 2
+            n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            for c in range(2, B // 2 + 1):
+                if B % c == 0 and -(-(B // c) * K // (128 // npad)) <= n_sm:
+                    self.ioc_chains = c
+                    break
+        if self.ioc_chains > 1:
+            Bc = B // self.ioc_chains
+            self.ioc_dims_c = _lib.IocDims(Bc, N, K, H, Tf, Cm, cfg.vel_dim, cfg.scene_channels, cfg.n_rad, cfg.n_ang,
+                                           Hm, Hm, cfg.ioc_iters)
+            self.ws_ioc_bytes = max(lib.desire_ioc_workspace_bytes(C.byref(self.ioc_dims_c)), 256)
+            self.ws_ioc = [torch.empty(self.ws_ioc_bytes, dtype=torch.uint8, device=self.device)
+                           for _ in range(self.ioc_chains)]
+            self.ioc_streams = [torch.cuda.Stream(self.device) for _ in range(self.ioc_chains - 1)]
+            self.scores_c = [torch.empty(max(cfg.ioc_iters, 1), Bc * N * K, dtype=torch.float32, device=self.device)
+                             for _ in range(self.ioc_chains)]
         # the two encoders run side by side on the tensor-core recurrence, each with its own scratch
         self.side2 = torch.cuda.Stream(self.device)
         self.ws_enc_bytes = max(lib.desire_gru_encode_workspace_bytes(M, max(Tp, Tf), H), 256)
@@ -157,9 +188,28 @@ class HotPath:
             if "scene" in stages and "generate" in stages:
                 cur.wait_stream(self.side)         # join the scene-CNN branch
             b["Y_refined"].copy_(b["Yhat"])
-            ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs), Tp,
-                                  _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["Y_refined"]), _p(b["ioc_scores"]),
-                                  ws, wsb, st), "ioc")
+            if self.ioc_chains == 1:
+                ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs), Tp,
+                                      _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["Y_refined"]), _p(b["ioc_scores"]),
+                                      ws, wsb, st), "ioc")
+            else:
+                nc, Bc = self.ioc_chains, self.B // self.ioc_chains
+                Mc, Rc = Bc * N, Bc * N * K
+                off = lambda t, rows_per_scene_block, c: C.c_void_p(t.data_ptr() + 4 * c * rows_per_scene_block)
+                for c in range(nc):
+                    s_c = cur if c == 0 else self.ioc_streams[c - 1]
+                    if c > 0:
+                        s_c.wait_stream(cur)
+                    ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims_c), C.byref(self.w_ioc),
+                                          off(b["scene_features"], Bc * self.Hm * self.Hm * cfg.scene_channels, c),
+                                          off(obs, Mc * Tp * 3, c), Tp, off(b["HxHy"], Mc * 2 * H, c), 2 * H,
+                                          off(b["feature_pooling"], Rc * Tf * 2 * Cm, c), off(b["Y_refined"], Rc * Tf * 2, c),
+                                          _p(self.scores_c[c]), _p(self.ws_ioc[c]), self.ws_ioc_bytes,
+                                          C.c_void_p(s_c.cuda_stream)), "ioc chain %d" % c)
+                    with torch.cuda.stream(s_c):
+                        b["ioc_scores"][:, c * Rc:(c + 1) * Rc].copy_(self.scores_c[c])
+                for c in range(1, nc):
+                    cur.wait_stream(self.ioc_streams[c - 1])
         return self.outputs()
 
     # ------------------------------------------------------------------ CUDA graph: capture once, replay per step
