@@ -994,10 +994,23 @@ __global__ void scene_gather_bwd_kernel(const float* __restrict__ dfs, int ld, i
   }
 }
 
+// score[r] = sum_t (hs2[r,t,:] . w + b)     one warp per row (single-pass schedule of the train step)
+__global__ void score_states_kernel(const float* __restrict__ hs2, long R, int T, int H, const float* __restrict__ w,
+                                    const float* __restrict__ b, float* __restrict__ score) {
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float s = 0.f;
+  for (int e = lane; e < T * H; e += 32) s = fmaf(hs2[row * T * H + e], __ldg(w + e % H), s);
+  s = warp_sum(s);
+  if (lane == 0) score[row] = s + (float)T * __ldg(b);
+}
+
 struct IocTrainLayout {
   size_t snaps, dscore, dDY, rows, Xs, XP, dXP, fsp, hs2, dhs, pooled, dpool, h0e, dh0, dpre, cnt, dX48, vel, dsT, bptt, pack,
       wpack, wpack_bytes, fwd, total;
   bool keep;   // every step's pooled tensor is kept for the sp_w gradient (one GEMM over all steps) when it fits
+  bool single; // ... and the intermediates of ALL iterations fit: one forward pass, no fused phase A / recompute
 };
 IocTrainLayout ioc_train_layout(const desire_ioc_dims_t* d) {
   const size_t R = (size_t)d->B * d->N * d->K, T = d->Tf, H = d->H, M = (size_t)d->B * d->N;
@@ -1014,18 +1027,21 @@ IocTrainLayout ioc_train_layout(const desire_ioc_dims_t* d) {
   L.dscore = take(it * R * 4);
   L.dDY = take(it * R * T * 2 * 4);
   L.rows = take(M * 4);
-  L.Xs = take(R * T * Dst * 4);
-  L.XP = take(R * T * 3 * H * 4);
-  L.dXP = take(R * T * 3 * H * 4);
-  L.fsp = take(R * T * H * 4);
-  L.hs2 = take(R * T * H * 4);
-  L.dhs = take(R * T * H * 4);
-  // budget for keeping every step's pooled tensor (default 12 GiB; DESIRE_IOC_KEEP_POOLED_BYTES overrides it — the
-  // tests use 0 to exercise the rebuild-per-step path that large scenes take)
+  // budget for keeping every step's pooled tensor (default 12 GiB per iteration; DESIRE_IOC_KEEP_POOLED_BYTES overrides
+  // it — the tests use 0 to exercise the rebuild-per-step path that large scenes take)
   size_t keep_budget = (size_t)12 << 30;
   if (const char* e = getenv("DESIRE_IOC_KEEP_POOLED_BYTES")) keep_budget = (size_t)strtoull(e, nullptr, 10);
   L.keep = R * G * H * 4 * T <= keep_budget;
-  L.pooled = take((L.keep ? T : 1) * R * G * H * 4);
+  const size_t per_it = R * T * (Dst + 3 * H + 2 * H) * 4 + R * G * H * 4 * T;
+  L.single = L.keep && it * per_it <= 2 * keep_budget && getenv("DESIRE_IOC_TWO_PHASE") == nullptr;
+  const size_t nit = L.single ? it : 1;
+  L.Xs = take(nit * R * T * Dst * 4);
+  L.XP = take(nit * R * T * 3 * H * 4);
+  L.dXP = take(R * T * 3 * H * 4);
+  L.fsp = take(nit * R * T * H * 4);
+  L.hs2 = take(nit * R * T * H * 4);
+  L.dhs = take(R * T * H * 4);
+  L.pooled = take(nit * (L.keep ? T : 1) * R * G * H * 4);
   L.dpool = L.keep ? take(R * G * H * 4) : L.pooled;
   L.h0e = take(R * H * 4);
   L.dh0 = take(R * H * 4);
@@ -1077,8 +1093,8 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
   DESIRE_CHECK_ARG(R * T < (1L << 31) / 4, "desire_ioc_train: R*T too large");
   char* base = (char*)ws;
   auto fp = [&](size_t o) { return (float*)(base + o); };
-  float *snaps = fp(L.snaps), *dscore = fp(L.dscore), *dDY = fp(L.dDY), *rows = fp(L.rows), *Xs = fp(L.Xs), *XP = fp(L.XP),
-        *dXP = fp(L.dXP), *fsp = fp(L.fsp), *hs2 = fp(L.hs2), *dhs = fp(L.dhs), *pooled0 = fp(L.pooled), *dpool = fp(L.dpool),
+  float *snaps = fp(L.snaps), *dscore = fp(L.dscore), *dDY = fp(L.dDY), *rows = fp(L.rows), *Xs_base = fp(L.Xs), *XP_base = fp(L.XP),
+        *dXP = fp(L.dXP), *fsp_base = fp(L.fsp), *hs2_base = fp(L.hs2), *dhs = fp(L.dhs), *pooled0 = fp(L.pooled), *dpool = fp(L.dpool),
         *h0e = fp(L.h0e), *dh0 = fp(L.dh0), *dpre0 = fp(L.dpre), *cnt = fp(L.cnt), *dX48 = fp(L.dX48), *vel = fp(L.vel),
         *dsT = fp(L.dsT);
   const bool keep = L.keep;
@@ -1090,22 +1106,23 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
   const desire_gru_grad_t& gg = g->dec2;
   const int I = Dst + H;                                   // input rows of the Decoder-2 kernels
 
-  // ---- phase A: the forward of every iteration (fast fused path) with snapshots of the trajectories
-  DESIRE_CUDA(cudaMemcpyAsync(Y, Yhat, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
-  DESIRE_TRY(ioc_fwd_impl(d, w, fmap, obs, Tp, Hx, ld_hx, fpool, Y, scores, base + L.fwd, ws_bytes - L.fwd, stream, snaps));
-  DESIRE_LAUNCH(st, (ioc_loss_kernel<<<blocks((long)M * 32, 256), 256, 0, st>>>(scores, snaps, target, obs, count, M, K, T, Tp,
-                                                                                iters, rows, dscore, dDY)));
-  DESIRE_LAUNCH(st, (ioc_cost_kernel<<<1, 1024, 0, st>>>(rows, obs, count, M, Tp, ioc_cost)));
-
-  // ---- phase B: per iteration, recompute with every intermediate kept, then backward
-  DESIRE_LAUNCH(st, (copy_cols_kernel<<<blocks(R * T * C2, 256), 256, 0, st>>>(fpool, C2, R * T, Xs + Fv + Cs, Dst)));
-  DESIRE_LAUNCH(st, (expand_rows_kernel<<<blocks(R * H, 256), 256, 0, st>>>(Hx, ld_hx, K, H, R, h0e)));
   const float* wg_sp = gw.wg + (size_t)Dst * 2 * H;        // rows multiplying the social feature
   const float* wc_sp = gw.wc + (size_t)Dst * H;
   const float* wg_h = gw.wg + (size_t)I * 2 * H;           // rows multiplying the state
   const float* wc_h = gw.wc + (size_t)I * H;
-  for (int it = 0; it < iters; ++it) {
-    const float* Yi = snaps + (size_t)it * R * T * 2;
+  // Two schedules.  single == true (the per-iteration intermediates of ALL iterations fit the budget): the forward of
+  // every iteration runs ONCE, with everything the backward needs kept per iteration; otherwise the fast fused forward
+  // produces scores / trajectories first (phase A) and every iteration is recomputed right before its backward.
+  const bool single = L.single;
+  const size_t xs_it = single ? (size_t)R * T * Dst : 0, xp_it = single ? (size_t)R * T * 3 * H : 0,
+               st_it = single ? (size_t)R * T * H : 0, pool_it = single ? (size_t)T * R * G * H : 0;
+  DESIRE_LAUNCH(st, (expand_rows_kernel<<<blocks(R * H, 256), 256, 0, st>>>(Hx, ld_hx, K, H, R, h0e)));
+
+  // ---- forward of iteration `it` from the trajectories Yi, keeping Xs, XP, fsp, hs2 (and pooled when `keep`)
+  auto forward_iter = [&](int it, const float* Yi) -> int {
+    float *Xs = Xs_base + it * xs_it, *XP = XP_base + it * xp_it, *fsp = fsp_base + it * st_it, *hs2 = hs2_base + it * st_it;
+    float* pooled_it = pooled0 + it * pool_it;
+    DESIRE_LAUNCH(st, (copy_cols_kernel<<<blocks(R * T * C2, 256), 256, 0, st>>>(fpool, C2, R * T, Xs + Fv + Cs, Dst)));
     // static features and their hoisted projection (biases included)
     DESIRE_LAUNCH(st, (vel_fc_kernel<<<blocks(R * T * Fv, 256), 256, 0, st>>>(Yi, obs, Tp, R, K, T, Fv, w->vel_w, w->vel_b, Xs, Dst)));
     DESIRE_LAUNCH(st, (scene_gather_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(fmap, d->Hm, d->Wm, Cs, Yi, 2, R * T,
@@ -1115,7 +1132,7 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
     for (int t = 0; t < T; ++t) {
       const float* hp = t > 0 ? hs2 + (size_t)(t - 1) * H : h0e;
       const int hp_ld = t > 0 ? T * H : H;
-      float* pooled = pooled0 + (size_t)t * pooled_step;
+      float* pooled = pooled_it + (size_t)t * pooled_step;
       DESIRE_TRY(social_pool_launch(Yi + 2 * t, 2L * T, hp, hp_ld, obs, Tp, d->B, N, K, H, d->n_rad, d->n_ang, w->r2_edges,
                                     w->dirs, pooled, st));
       float* fsp_t = fsp + (size_t)t * H;
@@ -1131,6 +1148,13 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
       a.h_final = hs2 + (size_t)t * H; a.ld_hf = T * H;
       DESIRE_TRY(gru_seq(a, st, pw));
     }
+    return DESIRE_OK;
+  };
+
+  // ---- backward of iteration `it` (needs dscore[it], dDY[it] and the buffers forward_iter(it, .) left)
+  auto backward_iter = [&](int it, const float* Yi) -> int {
+    float *Xs = Xs_base + it * xs_it, *XP = XP_base + it * xp_it, *fsp = fsp_base + it * st_it, *hs2 = hs2_base + it * st_it;
+    float* pooled_it = pooled0 + it * pool_it;
     // ---- gradients reaching the states: score head on every step, regression head on the last
     const float* ds = dscore + (size_t)it * R;
     const float* dDYi = dDY + (size_t)it * R * T * 2;
@@ -1161,7 +1185,7 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
       const float* dxp_t = dXP + (size_t)t * 3 * H;
       // d fsp_t = dxp_t @ W[social rows]^T, through the ReLU
       float* dpre = dpre0 + (size_t)t * dpre_step;
-      float* pooled = pooled0 + (size_t)t * pooled_step;
+      float* pooled = pooled_it + (size_t)t * pooled_step;
       DESIRE_TRY(sgemm(dxp_t, T * 3 * H, wg_sp, 2 * H, true, nullptr, dpre, H, (int)R, H, 2 * H, DESIRE_ACT_NONE, false, st, pw));
       DESIRE_TRY(sgemm(dxp_t + 2 * H, T * 3 * H, wc_sp, H, true, nullptr, dpre, H, (int)R, H, H, DESIRE_ACT_NONE, true, st, pw));
       DESIRE_TRY(act_bwd_post(fsp + (size_t)t * H, T * H, dpre, H, (size_t)R, H, DESIRE_ACT_RELU, st));
@@ -1184,7 +1208,7 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
     DESIRE_TRY(gru_bptt(a, base + L.bptt, L.pack - L.bptt, st, &social_bwd));
     if (keep) {
       // social fc weights: ONE product over all T steps (pooled [T*R, G*H]^T @ dpre [T*R, H])
-      DESIRE_TRY(wgrad_tn(pooled0, G * H, dpre0, H, g->sp_w, H, (int)(R * T), G * H, H, st, wp));
+      DESIRE_TRY(wgrad_tn(pooled_it, G * H, dpre0, H, g->sp_w, H, (int)(R * T), G * H, H, st, wp));
       DESIRE_TRY(colsum_acc(dpre0, H, (int)(R * T), H, g->sp_b, st));
     }
     // ---- input rows of Decoder-2: static features, social feature, biases
@@ -1206,6 +1230,36 @@ extern "C" int desire_ioc_train(const desire_ioc_dims_t* d, const desire_ioc_t* 
     // scene features: scatter the gather's gradient into the feature-map gradient
     DESIRE_LAUNCH(st, (scene_gather_bwd_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(dX48 + Fv, F48, d->Hm, d->Wm, Cs, Yi, 2,
                                                                                         R * T, N * K * T, dfmap)));
+    return DESIRE_OK;
+  };
+
+  if (single) {
+    DESIRE_CUDA(cudaMemcpyAsync(snaps, Yhat, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
+    for (int it = 0; it < iters; ++it) {
+      const float* Yi = snaps + (size_t)it * R * T * 2;
+      float* Yn = snaps + (size_t)(it + 1) * R * T * 2;
+      DESIRE_TRY(forward_iter(it, Yi));
+      const float* hs2 = hs2_base + it * st_it;
+      DESIRE_LAUNCH(st, (score_states_kernel<<<blocks(R * 32, 256), 256, 0, st>>>(hs2, R, T, H, w->score_w, w->score_b,
+                                                                                  scores + (size_t)it * R)));
+      // regression refinement: Y_{it+1} = Y_it + h2_T @ reg_w + reg_b
+      DESIRE_CUDA(cudaMemcpyAsync(Yn, Yi, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
+      DESIRE_TRY(sgemm(hs2 + (size_t)(T - 1) * H, T * H, w->reg_w, 2 * T, false, w->reg_b, Yn, 2 * T, (int)R, 2 * T, H,
+                       DESIRE_ACT_NONE, true, st, pw));
+    }
+    DESIRE_CUDA(cudaMemcpyAsync(Y, snaps + (size_t)iters * R * T * 2, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    // phase A: the forward of every iteration (fast fused path) with snapshots of the trajectories
+    DESIRE_CUDA(cudaMemcpyAsync(Y, Yhat, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
+    DESIRE_TRY(ioc_fwd_impl(d, w, fmap, obs, Tp, Hx, ld_hx, fpool, Y, scores, base + L.fwd, ws_bytes - L.fwd, stream, snaps));
+  }
+  DESIRE_LAUNCH(st, (ioc_loss_kernel<<<blocks((long)M * 32, 256), 256, 0, st>>>(scores, snaps, target, obs, count, M, K, T, Tp,
+                                                                                iters, rows, dscore, dDY)));
+  DESIRE_LAUNCH(st, (ioc_cost_kernel<<<1, 1024, 0, st>>>(rows, obs, count, M, Tp, ioc_cost)));
+  for (int it = 0; it < iters; ++it) {
+    const float* Yi = snaps + (size_t)it * R * T * 2;
+    if (!single) DESIRE_TRY(forward_iter(it, Yi));          // phase B: recompute with every intermediate kept
+    DESIRE_TRY(backward_iter(it, Yi));
   }
   return DESIRE_OK;
 }

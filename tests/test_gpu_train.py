@@ -247,18 +247,24 @@ def test_ioc_backward_logpolar(H, N, K, B, missing):
     assert not bad, bad
 
 
-def test_ioc_backward_rebuild_pooled_path_agrees(monkeypatch):
-    """Large scenes rebuild each step's pooled tensor for the sp_w gradient instead of keeping all of them; force that
-    path and compare with the default one."""
+def test_ioc_backward_schedules_agree(monkeypatch):
+    """desire_ioc_train has three schedules, picked by what fits in memory: single forward pass with everything kept
+    (default at test sizes), fused forward + per-iteration recompute keeping every step's pooled tensor, and the same
+    with the pooled tensor rebuilt per step (large scenes).  All three must produce the same outputs and gradients."""
     cfg = small_cfg(d_dim=64, max_num_obj=12, num_samples=4, ioc_iters=2)
-    grads = []
-    for budget in (None, "0"):
-        if budget is not None:
-            monkeypatch.setenv("DESIRE_IOC_KEEP_POOLED_BYTES", budget)
+    res = []
+    for env in ({}, {"DESIRE_IOC_TWO_PHASE": "1"}, {"DESIRE_IOC_KEEP_POOLED_BYTES": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         tp, G = run_ioc_train(cfg, 3, 1)
-        grads.append(tp.grad_flat.cpu().numpy().copy())
-    monkeypatch.delenv("DESIRE_IOC_KEEP_POOLED_BYTES")
-    assert rel_l2(grads[1], grads[0]) <= 1e-5
+        res.append((tp.grad_flat.cpu().numpy().copy(), tp.buf["ioc_scores"].cpu().numpy().copy(),
+                    tp.buf["Y_refined"].cpu().numpy().copy(), float(tp.buf["ioc_cost"][0])))
+        for k in env:
+            monkeypatch.delenv(k)
+    for other in res[1:]:
+        assert rel_l2(other[0], res[0][0]) <= 1e-5
+        assert rel_l2(other[1], res[0][1]) <= 1e-5 and rel_l2(other[2], res[0][2]) <= 1e-5
+        assert abs(other[3] - res[0][3]) <= 1e-5 * abs(res[0][3])
 
 
 def test_full_train_step_with_ioc_reduces_both_costs():
