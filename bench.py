@@ -277,10 +277,12 @@ def ours_arm(a):
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     # ---- per-kernel CUDA-event timing: same steps, launched un-graphed so each tagged launch can be bracketed
     lib.desire_prof_enable(1)
+    hp.serial = True               # no parallel graph branches here: every tagged launch is timed alone
     for _ in range(steps):
         flush.zero_()
         hp.run(*dev_in)
     torch.cuda.synchronize()
+    hp.serial = False
     prof = {}
     for slot in range(16):
         n, ms = C.c_long(0), C.c_double(0)
@@ -381,8 +383,10 @@ def ours_arm(a):
                                            "l2": "flushed (256 MiB memset) before every timed step; timed with CUDA "
                                                  "events per step, max over ranks",
                                            "launch": "one CUDA-graph replay per step (%d kernels of the library inside); "
-                                                     "roofline kernels timed in a second, un-graphed pass of the same "
-                                                     "steps with per-launch CUDA events" % launches_per_step,
+                                                     "roofline kernels timed in a second, un-graphed and "
+                                                     "branch-free pass of the same steps with per-launch CUDA events "
+                                                     "(their sum exceeds ms_per_step: the graph overlaps them)"
+                                                     % launches_per_step,
                                            "wall_s_timed_region": t_wall}),
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

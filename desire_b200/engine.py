@@ -114,6 +114,7 @@ class HotPath:
         self.ws_enc_bytes = max(lib.desire_gru_encode_workspace_bytes(M, max(Tp, Tf), H), 256)
         self.ws_encx = torch.empty(self.ws_enc_bytes, dtype=torch.uint8, device=self.device)
         self.ws_ency = torch.empty(self.ws_enc_bytes, dtype=torch.uint8, device=self.device)
+        self.serial = False      # True: no parallel branches (bench.py's per-kernel timing pass needs launches that do not overlap)
         self.graph = None
         self.graph_gen = self.graph_rank = None
         self.static_in = None
@@ -153,7 +154,7 @@ class HotPath:
         if "scene" in stages:
             if tuple(scene.shape) != (self.B, cfg.scene_size, cfg.scene_size, 3) or not scene.is_contiguous():
                 raise ValueError("scene must be contiguous [B,%d,%d,3]" % (cfg.scene_size, cfg.scene_size))
-            fork = "generate" in stages            # overlap with the generation stage when both run in this call
+            fork = "generate" in stages and not self.serial   # overlap with the generation stage when both run in this call
             s_str = self.side if fork else cur
             if fork:
                 self.side.wait_stream(cur)
@@ -162,13 +163,16 @@ class HotPath:
                                         self.ws_scene_bytes, C.c_void_p(s_str.cuda_stream)), "scene_cnn")
         if "encode" in stages:
             ck(lib.desire_tconv_fwd(_p(obs), M, Tp, Cm, _p(P["temporal_w"]), _p(P["temporal_b"]), _p(b["rho_i"]), st), "tconv")
-            self.side2.wait_stream(cur)
+            s_y = cur if self.serial else self.side2
+            if not self.serial:
+                self.side2.wait_stream(cur)
             ck(lib.desire_gru_encode_ws_fwd(_p(tgt), M, Tf, H, C.byref(self.w_ency), C.c_void_p(b["HxHy"].data_ptr() + 4 * H),
                                             2 * H, _p(self.ws_ency), self.ws_enc_bytes,
-                                            C.c_void_p(self.side2.cuda_stream)), "gru_encode_y")
+                                            C.c_void_p(s_y.cuda_stream)), "gru_encode_y")
             ck(lib.desire_gru_encode_ws_fwd(_p(obs), M, Tp, H, C.byref(self.w_encx), _p(b["HxHy"]), 2 * H,
                                             _p(self.ws_encx), self.ws_enc_bytes, st), "gru_encode_x")
-            cur.wait_stream(self.side2)
+            if not self.serial:
+                cur.wait_stream(self.side2)
             ck(lib.desire_fc_fwd(_p(b["HxHy"]), 2 * H, _p(P["w_hidden_enc1"]), S2, _p(P["b_hidden_enc1"]),
                                  _p(b["vae_inputs"]), S2, M, S2, 2 * H, 1, 0, st), "fc_c")
             ck(lib.desire_cvae_encode_fwd(_p(b["vae_inputs"]), M, Zl, C.byref(self.w_venc), _p(b["mu_logvar"]), ws, wsb, st), "cvae_encode")
@@ -185,10 +189,10 @@ class HotPath:
             ck(lib.desire_recon_rows_fwd(_p(b["Yhat"]), _p(tgt), M, K, Tf, _p(b["recon_rows"]), st), "recon_rows")
             ck(lib.desire_masked_cost_fwd(_p(b["recon_rows"]), _p(b["kld_rows"]), _p(obs), M, Tp, _p(b["cost"]), st), "masked_cost")
         if "ioc" in stages:
-            if "scene" in stages and "generate" in stages:
+            if "scene" in stages and "generate" in stages and not self.serial:
                 cur.wait_stream(self.side)         # join the scene-CNN branch
             b["Y_refined"].copy_(b["Yhat"])
-            if self.ioc_chains == 1:
+            if self.ioc_chains == 1 or self.serial:
                 ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs), Tp,
                                       _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["Y_refined"]), _p(b["ioc_scores"]),
                                       ws, wsb, st), "ioc")

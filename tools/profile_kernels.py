@@ -25,12 +25,14 @@ def main():
     ap.add_argument("--agents", type=int, default=60)
     ap.add_argument("--samples", type=int, default=20)
     ap.add_argument("--ioc-iters", type=int, default=1)
+    ap.add_argument("--serial", action="store_true", help="no parallel branches / IOC chains (full-size launches)")
     ap.add_argument("--pred-length", type=int, default=12)
     ap.add_argument("--scene-size", type=int, default=256)
     a = ap.parse_args()
     cfg = DesireConfig(d_dim=a.hidden, max_num_obj=a.agents, num_samples=a.samples, ioc_iters=a.ioc_iters,
                        pred_length=a.pred_length, scene_size=a.scene_size)
     hp = HotPath(cfg, init_params(cfg, 1), a.scenes)
+    hp.serial = a.serial
     inp = [t.cuda() for t in make_batch(cfg, a.scenes, 100)]
     for _ in range(a.passes):
         hp.run(*inp)
