@@ -202,6 +202,9 @@ struct PackedW {
 int pack_weight(PackedW& w, void* ws, size_t ws_bytes, cudaStream_t st);
 int gemm_packed(const float* A, int lda, const PackedW& w, const float* bias, float* C, int ldc, int M, int act,
                 bool accumulate, cudaStream_t st);
+// C = [A1 | A2] @ W + bias (K1 columns from A1, the rest from A2) on the tensor-core path; false = not eligible
+bool gemm_packed_dual(const float* A1, int lda1, int K1, const float* A2, int lda2, const PackedW& w, const float* bias,
+                      float* C, int ldc, int M, int act, cudaStream_t st, int* rc);
 // fully fused social pooling + fc on tensor cores (social_tc.cu): fsp = relu(pool(h) @ sp_w + b)
 struct SocialFcArgs {
   const float* pos;      // position of row r at pos + r*pos_stride (x,y)

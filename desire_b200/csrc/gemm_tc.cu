@@ -57,6 +57,35 @@ struct DenseA8 {
   }
 };
 
+// A = [A1 | A2] column-wise (two row-major sources, K1 a multiple of 8): lets the Decoder-2 input projection read
+// feature_pooling in place instead of from a copy inside a concatenated feature matrix
+struct DualDenseA8 {
+  const float *A1, *A2;
+  int lda1, lda2, K1, M, K;
+  const float *r1, *r2;
+  __device__ __forceinline__ void init(int m) {
+    r1 = m < M ? A1 + (size_t)m * lda1 : nullptr;
+    r2 = m < M ? A2 + (size_t)m * lda2 - K1 : nullptr;      // indexed with the global k
+  }
+  __device__ __forceinline__ void load_stage(int ks, float (*v)[8]) const {
+    const int k0 = ks * BK;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+      const int k = k0 + c * 8;
+      const float* src = k < K1 ? r1 : r2;                   // a chunk of 8 never straddles K1
+      if (r1 && k + 8 <= K) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src + k) + 1);
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+        v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] = (r1 && k + i < K) ? __ldg(src + k + i) : 0.f;
+      }
+    }
+  }
+};
+
 struct Im2colA8 {
   const float* X;
   Im2col g;
@@ -548,6 +577,19 @@ int gemm_packed(const float* A, int lda, const PackedW& w, const float* bias, fl
     return run_tc(a, w.packed, bias, C, ldc, M, w.N, w.K, act, accumulate, st);
   }
   return sgemm(A, lda, w.W, w.ldw, w.trans, bias, C, ldc, M, w.N, w.K, act, accumulate, st);
+}
+
+// C = [A1 | A2] @ W + bias with W already packed (K = K1 + K2).  Requirements: tensor-core path available, K1 % 8 == 0,
+// lda1/lda2 % 4 == 0 and 16-byte aligned sources (returns false otherwise and the caller concatenates).
+bool gemm_packed_dual(const float* A1, int lda1, int K1, const float* A2, int lda2, const PackedW& w, const float* bias,
+                      float* C, int ldc, int M, int act, cudaStream_t st, int* rc) {
+  const bool ok = w.packed && g_gemm_mode != 0 && M >= 64 && (M + TM - 1) / TM <= 65535 && K1 % 8 == 0 && lda1 % 4 == 0 &&
+                  lda2 % 4 == 0 && (w.K - K1) % 4 == 0 && ((reinterpret_cast<uintptr_t>(A1) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(A2) & 15) == 0) && K1 > 0 && K1 < w.K;
+  if (!ok) return false;
+  DualDenseA8 a{A1, A2, lda1, lda2, K1, M, w.K, nullptr, nullptr};
+  *rc = run_tc(a, w.packed, bias, C, ldc, M, w.N, w.K, act, false, st);
+  return true;
 }
 
 int gemm_tc_im2col(const float* X, const Im2col& g, const float* W, int ldw, const float* bias, float* C, int ldc, int M,

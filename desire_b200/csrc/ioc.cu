@@ -663,25 +663,43 @@ static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const
   sfa.packed = pw_sp.packed; sfa.bias = w->sp_b; sfa.out = fsp;
   const bool fused_pool = social_fc_tc_eligible(sfa);
 
-  // feature_pooling columns of the static input are iteration-invariant
-  copy_cols_kernel<<<blocks(R * T * C2, 256), 256, 0, st>>>(fpool, C2, R * T, Xs + Fv + Cs, Dst);
-  DESIRE_LAUNCH_CHECK();
+  // The static input is [velocity fc | scene gather | feature_pooling].  On the tensor-core path the GEMM reads the
+  // feature_pooling columns in place (two-source A loader) and Xs only holds the first Fv+Cs columns (row stride F48);
+  // otherwise feature_pooling is copied once into a concatenated [.., Dst] matrix (it is iteration-invariant).
+  const int F48 = Fv + Cs;
+  int xs_ld = Dst;
+  {
+    int rc_probe = 0;
+    (void)rc_probe;
+    const bool dual = pw_st.packed && gemm_mode() != 0 && F48 % 8 == 0 && C2 % 4 == 0 && R * T >= 64 &&
+                      (R * T + 127) / 128 <= 65535 && ((reinterpret_cast<uintptr_t>(fpool) & 15) == 0);
+    if (dual) xs_ld = F48;
+  }
+  if (xs_ld == Dst) {
+    copy_cols_kernel<<<blocks(R * T * C2, 256), 256, 0, st>>>(fpool, C2, R * T, Xs + Fv + Cs, Dst);
+    DESIRE_LAUNCH_CHECK();
+  }
 
   for (int it = 0; it < d->iters; ++it) {
     float* score = scores + (size_t)it * R;
     if (snaps)
       DESIRE_CUDA(cudaMemcpyAsync(snaps + (size_t)it * R * T * 2, Y, (size_t)R * T * 2 * f4, cudaMemcpyDeviceToDevice, st));
-    vel_fc_kernel<<<blocks(R * T * Fv, 256), 256, 0, st>>>(Y, obs, Tp, R, K, T, Fv, w->vel_w, w->vel_b, Xs, Dst);
+    vel_fc_kernel<<<blocks(R * T * Fv, 256), 256, 0, st>>>(Y, obs, Tp, R, K, T, Fv, w->vel_w, w->vel_b, Xs, xs_ld);
     DESIRE_LAUNCH_CHECK();
     {
       ProfScope ps_(DESIRE_PROF_GATHER, st);
       DESIRE_LAUNCH(st, (scene_gather_kernel<<<blocks(R * T * 32, 256), 256, 0, st>>>(fmap, d->Hm, d->Wm, Cs, Y, 2, R * T,
-                                                                                      d->N * K * T, Xs + Fv, Dst)));
+                                                                                      d->N * K * T, Xs + Fv, xs_ld)));
     }
     {
       // hoisted input projection of the static features for all T steps: XP[(r,t), r|u|c]
       ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
-      DESIRE_TRY(gemm_packed(Xs, Dst, pw_st, bst3, XP, 3 * H, (int)(R * T), DESIRE_ACT_NONE, false, st));
+      int rc2 = DESIRE_OK;
+      if (xs_ld == Dst || !gemm_packed_dual(Xs, F48, F48, fpool, C2, pw_st, bst3, XP, 3 * H, (int)(R * T), DESIRE_ACT_NONE, st, &rc2)) {
+        DESIRE_CHECK_ARG(xs_ld == Dst, "ioc: two-source projection became ineligible");
+        DESIRE_TRY(gemm_packed(Xs, Dst, pw_st, bst3, XP, 3 * H, (int)(R * T), DESIRE_ACT_NONE, false, st));
+      }
+      DESIRE_TRY(rc2);
     }
     expand_rows_kernel<<<blocks(R * H, 256), 256, 0, st>>>(Hx, ld_hx, K, H, R, h2);
     DESIRE_LAUNCH_CHECK();
