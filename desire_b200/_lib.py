@@ -129,6 +129,8 @@ SIGNATURES = {
     "desire_scene_cnn_bwd": (I, [P, I, I, I, I, C.POINTER(SceneCnnW), P, C.POINTER(SceneCnnG), P, Z, P]),
     "desire_wgrad_workspace_bytes": (Z, [I, I]),
     "desire_wgrad_tn": (I, [P, I, P, I, P, I, I, I, I, P, Z, P]),
+    "desire_deconv2d_workspace_bytes": (Z, [I, I, I, I, I, I, I]),
+    "desire_deconv2d_fwd": (I, [P, I, I, I, P, I, I, I, I, P, P, P, I, P, P, Z, P]),
     "desire_sumsq_fwd": (I, [P, L, P, I, P]),
     "desire_adam_step": (I, [P, P, P, P, L, P, F, F, F, F, I, F, F, P]),
 }

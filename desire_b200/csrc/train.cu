@@ -904,3 +904,53 @@ extern "C" int desire_wgrad_tn(const float* A, int lda, const float* dC, int ldd
                    "desire_wgrad_tn: bad arguments");
   return wgrad_tn(A, lda, dC, lddc, dW, lddw, M, K, N, (cudaStream_t)stream, PackWs{ws, ws_bytes});
 }
+
+// ---- generic transposed convolution (un-fused): the operator behind utils/convolutional_vae_util.py:deconv2d for
+// arbitrary square geometries (the CVAE decoder's four layers have their own fused kernels in cvae.cu/deconv_tc.cu).
+//   y = act( [BN_row]( conv2d_transpose(x, w) + bias ) ),  x [R,Hin,Hin,Cin] NHWC, w [k,k,Cout,Cin], y [R,Hout,Hout,Cout]
+namespace {
+__global__ void act_inplace_kernel(float* __restrict__ y, size_t n, int act) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = act_apply(y[i], act);
+}
+int deconv_out_size(int in, int k, int s, int same) { return same ? in * s : (in - 1) * s + k; }
+}  // namespace
+
+extern "C" size_t desire_deconv2d_workspace_bytes(int R, int Hin, int Cin, int k, int stride, int same, int Cout) {
+  (void)Cin;
+  const size_t Hout = deconv_out_size(Hin, k, stride, same);
+  return align_up((size_t)R * Hin * Hin * k * k * Cout * 4) + align_up((size_t)R * Hout * Hout * Cout * 4) + PACK_WS_BYTES;
+}
+
+extern "C" int desire_deconv2d_fwd(const float* x, int R, int Hin, int Cin, const float* w, int k, int stride, int same,
+                                   int Cout, const float* bias, const float* gamma, const float* beta, int act, float* y,
+                                   void* ws, size_t ws_bytes, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(x && w && y && R >= 0 && Hin > 0 && Cin > 0 && k > 0 && stride > 0 && Cout > 0,
+                   "desire_deconv2d_fwd: bad arguments");
+  DESIRE_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "desire_deconv2d_fwd: batch-norm needs both gamma and beta");
+  if (!ws || ws_bytes < desire_deconv2d_workspace_bytes(R, Hin, Cin, k, stride, same, Cout)) {
+    set_error("desire_deconv2d_fwd: workspace too small");
+    return DESIRE_ERR_WORKSPACE;
+  }
+  if (R == 0) return DESIRE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Hout = deconv_out_size(Hin, k, stride, same);
+  const int full = (Hin - 1) * stride + k;
+  const int pad = same ? (full - Hout > 0 ? (full - Hout) / 2 : 0) : 0;      // TF: conv_transpose is the gradient of a conv
+  Workspace W(ws, ws_bytes);                                                  // whose SAME padding puts total//2 before
+  float* col = W.take<float>((size_t)R * Hin * Hin * k * k * Cout);
+  float* ypre = W.take<float>((size_t)R * Hout * Hout * Cout);
+  PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
+  const long rows = (long)R * Hin * Hin;
+  DESIRE_CHECK_ARG(rows < (1L << 31), "desire_deconv2d_fwd: too many input positions");
+  DESIRE_TRY(sgemm(x, Cin, w, Cin, true, nullptr, col, k * k * Cout, (int)rows, k * k * Cout, Cin, DESIRE_ACT_NONE, false, st, pw));
+  if (gamma) {
+    DESIRE_TRY(col2im_gather(col, R, Hin, Hout, k, stride, pad, Cout, bias, ypre, st));
+    DESIRE_TRY(bn_row_fwd(ypre, R, Hout * Hout, Cout, gamma, beta, act, y, st));
+  } else {
+    DESIRE_TRY(col2im_gather(col, R, Hin, Hout, k, stride, pad, Cout, bias, y, st));
+    const size_t n = (size_t)R * Hout * Hout * Cout;
+    if (act != DESIRE_ACT_NONE) DESIRE_LAUNCH(st, (act_inplace_kernel<<<grid1d(n), 256, 0, st>>>(y, n, act)));
+  }
+  return DESIRE_OK;
+}

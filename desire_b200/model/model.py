@@ -79,6 +79,45 @@ class DESIREModel(object):
         `batch_size` scenes and loads the kernel library (raises if it is missing)."""
         self._path(max(int(self.batch_size), 1))
 
+    def vae_encoder(self, inputs, latent_size=None, activ=None, phase=None):
+        """model/model.py:471-492: inputs [M, 1024] (the fc_c features viewed as 32x32x1) -> (mean [M,Z], logvar [M,Z]).
+        `activ` / `phase` are accepted for signature parity (ELU and train-phase statistics are what the reference
+        passes and what the kernels implement)."""
+        import ctypes as C
+        from .. import _lib
+        x = inputs.to(self.device, torch.float32).contiguous().reshape(-1, self.vae_input_size)
+        Zl = int(latent_size or self.cfg.Z)
+        if Zl != self.cfg.Z:
+            raise ValueError("vae_encoder: latent_size %d does not match the model's %d" % (Zl, self.cfg.Z))
+        M = x.shape[0]
+        hp = self._path(max(int(self.batch_size), 1))
+        lib = hp.lib
+        out = torch.empty(M, 2 * Zl, dtype=torch.float32, device=self.device)
+        wsb = lib.desire_cvae_encode_workspace_bytes(M, Zl)
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=self.device)
+        _lib.check(lib.desire_cvae_encode_fwd(C.c_void_p(x.data_ptr()), M, Zl, C.byref(hp.w_venc), C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(ws.data_ptr()), wsb,
+                                              C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "vae_encoder")
+        return out[:, :Zl], out[:, Zl:]
+
+    def vae_decoder(self, zval, projection_size=None, activ=None, phase=None):
+        """model/model.py:453-469: zval [R, Z] -> x_reconstr_mean [R, 1024] (32x32x1 flattened, sigmoid)."""
+        import ctypes as C
+        from .. import _lib
+        z = zval.to(self.device, torch.float32).contiguous().reshape(-1, self.cfg.Z)
+        if projection_size is not None and int(projection_size) != self.vae_input_size:
+            raise ValueError("vae_decoder: the decoder always emits %d values (model.py:465-468)" % self.vae_input_size)
+        R = z.shape[0]
+        hp = self._path(max(int(self.batch_size), 1))
+        lib = hp.lib
+        out = torch.empty(R, self.vae_input_size, dtype=torch.float32, device=self.device)
+        wsb = lib.desire_cvae_decode_workspace_bytes(R, self.cfg.Z)
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=self.device)
+        _lib.check(lib.desire_cvae_decode_fwd(C.c_void_p(z.data_ptr()), R, self.cfg.Z, C.byref(hp.w_vdec),
+                                              C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), wsb,
+                                              C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "vae_decoder")
+        return out
+
     def get_name(self):
         """model/model.py:405-412."""
         return "cvae_input_%dx%d_latent%d_edim%d_ddim%d" % (

@@ -315,6 +315,16 @@ size_t desire_wgrad_workspace_bytes(int M, int N);
 int desire_wgrad_tn(const float* A, int lda, const float* dC, int lddc, float* dW, int lddw, int M, int N, int K,
                     void* ws, size_t ws_bytes, desire_stream_t stream);
 
+/* generic transposed convolution, the operator of utils/convolutional_vae_util.py:31-135 (deconv2d: conv2d_transpose ->
+ * +bias -> batch-normalise -> activation) for any square geometry; the CVAE decoder's own four layers run through the
+ * fused kernels of desire_cvae_decode_fwd.  x [R,Hin,Hin,Cin] NHWC; w [k,k,Cout,Cin] (:83); same != 0: SAME (output
+ * Hin*stride, :165-167) else VALID ((Hin-1)*stride+k, :161-163); bias / gamma+beta may be NULL (no bias / no BN; BN is the
+ * per-row statistics of DESIGN.md D5 and needs Cout dividing 256); y [R,Hout,Hout,Cout]. */
+size_t desire_deconv2d_workspace_bytes(int R, int Hin, int Cin, int k, int stride, int same, int Cout);
+int desire_deconv2d_fwd(const float* x, int R, int Hin, int Cin, const float* w, int k, int stride, int same, int Cout,
+                        const float* bias, const float* gamma, const float* beta, int act, float* y, void* ws,
+                        size_t ws_bytes, desire_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
