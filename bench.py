@@ -364,6 +364,12 @@ def ours_arm(a):
         roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
                     "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "peak_source": pk["src"],
                     "share_of_step": top["share_of_step"]}
+    # second half of BASELINE's metric ("GRU tensor-pipe %"): ncu-measured, so it comes from the committed captures
+    tensor_pipe = None
+    tp_path = os.path.join(ROOT, "profiles", "tensor_pipe.json")
+    if os.path.exists(tp_path):
+        tensor_pipe = {k: v for k, v in json.load(open(tp_path)).items() if not k.startswith("_")}
+        tensor_pipe["source"] = "profiles/tensor_pipe.json (ncu --set full captures, sm__pipe_tensor_cycles_active)"
     if a.breakdown:
         os.makedirs(os.path.dirname(os.path.abspath(a.breakdown)), exist_ok=True)
         json.dump({"ms_per_step": dev_ms / steps, "kernels": rows}, open(a.breakdown, "w"), indent=1)
@@ -395,6 +401,7 @@ def ours_arm(a):
         "kernels": rows[:8],
         "cpu_baseline": cpu,
         "train_step": train,
+        "gru_tensor_pipe_pct": tensor_pipe,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
