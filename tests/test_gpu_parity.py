@@ -23,7 +23,7 @@ IOC = ["ioc_scores", "Y_refined"]
 ONE_BIN = dict(n_rad=1, n_ang=1, r_min=1e-6, r_max=1e3)
 
 SHAPES = [(48, 8, 1, 2, 0), (48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (16, 5, 2, 1, 0), (64, 10, 5, 2, 1), (256, 6, 6, 2, 0),
-          (32, 40, 2, 2, 0)]
+          (32, 40, 2, 2, 0), (16, 1, 1, 1, 0), (32, 3, 1, 5, 2)]
 
 
 def run_gpu(cfg, B, seed=0, n_missing=0):

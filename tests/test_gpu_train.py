@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 GTOL = 2e-3
 
 SHAPES = [(48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (16, 5, 2, 1, 0), (64, 10, 5, 2, 1), (32, 40, 2, 2, 0),
-          (16, 5, 2, 2, 5)]      # last: every agent of the odd scene is non-existent (an empty scene in the minibatch)
+          (16, 5, 2, 2, 5),      # every agent of the odd scene is non-existent (an empty scene in the minibatch)
+          (16, 1, 1, 1, 0)]      # degenerate: one scene, one agent, one sample
 ACT = {"dYhat": "Yhat", "dx_z": "x_z", "dxr": "x_reconstr_mean", "dz": "zval", "dv": "vae_inputs"}
 
 
@@ -220,7 +221,7 @@ def compare_ioc(tp, G, out, ref_g, tol):
 
 
 @pytest.mark.parametrize("H,N,K,B,missing,iters", [(48, 8, 3, 2, 3, 2), (128, 12, 4, 3, 2, 2), (16, 5, 2, 1, 0, 1),
-                                                   (64, 10, 5, 2, 1, 3), (16, 5, 2, 2, 5, 2)])
+                                                   (64, 10, 5, 2, 1, 3), (16, 5, 2, 2, 5, 2), (16, 1, 1, 1, 0, 2)])
 def test_ioc_backward_single_bin_strict(H, N, K, B, missing, iters):
     """One social bin (no bin edges, everything smooth): strict comparison against float64 autograd of the twin fed
     with the float64 oracle's stage-1 outputs."""
