@@ -6,9 +6,11 @@
 //
 // Design (v2, after the ncu capture of v1 showed 12 % tensor-pipe: serial phases, epilogues stalled on
 // dependent global loads):
-//   * one CTA owns NT (=2 for H<=128) independent 128-row tiles for all T steps and ONE MMA warp serves both:
+//   * one CTA owns NT independent 128-row tiles for all T steps and ONE MMA warp serves them:
 //     gates(0) gates(1) cand(0) cand(1) ...  While a tile's epilogue warps work, the tensor core runs the
-//     other tile's MMAs (ping-pong inside the CTA; TMEM = NT * 2H columns).
+//     other tile's MMAs (ping-pong inside the CTA; TMEM = NT * 2H columns).  The kernel supports NT = 2 for H <= 128,
+//     but shape_of() ships NT = 1: at the bench workload 150 two-tile CTAs still need two rounds of the 148 SMs and
+//     measured no faster than 300 one-tile CTAs ("Measured and not kept").
 //   * the hoisted input projection xp is never added in an epilogue: it is PRE-LOADED into the TMEM accumulator
 //     with tcgen05.st (xp_r|xp_u by the previous step's epilogue right after it consumed those columns, xp_c by
 //     the gate epilogue right after it consumed r) and every MMA accumulates on top of it.  The epilogues'
