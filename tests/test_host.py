@@ -63,3 +63,27 @@ def test_model_fails_loudly_without_cuda():
     from desire_b200.model.model import DESIREModel
     with pytest.raises((DesireError, RuntimeError, AssertionError)):
         DESIREModel(small_cfg(), device="cpu")
+
+
+def test_flatten_params_views_alias_one_aligned_flat_buffer():
+    """Train-step host logic: every parameter is a view into ONE flat buffer (256-byte aligned starts, zero padding), so
+    clip / Adam / the gradient all-reduce can work on the flat tensor."""
+    import torch
+    from desire_b200.config import init_params
+    from desire_b200.engine import FLAT_ALIGN, flatten_params
+    from helpers import small_cfg
+    cfg = small_cfg(d_dim=16, max_num_obj=4, num_samples=2)
+    P = init_params(cfg, 1)
+    flat, views, offs = flatten_params(P, "cpu")
+    assert set(views) == set(P) and flat.dtype == torch.float32
+    used = torch.zeros_like(flat, dtype=torch.bool)
+    for k, (o, cnt, shp) in offs.items():
+        assert o % FLAT_ALIGN == 0 and cnt == P[k].numel() and tuple(views[k].shape) == tuple(P[k].shape)
+        assert torch.equal(views[k], P[k])
+        assert views[k].data_ptr() == flat.data_ptr() + 4 * o          # a view, not a copy
+        assert not used[o:o + cnt].any()
+        used[o:o + cnt] = True
+    assert float(flat[~used].abs().sum()) == 0.0                        # padding stays zero
+    views["output_b"].add_(1.0)                                         # writes go through to the flat buffer
+    o, cnt, _ = offs["output_b"]
+    assert torch.equal(flat[o:o + cnt], views["output_b"].reshape(-1))
