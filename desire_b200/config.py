@@ -22,6 +22,8 @@ class DesireConfig:
     seq_length: int = 8            # T_p
     max_num_obj: int = 60          # N
     stride: int = 1
+    num_layers: int = 1            # train.py:32; MultiRNNCell depth (model.py:137-141) — only 1 is built
+    model: str = "gru"             # train.py:34 "rnn, gru, or lstm" — the reference graph only ever builds GRUCells
     # added knobs
     pred_length: int = 12          # T_f   (D2)
     num_samples: int = 20          # K     (D1)
@@ -65,6 +67,16 @@ class DesireConfig:
             # the CVAE decoder always emits 32x32 (model.py:465-468 + convolutional_vae_util.py:154-157),
             # so w_post_vae [S*S, H] (model.py:440-441) only type-checks at S == 32 (D5)
             raise ValueError("rnn_size must give S = int(sqrt(2*rnn_size)) == 32 (got %d)" % self.S)
+        # flags the reference accepts and this build does not implement must not be dropped silently
+        if self.stride != 1:
+            raise ValueError("stride=%d: only the reference default stride=1 of the temporal convolution is built "
+                             "(model.py:48,130)" % self.stride)
+        if self.num_layers != 1:
+            raise ValueError("num_layers=%d: only single-layer GRUs are built (MultiRNNCell of model.py:137-141 with "
+                             "the default num_layers=1)" % self.num_layers)
+        if str(self.model).lower() != "gru":
+            raise ValueError("model=%r: the path is built for GRU cells only (the reference graph constructs "
+                             "rnn.GRUCell regardless of this flag, model.py:137,144)" % (self.model,))
         if self.d_dim % 4:
             raise ValueError("d_dim must be a multiple of 4")
         if self.latent_size % 4:

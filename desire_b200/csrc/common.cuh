@@ -258,6 +258,13 @@ size_t gru_tc_pack_bytes(int H, int Ka = 0);
 bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes);
 int gru_seq_tc(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
 
+// third design of the tcgen05 recurrence (gru_tc3.cu): register-resident state, TMA-staged xp, phases overlapped with
+// the MMA groups; H in {128, 256}, no extra operand.  Weights packed with n-tile = H.
+size_t gru_tc3_pack_bytes(int H);
+int gru_tc3_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st);
+bool gru_tc3_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes);
+int gru_seq_tc3(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
+
 // fused transposed conv + bias + per-row BN + activation on tcgen05 (deconv_tc.cu)
 size_t deconv_tc_pack_bytes(int Cin, int Cout, int ks);
 bool deconv_tc_eligible(int R, int Hin, int Hout, int Cin, int Cout, int ks, int stride, const void* pack_ws,

@@ -1,0 +1,519 @@
+// Persistent tcgen05 GRU recurrence, third design (TF-1.x GRUCell, reference model/model.py:137-148,279-285):
+//
+//   r = sigmoid(xp_r + h @ Wr)     u = sigmoid(xp_u + h @ Wu)     c = tanh(xp_c + (r*h) @ Wc)     h' = u*h + (1-u)*c
+//
+// What the ncu capture of the second design showed (profiles/r1i_ncu_summaries.txt: tensor pipe 12-19 %, 69 % of the
+// warp stalls on the long scoreboard): the epilogue threads own one row each (that is how tcgen05.ld hands out the
+// accumulator), so every global load/store of theirs touched 32 different 128-byte lines — 30 sectors per request —
+// and with the shared-memory carve-out at its maximum there is no L1 left to catch the re-use; h_{t-1} was re-read
+// from global memory twice per step; the four phases of a step ran strictly one after the other.  This design:
+//
+//   * state in registers: a thread keeps the FP32 h of its (row, HC columns) for the whole kernel;
+//   * the hoisted input projection xp arrives by TMA: 2-D tensor-map copies (cp.async.bulk.tensor, SASS UTMALDG) of
+//     [128 rows x 32 columns] boxes with the 128-byte swizzle into a small ring, issued by a loader thread that runs
+//     ahead of the epilogues; a thread reads its row's 128 bytes as eight conflict-free 16-byte loads;
+//   * a step is three MMA groups — r columns, u columns, candidate — and three epilogue phases that each run in the
+//     shadow of the next MMA group:
+//         MMA     | r(t)        | u(t)              | cand(t)             | (idle)        | r(t+1) ...
+//         SIMT    |  E2b(t-1)   | E1: r, r*h -> A   | E2a: u -> TMEM      | E2b: c, h'    |
+//     E1 overwrites the A operand chunk by chunk behind the u-group (a_free[kc] is committed after the u-group's MMAs
+//     on K chunk kc), E2a parks sigmoid(u) in the u columns of TMEM, and only E2b (tanh + blend) is exposed;
+//   * with H = 128 the candidate has its own TMEM columns, so the next step's r-group starts on the K chunks of h'
+//     as they are produced (h_ready[kc]); with H = 256 the gates fill all 512 columns, the candidate re-uses the r
+//     columns and the r-group waits for the whole tile;
+//   * recurrent weights: the packed BF16 hi/lo images of gru_tc_pack (n-tile = H) streamed through a ring of 16 KB
+//     slots by 1-D bulk copies with an evict-last L2 hint.
+//
+// 3xBF16 (A_hi B_hi + A_lo B_hi + A_hi B_lo, FP32 accumulation in TMEM) as everywhere else in the library.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace desire {
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128;
+constexpr int XBOX_BYTES = TM * 32 * 4;   // one xp box: 128 rows x 32 FP32 columns, 128-byte rows
+constexpr int EPI_WARPS = 16;             // 4 TMEM lane quadrants x 4 column groups
+constexpr int NTHR3 = (EPI_WARPS + 4) * 32;   // + one warpgroup: MMA issuer, loader, two idle warps (setmaxnreg is per warpgroup)
+
+template <int H>
+struct Cfg3 {
+  static constexpr int HC = H / 4;                     // columns per epilogue thread
+  static constexpr int NB = HC / 32;                   // 32-column chunks (= xp boxes per gate) per thread
+  static constexpr int NKC = H / 32;                   // K chunks of the A operand
+  static constexpr int KSLOT = (H >= 256) ? 16 : 32;   // K extent of one weight slot
+  static constexpr int SPC = 32 / KSLOT;               // slots per K chunk
+  static constexpr int SLOT_HALF = (KSLOT / 8) * H * 16;
+  static constexpr int SLOT_BYTES = 2 * SLOT_HALF;     // hi + lo: 16 KB for both sizes
+  static constexpr int BLOCK_BYTES = 2 * 4 * H * 16;   // one packed (n-tile, 32-wide K) block of tc_pack_b
+  static constexpr int NSW = (H >= 256) ? 4 : 6;       // weight ring slots
+  static constexpr int NXB = (H >= 256) ? 2 : 4;       // xp ring boxes
+  static constexpr int A_HALF = (H / 8) * 2048;        // [H/8 chunks][128 rows][16 B]
+  static constexpr bool ALIAS = (3 * H > 512);         // candidate accumulates in the consumed r columns
+  static constexpr int CAND_COL = ALIAS ? 0 : 2 * H;
+  static constexpr int BPS = 3 * NKC;                  // xp boxes per step: r | u | c, each in (chunk-in-thread, column group) order
+  static constexpr int WPS = 3 * NKC * SPC;            // weight slots per step
+  static constexpr int NBAR = 2 * NSW + 2 * NXB + 4 + 2 * NKC;
+  static constexpr size_t SMEM = 1024 + 2 * (size_t)A_HALF + (size_t)NSW * SLOT_BYTES + (size_t)NXB * XBOX_BYTES + NBAR * 8 + 16;
+};
+
+struct Gru3Args {
+  int R, T;
+  int xp_step;          // column offset of step t inside an xp row = t * xp_step
+  const float* h0;
+  int h0_div, ld_h0;
+  float* hs;
+  long hs_row_stride, hs_step_stride;
+  float* h_final;
+  int ld_hf;
+  const uint8_t* wg;    // packed gates, n-tile H: [2][H/32] blocks (r columns, then u columns)
+  const uint8_t* wc;    // packed candidate: [H/32] blocks
+  int passes;
+  int xp_const;         // 1: the same xp every step (Decoder-1) -> keep it in L2
+  int dbg;              // timing experiments only (DESIRE_GRU3_DBG): 1 = no xp copies, 2 = no weight copies (results are wrong)
+};
+
+__device__ __forceinline__ float4 lds128(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+
+// Wait for fill number `phase` (0-based) of an xp ring slot.  The fills of one slot are consumed by up to two column
+// groups in alternation, so a group can reach its wait while the slot is still one fill short of the one before its
+// own — and a parity wait cannot tell fill p-1 pending from fill p+1 pending.  Waiting for fill p-1 first (it is this
+// group's predecessor in the slot, or already long complete) removes the ambiguity.
+__device__ __forceinline__ void xbox_wait(uint64_t* bar, uint32_t phase) {
+  mbar_wait(bar, (phase & 1) ^ 1);
+  mbar_wait(bar, phase & 1);
+}
+
+template <int H>
+__global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant__ CUtensorMap tm_xp, Gru3Args a) {
+  using C = Cfg3<H>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzled boxes need 1024-byte alignment
+  uint8_t* xring = smem;                                             // [NXB] boxes, each 1024-aligned
+  uint8_t* a_hi = xring + (size_t)C::NXB * XBOX_BYTES;
+  uint8_t* a_lo = a_hi + C::A_HALF;
+  uint8_t* wring = a_lo + C::A_HALF;
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + (size_t)C::NSW * C::SLOT_BYTES);
+  uint64_t* wempty = wfull + C::NSW;
+  uint64_t* xfull = wempty + C::NSW;
+  uint64_t* xempty = xfull + C::NXB;
+  uint64_t* g_r_done = xempty + C::NXB;
+  uint64_t* g_u_done = g_r_done + 1;
+  uint64_t* c_done = g_u_done + 1;
+  uint64_t* rh_ready = c_done + 1;
+  uint64_t* h_ready = rh_ready + 1;       // [NKC]
+  uint64_t* a_free = h_ready + C::NKC;    // [NKC]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(a_free + C::NKC);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long row0 = (long)blockIdx.x * TM;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::NSW; ++s) {
+      mbar_init(&wfull[s], 1);
+      mbar_init(&wempty[s], 1);
+    }
+    for (int s = 0; s < C::NXB; ++s) {
+      mbar_init(&xfull[s], 1);
+      mbar_init(&xempty[s], 4);           // the four quadrant warps of the column group that reads the box
+    }
+    mbar_init(g_r_done, 1);
+    mbar_init(g_u_done, 1);
+    mbar_init(c_done, 1);
+    mbar_init(rh_ready, EPI_WARPS);
+    for (int k = 0; k < C::NKC; ++k) {
+      mbar_init(&h_ready[k], 4);
+      mbar_init(&a_free[k], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS) tmem_alloc<512>(tslot);
+  if (warp == EPI_WARPS + 1 && lane == 0) tma_prefetch_desc(&tm_xp);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  // 640 threads launch with 96 registers each; the last warpgroup (two single-thread roles) gives most of its share
+  // back so the epilogue threads can hold 64 FP32 state values next to a 16-column working set
+  if (warp < EPI_WARPS) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ======================================================================== epilogue warps
+    const int q = warp & 3, cs = warp >> 2;          // TMEM lane quadrant (must equal warp % 4), column group
+    const int rloc = q * 32 + lane;                  // TMEM lane == row of the tile
+    const long row = row0 + rloc;
+    const bool ok = row < a.R;
+    const int cbeg = cs * C::HC;                     // this thread's columns [cbeg, cbeg + HC)
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    uint8_t* my_hi = a_hi + rloc * 16;
+    uint8_t* my_lo = a_lo + rloc * 16;
+    float h[C::HC];
+
+    // ---- initial state: registers + A operand
+    {
+      const float* h0r = (a.h0 && ok) ? a.h0 + (row / a.h0_div) * (long)a.ld_h0 + cbeg : nullptr;
+#pragma unroll
+      for (int c = 0; c < C::HC; c += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h0r) v = __ldg(reinterpret_cast<const float4*>(h0r + c));
+        h[c] = v.x; h[c + 1] = v.y; h[c + 2] = v.z; h[c + 3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < C::NB; ++j) {
+        const int kc = cs * C::NB + j;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const Split8 s = split8(&h[j * 32 + g8 * 8]);
+          *reinterpret_cast<uint4*>(my_hi + (kc * 4 + g8) * 2048) = s.hi;
+          *reinterpret_cast<uint4*>(my_lo + (kc * 4 + g8) * 2048) = s.lo;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_ready[kc]);
+      }
+    }
+
+    for (int t = 0; t < a.T; ++t) {
+      const uint32_t par = t & 1;
+      const uint32_t gbase = (uint32_t)t * C::BPS;
+      // ---------------- E1 (behind the u-group): r = sigmoid(.), r*h replaces h in the A operand
+      mbar_wait(g_r_done, par);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < C::NB; ++j) {
+        const int kc = cs * C::NB + j;
+        const uint32_t g = gbase + j * 4 + cs;
+        const int slot = g % C::NXB;
+        xbox_wait(&xfull[slot], g / C::NXB);
+        const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {               // 8 columns = one 16-byte chunk of the A operand
+          float acc[8];
+          tmem_ld8(trow + kc * 32 + g8 * 8, acc);
+          tmem_ld_wait();
+          const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
+          const int hc = j * 32 + g8 * 8;
+          acc[0] = sigmoid_a(acc[0] + x0.x) * h[hc + 0];
+          acc[1] = sigmoid_a(acc[1] + x0.y) * h[hc + 1];
+          acc[2] = sigmoid_a(acc[2] + x0.z) * h[hc + 2];
+          acc[3] = sigmoid_a(acc[3] + x0.w) * h[hc + 3];
+          acc[4] = sigmoid_a(acc[4] + x1.x) * h[hc + 4];
+          acc[5] = sigmoid_a(acc[5] + x1.y) * h[hc + 5];
+          acc[6] = sigmoid_a(acc[6] + x1.z) * h[hc + 6];
+          acc[7] = sigmoid_a(acc[7] + x1.w) * h[hc + 7];
+          if (g8 == 0) mbar_wait(&a_free[kc], par);     // the u-group's MMAs have read h chunk kc
+          const Split8 s = split8(acc);
+          *reinterpret_cast<uint4*>(my_hi + (kc * 4 + g8) * 2048) = s.hi;
+          *reinterpret_cast<uint4*>(my_lo + (kc * 4 + g8) * 2048) = s.lo;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xempty[slot]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rh_ready);
+
+      // ---------------- E2a (behind the candidate group): u = sigmoid(.) parked in its TMEM columns
+      mbar_wait(g_u_done, par);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < C::NB; ++j) {
+        const int kc = cs * C::NB + j;
+        const uint32_t g = gbase + C::NKC + j * 4 + cs;
+        const int slot = g % C::NXB;
+        xbox_wait(&xfull[slot], g / C::NXB);
+        const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float acc[8];
+          tmem_ld8(trow + H + kc * 32 + g8 * 8, acc);
+          tmem_ld_wait();
+          const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
+          acc[0] = sigmoid_a(acc[0] + x0.x);
+          acc[1] = sigmoid_a(acc[1] + x0.y);
+          acc[2] = sigmoid_a(acc[2] + x0.z);
+          acc[3] = sigmoid_a(acc[3] + x0.w);
+          acc[4] = sigmoid_a(acc[4] + x1.x);
+          acc[5] = sigmoid_a(acc[5] + x1.y);
+          acc[6] = sigmoid_a(acc[6] + x1.z);
+          acc[7] = sigmoid_a(acc[7] + x1.w);
+          tmem_st8(trow + H + kc * 32 + g8 * 8, acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xempty[slot]);
+      }
+      tmem_st_wait();
+
+      // ---------------- E2b (exposed): candidate, state update, h' -> registers, HBM and the A operand
+      mbar_wait(c_done, par);
+      tc_fence_after();
+      float* hout = (ok && a.hs) ? a.hs + row * a.hs_row_stride + (long)t * a.hs_step_stride + cbeg : nullptr;
+      float* hfin = (ok && a.h_final && t == a.T - 1) ? a.h_final + row * (long)a.ld_hf + cbeg : nullptr;
+#pragma unroll
+      for (int j = 0; j < C::NB; ++j) {
+        const int kc = cs * C::NB + j;
+        const uint32_t g = gbase + 2 * C::NKC + j * 4 + cs;
+        const int slot = g % C::NXB;
+        xbox_wait(&xfull[slot], g / C::NXB);
+        const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float accc[8], u[8];
+          tmem_ld8(trow + C::CAND_COL + kc * 32 + g8 * 8, accc);
+          tmem_ld8(trow + H + kc * 32 + g8 * 8, u);
+          tmem_ld_wait();
+          const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
+          const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          const int hc = j * 32 + g8 * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float cd = tanh_a(accc[i] + xs[i]);
+            const float hn = fmaf(u[i], h[hc + i] - cd, cd);     // u*h + (1-u)*cd
+            h[hc + i] = hn;
+          }
+          if (hout) {
+            __stcs(reinterpret_cast<float4*>(hout + hc), make_float4(h[hc], h[hc + 1], h[hc + 2], h[hc + 3]));
+            __stcs(reinterpret_cast<float4*>(hout + hc + 4), make_float4(h[hc + 4], h[hc + 5], h[hc + 6], h[hc + 7]));
+          }
+          if (hfin) {
+            *reinterpret_cast<float4*>(hfin + hc) = make_float4(h[hc], h[hc + 1], h[hc + 2], h[hc + 3]);
+            *reinterpret_cast<float4*>(hfin + hc + 4) = make_float4(h[hc + 4], h[hc + 5], h[hc + 6], h[hc + 7]);
+          }
+          const Split8 s = split8(&h[hc]);
+          *reinterpret_cast<uint4*>(my_hi + (kc * 4 + g8) * 2048) = s.hi;
+          *reinterpret_cast<uint4*>(my_lo + (kc * 4 + g8) * 2048) = s.lo;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&xempty[slot]);
+          mbar_arrive(&h_ready[kc]);
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(TM, H);
+      const uint32_t lbo = H * 16;
+      const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), wr_s = smem_u32(wring);
+      uint32_t itw = 0;
+      for (int t = 0; t < a.T; ++t) {
+        const uint32_t par = t & 1;
+#pragma unroll 1
+        for (int nb = 0; nb < 3; ++nb) {          // r columns, u columns, candidate
+          const uint32_t d = tmem + (nb == 0 ? 0 : (nb == 1 ? H : C::CAND_COL));
+          if (nb == 2) {
+            mbar_wait(rh_ready, par);
+            tc_fence_after();
+          }
+          uint32_t accf = 0;
+#pragma unroll 1
+          for (int kc = 0; kc < C::NKC; ++kc) {
+            if (nb == 0) {
+              if (C::ALIAS) {                      // the r columns still hold the candidate the epilogues are reading
+                if (kc == 0)
+                  for (int k = 0; k < C::NKC; ++k) mbar_wait(&h_ready[k], par);
+              } else {
+                mbar_wait(&h_ready[kc], par);
+              }
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int s = 0; s < C::SPC; ++s, ++itw) {
+              const int slot = itw % C::NSW;
+              mbar_wait(&wfull[slot], (itw / C::NSW) & 1);
+              tc_fence_after();
+              const uint32_t sb = wr_s + slot * C::SLOT_BYTES;
+#pragma unroll
+              for (int j = 0; j < C::KSLOT / 16; ++j) {
+                const uint32_t ao = (kc * 4 + (s * (C::KSLOT / 16) + j) * 2) * 2048;
+                const uint64_t ahi = smem_desc(a_hi_s + ao, 2048, 128), alo = smem_desc(a_lo_s + ao, 2048, 128);
+                const uint64_t bhi = smem_desc(sb + j * 2 * lbo, lbo, 128);
+                const uint64_t blo = smem_desc(sb + C::SLOT_HALF + j * 2 * lbo, lbo, 128);
+                mma_bf16(d, ahi, bhi, idesc, accf);
+                accf = 1;
+                if (a.passes == 3) {
+                  mma_bf16(d, alo, bhi, idesc, 1);
+                  mma_bf16(d, ahi, blo, idesc, 1);
+                }
+              }
+              mma_commit(&wempty[slot]);
+            }
+            if (nb == 1) mma_commit(&a_free[kc]);  // h chunk kc has been read by both gate groups
+          }
+          if (nb == 0) mma_commit(g_r_done);
+          if (nb == 1) mma_commit(g_u_done);
+          if (nb == 2) mma_commit(c_done);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    // ======================================================================== loader: weight ring + xp ring
+    if (warp == EPI_WARPS + 1 && lane == 0) {
+      const uint32_t totW = (uint32_t)a.T * C::WPS, totX = (uint32_t)a.T * C::BPS;
+      const uint64_t xpol = a.xp_const ? L2_EVICT_LAST : L2_EVICT_FIRST;
+      uint32_t itw = 0, g = 0;
+      while (itw < totW || g < totX) {
+        if (g < totX) {
+          const int slot = g % C::NXB;
+          if (mbar_test_wait(&xempty[slot], ((g / C::NXB) & 1) ^ 1)) {
+            const uint32_t t = g / C::BPS, ib = g % C::BPS;
+            const int gate = ib / C::NKC, w = ib % C::NKC;          // w = j*4 + cs
+            const int col = (w & 3) * C::HC + (w >> 2) * 32;
+            if (a.dbg & 1) {
+              mbar_arrive(&xfull[slot]);
+            } else {
+              mbar_arrive_expect_tx(&xfull[slot], XBOX_BYTES);
+              tma_load_2d(xring + (size_t)slot * XBOX_BYTES, &tm_xp, (int)(t * a.xp_step + gate * H + col), (int)row0,
+                          &xfull[slot], xpol);
+            }
+            ++g;
+          }
+        }
+        if (itw < totW) {
+          const int slot = itw % C::NSW;
+          if (mbar_test_wait(&wempty[slot], ((itw / C::NSW) & 1) ^ 1)) {
+            const uint32_t wi = itw % C::WPS;
+            const int nb = wi / (C::NKC * C::SPC), r = wi % (C::NKC * C::SPC);
+            const int blk = r / C::SPC, part = r % C::SPC;
+            const uint8_t* src = (nb < 2 ? a.wg + ((size_t)nb * C::NKC + blk) * C::BLOCK_BYTES
+                                         : a.wc + (size_t)blk * C::BLOCK_BYTES);
+            uint8_t* dst = wring + (size_t)slot * C::SLOT_BYTES;
+            if (a.dbg & 2) {
+              mbar_arrive(&wfull[slot]);
+              ++itw;
+              continue;
+            }
+            mbar_arrive_expect_tx(&wfull[slot], C::SLOT_BYTES);
+            if (C::SPC == 1) {
+              bulk_g2s_hint(dst, src, C::SLOT_BYTES, &wfull[slot], L2_EVICT_LAST);
+            } else {                               // half a block: chunks {2p, 2p+1} of hi, then of lo
+              bulk_g2s_hint(dst, src + (size_t)part * C::SLOT_HALF, C::SLOT_HALF, &wfull[slot], L2_EVICT_LAST);
+              bulk_g2s_hint(dst + C::SLOT_HALF, src + 4 * H * 16 + (size_t)part * C::SLOT_HALF, C::SLOT_HALF, &wfull[slot],
+                            L2_EVICT_LAST);
+            }
+            ++itw;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem, 512);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+template <int H>
+int launch3(const CUtensorMap& tm, const Gru3Args& a, unsigned grid, cudaStream_t st) {
+  DESIRE_ENSURE_SMEM(gru_tc3_kernel<H>, Cfg3<H>::SMEM);
+  DESIRE_LAUNCH(st, (gru_tc3_kernel<H><<<grid, NTHR3, Cfg3<H>::SMEM, st>>>(tm, a)));
+  return DESIRE_OK;
+}
+
+bool v3_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DESIRE_GRU_V2");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+}  // namespace
+
+// FP32 row-major [rows, row_stride] tensor -> tiled map with [128 rows x 32 columns] boxes, 128-byte swizzle
+int make_tmap_rows32(CUtensorMap* tm, const float* base, long rows, long row_stride) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return DESIRE_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)row_stride, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_stride * 4};
+  const cuuint32_t box[2] = {32, TM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a [%ld x %ld] FP32 tensor", (int)r, rows, row_stride);
+    return DESIRE_ERR_CUDA;
+  }
+  return DESIRE_OK;
+}
+
+bool gru_tc3_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes) {
+  if (v3_disabled() || gemm_mode() == 0 || !a.xp || a.traj || a.ex || a.Ka != 0) return false;
+  if (a.H != 128 && a.H != 256) return false;
+  if (a.R < 64 || a.T < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(a.xp) & 15) || a.xp_row_stride % 4 != 0 || a.xp_step_stride % 4 != 0) return false;
+  if (a.xp_row_stride < (long)(a.T - 1) * a.xp_step_stride + 3 * a.H) return false;   // a step is a column window of the row
+  if (a.T > 1 && !a.hs && !a.h_final) return false;
+  if (!a.packed && (!pack_ws || pack_bytes < gru_tc3_pack_bytes(a.H))) return false;
+  return encode_fn() != nullptr;
+}
+
+size_t gru_tc3_pack_bytes(int H) { return align_up(tc_pack_bytes(H, 2 * H, H)) + align_up(tc_pack_bytes(H, H, H)); }
+
+int gru_tc3_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DESIRE_CHECK_ARG(ws && ws_bytes >= gru_tc3_pack_bytes(H), "gru_tc3_pack: workspace too small");
+  uint8_t* pg = (uint8_t*)ws;
+  DESIRE_TRY(tc_pack_b(w_g, 2 * H, false, H, 2 * H, H, pg, st));
+  DESIRE_TRY(tc_pack_b(w_c, H, false, H, H, H, pg + align_up(tc_pack_bytes(H, 2 * H, H)), st));
+  return DESIRE_OK;
+}
+
+int gru_seq_tc3(const GruSeqArgs& s, void* pack_ws, cudaStream_t st) {
+  const int H = s.H;
+  if (s.R == 0 || s.T == 0) return DESIRE_OK;
+  Gru3Args a{};
+  a.R = s.R; a.T = s.T;
+  a.xp_step = (int)s.xp_step_stride;
+  a.h0 = s.h0; a.h0_div = s.h0_div > 0 ? s.h0_div : 1; a.ld_h0 = s.ld_h0;
+  a.hs = s.hs; a.hs_row_stride = s.hs_row_stride; a.hs_step_stride = s.hs_step_stride;
+  a.h_final = s.h_final; a.ld_hf = s.ld_hf;
+  a.passes = gemm_mode() == 1 ? 1 : 3;
+  a.xp_const = (s.xp_step_stride == 0 && s.T > 1) ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("DESIRE_GRU3_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    a.dbg = dbg;
+  }
+  const uint8_t* pg = (const uint8_t*)(s.packed ? s.packed : pack_ws);
+  if (!s.packed) DESIRE_TRY(gru_tc3_pack(s.w_g, s.w_c, H, pack_ws, gru_tc3_pack_bytes(H), st));
+  a.wg = pg;
+  a.wc = pg + align_up(tc_pack_bytes(H, 2 * H, H));
+  CUtensorMap tm;
+  DESIRE_TRY(make_tmap_rows32(&tm, s.xp, s.R, s.xp_row_stride));
+  const unsigned grid = (unsigned)(((long)s.R + TM - 1) / TM);
+  return H == 128 ? launch3<128>(tm, a, grid, st) : launch3<256>(tm, a, grid, st);
+}
+
+}  // namespace desire

@@ -316,7 +316,9 @@ class TrainPath(HotPath):
     multi-GPU step is ONE all-reduce of `grad_flat`."""
 
     def __init__(self, cfg: DesireConfig, flat: torch.Tensor, params: dict, offsets: dict, B: int, device="cuda:0",
-                 train_ioc=True):
+                 train_ioc=True, opt_state=None):
+        """opt_state: (adam_m, adam_v, step) with step a one-element list — the optimiser state belongs to the
+        parameters, not to a batch size: DESIREModel passes the same triple to every TrainPath it builds."""
         super().__init__(cfg, params, B, device)
         self.train_ioc = bool(train_ioc) and cfg.ioc_iters > 0
         for k, (o, cnt, shp) in offsets.items():
@@ -325,10 +327,11 @@ class TrainPath(HotPath):
         self.flat, self.offsets = flat, offsets
         self.grad_flat = torch.zeros_like(flat)
         self.G = {k: self.grad_flat[o:o + cnt].view(shp) for k, (o, cnt, shp) in offsets.items()}
-        self.adam_m, self.adam_v = torch.zeros_like(flat), torch.zeros_like(flat)
+        if opt_state is None:
+            opt_state = (torch.zeros_like(flat), torch.zeros_like(flat), [0])
+        self.adam_m, self.adam_v, self._step = opt_state
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.count = torch.ones(1, dtype=torch.float32, device=self.device)
-        self.step_no = 0
         N, K, H, Zl, Tf = cfg.max_num_obj, cfg.K, cfg.H, cfg.Z, cfg.pred_length
         M, R, S2 = self.M, self.R, cfg.S * cfg.S
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
@@ -358,6 +361,14 @@ class TrainPath(HotPath):
             self.ws_bytes = bws
             self.ws = torch.empty(bws, dtype=torch.uint8, device=self.device)
         self.train_graph = None
+
+    @property
+    def step_no(self):
+        return self._step[0]
+
+    @step_no.setter
+    def step_no(self, v):
+        self._step[0] = int(v)
 
     def set_count(self, obs):
         """Number of existing agents (id != 0, D8) of this rank's scenes, summed over ranks: the normaliser of

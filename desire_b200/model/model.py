@@ -27,6 +27,7 @@ def config_from_args(args) -> DesireConfig:
     return DesireConfig(
         rnn_size=g("rnn_size", 512), d_dim=g("d_dim", 16), latent_size=g("latent_size", 128),
         seq_length=g("seq_length", 8), max_num_obj=g("max_num_obj", 60), stride=g("stride", 1),
+        num_layers=g("num_layers", 1), model=g("model", "gru"),
         pred_length=g("pred_length", 12), num_samples=g("num_samples", 20), ioc_iters=g("ioc_iters", 2),
         scene_size=g("scene_size", 256), scene_channels=g("scene_channels", 32), vel_dim=g("vel_dim", 16),
         n_rad=g("n_rad", 6), n_ang=g("n_ang", 6), r_min=g("r_min", 0.01), r_max=g("r_max", 0.5))
@@ -60,6 +61,9 @@ class DESIREModel(object):
         init = params if params is not None else self.define_weights(seed)
         self.flat_weights, self.weights, self._offsets = flatten_params(init, self.device)
         self.grad_clip = float(getattr(args, "grad_clip", 10.0))
+        # Adam moments + step live next to the flat weight buffer and are shared by the train paths of every batch size
+        self.adam_m, self.adam_v = torch.zeros_like(self.flat_weights), torch.zeros_like(self.flat_weights)
+        self.adam_step = [0]
         self._paths = {}
         self._train_paths = {}
         self._pinned = {}
@@ -79,12 +83,24 @@ class DESIREModel(object):
         `batch_size` scenes and loads the kernel library (raises if it is missing)."""
         self._path(max(int(self.batch_size), 1))
 
+    @staticmethod
+    def _check_activ_phase(who, activ, phase):
+        """The reference calls these layers with activ=tf.nn.elu and phase=pt.Phase.train only
+        (model/model.py:258,266,457-462,476-481): per-row train-phase batch statistics are what the kernels implement.
+        Anything else would silently compute something different, so it raises."""
+        if activ is not None and getattr(activ, "__name__", str(activ)).lower() not in ("elu",):
+            raise ValueError("%s: only the ELU activation of the reference (model.py:258,266) is built, got %r" % (who, activ))
+        if phase is not None and str(getattr(phase, "name", phase)).lower() not in ("train", "phase.train"):
+            raise ValueError("%s: only phase=train (batch statistics, model.py:457-462,476-481) is built; the "
+                             "inference phase with learned moments (learned_moments_update_rate=0.0003) is not, "
+                             "got %r" % (who, phase))
+
     def vae_encoder(self, inputs, latent_size=None, activ=None, phase=None):
         """model/model.py:471-492: inputs [M, 1024] (the fc_c features viewed as 32x32x1) -> (mean [M,Z], logvar [M,Z]).
-        `activ` / `phase` are accepted for signature parity (ELU and train-phase statistics are what the reference
-        passes and what the kernels implement)."""
+        `activ` / `phase`: None or the reference's values (ELU, train phase); anything else raises."""
         import ctypes as C
         from .. import _lib
+        self._check_activ_phase("vae_encoder", activ, phase)
         x = inputs.to(self.device, torch.float32).contiguous().reshape(-1, self.vae_input_size)
         Zl = int(latent_size or self.cfg.Z)
         if Zl != self.cfg.Z:
@@ -104,6 +120,7 @@ class DESIREModel(object):
         """model/model.py:453-469: zval [R, Z] -> x_reconstr_mean [R, 1024] (32x32x1 flattened, sigmoid)."""
         import ctypes as C
         from .. import _lib
+        self._check_activ_phase("vae_decoder", activ, phase)
         z = zval.to(self.device, torch.float32).contiguous().reshape(-1, self.cfg.Z)
         if projection_size is not None and int(projection_size) != self.vae_input_size:
             raise ValueError("vae_decoder: the decoder always emits %d values (model.py:465-468)" % self.vae_input_size)
@@ -132,7 +149,8 @@ class DESIREModel(object):
 
     def _train_path(self, B) -> TrainPath:
         if B not in self._train_paths:
-            self._train_paths[B] = TrainPath(self.cfg, self.flat_weights, self.weights, self._offsets, B, self.device)
+            self._train_paths[B] = TrainPath(self.cfg, self.flat_weights, self.weights, self._offsets, B, self.device,
+                                             opt_state=(self.adam_m, self.adam_v, self.adam_step))
         return self._train_paths[B]
 
     def train_step(self, input_data, target_data, eps=None, scene=None, seed=None):

@@ -53,8 +53,11 @@ def build_parser():
     p.add_argument('--data_dir', type=str, default='data/', help='directory holding <scene>/<video>/annotations_processed.csv')
     p.add_argument('--save_dir', type=str, default='save', help='checkpoint / config directory (reference: save/)')
     p.add_argument('--clip_objects', action='store_true', help='keep the first max_num_obj objects of crowded frames instead of raising')
-    p.add_argument('--norm_w', type=float, default=0.0, help='divide x by this (0 = raw pixels as in the reference)')
+    p.add_argument('--norm_w', type=float, default=0.0, help='divide x by this (0 with --norm_h 0: the extent of the loaded data, so positions land in [0,1])')
     p.add_argument('--norm_h', type=float, default=0.0, help='divide y by this')
+    p.add_argument('--raw_pixels', action='store_true', help="keep the reference's raw pixel coordinates (the IOC stage's scene gather and log-polar radii assume the unit square: only sensible with --ioc_iters 0)")
+    p.add_argument('--fix_id0', action='store_true', help='shift track ids by +1 so SDD track 0 is not taken for the "no object" sentinel (reference quirk, utils/data_loader.py:221-222)')
+    p.add_argument('--prefetch', type=int, default=2, help='minibatches built ahead by the DataLoader thread into pinned buffers (0 = build each batch inside the step loop)')
     p.add_argument('--max_batches', type=int, default=0, help='stop an epoch after this many batches (0 = all)')
     p.add_argument('--optimize', type=int, default=1, help='1: run the Adam step per minibatch (D9); 0: evaluate cost only, as the reference loop does')
     p.add_argument('--resume', type=str, default='', help='checkpoint file written by a previous run to continue from')
@@ -68,27 +71,28 @@ def main(argv=None):
     train(args)
 
 
-def save_checkpoint(model, path, next_step):
+def save_checkpoint(model, path, next_step, loader_state=None):
     """Weights by name (the reference's tf.train.Saver keeps variables by name, train.py:114,200-205) plus the
-    optimiser state of every TrainPath-independent buffer so a resumed run continues the same trajectory."""
+    optimiser state (Adam moments + step, kept on the model next to the flat weight buffer and shared by every batch
+    size) and the DataLoader's pointers / RNG state, so a resumed run continues the same trajectory on the same data."""
     import torch
-    state = {"weights": {k: v.detach().cpu() for k, v in model.weights.items()}, "next_step": int(next_step)}
-    tps = list(model._train_paths.values())
-    if tps:
-        state["adam_m"], state["adam_v"], state["adam_t"] = tps[0].adam_m.cpu(), tps[0].adam_v.cpu(), tps[0].step_no
+    state = {"weights": {k: v.detach().cpu() for k, v in model.weights.items()}, "next_step": int(next_step),
+             "adam_m": model.adam_m.cpu(), "adam_v": model.adam_v.cpu(), "adam_t": int(model.adam_step[0]),
+             "loader": loader_state}
     torch.save(state, path)
 
 
-def load_checkpoint(model, path):
+def load_checkpoint(model, path, data_loader=None):
     import torch
-    state = torch.load(path, map_location="cpu")
+    state = torch.load(path, map_location="cpu", weights_only=False)
     for k, v in state["weights"].items():
         model.weights[k].copy_(v)
     if "adam_m" in state:
-        tp = model._train_path(max(int(model.batch_size), 1))
-        tp.adam_m.copy_(state["adam_m"])
-        tp.adam_v.copy_(state["adam_v"])
-        tp.step_no = int(state["adam_t"])
+        model.adam_m.copy_(state["adam_m"])
+        model.adam_v.copy_(state["adam_v"])
+        model.adam_step[0] = int(state["adam_t"])
+    if data_loader is not None and state.get("loader") is not None:
+        data_loader.set_state(state["loader"])
     return int(state.get("next_step", 0))
 
 
@@ -127,43 +131,61 @@ def _check_replicas_in_sync(model, world):
 
 
 def train(args):
-    from desire_b200.dist import global_masked_cost, shard_scenes
+    from desire_b200.dist import global_masked_cost
     from desire_b200.model.model import DESIREModel
     from desire_b200.utils.data_loader import DataLoader
     import torch
+    import torch.distributed as dist
 
     rank, world = _init_distributed(args)
-    norm = (args.norm_w, args.norm_h) if args.norm_w > 0 and args.norm_h > 0 else None
-    data_loader = DataLoader(args.batch_size, args.seq_length, args.max_num_obj, args.leave_dataset, preprocess=False,
-                             data_dir=args.data_dir, pred_length=args.pred_length, clip=args.clip_objects,
-                             normalize=norm)
+    if args.raw_pixels:
+        norm = None
+        if args.ioc_iters > 0 and rank == 0:
+            print("warning: --raw_pixels with ioc_iters > 0: the scene gather clamps every sample to the map border and no "
+                  "neighbour falls inside the log-polar radii [r_min, r_max) = unit-square fractions")
+    else:
+        norm = (args.norm_w, args.norm_h) if args.norm_w > 0 and args.norm_h > 0 else "auto"
+    lkw = dict(data_dir=args.data_dir, pred_length=args.pred_length, clip=args.clip_objects, normalize=norm,
+               seed=args.seed, fix_id0=args.fix_id0)     # the SAME seed on every rank: all ranks cut the same minibatches
+    if world > 1:
+        # rank 0 alone (re)builds the preprocessed cache; the others read it after the barrier
+        if rank == 0:
+            DataLoader(args.batch_size, args.seq_length, args.max_num_obj, args.leave_dataset, preprocess=False, **lkw)
+        dist.barrier()
+    data_loader = DataLoader(args.batch_size, args.seq_length, args.max_num_obj, args.leave_dataset, preprocess=False, **lkw)
+    if rank == 0 and norm == "auto":
+        print("coordinates divided by the data extent {} x {} (pass --norm_w/--norm_h to fix it)".format(*data_loader.normalize))
     os.makedirs(args.save_dir, exist_ok=True)
-    with open(os.path.join(args.save_dir, 'config.pkl'), 'wb') as fh:     # train.py:102-103
-        pickle.dump(args, fh)
+    if rank == 0:
+        with open(os.path.join(args.save_dir, 'config.pkl'), 'wb') as fh:     # train.py:102-103
+            pickle.dump(args, fh)
 
     model = DESIREModel(args, device=args.device, seed=args.seed)      # same seed => identical weights on every rank
     model.batch_size = args.batch_size // world
     start_step = 0
     if args.resume:
-        start_step = load_checkpoint(model, args.resume)
+        start_step = load_checkpoint(model, args.resume, data_loader)
         print("resumed from {} at step {}".format(args.resume, start_step))
     losses = []
+    shard = (rank, world) if world > 1 else None
     for epoch in range(args.num_epochs):
         model.learning_rate = args.learning_rate * (args.decay_rate ** epoch)   # train.py:122-126
-        data_loader.reset_batch_pointer()
         nb = data_loader.num_batches if not args.max_batches else min(args.max_batches, data_loader.num_batches)
-        for batch in range(nb):
-            start = time.time()
-            xval, yval, dval = data_loader.next_batch()
-            x = DataLoader.to_model_layout(xval)         # [B,N,Tp,3] agent-major (the transpose train.py:158-173 forgot)
-            y = DataLoader.to_model_layout(yval)
-            scene = data_loader.scene_images(dval, args.scene_size)   # reference.jpg next to the CSV, blank if absent
-            if world > 1:                                # this rank's scenes of the minibatch
-                mine = shard_scenes(x.shape[0], rank, world)
-                x, y, scene = np.ascontiguousarray(x[mine]), np.ascontiguousarray(y[mine]), np.ascontiguousarray(scene[mine])
-            step = epoch * data_loader.num_batches + batch
-            if step < start_step:
+        first = 0
+        if start_step > epoch * data_loader.num_batches:
+            # resuming inside this epoch: the checkpoint restored the loader's pointers / RNG at `start_step`
+            first = min(nb, start_step - epoch * data_loader.num_batches)
+            if first >= nb:
                 continue
+        else:
+            data_loader.reset_batch_pointer()
+        if args.prefetch > 0:
+            batches = data_loader.prefetch_epoch(nb - first, args.scene_size, depth=args.prefetch, shard=shard)
+        else:
+            batches = _inline_batches(data_loader, nb - first, args.scene_size, shard)
+        start = time.time()
+        for batch, (x, y, scene, _dval, lstate) in enumerate(batches, start=first):
+            step = epoch * data_loader.num_batches + batch
             if args.optimize:
                 c = model.train_step(x, y, eps=None, scene=scene, seed=args.seed + epoch * 100003 + batch + 7919 * rank)
                 # cost over the whole minibatch: sum_ranks(cost_r * n_r) / sum_ranks(n_r)   (model/model.py:376)
@@ -180,11 +202,27 @@ def train(args):
                 sys.stdout.flush()
             if rank == 0 and step % args.save_every == 0 and step > 0:    # train.py:197-207
                 checkpoint_path = os.path.join(args.save_dir, 'social_model.ckpt')
-                save_checkpoint(model, "%s-%d" % (checkpoint_path, step), step + 1)
+                save_checkpoint(model, "%s-%d" % (checkpoint_path, step), step + 1, lstate)
                 print("model saved to {}".format(checkpoint_path))
                 sys.stdout.flush()
+            start = time.time()
         _check_replicas_in_sync(model, world)
     return losses
+
+
+def _inline_batches(data_loader, n, scene_size, shard):
+    """--prefetch 0: each minibatch is built inside the step loop (the reference's order of work, train.py:140)."""
+    from desire_b200.utils.data_loader import DataLoader
+    for _ in range(n):
+        xval, yval, dval = data_loader.next_batch()
+        x = DataLoader.to_model_layout(xval)         # [B,N,Tp,3] agent-major (the transpose train.py:158-173 forgot)
+        y = DataLoader.to_model_layout(yval)
+        scene = data_loader.scene_images(dval, scene_size)   # reference.jpg next to the CSV, blank if absent
+        if shard is not None:
+            mine = list(range(shard[0], x.shape[0], shard[1]))
+            x, y, scene = np.ascontiguousarray(x[mine]), np.ascontiguousarray(y[mine]), np.ascontiguousarray(scene[mine])
+            dval = [dval[j] for j in mine]
+        yield x, y, scene, dval, data_loader.state()
 
 
 if __name__ == '__main__':

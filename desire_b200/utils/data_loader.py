@@ -14,7 +14,14 @@ What is kept exactly (tests/test_data_loader.py checks it against a literal rest
 What is added: `pred_length` — when set, the target holds the NEXT pred_length frames after the
 observed window (what the model's future encoder and losses need); `data_dir`; `clip` — the reference raises
 when a frame holds more than max_num_obj objects (10 of the 60 SDD videos do), clip=True keeps the
-first max_num_obj instead; `normalize=(W,H)` divides pixel coordinates.
+first max_num_obj instead; `normalize=(W,H)` divides pixel coordinates ("auto" = the data's own extent, so that
+positions land in the unit square the IOC stage's scene gather and log-polar radii assume); `seed` — a private
+random.Random for the frame-pointer stride (the reference draws from Python's global, unseeded `random`, :236), so
+every rank of a data-parallel job walks the same windows and a checkpoint can restore the order (state()/set_state());
+`fix_id0` — SDD track ids start at 0 and 0 is also the "no object" sentinel (:221-222, model/model.py:206,357), so
+the reference silently drops track 0 of every video; fix_id0=True shifts the real ids by +1 when the cache is loaded;
+`prefetch_epoch()` — a background thread builds batch t+1 (windows, agent-major layout, scene images) into pinned
+host buffers while the GPU runs step t.
 
 The reference's frame_preprocess is O(frames x annotations) boolean masking (4.8e9 compares for
 bookstore/video0); here one stable sort by frame + a rank-within-frame scatter does it.
@@ -23,14 +30,17 @@ from __future__ import annotations
 
 import os
 import pickle
+import queue
 import random
+import threading
 
 import numpy as np
 
 
 class DataLoader(object):
     def __init__(self, batch_size=50, seq_length=5, max_num_obj=40, leave_dataset=1, preprocess=False,
-                 data_dir="data/", pred_length=None, clip=False, normalize=None, cache=True):
+                 data_dir="data/", pred_length=None, clip=False, normalize=None, cache=True, seed=None,
+                 fix_id0=False):
         self.leave_dataset = leave_dataset
         self.data_dir = data_dir
         self.frame_pointer = 0
@@ -41,6 +51,9 @@ class DataLoader(object):
         self.pred_length = pred_length
         self.clip = clip
         self.normalize = normalize
+        self.fix_id0 = bool(fix_id0)
+        # seed=None keeps the reference's behaviour (the process-global `random`, data_loader.py:236)
+        self.rng = random.Random(seed) if seed is not None else random
         data_file = os.path.join(self.data_dir, "trajectories.cpkl")
         # the reference ALWAYS re-runs the preprocessing (its guard is commented out, :53-59); here the cache is
         # reused unless preprocess=True or it is missing/stale
@@ -90,9 +103,11 @@ class DataLoader(object):
             frame_list_data.append(frame_list.tolist())
             num_obj_data.append(counts.tolist())
         os.makedirs(os.path.dirname(os.path.abspath(data_file)), exist_ok=True)
-        with open(data_file, "wb") as fh:
+        tmp = "%s.tmp.%d" % (data_file, os.getpid())          # a concurrent reader never sees a partial file
+        with open(tmp, "wb") as fh:
             pickle.dump((all_frame_data, frame_list_data, num_obj_data,
                          (self._csv_files(), self.max_num_obj, self.clip)), fh, protocol=2)
+        os.replace(tmp, data_file)
 
     def load_preprocessed(self, data_file):
         with open(data_file, "rb") as fh:
@@ -100,6 +115,22 @@ class DataLoader(object):
         self.data = self.raw_data[0]
         self.frame_list = self.raw_data[1]
         self.num_obj_list = self.raw_data[2]
+        if self.fix_id0:
+            # slots [0, count_f) of frame f hold real objects (frame_preprocess fills them in file order): shift their
+            # ids so that a real track 0 is no longer mistaken for an empty slot
+            fixed = []
+            for d, counts in zip(self.data, self.num_obj_list):
+                d = d.copy()
+                real = np.arange(d.shape[1])[None, :] < np.minimum(np.asarray(counts), d.shape[1])[:, None]
+                d[..., 0] = np.where(real, d[..., 0] + 1, d[..., 0])
+                fixed.append(d)
+            self.data = fixed
+        if isinstance(self.normalize, str):
+            if self.normalize != "auto":
+                raise ValueError("normalize must be None, (W, H) or 'auto'")
+            w = max([float(d[..., 1].max()) for d in self.data] + [1.0])
+            h = max([float(d[..., 2].max()) for d in self.data] + [1.0])
+            self.normalize = (float(np.ceil(w)), float(np.ceil(h)))
         if self.normalize is not None:
             w, h = self.normalize
             self.data = [np.concatenate([d[..., :1], d[..., 1:2] / w, d[..., 2:3] / h], -1) for d in self.data]
@@ -151,7 +182,7 @@ class DataLoader(object):
                 x_batch.append(src)
                 y_batch.append(tgt)
                 if random_update:
-                    self.frame_pointer += random.randint(1, self.seq_length)
+                    self.frame_pointer += self.rng.randint(1, self.seq_length)
                 else:
                     self.frame_pointer += self.seq_length
                 dval.append(self.dataset_pointer)
@@ -173,6 +204,84 @@ class DataLoader(object):
     def reset_batch_pointer(self):
         self.dataset_pointer = 0
         self.frame_pointer = 0
+
+    # ------------------------------------------------------------------ resumable order (checkpoints)
+    def state(self):
+        """Pointers + RNG state: what a checkpoint needs to replay the same sequence of minibatches."""
+        rng = self.rng.getstate() if self.rng is not random else None
+        return {"dataset_pointer": self.dataset_pointer, "frame_pointer": self.frame_pointer, "rng": rng}
+
+    def set_state(self, st):
+        self.dataset_pointer, self.frame_pointer = int(st["dataset_pointer"]), int(st["frame_pointer"])
+        if st.get("rng") is not None and self.rng is not random:
+            self.rng.setstate(st["rng"])
+
+    # ------------------------------------------------------------------ background prefetch into pinned buffers
+    def prefetch_epoch(self, n_batches, scene_size=None, depth=2, shard=None, random_update=True):
+        """Generator over the next `n_batches` minibatches, built one ahead by a background thread:
+            for x, y, scene, dval, state in loader.prefetch_epoch(nb, scene_size): ...
+        x [B,N,Tp,3], y [B,N,Tf,3] (agent-major, float32) and scene [B,S,S,3] (None without scene_size) are torch
+        tensors in pinned host memory (plain host memory when CUDA is absent) taken from a ring of depth+1 buffer
+        sets, so the batch handed out stays valid until the next iteration asks for another one.  `shard` =
+        (rank, world) keeps only this rank's scenes (round-robin, dist.shard_scenes); every rank must build its loader
+        with the same seed so that all ranks cut the same minibatch.  `state` is loader.state() AFTER that batch —
+        store it in a checkpoint to resume the order.  Only the background thread touches the pointers meanwhile."""
+        import torch
+        pin = torch.cuda.is_available()
+        ring, q = {}, queue.Queue(maxsize=max(1, depth))
+        stop = threading.Event()
+
+        def buf(slot, name, shape):
+            key = (slot, name)
+            if key not in ring or tuple(ring[key].shape) != tuple(shape):
+                ring[key] = torch.empty(shape, dtype=torch.float32, pin_memory=pin)
+            return ring[key]
+
+        def work():
+            try:
+                for i in range(n_batches):
+                    if stop.is_set():
+                        return
+                    xval, yval, dval = self.next_batch(random_update)
+                    x, y = self.to_model_layout(xval), self.to_model_layout(yval)
+                    sc = self.scene_images(dval, scene_size) if scene_size else None
+                    if shard is not None:
+                        mine = list(range(shard[0], x.shape[0], shard[1]))
+                        x, y = x[mine], y[mine]
+                        sc = sc[mine] if sc is not None else None
+                        dval = [dval[j] for j in mine]
+                    slot = i % (depth + 1)
+                    out = []
+                    for name, a in (("x", x), ("y", y), ("scene", sc)):
+                        if a is None:
+                            out.append(None)
+                            continue
+                        t = buf(slot, name, a.shape)
+                        t.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)))
+                        out.append(t)
+                    q.put((out[0], out[1], out[2], dval, self.state()))
+                q.put(None)
+            except BaseException as e:      # surfaced in the consumer
+                q.put(e)
+
+        th = threading.Thread(target=work, name="desire-prefetch", daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            while th.is_alive():            # unblock a producer waiting on a full queue
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    pass
+                th.join(timeout=0.05)
 
     # ------------------------------------------------------------------ scene context (SURVEY 8f #4)
     SCENE_IMAGE_NAMES = ("reference.jpg", "reference.png", "reference.jpeg")

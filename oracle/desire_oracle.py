@@ -323,6 +323,34 @@ def logpolar_bin(dx, dy, r2_edges, dirs):
     return np.where(valid, rb * n_ang + ab, -1)
 
 
+def logpolar_margin(dx, dy, r2_edges, dirs):
+    """Distance, in position units, from d = (dx, dy) to the nearest edge of the log-polar grid: the radial
+    circles |d| = r_e and, for d inside the radial range, the sector boundary rays.  A perturbation of the
+    positions smaller than this cannot change logpolar_bin(d).  Test infrastructure for the parity tests
+    (which (scene, sample) groups may legitimately differ between two fp32 implementations)."""
+    r = np.sqrt(dx * dx + dy * dy)
+    edges = np.sqrt(np.asarray(r2_edges, np.float64))
+    m_r = np.abs(r[..., None].astype(np.float64) - edges).min(-1)
+    cr = np.abs(dirs[:, 0].astype(np.float64) * dy[..., None] - dirs[:, 1].astype(np.float64) * dx[..., None])
+    inside = (r >= edges[0]) & (r < edges[-1])
+    m_a = np.where(inside, cr.min(-1), np.inf)
+    return np.minimum(m_r, m_a)
+
+
+def group_margin(pos, mask, r2_edges, dirs):
+    """min over the pairs (i, j != i, j existing) of logpolar_margin, per (scene, sample): pos [B,N,K,2] -> [B,K]."""
+    B, N, K, _ = pos.shape
+    out = np.full((B, K), np.inf)
+    eye = np.eye(N, dtype=bool)[:, :, None]
+    for b in range(B):
+        dx = pos[b, None, :, :, 0] - pos[b, :, None, :, 0]
+        dy = pos[b, None, :, :, 1] - pos[b, :, None, :, 1]
+        m = logpolar_margin(dx, dy, r2_edges, dirs)
+        m = np.where((mask[b][None, :, None] > 0) & ~eye, m, np.inf)
+        out[b] = m.reshape(N * N, K).min(0)
+    return out
+
+
 def social_pool(pos, h, mask, r2_edges, dirs):
     """D11 log-polar social pooling: for row (b,i,k) average the hidden vectors h[b,j,k] of the
     other existing agents j != i of the same scene and sample index into the bin of
@@ -337,6 +365,14 @@ def social_pool(pos, h, mask, r2_edges, dirs):
         dy = pos[b, None, :, :, 1] - pos[b, :, None, :, 1]
         bins = logpolar_bin(dx, dy, r2_edges, dirs)               # [i, j, K]
         ok = (bins >= 0) & (mask[b][None, :, None] > 0) & ~eye
+        if N > 128:
+            # crowds (BASELINE configs[4], N=1024): the same sums as one BLAS product per sample,
+            # [(i,g), j] @ [j, H] — the einsum below takes minutes there
+            for k in range(K):
+                oh = ((bins[:, :, k, None] == np.arange(G)) & ok[:, :, k, None]).astype(h.dtype)     # [i,j,G]
+                s = (oh.transpose(0, 2, 1).reshape(N * G, N) @ h[b, :, k]).reshape(N, G, H)
+                out[b, :, k] = s / np.maximum(oh.sum(1), 1)[..., None]
+            continue
         onehot = ((bins[..., None] == np.arange(G)) & ok[..., None]).astype(h.dtype)   # [i,j,K,G]
         s = np.einsum("ijkg,jkh->ikgh", onehot, h[b])
         cnt = onehot.sum(1)                                        # [i,K,G]
@@ -367,7 +403,7 @@ def social_pool_loops(pos, h, mask, r2_edges, dirs):
     return out
 
 
-def ioc_refine(Yhat, x_last, Hx, fpool, fmap, mask, P, dims, iters, r2_edges, dirs, snapshots=None):
+def ioc_refine(Yhat, x_last, Hx, fpool, fmap, mask, P, dims, iters, r2_edges, dirs, snapshots=None, margins=None):
     """D11 ranking & refinement (absent in the reference, marker model/model.py:312-313).
 
     Per iteration, per step t and row (b,n,k):
@@ -393,6 +429,8 @@ def ioc_refine(Yhat, x_last, Hx, fpool, fmap, mask, P, dims, iters, r2_edges, di
             fv = relu((Y[:, t] - prev) @ P["ioc_vel_w"] + P["ioc_vel_b"])
             fs = bilinear_gather(fmap, Y[:, t].reshape(B, N * K, 2)).reshape(MK, -1)
             pooled = social_pool(Y[:, t].reshape(B, N, K, 2), h2.reshape(B, N, K, H), mask, r2_edges, dirs)
+            if margins is not None:      # [B,K] per (iteration, step): how close this step's binning is to an edge
+                margins.append(group_margin(Y[:, t].reshape(B, N, K, 2), mask, r2_edges, dirs))
             fsp = relu(pooled.reshape(MK, -1) @ P["ioc_sp_w"] + P["ioc_sp_b"])
             x_t = np.concatenate([fv, fs, fpool[:, t], fsp], 1)
             h2 = gru_cell(x_t, h2, P["dec2_wg"], P["dec2_bg"], P["dec2_wc"], P["dec2_bc"])
@@ -469,9 +507,12 @@ def forward(P, cfg, input_data, target_data, eps, scene_img, r2_edges, dirs):
     fmap = scene_cnn(scene_img, P)
     out["scene_features"] = fmap
     snaps = []
+    margins = [] if cfg.get("margins") else None
     scores, Yref = ioc_refine(Yhat, x_last, Hx, fpool, fmap, mask, P, (B, N, K),
-                              cfg["ioc_iters"], r2_edges, dirs, snaps)
+                              cfg["ioc_iters"], r2_edges, dirs, snaps, margins)
     out["ioc_scores"], out["Y_refined"] = scores, Yref
+    if margins:
+        out["bin_margin"] = np.min(np.stack(margins, 0), 0)      # [B,K], min over iterations and steps
     out["ioc_rows"] = ioc_loss_rows(scores, snaps, Y, K)
     out["ioc_cost"] = masked_cost(out["ioc_rows"], mask.reshape(M)) if cfg["ioc_iters"] > 0 else np.zeros((), Y.dtype)
     return out

@@ -139,3 +139,66 @@ def test_scene_images_loaded_resized_and_blank_when_absent(tmp_path):
     assert sc.shape == (2, 8, 8, 3) and sc.dtype == np.float32
     assert sc[0, :, :3, 0].min() > 0.9 and sc[0, :, 5:, 0].max() < 0.1 and sc[0, ..., 1:].max() == 0
     assert sc[1].max() == 0
+
+
+def test_seeded_loaders_walk_the_same_windows_and_state_restores_the_order():
+    """Two ranks with the same seed must cut the same minibatches (train.py under torchrun), and a checkpointed
+    loader state must replay the same order (--resume)."""
+    a = DataLoader(2, 8, 40, 1, data_dir=SDD, pred_length=12, cache=False, seed=11)
+    b = DataLoader(2, 8, 40, 1, data_dir=SDD, pred_length=12, cache=False, seed=11)
+    for _ in range(3):
+        xa, ya, da = a.next_batch()
+        xb, yb, db = b.next_batch()
+        assert all(np.array_equal(p, q) for p, q in zip(xa, xb)) and da == db
+    st = a.state()
+    nxt = a.next_batch()
+    c = DataLoader(2, 8, 40, 1, data_dir=SDD, pred_length=12, cache=False, seed=999)
+    c.set_state(st)
+    again = c.next_batch()
+    assert all(np.array_equal(p, q) for p, q in zip(nxt[0], again[0]))
+    assert all(np.array_equal(p, q) for p, q in zip(nxt[1], again[1]))
+
+
+def test_fix_id0_keeps_track_zero_and_auto_normalisation_maps_into_the_unit_square(tmp_path):
+    root = tmp_path / "data"
+    v = root / "scene" / "video0"
+    v.mkdir(parents=True)
+    # 30 frames, tracks 0 and 5 everywhere (SDD ids start at 0): frame, id, x, y rows as scripts/preprocess.py writes
+    frames = np.repeat(np.arange(30), 2)
+    ids = np.tile([0, 5], 30)
+    xs = 100.0 + frames * 3 + ids
+    ys = 700.0 - frames * 2 + ids
+    np.savetxt(v / "annotations_processed.csv", np.stack([frames, ids, xs, ys]), delimiter=",")
+    plain = DataLoader(1, 8, 4, 1, data_dir=str(root) + "/", pred_length=12, cache=False, seed=0)
+    x, _, _ = plain.next_batch()
+    assert set(np.unique(x[0][:, :, 0])) == {0.0, 5.0}
+    assert (x[0][:, :, 0] == 5).sum() == 8                 # the reference quirk: track 0 is invisible (data_loader.py:221-222)
+    assert np.count_nonzero(x[0][:, :, 1]) == 8
+    fixed = DataLoader(1, 8, 4, 1, data_dir=str(root) + "/", pred_length=12, cache=False, seed=0, fix_id0=True,
+                       normalize="auto")
+    x, y, _ = fixed.next_batch()
+    assert set(np.unique(x[0][:, :, 0])) == {0.0, 1.0, 6.0}      # ids shifted by one, 0 = empty slot only
+    assert np.count_nonzero(x[0][:, :, 1]) == 16
+    assert 0.0 < x[0][:, :, 1:][x[0][:, :, 0] > 0].min() and max(x[0][:, :, 1:].max(), y[0][:, :, 1:].max()) <= 1.0
+
+
+def test_prefetch_thread_yields_the_same_batches_in_pinned_layout():
+    a = DataLoader(2, 8, 40, 1, data_dir=SDD, pred_length=12, cache=False, seed=4)
+    b = DataLoader(2, 8, 40, 1, data_dir=SDD, pred_length=12, cache=False, seed=4)
+    got = []
+    for x, y, sc, dval, st in a.prefetch_epoch(3, scene_size=16, depth=2):
+        got.append((x.numpy().copy(), y.numpy().copy(), sc.numpy().copy(), list(dval), st))
+    assert len(got) == 3
+    for g in got:
+        xb, yb, db = b.next_batch()
+        assert np.array_equal(g[0], DataLoader.to_model_layout(xb)) and np.array_equal(g[1], DataLoader.to_model_layout(yb))
+        assert g[0].shape == (2, 40, 8, 3) and g[1].shape == (2, 40, 12, 3) and g[2].shape == (2, 16, 16, 3)
+        assert g[3] == db and g[4]["frame_pointer"] == b.frame_pointer
+    # a rank's shard of the same minibatches: scenes rank, rank+world, ...
+    c = DataLoader(2, 8, 40, 1, data_dir=SDD, pred_length=12, cache=False, seed=4)
+    sh = [x.numpy().copy() for x, *_ in c.prefetch_epoch(3, depth=1, shard=(1, 2))]
+    assert all(np.array_equal(s[0], g[0][1]) and s.shape[0] == 1 for s, g in zip(sh, got))
+    # leaving the generator early stops the thread
+    gen = a.prefetch_epoch(50, depth=1)
+    next(gen)
+    gen.close()

@@ -59,14 +59,12 @@ def test_cuda_reproduces_golden(path):
     got = {k: v.cpu().numpy() for k, v in out.items()}
     ioc = {k: gold.pop(k) for k in ("ioc_scores", "Y_refined")}
     assert not compare(got, gold, TOL)
-    # IOC outputs per (scene, sample) group: a log-polar bin flip (step function of the positions) may
-    # perturb single groups, see tests/test_gpu_parity.py
-    N, K = cfg.max_num_obj, cfg.K
-    for k, ref in ioc.items():
-        a = got[k].reshape(-1, B, N, K) if k == "ioc_scores" else got[k].reshape(1, B, N, K, -1)
-        r = ref.reshape(-1, B, N, K) if k == "ioc_scores" else ref.reshape(1, B, N, K, -1)
-        errs = [rel_l2(a[:, b, :, kk], r[:, b, :, kk]) for b in range(B) for kk in range(K)]
-        assert np.median(errs) <= TOL and np.mean(np.array(errs) <= TOL) >= 0.75, (k, errs)
+    # IOC outputs per (scene, sample) group: every group within TOL unless the oracle puts one of its pairs on a
+    # log-polar bin edge (helpers.check_ioc_groups; margins from a fresh oracle run of the same seeded inputs)
+    from helpers import check_ioc_groups
+    ref = oracle_forward(cfg, np_params(cfg), np_batch(cfg, B, 0, miss), np_tables(cfg), margins=True)
+    n, excused = check_ioc_groups(got, dict(ioc, bin_margin=ref["bin_margin"]), cfg, B)
+    assert excused <= max(1, n // 4)
 
 
 # ------------------------------------------------------------------------------------------ gradients (train step)

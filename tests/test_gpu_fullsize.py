@@ -5,27 +5,28 @@ pooling couples only the agents of one scene within one sample; nothing reduces 
 scalar cost).  So the rows of group (b, k) in a full-size run must equal what the CPU oracle computes for that
 scene alone with K=1 and that sample's eps — which the oracle finishes in seconds even at N=256/1024.  A handful
 of groups is checked per configuration:
-  cfg2  B=32 N=60  K=20 H=128            (the bench workload)
-  cfg3  B=16 N=256 K=20 H=256            (BASELINE configs[2] per-scene shape; fewer scenes to bound the test's HBM)
-  cfg5  B=2  N=512 K=4  H=128 T_f=40, 512x512 scene, 1 IOC iteration   (configs[4]-shaped: long horizon, big map, a
-        crowd that no longer fits the shared-memory pooling tile; N, K and the iteration count are reduced so the
-        NumPy oracle's O(N^2 G) pooling finishes in ~40 s per group)
-Tolerances: stage-1 tensors 1e-4 rel-L2 (north_star); IOC outputs 1e-4 with a single social bin (smooth), and with
-the 6x6 log-polar grid 5e-3 per group (a neighbour crossing a bin edge on a 1e-7 position difference perturbs that
-group, see test_gpu_parity.py)."""
+  cfg2  B=32 N=60   K=20 H=128                                  (BASELINE configs[1], the bench workload)
+  cfg3  B=64 N=256  K=20 H=256                                  (BASELINE configs[2] as written)
+  cfg5  B=1  N=1024 K=50 H=128 T_f=40, 512x512 scene, 2 IOC iterations   (BASELINE configs[4] as written, one GPU's scene;
+        the oracle pools the 1024-agent crowd with one BLAS product per step, ~2 min for the one group checked)
+Tolerances: stage-1 tensors 1e-4 rel-L2 (north_star); IOC outputs 1e-4 with a single social bin (smooth).  With the
+6x6 log-polar grid the bar is 1e-4 too unless the oracle's own trajectory puts a pair of that group within
+helpers.BIN_MARGIN of a bin edge (then a neighbour may land in the other bin on a 1e-7 position difference and the
+group is perturbed: 5e-3) — with 256 or 1024 agents (65 k .. 1 M pairs per step) some pair always is, see
+test_gpu_parity.py for the small-scene version where most groups are not."""
 import numpy as np
 import pytest
 import torch
 
-from helpers import TOL, np_params, np_tables, rel_l2, small_cfg
+from helpers import BIN_MARGIN, TOL, np_params, np_tables, rel_l2, small_cfg
 
 pytestmark = pytest.mark.gpu
 ONE_BIN = dict(n_rad=1, n_ang=1, r_min=1e-6, r_max=1e3)
 
 CASES = [
     ("cfg2", dict(d_dim=128, max_num_obj=60, num_samples=20, scene_size=256), 32, [(0, 0), (17, 7), (31, 19)]),
-    ("cfg3", dict(d_dim=256, max_num_obj=256, num_samples=20, scene_size=256), 16, [(0, 3), (15, 19)]),
-    ("cfg5", dict(d_dim=128, max_num_obj=512, num_samples=4, pred_length=40, scene_size=512, ioc_iters=1), 2, [(1, 2)]),
+    ("cfg3", dict(d_dim=256, max_num_obj=256, num_samples=20, scene_size=256), 64, [(0, 3), (63, 19)]),
+    ("cfg5", dict(d_dim=128, max_num_obj=1024, num_samples=50, pred_length=40, scene_size=512, ioc_iters=2), 1, [(0, 37)]),
 ]
 
 
@@ -47,7 +48,8 @@ def _oracle_group(cfg, host, b, k):
     P = np_params(cfg)
     r2, dirs = np_tables(cfg)
     e = eps.reshape(-1, N, cfg.K, cfg.Z)[b, :, k:k + 1]
-    return O.forward(P, dict(K=1, Z=cfg.Z, ioc_iters=cfg.ioc_iters), inp[b:b + 1], tgt[b:b + 1], e, scene[b:b + 1], r2, dirs)
+    return O.forward(P, dict(K=1, Z=cfg.Z, ioc_iters=cfg.ioc_iters, margins=True), inp[b:b + 1], tgt[b:b + 1], e,
+                     scene[b:b + 1], r2, dirs)
 
 
 def _group(t, B, N, K, b, k):
@@ -70,7 +72,9 @@ def test_group_slices_match_oracle(name, kw, B, groups, bins):
             e = rel_l2(_group(out[key], B, N, K, b, k).reshape(-1), np.asarray(ref[key]).reshape(-1))
             print("%s (b=%d,k=%d) %-16s rel-L2 %.3e" % (name, b, k, key, e))
             assert e <= TOL, (key, e)
-        tol = TOL if bins == "one_bin" else 5e-3
+        margin = float(np.asarray(ref["bin_margin"]).min())
+        tol = TOL if (bins == "one_bin" or margin >= BIN_MARGIN) else 5e-3
+        print("%s (b=%d,k=%d) oracle bin margin %.2e -> IOC tolerance %.0e" % (name, b, k, margin, tol))
         e = rel_l2(_group(out["Y_refined"], B, N, K, b, k).reshape(-1), np.asarray(ref["Y_refined"]).reshape(-1))
         print("%s (b=%d,k=%d) %-16s rel-L2 %.3e" % (name, b, k, "Y_refined", e))
         assert e <= tol, ("Y_refined", e)

@@ -4,8 +4,9 @@ Tolerance: rel-L2 <= 1e-4 (north_star) on every named tensor of the path.
 Log-polar social pooling is a step function of the positions: a 1e-6 difference in Y can move one
 neighbour across a bin edge and change one (scene, sample) group's IOC outputs by O(1e-3).  So
   * the whole path is compared strictly with a SINGLE social bin (no edges: everything is smooth);
-  * with the real 6x6 grid, stage 1 is compared strictly and the IOC outputs per (scene, sample) group:
-    the median group and at least 3/4 of the groups must meet 1e-4;
+  * with the real 6x6 grid, stage 1 is compared strictly and the IOC outputs per (scene, sample) group: EVERY group
+    must meet 1e-4 unless the oracle's own trajectory puts one of the group's pairs within 3e-6 of a bin edge
+    (helpers.check_ioc_groups; the margin comes from oracle.logpolar_margin);
   * the binning itself is compared EXACTLY in the stand-alone social-pool test (identical inputs)."""
 import ctypes as C
 
@@ -13,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import TOL, np_batch, np_params, np_tables, oracle_forward, rel_l2, small_cfg
+from helpers import TOL, check_ioc_groups, np_batch, np_params, np_tables, oracle_forward, rel_l2, small_cfg
 
 pytestmark = pytest.mark.gpu
 
@@ -60,21 +61,13 @@ def test_full_path_single_bin_strict(H, N, K, B, missing):
 def test_full_path_logpolar(H, N, K, B, missing):
     cfg = small_cfg(d_dim=H, max_num_obj=N, num_samples=K)
     got = run_gpu(cfg, B, n_missing=missing)
-    ref = oracle_forward(cfg, np_params(cfg), np_batch(cfg, B, n_missing=missing), np_tables(cfg))
+    ref = oracle_forward(cfg, np_params(cfg), np_batch(cfg, B, n_missing=missing), np_tables(cfg), margins=True)
     bad = strict(got, ref, STAGE1)
     assert not bad, bad
-    # IOC outputs per (scene b, sample k) group — the unit a bin flip can disturb
-    T = cfg.pred_length
-    y_g = got["Y_refined"].reshape(B, N, K, T * 2).transpose(0, 2, 1, 3).reshape(B * K, -1)
-    y_r = np.asarray(ref["Y_refined"]).reshape(B, N, K, T * 2).transpose(0, 2, 1, 3).reshape(B * K, -1)
-    s_g = got["ioc_scores"].reshape(-1, B, N, K).transpose(1, 3, 0, 2).reshape(B * K, -1)
-    s_r = np.asarray(ref["ioc_scores"]).reshape(-1, B, N, K).transpose(1, 3, 0, 2).reshape(B * K, -1)
-    for name, g, r in (("Y_refined", y_g, y_r), ("ioc_scores", s_g, s_r)):
-        errs = np.array([rel_l2(g[i], r[i]) for i in range(B * K)])
-        print("%-12s groups: median %.2e, within tol %d/%d, worst %.2e" % (name, np.median(errs), (errs <= TOL).sum(), len(errs), errs.max()))
-        assert np.median(errs) <= TOL
-        assert (errs <= TOL).mean() >= 0.75
-        assert errs.max() < 0.2          # a flipped group is perturbed, never garbage
+    # IOC outputs per (scene b, sample k) group — the unit a bin flip can disturb.  Every group must meet the bar
+    # unless the oracle itself says one of its pairs sits on a bin edge (helpers.check_ioc_groups).
+    n, excused = check_ioc_groups(got, ref, cfg, B)
+    assert excused <= max(1, n // 4), "too many groups on a bin edge for this to be rounding: %d / %d" % (excused, n)
 
 
 def _ptr(t):

@@ -87,3 +87,23 @@ def test_flatten_params_views_alias_one_aligned_flat_buffer():
     views["output_b"].add_(1.0)                                         # writes go through to the flat buffer
     o, cnt, _ = offs["output_b"]
     assert torch.equal(flat[o:o + cnt], views["output_b"].reshape(-1))
+
+
+def test_config_raises_on_flags_the_build_does_not_implement():
+    # reference flags that change semantics (train.py:32,34,86; model/model.py:48,130,137-141) must not be dropped silently
+    for kw in (dict(stride=2), dict(num_layers=2), dict(model="lstm"), dict(model="rnn")):
+        with pytest.raises(ValueError):
+            DesireConfig(**kw).validate()
+    DesireConfig(stride=1, num_layers=1, model="gru").validate()
+
+
+def test_vae_layers_reject_inference_phase_and_other_activations():
+    # model/model.py:457-462,476-481 pass phase=train + ELU; anything else is not what the kernels compute
+    from desire_b200.model.model import DESIREModel
+    chk = DESIREModel._check_activ_phase
+    chk("vae_encoder", None, None)
+    chk("vae_encoder", type("elu", (), {"__name__": "elu"}), "train")
+    with pytest.raises(ValueError):
+        chk("vae_decoder", None, "infer")
+    with pytest.raises(ValueError):
+        chk("vae_decoder", "relu", None)
