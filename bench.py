@@ -5,8 +5,12 @@
     python bench.py --impl reference --steps K --warmup W     # the reference's algorithm on host cores
 
 A "step" is one pass of the hot path (a2-a14: CVAE sample generation, then `ioc_iters` iterations of
-IOC ranking/refinement) over one synthetic minibatch of BASELINE.json configs[1]'s shape
-(B=32 scenes x N=60 agents x K=20 samples, H=128, Z=128, T_p=8, T_f=12).  One JSON line on stdout.
+IOC ranking/refinement) over one synthetic minibatch.  `--config` picks the BASELINE.json workload:
+    cfg2 (default, the headline)  configs[1]/[3] shape: B=32 scenes x N=60 agents x K=20 samples, H=128, T_f=12
+    cfg3                          configs[2]: B=64 x N=256 x K=20, H=256 (GRU-GEMM tensor-core roofline)
+    cfg5                          configs[4]: N=1024 agents, K=50, T_f=40, 512x512 scene map, one scene per GPU
+`--scaling strong` keeps the GLOBAL minibatch at --scenes and gives every rank scenes/N of it (configs[3] as written:
+"minibatch-sharded over 8xB200"); the default is weak scaling (every rank owns --scenes scenes).  One JSON line on stdout.
 """
 from __future__ import annotations
 
@@ -26,26 +30,51 @@ METRIC = "agent-samples/sec (NxK, T_fut=12), sample-generate + rank-refine"
 UNIT = "agent-samples/s"
 
 
+PRESETS = {
+    "cfg2": dict(scenes=32, agents=60, samples=20, hidden=128, latent=128, pred_length=12, ioc_iters=2, scene_size=256,
+                 what="BASELINE configs[1] (and configs[3] under --scaling strong) shape"),
+    "cfg3": dict(scenes=64, agents=256, samples=20, hidden=256, latent=128, pred_length=12, ioc_iters=2, scene_size=256,
+                 what="BASELINE configs[2] (GRU-GEMM tensor-core roofline) as written"),
+    "cfg5": dict(scenes=1, agents=1024, samples=50, hidden=128, latent=128, pred_length=40, ioc_iters=2, scene_size=512,
+                 what="BASELINE configs[4] (social-pool scatter + scene-feature gather stress) as written, one scene per GPU"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    # workload = BASELINE.json configs[1] shape
-    ap.add_argument("--scenes", type=int, default=32, help="B, scenes per GPU per step")
-    ap.add_argument("--agents", type=int, default=60)
-    ap.add_argument("--samples", type=int, default=20)
-    ap.add_argument("--hidden", type=int, default=128)
-    ap.add_argument("--latent", type=int, default=128)
-    ap.add_argument("--pred-length", type=int, default=12)
-    ap.add_argument("--ioc-iters", type=int, default=2)
-    ap.add_argument("--scene-size", type=int, default=256)
+    ap.add_argument("--config", default="cfg2", choices=sorted(PRESETS), help="BASELINE.json workload preset")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --scenes per GPU; strong: --scenes in total, scenes/N per GPU (BASELINE configs[3])")
+    # any of these overrides the preset
+    ap.add_argument("--scenes", type=int, default=None, help="B, scenes per step (per GPU when weak, in total when strong)")
+    ap.add_argument("--agents", type=int, default=None)
+    ap.add_argument("--samples", type=int, default=None)
+    ap.add_argument("--hidden", type=int, default=None)
+    ap.add_argument("--latent", type=int, default=None)
+    ap.add_argument("--pred-length", type=int, default=None)
+    ap.add_argument("--ioc-iters", type=int, default=None)
+    ap.add_argument("--scene-size", type=int, default=None)
     ap.add_argument("--cpu-sample-scenes", type=int, default=1, help="scenes per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step timing block")
     ap.add_argument("--breakdown", default="", help="write the per-kernel timing table to this file")
-    return ap.parse_args()
+    a = ap.parse_args()
+    preset = PRESETS[a.config]
+    a.overridden = [k for k in preset if k != "what" and getattr(a, k) is not None]
+    for k, v in preset.items():
+        if getattr(a, k, None) is None:
+            setattr(a, k, v)
+    a.scenes_global = a.scenes
+    if a.scaling == "strong":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if a.scenes % world:
+            raise SystemExit("bench.py: --scaling strong needs --scenes (%d) divisible by the number of ranks (%d)" % (a.scenes, world))
+        a.scenes = a.scenes // world
+    return a
 
 
 def make_cfg(a):
@@ -58,12 +87,13 @@ def make_cfg(a):
 
 def workload_config(a, cfg, extra):
     d = {
-        "workload": "BASELINE configs[1] shape, synthetic: B=%d scenes x N=%d agents x K=%d samples, H=%d, Z=%d, "
+        "workload": "%s%s, synthetic: B=%d scenes per GPU x N=%d agents x K=%d samples, H=%d, Z=%d, "
                     "T_p=%d, T_f=%d, scene %dx%dx3, ioc_iters=%d; one step = CVAE sample generation + IOC "
-                    "rank/refine (forward pass of the path)" % (a.scenes, a.agents, a.samples, a.hidden, a.latent,
-                                                                cfg.seq_length, cfg.pred_length, a.scene_size,
-                                                                a.scene_size, a.ioc_iters),
-        "scenes_per_gpu": a.scenes, "agents": a.agents, "samples": a.samples, "hidden": a.hidden,
+                    "rank/refine (forward pass of the path)" % (
+                        PRESETS[a.config]["what"], (" with overrides %s" % a.overridden) if a.overridden else "",
+                        a.scenes, a.agents, a.samples, a.hidden, a.latent, cfg.seq_length, cfg.pred_length, a.scene_size,
+                        a.scene_size, a.ioc_iters),
+        "preset": a.config, "scenes_per_gpu": a.scenes, "scenes_global": a.scenes_global if a.scaling == "strong" else None, "agents": a.agents, "samples": a.samples, "hidden": a.hidden,
         "latent": a.latent, "T_past": cfg.seq_length, "T_fut": cfg.pred_length, "ioc_iters": a.ioc_iters,
         "scene_size": a.scene_size, "log_polar_bins": cfg.G,
     }
@@ -122,7 +152,7 @@ def reference_arm(a):
         a.cpu_sample_scenes, a.agents, a.samples, units)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, cfg, {"note": "reference TF1 graph cannot run (SURVEY.md 0.4); this is the "
                                                    "oracle port of its algorithm on the host cores"}),
@@ -212,8 +242,15 @@ def ours_arm(a):
     import torch
     import torch.distributed as dist
     from desire_b200 import _lib
+    from desire_b200.dist import global_masked_cost
     from desire_b200.model.model import DESIREModel
     from desire_b200.synthetic import make_batch
+
+    def _sum_over_ranks(x, world):
+        t = x.detach().clone().double().reshape(1)
+        if world > 1:
+            dist.all_reduce(t)
+        return t
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -296,20 +333,32 @@ def ours_arm(a):
     dev_ms_max = float(t.item())
     value = R_local * world * steps / (dev_ms_max / 1e3)
 
-    # ---- end to end through the public API with host buffers (pinned staging inside the model)
+    # ---- end to end through the public API with HOST buffers: DESIREModel.submit()/result(), the serving loop.  Per
+    # step inside the timed region: numpy inputs -> pinned staging -> H2D (observations, targets, scene images), the
+    # CUDA graphs (eps is drawn on the device, as the reference draws it inside its graph, model/model.py:262), D2H of
+    # the refined trajectories + scores + cost, and reading them on the host.  Pass t+1 is submitted before pass t is
+    # collected (two staging / result slots), so the host-side staging overlaps the GPU work of the previous pass.
     host_np = [x.numpy() for x in host]
-    for _ in range(2):
-        model.sample_and_rank(*host_np)
+    inp_np, tgt_np, scene_np = host_np[0], host_np[1], host_np[3]
+    for _ in range(3):
+        model.sample_and_rank(inp_np, tgt_np, None, scene_np)
     barrier()
     t0 = time.perf_counter()
+    pending, checksum = None, 0.0
     for _ in range(steps):
-        y, sc, cost = model.sample_and_rank(*host_np)
+        h = model.submit(inp_np, tgt_np, None, scene_np, seed=7)
+        if pending is not None:
+            y, sc, cost = model.result(pending)
+            checksum += float(sc[-1].max()) + cost            # the host reads the result
+        pending = h
+    y, sc, cost = model.result(pending)
+    checksum += float(sc[-1].max()) + cost
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = R_local * world * steps / float(te.item())
-    h2d = sum(x.nbytes for x in host_np)
+    h2d = inp_np.nbytes + tgt_np.nbytes + scene_np.nbytes
     d2h = y.nbytes + sc.nbytes + 8
 
     # ---- train step (D9): forward of the sample-generation stage + backward of `cost` + all-reduce + clip + Adam,
@@ -336,7 +385,10 @@ def ours_arm(a):
                  "what": "full CVAE+IOC train step: sample-generation forward, backward of cost, IOC forward + D13 loss + "
                          "backward (ioc_iters=%d), scene-CNN backward, %sclip_by_global_norm + Adam over %d parameters"
                          % (cfg.ioc_iters, "NCCL all-reduce of the flat gradient, " if world > 1 else "", tp.flat.numel()),
-                 "cost_after": float(tp.buf["cost"][0]), "ioc_cost_after": float(tp.buf["ioc_cost"][0])}
+                 # both all-reduced: cost = sum_ranks(cost_r * n_r) / sum_ranks(n_r); ioc_cost is already divided by
+                 # the GLOBAL agent count on every rank, so the global value is the plain sum over ranks
+                 "cost_after": float(global_masked_cost(tp.buf["cost"][0] * tp.buf["cost"][1], tp.buf["cost"][1])),
+                 "ioc_cost_after": float(_sum_over_ranks(tp.buf["ioc_cost"][0], world))}
 
     if rank != 0:
         if world > 1:
@@ -383,9 +435,12 @@ def ours_arm(a):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, cfg, {"parallelism": "scenes sharded over %d GPU(s), no data-path collective" % world,
+        "config": workload_config(a, cfg, {"parallelism": ("scenes sharded over %d GPU(s), no data-path collective" % world) + (
+                                               "; strong scaling: the global minibatch of %d scenes is split, %d per GPU"
+                                               % (a.scenes_global, a.scenes) if a.scaling == "strong" else
+                                               "; weak scaling: every GPU owns %d scenes" % a.scenes),
                                            "l2": "flushed (256 MiB memset) before every timed step; timed with CUDA "
                                                  "events per step, max over ranks",
                                            "launch": "one CUDA-graph replay per step (%d kernels of the library inside); "
@@ -395,7 +450,9 @@ def ours_arm(a):
                                                      % launches_per_step,
                                            "wall_s_timed_region": t_wall}),
         "clocks": clk,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "DESIREModel.submit()/result() with numpy inputs, depth-2 pipeline; eps drawn on the device "
+                       "(desire_randn_fwd inside the decoder graph)", "result_checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "kernels": rows[:8],

@@ -101,6 +101,8 @@ SIGNATURES = {
     "desire_kld_rows_fwd": (I, [P, I, I, P, P]),
     "desire_recon_rows_fwd": (I, [P, P, I, I, I, P, P]),
     "desire_masked_cost_fwd": (I, [P, P, P, I, I, P, P]),
+    "desire_existence_fwd": (I, [P, P, I, I, I, I, P, P]),
+    "desire_randn_fwd": (I, [P, P, Z, P]),
     "desire_scene_cnn_workspace_bytes": (Z, [I, I, I]),
     "desire_scene_cnn_fwd": (I, [P, I, I, I, I, C.POINTER(SceneCnnW), P, P, Z, P]),
     "desire_scene_gather_fwd": (I, [P, I, I, I, I, P, L, I, P, I, P]),

@@ -36,6 +36,8 @@ class DesireConfig:
     r_min: float = 0.01
     r_max: float = 0.5
     channel_multiplier: int = 100  # model.py:46
+    exist_mode: int = 1            # D8: 1 = an agent exists if present at observed frame 0, at the last observed frame and
+                                   # at every target frame (obj_id / target_obj_id of model.py:351-366); 0 = frame 0 only
 
     @property
     def H(self):

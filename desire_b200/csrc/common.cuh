@@ -246,7 +246,8 @@ struct GruSeqArgs {
   long hs_row_stride, hs_step_stride;
   float* h_final;           // [R] rows, stride ld_hf, or null
   int ld_hf;
-  const void* packed = nullptr;   // optional: weights already packed by gru_tc_pack (skips per-call packing)
+  const void* packed = nullptr;   // optional: weights already packed (skips per-call packing) ...
+  int packed_fmt = 0;             // ... by gru_tc_pack (0, n-tile 2H) or gru_tc3_pack (3, n-tile H)
 };
 int gru_tc_pack(const float* w_g, const float* w_c, int H, int Ka, void* ws, size_t ws_bytes, cudaStream_t st);
 int gru_seq(const GruSeqArgs& a, cudaStream_t st, PackWs pw = PackWs());
@@ -258,10 +259,11 @@ size_t gru_tc_pack_bytes(int H, int Ka = 0);
 bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes);
 int gru_seq_tc(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
 
-// third design of the tcgen05 recurrence (gru_tc3.cu): register-resident state, TMA-staged xp, phases overlapped with
-// the MMA groups; H in {128, 256}, no extra operand.  Weights packed with n-tile = H.
-size_t gru_tc3_pack_bytes(int H);
-int gru_tc3_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st);
+// third design of the tcgen05 recurrence (gru_tc3.cu): register-resident state, TMA-staged per-row inputs, phases
+// overlapped with the MMA groups; H in {128, 256} without extra operand, H = 128 with it (one Decoder-2 step).
+// Weights packed with n-tile = H.
+size_t gru_tc3_pack_bytes(int H, int Ka = 0);
+int gru_tc3_pack(const float* w_g, const float* w_c, int H, int Ka, void* ws, size_t ws_bytes, cudaStream_t st);
 bool gru_tc3_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes);
 int gru_seq_tc3(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
 

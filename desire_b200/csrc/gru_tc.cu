@@ -359,7 +359,7 @@ bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes
   if (a.H % 32 != 0 || a.H < 32 || a.H > 256) return false;
   if (a.ex ? (a.Ka != a.H || a.T != 1 || a.ld_ex % 4 != 0) : a.Ka != 0) return false;
   if (a.T > 1 && !a.hs) return false;
-  if (!a.packed && (!pack_ws || pack_bytes < gru_tc_pack_bytes(a.H, a.Ka))) return false;
+  if (a.packed ? a.packed_fmt != 0 : (!pack_ws || pack_bytes < gru_tc_pack_bytes(a.H, a.Ka))) return false;
   const Shape s = shape_of(a.H, a.Ka);
   return s.smem <= 227 * 1024 && s.nthr <= 1024 && a.R >= 64;
 }

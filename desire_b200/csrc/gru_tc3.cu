@@ -1,6 +1,6 @@
 // Persistent tcgen05 GRU recurrence, third design (TF-1.x GRUCell, reference model/model.py:137-148,279-285):
 //
-//   r = sigmoid(xp_r + h @ Wr)     u = sigmoid(xp_u + h @ Wu)     c = tanh(xp_c + (r*h) @ Wc)     h' = u*h + (1-u)*c
+//   r = sigmoid(xp_r + [ex,h] @ Wr)   u = sigmoid(xp_u + [ex,h] @ Wu)   c = tanh(xp_c + [ex, r*h] @ Wc)   h' = u*h + (1-u)*c
 //
 // What the ncu capture of the second design showed (profiles/r1i_ncu_summaries.txt: tensor pipe 12-19 %, 69 % of the
 // warp stalls on the long scoreboard): the epilogue threads own one row each (that is how tcgen05.ld hands out the
@@ -9,20 +9,24 @@
 // from global memory twice per step; the four phases of a step ran strictly one after the other.  This design:
 //
 //   * state in registers: a thread keeps the FP32 h of its (row, HC columns) for the whole kernel;
-//   * the hoisted input projection xp arrives by TMA: 2-D tensor-map copies (cp.async.bulk.tensor, SASS UTMALDG) of
-//     [128 rows x 32 columns] boxes with the 128-byte swizzle into a small ring, issued by a loader thread that runs
-//     ahead of the epilogues; a thread reads its row's 128 bytes as eight conflict-free 16-byte loads;
+//   * every per-row input arrives by TMA: 2-D tensor-map copies (cp.async.bulk.tensor, SASS UTMALDG) of
+//     [128 rows x 32 columns] FP32 boxes with the 128-byte swizzle into a small ring, issued by a loader thread that
+//     runs ahead of the epilogues — the hoisted input projection xp (three boxes per 32 columns and step) and, in the
+//     Decoder-2 form (EX), the extra operand and the initial state; a thread reads its row's 128 bytes as eight
+//     conflict-free 16-byte loads.  A box is announced on the full-barrier of the COLUMN GROUP that consumes it
+//     (each group sees every phase of its own barrier in order; a per-slot barrier shared by groups that alternate on
+//     the slot cannot be waited on by parity), and released on the empty-barrier of its ring slot;
 //   * a step is three MMA groups — r columns, u columns, candidate — and three epilogue phases that each run in the
 //     shadow of the next MMA group:
 //         MMA     | r(t)        | u(t)              | cand(t)             | (idle)        | r(t+1) ...
 //         SIMT    |  E2b(t-1)   | E1: r, r*h -> A   | E2a: u -> TMEM      | E2b: c, h'    |
 //     E1 overwrites the A operand chunk by chunk behind the u-group (a_free[kc] is committed after the u-group's MMAs
 //     on K chunk kc), E2a parks sigmoid(u) in the u columns of TMEM, and only E2b (tanh + blend) is exposed;
-//   * with H = 128 the candidate has its own TMEM columns, so the next step's r-group starts on the K chunks of h'
+//   * when the candidate has its own TMEM columns (3H <= 512) the next step's r-group starts on the K chunks of h'
 //     as they are produced (h_ready[kc]); with H = 256 the gates fill all 512 columns, the candidate re-uses the r
 //     columns and the r-group waits for the whole tile;
-//   * recurrent weights: the packed BF16 hi/lo images of gru_tc_pack (n-tile = H) streamed through a ring of 16 KB
-//     slots by 1-D bulk copies with an evict-last L2 hint.
+//   * recurrent weights: packed BF16 hi/lo images (tc_pack_b, n-tile = H) streamed through a ring of 16 KB slots by
+//     1-D bulk copies with an evict-last L2 hint.
 //
 // 3xBF16 (A_hi B_hi + A_lo B_hi + A_hi B_lo, FP32 accumulation in TMEM) as everywhere else in the library.
 #include <cuda.h>
@@ -39,61 +43,61 @@ namespace {
 using namespace tc;
 
 constexpr int TM = 128;
-constexpr int XBOX_BYTES = TM * 32 * 4;   // one xp box: 128 rows x 32 FP32 columns, 128-byte rows
+constexpr int XBOX_BYTES = TM * 32 * 4;   // one box: 128 rows x 32 FP32 columns, 128-byte rows
 constexpr int EPI_WARPS = 16;             // 4 TMEM lane quadrants x 4 column groups
 constexpr int NTHR3 = (EPI_WARPS + 4) * 32;   // + one warpgroup: MMA issuer, loader, two idle warps (setmaxnreg is per warpgroup)
 
-template <int H>
+template <int H, bool EX>
 struct Cfg3 {
   static constexpr int HC = H / 4;                     // columns per epilogue thread
-  static constexpr int NB = HC / 32;                   // 32-column chunks (= xp boxes per gate) per thread
-  static constexpr int NKC = H / 32;                   // K chunks of the A operand
+  static constexpr int NB = HC / 32;                   // 32-column chunks (= boxes per gate) per thread
+  static constexpr int NKC = H / 32;                   // K chunks of the state part of the A operand
+  static constexpr int NKA = EX ? 2 * NKC : NKC;       // K chunks of the whole A operand: [ex | h]
+  static constexpr int KOFF = EX ? NKC : 0;            // first chunk of the state part
   static constexpr int KSLOT = (H >= 256) ? 16 : 32;   // K extent of one weight slot
   static constexpr int SPC = 32 / KSLOT;               // slots per K chunk
   static constexpr int SLOT_HALF = (KSLOT / 8) * H * 16;
   static constexpr int SLOT_BYTES = 2 * SLOT_HALF;     // hi + lo: 16 KB for both sizes
   static constexpr int BLOCK_BYTES = 2 * 4 * H * 16;   // one packed (n-tile, 32-wide K) block of tc_pack_b
-  static constexpr int NSW = (H >= 256) ? 4 : 6;       // weight ring slots
-  static constexpr int NXB = (H >= 256) ? 2 : 4;       // xp ring boxes
-  static constexpr int A_HALF = (H / 8) * 2048;        // [H/8 chunks][128 rows][16 B]
+  static constexpr int NSW = (H >= 256 || EX) ? 4 : 6; // weight ring slots
+  static constexpr int NXB = (H >= 256 || EX) ? 2 : 4; // box ring slots (<= 4: one box in flight per column group)
+  static constexpr int A_HALF = NKA * 4 * 2048;        // [K/8 chunks][128 rows][16 B]
   static constexpr bool ALIAS = (3 * H > 512);         // candidate accumulates in the consumed r columns
   static constexpr int CAND_COL = ALIAS ? 0 : 2 * H;
-  static constexpr int BPS = 3 * NKC;                  // xp boxes per step: r | u | c, each in (chunk-in-thread, column group) order
-  static constexpr int WPS = 3 * NKC * SPC;            // weight slots per step
-  static constexpr int NBAR = 2 * NSW + 2 * NXB + 4 + 2 * NKC;
+  static constexpr int PRO = EX ? 2 * NKC : 0;         // prologue boxes: ex, then h0 (each in (chunk-in-thread, group) order)
+  static constexpr int BPS = 3 * NKC;                  // boxes per step: xp_r | xp_u | xp_c
+  static constexpr int WPS = 3 * NKA * SPC;            // weight slots per step
+  static constexpr int NBAR = 2 * NSW + 4 + NXB + 4 + NKA + NKC;
   static constexpr size_t SMEM = 1024 + 2 * (size_t)A_HALF + (size_t)NSW * SLOT_BYTES + (size_t)NXB * XBOX_BYTES + NBAR * 8 + 16;
+  static_assert(NXB <= 4, "a column group may have one box in flight");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 struct Gru3Args {
   int R, T;
   int xp_step;          // column offset of step t inside an xp row = t * xp_step
-  const float* h0;
+  const float* h0;      // non-EX: read directly (rows shared by h0_div samples); EX: through tm_h0
   int h0_div, ld_h0;
   float* hs;
   long hs_row_stride, hs_step_stride;
   float* h_final;
   int ld_hf;
-  const uint8_t* wg;    // packed gates, n-tile H: [2][H/32] blocks (r columns, then u columns)
-  const uint8_t* wc;    // packed candidate: [H/32] blocks
+  const uint8_t* wg;    // packed gates, n-tile H: [2][K/32] blocks (r columns, then u columns)
+  const uint8_t* wc;    // packed candidate: [K/32] blocks
   int passes;
   int xp_const;         // 1: the same xp every step (Decoder-1) -> keep it in L2
-  int dbg;              // timing experiments only (DESIRE_GRU3_DBG): 1 = no xp copies, 2 = no weight copies (results are wrong)
+  int dbg;              // timing experiments only (DESIRE_GRU3_DBG): 1 = no box copies, 2 = no weight copies (results are wrong)
 };
 
 __device__ __forceinline__ float4 lds128(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
 
-// Wait for fill number `phase` (0-based) of an xp ring slot.  The fills of one slot are consumed by up to two column
-// groups in alternation, so a group can reach its wait while the slot is still one fill short of the one before its
-// own — and a parity wait cannot tell fill p-1 pending from fill p+1 pending.  Waiting for fill p-1 first (it is this
-// group's predecessor in the slot, or already long complete) removes the ambiguity.
-__device__ __forceinline__ void xbox_wait(uint64_t* bar, uint32_t phase) {
-  mbar_wait(bar, (phase & 1) ^ 1);
-  mbar_wait(bar, phase & 1);
-}
-
-template <int H>
-__global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant__ CUtensorMap tm_xp, Gru3Args a) {
-  using C = Cfg3<H>;
+// WD: watchdog on every mbarrier wait (DESIRE_GRU3_WATCHDOG=1; the tests set it) — a protocol error traps with the
+// name of the barrier instead of hanging the device.
+template <int H, bool EX, bool WD>
+__global__ void __launch_bounds__(NTHR3, 1)
+    gru_tc3_kernel(const __grid_constant__ CUtensorMap tm_xp, const __grid_constant__ CUtensorMap tm_ex,
+                   const __grid_constant__ CUtensorMap tm_h0, Gru3Args a) {
+  using C = Cfg3<H, EX>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzled boxes need 1024-byte alignment
   uint8_t* xring = smem;                                             // [NXB] boxes, each 1024-aligned
@@ -102,14 +106,14 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
   uint8_t* wring = a_lo + C::A_HALF;
   uint64_t* wfull = reinterpret_cast<uint64_t*>(wring + (size_t)C::NSW * C::SLOT_BYTES);
   uint64_t* wempty = wfull + C::NSW;
-  uint64_t* xfull = wempty + C::NSW;
-  uint64_t* xempty = xfull + C::NXB;
+  uint64_t* xfull = wempty + C::NSW;      // [4]   one per column group: "your next box has landed"
+  uint64_t* xempty = xfull + 4;           // [NXB] one per ring slot
   uint64_t* g_r_done = xempty + C::NXB;
   uint64_t* g_u_done = g_r_done + 1;
   uint64_t* c_done = g_u_done + 1;
   uint64_t* rh_ready = c_done + 1;
-  uint64_t* h_ready = rh_ready + 1;       // [NKC]
-  uint64_t* a_free = h_ready + C::NKC;    // [NKC]
+  uint64_t* h_ready = rh_ready + 1;       // [NKA]  A chunk kc holds its operand for the gate groups
+  uint64_t* a_free = h_ready + C::NKA;    // [NKC]  the u-group has read state chunk kc
   uint32_t* tslot = reinterpret_cast<uint32_t*>(a_free + C::NKC);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -120,29 +124,33 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
       mbar_init(&wfull[s], 1);
       mbar_init(&wempty[s], 1);
     }
-    for (int s = 0; s < C::NXB; ++s) {
-      mbar_init(&xfull[s], 1);
-      mbar_init(&xempty[s], 4);           // the four quadrant warps of the column group that reads the box
-    }
+    for (int s = 0; s < 4; ++s) mbar_init(&xfull[s], 1);
+    for (int s = 0; s < C::NXB; ++s) mbar_init(&xempty[s], 4);   // the four quadrant warps of the group that read the box
     mbar_init(g_r_done, 1);
     mbar_init(g_u_done, 1);
     mbar_init(c_done, 1);
     mbar_init(rh_ready, EPI_WARPS);
-    for (int k = 0; k < C::NKC; ++k) {
-      mbar_init(&h_ready[k], 4);
-      mbar_init(&a_free[k], 1);
-    }
+    for (int k = 0; k < C::NKA; ++k) mbar_init(&h_ready[k], 4);
+    for (int k = 0; k < C::NKC; ++k) mbar_init(&a_free[k], 1);
     fence_barrier_init();
   }
   if (warp == EPI_WARPS) tmem_alloc<512>(tslot);
-  if (warp == EPI_WARPS + 1 && lane == 0) tma_prefetch_desc(&tm_xp);
+  if (warp == EPI_WARPS + 1 && lane == 0) {
+    tma_prefetch_desc(&tm_xp);
+    if (EX) {
+      tma_prefetch_desc(&tm_ex);
+      tma_prefetch_desc(&tm_h0);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
 
   // 640 threads launch with 96 registers each; the last warpgroup (two single-thread roles) gives most of its share
-  // back so the epilogue threads can hold 64 FP32 state values next to a 16-column working set
+  // back so the epilogue threads can hold 64 FP32 state values next to an 8-column working set.  (setmaxnreg is
+  // .aligned: every warp of a warpgroup must execute the SAME instruction, so the release sits before the role split.)
+  if (warp >= EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
   if (warp < EPI_WARPS) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ======================================================================== epilogue warps
@@ -154,10 +162,51 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     uint8_t* my_hi = a_hi + rloc * 16;
     uint8_t* my_lo = a_lo + rloc * 16;
+    uint64_t* my_full = &xfull[cs];
     float h[C::HC];
+    uint32_t xk = 0;                                 // boxes this column group has consumed (phase of my_full)
+    uint32_t xg = cs;                                // ring position of this group's next box: they are 4 apart
 
-    // ---- initial state: registers + A operand
-    {
+    // Wait for this group's next box; returns its ring slot.  The loader issues boxes in ring order and a group's
+    // boxes are every fourth one, so the slot sequence is a function of the running position alone.
+    auto next_box = [&](int tag) -> int {
+      mbar_wait_tag<WD>(my_full, xk & 1, tag);
+      const int slot = xg % C::NXB;
+      ++xk;
+      xg += 4;
+      return slot;
+    };
+
+    // ---- prologue: extra operand and initial state -> registers + A operand
+    if (EX) {
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {         // 0: ex -> chunks [0,NKC), 1: h0 -> registers + chunks [NKC,2NKC)
+#pragma unroll
+        for (int j = 0; j < C::NB; ++j) {
+          const int kc = part * C::NKC + cs * C::NB + j;
+          const int slot = next_box(70 + part);
+          const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
+            float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            if (part == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[j * 32 + g8 * 8 + i] = v[i];
+            }
+            const Split8 s = split8(v);
+            *reinterpret_cast<uint4*>(my_hi + (kc * 4 + g8) * 2048) = s.hi;
+            *reinterpret_cast<uint4*>(my_lo + (kc * 4 + g8) * 2048) = s.lo;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&xempty[slot]);
+            mbar_arrive(&h_ready[kc]);
+          }
+        }
+      }
+    } else {
       const float* h0r = (a.h0 && ok) ? a.h0 + (row / a.h0_div) * (long)a.ld_h0 + cbeg : nullptr;
 #pragma unroll
       for (int c = 0; c < C::HC; c += 4) {
@@ -182,16 +231,13 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
 
     for (int t = 0; t < a.T; ++t) {
       const uint32_t par = t & 1;
-      const uint32_t gbase = (uint32_t)t * C::BPS;
       // ---------------- E1 (behind the u-group): r = sigmoid(.), r*h replaces h in the A operand
-      mbar_wait(g_r_done, par);
+      mbar_wait_tag<WD>(g_r_done, par, 10);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < C::NB; ++j) {
-        const int kc = cs * C::NB + j;
-        const uint32_t g = gbase + j * 4 + cs;
-        const int slot = g % C::NXB;
-        xbox_wait(&xfull[slot], g / C::NXB);
+        const int kc = cs * C::NB + j;               // chunk of the state (0-based inside the state part)
+        const int slot = next_box(60);
         const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {               // 8 columns = one 16-byte chunk of the A operand
@@ -208,10 +254,10 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
           acc[5] = sigmoid_a(acc[5] + x1.y) * h[hc + 5];
           acc[6] = sigmoid_a(acc[6] + x1.z) * h[hc + 6];
           acc[7] = sigmoid_a(acc[7] + x1.w) * h[hc + 7];
-          if (g8 == 0) mbar_wait(&a_free[kc], par);     // the u-group's MMAs have read h chunk kc
+          if (g8 == 0) mbar_wait_tag<WD>(&a_free[kc], par, 20 + kc);     // the u-group's MMAs have read h chunk kc
           const Split8 s = split8(acc);
-          *reinterpret_cast<uint4*>(my_hi + (kc * 4 + g8) * 2048) = s.hi;
-          *reinterpret_cast<uint4*>(my_lo + (kc * 4 + g8) * 2048) = s.lo;
+          *reinterpret_cast<uint4*>(my_hi + ((C::KOFF + kc) * 4 + g8) * 2048) = s.hi;
+          *reinterpret_cast<uint4*>(my_lo + ((C::KOFF + kc) * 4 + g8) * 2048) = s.lo;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&xempty[slot]);
@@ -222,14 +268,12 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
       if (lane == 0) mbar_arrive(rh_ready);
 
       // ---------------- E2a (behind the candidate group): u = sigmoid(.) parked in its TMEM columns
-      mbar_wait(g_u_done, par);
+      mbar_wait_tag<WD>(g_u_done, par, 11);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < C::NB; ++j) {
         const int kc = cs * C::NB + j;
-        const uint32_t g = gbase + C::NKC + j * 4 + cs;
-        const int slot = g % C::NXB;
-        xbox_wait(&xfull[slot], g / C::NXB);
+        const int slot = next_box(62);
         const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -253,16 +297,14 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
       tmem_st_wait();
 
       // ---------------- E2b (exposed): candidate, state update, h' -> registers, HBM and the A operand
-      mbar_wait(c_done, par);
+      mbar_wait_tag<WD>(c_done, par, 12);
       tc_fence_after();
       float* hout = (ok && a.hs) ? a.hs + row * a.hs_row_stride + (long)t * a.hs_step_stride + cbeg : nullptr;
       float* hfin = (ok && a.h_final && t == a.T - 1) ? a.h_final + row * (long)a.ld_hf + cbeg : nullptr;
 #pragma unroll
       for (int j = 0; j < C::NB; ++j) {
         const int kc = cs * C::NB + j;
-        const uint32_t g = gbase + 2 * C::NKC + j * 4 + cs;
-        const int slot = g % C::NXB;
-        xbox_wait(&xfull[slot], g / C::NXB);
+        const int slot = next_box(64);
         const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -288,20 +330,19 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
             *reinterpret_cast<float4*>(hfin + hc + 4) = make_float4(h[hc + 4], h[hc + 5], h[hc + 6], h[hc + 7]);
           }
           const Split8 s = split8(&h[hc]);
-          *reinterpret_cast<uint4*>(my_hi + (kc * 4 + g8) * 2048) = s.hi;
-          *reinterpret_cast<uint4*>(my_lo + (kc * 4 + g8) * 2048) = s.lo;
+          *reinterpret_cast<uint4*>(my_hi + ((C::KOFF + kc) * 4 + g8) * 2048) = s.hi;
+          *reinterpret_cast<uint4*>(my_lo + ((C::KOFF + kc) * 4 + g8) * 2048) = s.lo;
         }
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&xempty[slot]);
-          mbar_arrive(&h_ready[kc]);
+          mbar_arrive(&h_ready[C::KOFF + kc]);
         }
       }
     }
   } else if (warp == EPI_WARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     // ======================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(TM, H);
@@ -314,25 +355,26 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
         for (int nb = 0; nb < 3; ++nb) {          // r columns, u columns, candidate
           const uint32_t d = tmem + (nb == 0 ? 0 : (nb == 1 ? H : C::CAND_COL));
           if (nb == 2) {
-            mbar_wait(rh_ready, par);
+            mbar_wait_tag<WD>(rh_ready, par, 30);
             tc_fence_after();
           }
           uint32_t accf = 0;
 #pragma unroll 1
-          for (int kc = 0; kc < C::NKC; ++kc) {
+          for (int kc = 0; kc < C::NKA; ++kc) {
             if (nb == 0) {
+              // the extra-operand chunks are written once (phase 0); state chunk phases advance every step
               if (C::ALIAS) {                      // the r columns still hold the candidate the epilogues are reading
                 if (kc == 0)
-                  for (int k = 0; k < C::NKC; ++k) mbar_wait(&h_ready[k], par);
+                  for (int k = 0; k < C::NKA; ++k) mbar_wait_tag<WD>(&h_ready[k], k < C::KOFF ? 0u : par, 40 + k);
               } else {
-                mbar_wait(&h_ready[kc], par);
+                mbar_wait_tag<WD>(&h_ready[kc], kc < C::KOFF ? 0u : par, 40 + kc);
               }
               tc_fence_after();
             }
 #pragma unroll
             for (int s = 0; s < C::SPC; ++s, ++itw) {
               const int slot = itw % C::NSW;
-              mbar_wait(&wfull[slot], (itw / C::NSW) & 1);
+              mbar_wait_tag<WD>(&wfull[slot], (itw / C::NSW) & 1, 50 + slot);
               tc_fence_after();
               const uint32_t sb = wr_s + slot * C::SLOT_BYTES;
 #pragma unroll
@@ -350,7 +392,7 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
               }
               mma_commit(&wempty[slot]);
             }
-            if (nb == 1) mma_commit(&a_free[kc]);  // h chunk kc has been read by both gate groups
+            if (nb == 1 && kc >= C::KOFF) mma_commit(&a_free[kc - C::KOFF]);  // state chunk read by both gate groups
           }
           if (nb == 0) mma_commit(g_r_done);
           if (nb == 1) mma_commit(g_u_done);
@@ -359,25 +401,34 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
       }
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    // ======================================================================== loader: weight ring + xp ring
+    // ======================================================================== loader: weight ring + box ring
     if (warp == EPI_WARPS + 1 && lane == 0) {
-      const uint32_t totW = (uint32_t)a.T * C::WPS, totX = (uint32_t)a.T * C::BPS;
+      const uint32_t totW = (uint32_t)a.T * C::WPS, totX = C::PRO + (uint32_t)a.T * C::BPS;
       const uint64_t xpol = a.xp_const ? L2_EVICT_LAST : L2_EVICT_FIRST;
       uint32_t itw = 0, g = 0;
       while (itw < totW || g < totX) {
         if (g < totX) {
           const int slot = g % C::NXB;
           if (mbar_test_wait(&xempty[slot], ((g / C::NXB) & 1) ^ 1)) {
-            const uint32_t t = g / C::BPS, ib = g % C::BPS;
-            const int gate = ib / C::NKC, w = ib % C::NKC;          // w = j*4 + cs
+            // box g: prologue [ex x NKC | h0 x NKC] (EX only), then per step [xp_r | xp_u | xp_c] x NKC; inside a
+            // block of NKC boxes, box w = j*4 + cs is chunk j of column group cs
+            const void* tm = &tm_xp;
+            int c0;
+            const int w = ((int)g < C::PRO ? g : g - C::PRO) % C::NKC;
             const int col = (w & 3) * C::HC + (w >> 2) * 32;
-            if (a.dbg & 1) {
-              mbar_arrive(&xfull[slot]);
+            if ((int)g < C::PRO) {
+              tm = (g < C::NKC) ? (const void*)&tm_ex : (const void*)&tm_h0;
+              c0 = col;
             } else {
-              mbar_arrive_expect_tx(&xfull[slot], XBOX_BYTES);
-              tma_load_2d(xring + (size_t)slot * XBOX_BYTES, &tm_xp, (int)(t * a.xp_step + gate * H + col), (int)row0,
-                          &xfull[slot], xpol);
+              const uint32_t t = (g - C::PRO) / C::BPS, ib = (g - C::PRO) % C::BPS;
+              c0 = (int)(t * a.xp_step + (ib / C::NKC) * H + col);
+            }
+            uint64_t* fb = &xfull[w & 3];
+            if (a.dbg & 1) {
+              mbar_arrive(fb);
+            } else {
+              mbar_arrive_expect_tx(fb, XBOX_BYTES);
+              tma_load_2d(xring + (size_t)slot * XBOX_BYTES, tm, c0, (int)row0, fb, (int)g < C::PRO ? L2_EVICT_FIRST : xpol);
             }
             ++g;
           }
@@ -385,17 +436,17 @@ __global__ void __launch_bounds__(NTHR3, 1) gru_tc3_kernel(const __grid_constant
         if (itw < totW) {
           const int slot = itw % C::NSW;
           if (mbar_test_wait(&wempty[slot], ((itw / C::NSW) & 1) ^ 1)) {
-            const uint32_t wi = itw % C::WPS;
-            const int nb = wi / (C::NKC * C::SPC), r = wi % (C::NKC * C::SPC);
-            const int blk = r / C::SPC, part = r % C::SPC;
-            const uint8_t* src = (nb < 2 ? a.wg + ((size_t)nb * C::NKC + blk) * C::BLOCK_BYTES
-                                         : a.wc + (size_t)blk * C::BLOCK_BYTES);
-            uint8_t* dst = wring + (size_t)slot * C::SLOT_BYTES;
             if (a.dbg & 2) {
               mbar_arrive(&wfull[slot]);
               ++itw;
               continue;
             }
+            const uint32_t wi = itw % C::WPS;
+            const int nb = wi / (C::NKA * C::SPC), r = wi % (C::NKA * C::SPC);
+            const int blk = r / C::SPC, part = r % C::SPC;
+            const uint8_t* src = (nb < 2 ? a.wg + ((size_t)nb * C::NKA + blk) * C::BLOCK_BYTES
+                                         : a.wc + (size_t)blk * C::BLOCK_BYTES);
+            uint8_t* dst = wring + (size_t)slot * C::SLOT_BYTES;
             mbar_arrive_expect_tx(&wfull[slot], C::SLOT_BYTES);
             if (C::SPC == 1) {
               bulk_g2s_hint(dst, src, C::SLOT_BYTES, &wfull[slot], L2_EVICT_LAST);
@@ -427,24 +478,6 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
-template <int H>
-int launch3(const CUtensorMap& tm, const Gru3Args& a, unsigned grid, cudaStream_t st) {
-  DESIRE_ENSURE_SMEM(gru_tc3_kernel<H>, Cfg3<H>::SMEM);
-  DESIRE_LAUNCH(st, (gru_tc3_kernel<H><<<grid, NTHR3, Cfg3<H>::SMEM, st>>>(tm, a)));
-  return DESIRE_OK;
-}
-
-bool v3_disabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DESIRE_GRU_V2");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-}  // namespace
-
 // FP32 row-major [rows, row_stride] tensor -> tiled map with [128 rows x 32 columns] boxes, 128-byte swizzle
 int make_tmap_rows32(CUtensorMap* tm, const float* base, long rows, long row_stride) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
@@ -466,24 +499,49 @@ int make_tmap_rows32(CUtensorMap* tm, const float* base, long rows, long row_str
   return DESIRE_OK;
 }
 
+template <int H, bool EX, bool WD>
+int launch3(const CUtensorMap& tx, const CUtensorMap& te, const CUtensorMap& th, const Gru3Args& a, unsigned grid,
+            cudaStream_t st) {
+  DESIRE_ENSURE_SMEM((gru_tc3_kernel<H, EX, WD>), (Cfg3<H, EX>::SMEM));
+  DESIRE_LAUNCH(st, (gru_tc3_kernel<H, EX, WD><<<grid, NTHR3, Cfg3<H, EX>::SMEM, st>>>(tx, te, th, a)));
+  return DESIRE_OK;
+}
+
+bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+
+bool tma_ok(const float* p, long ld) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0; }
+
+}  // namespace
+
 bool gru_tc3_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes) {
-  if (v3_disabled() || gemm_mode() == 0 || !a.xp || a.traj || a.ex || a.Ka != 0) return false;
-  if (a.H != 128 && a.H != 256) return false;
+  static const bool off = env_flag("DESIRE_GRU_V2");
+  if (off || gemm_mode() == 0 || !a.xp || a.traj) return false;
   if (a.R < 64 || a.T < 1) return false;
-  if ((reinterpret_cast<uintptr_t>(a.xp) & 15) || a.xp_row_stride % 4 != 0 || a.xp_step_stride % 4 != 0) return false;
+  if (!tma_ok(a.xp, a.xp_row_stride) || a.xp_step_stride % 4 != 0) return false;
   if (a.xp_row_stride < (long)(a.T - 1) * a.xp_step_stride + 3 * a.H) return false;   // a step is a column window of the row
-  if (a.T > 1 && !a.hs && !a.h_final) return false;
-  if (!a.packed && (!pack_ws || pack_bytes < gru_tc3_pack_bytes(a.H))) return false;
+  if (a.ex) {        // Decoder-2 form: one step, [ex | h] operand, both through TMA
+    if (a.H != 128 || a.Ka != a.H || a.T != 1 || !a.h_final) return false;
+    if (!tma_ok(a.ex, a.ld_ex) || !tma_ok(a.h0, a.ld_h0) || a.h0_div > 1 || a.ld_ex < a.H || a.ld_h0 < a.H) return false;
+  } else {
+    if ((a.H != 128 && a.H != 256) || a.Ka != 0) return false;
+    if (a.T > 1 && !a.hs && !a.h_final) return false;
+  }
+  if (a.packed ? a.packed_fmt != 3 : (!pack_ws || pack_bytes < gru_tc3_pack_bytes(a.H, a.Ka))) return false;
   return encode_fn() != nullptr;
 }
 
-size_t gru_tc3_pack_bytes(int H) { return align_up(tc_pack_bytes(H, 2 * H, H)) + align_up(tc_pack_bytes(H, H, H)); }
+size_t gru_tc3_pack_bytes(int H, int Ka) {
+  return align_up(tc_pack_bytes(Ka + H, 2 * H, H)) + align_up(tc_pack_bytes(Ka + H, H, H));
+}
 
-int gru_tc3_pack(const float* w_g, const float* w_c, int H, void* ws, size_t ws_bytes, cudaStream_t st) {
-  DESIRE_CHECK_ARG(ws && ws_bytes >= gru_tc3_pack_bytes(H), "gru_tc3_pack: workspace too small");
+int gru_tc3_pack(const float* w_g, const float* w_c, int H, int Ka, void* ws, size_t ws_bytes, cudaStream_t st) {
+  DESIRE_CHECK_ARG(ws && ws_bytes >= gru_tc3_pack_bytes(H, Ka), "gru_tc3_pack: workspace too small");
   uint8_t* pg = (uint8_t*)ws;
-  DESIRE_TRY(tc_pack_b(w_g, 2 * H, false, H, 2 * H, H, pg, st));
-  DESIRE_TRY(tc_pack_b(w_c, H, false, H, H, H, pg + align_up(tc_pack_bytes(H, 2 * H, H)), st));
+  DESIRE_TRY(tc_pack_b(w_g, 2 * H, false, Ka + H, 2 * H, H, pg, st));
+  DESIRE_TRY(tc_pack_b(w_c, H, false, Ka + H, H, H, pg + align_up(tc_pack_bytes(Ka + H, 2 * H, H)), st));
   return DESIRE_OK;
 }
 
@@ -507,13 +565,22 @@ int gru_seq_tc3(const GruSeqArgs& s, void* pack_ws, cudaStream_t st) {
     a.dbg = dbg;
   }
   const uint8_t* pg = (const uint8_t*)(s.packed ? s.packed : pack_ws);
-  if (!s.packed) DESIRE_TRY(gru_tc3_pack(s.w_g, s.w_c, H, pack_ws, gru_tc3_pack_bytes(H), st));
+  if (!s.packed) DESIRE_TRY(gru_tc3_pack(s.w_g, s.w_c, H, s.Ka, pack_ws, gru_tc3_pack_bytes(H, s.Ka), st));
   a.wg = pg;
-  a.wc = pg + align_up(tc_pack_bytes(H, 2 * H, H));
-  CUtensorMap tm;
-  DESIRE_TRY(make_tmap_rows32(&tm, s.xp, s.R, s.xp_row_stride));
+  a.wc = pg + align_up(tc_pack_bytes(s.Ka + H, 2 * H, H));
+  CUtensorMap tx, te, th;
+  DESIRE_TRY(make_tmap_rows32(&tx, s.xp, s.R, s.xp_row_stride));
+  te = tx;
+  th = tx;
+  if (s.ex) {
+    DESIRE_TRY(make_tmap_rows32(&te, s.ex, s.R, s.ld_ex));
+    DESIRE_TRY(make_tmap_rows32(&th, s.h0, s.R, s.ld_h0));
+  }
   const unsigned grid = (unsigned)(((long)s.R + TM - 1) / TM);
-  return H == 128 ? launch3<128>(tm, a, grid, st) : launch3<256>(tm, a, grid, st);
+  static const bool wd = env_flag("DESIRE_GRU3_WATCHDOG");
+  if (s.ex) return wd ? launch3<128, true, true>(tx, te, th, a, grid, st) : launch3<128, true, false>(tx, te, th, a, grid, st);
+  if (H == 128) return wd ? launch3<128, false, true>(tx, te, th, a, grid, st) : launch3<128, false, false>(tx, te, th, a, grid, st);
+  return wd ? launch3<256, false, true>(tx, te, th, a, grid, st) : launch3<256, false, false>(tx, te, th, a, grid, st);
 }
 
 }  // namespace desire

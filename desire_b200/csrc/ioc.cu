@@ -564,7 +564,7 @@ IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   L.pk_sp = take(gemm_tc_pack_bytes((int)H, (int)(G * H)));
   L.pk_sp3 = take(gemm_tc_pack_bytes(3 * (int)H, (int)H));
   L.pk_reg = take(gemm_tc_pack_bytes(2 * (int)T, (int)H));
-  L.pk_gru = take(H % 32 == 0 && H <= 256 ? gru_tc_pack_bytes((int)H, (int)H) : 256);
+  L.pk_gru = take(H % 32 == 0 && H <= 256 ? std::max(gru_tc_pack_bytes((int)H, (int)H), gru_tc3_pack_bytes((int)H, (int)H)) : 256);
   L.total = off;
   return L;
 }
@@ -640,11 +640,19 @@ static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const
   const float* wg_h = g.wg + (size_t)(Dst + H) * 2 * H;   // state rows only (fallback form)
   const float* wc_h = g.wc + (size_t)(Dst + H) * H;
   const void* gru_packed = nullptr;
+  int gru_fmt = 0;
   bool gru_ex = false;
   {
     GruSeqArgs probe{};
     probe.R = (int)R; probe.H = H; probe.T = 1; probe.xp = XP; probe.ex = fsp; probe.Ka = H; probe.ld_ex = H;
-    if (gru_tc_eligible(probe, base + L.pk_gru, L.total - L.pk_gru)) {
+    probe.xp_row_stride = (long)T * 3 * H; probe.h0 = h2; probe.h0_div = 1; probe.ld_h0 = H; probe.h_final = h2; probe.ld_hf = H;
+    if (gru_tc3_eligible(probe, base + L.pk_gru, L.total - L.pk_gru)) {
+      // third design of the recurrence: [fsp | h] operand, every per-row input through TMA boxes
+      DESIRE_TRY(gru_tc3_pack(wg_sh, wc_sh, H, H, base + L.pk_gru, L.total - L.pk_gru, st));
+      gru_packed = base + L.pk_gru;
+      gru_fmt = 3;
+      gru_ex = true;
+    } else if (gru_tc_eligible(probe, base + L.pk_gru, L.total - L.pk_gru)) {
       DESIRE_TRY(gru_tc_pack(wg_sh, wc_sh, H, H, base + L.pk_gru, L.total - L.pk_gru, st));
       gru_packed = base + L.pk_gru;
       gru_ex = true;
@@ -739,6 +747,7 @@ static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const
       a.h0 = h2; a.h0_div = 1; a.ld_h0 = H;
       a.h_final = h2; a.ld_hf = H;
       a.packed = gru_packed;
+      a.packed_fmt = gru_fmt;
       {
         ProfScope ps_(DESIRE_PROF_GRU_DEC2, st);
         DESIRE_TRY(gru_seq(a, st));

@@ -165,6 +165,67 @@ __global__ void masked_cost_kernel(const float* __restrict__ a, const float* __r
   }
 }
 
+// ---- D8 existence: a copy of the observations whose id at observed frame 0 — the field every kernel of the path tests
+// for "this agent exists" — is zeroed for agents that are absent where the losses and the decoders need them.
+//   mode 0: the id at observed frame 0 only (obj_id of model/model.py:214,357);
+//   mode 1: also absent at the LAST observed frame (the read-out anchors on that position) or at ANY target frame
+//           (`target_obj_id` of model/model.py:358: an object missing from the target must not contribute to the cost).
+__global__ void existence_kernel(const float* __restrict__ obs, const float* __restrict__ tgt, int M, int Tp, int Tf,
+                                 int mode, float* __restrict__ out) {
+  const size_t n = (size_t)M * Tp * 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = obs[i];
+    if (i % ((size_t)Tp * 3) == 0 && mode == 1 && v != 0.f) {
+      const size_t m = i / ((size_t)Tp * 3);
+      bool ok = obs[i + (size_t)(Tp - 1) * 3] != 0.f;
+      for (int t = 0; t < Tf && ok; ++t) ok = tgt[(m * Tf + t) * 3] != 0.f;
+      if (!ok) v = 0.f;
+    }
+    out[i] = v;
+  }
+}
+
+// ---- a7 noise source: eps ~ N(0, I) drawn on the device (the reference draws it inside the graph with
+// tf.random_normal, model/model.py:262).  Philox4x32-10 counter-based generator (Salmon et al., SC'11): thread i
+// encrypts counter (i, offset) under key `seed` into four 32-bit words -> four uniforms -> two Box-Muller pairs, so
+// element e of a draw is a pure function of (seed, offset, e) — any rank or the oracle can reproduce it.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__global__ void randn_kernel(const unsigned long long* __restrict__ state, float* __restrict__ out, size_t n) {
+  const unsigned long long seed = state[0], offset = state[1];
+  const size_t quads = (n + 3) / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      philox_round(c, k0, k1);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = ((float)(c[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-8f;       // (0,1), 24 bits
+      const float u2 = ((float)(c[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+      const float rad = sqrtf(-2.f * logf(u1));
+      float sn, cs;
+      sincosf(6.283185307179586f * u2, &sn, &cs);
+      z[2 * h] = rad * cs;
+      z[2 * h + 1] = rad * sn;
+    }
+    if (4 * i + 3 < n) {
+      *reinterpret_cast<float4*>(out + 4 * i) = make_float4(z[0], z[1], z[2], z[3]);
+    } else {
+      for (size_t e = 4 * i; e < n; ++e) out[e] = z[e - 4 * i];
+    }
+  }
+}
+
 inline unsigned warps_grid(size_t warps, int threads) { return (unsigned)((warps * 32 + threads - 1) / threads); }
 
 }  // namespace
@@ -241,6 +302,28 @@ extern "C" int desire_recon_rows_fwd(const float* Yhat, const float* target, int
   DESIRE_CHECK_ARG(Yhat && target && recon_rows && M >= 0 && K > 0 && T > 0, "desire_recon_rows_fwd: bad arguments");
   if (M == 0) return DESIRE_OK;
   recon_rows_kernel<<<warps_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(Yhat, target, M, K, T, recon_rows);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}
+
+extern "C" int desire_randn_fwd(const unsigned long long* state, float* out, size_t n, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(state && out && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "desire_randn_fwd: bad arguments");
+  if (n == 0) return DESIRE_OK;
+  const size_t quads = (n + 3) / 4;
+  randn_kernel<<<(unsigned)((quads + 255) / 256 < 148 * 16 ? (quads + 255) / 256 : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      state, out, n);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}
+
+extern "C" int desire_existence_fwd(const float* obs, const float* target, int M, int Tp, int Tf, int mode, float* obs_out,
+                                    desire_stream_t stream) {
+  DESIRE_CHECK_ARG(obs && obs_out && M >= 0 && Tp > 0 && (mode == 0 || (mode == 1 && target && Tf > 0)),
+                   "desire_existence_fwd: bad arguments");
+  if (M == 0) return DESIRE_OK;
+  const size_t n = (size_t)M * Tp * 3;
+  existence_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, (cudaStream_t)stream>>>(
+      obs, target, M, Tp, Tf, mode, obs_out);
   DESIRE_LAUNCH_CHECK();
   return DESIRE_OK;
 }

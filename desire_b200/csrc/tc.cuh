@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace desire {
 namespace tc {
@@ -43,6 +44,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// mbar_wait with a watchdog: a protocol error in a warp-specialised kernel shows up as a hang; after ~2 s of waiting
+// this names the barrier (tag), the waiter and the phase it wanted, then traps so the launch fails instead of hanging.
+static __device__ __noinline__ void mbar_stuck(int tag, uint32_t parity) {
+  printf("desire: mbarrier wait stuck: tag %d parity %u block %d thread %d\n", tag, parity, (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
+// WD = false compiles to the plain wait (the watchdog's cold call costs registers around every wait site).
+template <bool WD>
+__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag) {
+  if (!WD) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) mbar_stuck(tag, parity);
   }
 }
 // non-blocking probe (a thread that serves two rings polls both)

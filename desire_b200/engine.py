@@ -36,6 +36,16 @@ def flatten_params(params: dict, device):
     return flat, views, offs
 
 
+def existing_agents(obs, tgt, mode=1):
+    """[B,N] bool: the agents that desire_existence_fwd keeps (host-side mirror, used for the count normaliser)."""
+    m = obs[:, :, 0, 0] != 0
+    if mode == 1:
+        m = m & (obs[:, :, -1, 0] != 0)
+        if tgt is not None:
+            m = m & (tgt[:, :, :, 0] != 0).all(-1)
+    return m
+
+
 class HotPath:
     """Sample generation (a2-a13) + IOC ranking/refinement (a14) for a fixed batch of B scenes."""
 
@@ -59,7 +69,8 @@ class HotPath:
             rho_i=f(M, 2 * Cm), HxHy=f(M, 2 * H), vae_inputs=f(M, cfg.S * cfg.S), mu_logvar=f(M, 2 * Zl),
             zval=f(R, Zl), x_reconstr_mean=f(R, cfg.S * cfg.S), x_z=f(R, H), output_states=f(R, Tf, H),
             Yhat=f(R, Tf, 2), feature_pooling=f(R, Tf, 2 * Cm), kld_rows=f(M), recon_rows=f(M), cost=f(2),
-            scene_features=f(B, Hm, Hm, cfg.scene_channels), Y_refined=f(R, Tf, 2),
+            scene_features=f(B, Hm, Hm, cfg.scene_channels), Y_refined=f(R, Tf, 2), obs_eff=f(B, N, Tp, 3),
+            eps=f(M, K, Zl),
             ioc_scores=f(max(cfg.ioc_iters, 1), R),
         )
         self._structs()
@@ -114,6 +125,10 @@ class HotPath:
         self.ws_enc_bytes = max(lib.desire_gru_encode_workspace_bytes(M, max(Tp, Tf), H), 256)
         self.ws_encx = torch.empty(self.ws_enc_bytes, dtype=torch.uint8, device=self.device)
         self.ws_ency = torch.empty(self.ws_enc_bytes, dtype=torch.uint8, device=self.device)
+        # {seed, offset} of the device noise source (desire_randn_fwd), read by the kernel at execution time: a captured
+        # graph draws fresh eps when set_noise() bumps the offset between replays
+        self.rng_state = torch.tensor([2, 0], dtype=torch.int64, device=self.device)
+        self._rng_host = torch.empty(2, dtype=torch.int64).pin_memory()
         self.serial = False      # True: no parallel branches (bench.py's per-kernel timing pass needs launches that do not overlap)
         self.graph = None
         self.graph_gen = self.graph_rank = None
@@ -133,13 +148,23 @@ class HotPath:
                                P["ioc_score_b"].data_ptr(), P["ioc_reg_w"].data_ptr(), P["ioc_reg_b"].data_ptr(),
                                self.r2_edges.data_ptr(), self.dirs.data_ptr())
 
+    def set_noise(self, seed, offset):
+        """Select the eps draw of the next pass that runs with eps=None (async 16-byte copy on the current stream)."""
+        self._rng_host[0], self._rng_host[1] = int(seed), int(offset)
+        self.rng_state.copy_(self._rng_host, non_blocking=True)
+
     # ------------------------------------------------------------------ one pass of the hot path
     def run(self, obs, tgt, eps, scene, stages=("generate", "rank")):
-        """obs [B,N,Tp,3], tgt [B,N,Tf,3], eps [M,K,Z], scene [B,Hi,Wi,3] — contiguous fp32 CUDA tensors.
+        """obs [B,N,Tp,3], tgt [B,N,Tf,3], eps [M,K,Z] or None, scene [B,Hi,Wi,3] — contiguous fp32 CUDA tensors.
+        eps=None draws the noise on the device (desire_randn_fwd with the state of set_noise(); the reference draws it
+        inside the graph too, model/model.py:262) into buf["eps"].
         Enqueues everything on the current stream; returns the dict of output buffers (views)."""
         cfg, lib, b, P = self.cfg, self.lib, self.buf, self.P
         N, K, H, Zl, Tp, Tf, Cm = cfg.max_num_obj, cfg.K, cfg.H, cfg.Z, cfg.seq_length, cfg.pred_length, cfg.channel_multiplier
         M, R, S2 = self.M, self.R, cfg.S * cfg.S
+        draw = eps is None
+        if draw:
+            eps = b["eps"]
         for t, shp in ((obs, (self.B, N, Tp, 3)), (tgt, (self.B, N, Tf, 3)), (eps, (M, K, Zl))):
             if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
                 raise ValueError("expected contiguous float32 %s on %s, got %s %s" % (shp, self.device, tuple(t.shape), t.dtype))
@@ -162,6 +187,11 @@ class HotPath:
                                         C.byref(self.w_scene), _p(b["scene_features"]), _p(self.ws_scene),
                                         self.ws_scene_bytes, C.c_void_p(s_str.cuda_stream)), "scene_cnn")
         if "encode" in stages:
+            # D8: from here on every kernel sees obs_eff, whose frame-0 id is zero for agents that do not exist where
+            # the losses / decoders need them (absent at the last observed frame or in the target, cfg.exist_mode)
+            ck(lib.desire_existence_fwd(_p(obs), _p(tgt), M, Tp, Tf, cfg.exist_mode, _p(b["obs_eff"]), st), "existence")
+        obs = b["obs_eff"]          # stages run in order on one HotPath: later stages reuse the encode stage's copy
+        if "encode" in stages:
             ck(lib.desire_tconv_fwd(_p(obs), M, Tp, Cm, _p(P["temporal_w"]), _p(P["temporal_b"]), _p(b["rho_i"]), st), "tconv")
             s_y = cur if self.serial else self.side2
             if not self.serial:
@@ -177,6 +207,8 @@ class HotPath:
                                  _p(b["vae_inputs"]), S2, M, S2, 2 * H, 1, 0, st), "fc_c")
             ck(lib.desire_cvae_encode_fwd(_p(b["vae_inputs"]), M, Zl, C.byref(self.w_venc), _p(b["mu_logvar"]), ws, wsb, st), "cvae_encode")
         if "decode" in stages:
+            if draw:
+                ck(lib.desire_randn_fwd(_p(self.rng_state), _p(eps), M * K * Zl, st), "randn")
             ck(lib.desire_reparam_fwd(_p(b["mu_logvar"]), _p(eps), M, K, Zl, _p(b["zval"]), st), "reparam")
             ck(lib.desire_cvae_decode_fwd(_p(b["zval"]), R, Zl, C.byref(self.w_vdec), _p(b["x_reconstr_mean"]), ws, wsb, st), "cvae_decode")
             ck(lib.desire_mask_softmax_fwd(_p(b["x_reconstr_mean"]), R, S2, H, K, _p(P["w_post_vae"]), _p(P["b_post_vae"]),
@@ -220,7 +252,7 @@ class HotPath:
     def capture(self, obs, tgt, eps, scene):
         """Capture one whole pass (every kernel of run()) into a CUDA graph over static input buffers.
         ~10^3 launches per step otherwise leave the GPU waiting on the host between small kernels."""
-        self.static_in = [t.clone() for t in (obs, tgt, eps, scene)]
+        self.static_in = [t.clone() if t is not None else None for t in (obs, tgt, eps, scene)]
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -238,7 +270,7 @@ class HotPath:
         """Two graphs over the same static buffers: sample generation, then ranking/refinement.  The host-buffer
         entry point (replay_split) uses the gap to stage the scene images — the largest input, which only the
         second graph reads — while the first graph is already running."""
-        self.static_in = [t.clone() for t in (obs, tgt, eps, scene)]
+        self.static_in = [t.clone() if t is not None else None for t in (obs, tgt, eps, scene)]
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -259,33 +291,45 @@ class HotPath:
         self.copy_stream = torch.cuda.Stream(self.device)
         self.copy_done = torch.cuda.Event()
         self.eps_done = torch.cuda.Event()
+        self.gen_done = torch.cuda.Event()
+        self.rank_done = torch.cuda.Event()
+        self.gen_done.record(torch.cuda.current_stream(self.device))
+        self.rank_done.record(torch.cuda.current_stream(self.device))
+        self.split_draws = eps is None               # the decoder graph holds the device noise kernel
         return self.graph_gen, self.graph_rank
 
     def replay_split(self, obs, tgt, stage_eps, stage_scene):
         """Host-buffer replay.  obs/tgt: pinned host tensors (small); stage_eps() / stage_scene() return the pinned eps
         and scene tensors and are called only AFTER GPU work that does not need them has been launched, so their
         host-side memcpy, their H2D copies (second stream) and the scene CNN overlap the encoder graph and the
-        decoder graph respectively:
+        decoder graph respectively (stage_eps=None: the graphs were captured with eps=None and draw it on the device):
             main:  H2D obs,tgt | encode graph ............ | wait eps | decode graph ............... | wait scene | IOC graph
             host:              | memcpy eps -> pinned      |          | memcpy scene -> pinned       |
-            copy:                          | H2D eps       |                       | H2D scene, scene CNN |"""
+            copy:                          | H2D eps       |                       | H2D scene, scene CNN |
+        Calls may be issued back to back without a host synchronisation in between (DESIREModel.submit): the events
+        below keep pass t+1's copies and scene CNN off the buffers pass t's graphs are still reading."""
         cur = torch.cuda.current_stream(self.device)
         self.static_in[0].copy_(obs, non_blocking=True)
         self.static_in[1].copy_(tgt, non_blocking=True)
         self.graph_enc.replay()
-        eps = stage_eps()
-        with torch.cuda.stream(self.copy_stream):
-            self.static_in[2].copy_(eps, non_blocking=True)
-            self.eps_done.record(self.copy_stream)
-        cur.wait_event(self.eps_done)
+        if stage_eps is not None:
+            eps = stage_eps()
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.gen_done)          # the previous pass's decoder graph read static eps
+                self.static_in[2].copy_(eps, non_blocking=True)
+                self.eps_done.record(self.copy_stream)
+            cur.wait_event(self.eps_done)
         self.graph_gen.replay()
+        self.gen_done.record(cur)
         scene = stage_scene()
         with torch.cuda.stream(self.copy_stream):
             self.static_in[3].copy_(scene, non_blocking=True)
+            self.copy_stream.wait_event(self.rank_done)             # the previous pass's IOC graph read scene_features
             self.graph_scene.replay()              # the scene CNN runs next to the rest of the decoder graph
             self.copy_done.record(self.copy_stream)
         cur.wait_event(self.copy_done)
         self.graph_rank.replay()
+        self.rank_done.record(cur)
         return self.outputs()
 
     def replay(self, obs=None, tgt=None, eps=None, scene=None, non_blocking=True):
@@ -293,7 +337,7 @@ class HotPath:
         if self.graph is None:
             raise _lib.DesireError("replay() before capture()")
         for dst, src in zip(self.static_in, (obs, tgt, eps, scene)):
-            if src is not None:
+            if src is not None and dst is not None:
                 dst.copy_(src, non_blocking=non_blocking)
         self.graph.replay()
         return self.outputs()
@@ -370,11 +414,11 @@ class TrainPath(HotPath):
     def step_no(self, v):
         self._step[0] = int(v)
 
-    def set_count(self, obs):
-        """Number of existing agents (id != 0, D8) of this rank's scenes, summed over ranks: the normaliser of
+    def set_count(self, obs, tgt=None):
+        """Number of existing agents (D8, cfg.exist_mode) of this rank's scenes, summed over ranks: the normaliser of
         `cost` (model/model.py:376) every rank must share."""
         from .dist import global_count_
-        self.count.copy_((obs[:, :, 0, 0] != 0).sum().to(torch.float32).reshape(1))
+        self.count.copy_(existing_agents(obs, tgt, self.cfg.exist_mode).sum().to(torch.float32).reshape(1))
         return global_count_(self.count)
 
     def backward(self, obs, tgt, eps, scene=None):
@@ -383,6 +427,9 @@ class TrainPath(HotPath):
         forward runs inside (Y_refined, ioc_scores, ioc_cost are outputs of this call)."""
         cfg, lib, b, d, P, G = self.cfg, self.lib, self.buf, self.dbuf, self.P, self.G
         N, K, H, Zl, Tp, Tf = cfg.max_num_obj, cfg.K, cfg.H, cfg.Z, cfg.seq_length, cfg.pred_length
+        obs = b["obs_eff"]          # the existence-masked copy written by the forward's encode stage (same inputs)
+        if eps is None:
+            eps = b["eps"]          # the noise the forward drew on the device
         M, R, S2 = self.M, self.R, cfg.S * cfg.S
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         ws, wsb = _p(self.ws), self.ws_bytes
@@ -441,7 +488,7 @@ class TrainPath(HotPath):
 
     def capture_train(self, obs, tgt, eps, scene):
         """Capture forward (generate stage) + backward into one CUDA graph over static inputs."""
-        self.static_in = [t.clone() for t in (obs, tgt, eps, scene)]
+        self.static_in = [t.clone() if t is not None else None for t in (obs, tgt, eps, scene)]
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -461,15 +508,15 @@ class TrainPath(HotPath):
         """One optimiser step on this rank's scenes.  Returns the (local) cost tensor [cost, count]."""
         if use_graph:
             if self.train_graph is None:
-                self.set_count(obs)
+                self.set_count(obs, tgt)
                 self.capture_train(obs, tgt, eps, scene)
             for dst, src in zip(self.static_in, (obs, tgt, eps, scene)):
-                if src is not None and src.data_ptr() != dst.data_ptr():
+                if src is not None and dst is not None and src.data_ptr() != dst.data_ptr():
                     dst.copy_(src, non_blocking=True)
-            self.set_count(self.static_in[0])
+            self.set_count(self.static_in[0], self.static_in[1])
             self.train_graph.replay()
         else:
-            self.set_count(obs)
+            self.set_count(obs, tgt)
             self.run(obs, tgt, eps, scene, stages=("generate",))
             self.backward(obs, tgt, eps, scene)
         self.apply(lr, clip)

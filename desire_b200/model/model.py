@@ -67,6 +67,7 @@ class DESIREModel(object):
         self._paths = {}
         self._train_paths = {}
         self._pinned = {}
+        self._submit_no, self._noise_offset, self._slot_done = 0, 0, {}
         # filled by forward(); same names as the reference's graph nodes
         self.input_data = self.target_data = self.target_data_enc = self.temporal_data = None
         self.rho_i = self.output_states = self.feature_pooling = None
@@ -163,17 +164,15 @@ class DESIREModel(object):
         to_dev = lambda n, x: x if (torch.is_tensor(x) and x.is_cuda) else self._stage(n, x.numpy() if torch.is_tensor(x) else x)
         obs, tgt = to_dev("obs", input_data), to_dev("tgt", target_data)
         B = obs.shape[0]
+        tp = self._train_path(B)
         if eps is None:
-            g = torch.Generator(device=self.device)
-            g.manual_seed(2 if seed is None else seed)
-            eps = torch.randn(B * cfg.max_num_obj, cfg.K, cfg.Z, generator=g, device=self.device)
+            tp.set_noise(2 if seed is None else seed, 0)        # drawn on the device inside the step (desire_randn_fwd)
         else:
             eps = to_dev("eps", eps)
         if scene is None:
             scene = torch.zeros(B, cfg.scene_size, cfg.scene_size, 3, device=self.device)
         else:
             scene = to_dev("scene", scene)
-        tp = self._train_path(B)
         cost = tp.train_step(obs, tgt, eps, scene, lr=self.learning_rate, clip=self.grad_clip, use_graph=self.use_graph)
         self.input_data, self.target_data, self.target_data_enc, self.temporal_data = obs, tgt, tgt, obs
         self.cost, self.final_states, self.gradients = cost[0], tp.buf["HxHy"][:, :cfg.H], tp.G
@@ -191,10 +190,11 @@ class DESIREModel(object):
         dev.copy_(pin, non_blocking=True)
         return dev
 
-    def _pin(self, name, arr):
-        """numpy -> reused pinned host buffer."""
+    def _pin(self, name, arr, slot=0):
+        """numpy -> reused pinned host buffer (one per `slot`: back-to-back submissions alternate slots so the memcpy
+        for pass t+1 never lands in a buffer whose H2D copy for pass t is still in flight)."""
         t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
-        key = ("pin", name, tuple(t.shape))
+        key = ("pin", name, tuple(t.shape), slot)
         if key not in self._pinned:
             self._pinned[key] = torch.empty(t.shape, dtype=torch.float32).pin_memory()
         self._pinned[key].copy_(t)
@@ -202,51 +202,67 @@ class DESIREModel(object):
 
     def forward(self, input_data, target_data, eps=None, scene=None, stages=("generate", "rank"), seed=None):
         """input_data [B,N,Tp,3], target_data [B,N,Tf,3] (id,x,y), agent-major as the reference's
-        placeholders (model/model.py:91-105) with a leading scene axis; eps [B*N,K,Z] (drawn with
-        `seed` if None, D1); scene [B,Hi,Wi,3].  CUDA tensors are used in place, numpy/CPU inputs
-        are staged through pinned memory.  Returns the dict of device outputs."""
+        placeholders (model/model.py:91-105) with a leading scene axis; eps [B*N,K,Z] (None: drawn on the device from
+        `seed`, D1 — desire_randn_fwd, element e of the draw is a function of (seed, e) only); scene [B,Hi,Wi,3].
+        CUDA tensors are used in place, numpy/CPU inputs are staged through pinned memory.  Returns the dict of
+        device outputs."""
         cfg = self.cfg
         to_dev = lambda n, x: x if (torch.is_tensor(x) and x.is_cuda) else self._stage(n, x.numpy() if torch.is_tensor(x) else x)
         obs = to_dev("obs", input_data)
         tgt = to_dev("tgt", target_data)
         B = obs.shape[0]
+        hp = self._path(B)
         if eps is None:
-            g = torch.Generator(device=self.device)
-            g.manual_seed(2 if seed is None else seed)
-            eps = torch.randn(B * cfg.max_num_obj, cfg.K, cfg.Z, generator=g, device=self.device)
+            hp.set_noise(2 if seed is None else seed, 0)
         else:
             eps = to_dev("eps", eps)
         if scene is None:
             scene = torch.zeros(B, cfg.scene_size, cfg.scene_size, 3, device=self.device)
         else:
             scene = to_dev("scene", scene)
-        out = self._path(B).run(obs, tgt, eps, scene, stages)
+        out = hp.run(obs, tgt, eps, scene, stages)
         self.input_data, self.target_data, self.target_data_enc = obs, tgt, tgt
         self.temporal_data = obs
         self.rho_i, self.output_states, self.feature_pooling = out["rho_i"], out["output_states"], out["feature_pooling"]
         self.cost, self.final_states, self.final_output = out["cost"], out["H_x"], out["Y_refined"]
         return out
 
-    def sample_and_rank(self, input_data, target_data, eps=None, scene=None):
-        """End-to-end public call with HOST buffers: stage inputs, run sample generation + IOC
-        ranking/refinement, copy the ranked result back.  Returns (Y_refined [B,N,K,Tf,2],
-        scores [iters,B,N,K], cost) as numpy."""
+    # ------------------------------------------------------------------ host-buffer entry points
+    def submit(self, input_data, target_data, eps=None, scene=None, seed=None):
+        """Enqueue one pass of sample generation + IOC ranking/refinement for HOST buffers (numpy) and return a handle
+        for result() WITHOUT waiting for the GPU: pinned staging -> H2D -> CUDA graphs -> D2H into pinned result
+        buffers.  Two staging / result slots alternate, so a caller that submits pass t+1 before collecting pass t
+        overlaps its host-side staging with the GPU work (the serving loop; sample_and_rank is submit + result).
+        eps=None draws the noise on the device (reference: tf.random_normal inside the graph, model/model.py:262);
+        successive submissions use successive offsets of the stream selected by `seed`."""
         cfg = self.cfg
-        if self.use_graph and eps is not None and scene is not None and not torch.is_tensor(input_data):
-            # graph path: host -> pinned -> static device buffers -> one graph replay
+        if torch.is_tensor(input_data) or not self.use_graph:
+            out = self.forward(input_data, target_data, eps, scene, seed=seed)
+            B = out["Y_refined"].shape[0] // (cfg.max_num_obj * cfg.K)
+            hp = self._path(B)
+            slot = 0
+        else:
             B = int(np.shape(input_data)[0])
             hp = self._path(B)
-            if hp.graph_gen is None:
-                pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data), ("eps", eps), ("scene", scene))]
-                hp.capture_split(*[p.to(self.device) for p in pins])
-            pins = [self._pin(n, a) for n, a in (("obs", input_data), ("tgt", target_data))]
-            # eps and the scene images (the two large inputs) are staged while graphs that do not need them run
-            out = hp.replay_split(*pins, stage_eps=lambda: self._pin("eps", eps),
-                                  stage_scene=lambda: self._pin("scene", scene))
-        else:
-            out = self.forward(input_data, target_data, eps, scene)
-        B = out["Y_refined"].shape[0] // (cfg.max_num_obj * cfg.K)
-        key = ("res", B)
+            slot = self._submit_no & 1
+            self._submit_no += 1
+            ev = self._slot_done.get((B, slot))
+            if ev is not None:
+                ev.synchronize()           # the pass that last used this slot's pinned buffers has finished
+            if scene is None:
+                scene = np.zeros((B, cfg.scene_size, cfg.scene_size, 3), np.float32)
+            if hp.graph_gen is None or hp.split_draws != (eps is None):
+                pins = [self._pin(n, a, slot) for n, a in (("obs", input_data), ("tgt", target_data), ("scene", scene))]
+                e0 = None if eps is None else self._pin("eps", eps, slot).to(self.device)
+                hp.capture_split(pins[0].to(self.device), pins[1].to(self.device), e0, pins[2].to(self.device))
+            pins = [self._pin(n, a, slot) for n, a in (("obs", input_data), ("tgt", target_data))]
+            if eps is None:
+                hp.set_noise(2 if seed is None else seed, self._noise_offset)
+                self._noise_offset += 1
+            # eps and the scene images (the large inputs) are staged while graphs that do not need them run
+            out = hp.replay_split(*pins, stage_eps=None if eps is None else (lambda: self._pin("eps", eps, slot)),
+                                  stage_scene=lambda: self._pin("scene", scene, slot))
+        key = ("res", B, slot)
         if key not in self._pinned:
             self._pinned[key] = (torch.empty_like(out["Y_refined"], device="cpu").pin_memory(),
                                  torch.empty_like(out["ioc_scores"], device="cpu").pin_memory(),
@@ -254,10 +270,38 @@ class DESIREModel(object):
         y, s, c = self._pinned[key]
         y.copy_(out["Y_refined"], non_blocking=True)
         s.copy_(out["ioc_scores"], non_blocking=True)
-        c.copy_(self._path(B).buf["cost"], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        N, K, Tf = cfg.max_num_obj, cfg.K, cfg.pred_length
+        c.copy_(hp.buf["cost"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._slot_done[(B, slot)] = ev
+        return (B, slot, ev)
+
+    def result(self, handle):
+        """Wait for a submit() and return (Y_refined [B,N,K,Tf,2], scores [iters,B,N,K], cost) as numpy views of the
+        slot's pinned result buffers (valid until the slot is reused two submissions later)."""
+        B, slot, ev = handle
+        ev.synchronize()
+        y, s, c = self._pinned[("res", B, slot)]
+        N, K, Tf = self.cfg.max_num_obj, self.cfg.K, self.cfg.pred_length
         return (y.numpy().reshape(B, N, K, Tf, 2), s.numpy().reshape(-1, B, N, K), float(c[0]))
+
+    def sample_and_rank(self, input_data, target_data, eps=None, scene=None, seed=None):
+        """End-to-end public call with HOST buffers: stage inputs, run sample generation + IOC
+        ranking/refinement, copy the ranked result back.  Returns (Y_refined [B,N,K,Tf,2],
+        scores [iters,B,N,K], cost) as numpy."""
+        return self.result(self.submit(input_data, target_data, eps, scene, seed))
+
+    def rank_stream(self, batches, seed=None):
+        """Throughput loop over an iterable of (input_data, target_data, scene) host batches: pass t+1 is staged and
+        enqueued while the GPU runs pass t.  Yields result() tuples in order."""
+        pending = None
+        for inp, tgt, scene in batches:
+            h = self.submit(inp, tgt, None, scene, seed)
+            if pending is not None:
+                yield self.result(pending)
+            pending = h
+        if pending is not None:
+            yield self.result(pending)
 
     def sample(self, sess, traj, grid, dimensions, true_traj, num=10):
         """Signature of model/model.py:613 kept as an entry point (the reference body is a broken

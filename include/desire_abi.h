@@ -191,6 +191,14 @@ int desire_recon_rows_fwd(const float* Yhat, const float* target, int M, int K, 
                           desire_stream_t stream);
 int desire_masked_cost_fwd(const float* rows_a, const float* rows_b, const float* obs, int M, int Tp,
                            float* cost, desire_stream_t stream);
+/* D8 existence (model/model.py:206,214,351-366: an object contributes only if neither obj_id nor target_obj_id is
+ * the non-existent id 0).  Every entry point that takes `obs` treats "id at observed frame 0 != 0" as "exists";
+ * this writes obs_out [M,Tp,3] = obs with that id zeroed for agents that are absent
+ *   mode 0: at observed frame 0 only (identity copy);
+ *   mode 1: at observed frame 0, at the last observed frame, or at any of the Tf target frames (target [M,Tf,3]).
+ * Pass obs_out instead of obs to the rest of the path. */
+int desire_existence_fwd(const float* obs, const float* target, int M, int Tp, int Tf, int mode, float* obs_out,
+                         desire_stream_t stream);
 
 /* ---- a14  stage 2 pieces (D11) */
 size_t desire_scene_cnn_workspace_bytes(int B, int Hi, int Wi);

@@ -466,6 +466,40 @@ def ioc_loss_rows(scores, snaps, Y_true, K):
     return rows
 
 
+def philox_randn(seed, offset, n):
+    """The device noise source restated (desire_randn_fwd; replaces tf.random_normal of model/model.py:262):
+    Philox4x32-10 (Salmon et al. 2011) on counter (i, offset) under key `seed`, four words -> four 24-bit uniforms
+    -> two Box-Muller pairs.  -> float32 [n]."""
+    quads = (n + 3) // 4
+    i = np.arange(quads, dtype=np.uint64)
+    M = np.uint64(0xFFFFFFFF)
+    c = [i & M, i >> np.uint64(32), np.full(quads, offset & 0xFFFFFFFF, np.uint64), np.full(quads, (offset >> 32) & 0xFFFFFFFF, np.uint64)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c[0], np.uint64(0xCD9E8D57) * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & M, p1 & M, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & M, p0 & M]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & M, (k1 + np.uint64(0xBB67AE85)) & M
+    z = np.empty((quads, 4), np.float32)
+    for h in range(2):
+        u1 = ((c[2 * h] >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+        u2 = ((c[2 * h + 1] >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+        rad = np.sqrt(np.float32(-2.0) * np.log(u1))
+        th = np.float32(6.283185307179586) * u2
+        z[:, 2 * h], z[:, 2 * h + 1] = rad * np.cos(th), rad * np.sin(th)
+    return z.reshape(-1)[:n]
+
+
+def existence_mask(input_data, target_data, mode=1):
+    """D8.  model/model.py:351-366 leaves an object out of the cost when `obj_id` (its id at the first frame of the
+    observed window, :214) or `target_obj_id` (undefined in the reference; its id in the target data) equals the
+    non-existent id 0 (:206).  mode 0: observed frame 0 only.  mode 1: the object must also be present at the last
+    observed frame (the read-out is anchored there, D3) and at every target frame.  -> [B,N] bool."""
+    m = input_data[:, :, 0, 0] != 0
+    if mode == 1:
+        m = m & (input_data[:, :, -1, 0] != 0) & (target_data[:, :, :, 0] != 0).all(-1)
+    return m
+
+
 # --------------------------------------------------------------------------- whole path
 def forward(P, cfg, input_data, target_data, eps, scene_img, r2_edges, dirs):
     """Sample generation (a2-a13) + ranking/refinement (a14).
@@ -478,7 +512,7 @@ def forward(P, cfg, input_data, target_data, eps, scene_img, r2_edges, dirs):
     M = B * N
     X = input_data.reshape(M, Tp, 3)[..., 1:3]
     Y = target_data.reshape(M, Tf, 3)[..., 1:3]
-    mask = (input_data[:, :, 0, 0] != 0)                       # D8: id 0 == non-existent
+    mask = existence_mask(input_data, target_data, cfg.get("exist_mode", 1))     # D8: id 0 == non-existent
     out = {}
     out["rho_i"] = tconv(X, P["temporal_w"], P["temporal_b"])
     Hx = gru_encode(X, P["encx_wg"], P["encx_bg"], P["encx_wc"], P["encx_bc"])

@@ -37,7 +37,7 @@ def np_tables(cfg, dtype=np.float32):
 def oracle_forward(cfg, P, batch, tables, margins=False):
     from oracle import desire_oracle as O
     inp, tgt, eps, scene = batch
-    return O.forward(P, dict(K=cfg.K, Z=cfg.Z, ioc_iters=cfg.ioc_iters, margins=margins), inp, tgt, eps, scene, *tables)
+    return O.forward(P, dict(K=cfg.K, Z=cfg.Z, ioc_iters=cfg.ioc_iters, margins=margins, exist_mode=cfg.exist_mode), inp, tgt, eps, scene, *tables)
 
 
 # A (scene, sample) group's IOC outputs may differ from the oracle's by more than TOL only if some step of some

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 GTOL = 2e-3
 
 SHAPES = [(48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (16, 5, 2, 1, 0), (64, 10, 5, 2, 1), (32, 40, 2, 2, 0),
+          (128, 60, 20, 1, 3),   # the bench workload's per-scene size (BASELINE configs[1]: N=60, K=20, H=128)
           (16, 5, 2, 2, 5),      # every agent of the odd scene is non-existent (an empty scene in the minibatch)
           (16, 1, 1, 1, 0)]      # degenerate: one scene, one agent, one sample
 ACT = {"dYhat": "Yhat", "dx_z": "x_z", "dxr": "x_reconstr_mean", "dz": "zval", "dv": "vae_inputs"}
@@ -223,6 +224,7 @@ def compare_ioc(tp, G, out, ref_g, tol):
 
 
 @pytest.mark.parametrize("H,N,K,B,missing,iters", [(48, 8, 3, 2, 3, 2), (128, 12, 4, 3, 2, 2), (16, 5, 2, 1, 0, 1),
+                                                   (128, 60, 20, 1, 3, 2),     # bench per-scene size, single-pass schedule
                                                    (64, 10, 5, 2, 1, 3), (16, 5, 2, 2, 5, 2), (16, 1, 1, 1, 0, 2)])
 def test_ioc_backward_single_bin_strict(H, N, K, B, missing, iters):
     """One social bin (no bin edges, everything smooth): strict comparison against float64 autograd of the twin fed
@@ -237,7 +239,7 @@ def test_ioc_backward_single_bin_strict(H, N, K, B, missing, iters):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("H,N,K,B,missing", [(48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (32, 40, 2, 2, 0)])
+@pytest.mark.parametrize("H,N,K,B,missing", [(48, 8, 3, 2, 3), (128, 12, 4, 3, 2), (32, 40, 2, 2, 0), (128, 60, 20, 1, 3)])
 def test_ioc_backward_logpolar(H, N, K, B, missing):
     """Real 6x6 log-polar grid, one iteration: the twin is fed with the GPU's own stage-1 outputs (constants of the
     IOC module, D13) and bins in fp32 with the kernels' arithmetic, so both sides pool identical neighbour sets."""
