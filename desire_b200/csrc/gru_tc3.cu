@@ -25,6 +25,11 @@
 //   * when the candidate has its own TMEM columns (3H <= 512) the next step's r-group starts on the K chunks of h'
 //     as they are produced (h_ready[kc]); with H = 256 the gates fill all 512 columns, the candidate re-uses the r
 //     columns and the r-group waits for the whole tile;
+//   * h' leaves through TMA as well: E2b overwrites its own row of the xp_c box it has just read with the FP32 h'
+//     (same thread, same bytes), and a store thread sends the [128 x 32] box to HBM with cp.async.bulk.tensor
+//     (SASS UTMASTG) before it releases the ring slot — 128-byte rows instead of 32 scattered 16-byte sectors per
+//     store instruction (the direct stores were 15 % of the kernel's stall samples as MIO throttle, in the one
+//     phase that is not hidden behind an MMA group);
 //   * recurrent weights: packed BF16 hi/lo images (tc_pack_b, n-tile = H) streamed through a ring of 16 KB slots by
 //     1-D bulk copies with an evict-last L2 hint.
 //
@@ -45,7 +50,7 @@ using namespace tc;
 constexpr int TM = 128;
 constexpr int XBOX_BYTES = TM * 32 * 4;   // one box: 128 rows x 32 FP32 columns, 128-byte rows
 constexpr int EPI_WARPS = 16;             // 4 TMEM lane quadrants x 4 column groups
-constexpr int NTHR3 = (EPI_WARPS + 4) * 32;   // + one warpgroup: MMA issuer, loader, two idle warps (setmaxnreg is per warpgroup)
+constexpr int NTHR3 = (EPI_WARPS + 4) * 32;   // + one warpgroup: MMA issuer, weight loader, box loader, store thread
 
 template <int H, bool EX>
 struct Cfg3 {
@@ -67,7 +72,11 @@ struct Cfg3 {
   static constexpr int PRO = EX ? 2 * NKC : 0;         // prologue boxes: ex, then h0 (each in (chunk-in-thread, group) order)
   static constexpr int BPS = 3 * NKC;                  // boxes per step: xp_r | xp_u | xp_c
   static constexpr int WPS = 3 * NKA * SPC;            // weight slots per step
-  static constexpr int NBAR = 2 * NSW + 4 + NXB + 4 + NKA + NKC;
+  // columns per tcgen05.ld / wait in the three epilogue phases: as many as the registers allow
+  // (16 independent activation chains per wait instead of 8: the phases are latency-bound, 4 warps per scheduler)
+  static constexpr int GR1 = 16;                        // E1, E2a (32 does not fit the 112-register budget next to the state)
+  static constexpr int GR2 = (HC <= 32) ? 16 : 8;      // E2b holds two accumulator granules next to the state
+  static constexpr int NBAR = 2 * NSW + 4 + NXB + 4 + NKA + NKC + 4;
   static constexpr size_t SMEM = 1024 + 2 * (size_t)A_HALF + (size_t)NSW * SLOT_BYTES + (size_t)NXB * XBOX_BYTES + NBAR * 8 + 16;
   static_assert(NXB <= 4, "a column group may have one box in flight");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -78,10 +87,8 @@ struct Gru3Args {
   int xp_step;          // column offset of step t inside an xp row = t * xp_step
   const float* h0;      // non-EX: read directly (rows shared by h0_div samples); EX: through tm_h0
   int h0_div, ld_h0;
-  float* hs;
-  long hs_row_stride, hs_step_stride;
-  float* h_final;
-  int ld_hf;
+  int has_hs, hs_step;  // all states through tm_hs: step t at column t * hs_step
+  int has_hf;           // final state through tm_hf
   const uint8_t* wg;    // packed gates, n-tile H: [2][K/32] blocks (r columns, then u columns)
   const uint8_t* wc;    // packed candidate: [K/32] blocks
   int passes;
@@ -90,13 +97,25 @@ struct Gru3Args {
 };
 
 __device__ __forceinline__ float4 lds128(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
+  if (N == 32) tmem_ld32(taddr, v);
+  else if (N == 16) tmem_ld16(taddr, v);
+  else tmem_ld8(taddr, v);
+}
+template <int N>
+__device__ __forceinline__ void tmem_stn(uint32_t taddr, const float* v) {
+#pragma unroll
+  for (int i = 0; i < N; i += 8) tmem_st8(taddr + i, v + i);
+}
 
 // WD: watchdog on every mbarrier wait (DESIRE_GRU3_WATCHDOG=1; the tests set it) — a protocol error traps with the
 // name of the barrier instead of hanging the device.
 template <int H, bool EX, bool WD>
 __global__ void __launch_bounds__(NTHR3, 1)
     gru_tc3_kernel(const __grid_constant__ CUtensorMap tm_xp, const __grid_constant__ CUtensorMap tm_ex,
-                   const __grid_constant__ CUtensorMap tm_h0, Gru3Args a) {
+                   const __grid_constant__ CUtensorMap tm_h0, const __grid_constant__ CUtensorMap tm_hs,
+                   const __grid_constant__ CUtensorMap tm_hf, Gru3Args a) {
   using C = Cfg3<H, EX>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the swizzled boxes need 1024-byte alignment
@@ -114,7 +133,8 @@ __global__ void __launch_bounds__(NTHR3, 1)
   uint64_t* rh_ready = c_done + 1;
   uint64_t* h_ready = rh_ready + 1;       // [NKA]  A chunk kc holds its operand for the gate groups
   uint64_t* a_free = h_ready + C::NKA;    // [NKC]  the u-group has read state chunk kc
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(a_free + C::NKC);
+  uint64_t* hdone = a_free + C::NKC;      // [4]    column group: h' of its current box is in the ring slot
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(hdone + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long row0 = (long)blockIdx.x * TM;
@@ -132,10 +152,15 @@ __global__ void __launch_bounds__(NTHR3, 1)
     mbar_init(rh_ready, EPI_WARPS);
     for (int k = 0; k < C::NKA; ++k) mbar_init(&h_ready[k], 4);
     for (int k = 0; k < C::NKC; ++k) mbar_init(&a_free[k], 1);
+    for (int k = 0; k < 4; ++k) mbar_init(&hdone[k], 4);
     fence_barrier_init();
   }
   if (warp == EPI_WARPS) tmem_alloc<512>(tslot);
-  if (warp == EPI_WARPS + 1 && lane == 0) {
+  if (warp == EPI_WARPS + 3 && lane == 0) {
+    tma_prefetch_desc(&tm_hs);
+    tma_prefetch_desc(&tm_hf);
+  }
+  if (warp == EPI_WARPS + 2 && lane == 0) {
     tma_prefetch_desc(&tm_xp);
     if (EX) {
       tma_prefetch_desc(&tm_ex);
@@ -240,24 +265,33 @@ __global__ void __launch_bounds__(NTHR3, 1)
         const int slot = next_box(60);
         const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {               // 8 columns = one 16-byte chunk of the A operand
-          float acc[8];
-          tmem_ld8(trow + kc * 32 + g8 * 8, acc);
+        for (int gi = 0; gi < 32 / C::GR1; ++gi) {
+          float acc[C::GR1];
+          tmem_ldn<C::GR1>(trow + kc * 32 + gi * C::GR1, acc);
           tmem_ld_wait();
-          const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
-          const int hc = j * 32 + g8 * 8;
-          acc[0] = sigmoid_a(acc[0] + x0.x) * h[hc + 0];
-          acc[1] = sigmoid_a(acc[1] + x0.y) * h[hc + 1];
-          acc[2] = sigmoid_a(acc[2] + x0.z) * h[hc + 2];
-          acc[3] = sigmoid_a(acc[3] + x0.w) * h[hc + 3];
-          acc[4] = sigmoid_a(acc[4] + x1.x) * h[hc + 4];
-          acc[5] = sigmoid_a(acc[5] + x1.y) * h[hc + 5];
-          acc[6] = sigmoid_a(acc[6] + x1.z) * h[hc + 6];
-          acc[7] = sigmoid_a(acc[7] + x1.w) * h[hc + 7];
-          if (g8 == 0) mbar_wait_tag<WD>(&a_free[kc], par, 20 + kc);     // the u-group's MMAs have read h chunk kc
-          const Split8 s = split8(acc);
-          *reinterpret_cast<uint4*>(my_hi + ((C::KOFF + kc) * 4 + g8) * 2048) = s.hi;
-          *reinterpret_cast<uint4*>(my_lo + ((C::KOFF + kc) * 4 + g8) * 2048) = s.lo;
+#pragma unroll
+          for (int c8 = 0; c8 < C::GR1 / 8; ++c8) {      // 8 columns = one 16-byte chunk of the A operand
+            const int g8 = gi * (C::GR1 / 8) + c8;
+            const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
+            const int hc = j * 32 + g8 * 8;
+            float* v = acc + c8 * 8;
+            v[0] = sigmoid_a(v[0] + x0.x) * h[hc + 0];
+            v[1] = sigmoid_a(v[1] + x0.y) * h[hc + 1];
+            v[2] = sigmoid_a(v[2] + x0.z) * h[hc + 2];
+            v[3] = sigmoid_a(v[3] + x0.w) * h[hc + 3];
+            v[4] = sigmoid_a(v[4] + x1.x) * h[hc + 4];
+            v[5] = sigmoid_a(v[5] + x1.y) * h[hc + 5];
+            v[6] = sigmoid_a(v[6] + x1.z) * h[hc + 6];
+            v[7] = sigmoid_a(v[7] + x1.w) * h[hc + 7];
+          }
+          if (gi == 0) mbar_wait_tag<WD>(&a_free[kc], par, 20 + kc);     // the u-group's MMAs have read h chunk kc
+#pragma unroll
+          for (int c8 = 0; c8 < C::GR1 / 8; ++c8) {
+            const int g8 = gi * (C::GR1 / 8) + c8;
+            const Split8 sp = split8(acc + c8 * 8);
+            *reinterpret_cast<uint4*>(my_hi + ((C::KOFF + kc) * 4 + g8) * 2048) = sp.hi;
+            *reinterpret_cast<uint4*>(my_lo + ((C::KOFF + kc) * 4 + g8) * 2048) = sp.lo;
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&xempty[slot]);
@@ -276,20 +310,25 @@ __global__ void __launch_bounds__(NTHR3, 1)
         const int slot = next_box(62);
         const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float acc[8];
-          tmem_ld8(trow + H + kc * 32 + g8 * 8, acc);
+        for (int gi = 0; gi < 32 / C::GR1; ++gi) {
+          float acc[C::GR1];
+          tmem_ldn<C::GR1>(trow + H + kc * 32 + gi * C::GR1, acc);
           tmem_ld_wait();
-          const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
-          acc[0] = sigmoid_a(acc[0] + x0.x);
-          acc[1] = sigmoid_a(acc[1] + x0.y);
-          acc[2] = sigmoid_a(acc[2] + x0.z);
-          acc[3] = sigmoid_a(acc[3] + x0.w);
-          acc[4] = sigmoid_a(acc[4] + x1.x);
-          acc[5] = sigmoid_a(acc[5] + x1.y);
-          acc[6] = sigmoid_a(acc[6] + x1.z);
-          acc[7] = sigmoid_a(acc[7] + x1.w);
-          tmem_st8(trow + H + kc * 32 + g8 * 8, acc);
+#pragma unroll
+          for (int c8 = 0; c8 < C::GR1 / 8; ++c8) {
+            const int g8 = gi * (C::GR1 / 8) + c8;
+            const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
+            float* v = acc + c8 * 8;
+            v[0] = sigmoid_a(v[0] + x0.x);
+            v[1] = sigmoid_a(v[1] + x0.y);
+            v[2] = sigmoid_a(v[2] + x0.z);
+            v[3] = sigmoid_a(v[3] + x0.w);
+            v[4] = sigmoid_a(v[4] + x1.x);
+            v[5] = sigmoid_a(v[5] + x1.y);
+            v[6] = sigmoid_a(v[6] + x1.z);
+            v[7] = sigmoid_a(v[7] + x1.w);
+          }
+          tmem_stn<C::GR1>(trow + H + kc * 32 + gi * C::GR1, acc);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&xempty[slot]);
@@ -299,45 +338,41 @@ __global__ void __launch_bounds__(NTHR3, 1)
       // ---------------- E2b (exposed): candidate, state update, h' -> registers, HBM and the A operand
       mbar_wait_tag<WD>(c_done, par, 12);
       tc_fence_after();
-      float* hout = (ok && a.hs) ? a.hs + row * a.hs_row_stride + (long)t * a.hs_step_stride + cbeg : nullptr;
-      float* hfin = (ok && a.h_final && t == a.T - 1) ? a.h_final + row * (long)a.ld_hf + cbeg : nullptr;
 #pragma unroll
       for (int j = 0; j < C::NB; ++j) {
         const int kc = cs * C::NB + j;
         const int slot = next_box(64);
-        const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
+        uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float accc[8], u[8];
-          tmem_ld8(trow + C::CAND_COL + kc * 32 + g8 * 8, accc);
-          tmem_ld8(trow + H + kc * 32 + g8 * 8, u);
+        for (int gi = 0; gi < 32 / C::GR2; ++gi) {
+          float accc[C::GR2], u[C::GR2];
+          tmem_ldn<C::GR2>(trow + C::CAND_COL + kc * 32 + gi * C::GR2, accc);
+          tmem_ldn<C::GR2>(trow + H + kc * 32 + gi * C::GR2, u);
           tmem_ld_wait();
-          const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
-          const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-          const int hc = j * 32 + g8 * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float cd = tanh_a(accc[i] + xs[i]);
-            const float hn = fmaf(u[i], h[hc + i] - cd, cd);     // u*h + (1-u)*cd
-            h[hc + i] = hn;
+          for (int c8 = 0; c8 < C::GR2 / 8; ++c8) {
+            const int g8 = gi * (C::GR2 / 8) + c8;
+            const float4 x0 = lds128(box + swz128(rloc, g8 * 2)), x1 = lds128(box + swz128(rloc, g8 * 2 + 1));
+            const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            const int hc = j * 32 + g8 * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float cd = tanh_a(accc[c8 * 8 + i] + xs[i]);
+              h[hc + i] = fmaf(u[c8 * 8 + i], h[hc + i] - cd, cd);     // u*h + (1-u)*cd
+            }
+            // h' replaces this thread's row of the xp_c box (read above): the store thread sends the box to HBM
+            *reinterpret_cast<float4*>(box + swz128(rloc, g8 * 2)) = make_float4(h[hc], h[hc + 1], h[hc + 2], h[hc + 3]);
+            *reinterpret_cast<float4*>(box + swz128(rloc, g8 * 2 + 1)) = make_float4(h[hc + 4], h[hc + 5], h[hc + 6], h[hc + 7]);
+            const Split8 sp = split8(&h[hc]);
+            *reinterpret_cast<uint4*>(my_hi + ((C::KOFF + kc) * 4 + g8) * 2048) = sp.hi;
+            *reinterpret_cast<uint4*>(my_lo + ((C::KOFF + kc) * 4 + g8) * 2048) = sp.lo;
           }
-          if (hout) {
-            __stcs(reinterpret_cast<float4*>(hout + hc), make_float4(h[hc], h[hc + 1], h[hc + 2], h[hc + 3]));
-            __stcs(reinterpret_cast<float4*>(hout + hc + 4), make_float4(h[hc + 4], h[hc + 5], h[hc + 6], h[hc + 7]));
-          }
-          if (hfin) {
-            *reinterpret_cast<float4*>(hfin + hc) = make_float4(h[hc], h[hc + 1], h[hc + 2], h[hc + 3]);
-            *reinterpret_cast<float4*>(hfin + hc + 4) = make_float4(h[hc + 4], h[hc + 5], h[hc + 6], h[hc + 7]);
-          }
-          const Split8 s = split8(&h[hc]);
-          *reinterpret_cast<uint4*>(my_hi + ((C::KOFF + kc) * 4 + g8) * 2048) = s.hi;
-          *reinterpret_cast<uint4*>(my_lo + ((C::KOFF + kc) * 4 + g8) * 2048) = s.lo;
         }
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&xempty[slot]);
+          mbar_arrive(&hdone[cs]);                  // the store thread releases the slot once the box has left
           mbar_arrive(&h_ready[C::KOFF + kc]);
         }
       }
@@ -401,62 +436,75 @@ __global__ void __launch_bounds__(NTHR3, 1)
       }
     }
   } else {
-    // ======================================================================== loader: weight ring + box ring
-    if (warp == EPI_WARPS + 1 && lane == 0) {
-      const uint32_t totW = (uint32_t)a.T * C::WPS, totX = C::PRO + (uint32_t)a.T * C::BPS;
+    // ======================================================================== loaders: warp 17 weights, warp 18 boxes
+    if (warp == EPI_WARPS + 2 && lane == 0) {
+      const uint32_t totX = C::PRO + (uint32_t)a.T * C::BPS;
       const uint64_t xpol = a.xp_const ? L2_EVICT_LAST : L2_EVICT_FIRST;
-      uint32_t itw = 0, g = 0;
-      while (itw < totW || g < totX) {
-        if (g < totX) {
-          const int slot = g % C::NXB;
-          if (mbar_test_wait(&xempty[slot], ((g / C::NXB) & 1) ^ 1)) {
-            // box g: prologue [ex x NKC | h0 x NKC] (EX only), then per step [xp_r | xp_u | xp_c] x NKC; inside a
-            // block of NKC boxes, box w = j*4 + cs is chunk j of column group cs
-            const void* tm = &tm_xp;
-            int c0;
-            const int w = ((int)g < C::PRO ? g : g - C::PRO) % C::NKC;
-            const int col = (w & 3) * C::HC + (w >> 2) * 32;
-            if ((int)g < C::PRO) {
-              tm = (g < C::NKC) ? (const void*)&tm_ex : (const void*)&tm_h0;
-              c0 = col;
-            } else {
-              const uint32_t t = (g - C::PRO) / C::BPS, ib = (g - C::PRO) % C::BPS;
-              c0 = (int)(t * a.xp_step + (ib / C::NKC) * H + col);
-            }
-            uint64_t* fb = &xfull[w & 3];
-            if (a.dbg & 1) {
-              mbar_arrive(fb);
-            } else {
-              mbar_arrive_expect_tx(fb, XBOX_BYTES);
-              tma_load_2d(xring + (size_t)slot * XBOX_BYTES, tm, c0, (int)row0, fb, (int)g < C::PRO ? L2_EVICT_FIRST : xpol);
-            }
-            ++g;
-          }
+      for (uint32_t g = 0; g < totX; ++g) {
+        const int slot = g % C::NXB;
+        mbar_wait_tag<WD>(&xempty[slot], ((g / C::NXB) & 1) ^ 1, 80 + slot);
+        // box g: prologue [ex x NKC | h0 x NKC] (EX only), then per step [xp_r | xp_u | xp_c] x NKC; inside a
+        // block of NKC boxes, box w = j*4 + cs is chunk j of column group cs
+        const void* tm = &tm_xp;
+        int c0;
+        const int w = ((int)g < C::PRO ? g : g - C::PRO) % C::NKC;
+        const int col = (w & 3) * C::HC + (w >> 2) * 32;
+        if ((int)g < C::PRO) {
+          tm = (g < C::NKC) ? (const void*)&tm_ex : (const void*)&tm_h0;
+          c0 = col;
+        } else {
+          const uint32_t t = (g - C::PRO) / C::BPS, ib = (g - C::PRO) % C::BPS;
+          c0 = (int)(t * a.xp_step + (ib / C::NKC) * H + col);
         }
-        if (itw < totW) {
-          const int slot = itw % C::NSW;
-          if (mbar_test_wait(&wempty[slot], ((itw / C::NSW) & 1) ^ 1)) {
-            if (a.dbg & 2) {
-              mbar_arrive(&wfull[slot]);
-              ++itw;
-              continue;
+        uint64_t* fb = &xfull[w & 3];
+        if (a.dbg & 1) {
+          mbar_arrive(fb);
+        } else {
+          mbar_arrive_expect_tx(fb, XBOX_BYTES);
+          tma_load_2d(xring + (size_t)slot * XBOX_BYTES, tm, c0, (int)row0, fb, (int)g < C::PRO ? L2_EVICT_FIRST : xpol);
+        }
+      }
+    } else if (warp == EPI_WARPS + 3 && lane == 0) {
+      // ---- store thread: the E2b boxes (now holding h') in ring order -> HBM, then the slot is free again
+      for (int t = 0; t < a.T; ++t)
+        for (int j = 0; j < C::NB; ++j)
+          for (int cs = 0; cs < 4; ++cs) {
+            const uint32_t g = C::PRO + (uint32_t)t * C::BPS + 2 * C::NKC + j * 4 + cs;
+            const int slot = g % C::NXB;
+            mbar_wait_tag<WD>(&hdone[cs], (uint32_t)(t * C::NB + j) & 1, 95);
+            const uint8_t* box = xring + (size_t)slot * XBOX_BYTES;
+            const int col = cs * C::HC + j * 32;
+            const bool last = t == a.T - 1;
+            if (a.has_hs) tma_store_2d(&tm_hs, box, t * a.hs_step + col, (int)row0);
+            if (a.has_hf && last) tma_store_2d(&tm_hf, box, col, (int)row0);
+            if (a.has_hs || (a.has_hf && last)) {
+              tma_store_commit();
+              tma_store_wait_read();
             }
-            const uint32_t wi = itw % C::WPS;
-            const int nb = wi / (C::NKA * C::SPC), r = wi % (C::NKA * C::SPC);
-            const int blk = r / C::SPC, part = r % C::SPC;
-            const uint8_t* src = (nb < 2 ? a.wg + ((size_t)nb * C::NKA + blk) * C::BLOCK_BYTES
-                                         : a.wc + (size_t)blk * C::BLOCK_BYTES);
-            uint8_t* dst = wring + (size_t)slot * C::SLOT_BYTES;
-            mbar_arrive_expect_tx(&wfull[slot], C::SLOT_BYTES);
-            if (C::SPC == 1) {
-              bulk_g2s_hint(dst, src, C::SLOT_BYTES, &wfull[slot], L2_EVICT_LAST);
-            } else {                               // half a block: chunks {2p, 2p+1} of hi, then of lo
-              bulk_g2s_hint(dst, src + (size_t)part * C::SLOT_HALF, C::SLOT_HALF, &wfull[slot], L2_EVICT_LAST);
-              bulk_g2s_hint(dst + C::SLOT_HALF, src + 4 * H * 16 + (size_t)part * C::SLOT_HALF, C::SLOT_HALF, &wfull[slot],
-                            L2_EVICT_LAST);
-            }
-            ++itw;
+            mbar_arrive_cnt(&xempty[slot], 4);
           }
+    } else if (warp == EPI_WARPS + 1 && lane == 0) {
+      const uint32_t totW = (uint32_t)a.T * C::WPS;
+      for (uint32_t itw = 0; itw < totW; ++itw) {
+        const int slot = itw % C::NSW;
+        mbar_wait_tag<WD>(&wempty[slot], ((itw / C::NSW) & 1) ^ 1, 90 + slot);
+        if (a.dbg & 2) {
+          mbar_arrive(&wfull[slot]);
+          continue;
+        }
+        const uint32_t wi = itw % C::WPS;
+        const int nb = wi / (C::NKA * C::SPC), r = wi % (C::NKA * C::SPC);
+        const int blk = r / C::SPC, part = r % C::SPC;
+        const uint8_t* src = (nb < 2 ? a.wg + ((size_t)nb * C::NKA + blk) * C::BLOCK_BYTES
+                                     : a.wc + (size_t)blk * C::BLOCK_BYTES);
+        uint8_t* dst = wring + (size_t)slot * C::SLOT_BYTES;
+        mbar_arrive_expect_tx(&wfull[slot], C::SLOT_BYTES);
+        if (C::SPC == 1) {
+          bulk_g2s_hint(dst, src, C::SLOT_BYTES, &wfull[slot], L2_EVICT_LAST);
+        } else {                               // half a block: chunks {2p, 2p+1} of hi, then of lo
+          bulk_g2s_hint(dst, src + (size_t)part * C::SLOT_HALF, C::SLOT_HALF, &wfull[slot], L2_EVICT_LAST);
+          bulk_g2s_hint(dst + C::SLOT_HALF, src + 4 * H * 16 + (size_t)part * C::SLOT_HALF, C::SLOT_HALF, &wfull[slot],
+                        L2_EVICT_LAST);
         }
       }
     }
@@ -499,11 +547,13 @@ int make_tmap_rows32(CUtensorMap* tm, const float* base, long rows, long row_str
   return DESIRE_OK;
 }
 
+struct Maps3 {
+  CUtensorMap xp, ex, h0, hs, hf;
+};
 template <int H, bool EX, bool WD>
-int launch3(const CUtensorMap& tx, const CUtensorMap& te, const CUtensorMap& th, const Gru3Args& a, unsigned grid,
-            cudaStream_t st) {
+int launch3(const Maps3& m, const Gru3Args& a, unsigned grid, cudaStream_t st) {
   DESIRE_ENSURE_SMEM((gru_tc3_kernel<H, EX, WD>), (Cfg3<H, EX>::SMEM));
-  DESIRE_LAUNCH(st, (gru_tc3_kernel<H, EX, WD><<<grid, NTHR3, Cfg3<H, EX>::SMEM, st>>>(tx, te, th, a)));
+  DESIRE_LAUNCH(st, (gru_tc3_kernel<H, EX, WD><<<grid, NTHR3, Cfg3<H, EX>::SMEM, st>>>(m.xp, m.ex, m.h0, m.hs, m.hf, a)));
   return DESIRE_OK;
 }
 
@@ -529,6 +579,12 @@ bool gru_tc3_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_byte
     if ((a.H != 128 && a.H != 256) || a.Ka != 0) return false;
     if (a.T > 1 && !a.hs && !a.h_final) return false;
   }
+  // the states leave through tensor maps as well
+  if (a.hs && (!tma_ok(a.hs, a.hs_row_stride) || a.hs_step_stride % 4 != 0 ||
+               a.hs_row_stride < (long)(a.T - 1) * a.hs_step_stride + a.H))
+    return false;
+  if (a.h_final && (!tma_ok(a.h_final, a.ld_hf) || a.ld_hf < a.H)) return false;
+  if (!a.hs && !a.h_final) return false;
   if (a.packed ? a.packed_fmt != 3 : (!pack_ws || pack_bytes < gru_tc3_pack_bytes(a.H, a.Ka))) return false;
   return encode_fn() != nullptr;
 }
@@ -552,8 +608,8 @@ int gru_seq_tc3(const GruSeqArgs& s, void* pack_ws, cudaStream_t st) {
   a.R = s.R; a.T = s.T;
   a.xp_step = (int)s.xp_step_stride;
   a.h0 = s.h0; a.h0_div = s.h0_div > 0 ? s.h0_div : 1; a.ld_h0 = s.ld_h0;
-  a.hs = s.hs; a.hs_row_stride = s.hs_row_stride; a.hs_step_stride = s.hs_step_stride;
-  a.h_final = s.h_final; a.ld_hf = s.ld_hf;
+  a.has_hs = s.hs ? 1 : 0; a.hs_step = (int)s.hs_step_stride;
+  a.has_hf = s.h_final ? 1 : 0;
   a.passes = gemm_mode() == 1 ? 1 : 3;
   a.xp_const = (s.xp_step_stride == 0 && s.T > 1) ? 1 : 0;
   {
@@ -568,19 +624,20 @@ int gru_seq_tc3(const GruSeqArgs& s, void* pack_ws, cudaStream_t st) {
   if (!s.packed) DESIRE_TRY(gru_tc3_pack(s.w_g, s.w_c, H, s.Ka, pack_ws, gru_tc3_pack_bytes(H, s.Ka), st));
   a.wg = pg;
   a.wc = pg + align_up(tc_pack_bytes(s.Ka + H, 2 * H, H));
-  CUtensorMap tx, te, th;
-  DESIRE_TRY(make_tmap_rows32(&tx, s.xp, s.R, s.xp_row_stride));
-  te = tx;
-  th = tx;
+  Maps3 m;
+  DESIRE_TRY(make_tmap_rows32(&m.xp, s.xp, s.R, s.xp_row_stride));
+  m.ex = m.h0 = m.hs = m.hf = m.xp;
   if (s.ex) {
-    DESIRE_TRY(make_tmap_rows32(&te, s.ex, s.R, s.ld_ex));
-    DESIRE_TRY(make_tmap_rows32(&th, s.h0, s.R, s.ld_h0));
+    DESIRE_TRY(make_tmap_rows32(&m.ex, s.ex, s.R, s.ld_ex));
+    DESIRE_TRY(make_tmap_rows32(&m.h0, s.h0, s.R, s.ld_h0));
   }
+  if (s.hs) DESIRE_TRY(make_tmap_rows32(&m.hs, s.hs, s.R, s.hs_row_stride));
+  if (s.h_final) DESIRE_TRY(make_tmap_rows32(&m.hf, s.h_final, s.R, s.ld_hf));
   const unsigned grid = (unsigned)(((long)s.R + TM - 1) / TM);
   static const bool wd = env_flag("DESIRE_GRU3_WATCHDOG");
-  if (s.ex) return wd ? launch3<128, true, true>(tx, te, th, a, grid, st) : launch3<128, true, false>(tx, te, th, a, grid, st);
-  if (H == 128) return wd ? launch3<128, false, true>(tx, te, th, a, grid, st) : launch3<128, false, false>(tx, te, th, a, grid, st);
-  return wd ? launch3<256, false, true>(tx, te, th, a, grid, st) : launch3<256, false, false>(tx, te, th, a, grid, st);
+  if (s.ex) return wd ? launch3<128, true, true>(m, a, grid, st) : launch3<128, true, false>(m, a, grid, st);
+  if (H == 128) return wd ? launch3<128, false, true>(m, a, grid, st) : launch3<128, false, false>(m, a, grid, st);
+  return wd ? launch3<256, false, true>(m, a, grid, st) : launch3<256, false, false>(m, a, grid, st);
 }
 
 }  // namespace desire

@@ -232,10 +232,14 @@ class HotPath:
                 nc, Bc = self.ioc_chains, self.B // self.ioc_chains
                 Mc, Rc = Bc * N, Bc * N * K
                 off = lambda t, rows_per_scene_block, c: C.c_void_p(t.data_ptr() + 4 * c * rows_per_scene_block)
+                # fork BEFORE anything of chain 0 is enqueued: every side stream waits for the same point of `cur`
+                # (wait_stream after chain 0's launches would make chains 1.. start only when chain 0 has finished)
+                fork = torch.cuda.Event()
+                fork.record(cur)
+                for s_side in self.ioc_streams:
+                    s_side.wait_event(fork)
                 for c in range(nc):
                     s_c = cur if c == 0 else self.ioc_streams[c - 1]
-                    if c > 0:
-                        s_c.wait_stream(cur)
                     ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims_c), C.byref(self.w_ioc),
                                           off(b["scene_features"], Bc * self.Hm * self.Hm * cfg.scene_channels, c),
                                           off(obs, Mc * Tp * 3, c), Tp, off(b["HxHy"], Mc * 2 * H, c), 2 * H,
