@@ -8,13 +8,10 @@
 //   prologue   the groups' hidden vectors ([128][H+4] FP32, padded rows) and positions are staged in shared
 //              memory once; each producer thread (one row) bins its N-1 neighbours with the oracle's exact
 //              arithmetic and counting-sorts them into a private per-bin list (ascending j);
-//   warps 0-15 producers, as four GROUPS of four warps.  A K stage is 32 columns of one bin; stage ks is produced by
-//              group ks % 4 into ring slot ks % 4 (a group owns its slot), thread = tile row: it sums the listed
-//              neighbours' 32-column slices from shared memory in list order, scales by 1/count, splits to BF16 hi/lo
-//              and stores the four 16-byte chunks of the UMMA A operand.  The fixed cost of handing a stage over
-//              (empty-wait, proxy fence, arrive: ~2 us in the first design, where all 16 warps worked on every stage
-//              of a 2-deep ring and the tensor pipe sat at 28 %) is now paid once per FOUR stages by each warp, so
-//              the four groups together feed one stage per MMA period.
+//   warps 0-15 producers (16 warps so every SM sub-partition has four to hide shared-memory latency).  Warp w owns
+//              tile rows 8w..8w+7 and 8 lanes cooperate on a row (one 16-byte chunk of a 64-column K stage each):
+//              sum the listed neighbours' slices from shared memory in list order, scale by 1/count, split to
+//              BF16 hi/lo, store as the UMMA A operand.  Neighbour loops diverge over 4 rows, not 32.
 //              Afterwards: epilogue (bias + ReLU) of a 32x32 accumulator block each;
 //   warp 16    tcgen05.mma issuer (M=128, N=H, 3xBF16), accumulator in TMEM;
 //   warp 17    streams the packed sp_w stages with 1-D bulk TMA copies.
@@ -26,9 +23,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int TM = 128, BK = 32, KC = 4, STAGES = 4;   // a stage = 32 columns of one bin = one packed 32-col block
-constexpr int NPW = 16;                 // producer/epilogue warps: 4 groups x 4 warps, thread = row inside a group
-constexpr int NGRP = 4;
+constexpr int TM = 128, BK = 64, KC = 8, STAGES = 2;   // a stage = 64 columns of one bin = two packed 32-col blocks
+constexpr int NPW = 16;                 // producer/epilogue warps: 4 threads per row, one 8-column chunk each
 constexpr int NTHR = (NPW + 2) * 32;
 constexpr int MAXG = 64;
 
@@ -80,7 +76,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
   const long grp0 = (long)blockIdx.x * gpt;
   const int nks = (G * H) / BK;
   const int a_half = KC * TM * 16;          // bytes of A_hi per stage (8 chunk planes)
-  const int b_blk = 4 * H * 16;             // bytes of the packed hi (or lo) half of one 32-column block = one stage
+  const int b_blk = 4 * H * 16;             // bytes of one packed hi (or lo) block of 32 columns
+  const int b_half = 2 * b_blk;             // per stage: two blocks, each hi+lo => 2*b_half bytes in total
 
   // global row of tile lane l (or -1): group grp0 + l/Npad = (b, k), agent i = l % Npad
   auto row_of = [&](int l) -> long {
@@ -95,7 +92,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
   if (tid < TM) rowmap[tid] = row_of(tid);     // the 64-bit divisions happen once per lane, not per element
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], NPW / NGRP + 1);      // the producing group's four warps + the weight loader
+      mbar_init(&full[s], NPW + 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(tfull, 1);
@@ -178,57 +175,65 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
 
-    // ===================== A producer.  Group grp = warp / 4 produces the stages ks = grp, grp + 4, ... into ring slot
-    // grp; inside the group thread = tile row (warp % 4 = TMEM lane quadrant of the later epilogue), all 32 columns of
-    // the stage.  A warp stores 32 consecutive rows of one chunk plane = 512 contiguous bytes (conflict-free).
-    const int grp = warp >> 2;
-    const int prow = (warp & 3) * 32 + lane;
+    // ===================== A producer.  Warp w owns tile rows 8w..8w+7: lane -> (row 8w + lane%8, chunk pair
+    // lane/8 and 4 + lane/8 of the 64-column stage).  A quarter-warp therefore stores 8 consecutive rows of one
+    // chunk plane = 128 contiguous bytes (conflict-free), and every lane converts exactly the 16 values it stores.
+    const int prow = warp * 8 + (lane & 7);
+    const int kq = lane >> 3;
     const uint8_t* off = lists + (size_t)prow * L.list_stride;
     const uint8_t* lst = off + G + 1;
-    const float* hrow = hs + (size_t)((prow / Npad) * Npad) * L.hs_ld;
-    const uint32_t aoff = prow * 16;
+    const float* hrow = hs + (size_t)((prow / Npad) * Npad) * L.hs_ld + kq * 8;
+    const uint32_t aoff = kq * TM * 16 + prow * 16;
+    // list metadata is prefetched one bin ahead (off[] is a prefix array: the next bin starts where this one ends), so a
+    // stage never starts with a chain of dependent shared-memory loads
     const int spb = H / BK;                       // K stages per bin
-    uint8_t* my_stage = stages + (size_t)grp * L.stage_bytes + aoff;
-    for (int ks = grp; ks < nks; ks += NGRP) {
+    int g = 0, half = 0;
+    int o0 = 0, o1 = off[1], o1n = G > 1 ? off[2] : 0;
+    int jf = lst[0], jfn = lst[o1];              // first member of this / the next bin (unused when the bin is empty)
+    for (int ks = 0; ks < nks; ++ks) {
+      const int slot = ks % STAGES;
       const uint32_t ph = (ks / STAGES) & 1;
-      const int g = ks / spb, col = (ks - g * spb) * BK;
-      const int o0 = off[g], o1 = off[g + 1];
-      uint4 hi[KC], lo[KC];
-#pragma unroll
-      for (int c = 0; c < KC; ++c) hi[c] = lo[c] = make_uint4(0, 0, 0, 0);
+      const int col = half * BK;
+      uint4 hi0 = make_uint4(0, 0, 0, 0), lo0 = hi0, hi1 = hi0, lo1 = hi0;
       if (o1 > o0) {
-        float v[BK];
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < BK; ++i) v[i] = 0.f;
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
         for (int o = o0; o < o1; ++o) {
-          const float4* p = reinterpret_cast<const float4*>(hrow + (size_t)lst[o] * L.hs_ld + col);
-#pragma unroll
-          for (int c = 0; c < BK / 4; ++c) {
-            const float4 x = p[c];
-            v[4 * c] += x.x; v[4 * c + 1] += x.y; v[4 * c + 2] += x.z; v[4 * c + 3] += x.w;
-          }
+          const int jm = (o == o0) ? jf : (int)lst[o];
+          const float4* p = reinterpret_cast<const float4*>(hrow + (size_t)jm * L.hs_ld + col);
+          const float4 x0 = p[0], y0 = p[1], x1 = p[8], y1 = p[9];      // chunks kq and kq+4 (32 floats apart)
+          v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w;
+          v[4] += y0.x; v[5] += y0.y; v[6] += y0.z; v[7] += y0.w;
+          v[8] += x1.x; v[9] += x1.y; v[10] += x1.z; v[11] += x1.w;
+          v[12] += y1.x; v[13] += y1.y; v[14] += y1.z; v[15] += y1.w;
         }
         if (o1 - o0 > 1) {
           const float inv = __frcp_rn((float)(o1 - o0));       // mean = sum * (1/count)
 #pragma unroll
-          for (int i = 0; i < BK; ++i) v[i] *= inv;
+          for (int i = 0; i < 16; ++i) v[i] *= inv;
         }
-#pragma unroll
-        for (int c = 0; c < KC; ++c) {
-          const Split8 sp = split8(v + 8 * c);
-          hi[c] = sp.hi;
-          lo[c] = sp.lo;
-        }
+        const Split8 s0 = split8(v), s1 = split8(v + 8);
+        hi0 = s0.hi; lo0 = s0.lo; hi1 = s1.hi; lo1 = s1.lo;
       }
-      mbar_wait(&empty[grp], ph ^ 1);
-#pragma unroll
-      for (int c = 0; c < KC; ++c) {
-        *reinterpret_cast<uint4*>(my_stage + c * TM * 16) = hi[c];
-        *reinterpret_cast<uint4*>(my_stage + a_half + c * TM * 16) = lo[c];
-      }
+      mbar_wait(&empty[slot], ph ^ 1);
+      uint8_t* sa = stages + (size_t)slot * L.stage_bytes + aoff;
+      *reinterpret_cast<uint4*>(sa) = hi0;
+      *reinterpret_cast<uint4*>(sa + 4 * TM * 16) = hi1;
+      *reinterpret_cast<uint4*>(sa + a_half) = lo0;
+      *reinterpret_cast<uint4*>(sa + a_half + 4 * TM * 16) = lo1;
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[grp]);
+      if (lane == 0) mbar_arrive(&full[slot]);
+      if (++half == spb) {                        // next bin: shift the prefetched metadata, fetch the bin after it
+        half = 0;
+        ++g;
+        o0 = o1;
+        o1 = o1n;
+        jf = jfn;
+        o1n = g + 1 < G ? off[g + 2] : 0;
+        jfn = lst[o1];
+      }
     }
     const long myrow = rowmap[tid & (TM - 1)];
 
@@ -267,8 +272,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
         const uint32_t sb = sa + 2 * a_half;
 #pragma unroll
         for (int j = 0; j < BK / 16; ++j) {
-          // A: chunk planes 2j, 2j+1 of the stage; B: the packed block { hi [4][H][16B], lo [4][H][16B] }
-          const uint32_t sbb = sb + j * 2 * lbo_b;
+          // A: chunk planes 2j, 2j+1 of the stage; B: packed block j/2 = { hi [4][H][16B], lo [4][H][16B] }
+          const uint32_t sbb = sb + (j >> 1) * (2 * b_blk) + (j & 1) * 2 * lbo_b;
           const uint64_t ahi = smem_desc(sa + j * 2 * lbo_a, lbo_a, 128);
           const uint64_t alo = smem_desc(sa + a_half + j * 2 * lbo_a, lbo_a, 128);
           const uint64_t bhi = smem_desc(sbb, lbo_b, 128);
@@ -290,8 +295,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_tc_kernel(SocialFcArgs a, i
       for (int ks = 0; ks < nks; ++ks) {
         const int slot = ks % STAGES;
         mbar_wait(&empty[slot], ((ks / STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[slot], 2 * b_blk);
-        bulk_g2s(stages + (size_t)slot * L.stage_bytes + 2 * a_half, src + (size_t)ks * (2 * b_blk), 2 * b_blk,
+        mbar_arrive_expect_tx(&full[slot], 2 * b_half);
+        bulk_g2s(stages + (size_t)slot * L.stage_bytes + 2 * a_half, src + (size_t)ks * (2 * b_half), 2 * b_half,
                  &full[slot]);
       }
     }
@@ -312,7 +317,7 @@ int npad_of(int N) {
 bool social_fc_tc_eligible(const SocialFcArgs& a) {
   const int G = a.n_rad * a.n_ang;
   if (gemm_mode() == 0 || !a.packed) return false;
-  if (a.H % 32 != 0 || a.H < 64 || a.H > 128 || a.ld_h % 4 != 0) return false;   // a 32-column stage never straddles bins
+  if (a.H % 64 != 0 || a.H < 64 || a.H > 128 || a.ld_h % 4 != 0) return false;   // a 64-column stage never straddles bins
   if (a.N > 128 || a.N < 1 || G > MAXG || G < 1) return false;
   const Layout L = make_layout(a.H, npad_of(a.N), G, a.n_rad, a.n_ang);
   return L.total <= 227 * 1024;
