@@ -1,6 +1,7 @@
 // Library identity, the thread-local error string, the launch counter and the optional per-kernel
 // CUDA-event timers of the C-ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -20,6 +21,20 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- visibility of the non-tensor-core / non-fused paths.  Shapes the tcgen05 kernels do not cover run on FP32
+// CUDA cores or on the materialising social path: correct, much slower, and easy not to notice.  Every such launch is
+// counted per kind (desire_fallback_count) and, with DESIRE_LOG_FALLBACK=1, the first one of each kind is reported.
+static std::atomic<long> g_fallbacks[DESIRE_FALLBACK_KINDS];
+void note_fallback(int kind, const char* what, int a, int b, int c) {
+  if (kind < 0 || kind >= DESIRE_FALLBACK_KINDS) return;
+  const long n = g_fallbacks[kind].fetch_add(1, std::memory_order_relaxed);
+  static const bool log = [] {
+    const char* e = getenv("DESIRE_LOG_FALLBACK");
+    return e && e[0] == '1';
+  }();
+  if (log && n == 0) fprintf(stderr, "libdesire_b200: fallback kind %d: %s (%d, %d, %d)\n", kind, what, a, b, c);
+}
 
 // ---- per-kernel timing: ProfScope names the slot, DESIRE_LAUNCH brackets the launch itself with two
 // events taken from a pool (no event creation on the hot path), so host-side preparation between
@@ -66,6 +81,9 @@ void prof_kernel_end(cudaStream_t st) {
 extern "C" int desire_version(void) { return DESIRE_ABI_VERSION; }
 extern "C" const char* desire_last_error(void) { return desire::g_err; }
 extern "C" long desire_launch_count(void) { return desire::g_launches.load(); }
+extern "C" long desire_fallback_count(int kind) {
+  return (kind >= 0 && kind < DESIRE_FALLBACK_KINDS) ? desire::g_fallbacks[kind].load() : -1;
+}
 
 extern "C" int desire_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(desire::g_prof_mu);

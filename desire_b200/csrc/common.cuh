@@ -12,6 +12,7 @@ namespace desire {
 
 void set_error(const char* fmt, ...);
 void count_launch();
+void note_fallback(int kind, const char* what, int a = 0, int b = 0, int c = 0);
 
 // Optional per-kernel timing (desire_prof_enable): a ProfScope brackets ONE launch with CUDA events on
 // the launching stream; desire_prof_read sums them per slot.  Off by default (zero overhead but a branch).

@@ -239,6 +239,7 @@ int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const 
           int M, int N, int K, int act, bool accumulate, cudaStream_t st, PackWs pw) {
   if (gemm_tc_eligible(M, N, K, pw.p, pw.bytes))
     return gemm_tc(A, lda, B, ldb, trans_b, bias, C, ldc, M, N, K, act, accumulate, pw.p, st);
+  note_fallback(DESIRE_FALLBACK_GEMM_FP32, "GEMM on FP32 CUDA cores (M, N, K)", M, N, K);
   // split very tall problems so gridDim.y stays legal
   const int MAXM = 65535 * BM;
   for (long m0 = 0; m0 < M; m0 += MAXM) {
@@ -253,6 +254,7 @@ int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const
                  int M, int N, int K, int act, cudaStream_t st, PackWs pw) {
   if (gemm_tc_eligible(M, N, K, pw.p, pw.bytes))
     return gemm_tc_im2col(X, g, B, ldb, bias, C, ldc, M, N, K, act, pw.p, st);
+  note_fallback(DESIRE_FALLBACK_GEMM_FP32, "implicit-GEMM convolution on FP32 CUDA cores (M, N, K)", M, N, K);
   DESIRE_CHECK_ARG((M + BM - 1) / BM <= 65535, "sgemm_im2col: M=%d too large", M);
   Im2colA a{X, g, M, K};
   return launch(a, B, ldb, false, bias, C, ldc, M, N, K, act, false, st);

@@ -204,7 +204,11 @@ __global__ void __launch_bounds__(256) gru_seq_kernel(GruSeqArgs a, int cgn, int
 
 int gru_seq(const GruSeqArgs& a, cudaStream_t st, PackWs pw) {
   if (gru_tc3_eligible(a, pw.p, pw.bytes)) return gru_seq_tc3(a, pw.p, st);
-  if (gru_tc_eligible(a, pw.p, pw.bytes)) return gru_seq_tc(a, pw.p, st);
+  if (gru_tc_eligible(a, pw.p, pw.bytes)) {
+    note_fallback(DESIRE_FALLBACK_GRU_V2, "GRU recurrence on the second tcgen05 design (H, R, T)", a.H, a.R, a.T);
+    return gru_seq_tc(a, pw.p, st);
+  }
+  note_fallback(DESIRE_FALLBACK_GRU_FP32, "GRU recurrence on FP32 CUDA cores (H, R, T)", a.H, a.R, a.T);
   DESIRE_CHECK_ARG(a.H % 4 == 0 && a.H >= 4 && a.H <= 1024, "gru: H=%d must be a multiple of 4 in [4,1024]", a.H);
   DESIRE_CHECK_ARG(a.Ka % 4 == 0, "gru: extra operand width %d must be a multiple of 4", a.Ka);
   DESIRE_CHECK_ARG(!a.ex || a.T == 1, "gru: the extra operand is per-step (T must be 1)");

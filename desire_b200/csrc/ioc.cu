@@ -670,6 +670,8 @@ static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const
   sfa.H = H; sfa.n_rad = d->n_rad; sfa.n_ang = d->n_ang; sfa.r2_edges = w->r2_edges; sfa.dirs = w->dirs;
   sfa.packed = pw_sp.packed; sfa.bias = w->sp_b; sfa.out = fsp;
   const bool fused_pool = social_fc_tc_eligible(sfa);
+  if (!fused_pool && d->iters > 0)
+    note_fallback(DESIRE_FALLBACK_SOCIAL_POOL, "materialised social pooling + GEMM (H, N, bins)", H, d->N, G);
 
   // The static input is [velocity fc | scene gather | feature_pooling].  On the tensor-core path the GEMM reads the
   // feature_pooling columns in place (two-source A loader) and Xs only holds the first Fv+Cs columns (row stride F48);

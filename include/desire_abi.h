@@ -98,6 +98,15 @@ const char* desire_last_error(void);
 /* ---- measurement hooks (bench.py): number of kernels launched by this library so far, and optional
  * per-kernel CUDA-event timing of the tagged launches below. */
 long desire_launch_count(void);
+/* Launches that did NOT take the tensor-core / fused kernel because the shape is outside what it covers (counted
+ * per kind since load; DESIRE_LOG_FALLBACK=1 prints the first of each kind to stderr).  Nothing is computed on the
+ * host in any case — these are the FP32 CUDA-core / materialising forms of the same entry points. */
+#define DESIRE_FALLBACK_GRU_FP32 0      /* GRU recurrence on FP32 CUDA cores (H % 32 != 0, fewer than 64 rows, ...) */
+#define DESIRE_FALLBACK_GRU_V2 1        /* tcgen05 recurrence of the second design (H not in {128, 256}, ...) */
+#define DESIRE_FALLBACK_SOCIAL_POOL 2   /* materialised [R, G*H] social pooling + GEMM instead of the fused kernel */
+#define DESIRE_FALLBACK_GEMM_FP32 3     /* FP32 CUDA-core GEMM (no packing scratch, tiny shapes, gemm mode 0) */
+#define DESIRE_FALLBACK_KINDS 4
+long desire_fallback_count(int kind);
 #define DESIRE_PROF_GRU_DEC1 0      /* Decoder-1 recurrence (a10)                       */
 #define DESIRE_PROF_GRU_DEC2 1      /* one Decoder-2 step (a14)                         */
 #define DESIRE_PROF_GRU_ENC 2       /* encoder recurrences (a3/a4)                      */
@@ -191,6 +200,10 @@ int desire_recon_rows_fwd(const float* Yhat, const float* target, int M, int K, 
                           desire_stream_t stream);
 int desire_masked_cost_fwd(const float* rows_a, const float* rows_b, const float* obs, int M, int Tp,
                            float* cost, desire_stream_t stream);
+/* a7 noise: out[0..n) ~ N(0,1), Philox4x32-10 + Box-Muller; `state` = DEVICE pointer to {seed, offset} (two u64), read
+ * at execution time so a captured CUDA graph draws fresh noise when the host bumps `offset` between replays.  Replaces
+ * the in-graph tf.random_normal of model/model.py:262.  Element e depends on (seed, offset, e) only. */
+int desire_randn_fwd(const unsigned long long* state, float* out, size_t n, desire_stream_t stream);
 /* D8 existence (model/model.py:206,214,351-366: an object contributes only if neither obj_id nor target_obj_id is
  * the non-existent id 0).  Every entry point that takes `obs` treats "id at observed frame 0 != 0" as "exists";
  * this writes obs_out [M,Tp,3] = obs with that id zeroed for agents that are absent

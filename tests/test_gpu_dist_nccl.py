@@ -88,6 +88,6 @@ def test_allreduced_gradient_equals_single_gpu_gradient_of_the_union_batch():
     print("all-reduced 2-rank gradient vs 1-GPU union-batch gradient: rel-L2 %.3e (|g| %.3e)" % (e, np.linalg.norm(r0["g_1"])))
     assert e <= 2e-5
     assert np.array_equal(r0["w_dp"], r1["w_dp"])                 # replicas stay bit-identical after clip + Adam
-    dw = rel_l2(r0["w_dp"] - r0["w_1"], r0["w_1"])
-    print("weights after one step, 2 ranks vs 1 GPU: rel-L2 of the difference %.3e" % dw)
-    assert dw <= 1e-5
+    dw = float(np.linalg.norm(r0["w_dp"].astype(np.float64) - r0["w_1"]) / np.linalg.norm(r0["w_1"].astype(np.float64)))
+    print("weights after one step, 2 ranks vs 1 GPU: |w_dp - w_1| / |w_1| = %.3e" % dw)
+    assert dw <= 1e-5          # lr 1e-3: an Adam step moves a weight by at most ~1e-3; sign flips of ~zero gradients stay far below

@@ -153,3 +153,27 @@ def test_fp32_cuda_core_mode_still_matches(lib):
     ref = oracle_forward(cfg, np_params(cfg), np_batch(cfg, 2), np_tables(cfg))
     bad = strict(got, ref, STAGE1 + IOC)
     assert not bad, bad
+
+
+def test_long_horizon_h128_strict():
+    """T_f = 40 (BASELINE configs[4]'s horizon) at H = 128: the fast-math activations (ex2.approx / rcp.approx) and the
+    3xBF16 recurrences run 40 dependent steps in Decoder-1 and 2 x 40 in Decoder-2; every named tensor incl. the IOC
+    scores must still meet the 1e-4 bar (one social bin: no edges)."""
+    cfg = small_cfg(d_dim=128, max_num_obj=10, num_samples=4, pred_length=40, **ONE_BIN)
+    got = run_gpu(cfg, 2, n_missing=1)
+    ref = oracle_forward(cfg, np_params(cfg), np_batch(cfg, 2, n_missing=1), np_tables(cfg))
+    bad = strict(got, ref, STAGE1 + IOC)
+    assert not bad, bad
+
+
+def test_fallback_paths_are_counted(lib):
+    """Shapes outside the tensor-core kernels run the FP32 / materialising forms — visibly (desire_fallback_count)."""
+    kinds = range(4)
+    before = [lib.desire_fallback_count(k) for k in kinds]
+    run_gpu(small_cfg(d_dim=128, max_num_obj=12, num_samples=6), 3)          # every hot kernel on its tcgen05 form
+    mid = [lib.desire_fallback_count(k) for k in kinds]
+    assert mid[1] == before[1] and mid[2] == before[2], (before, mid)        # no second-design GRU, no materialised pool
+    run_gpu(small_cfg(d_dim=48, max_num_obj=8, num_samples=3), 2)            # H = 48: FP32 recurrence, materialised pool
+    after = [lib.desire_fallback_count(k) for k in kinds]
+    assert after[0] > mid[0] and after[2] > mid[2], (mid, after)
+    assert lib.desire_fallback_count(99) == -1
