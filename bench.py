@@ -230,7 +230,11 @@ def slot_table(a, cfg, world_local_R):
         # slot 8 today = deconv1's identity col2im+BN+ELU ([R,2048] read + write) and the fused tiny-N deconv4
         # kernel ([R,8192] read, [R,1024] write); deconv2/3 are fused into their tensor-core kernels (slots 6/7)
         8: ("cvae_deconv1_bn_act+deconv4_fused", "hbm", R * 4.0 * (2048 + 2048 + 8192 + 1024)),
-        9: ("decoder2_input_projection_gemm", "tensor", it * R * T * 2.0 * Dst * 3 * H),
+        # factored form (desire_ioc_factored_fwd): per iteration only the Fv+Cs columns that change go through the GEMM,
+        # feature_pooling's 2C columns are a rank-2 per-agent term (4 FLOP per output), its per-agent vectors once per call
+        9: ("decoder2_input_projection_gemm", "tensor",
+            it * R * T * (2.0 * (cfg.vel_dim + cfg.scene_channels) + 4.0) * 3 * H +
+            (R / cfg.K) * 2.0 * 2 * cfg.channel_multiplier * 3 * H),
         10: ("scene_cnn", "tensor", (R / (cfg.max_num_obj * cfg.K)) * ((a.scene_size + 1) // 2) ** 2 * 2.0 *
              (75 * 16 + 400 * 32 + 800 * cfg.scene_channels)),
         11: ("readout_feature_pool", "hbm", R * T * 4.0 * (H + 2 + 2 * cfg.channel_multiplier)),

@@ -110,6 +110,7 @@ SIGNATURES = {
     "desire_social_pool_fwd": (I, [P, L, P, I, P, I, I, I, I, I, I, I, P, P, P, P]),
     "desire_ioc_workspace_bytes": (Z, [C.POINTER(IocDims)]),
     "desire_ioc_fwd": (I, [C.POINTER(IocDims), C.POINTER(IocW), P, P, I, P, I, P, P, P, P, Z, P]),
+    "desire_ioc_factored_fwd": (I, [C.POINTER(IocDims), C.POINTER(IocW), P, P, I, P, I, P, P, P, P, P, P, Z, P]),
     # ---- train step
     "desire_cost_bwd": (I, [P, P, P, P, P, I, I, I, I, I, P, P, P]),
     "desire_readout_bwd": (I, [P, P, I, I, I, P, P, P, P, P]),

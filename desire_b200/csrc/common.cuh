@@ -8,6 +8,8 @@
 
 #include "../../include/desire_abi.h"
 
+struct CUtensorMap_st;   // cuda.h (CUtensorMap), forward-declared so this header needs no driver API
+
 namespace desire {
 
 void set_error(const char* fmt, ...);
@@ -203,6 +205,17 @@ struct PackedW {
 int pack_weight(PackedW& w, void* ws, size_t ws_bytes, cudaStream_t st);
 int gemm_packed(const float* A, int lda, const PackedW& w, const float* bias, float* C, int ldc, int M, int act,
                 bool accumulate, cudaStream_t st);
+// Extra epilogue term of the tensor-core GEMM: C[m,:] += s[m,0] * P[g,0,:] + s[m,1] * P[g,1,:] with g = m / div.
+// It is how the Decoder-2 input projection takes feature_pooling (model/model.py:291-311): row (r,t) of that tensor is
+// [yhat_x * rho_i[m,:C] | yhat_y * rho_i[m,C:]], so its product with the weights is yhat_x * (rho_i[m,:C] @ W_x) +
+// yhat_y * (rho_i[m,C:] @ W_y) — two per-AGENT vectors (P) scaled by two per-row scalars (s), not a K = 2C GEMM.
+struct Rank2 {
+  const float* s = nullptr;   // [M,2]
+  const float* P = nullptr;   // [groups, 2, N]
+  int div = 1;                // rows per group
+};
+bool gemm_packed_r2(const float* A, int lda, const PackedW& w, const float* bias, float* C, int ldc, int M, int act,
+                    const Rank2& r2, cudaStream_t st, int* rc);
 // C = [A1 | A2] @ W + bias (K1 columns from A1, the rest from A2) on the tensor-core path; false = not eligible
 bool gemm_packed_dual(const float* A1, int lda1, int K1, const float* A2, int lda2, const PackedW& w, const float* bias,
                       float* C, int ldc, int M, int act, cudaStream_t st, int* rc);
@@ -259,6 +272,10 @@ int tc_pack_b(const float* W, int ldw, bool trans, int K, int N, int BN, void* o
 size_t gru_tc_pack_bytes(int H, int Ka = 0);
 bool gru_tc_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes);
 int gru_seq_tc(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
+
+// FP32 row-major [rows, row_stride] tensor -> CUtensorMap (cuda.h) with [128 rows x 32 columns] boxes and the 128-byte
+// swizzle, through the driver entry point fetched at run time (the library does not link libcuda)
+int make_tmap_rows32(::CUtensorMap_st* tm, const float* base, long rows, long row_stride);
 
 // third design of the tcgen05 recurrence (gru_tc3.cu): register-resident state, TMA-staged per-row inputs, phases
 // overlapped with the MMA groups; H in {128, 256} without extra operand, H = 128 with it (one Decoder-2 step).

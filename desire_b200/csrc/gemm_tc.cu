@@ -13,6 +13,11 @@
 //              images, so a stage is ONE 1-D bulk TMA copy (cp.async.bulk) completing on the stage's
 //              mbarrier.
 // Full/empty mbarrier ring of `stages` stages; accumulator handed to the epilogue by tcgen05.commit.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -241,7 +246,8 @@ template <class ALoad>
 __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __restrict__ Bp,
                                                        const float* __restrict__ bias, float* __restrict__ C, int ldc,
                                                        int M, int N, int BN, int nks_total, int stages, int act,
-                                                       int accumulate, int passes, uint32_t tmem_cols, int ks_split) {
+                                                       int accumulate, int passes, uint32_t tmem_cols, int ks_split,
+                                                       Rank2 r2, const __grid_constant__ CUtensorMap tm_c, int tma_c) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int a_half = KC * TM * 16;              // bytes of A_hi (== A_lo) per stage
   const int b_half = KC * BN * 16;
@@ -310,6 +316,46 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
     tc_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const int n0 = jn * BN;
+    if (tma_c) {
+      // Output through shared memory + TMA tensor-map stores (SASS UTMASTG): the thread-per-row float4 stores below
+      // touch 32 different 128-byte lines per instruction, which throttled the huge-M GEMMs (Decoder-2 input projection:
+      // 708 MB of output per launch) on the memory-instruction queue.  Here a thread writes its row of a [128 x 32] box
+      // into the (now idle) stage ring with the 128-byte swizzle, one thread stores the box, two boxes alternate.
+      const uint32_t obox = smem_u32(smem);
+      int ci = 0;
+      for (int c0 = 0; c0 < BN && n0 + c0 < N; c0 += 32, ++ci) {
+        float acc[32];
+        tmem_ld32(trow + c0, acc);
+        tmem_ld_wait();
+        if (r2.P && m < M) {
+          const float s0 = __ldg(r2.s + 2 * (size_t)m), s1 = __ldg(r2.s + 2 * (size_t)m + 1);
+          const float* p0 = r2.P + (size_t)(m / r2.div) * 2 * N + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = fmaf(s0, __ldg(p0 + j), fmaf(s1, __ldg(p0 + N + j), acc[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = acc[j];
+          if (bias) x += __ldg(bias + n0 + c0 + j);
+          acc[j] = act_apply(x, act);
+        }
+        const uint32_t box = obox + (ci & 1) * (TM * 128);
+        if (ci >= 2) {                                   // the store that last read this box has finished reading it
+          if (tid == 0) tma_store_wait_read1();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16)
+          sts128(swz128_abs(box, tid, c16), make_float4(acc[4 * c16], acc[4 * c16 + 1], acc[4 * c16 + 2], acc[4 * c16 + 3]));
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+          tma_store_2d(&tm_c, smem + (ci & 1) * (TM * 128), n0 + c0, m0);
+          tma_store_commit();
+        }
+      }
+      if (tid == 0) tma_store_wait_all();
+    } else
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float acc[32];
       const int ncol = min(32, BN - c0);          // BN is a multiple of 16
@@ -318,6 +364,13 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
       tmem_ld_wait();
       if (m < M) {
         float* crow = C + (size_t)m * ldc + n0 + c0;
+        if (r2.P) {     // + s[m,0] * P[g,0,:] + s[m,1] * P[g,1,:], g = m / div (a per-group rank-2 term, see Rank2)
+          const float s0 = __ldg(r2.s + 2 * (size_t)m), s1 = __ldg(r2.s + 2 * (size_t)m + 1);
+          const float* p0 = r2.P + (size_t)(m / r2.div) * 2 * N + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncol && n0 + c0 + j < N) acc[j] = fmaf(s0, __ldg(p0 + j), fmaf(s1, __ldg(p0 + N + j), acc[j]));
+        }
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + ncol <= N);
         if (accumulate == 2) {
 #pragma unroll
@@ -471,13 +524,25 @@ int pack_for_plan(const Plan& p, const float* W, int ldw, bool trans_b, int K, i
 
 template <class ALoad>
 int run_tc(const ALoad& A, const void* packed, const float* bias, float* C, int ldc, int M, int N, int K, int act,
-           bool accumulate, cudaStream_t st) {
+           bool accumulate, cudaStream_t st, Rank2 r2 = Rank2()) {
   const Plan p = make_plan(N, K, M);
   DESIRE_ENSURE_SMEM(gemm_tc_kernel<ALoad>, p.smem);
   dim3 grid(p.ntn, (M + TM - 1) / TM);
+  // tall outputs made of whole 32-column boxes leave through TMA stores (see the kernel's epilogue)
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  int tma_c = 0;
+  static const bool no_tma = [] {
+    const char* e = getenv("DESIRE_GEMM_NO_TMA_STORE");
+    return e && e[0] == '1';
+  }();
+  if (!no_tma && !accumulate && M >= 4096 && N % 32 == 0 && p.BN % 32 == 0 && ldc % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(C) & 15) == 0 && make_tmap_rows32(&tm, C, M, ldc) == DESIRE_OK)
+    tma_c = 1;
   DESIRE_LAUNCH(st, (gemm_tc_kernel<ALoad><<<grid, NTHR, p.smem, st>>>(A, (const uint4*)packed, bias, C, ldc, M, N, p.BN,
                                                                        p.nks, p.stages, act, accumulate ? 1 : 0,
-                                                                       g_gemm_mode == 1 ? 1 : 3, p.tmem_cols, 0)));
+                                                                       g_gemm_mode == 1 ? 1 : 3, p.tmem_cols, 0, r2, tm,
+                                                                       tma_c)));
   return DESIRE_OK;
 }
 
@@ -511,7 +576,8 @@ int run_wgrad_tc(const ALoad& A, const float* B, int ldb, float* dW, int ldw, in
   dim3 grid(p.ntn, gy, splits);
   DESIRE_LAUNCH(st, (gemm_tc_kernel<ALoad><<<grid, NTHR, smem, st>>>(A, (const uint4*)pack_ws, nullptr, dW, ldw, Kd, N, p.BN,
                                                                      p.nks, stages, DESIRE_ACT_NONE, 2,
-                                                                     g_gemm_mode == 1 ? 1 : 3, p.tmem_cols, ks_split)));
+                                                                     g_gemm_mode == 1 ? 1 : 3, p.tmem_cols, ks_split, Rank2(),
+                                                                     CUtensorMap(), 0)));
   return DESIRE_OK;
 }
 
@@ -577,6 +643,16 @@ int gemm_packed(const float* A, int lda, const PackedW& w, const float* bias, fl
     return run_tc(a, w.packed, bias, C, ldc, M, w.N, w.K, act, accumulate, st);
   }
   return sgemm(A, lda, w.W, w.ldw, w.trans, bias, C, ldc, M, w.N, w.K, act, accumulate, st);
+}
+
+// C = A @ W + bias + s[:,0] * P[g,0,:] + s[:,1] * P[g,1,:] on the tensor-core path (W packed); false = not eligible
+bool gemm_packed_r2(const float* A, int lda, const PackedW& w, const float* bias, float* C, int ldc, int M, int act,
+                    const Rank2& r2, cudaStream_t st, int* rc) {
+  const bool ok = w.packed && g_gemm_mode != 0 && M >= 64 && (M + TM - 1) / TM <= 65535 && r2.P && r2.s && r2.div > 0;
+  if (!ok) return false;
+  DenseA8 a{A, lda, M, w.K, (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0), nullptr};
+  *rc = run_tc(a, w.packed, bias, C, ldc, M, w.N, w.K, act, false, st, r2);
+  return true;
 }
 
 // C = [A1 | A2] @ W + bias with W already packed (K = K1 + K2).  Requirements: tensor-core path available, K1 % 8 == 0,

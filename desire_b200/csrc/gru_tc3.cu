@@ -527,7 +527,7 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // FP32 row-major [rows, row_stride] tensor -> tiled map with [128 rows x 32 columns] boxes, 128-byte swizzle
-int make_tmap_rows32(CUtensorMap* tm, const float* base, long rows, long row_stride) {
+int make_tmap_impl(CUtensorMap* tm, const float* base, long rows, long row_stride) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -565,6 +565,10 @@ bool env_flag(const char* name) {
 bool tma_ok(const float* p, long ld) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0; }
 
 }  // namespace
+
+int make_tmap_rows32(::CUtensorMap_st* tm, const float* base, long rows, long row_stride) {
+  return make_tmap_impl(tm, base, rows, row_stride);
+}
 
 bool gru_tc3_eligible(const GruSeqArgs& a, const void* pack_ws, size_t pack_bytes) {
   static const bool off = env_flag("DESIRE_GRU_V2");

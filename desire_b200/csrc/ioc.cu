@@ -539,7 +539,7 @@ extern "C" int desire_social_pool_fwd(const float* pos, long pos_stride, const f
 // ------------------------------------------------------------------------------------------ IOC loop
 namespace {
 struct IocLayout {
-  size_t Xs, XP, pooled, fsp, h2, wst3, bst3, wsp3, pk_st, pk_sp, pk_sp3, pk_reg, pk_gru, total;
+  size_t Xs, XP, pooled, fsp, h2, wst3, bst3, wsp3, Pxy, pk_st, pk_st48, pk_sp, pk_sp3, pk_reg, pk_gru, total;
 };
 IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   const size_t R = (size_t)d->B * d->N * d->K, T = d->Tf, H = d->H;
@@ -559,8 +559,10 @@ IocLayout ioc_layout(const desire_ioc_dims_t* d) {
   L.wst3 = take(Dst * 3 * H * 4);
   L.bst3 = take(3 * H * 4);
   L.wsp3 = take(H * 3 * H * 4);
+  L.Pxy = take((size_t)d->B * d->N * 2 * 3 * H * 4);       // per-agent projections of rho_i (factored feature_pooling)
   // packed BF16 images, built once per call
   L.pk_st = take(gemm_tc_pack_bytes(3 * (int)H, (int)Dst));
+  L.pk_st48 = take(gemm_tc_pack_bytes(3 * (int)H, (int)(d->Fv + d->Cs)));
   L.pk_sp = take(gemm_tc_pack_bytes((int)H, (int)(G * H)));
   L.pk_sp3 = take(gemm_tc_pack_bytes(3 * (int)H, (int)H));
   L.pk_reg = take(gemm_tc_pack_bytes(2 * (int)T, (int)H));
@@ -574,7 +576,8 @@ extern "C" size_t desire_ioc_workspace_bytes(const desire_ioc_dims_t* d) { retur
 
 static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
                         int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores, void* ws,
-                        size_t ws_bytes, desire_stream_t stream, float* snaps);
+                        size_t ws_bytes, desire_stream_t stream, float* snaps, const float* rho = nullptr,
+                        const float* Yhat0 = nullptr);
 
 extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
                               int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores, void* ws,
@@ -582,10 +585,18 @@ extern "C" int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w,
   return ioc_fwd_impl(d, w, fmap, obs, Tp, Hx, ld_hx, fpool, Y, scores, ws, ws_bytes, stream, nullptr);
 }
 
+extern "C" int desire_ioc_factored_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap,
+                                       const float* obs, int Tp, const float* Hx, int ld_hx, const float* fpool,
+                                       const float* rho_i, const float* Yhat, float* Y, float* scores, void* ws,
+                                       size_t ws_bytes, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(rho_i && Yhat, "desire_ioc_factored_fwd: rho_i and Yhat are required");
+  return ioc_fwd_impl(d, w, fmap, obs, Tp, Hx, ld_hx, fpool, Y, scores, ws, ws_bytes, stream, nullptr, rho_i, Yhat);
+}
+
 // snaps (train step only): [iters+1, R, T, 2] — the trajectories entering every iteration, then the final ones
 static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
                         int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores, void* ws,
-                        size_t ws_bytes, desire_stream_t stream, float* snaps) {
+                        size_t ws_bytes, desire_stream_t stream, float* snaps, const float* rho, const float* Yhat0) {
   DESIRE_CHECK_ARG(d && w && fmap && obs && Hx && fpool && Y && scores, "desire_ioc_fwd: null argument");
   DESIRE_CHECK_ARG(d->B >= 0 && d->N > 0 && d->K > 0 && d->H > 0 && d->Tf > 0 && d->iters >= 0 && d->Fv % 4 == 0 &&
                        d->Cs % 4 == 0 && (2 * d->C) % 4 == 0,
@@ -624,12 +635,29 @@ static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const
                                 cudaMemcpyDeviceToDevice, st));
   DESIRE_CUDA(cudaMemcpy2DAsync(wsp3 + 2 * H, 3 * H * f4, g.wc + (size_t)Dst * H, H * f4, H * f4, H,
                                 cudaMemcpyDeviceToDevice, st));
-  PackedW pw_st, pw_sp, pw_sp3, pw_reg;
+  PackedW pw_st, pw_st48, pw_sp, pw_sp3, pw_reg;
   pw_st.W = wst3; pw_st.ldw = 3 * H; pw_st.K = Dst; pw_st.N = 3 * H;
+  pw_st48.W = wst3; pw_st48.ldw = 3 * H; pw_st48.K = Fv + Cs; pw_st48.N = 3 * H;
   pw_sp.W = w->sp_w; pw_sp.ldw = H; pw_sp.K = G * H; pw_sp.N = H;
   pw_sp3.W = wsp3; pw_sp3.ldw = 3 * H; pw_sp3.K = H; pw_sp3.N = 3 * H;
   pw_reg.W = w->reg_w; pw_reg.ldw = 2 * T; pw_reg.K = H; pw_reg.N = 2 * T;
-  DESIRE_TRY(pack_weight(pw_st, base + L.pk_st, L.pk_sp - L.pk_st, st));
+  DESIRE_TRY(pack_weight(pw_st, base + L.pk_st, L.pk_st48 - L.pk_st, st));
+  // Factored feature_pooling (Rank2 in common.cuh): with rho_i and the stage-1 trajectories at hand the 2C feature_pooling
+  // columns of the projection collapse to two per-agent vectors, computed ONCE per call (they do not depend on the IOC
+  // iteration), and the per-iteration GEMM keeps only the Fv + Cs columns that do change.
+  float* Pxy = (float*)(base + L.Pxy);
+  bool factored = false;
+  if (rho && Yhat0 && gemm_mode() != 0 && (Fv + Cs) % 8 == 0 && R * T >= 64) {
+    DESIRE_TRY(pack_weight(pw_st48, base + L.pk_st48, L.pk_sp - L.pk_st48, st));
+    if (pw_st48.packed) {
+      const int C1 = d->C, MA = d->B * d->N;
+      DESIRE_TRY(sgemm(rho, 2 * C1, wst3 + (size_t)(Fv + Cs) * 3 * H, 3 * H, false, nullptr, Pxy, 6 * H, MA, 3 * H, C1,
+                       DESIRE_ACT_NONE, false, st));
+      DESIRE_TRY(sgemm(rho + C1, 2 * C1, wst3 + (size_t)(Fv + Cs + C1) * 3 * H, 3 * H, false, nullptr, Pxy + 3 * H, 6 * H, MA,
+                       3 * H, C1, DESIRE_ACT_NONE, false, st));
+      factored = true;
+    }
+  }
   DESIRE_TRY(pack_weight(pw_sp, base + L.pk_sp, L.pk_sp3 - L.pk_sp, st));
   DESIRE_TRY(pack_weight(pw_sp3, base + L.pk_sp3, L.pk_reg - L.pk_sp3, st));
   DESIRE_TRY(pack_weight(pw_reg, base + L.pk_reg, L.pk_gru - L.pk_reg, st));
@@ -683,7 +711,7 @@ static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const
     (void)rc_probe;
     const bool dual = pw_st.packed && gemm_mode() != 0 && F48 % 8 == 0 && C2 % 4 == 0 && R * T >= 64 &&
                       (R * T + 127) / 128 <= 65535 && ((reinterpret_cast<uintptr_t>(fpool) & 15) == 0);
-    if (dual) xs_ld = F48;
+    if (dual || factored) xs_ld = F48;
   }
   if (xs_ld == Dst) {
     copy_cols_kernel<<<blocks(R * T * C2, 256), 256, 0, st>>>(fpool, C2, R * T, Xs + Fv + Cs, Dst);
@@ -705,7 +733,11 @@ static int ioc_fwd_impl(const desire_ioc_dims_t* d, const desire_ioc_t* w, const
       // hoisted input projection of the static features for all T steps: XP[(r,t), r|u|c]
       ProfScope ps_(DESIRE_PROF_DEC2_XPROJ, st);
       int rc2 = DESIRE_OK;
-      if (xs_ld == Dst || !gemm_packed_dual(Xs, F48, F48, fpool, C2, pw_st, bst3, XP, 3 * H, (int)(R * T), DESIRE_ACT_NONE, st, &rc2)) {
+      Rank2 r2;
+      r2.s = Yhat0; r2.P = Pxy; r2.div = K * T;
+      if (factored && gemm_packed_r2(Xs, F48, pw_st48, bst3, XP, 3 * H, (int)(R * T), DESIRE_ACT_NONE, r2, st, &rc2)) {
+        // XP = [vel | scene] @ W[:F48] + b + yhat_x * Px[agent] + yhat_y * Py[agent]
+      } else if (xs_ld == Dst || !gemm_packed_dual(Xs, F48, F48, fpool, C2, pw_st, bst3, XP, 3 * H, (int)(R * T), DESIRE_ACT_NONE, st, &rc2)) {
         DESIRE_CHECK_ARG(xs_ld == Dst, "ioc: two-source projection became ineligible");
         DESIRE_TRY(gemm_packed(Xs, Dst, pw_st, bst3, XP, 3 * H, (int)(R * T), DESIRE_ACT_NONE, false, st));
       }

@@ -122,6 +122,18 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING shared memory (the source may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one have
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// all committed bulk stores of this thread are complete (required before the CTA exits)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// swz128 for a box whose base is only 128-byte aligned: the XOR term comes from the row's absolute address
+__device__ __forceinline__ uint32_t swz128_abs(uint32_t box_saddr, int row, int c16) {
+  const uint32_t ra = box_saddr + row * 128;
+  return ra + ((c16 ^ ((ra >> 7) & 7)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -225,9 +225,9 @@ class HotPath:
                 cur.wait_stream(self.side)         # join the scene-CNN branch
             b["Y_refined"].copy_(b["Yhat"])
             if self.ioc_chains == 1 or self.serial:
-                ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs), Tp,
-                                      _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["Y_refined"]), _p(b["ioc_scores"]),
-                                      ws, wsb, st), "ioc")
+                ck(lib.desire_ioc_factored_fwd(C.byref(self.ioc_dims), C.byref(self.w_ioc), _p(b["scene_features"]), _p(obs),
+                                               Tp, _p(b["HxHy"]), 2 * H, _p(b["feature_pooling"]), _p(b["rho_i"]),
+                                               _p(b["Yhat"]), _p(b["Y_refined"]), _p(b["ioc_scores"]), ws, wsb, st), "ioc")
             else:
                 nc, Bc = self.ioc_chains, self.B // self.ioc_chains
                 Mc, Rc = Bc * N, Bc * N * K
@@ -240,12 +240,14 @@ class HotPath:
                     s_side.wait_event(fork)
                 for c in range(nc):
                     s_c = cur if c == 0 else self.ioc_streams[c - 1]
-                    ck(lib.desire_ioc_fwd(C.byref(self.ioc_dims_c), C.byref(self.w_ioc),
-                                          off(b["scene_features"], Bc * self.Hm * self.Hm * cfg.scene_channels, c),
-                                          off(obs, Mc * Tp * 3, c), Tp, off(b["HxHy"], Mc * 2 * H, c), 2 * H,
-                                          off(b["feature_pooling"], Rc * Tf * 2 * Cm, c), off(b["Y_refined"], Rc * Tf * 2, c),
-                                          _p(self.scores_c[c]), _p(self.ws_ioc[c]), self.ws_ioc_bytes,
-                                          C.c_void_p(s_c.cuda_stream)), "ioc chain %d" % c)
+                    ck(lib.desire_ioc_factored_fwd(C.byref(self.ioc_dims_c), C.byref(self.w_ioc),
+                                                   off(b["scene_features"], Bc * self.Hm * self.Hm * cfg.scene_channels, c),
+                                                   off(obs, Mc * Tp * 3, c), Tp, off(b["HxHy"], Mc * 2 * H, c), 2 * H,
+                                                   off(b["feature_pooling"], Rc * Tf * 2 * Cm, c),
+                                                   off(b["rho_i"], Mc * 2 * Cm, c), off(b["Yhat"], Rc * Tf * 2, c),
+                                                   off(b["Y_refined"], Rc * Tf * 2, c),
+                                                   _p(self.scores_c[c]), _p(self.ws_ioc[c]), self.ws_ioc_bytes,
+                                                   C.c_void_p(s_c.cuda_stream)), "ioc chain %d" % c)
                     with torch.cuda.stream(s_c):
                         b["ioc_scores"][:, c * Rc:(c + 1) * Rc].copy_(self.scores_c[c])
                 for c in range(1, nc):

@@ -233,6 +233,14 @@ size_t desire_ioc_workspace_bytes(const desire_ioc_dims_t* d);
 int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
                    int Tp, const float* Hx, int ld_hx, const float* fpool, float* Y, float* scores,
                    void* ws, size_t ws_bytes, desire_stream_t stream);
+/* Same, given rho_i [B*N,2C] (a2) and the stage-1 trajectories Yhat [R,T,2] that feature_pooling was built from
+ * (model/model.py:291-311: feature_pooling[r,t] = [yhat_x * rho_i[m,:C] | yhat_y * rho_i[m,C:]]): the feature_pooling
+ * columns of the Decoder-2 input projection then collapse to two per-agent vectors scaled by (yhat_x, yhat_y), computed
+ * once per call; the [R*T, 2C] tensor is not read at all.  Same results up to FP32 summation order. */
+int desire_ioc_factored_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,
+                            int Tp, const float* Hx, int ld_hx, const float* fpool, const float* rho_i,
+                            const float* Yhat, float* Y, float* scores, void* ws, size_t ws_bytes,
+                            desire_stream_t stream);
 
 /* ======================================================================================================
  * Train step (SURVEY 8.0 D9, 8.b "*_bwd twins"): gradients of `cost` (model/model.py:374-376) with respect
