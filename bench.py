@@ -120,6 +120,30 @@ def oracle_step_fn(a, cfg, n_scenes, seed=0):
     return step, n_scenes * cfg.max_num_obj * cfg.K
 
 
+def run_cpu_reference_shaped(a, cfg, n_objects=8):
+    """BASELINE.md section 2 mode (i): the reference's execution shape — ONE object per call, K samples, a Python loop
+    over the objects of a sequence (train.py:146-181, model/model.py:211-311).  The reference has no stage 2 and no
+    scene, so an object is one call of the oracle with N = 1 (its social pool is empty) on a 16x16 blank scene."""
+    import dataclasses
+    import numpy as np
+    from desire_b200.config import init_params, logpolar_tables
+    from desire_b200.synthetic import make_batch
+    from oracle import desire_oracle as O
+    c1 = dataclasses.replace(cfg, max_num_obj=1, scene_size=16)
+    P = {k: v.numpy() for k, v in init_params(c1, 1).items()}
+    r2, dirs = [t.numpy() for t in logpolar_tables(c1)]
+    objs = [[t.numpy() for t in make_batch(c1, 1, seed)] for seed in range(n_objects)]
+    ocfg = dict(K=c1.K, Z=c1.Z, ioc_iters=max(c1.ioc_iters, 1))
+    O.forward(P, ocfg, *objs[0], r2, dirs)
+    t0 = time.perf_counter()
+    for b in objs:
+        O.forward(P, ocfg, b[0], b[1], b[2], b[3], r2, dirs)
+    dt = time.perf_counter() - t0
+    return {"value": n_objects * c1.K / dt, "unit": UNIT,
+            "what": "reference-shaped: one object per call (N=1, K=%d), %d calls in a Python loop, no social "
+                    "neighbours, blank 16x16 scene" % (c1.K, n_objects)}
+
+
 def run_cpu(a, cfg, steps, warmup):
     # torchrun exports OMP_NUM_THREADS=1; the CPU legs must use every host core the BLAS can get
     try:
@@ -156,7 +180,8 @@ def reference_arm(a):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, cfg, {"note": "reference TF1 graph cannot run (SURVEY.md 0.4); this is the "
                                                    "oracle port of its algorithm on the host cores"}),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "reference_shaped": run_cpu_reference_shaped(a, cfg)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -435,7 +460,8 @@ def ours_arm(a):
         v, s_per, units = run_cpu(a, cfg, steps=2, warmup=1)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": "%d scene(s) x N=%d x K=%d = %d agent-samples per step x 2 steps, full path, numpy fp32 "
-                         "oracle (%.1f s/step)" % (a.cpu_sample_scenes, a.agents, a.samples, units, s_per)}
+                         "oracle (%.1f s/step)" % (a.cpu_sample_scenes, a.agents, a.samples, units, s_per),
+               "reference_shaped": run_cpu_reference_shaped(a, cfg)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(a.warmup, 3),
