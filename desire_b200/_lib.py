@@ -77,6 +77,7 @@ SIGNATURES = {
     "desire_version": (I, []),
     "desire_last_error": (C.c_char_p, []),
     "desire_launch_count": (L, []),
+    "desire_selftest_tsmma": (I, [P, P, P, P, I, P]),
     "desire_fallback_count": (L, [I]),
     "desire_set_gemm_mode": (I, [I]),
     "desire_get_gemm_mode": (I, []),

@@ -1,0 +1,117 @@
+// Hardware self-tests of the tcgen05 forms the kernels rely on (run through the C-ABI by tests/test_gpu_selftest.py).
+//
+// desire_selftest_tsmma: D = A @ B^T with the A operand read from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc —
+// CUTLASS: SM100_MMA_F16BF16_TS) against the same product with A in shared memory.  It pins the TMEM layout of a BF16 A
+// operand that the fused social kernel writes with tcgen05.st: lane = row, one 32-bit column = two consecutive K
+// elements, lower half = the smaller k.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace desire {
+namespace {
+using namespace tc;
+
+constexpr int M = 128, N = 64, K = 32;
+
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// A [128,32], B [64,32] FP32 (rounded to BF16 inside); out_ss / out_ts [128,64]
+__global__ void __launch_bounds__(160) tsmma_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                    float* __restrict__ out_ss, float* __restrict__ out_ts, int order) {
+  __shared__ __align__(1024) uint8_t sa[(K / 8) * M * 16];
+  __shared__ __align__(1024) uint8_t sb[(K / 8) * N * 16];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<256>(&tslot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tslot;               // columns [0,64) D_ss, [64,128) D_ts, [128,144) A
+  if (tid < M) {
+    // shared-memory A (K-major, no swizzle) and tensor-memory A (packed pairs)
+    float v[K];
+    for (int k = 0; k < K; ++k) v[k] = A[tid * K + k];
+    uint32_t packed[K / 2];
+    for (int c = 0; c < K / 8; ++c) {
+      uint32_t w[4];
+      for (int p = 0; p < 4; ++p) {
+        const float lo = v[c * 8 + 2 * p], hi = v[c * 8 + 2 * p + 1];
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[p]) : "f"(hi), "f"(lo));      // upper half = first source
+        packed[c * 4 + p] = order == 0 ? w[p] : ((w[p] >> 16) | (w[p] << 16));
+      }
+      *reinterpret_cast<uint4*>(sa + c * M * 16 + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + 128;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                 "%15, %16};" ::"r"(trow),
+                 "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]), "r"(packed[6]),
+                 "r"(packed[7]), "r"(packed[8]), "r"(packed[9]), "r"(packed[10]), "r"(packed[11]), "r"(packed[12]),
+                 "r"(packed[13]), "r"(packed[14]), "r"(packed[15])
+                 : "memory");
+    tmem_st_wait();
+    if (tid < N) {
+      float b[K];
+      for (int k = 0; k < K; ++k) b[k] = B[tid * K + k];
+      for (int c = 0; c < K / 8; ++c) {
+        uint32_t w[4];
+        for (int p = 0; p < 4; ++p) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[p]) : "f"(b[c * 8 + 2 * p + 1]), "f"(b[c * 8 + 2 * p]));
+        *reinterpret_cast<uint4*>(sb + c * N * 16 + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc = idesc_bf16(M, N);
+    for (int j = 0; j < K / 16; ++j) {
+      const uint64_t da = smem_desc(smem_u32(sa) + j * 2 * M * 16, M * 16, 128);
+      const uint64_t db = smem_desc(smem_u32(sb) + j * 2 * N * 16, N * 16, 128);
+      mma_bf16(tmem, da, db, idesc, j > 0);
+      mma_bf16_ts(tmem + 64, tmem + 128 + j * 8, db, idesc, j > 0);
+    }
+    mma_commit(&bar[0]);
+  }
+  if (tid < M) {
+    mbar_wait(&bar[0], 0);
+    tc_fence_after();
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float acc[32];
+      tmem_ld32(trow + c0, acc);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) out_ss[tid * N + c0 + j] = acc[j];
+      tmem_ld32(trow + 64 + c0, acc);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) out_ts[tid * N + c0 + j] = acc[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 256);
+}
+}  // namespace
+}  // namespace desire
+
+extern "C" int desire_selftest_tsmma(const float* A, const float* B, float* out_ss, float* out_ts, int order,
+                                     desire_stream_t stream) {
+  DESIRE_CHECK_ARG(A && B && out_ss && out_ts && (order == 0 || order == 1), "desire_selftest_tsmma: bad arguments");
+  desire::tsmma_kernel<<<1, 160, 0, (cudaStream_t)stream>>>(A, B, out_ss, out_ts, order);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}

@@ -98,6 +98,10 @@ const char* desire_last_error(void);
 /* ---- measurement hooks (bench.py): number of kernels launched by this library so far, and optional
  * per-kernel CUDA-event timing of the tagged launches below. */
 long desire_launch_count(void);
+/* Hardware self-test: D = A[128,32] @ B[64,32]^T (BF16 inputs) once with the A operand in shared memory (out_ss) and once
+ * with A in tensor memory (out_ts; tcgen05.mma with a TMEM A operand).  order = 0: lower half of a 32-bit TMEM column =
+ * the smaller k (what the fused social kernel assumes), 1: swapped.  out_* [128,64]. */
+int desire_selftest_tsmma(const float* A, const float* B, float* out_ss, float* out_ts, int order, desire_stream_t stream);
 /* Launches that did NOT take the tensor-core / fused kernel because the shape is outside what it covers (counted
  * per kind since load; DESIRE_LOG_FALLBACK=1 prints the first of each kind to stderr).  Nothing is computed on the
  * host in any case — these are the FP32 CUDA-core / materialising forms of the same entry points. */
