@@ -78,6 +78,7 @@ SIGNATURES = {
     "desire_last_error": (C.c_char_p, []),
     "desire_launch_count": (L, []),
     "desire_selftest_tsmma": (I, [P, P, P, P, I, P]),
+    "desire_selftest_mma_rate": (I, [I, I, I, I, P, P]),
     "desire_fallback_count": (L, [I]),
     "desire_set_gemm_mode": (I, [I]),
     "desire_get_gemm_mode": (I, []),
@@ -109,6 +110,8 @@ SIGNATURES = {
     "desire_scene_cnn_fwd": (I, [P, I, I, I, I, C.POINTER(SceneCnnW), P, P, Z, P]),
     "desire_scene_gather_fwd": (I, [P, I, I, I, I, P, L, I, P, I, P]),
     "desire_social_pool_fwd": (I, [P, L, P, I, P, I, I, I, I, I, I, I, P, P, P, P]),
+    "desire_social_fc_workspace_bytes": (C.c_size_t, [I, I]),
+    "desire_social_fc_fwd": (I, [P, L, P, I, P, I, I, I, I, I, I, I, P, P, P, P, P, P, C.c_size_t, P]),
     "desire_ioc_workspace_bytes": (Z, [C.POINTER(IocDims)]),
     "desire_ioc_fwd": (I, [C.POINTER(IocDims), C.POINTER(IocW), P, P, I, P, I, P, P, P, P, Z, P]),
     "desire_ioc_factored_fwd": (I, [C.POINTER(IocDims), C.POINTER(IocW), P, P, I, P, I, P, P, P, P, P, P, Z, P]),

@@ -235,6 +235,9 @@ struct SocialFcArgs {
 };
 bool social_fc_tc_eligible(const SocialFcArgs& a);
 int social_fc_tc(const SocialFcArgs& a, cudaStream_t st);
+// second design (social_ts.cu): pooled A operand in tensor memory; social_fc_tc() takes it whenever it is eligible
+bool social_fc_ts_eligible(const SocialFcArgs& a);
+int social_fc_ts(const SocialFcArgs& a, cudaStream_t st);
 size_t gemm_tc_pack_bytes(int N, int K);
 bool gemm_tc_eligible(int M, int N, int K, const void* pack_ws, size_t pack_bytes);
 int gemm_tc(const float* A, int lda, const float* W, int ldw, bool trans_b, const float* bias, float* C, int ldc,

@@ -536,6 +536,30 @@ extern "C" int desire_social_pool_fwd(const float* pos, long pos_stride, const f
                             (cudaStream_t)stream);
 }
 
+extern "C" size_t desire_social_fc_workspace_bytes(int H, int n_bins) { return gemm_tc_pack_bytes(H, n_bins * H) + 256; }
+
+// One step of the IOC stage's social feature on its own (the call desire_ioc_fwd makes T_f * iters times): the fused
+// kernel only — a shape outside it is an error here, not a fallback.
+extern "C" int desire_social_fc_fwd(const float* pos, long pos_stride, const float* h, int ld_h, const float* obs, int Tp,
+                                    int B, int N, int K, int H, int n_rad, int n_ang, const float* r2_edges,
+                                    const float* dirs, const float* sp_w, const float* sp_b, float* fsp, void* ws,
+                                    size_t ws_bytes, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(pos && h && obs && r2_edges && dirs && sp_w && sp_b && fsp && ws && B >= 0 && N > 0 && K > 0 && H > 0 &&
+                       n_rad > 0 && n_ang > 0 && ld_h >= H,
+                   "desire_social_fc_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  PackedW pw;
+  pw.W = sp_w; pw.ldw = H; pw.K = n_rad * n_ang * H; pw.N = H;
+  DESIRE_TRY(pack_weight(pw, ws, ws_bytes, st));
+  SocialFcArgs a{};
+  a.pos = pos; a.pos_stride = pos_stride; a.h = h; a.ld_h = ld_h; a.obs = obs; a.Tp = Tp; a.B = B; a.N = N; a.K = K; a.H = H;
+  a.n_rad = n_rad; a.n_ang = n_ang; a.r2_edges = r2_edges; a.dirs = dirs; a.packed = pw.packed; a.bias = sp_b; a.out = fsp;
+  DESIRE_CHECK_ARG(social_fc_tc_eligible(a), "desire_social_fc_fwd: shape outside the fused kernel (H %d, N %d, bins %d)", H, N,
+                   n_rad * n_ang);
+  ProfScope ps_(DESIRE_PROF_SOCIAL_FC, st);
+  return social_fc_tc(a, st);
+}
+
 // ------------------------------------------------------------------------------------------ IOC loop
 namespace {
 struct IocLayout {

@@ -105,6 +105,77 @@ __global__ void __launch_bounds__(160) tsmma_kernel(const float* __restrict__ A,
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem, 256);
 }
+
+
+// How fast does one thread's stream of tcgen05.mma (M = 128, K = 16, BF16) retire?  mode 0: both operands in shared
+// memory, 1: A in tensor memory.  Every CTA issues `iters` MMAs on the same operands; cycles of block 0 are returned.
+__global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iters, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 * 64 * 2 + 256 * 64 * 2) / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(&bar, mode == 4 ? 2 : 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tslot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tslot;
+  // mode 4: two threads (warps 0 and 1) issue at the same time, each into its own accumulator (TS)
+  if ((tid == 0 && mode != 5) || (mode == 4 && tid == 32)) {
+    const int w = tid >> 5;
+    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t sa = smem_u32(sm), sb = sa + 128 * 64 * 2;
+    uint64_t da[4], db[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                                // four K steps of a 64-wide stage, round robin
+      da[j] = smem_desc(sa + j * 2 * 128 * 16, 128 * 16, 128);
+      db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
+    }
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // modes 2, 3: consecutive MMAs alternate between two accumulators (no back-to-back dependency on D)
+        const uint32_t d = (mode == 2 || mode == 3) ? tmem + (j & 1) * 128 : tmem + w * 128;
+        if (mode == 0 || mode == 2) mma_bf16(d, da[j], db[j], idesc, 1);
+        else mma_bf16_ts(d, tmem + 256 + w * 64 + j * 8, db[j], idesc, 1);
+      }
+    }
+    mma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && tid == 0) out[0] = t1 - t0;
+  }
+  // mode 5: the whole warp runs the issue loop with warp-uniform operands and one ELECTED lane issues (TS) — the
+  // compiler then feeds UTCHMMA from uniform registers instead of wrapping every MMA in a lane-broadcast loop
+  if (mode == 5 && warp == 1) {
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t sb = smem_u32(sm) + 128 * 64 * 2;
+    uint64_t db[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (elect_one()) mma_bf16_ts(tm, tm + 256 + j * 8, db[j], idesc, 1);
+    }
+    if (elect_one()) mma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && tid == 32) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
 }  // namespace
 }  // namespace desire
 
@@ -112,6 +183,16 @@ extern "C" int desire_selftest_tsmma(const float* A, const float* B, float* out_
                                      desire_stream_t stream) {
   DESIRE_CHECK_ARG(A && B && out_ss && out_ts && (order == 0 || order == 1), "desire_selftest_tsmma: bad arguments");
   desire::tsmma_kernel<<<1, 160, 0, (cudaStream_t)stream>>>(A, B, out_ss, out_ts, order);
+  DESIRE_LAUNCH_CHECK();
+  return DESIRE_OK;
+}
+
+extern "C" int desire_selftest_mma_rate(int mode, int N, int iters, int grid, long long* out_cycles, desire_stream_t stream) {
+  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 5 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
+                   "desire_selftest_mma_rate: bad arguments");
+  const size_t smem = 128 * 64 * 2 + 256 * 64 * 2;
+  DESIRE_ENSURE_SMEM(desire::mma_rate_kernel, smem);
+  desire::mma_rate_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(mode, N, iters, out_cycles);
   DESIRE_LAUNCH_CHECK();
   return DESIRE_OK;
 }

@@ -15,6 +15,8 @@
 //              Afterwards: epilogue (bias + ReLU) of a 32x32 accumulator block each;
 //   warp 16    tcgen05.mma issuer (M=128, N=H, 3xBF16), accumulator in TMEM;
 //   warp 17    streams the packed sp_w stages with 1-D bulk TMA copies.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -314,8 +316,18 @@ int npad_of(int N) {
 
 }  // namespace
 
+// DESIRE_SOCIAL_V1=1 keeps the first design (A operand in shared memory) for A/B timing
+static bool use_ts(const SocialFcArgs& a) {
+  static const bool v1 = [] {
+    const char* e = getenv("DESIRE_SOCIAL_V1");
+    return e && e[0] == '1';
+  }();
+  return !v1 && social_fc_ts_eligible(a);
+}
+
 bool social_fc_tc_eligible(const SocialFcArgs& a) {
   const int G = a.n_rad * a.n_ang;
+  if (use_ts(a)) return true;
   if (gemm_mode() == 0 || !a.packed) return false;
   if (a.H % 64 != 0 || a.H < 64 || a.H > 128 || a.ld_h % 4 != 0) return false;   // a 64-column stage never straddles bins
   if (a.N > 128 || a.N < 1 || G > MAXG || G < 1) return false;
@@ -324,6 +336,7 @@ bool social_fc_tc_eligible(const SocialFcArgs& a) {
 }
 
 int social_fc_tc(const SocialFcArgs& a, cudaStream_t st) {
+  if (use_ts(a)) return social_fc_ts(a, st);
   const int Npad = npad_of(a.N), G = a.n_rad * a.n_ang;
   const Layout L = make_layout(a.H, Npad, G, a.n_rad, a.n_ang);
   const long ngroups = (long)a.B * a.K;

@@ -1,0 +1,497 @@
+// Fused log-polar social pooling + fc, second design: POOLING ITSELF RUNS ON THE TENSOR CORE and the pooled A operand of
+// the fc lives in TENSOR MEMORY.
+//     fsp[r, :] = relu( pool(h)[r, :] @ sp_w + sp_b ),   pool(h)[r, g*H + c] = mean_{j in bin g of r} h[j, c]
+//
+// Why (profiles/r2l_social_ts_trace.txt): gathering the neighbours' rows with SIMT loads costs 512 bytes of
+// shared-memory traffic per (row, neighbour) pair next to the MMA's own operand fetch, and its loops diverge (lists of
+// different rows have different lengths: 32 % of the lanes active) — both the first design (A operand assembled in shared
+// memory) and a gather that wrote straight to tensor memory ran at ~120 us per tile where the MMAs need 28.  Here, per bin g:
+//   pool MMA   P[128 x H] = S_g[128 x 128] @ h[128 x H]: S_g is the 0/1 selection matrix of the bin (rows = tile rows,
+//              columns = tile rows as neighbours; exact in BF16), h the tile's hidden vectors as BF16 hi + lo (two
+//              passes), both in shared memory; P accumulates in FP32 in tensor memory: the exact sum of hi + lo;
+//   finish     16 warps (thread = row, 32 columns each): tcgen05.ld P, scale by 1/count, split to BF16 hi/lo,
+//              tcgen05.st as the A operand of the fc (lane = row, one 32-bit column = two consecutive K values);
+//   fc MMA     D[128 x H] += A_g[128 x H] @ sp_w[g*H.., :]  (A from tensor memory, 3xBF16, weights streamed by bulk TMA).
+// The tensor pipe alternates pool(g+1) | fc(g); no loop of the kernel depends on how many neighbours a row has.
+// Building S_g is one byte compare per (row, neighbour): the prologue stores the bin of every pair as a byte.
+//
+// One CTA = one 128-row tile = 128/Npad complete (scene, sample) groups.  TMEM columns: D [0,H) | P [H,2H) | A0 | A1.
+//   warps 0-15  prologue (bins, transposed hidden vectors), S builder, finisher, epilogue (bias + ReLU)
+//   warp 16     tcgen05.mma issuer
+//   warp 17     streams the packed sp_w blocks (32 K values = one slot) with 1-D bulk TMA copies
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace desire {
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128;
+constexpr int NPW = 16;
+constexpr int NTHR = (NPW + 2) * 32;
+constexpr int PT = NPW * 32;   // producer threads
+constexpr int MAXG = 64;
+constexpr int MAXNB = 8;       // weight slots in shared memory (at most)
+
+struct Layout {
+  size_t ht, sm, bins, bin_stride, pc, px, py, rowmap, tab, bars, ring, slot_bytes, total;
+  int nb;
+};
+__host__ __device__ inline Layout make_layout(int H, int Npad, int n_rad, int n_ang) {
+  Layout L;
+  size_t off = 0;
+  L.ht = off; off += 2 * (size_t)H * TM * 2;                    // h as the pool MMA's B operand [H x 128] K-major: hi, lo
+  L.sm = off; off += 2 * (size_t)TM * TM * 2;                   // two selection matrices [128 x 128] BF16, K-major
+  L.bin_stride = (size_t)Npad + 16;                             // (+16: eight consecutive rows start on eight bank groups)
+  L.bins = off; off += TM * L.bin_stride;                       // bin of every (row, neighbour) pair, 255 = none
+  L.pc = off; off += 3 * 4 * TM * 4;                            // partial neighbour counts [3 buffers][4 parts][128 rows]
+  L.px = off; off += TM * 4;
+  L.py = off; off += TM * 4;
+  L.rowmap = off; off += TM * 8;
+  L.tab = off; off += (size_t)((n_rad + 1 + 2 * n_ang + 3) / 4 * 4) * 4;
+  L.bars = off; off += (2 * MAXNB + 10) * 8 + 32;
+  off = (off + 1023) / 1024 * 1024;
+  L.slot_bytes = 2 * (size_t)4 * H * 16;                        // one packed block of 32 K values: hi + lo
+  L.ring = off;
+  long room = 227L * 1024 - (long)off;
+  int nb = room > 0 ? (int)(room / (long)L.slot_bytes) : 0;
+  L.nb = nb > MAXNB ? MAXNB : nb;
+  L.total = off + (size_t)L.nb * L.slot_bytes;
+  return L;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand is read from tensor memory (lane = row, one 32-bit column = two
+// consecutive K values, lower half = the smaller k; pinned by tests/test_gpu_selftest.py)
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// single-thread roles wait with a suspend-time hint so their polling does not take issue slots from the other warps
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!ok);
+}
+
+// log-polar bin with every table read issued up front (the tables are a few broadcast shared-memory words): same
+// arithmetic and the same decisions as logpolar_bin() in common.cuh, without its dependent loops.  n_rad, n_ang <= 8.
+__device__ __forceinline__ int logpolar_bin_fast(float dx, float dy, const float* r2e, int n_rad, const float* dirs,
+                                                 int n_ang) {
+  const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  int rb = -1;
+  uint32_t ge = 0;
+#pragma unroll
+  for (int e = 0; e < 9; ++e)
+    if (e <= n_rad) rb += (r2 >= r2e[e]) ? 1 : 0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    if (s < n_ang) ge |= (__fsub_rn(__fmul_rn(dirs[2 * s], dy), __fmul_rn(dirs[2 * s + 1], dx)) >= 0.f ? 1u : 0u) << s;
+  if (rb < 0 || rb >= n_rad) return -1;
+  // the first sector s with ge[s] and not ge[s+1] (cyclically), else the last one
+  const uint32_t nxt = (ge >> 1) | ((ge & 1u) << (n_ang - 1));
+  const uint32_t hit = ge & ~nxt;
+  const int ab = hit ? __ffs(hit) - 1 : n_ang - 1;
+  return rb * n_ang + ab;
+}
+
+// 0x80 in every byte of w that equals the byte replicated in g4 (exact per byte, no cross-byte carries)
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t g4) {
+  const uint32_t t = w ^ g4;
+  return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+}
+// two flag bytes (0x80 / 0) -> two BF16 values 1.0 / 0.0 (0x80 * 0x7F = 0x3F80)
+__device__ __forceinline__ uint32_t ones_lo(uint32_t z) { return __byte_perm(z, 0u, 0x4140) * 0x7Fu; }
+__device__ __forceinline__ uint32_t ones_hi(uint32_t z) { return __byte_perm(z, 0u, 0x4342) * 0x7Fu; }
+
+template <int H>
+__global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, int Npad, int passes, int dbg,
+                                                               long long* __restrict__ trace) {
+  constexpr uint32_t TCOLS = 4 * H <= 256 ? 256 : 512;
+  static_assert(4 * H <= 512, "tensor memory: D + P + two A stages");
+  constexpr int CW = H / 4;                          // columns of P a finisher warp converts
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int N = a.N, K = a.K, G = a.n_rad * a.n_ang;
+  const Layout L = make_layout(H, Npad, a.n_rad, a.n_ang);
+  uint8_t* ht = smem + L.ht;
+  uint8_t* sm = smem + L.sm;
+  uint8_t* bins = smem + L.bins;
+  int* pc = reinterpret_cast<int*>(smem + L.pc);
+  float* px = reinterpret_cast<float*>(smem + L.px);
+  float* py = reinterpret_cast<float*>(smem + L.py);
+  float* tab = reinterpret_cast<float*>(smem + L.tab);
+  long* rowmap = reinterpret_cast<long*>(smem + L.rowmap);
+  uint8_t* ring = smem + L.ring;
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* bempty = bfull + MAXNB;
+  uint64_t* sfull = bempty + MAXNB;                  // [2] selection matrix written (16 warps)
+  uint64_t* sempty = sfull + 2;                      // [2] ... consumed by its pool MMAs (commit)
+  uint64_t* afull = sempty + 2;                      // [2] A stage written (16 warps)
+  uint64_t* aempty = afull + 2;                      // [2] ... consumed by its fc MMAs (commit)
+  uint64_t* pfull = aempty + 2;                      // pool MMAs of a bin complete (commit)
+  uint64_t* pempty = pfull + 1;                      // P read into registers (16 warps)
+  uint64_t* tfull = pempty + 1;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint32_t* exist = tslot + 1;                       // bit l of word l/32: tile lane l is an existing agent
+  const int nb = L.nb;
+  const bool tr = trace != nullptr && blockIdx.x == 0;
+#define TRACE(i) do { if (tr) trace[i] = clock64(); } while (0)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gpt = TM / Npad;                         // groups per tile
+  const long ngroups = (long)a.B * K;
+  const long grp0 = (long)blockIdx.x * gpt;
+  constexpr int CPB = H / 32;                        // weight blocks (slots) per bin
+  const int nblk = G * CPB;
+  const uint32_t b_blk = 4 * H * 16;                 // bytes of the hi (or lo) half of a weight block
+  if (tid == 0) TRACE(0);
+
+  if (tid < TM) {                                    // global row of tile lane l (or -1), its position, its existence
+    const long grp = grp0 + tid / Npad;
+    const int i = tid % Npad;
+    long r = -1;
+    float x = 0.f, y = 0.f;
+    bool ex = false;
+    if (grp < ngroups && i < N) {
+      const long b = grp / K;
+      const int k = (int)(grp % K);
+      r = (b * N + i) * K + k;
+      ex = __ldg(a.obs + (size_t)(b * N + i) * a.Tp * 3) != 0.f;
+      x = __ldg(a.pos + r * a.pos_stride);
+      y = __ldg(a.pos + r * a.pos_stride + 1);
+    }
+    rowmap[tid] = r;
+    px[tid] = x;
+    py[tid] = y;
+    const uint32_t em = __ballot_sync(0xffffffffu, ex);
+    if (lane == 0) exist[warp] = em;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < nb; ++s) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sfull[s], NPW);
+      mbar_init(&sempty[s], 1);
+      mbar_init(&afull[s], NPW);
+      mbar_init(&aempty[s], 1);
+    }
+    mbar_init(pfull, 1);
+    mbar_init(pempty, NPW);
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == NPW) tmem_alloc<TCOLS>(tslot);
+  tc_fence_before();
+  __syncthreads();
+
+  if (warp == NPW + 1) {
+    // ===================== weight loader
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed);
+      for (int kb = 0; kb < nblk; ++kb) {
+        const int slot = kb % nb;
+        mbar_wait_idle(&bempty[slot], ((kb / nb) & 1) ^ 1);
+        if ((dbg & 2) && kb >= nb) {                             // timing experiment: no weight traffic after the first ring fill
+          mbar_arrive(&bfull[slot]);
+          continue;
+        }
+        mbar_arrive_expect_tx(&bfull[slot], (uint32_t)L.slot_bytes);
+        bulk_g2s_hint(ring + (size_t)slot * L.slot_bytes, src + (size_t)kb * L.slot_bytes, (uint32_t)L.slot_bytes,
+                      &bfull[slot], L2_EVICT_LAST);
+      }
+    }
+  } else if (warp == NPW) {
+    // ===================== MMA issuer: pool(0) | pool(1) fc(0) | pool(2) fc(1) | ...
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(TM, H);
+      const uint32_t lbo_b = H * 16, lbo_s = TM * 16;
+      const uint32_t t_p = tmem + H;
+      const uint32_t ht_hi = smem_u32(ht), ht_lo = ht_hi + H * TM * 2;
+      auto pool = [&](int g) {
+        const int sb = g & 1;
+        mbar_wait_idle(&sfull[sb], (g >> 1) & 1);
+        if (g > 0) mbar_wait_idle(pempty, (g - 1) & 1);
+        tc_fence_after();
+        const uint32_t s0 = smem_u32(sm + (size_t)sb * TM * TM * 2);
+        if (!(dbg & 4)) {
+#pragma unroll
+          for (int j = 0; j < TM / 16; ++j) {                    // K = the 128 tile rows as neighbours
+            const uint64_t ds = smem_desc(s0 + j * 2 * lbo_s, lbo_s, 128);
+            mma_bf16(t_p, ds, smem_desc(ht_hi + j * 2 * lbo_b, lbo_b, 128), idesc, j > 0);
+            if (passes == 3) mma_bf16(t_p, ds, smem_desc(ht_lo + j * 2 * lbo_b, lbo_b, 128), idesc, 1);
+          }
+        }
+        mma_commit(pfull);
+        mma_commit(&sempty[sb]);
+      };
+      pool(0);
+      uint32_t accf = 0;
+      int kb = 0;
+      for (int g = 0; g < G; ++g) {
+        if (g + 1 < G) pool(g + 1);
+        const int as = g & 1;
+        mbar_wait_idle(&afull[as], (g >> 1) & 1);
+        tc_fence_after();
+        TRACE(16 + 8 * g + 5);
+        const uint32_t a_hi = tmem + 2 * H + as * H, a_lo = a_hi + H / 2;
+#pragma unroll 1
+        for (int c = 0; c < CPB; ++c, ++kb) {
+          const int slot = kb % nb;
+          mbar_wait_idle(&bfull[slot], (kb / nb) & 1);
+          tc_fence_after();
+          const uint32_t sb = smem_u32(ring + (size_t)slot * L.slot_bytes);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            if (dbg & 4) break;                                  // timing experiment: no MMAs
+            const uint32_t j = 2 * c + jj;                       // 16-wide K step inside the bin
+            const uint64_t bhi = smem_desc(sb + jj * 2 * lbo_b, lbo_b, 128);
+            const uint64_t blo = smem_desc(sb + b_blk + jj * 2 * lbo_b, lbo_b, 128);
+            mma_bf16_ts(tmem, a_hi + 8 * j, bhi, idesc, accf);
+            accf = 1;
+            if (passes == 3) {
+              mma_bf16_ts(tmem, a_lo + 8 * j, bhi, idesc, 1);
+              mma_bf16_ts(tmem, a_hi + 8 * j, blo, idesc, 1);
+            }
+          }
+          mma_commit(&bempty[slot]);
+        }
+        mma_commit(&aempty[as]);
+        TRACE(16 + 8 * g + 6);
+      }
+      mma_commit(tfull);
+    }
+  } else {
+    // ===================== prologue (producer warps): tables, zeroed selection matrices, transposed hidden vectors
+    for (int e = tid; e < a.n_rad + 1; e += PT) tab[e] = __ldg(a.r2_edges + e);
+    for (int e = tid; e < 2 * a.n_ang; e += PT) tab[a.n_rad + 1 + e] = __ldg(a.dirs + e);
+    {
+      uint4* z = reinterpret_cast<uint4*>(sm);
+      for (int e = tid; e < 2 * TM * TM * 2 / 16; e += PT) z[e] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // h^T as a K-major operand: byte(c, j) = (j/8) * H*16 + c*16 + (j%8)*2.  A thread owns column c and eight neighbours
+    // j (one 16-byte chunk of the hi and of the lo image); a warp reads 32 consecutive columns of a row (coalesced).
+    for (int item = tid; item < H * (TM / 8); item += PT) {
+      const int c = item % H, oct = item / H;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const long r = rowmap[oct * 8 + e];
+        v[e] = r >= 0 ? __ldg(a.h + r * (long)a.ld_h + c) : 0.f;
+      }
+      const Split8 s8 = split8(v);
+      const size_t o = (size_t)oct * H * 16 + (size_t)c * 16;
+      *reinterpret_cast<uint4*>(ht + o) = s8.hi;
+      *reinterpret_cast<uint4*>(ht + (size_t)H * TM * 2 + o) = s8.lo;
+    }
+    // bins: thread (row = tid % 128, quarter = tid / 128) takes neighbours j = quarter, quarter + 4, ...
+    {
+      const int rl = tid & (TM - 1), q = tid >> 7;
+      const bool valid = rowmap[rl] >= 0;
+      const int gbase = (rl / Npad) * Npad, me = rl % Npad;
+      const float xi = px[rl], yi = py[rl];
+      uint8_t* brow = bins + (size_t)rl * L.bin_stride;
+      for (int j = q; j < Npad; j += 4) {
+        int g = -1;
+        if (valid && j < N && j != me && ((exist[(gbase + j) >> 5] >> ((gbase + j) & 31)) & 1u))
+          g = logpolar_bin_fast(px[gbase + j] - xi, py[gbase + j] - yi, tab, a.n_rad, tab + a.n_rad + 1, a.n_ang);
+        brow[j] = (uint8_t)g;                                    // 255 = no bin (a masked row still pools its neighbours)
+      }
+    }
+    fence_proxy_async();
+    asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+    if (tid == 0) TRACE(1);
+
+    // ---- S builder role: thread (row = tid % 128, part = tid / 128) owns JT consecutive neighbours of its row
+    const int srow = tid & (TM - 1), part = tid >> 7;
+    const int JT = Npad >= 32 ? Npad / 4 : 8;                    // neighbours per thread (8, 16 or 32)
+    const bool s_on = part * JT < Npad;
+    const uint8_t* sb_src = bins + (size_t)srow * L.bin_stride + part * JT;
+    // K index of neighbour j of this row = its tile lane: group base + j
+    const uint32_t s_dst = smem_u32(sm) + (uint32_t)(((srow / Npad) * Npad + part * JT) / 8) * (TM * 16) + srow * 16;
+    auto build = [&](int g) {                                    // selection matrix + partial counts of bin g
+      const uint32_t g4 = (uint32_t)g * 0x01010101u;
+      int cnt = 0;
+      if (s_on) {
+        const uint32_t dst = s_dst + (uint32_t)(g & 1) * (TM * TM * 2);
+        for (int o = 0; o < JT / 8; ++o) {
+          const uint2 w = *reinterpret_cast<const uint2*>(sb_src + 8 * o);
+          const uint32_t z0 = eq_bytes(w.x, g4), z1 = eq_bytes(w.y, g4);
+          cnt += __popc(z0) + __popc(z1);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + o * (TM * 16)), "r"(ones_lo(z0)),
+                       "r"(ones_hi(z0)), "r"(ones_lo(z1)), "r"(ones_hi(z1))
+                       : "memory");
+        }
+      }
+      pc[((g % 3) * 4 + part) * TM + srow] = cnt;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sfull[g & 1]);
+    };
+
+    // ---- finisher role: thread = TMEM lane (row) 32*(warp%4) + lane, columns CW*(warp/4) .. +CW of P
+    const int q4 = warp & 3, cg = warp >> 2;
+    const int frow = 32 * q4 + lane;
+    const uint32_t lane_f = (uint32_t)(32 * q4) << 16;
+    const uint32_t t_p = tmem + lane_f + H + cg * CW;
+    const uint32_t t_a = tmem + lane_f + 2 * H + cg * (CW / 2);
+
+    build(0);
+    for (int g = 0; g < G; ++g) {
+      if (tid == 0) TRACE(16 + 8 * g);
+      if (g + 1 < G) {
+        if (g >= 1) mbar_wait(&sempty[(g + 1) & 1], ((g - 1) >> 1) & 1);     // pool(g-1) has read this buffer
+        build(g + 1);
+      }
+      if (tid == 0) TRACE(16 + 8 * g + 1);
+      mbar_wait(pfull, g & 1);                                   // pool(g) complete (=> every warp's build(g) is visible)
+      tc_fence_after();
+      if (tid == 0) TRACE(16 + 8 * g + 2);
+      const int* pcg = pc + (size_t)(g % 3) * 4 * TM + frow;     // read before pempty: buffer g%3 is rewritten by build(g+3)
+      const int cnt = pcg[0] + pcg[TM] + pcg[2 * TM] + pcg[3 * TM];
+      float v[CW];
+      if constexpr (CW == 32) tmem_ld32(t_p, v); else tmem_ld16(t_p, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pempty);
+      if (cnt > 1) {
+        const float inv = __frcp_rn((float)cnt);                 // mean = sum * (1/count)
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] *= inv;
+      }
+      uint32_t hi[CW / 2], lo[CW / 2];
+#pragma unroll
+      for (int i = 0; i < CW / 2; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+      if (tid == 0) TRACE(16 + 8 * g + 3);
+      if (g >= 2) mbar_wait(&aempty[g & 1], ((g - 2) >> 1) & 1);             // fc(g-2) has read this stage
+      tc_fence_after();
+      const uint32_t ta = t_a + (g & 1) * H;
+      if constexpr (CW == 32) {
+        tmem_st16(ta, reinterpret_cast<const float*>(hi));
+        tmem_st16(ta + H / 2, reinterpret_cast<const float*>(lo));
+      } else {
+        tmem_st8(ta, reinterpret_cast<const float*>(hi));
+        tmem_st8(ta + H / 2, reinterpret_cast<const float*>(lo));
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&afull[g & 1]);
+      if (tid == 0) TRACE(16 + 8 * g + 4);
+    }
+
+    // ===================== epilogue: warp w -> TMEM lanes 32*(w%4).., columns 32*(w/4)..
+    const long myrow = rowmap[frow];
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    if (tid == 0) TRACE(3);
+    const int c0 = cg * 32;
+    if (c0 < H && !(dbg & 4)) {
+      float acc[32];
+      tmem_ld32(tmem + lane_f + c0, acc);
+      tmem_ld_wait();
+      if (myrow >= 0) {
+        float* orow = a.out + myrow * (long)H + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + j));
+          float4 o;
+          o.x = fmaxf(acc[j] + bv.x, 0.f);
+          o.y = fmaxf(acc[j + 1] + bv.y, 0.f);
+          o.z = fmaxf(acc[j + 2] + bv.z, 0.f);
+          o.w = fmaxf(acc[j + 3] + bv.w, 0.f);
+          *reinterpret_cast<float4*>(orow + j) = o;
+        }
+      }
+    }
+    if (tid == 0) TRACE(4);
+  }
+#undef TRACE
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NPW) tmem_dealloc(*tslot, TCOLS);
+}
+
+int npad_of(int N) {
+  int p = 8;
+  while (p < N) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+bool social_fc_ts_eligible(const SocialFcArgs& a) {
+  const int G = a.n_rad * a.n_ang;
+  if (gemm_mode() == 0 || !a.packed) return false;
+  if ((a.H != 64 && a.H != 128) || a.ld_h % 4 != 0) return false;
+  if (a.N > 128 || a.N < 1 || G > MAXG || G < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(a.h) & 15) || (reinterpret_cast<uintptr_t>(a.bias) & 15)) return false;
+  if (a.n_rad > 8 || a.n_ang > 8) return false;
+  const Layout L = make_layout(a.H, npad_of(a.N), a.n_rad, a.n_ang);
+  return L.nb >= 3;
+}
+
+int social_fc_ts(const SocialFcArgs& a, cudaStream_t st) {
+  const int Npad = npad_of(a.N), G = a.n_rad * a.n_ang;
+  const Layout L = make_layout(a.H, Npad, a.n_rad, a.n_ang);
+  const long ngroups = (long)a.B * a.K;
+  if (ngroups == 0) return DESIRE_OK;
+  const int gpt = TM / Npad;
+  const unsigned grid = (unsigned)((ngroups + gpt - 1) / gpt);
+  const int passes = gemm_mode() == 1 ? 1 : 3;
+  int dbg = 0;                                                   // DESIRE_SOCIAL_DBG: timing experiments (results are wrong)
+  if (const char* e = getenv("DESIRE_SOCIAL_DBG")) dbg = atoi(e);
+  // DESIRE_SOCIAL_TRACE=1: block 0 records clock64() at its milestones; printed after the launch (timing tool only)
+  static long long* trace = nullptr;
+  static const bool want_trace = [] {
+    const char* e = getenv("DESIRE_SOCIAL_TRACE");
+    return e && e[0] == '1';
+  }();
+  if (want_trace && !trace) DESIRE_CUDA(cudaMalloc(&trace, 1024 * sizeof(long long)));
+  if (want_trace) DESIRE_CUDA(cudaMemsetAsync(trace, 0, 1024 * sizeof(long long), st));
+  if (a.H == 128) {
+    DESIRE_ENSURE_SMEM(social_fc_ts_kernel<128>, L.total);
+    DESIRE_LAUNCH(st, (social_fc_ts_kernel<128><<<grid, NTHR, L.total, st>>>(a, Npad, passes, dbg, trace)));
+  } else {
+    DESIRE_ENSURE_SMEM(social_fc_ts_kernel<64>, L.total);
+    DESIRE_LAUNCH(st, (social_fc_ts_kernel<64><<<grid, NTHR, L.total, st>>>(a, Npad, passes, dbg, trace)));
+  }
+  if (want_trace) {
+    static int printed = 0;
+    long long h[1024];
+    DESIRE_CUDA(cudaStreamSynchronize(st));
+    DESIRE_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    if (printed++ == 4) {
+      const long long t0 = h[0];
+      fprintf(stderr, "social trace (cycles from start): prologue %lld tfull %lld end %lld\n", h[1] - t0, h[3] - t0, h[4] - t0);
+      for (int g = 0; g < G; ++g) {
+        const long long* e = h + 16 + 8 * g;
+        fprintf(stderr, "  stage %2d: start %7lld build-next %6lld wait-pool %5lld ld+convert %6lld wait+st+arrive %5lld | mma: afull at %7lld fc issue %5lld\n",
+                g, e[0] - t0, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - t0, e[6] - e[5]);
+      }
+    }
+  }
+  return DESIRE_OK;
+}
+
+}  // namespace desire

@@ -157,6 +157,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp (elect.sync).  Issue tcgen05.mma / commit / bulk copies as
+//     if (elect_one()) mma_bf16(...)
+// inside code the WHOLE warp executes with warp-uniform operands: the compiler then keeps descriptors and addresses in
+// uniform registers.  Under a per-thread condition such as `if (lane == 0)` it wraps every UTCHMMA in a lane-broadcast
+// loop (VOTEU / ELECT / R2UR / BRA.U.ANY) and one thread retires an MMA only every ~93 cycles whatever its shape
+// (tools/mma_rate.py: M=128, N=128 needs 64).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, BF16 inputs, FP32 accumulate, M=128 per CTA
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {

@@ -102,6 +102,9 @@ long desire_launch_count(void);
  * with A in tensor memory (out_ts; tcgen05.mma with a TMEM A operand).  order = 0: lower half of a 32-bit TMEM column =
  * the smaller k (what the fused social kernel assumes), 1: swapped.  out_* [128,64]. */
 int desire_selftest_tsmma(const float* A, const float* B, float* out_ss, float* out_ts, int order, desire_stream_t stream);
+/* Timing probe: `grid` CTAs each issue `iters` back-to-back tcgen05.mma (M=128, N, K=16, BF16; mode 0 = A and B in shared
+ * memory, 1 = A in tensor memory); out_cycles[0] = SM cycles block 0 needed (device pointer). */
+int desire_selftest_mma_rate(int mode, int N, int iters, int grid, long long* out_cycles, desire_stream_t stream);
 /* Launches that did NOT take the tensor-core / fused kernel because the shape is outside what it covers (counted
  * per kind since load; DESIRE_LOG_FALLBACK=1 prints the first of each kind to stderr).  Nothing is computed on the
  * host in any case — these are the FP32 CUDA-core / materialising forms of the same entry points. */
@@ -232,6 +235,14 @@ int desire_social_pool_fwd(const float* pos, long pos_stride, const float* h, in
                            int Tp, int B, int N, int K, int H, int n_rad, int n_ang,
                            const float* r2_edges, const float* dirs, float* pooled,
                            desire_stream_t stream);
+/* One step of the social feature, fused (binning + pooling + fc on tensor cores; the [R, G*H] pooled tensor is never
+ * written): fsp [R,H] = relu(pool(h) @ sp_w [G*H,H] + sp_b).  ws: scratch for the packed weights.  Returns
+ * DESIRE_ERR_INVALID when the shape is outside the fused kernels (H in {64,128}, N <= 128) — no fallback here. */
+size_t desire_social_fc_workspace_bytes(int H, int n_bins);
+int desire_social_fc_fwd(const float* pos, long pos_stride, const float* h, int ld_h, const float* obs, int Tp, int B,
+                         int N, int K, int H, int n_rad, int n_ang, const float* r2_edges, const float* dirs,
+                         const float* sp_w, const float* sp_b, float* fsp, void* ws, size_t ws_bytes,
+                         desire_stream_t stream);
 /* full ranking & refinement loop.  Y [R,Tf,2] is refined IN PLACE; scores [iters, R]. */
 size_t desire_ioc_workspace_bytes(const desire_ioc_dims_t* d);
 int desire_ioc_fwd(const desire_ioc_dims_t* d, const desire_ioc_t* w, const float* fmap, const float* obs,

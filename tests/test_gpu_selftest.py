@@ -28,3 +28,4 @@ def test_tcgen05_mma_with_a_operand_in_tensor_memory(lib):
     assert np.abs(res[0][0] - ref).max() < 1e-4
     assert np.abs(res[0][1] - ref).max() < 1e-4, "TMEM A operand: packed pairs with the smaller k in the lower half"
     assert np.abs(res[1][1] - ref).max() > 1e-2          # the swapped order is a different product
+

@@ -1,0 +1,61 @@
+"""-m gpu: the fused social pooling + fc kernels (desire_social_fc_fwd) against the oracle's pool followed by a float64
+fc on IDENTICAL inputs (identical inputs -> identical bins, so the comparison is strict)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import np_tables, rel_l2, small_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def social_fc_gpu(lib, pos, h, obs, W, b, cfg, r2, dirs):
+    from desire_b200 import _lib
+    B, N, K, H = h.shape
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pos_d, h_d, obs_d, r2_d, dirs_d, W_d, b_d = d(pos), d(h), d(obs), d(r2), d(dirs), d(W), d(b)
+    out = torch.full((B * N * K, H), -7.0, device="cuda")
+    nbytes = lib.desire_social_fc_workspace_bytes(H, cfg.G)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.desire_social_fc_fwd(_ptr(pos_d), 2, _ptr(h_d), H, _ptr(obs_d), obs.shape[1], B, N, K, H, cfg.n_rad, cfg.n_ang,
+                                        _ptr(r2_d), _ptr(dirs_d), _ptr(W_d), _ptr(b_d), _ptr(out), _ptr(ws), nbytes, None),
+               "social_fc")
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+CASES = [(3, 60, 4, 128, 5), (2, 7, 3, 64, 2), (1, 128, 2, 128, 0), (2, 100, 3, 64, 3), (5, 33, 5, 128, 1), (1, 1, 3, 128, 0),
+         (2, 16, 9, 128, 0), (1, 65, 1, 128, 4)]
+
+
+@pytest.mark.parametrize("B,N,K,H,missing", CASES)
+def test_fused_social_fc_matches_oracle(lib, B, N, K, H, missing):
+    from oracle import desire_oracle as O
+    cfg = small_cfg()
+    r2, dirs = np_tables(cfg)
+    rng = np.random.default_rng(11 + N)
+    pos = (rng.random((B, N, K, 2)) * 0.6).astype(np.float32)
+    h = np.tanh(rng.normal(size=(B, N, K, H))).astype(np.float32)
+    obs = np.ones((B * N, 8, 3), np.float32)
+    mask = np.ones((B, N), bool)
+    if missing:
+        mask[-1, N - missing:] = False
+        obs.reshape(B, N, 8, 3)[-1, N - missing:, :, 0] = 0
+    W = (rng.normal(size=(cfg.G * H, H)) / np.sqrt(H)).astype(np.float32)
+    b = rng.normal(size=H).astype(np.float32) * 0.1
+    pooled = O.social_pool(pos, h, mask, r2, dirs).reshape(B * N * K, -1).astype(np.float64)
+    ref = np.maximum(pooled @ W.astype(np.float64) + b, 0.0)
+    got = social_fc_gpu(lib, pos, h, obs, W, b, cfg, r2, dirs)
+    e = rel_l2(got, ref)
+    print("fused social fc B%d N%d K%d H%d: rel-L2 %.3e" % (B, N, K, H, e))
+    assert e < 2e-5
+    # rows without any neighbour in range: exactly relu(bias)
+    lonely = ~(pooled != 0).any(axis=1)
+    if lonely.any():
+        assert np.array_equal(got[lonely], np.broadcast_to(np.maximum(b, 0), got[lonely].shape))
