@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
   tc_fence_after();
   const uint32_t tmem = tslot;
   // mode 4: two threads (warps 0 and 1) issue at the same time, each into its own accumulator (TS)
-  if ((tid == 0 && mode != 5) || (mode == 4 && tid == 32)) {
+  if ((tid == 0 && mode < 5) || (mode == 4 && tid == 32)) {
     const int w = tid >> 5;
     const uint32_t idesc = idesc_bf16(128, N);
     const uint32_t sa = smem_u32(sm), sb = sa + 128 * 64 * 2;
@@ -153,18 +153,29 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
   }
   // mode 5: the whole warp runs the issue loop with warp-uniform operands and one ELECTED lane issues (TS) — the
   // compiler then feeds UTCHMMA from uniform registers instead of wrapping every MMA in a lane-broadcast loop
-  if (mode == 5 && warp == 1) {
+  if ((mode == 5 || mode == 6) && warp == 1) {
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc = idesc_bf16(128, N);
     const uint32_t sb = smem_u32(sm) + 128 * 64 * 2;
-    uint64_t db[4];
+    uint64_t da[4], db[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
+    for (int j = 0; j < 4; ++j) {
+      da[j] = smem_desc(smem_u32(sm) + j * 2 * 128 * 16, 128 * 16, 128);
+      db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
+    }
     const long long t0 = clock64();
-    for (int i = 0; i < iters; i += 4) {
+    if (mode == 5) {
+      for (int i = 0; i < iters; i += 4) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (elect_one()) mma_bf16_ts(tm, tm + 256 + j * 8, db[j], idesc, 1);
+        for (int j = 0; j < 4; ++j)
+          if (elect_one()) mma_bf16_ts(tm, tm + 256 + j * 8, db[j], idesc, 1);
+      }
+    } else {                                                     // mode 6: both operands in shared memory
+      for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (elect_one()) mma_bf16(tm, da[j], db[j], idesc, 1);
+      }
     }
     if (elect_one()) mma_commit(&bar);
     __syncwarp();
@@ -188,7 +199,7 @@ extern "C" int desire_selftest_tsmma(const float* A, const float* B, float* out_
 }
 
 extern "C" int desire_selftest_mma_rate(int mode, int N, int iters, int grid, long long* out_cycles, desire_stream_t stream) {
-  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 5 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
+  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 6 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
                    "desire_selftest_mma_rate: bad arguments");
   const size_t smem = 128 * 64 * 2 + 256 * 64 * 2;
   DESIRE_ENSURE_SMEM(desire::mma_rate_kernel, smem);

@@ -17,7 +17,7 @@
 //
 // One CTA = one 128-row tile = 128/Npad complete (scene, sample) groups.  TMEM columns: D [0,H) | P [H,2H) | A0 | A1.
 //   warps 0-15  prologue (bins, transposed hidden vectors), S builder, finisher, epilogue (bias + ReLU)
-//   warp 16     tcgen05.mma issuer
+//   warp 16     issues the fc MMAs, warp 18 the pool MMAs
 //   warp 17     streams the packed sp_w blocks (32 K values = one slot) with 1-D bulk TMA copies
 #include <stdlib.h>
 
@@ -31,7 +31,7 @@ using namespace tc;
 
 constexpr int TM = 128;
 constexpr int NPW = 16;
-constexpr int NTHR = (NPW + 2) * 32;
+constexpr int NTHR = (NPW + 3) * 32;
 constexpr int PT = NPW * 32;   // producer threads
 constexpr int MAXG = 64;
 constexpr int MAXNB = 8;       // weight slots in shared memory (at most)
@@ -51,7 +51,8 @@ __host__ __device__ inline Layout make_layout(int H, int Npad, int n_rad, int n_
   L.px = off; off += TM * 4;
   L.py = off; off += TM * 4;
   L.rowmap = off; off += TM * 8;
-  L.tab = off; off += (size_t)((n_rad + 1 + 2 * n_ang + 3) / 4 * 4) * 4;
+  off = (off + 15) / 16 * 16;
+  L.tab = off; off += 24 * 4;                                   // 8 squared radial edges (+inf padded), 8 directions
   L.bars = off; off += (2 * MAXNB + 10) * 8 + 32;
   off = (off + 1023) / 1024 * 1024;
   L.slot_bytes = 2 * (size_t)4 * H * 16;                        // one packed block of 32 K values: hi + lo
@@ -88,25 +89,24 @@ __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
-// log-polar bin with every table read issued up front (the tables are a few broadcast shared-memory words): same
-// arithmetic and the same decisions as logpolar_bin() in common.cuh, without its dependent loops.  n_rad, n_ang <= 8.
-__device__ __forceinline__ int logpolar_bin_fast(float dx, float dy, const float* r2e, int n_rad, const float* dirs,
+// log-polar bin from tables held in registers (8 squared radial edges padded with +inf, 8 sector directions): the same
+// arithmetic and the same decisions as logpolar_bin() in common.cuh, branch-free.  n_rad <= 7, n_ang <= 8.
+__device__ __forceinline__ int logpolar_bin_regs(float dx, float dy, const float (&re)[8], const float (&dr)[16], int n_rad,
                                                  int n_ang) {
   const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
   int rb = -1;
   uint32_t ge = 0;
 #pragma unroll
-  for (int e = 0; e < 9; ++e)
-    if (e <= n_rad) rb += (r2 >= r2e[e]) ? 1 : 0;
+  for (int e = 0; e < 8; ++e) rb += (r2 >= re[e]) ? 1 : 0;
 #pragma unroll
   for (int s = 0; s < 8; ++s)
-    if (s < n_ang) ge |= (__fsub_rn(__fmul_rn(dirs[2 * s], dy), __fmul_rn(dirs[2 * s + 1], dx)) >= 0.f ? 1u : 0u) << s;
-  if (rb < 0 || rb >= n_rad) return -1;
+    ge |= (__fsub_rn(__fmul_rn(dr[2 * s], dy), __fmul_rn(dr[2 * s + 1], dx)) >= 0.f ? 1u : 0u) << s;
+  ge &= (1u << n_ang) - 1u;
   // the first sector s with ge[s] and not ge[s+1] (cyclically), else the last one
   const uint32_t nxt = (ge >> 1) | ((ge & 1u) << (n_ang - 1));
   const uint32_t hit = ge & ~nxt;
   const int ab = hit ? __ffs(hit) - 1 : n_ang - 1;
-  return rb * n_ang + ab;
+  return (rb < 0 || rb >= n_rad) ? -1 : rb * n_ang + ab;
 }
 
 // 0x80 in every byte of w that equals the byte replicated in g4 (exact per byte, no cross-byte carries)
@@ -118,8 +118,8 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t g4) {
 __device__ __forceinline__ uint32_t ones_lo(uint32_t z) { return __byte_perm(z, 0u, 0x4140) * 0x7Fu; }
 __device__ __forceinline__ uint32_t ones_hi(uint32_t z) { return __byte_perm(z, 0u, 0x4342) * 0x7Fu; }
 
-template <int H>
-__global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, int Npad, int passes, int dbg,
+template <int H, bool P3>
+__global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, int Npad, int dbg,
                                                                long long* __restrict__ trace) {
   constexpr uint32_t TCOLS = 4 * H <= 256 ? 256 : 512;
   static_assert(4 * H <= 512, "tensor memory: D + P + two A stages");
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
   const long grp0 = (long)blockIdx.x * gpt;
   constexpr int CPB = H / 32;                        // weight blocks (slots) per bin
   const int nblk = G * CPB;
-  const uint32_t b_blk = 4 * H * 16;                 // bytes of the hi (or lo) half of a weight block
+  constexpr uint32_t b_blk = 4 * H * 16;                 // bytes of the hi (or lo) half of a weight block
   if (tid == 0) TRACE(0);
 
   if (tid < TM) {                                    // global row of tile lane l (or -1), its position, its existence
@@ -217,103 +217,139 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       }
     }
   } else if (warp == NPW) {
-    // ===================== MMA issuer: pool(0) | pool(1) fc(0) | pool(2) fc(1) | ...
+    // ===================== fc MMA issuer.  The whole warp runs the loop with warp-uniform operands and one elected lane
+    // issues (tc.cuh: elect_one); every descriptor is a base built once plus a compile-time offset, so nothing but
+    // the MMAs sits between two MMAs.  The pool MMAs have their own issuing warp: while one warp waits, commits and
+    // prepares, the other one's MMAs keep the tensor pipe busy (the queue behind one issuer is only a few MMAs deep).
     tc_fence_after();
-    const uint32_t tmem = *tslot;
-    if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(TM, H);
-      const uint32_t lbo_b = H * 16, lbo_s = TM * 16;
-      const uint32_t t_p = tmem + H;
-      const uint32_t ht_hi = smem_u32(ht), ht_lo = ht_hi + H * TM * 2;
-      auto pool = [&](int g) {
-        const int sb = g & 1;
-        mbar_wait_idle(&sfull[sb], (g >> 1) & 1);
-        if (g > 0) mbar_wait_idle(pempty, (g - 1) & 1);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);
+    constexpr uint32_t idesc = idesc_bf16(TM, H);
+    constexpr uint32_t lbo_b = H * 16;
+    const uint64_t d_ring = smem_desc(smem_u32(ring), lbo_b, 128);
+    int kb = 0;
+    for (int g = 0; g < G; ++g) {
+      const int as = g & 1;
+      mbar_wait(&afull[as], (g >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) TRACE(16 + 8 * g + 5);
+      const uint32_t a_hi = tmem + 2 * H + as * H, a_lo = a_hi + H / 2;
+      const uint32_t acc0 = g > 0;
+#pragma unroll
+      for (int c = 0; c < CPB; ++c, ++kb) {
+        const int slot = kb % nb;
+        const uint64_t dsl = desc_adv(d_ring, slot * (uint32_t)L.slot_bytes);
+        mbar_wait(&bfull[slot], (kb / nb) & 1);
         tc_fence_after();
-        const uint32_t s0 = smem_u32(sm + (size_t)sb * TM * TM * 2);
+        if (elect_one()) {
+          if (!(dbg & 4)) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = 2 * c + jj;                          // 16-wide K step inside the bin
+              const uint64_t bhi = desc_adv(dsl, jj * 2 * lbo_b), blo = desc_adv(dsl, b_blk + jj * 2 * lbo_b);
+              mma_bf16_ts(tmem, a_hi + 8 * j, bhi, idesc, j == 0 ? acc0 : 1u);
+              if (P3) {
+                mma_bf16_ts(tmem, a_lo + 8 * j, bhi, idesc, 1);
+                mma_bf16_ts(tmem, a_hi + 8 * j, blo, idesc, 1);
+              }
+            }
+          }
+          mma_commit(&bempty[slot]);
+          if (c == CPB - 1) mma_commit(&aempty[as]);
+        }
+      }
+      if (lane == 0) TRACE(16 + 8 * g + 6);
+    }
+    if (elect_one()) mma_commit(tfull);
+    __syncwarp();
+  } else if (warp == NPW + 2) {
+    // ===================== pool MMA issuer: P = S_g @ h (hi, then lo), both operands in shared memory
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);
+    constexpr uint32_t idesc = idesc_bf16(TM, H);
+    constexpr uint32_t lbo_b = H * 16, lbo_s = TM * 16;
+    const uint32_t t_p = tmem + H;
+    const uint64_t d_s0 = smem_desc(smem_u32(sm), lbo_s, 128);
+    const uint64_t d_hh = smem_desc(smem_u32(ht), lbo_b, 128), d_hl = desc_adv(d_hh, H * TM * 2);
+    for (int g = 0; g < G; ++g) {
+      const int sb = g & 1;
+      const uint64_t ds = desc_adv(d_s0, sb * (TM * TM * 2));
+      mbar_wait(&sfull[sb], (g >> 1) & 1);
+      if (g > 0) mbar_wait(pempty, (g - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         if (!(dbg & 4)) {
 #pragma unroll
           for (int j = 0; j < TM / 16; ++j) {                    // K = the 128 tile rows as neighbours
-            const uint64_t ds = smem_desc(s0 + j * 2 * lbo_s, lbo_s, 128);
-            mma_bf16(t_p, ds, smem_desc(ht_hi + j * 2 * lbo_b, lbo_b, 128), idesc, j > 0);
-            if (passes == 3) mma_bf16(t_p, ds, smem_desc(ht_lo + j * 2 * lbo_b, lbo_b, 128), idesc, 1);
+            mma_bf16(t_p, desc_adv(ds, j * 2 * lbo_s), desc_adv(d_hh, j * 2 * lbo_b), idesc, j > 0);
+            if (P3) mma_bf16(t_p, desc_adv(ds, j * 2 * lbo_s), desc_adv(d_hl, j * 2 * lbo_b), idesc, 1);
           }
         }
         mma_commit(pfull);
         mma_commit(&sempty[sb]);
-      };
-      pool(0);
-      uint32_t accf = 0;
-      int kb = 0;
-      for (int g = 0; g < G; ++g) {
-        if (g + 1 < G) pool(g + 1);
-        const int as = g & 1;
-        mbar_wait_idle(&afull[as], (g >> 1) & 1);
-        tc_fence_after();
-        TRACE(16 + 8 * g + 5);
-        const uint32_t a_hi = tmem + 2 * H + as * H, a_lo = a_hi + H / 2;
-#pragma unroll 1
-        for (int c = 0; c < CPB; ++c, ++kb) {
-          const int slot = kb % nb;
-          mbar_wait_idle(&bfull[slot], (kb / nb) & 1);
-          tc_fence_after();
-          const uint32_t sb = smem_u32(ring + (size_t)slot * L.slot_bytes);
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            if (dbg & 4) break;                                  // timing experiment: no MMAs
-            const uint32_t j = 2 * c + jj;                       // 16-wide K step inside the bin
-            const uint64_t bhi = smem_desc(sb + jj * 2 * lbo_b, lbo_b, 128);
-            const uint64_t blo = smem_desc(sb + b_blk + jj * 2 * lbo_b, lbo_b, 128);
-            mma_bf16_ts(tmem, a_hi + 8 * j, bhi, idesc, accf);
-            accf = 1;
-            if (passes == 3) {
-              mma_bf16_ts(tmem, a_lo + 8 * j, bhi, idesc, 1);
-              mma_bf16_ts(tmem, a_hi + 8 * j, blo, idesc, 1);
-            }
-          }
-          mma_commit(&bempty[slot]);
-        }
-        mma_commit(&aempty[as]);
-        TRACE(16 + 8 * g + 6);
       }
-      mma_commit(tfull);
     }
+    __syncwarp();
   } else {
     // ===================== prologue (producer warps): tables, zeroed selection matrices, transposed hidden vectors
-    for (int e = tid; e < a.n_rad + 1; e += PT) tab[e] = __ldg(a.r2_edges + e);
-    for (int e = tid; e < 2 * a.n_ang; e += PT) tab[a.n_rad + 1 + e] = __ldg(a.dirs + e);
+    if (tid == 0) TRACE(5);
+    if (tid < 8) tab[tid] = tid <= a.n_rad ? __ldg(a.r2_edges + tid) : __int_as_float(0x7f800000);   // +inf: never reached
+    if (tid >= 32 && tid < 48) tab[8 + tid - 32] = tid - 32 < 2 * a.n_ang ? __ldg(a.dirs + tid - 32) : 0.f;
     {
       uint4* z = reinterpret_cast<uint4*>(sm);
       for (int e = tid; e < 2 * TM * TM * 2 / 16; e += PT) z[e] = make_uint4(0u, 0u, 0u, 0u);
     }
     // h^T as a K-major operand: byte(c, j) = (j/8) * H*16 + c*16 + (j%8)*2.  A thread owns column c and eight neighbours
     // j (one 16-byte chunk of the hi and of the lo image); a warp reads 32 consecutive columns of a row (coalesced).
-    for (int item = tid; item < H * (TM / 8); item += PT) {
+    // All loads are issued first and converted after the binning below, which hides their latency.
+    if (tid == 0) TRACE(6);
+    constexpr int HT_ITEMS = H * (TM / 8) / PT;
+    static_assert(H * (TM / 8) % PT == 0, "h^T items per thread");
+    float hv[HT_ITEMS][8];
+#pragma unroll
+    for (int it = 0; it < HT_ITEMS; ++it) {
+      const int item = it * PT + tid;
       const int c = item % H, oct = item / H;
-      float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const long r = rowmap[oct * 8 + e];
-        v[e] = r >= 0 ? __ldg(a.h + r * (long)a.ld_h + c) : 0.f;
+        hv[it][e] = r >= 0 ? __ldg(a.h + r * (long)a.ld_h + c) : 0.f;
       }
-      const Split8 s8 = split8(v);
-      const size_t o = (size_t)oct * H * 16 + (size_t)c * 16;
-      *reinterpret_cast<uint4*>(ht + o) = s8.hi;
-      *reinterpret_cast<uint4*>(ht + (size_t)H * TM * 2 + o) = s8.lo;
     }
+    if (tid == 0) TRACE(7);
+    asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");          // the tables are complete
+    if (tid == 0) TRACE(8);
     // bins: thread (row = tid % 128, quarter = tid / 128) takes neighbours j = quarter, quarter + 4, ...
     {
       const int rl = tid & (TM - 1), q = tid >> 7;
       const bool valid = rowmap[rl] >= 0;
       const int gbase = (rl / Npad) * Npad, me = rl % Npad;
       const float xi = px[rl], yi = py[rl];
+      float re[8], dr[16];
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) *reinterpret_cast<float4*>(re + e) = *reinterpret_cast<const float4*>(tab + e);
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(dr + e) = *reinterpret_cast<const float4*>(tab + 8 + e);
+      // (opaque to the compiler from here on: otherwise it re-reads the tables from shared memory in every iteration)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) asm volatile("" : "+f"(re[e]));
+#pragma unroll
+      for (int e = 0; e < 16; ++e) asm volatile("" : "+f"(dr[e]));
       uint8_t* brow = bins + (size_t)rl * L.bin_stride;
       for (int j = q; j < Npad; j += 4) {
-        int g = -1;
-        if (valid && j < N && j != me && ((exist[(gbase + j) >> 5] >> ((gbase + j) & 31)) & 1u))
-          g = logpolar_bin_fast(px[gbase + j] - xi, py[gbase + j] - yi, tab, a.n_rad, tab + a.n_rad + 1, a.n_ang);
-        brow[j] = (uint8_t)g;                                    // 255 = no bin (a masked row still pools its neighbours)
+        const bool on = valid && j < N && j != me && ((exist[(gbase + j) >> 5] >> ((gbase + j) & 31)) & 1u);
+        const int g = logpolar_bin_regs(px[gbase + j] - xi, py[gbase + j] - yi, re, dr, a.n_rad, a.n_ang);
+        brow[j] = (uint8_t)(on ? g : -1);                        // 255 = no bin (a masked row still pools its neighbours)
       }
+    }
+    if (tid == 0) TRACE(9);
+#pragma unroll
+    for (int it = 0; it < HT_ITEMS; ++it) {
+      const int item = it * PT + tid;
+      const int c = item % H, oct = item / H;
+      const Split8 s8 = split8(hv[it]);
+      const size_t o = (size_t)oct * H * 16 + (size_t)c * 16;
+      *reinterpret_cast<uint4*>(ht + o) = s8.hi;
+      *reinterpret_cast<uint4*>(ht + (size_t)H * TM * 2 + o) = s8.lo;
     }
     fence_proxy_async();
     asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
@@ -400,18 +436,23 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       if (tid == 0) TRACE(16 + 8 * g + 4);
     }
 
-    // ===================== epilogue: warp w -> TMEM lanes 32*(w%4).., columns 32*(w/4)..
-    const long myrow = rowmap[frow];
+    // ===================== epilogue: warp w reads TMEM lanes 32*(w%4).., columns 32*(w/4).., adds the bias, applies the
+    // ReLU and parks its block in shared memory (the operands of the pool MMAs are dead by now); then every warp
+    // writes whole 4*H-byte rows (the thread-per-row stores of the first version took 8.7k cycles: 32 lines per
+    // instruction)
     mbar_wait(tfull, 0);
     tc_fence_after();
     if (tid == 0) TRACE(3);
-    const int c0 = cg * 32;
-    if (c0 < H && !(dbg & 4)) {
-      float acc[32];
-      tmem_ld32(tmem + lane_f + c0, acc);
-      tmem_ld_wait();
-      if (myrow >= 0) {
-        float* orow = a.out + myrow * (long)H + c0;
+    constexpr int OLD = H + 4;                                   // floats per staged row
+    float* ostage = reinterpret_cast<float*>(smem);              // [128][H + 4] <= the h^T + S region
+    static_assert((size_t)TM * OLD * 4 <= 2 * (size_t)H * TM * 2 + 2 * (size_t)TM * TM * 2, "epilogue staging");
+    {
+      const int c0 = cg * 32;
+      if (c0 < H) {
+        float acc[32];
+        tmem_ld32(tmem + lane_f + c0, acc);
+        tmem_ld_wait();
+        float* orow = ostage + (size_t)frow * OLD + c0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + j));
@@ -422,6 +463,20 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
           o.w = fmaxf(acc[j + 3] + bv.w, 0.f);
           *reinterpret_cast<float4*>(orow + j) = o;
         }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+    if (!(dbg & 4)) {
+      constexpr int LPR = H / 4;                                 // lanes per row (one float4 each)
+      constexpr int RPI = 32 / LPR;                              // rows per warp instruction
+      const int sub = lane / LPR, c4 = lane % LPR;
+#pragma unroll
+      for (int rr = 0; rr < 8; rr += RPI) {
+        const int rl = warp * 8 + rr + sub;
+        const long r = rowmap[rl];
+        if (r >= 0)
+          *reinterpret_cast<float4*>(a.out + r * (long)H + c4 * 4) =
+              *reinterpret_cast<const float4*>(ostage + (size_t)rl * OLD + c4 * 4);
       }
     }
     if (tid == 0) TRACE(4);
@@ -446,7 +501,7 @@ bool social_fc_ts_eligible(const SocialFcArgs& a) {
   if ((a.H != 64 && a.H != 128) || a.ld_h % 4 != 0) return false;
   if (a.N > 128 || a.N < 1 || G > MAXG || G < 1) return false;
   if ((reinterpret_cast<uintptr_t>(a.h) & 15) || (reinterpret_cast<uintptr_t>(a.bias) & 15)) return false;
-  if (a.n_rad > 8 || a.n_ang > 8) return false;
+  if (a.n_rad > 7 || a.n_ang > 8) return false;
   const Layout L = make_layout(a.H, npad_of(a.N), a.n_rad, a.n_ang);
   return L.nb >= 3;
 }
@@ -469,13 +524,17 @@ int social_fc_ts(const SocialFcArgs& a, cudaStream_t st) {
   }();
   if (want_trace && !trace) DESIRE_CUDA(cudaMalloc(&trace, 1024 * sizeof(long long)));
   if (want_trace) DESIRE_CUDA(cudaMemsetAsync(trace, 0, 1024 * sizeof(long long), st));
+#define SOCIAL_TS_LAUNCH(HH, PP)                                                                              \
+  do {                                                                                                        \
+    DESIRE_ENSURE_SMEM((social_fc_ts_kernel<HH, PP>), L.total);                                               \
+    DESIRE_LAUNCH(st, (social_fc_ts_kernel<HH, PP><<<grid, NTHR, L.total, st>>>(a, Npad, dbg, trace)));       \
+  } while (0)
   if (a.H == 128) {
-    DESIRE_ENSURE_SMEM(social_fc_ts_kernel<128>, L.total);
-    DESIRE_LAUNCH(st, (social_fc_ts_kernel<128><<<grid, NTHR, L.total, st>>>(a, Npad, passes, dbg, trace)));
+    if (passes == 3) SOCIAL_TS_LAUNCH(128, true); else SOCIAL_TS_LAUNCH(128, false);
   } else {
-    DESIRE_ENSURE_SMEM(social_fc_ts_kernel<64>, L.total);
-    DESIRE_LAUNCH(st, (social_fc_ts_kernel<64><<<grid, NTHR, L.total, st>>>(a, Npad, passes, dbg, trace)));
+    if (passes == 3) SOCIAL_TS_LAUNCH(64, true); else SOCIAL_TS_LAUNCH(64, false);
   }
+#undef SOCIAL_TS_LAUNCH
   if (want_trace) {
     static int printed = 0;
     long long h[1024];
@@ -483,7 +542,7 @@ int social_fc_ts(const SocialFcArgs& a, cudaStream_t st) {
     DESIRE_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
     if (printed++ == 4) {
       const long long t0 = h[0];
-      fprintf(stderr, "social trace (cycles from start): prologue %lld tfull %lld end %lld\n", h[1] - t0, h[3] - t0, h[4] - t0);
+      fprintf(stderr, "social trace (cycles from start): sync %lld zeroed %lld loads issued %lld tables barrier %lld binned %lld prologue %lld tfull %lld end %lld\n", h[5] - t0, h[6] - t0, h[7] - t0, h[8] - t0, h[9] - t0, h[1] - t0, h[3] - t0, h[4] - t0);
       for (int g = 0; g < G; ++g) {
         const long long* e = h + 16 + 8 * g;
         fprintf(stderr, "  stage %2d: start %7lld build-next %6lld wait-pool %5lld ld+convert %6lld wait+st+arrive %5lld | mma: afull at %7lld fc issue %5lld\n",

@@ -245,6 +245,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// the same descriptor `bytes` further into shared memory (only the 14-bit start-address field changes: no carry out of
+// it as long as the operand stays inside the 256 KB window) — one add instead of rebuilding the descriptor per MMA
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 // cute::UMMA::InstrDescriptor for kind::f16: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1),
 // both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
