@@ -275,9 +275,13 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   } else if (warp == 8) {
-    // ===================== MMA issuer
-    if (lane == 0) {
-      const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
+    // ===================== MMA issuer: the whole warp runs the loops, one elected lane issues with warp-uniform operands
+    // (tc.cuh: elect_one — under `if (lane == 0)` every UTCHMMA sat inside a lane-broadcast loop, ~93 cycles per MMA)
+    {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint64_t d_ahi = smem_desc(smem_u32(A_hi), 2048, 128), d_alo = smem_desc(smem_u32(A_lo), 2048, 128);
+      const uint32_t ring_s = smem_u32(ring);
+      const bool p3 = a.passes == 3;
       mbar_wait(a_ready, 0);
       tc_fence_after();
       uint32_t it = 0, use = 0;
@@ -287,32 +291,34 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
           const int BNt = min(TPT, ntaps - nt * TPT) * CG;
           const uint32_t idesc = idesc_bf16(TM, BNt);
           const uint32_t lbo_b = BNt * 16, b_half = 4 * BNt * 16;
+          const uint64_t d_b = smem_desc(ring_s, lbo_b, 128);
+          const uint32_t d = tm + ab * 256;
           mbar_wait(&acc_empty[ab], ((use >> 1) & 1) ^ 1);
           tc_fence_after();
           for (int ks = 0; ks < nks; ++ks, ++it) {
             const int slot = it % a.nstg;
+            const uint64_t db = desc_adv(d_b, slot * (uint32_t)SLOT);
+            const uint64_t dah = desc_adv(d_ahi, ks * 4 * 2048), dal = desc_adv(d_alo, ks * 4 * 2048);
             mbar_wait(&full[slot], (it / a.nstg) & 1);
             tc_fence_after();
-            const uint32_t sb = smem_u32(ring + (size_t)slot * SLOT);
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint32_t ao = (ks * 4 + j * 2) * 2048;
-              const uint64_t ahi = smem_desc(a_hi + ao, 2048, 128), alo = smem_desc(a_lo + ao, 2048, 128);
-              const uint64_t bhi = smem_desc(sb + j * 2 * lbo_b, lbo_b, 128);
-              const uint64_t blo = smem_desc(sb + b_half + j * 2 * lbo_b, lbo_b, 128);
-              const uint32_t d = tmem + ab * 256;
-              const uint32_t accf = (ks > 0 || j > 0) ? 1u : 0u;
-              mma_bf16(d, ahi, bhi, idesc, accf);
-              if (a.passes == 3) {
-                mma_bf16(d, alo, bhi, idesc, 1);
-                mma_bf16(d, ahi, blo, idesc, 1);
+              for (int j = 0; j < 2; ++j) {
+                const uint64_t bhi = desc_adv(db, j * 2 * lbo_b), blo = desc_adv(db, b_half + j * 2 * lbo_b);
+                const uint32_t accf = (ks > 0 || j > 0) ? 1u : 0u;
+                mma_bf16(d, desc_adv(dah, j * 2 * 2048), bhi, idesc, accf);
+                if (p3) {
+                  mma_bf16(d, desc_adv(dal, j * 2 * 2048), bhi, idesc, 1);
+                  mma_bf16(d, desc_adv(dah, j * 2 * 2048), blo, idesc, 1);
+                }
               }
+              mma_commit(&empty[slot]);
+              if (ks == nks - 1) mma_commit(&acc_full[ab]);
             }
-            mma_commit(&empty[slot]);
           }
-          mma_commit(&acc_full[ab]);
         }
       }
+      __syncwarp();
     }
   } else {
     // ===================== weight streamer

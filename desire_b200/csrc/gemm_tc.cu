@@ -411,34 +411,42 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
       }
     }
   } else if (warp == 4) {
-    // ===================== MMA issuer
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues with warp-uniform operands
+    // (tc.cuh: elect_one — under `if (lane == 0)` every UTCHMMA sat inside a lane-broadcast loop, ~93 cycles per MMA)
+    {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc = idesc_bf16(TM, BN);
       const uint32_t lbo_a = TM * 16, lbo_b = BN * 16;
+      const uint64_t d_a = smem_desc(smem_u32(smem), lbo_a, 128), d_b = smem_desc(smem_u32(smem) + 2 * a_half, lbo_b, 128);
+      const bool p3 = passes == 3;
       uint32_t acc_flag = 0;
       for (int ks = 0; ks < nks; ++ks) {
         const int slot = ks % stages;
         const uint32_t ph = (ks / stages) & 1;
+        const uint64_t da = desc_adv(d_a, slot * (uint32_t)stage_bytes), db = desc_adv(d_b, slot * (uint32_t)stage_bytes);
         mbar_wait(&full[slot], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)slot * stage_bytes);
-        const uint32_t sb = sa + 2 * a_half;
+        if (elect_one()) {
+          if (p3) {
 #pragma unroll
-        for (int j = 0; j < BK / 16; ++j) {
-          const uint64_t ahi = smem_desc(sa + j * 2 * lbo_a, lbo_a, 128);
-          const uint64_t alo = smem_desc(sa + a_half + j * 2 * lbo_a, lbo_a, 128);
-          const uint64_t bhi = smem_desc(sb + j * 2 * lbo_b, lbo_b, 128);
-          const uint64_t blo = smem_desc(sb + b_half + j * 2 * lbo_b, lbo_b, 128);
-          mma_bf16(tmem, ahi, bhi, idesc, acc_flag);
-          acc_flag = 1;
-          if (passes == 3) {
-            mma_bf16(tmem, alo, bhi, idesc, 1);
-            mma_bf16(tmem, ahi, blo, idesc, 1);
+            for (int j = 0; j < BK / 16; ++j) {
+              const uint64_t ahi = desc_adv(da, j * 2 * lbo_a), alo = desc_adv(da, a_half + j * 2 * lbo_a);
+              const uint64_t bhi = desc_adv(db, j * 2 * lbo_b), blo = desc_adv(db, b_half + j * 2 * lbo_b);
+              mma_bf16(tm, ahi, bhi, idesc, j == 0 ? acc_flag : 1u);
+              mma_bf16(tm, alo, bhi, idesc, 1);
+              mma_bf16(tm, ahi, blo, idesc, 1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j)
+              mma_bf16(tm, desc_adv(da, j * 2 * lbo_a), desc_adv(db, j * 2 * lbo_b), idesc, j == 0 ? acc_flag : 1u);
           }
+          mma_commit(&empty[slot]);     // frees the stage when these MMAs have read it
+          if (ks == nks - 1) mma_commit(tfull);              // accumulator complete
         }
-        mma_commit(&empty[slot]);     // frees the stage when these MMAs have read it
+        acc_flag = 1;
       }
-      mma_commit(tfull);              // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== B loader: one bulk TMA copy per stage

@@ -379,16 +379,22 @@ __global__ void __launch_bounds__(NTHR3, 1)
     }
   } else if (warp == EPI_WARPS) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(TM, H);
-      const uint32_t lbo = H * 16;
-      const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), wr_s = smem_u32(wring);
+    // The whole warp runs the loops with warp-uniform operands and one elected lane issues (tc.cuh: elect_one): under
+    // `if (lane == 0)` the compiler wrapped every UTCHMMA in a lane-broadcast loop and an MMA left only every ~93 cycles
+    // (tools/mma_rate.py), whatever its shape.  Descriptors are bases built once plus offsets.
+    {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      constexpr uint32_t idesc = idesc_bf16(TM, H);
+      constexpr uint32_t lbo = H * 16;
+      const uint64_t d_ahi = smem_desc(smem_u32(a_hi), 2048, 128), d_alo = smem_desc(smem_u32(a_lo), 2048, 128);
+      const uint64_t d_w = smem_desc(smem_u32(wring), lbo, 128);
+      const bool p3 = a.passes == 3;
       uint32_t itw = 0;
       for (int t = 0; t < a.T; ++t) {
         const uint32_t par = t & 1;
 #pragma unroll 1
         for (int nb = 0; nb < 3; ++nb) {          // r columns, u columns, candidate
-          const uint32_t d = tmem + (nb == 0 ? 0 : (nb == 1 ? H : C::CAND_COL));
+          const uint32_t d = tm + (nb == 0 ? 0 : (nb == 1 ? H : C::CAND_COL));
           if (nb == 2) {
             mbar_wait_tag<WD>(rh_ready, par, 30);
             tc_fence_after();
@@ -409,31 +415,35 @@ __global__ void __launch_bounds__(NTHR3, 1)
 #pragma unroll
             for (int s = 0; s < C::SPC; ++s, ++itw) {
               const int slot = itw % C::NSW;
+              const uint64_t dsl = desc_adv(d_w, slot * C::SLOT_BYTES);
+              const uint32_t ao = (kc * 4 + s * (C::KSLOT / 16) * 2) * 2048;
+              const uint64_t dah = desc_adv(d_ahi, ao), dal = desc_adv(d_alo, ao);
               mbar_wait_tag<WD>(&wfull[slot], (itw / C::NSW) & 1, 50 + slot);
               tc_fence_after();
-              const uint32_t sb = wr_s + slot * C::SLOT_BYTES;
+              if (elect_one()) {
+                if (p3) {
 #pragma unroll
-              for (int j = 0; j < C::KSLOT / 16; ++j) {
-                const uint32_t ao = (kc * 4 + (s * (C::KSLOT / 16) + j) * 2) * 2048;
-                const uint64_t ahi = smem_desc(a_hi_s + ao, 2048, 128), alo = smem_desc(a_lo_s + ao, 2048, 128);
-                const uint64_t bhi = smem_desc(sb + j * 2 * lbo, lbo, 128);
-                const uint64_t blo = smem_desc(sb + C::SLOT_HALF + j * 2 * lbo, lbo, 128);
-                mma_bf16(d, ahi, bhi, idesc, accf);
-                accf = 1;
-                if (a.passes == 3) {
-                  mma_bf16(d, alo, bhi, idesc, 1);
-                  mma_bf16(d, ahi, blo, idesc, 1);
+                  for (int j = 0; j < C::KSLOT / 16; ++j) {
+                    const uint64_t bhi = desc_adv(dsl, j * 2 * lbo), blo = desc_adv(dsl, C::SLOT_HALF + j * 2 * lbo);
+                    mma_bf16(d, desc_adv(dah, j * 2 * 2048), bhi, idesc, j == 0 ? accf : 1u);
+                    mma_bf16(d, desc_adv(dal, j * 2 * 2048), bhi, idesc, 1);
+                    mma_bf16(d, desc_adv(dah, j * 2 * 2048), blo, idesc, 1);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < C::KSLOT / 16; ++j)
+                    mma_bf16(d, desc_adv(dah, j * 2 * 2048), desc_adv(dsl, j * 2 * lbo), idesc, j == 0 ? accf : 1u);
                 }
+                mma_commit(&wempty[slot]);
+                if (s == C::SPC - 1 && nb == 1 && kc >= C::KOFF) mma_commit(&a_free[kc - C::KOFF]);  // state chunk read by both gate groups
+                if (s == C::SPC - 1 && kc == C::NKA - 1) mma_commit(nb == 0 ? g_r_done : (nb == 1 ? g_u_done : c_done));
               }
-              mma_commit(&wempty[slot]);
+              accf = 1;
             }
-            if (nb == 1 && kc >= C::KOFF) mma_commit(&a_free[kc - C::KOFF]);  // state chunk read by both gate groups
           }
-          if (nb == 0) mma_commit(g_r_done);
-          if (nb == 1) mma_commit(g_u_done);
-          if (nb == 2) mma_commit(c_done);
         }
       }
+      __syncwarp();
     }
   } else {
     // ======================================================================== loaders: warp 17 weights, warp 18 boxes
