@@ -111,12 +111,15 @@ __global__ void __launch_bounds__(160) tsmma_kernel(const float* __restrict__ A,
 // memory, 1: A in tensor memory.  Every CTA issues `iters` MMAs on the same operands; cycles of block 0 are returned.
 __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iters, long long* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t sm[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, dummy, done0;
   __shared__ uint32_t tslot;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (128 * 64 * 2 + 256 * 64 * 2) / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     mbar_init(&bar, mode == 4 ? 2 : 1);
+    mbar_init(&dummy, 1 << 20);
+    mbar_init(&done0, 1);
+    mbar_arrive(&done0);                                         // phase 0 of done0 is complete from the start
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(&tslot);
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
   }
   // mode 5: the whole warp runs the issue loop with warp-uniform operands and one ELECTED lane issues (TS) — the
   // compiler then feeds UTCHMMA from uniform registers instead of wrapping every MMA in a lane-broadcast loop
-  if ((mode == 5 || mode == 6) && warp == 1) {
+  if (mode >= 5 && warp == 1) {
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc = idesc_bf16(128, N);
     const uint32_t sb = smem_u32(sm) + 128 * 64 * 2;
@@ -164,7 +167,32 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
       db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
     }
     const long long t0 = clock64();
-    if (mode == 5) {
+    if (mode == 10 || mode == 11) {
+      // alternate between two accumulators: 10 = every MMA, 11 = every 6 MMAs
+      for (int i = 0; i < iters; i += 12) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) {
+            const uint32_t d = tm + ((mode == 10 ? j : j / 6) & 1) * 128;
+            mma_bf16_ts(d, tm + 256 + (j & 3) * 8, db[j & 3], idesc, 1);
+          }
+        }
+      }
+    } else if (mode == 7 || mode == 8 || mode == 9) {
+      // 7: a commit (to a barrier nobody waits on) after every 6 MMAs; 8: plus a wait on an already completed barrier and
+      // the fence in front of every group of 6; 9: wait + fence only (no commits)
+      for (int i = 0; i < iters; i += 6) {
+        if (mode >= 8) {
+          mbar_wait(&done0, 0);
+          tc_fence_after();
+        }
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) mma_bf16_ts(tm, tm + 256 + (j & 3) * 8, db[j & 3], idesc, 1);
+          if (mode != 9) mma_commit(&dummy);
+        }
+      }
+    } else if (mode == 5) {
       for (int i = 0; i < iters; i += 4) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -199,7 +227,7 @@ extern "C" int desire_selftest_tsmma(const float* A, const float* B, float* out_
 }
 
 extern "C" int desire_selftest_mma_rate(int mode, int N, int iters, int grid, long long* out_cycles, desire_stream_t stream) {
-  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 6 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
+  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 11 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
                    "desire_selftest_mma_rate: bad arguments");
   const size_t smem = 128 * 64 * 2 + 256 * 64 * 2;
   DESIRE_ENSURE_SMEM(desire::mma_rate_kernel, smem);

@@ -277,11 +277,11 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       if (g > 0) mbar_wait(pempty, (g - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        if (!(dbg & 4)) {
-#pragma unroll
+        if (!(dbg & 12)) {                                         // (timing experiments: 4 = no MMAs, 8 = no pool MMAs,
+#pragma unroll                                                   //  16 = pool hi pass only)
           for (int j = 0; j < TM / 16; ++j) {                    // K = the 128 tile rows as neighbours
             mma_bf16(t_p, desc_adv(ds, j * 2 * lbo_s), desc_adv(d_hh, j * 2 * lbo_b), idesc, j > 0);
-            if (P3) mma_bf16(t_p, desc_adv(ds, j * 2 * lbo_s), desc_adv(d_hl, j * 2 * lbo_b), idesc, 1);
+            if (P3 && !(dbg & 16)) mma_bf16(t_p, desc_adv(ds, j * 2 * lbo_s), desc_adv(d_hl, j * 2 * lbo_b), idesc, 1);
           }
         }
         mma_commit(pfull);
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     auto build = [&](int g) {                                    // selection matrix + partial counts of bin g
       const uint32_t g4 = (uint32_t)g * 0x01010101u;
       int cnt = 0;
-      if (s_on) {
+      if (s_on && !(dbg & 32)) {                                 // (32: timing experiment, handshakes only)
         const uint32_t dst = s_dst + (uint32_t)(g & 1) * (TM * TM * 2);
         for (int o = 0; o < JT / 8; ++o) {
           const uint2 w = *reinterpret_cast<const uint2*>(sb_src + 8 * o);
@@ -405,8 +405,13 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       const int* pcg = pc + (size_t)(g % 3) * 4 * TM + frow;     // read before pempty: buffer g%3 is rewritten by build(g+3)
       const int cnt = pcg[0] + pcg[TM] + pcg[2 * TM] + pcg[3 * TM];
       float v[CW];
-      if constexpr (CW == 32) tmem_ld32(t_p, v); else tmem_ld16(t_p, v);
-      tmem_ld_wait();
+      if (!(dbg & 32)) {
+        if constexpr (CW == 32) tmem_ld32(t_p, v); else tmem_ld16(t_p, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] = 0.f;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pempty);
@@ -422,7 +427,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       if (g >= 2) mbar_wait(&aempty[g & 1], ((g - 2) >> 1) & 1);             // fc(g-2) has read this stage
       tc_fence_after();
       const uint32_t ta = t_a + (g & 1) * H;
-      if constexpr (CW == 32) {
+      if (dbg & 32) {
+      } else if constexpr (CW == 32) {
         tmem_st16(ta, reinterpret_cast<const float*>(hi));
         tmem_st16(ta + H / 2, reinterpret_cast<const float*>(lo));
       } else {
