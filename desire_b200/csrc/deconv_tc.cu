@@ -17,6 +17,7 @@
 //              of n-tile t+1 overlap the scatter of n-tile t.
 //   warp 9     streams the packed weights (one 32-wide K stage of one n-tile per 1-D bulk TMA copy).
 #include <algorithm>
+#include <utility>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -57,8 +58,58 @@ __host__ __device__ inline DcLayout dc_layout(int Cin, int nstg, int spt) {
   return L;
 }
 
-// packed weights: for cg, nt, ks: { hi [4][BNt][8 bf16], lo [4][BNt][8 bf16] } with n = tap_local*32 + c
-__global__ void pack_deconv_kernel(const float* __restrict__ W, int Cin, int Cout, int ntaps, uint4* __restrict__ out) {
+// Order in which the taps are laid out along N and scattered.  Two taps can write the same output cell only if they
+// agree in (ky mod stride, kx mod stride), so the taps are taken ROUND by round — round r holds the r-th tap of every
+// such class — and a round's taps (up to stride^2 of them) are scattered back to back; the lockstep barrier is only
+// needed between rounds: 9 barriers instead of 25 for the 5x5 stride-2 layer (stride 1: every tap is its own round).
+template <int KS, int STRIDE>
+struct TapOrder {
+  int tap[KS * KS];        // slot -> tap (ky * KS + kx)
+  bool last[KS * KS];      // slot is the last one of its round
+  constexpr TapOrder() : tap{}, last{} {
+    int cls_n[STRIDE * STRIDE] = {};
+    int cls_tap[STRIDE * STRIDE][KS * KS] = {};
+    for (int t = 0; t < KS * KS; ++t) {
+      const int c = ((t / KS) % STRIDE) * STRIDE + (t % KS) % STRIDE;
+      cls_tap[c][cls_n[c]++] = t;
+    }
+    int s = 0;
+    for (int r = 0; s < KS * KS; ++r) {
+      for (int c = 0; c < STRIDE * STRIDE; ++c)
+        if (cls_n[c] > r) tap[s++] = cls_tap[c][r];
+      last[s - 1] = true;
+    }
+  }
+};
+struct TapPerm {
+  int tap[32];
+};
+// everything the scatter loop needs to know about a slot, as constant expressions
+template <int KS, int STRIDE, int TPT_>
+struct TapPlan {
+  static constexpr TapOrder<KS, STRIDE> ORD{};
+  static constexpr int NT = KS * KS;
+  // the taps loaded so far are scattered after this slot: its round ends, or its n-tile (= the accumulator) ends
+  static constexpr bool flush(int s) { return ORD.last[s] || s % TPT_ == TPT_ - 1 || s == NT - 1; }
+  // taps of the same n-tile loaded before slot s and not scattered yet
+  static constexpr int pending(int s) {
+    int n = 0;
+    for (int q = s - 1; q >= (s / TPT_) * TPT_ && !flush(q); --q) ++n;
+    return n;
+  }
+};
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+// packed weights: for cg, nt, ks: { hi [4][BNt][8 bf16], lo [4][BNt][8 bf16] } with n = slot_local*32 + c (slot -> tap: TapOrder)
+__global__ void pack_deconv_kernel(const float* __restrict__ W, int Cin, int Cout, int ntaps, TapPerm perm,
+                                   uint4* __restrict__ out) {
   const int nks = Cin / 32, ncg = Cout / CG, nnt = (ntaps + TPT - 1) / TPT;
   // chunk-granular work items: (cg, nt, ks, c, n)
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,7 +124,7 @@ __global__ void pack_deconv_kernel(const float* __restrict__ W, int Cin, int Cou
         long t = idx / BNt;
         const int c = (int)(t % 4);
         const int ks = (int)(t / 4);
-        const int tap = nt * TPT + n / CG, o = cg * CG + n % CG;
+        const int tap = perm.tap[nt * TPT + n / CG], o = cg * CG + n % CG;
         const float* src = W + ((size_t)tap * Cout + o) * Cin + ks * 32 + c * 8;
         float v[8];
 #pragma unroll
@@ -169,36 +220,49 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
       // zero the output tile of this channel group
       for (int e = tid; e < ntile_el / 4; e += 256) reinterpret_cast<float4*>(outt)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // ---- (b) scatter the accumulators, n-tile by n-tile, tap by tap
-      for (int nt = 0; nt < nnt; ++nt, ++use) {
+      // ---- (b) scatter the accumulators, n-tile by n-tile, round by round (TapOrder): the taps of a round cannot meet in
+      // an output cell, so their TMEM loads are issued together and their read-modify-writes run back to back; rounds
+      // stay in lockstep (named barrier) => deterministic, race-free
+      using Plan = TapPlan<KS, STRIDE, TPT>;
+      static_for<nnt>([&](auto ntc) {
+        constexpr int nt = decltype(ntc)::value;
         const int ab = use & 1;
-        const int taps = min(TPT, ntaps - nt * TPT);
         mbar_wait(&acc_full[ab], (use >> 1) & 1);
         tc_fence_after();
-        for (int tl = 0; tl < taps; ++tl) {
-          const int t = nt * TPT + tl;
-          const int ky = t / KS, kx = t - ky * KS;
-          const int oy = iy * STRIDE + ky - a.pad, ox = ix * STRIDE + kx - a.pad;
-          float v[16];
-          tmem_ld16(trow + ab * 256 + tl * CG + half * 16, v);
-          tmem_ld_wait();
-          if (oy >= 0 && oy < HOUT && ox >= 0 && ox < HOUT) {
-            float* o = osamp + (size_t)(oy * HOUT + ox) * CG;
-            const int rot = swz(oy, ox, sh);
+        float v[STRIDE * STRIDE][16];
+        static_for<TPT>([&](auto tlc) {
+          constexpr int tl = decltype(tlc)::value, slot = nt * TPT + tl;
+          if constexpr (slot < ntaps) {
+            constexpr int nvb = Plan::pending(slot);
+            tmem_ld16(trow + ab * 256 + tl * CG + half * 16, v[nvb]);
+            if constexpr (Plan::flush(slot)) {
+              tmem_ld_wait();
+              static_for<nvb + 1>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                constexpr int t = Plan::ORD.tap[slot - nvb + k];
+                constexpr int ky = t / KS, kx = t - ky * KS;
+                const int oy = iy * STRIDE + ky - a.pad, ox = ix * STRIDE + kx - a.pad;
+                if (oy >= 0 && oy < HOUT && ox >= 0 && ox < HOUT) {
+                  float* o = osamp + (size_t)(oy * HOUT + ox) * CG;
+                  const int rot = swz(oy, ox, sh);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4* dst = reinterpret_cast<float4*>(o) + ((half * 4 + q + rot) & 7);
-              float4 cur = *dst;
-              cur.x += v[4 * q]; cur.y += v[4 * q + 1]; cur.z += v[4 * q + 2]; cur.w += v[4 * q + 3];
-              *dst = cur;
+                  for (int q = 0; q < 4; ++q) {
+                    float4* dst = reinterpret_cast<float4*>(o) + ((half * 4 + q + rot) & 7);
+                    float4 cur = *dst;
+                    cur.x += v[k][4 * q]; cur.y += v[k][4 * q + 1]; cur.z += v[k][4 * q + 2]; cur.w += v[k][4 * q + 3];
+                    *dst = cur;
+                  }
+                }
+              });
+              if constexpr (Plan::ORD.last[slot]) asm volatile("bar.sync 1, 256;" ::: "memory");
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");     // taps in lockstep: no two taps touch a cell at once
-        }
+        });
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[ab]);
-      }
+        ++use;
+      });
       // ---- (c) bias + per-(sample, channel) BN over the Pout positions + activation + store, four channels per
       // thread: a thread owns one channel quad (its bias / gamma / beta live in registers), every tile access is one
       // LDS.128 of the XOR-rotated quad and every store one 16-byte STG (the scalar form of this phase was 47 % of
@@ -509,7 +573,14 @@ int deconv_tc(const float* X, int R, int Hin, int Hout, int Cin, int Cout, int k
   for (int nt = 0; nt * TPT < ntaps; ++nt) items += (long)nks * 4 * std::min(TPT, ntaps - nt * TPT) * CG;
   items *= ncg;
   // the pack kernel walks the (cg, nt) tiles per thread; give every tile's items a thread
-  pack_deconv_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(W, Cin, Cout, ntaps, (uint4*)pack_ws);
+  TapPerm perm{};
+  if (stride == 2 && ks == 5) {
+    constexpr TapOrder<5, 2> o{};
+    for (int i = 0; i < 25; ++i) perm.tap[i] = o.tap[i];
+  } else {
+    for (int i = 0; i < 32; ++i) perm.tap[i] = i;               // stride 1: natural order (TapOrder<KS, 1> is the identity)
+  }
+  pack_deconv_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(W, Cin, Cout, ntaps, perm, (uint4*)pack_ws);
   DESIRE_LAUNCH_CHECK();
   DcArgs a{};
   a.X = X; a.R = R; a.Hin = Hin; a.Hout = Hout; a.Cin = Cin; a.Cout = Cout; a.ks = ks; a.stride = stride; a.pad = pad;

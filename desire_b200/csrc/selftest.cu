@@ -167,7 +167,18 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
       db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
     }
     const long long t0 = clock64();
-    if (mode == 10 || mode == 11) {
+    if (mode == 12) {
+      // how many MMAs does the queue behind an issuing thread take before the issue itself blocks?  out[1 + k] = cycles
+      // after which the (4k + 4)-th MMA had been ISSUED
+      for (int k = 0; k < 16; ++k) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_bf16_ts(tm, tm + 256 + j * 8, db[j], idesc, 1);
+        }
+        __syncwarp();
+        if (blockIdx.x == 0 && tid == 32) out[1 + k] = clock64() - t0;
+      }
+    } else if (mode == 10 || mode == 11) {
       // alternate between two accumulators: 10 = every MMA, 11 = every 6 MMAs
       for (int i = 0; i < iters; i += 12) {
         if (elect_one()) {
@@ -227,7 +238,7 @@ extern "C" int desire_selftest_tsmma(const float* A, const float* B, float* out_
 }
 
 extern "C" int desire_selftest_mma_rate(int mode, int N, int iters, int grid, long long* out_cycles, desire_stream_t stream) {
-  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 11 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
+  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 12 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
                    "desire_selftest_mma_rate: bad arguments");
   const size_t smem = 128 * 64 * 2 + 256 * 64 * 2;
   DESIRE_ENSURE_SMEM(desire::mma_rate_kernel, smem);

@@ -19,3 +19,9 @@ for grid in (148,):
             cyc = out.item() / 4092
             print("grid %3d  %s  N=%3d: %.1f cycles per MMA (floor %d) -> %.0f%% of the tensor peak" % (
                 grid, ("SS", "TS", "SS two accumulators", "TS two accumulators", "TS two issuing threads (cycles per MMA of ONE thread)", "TS elected lane, uniform operands", "SS elected lane, uniform operands", "TS elected + commit per 6 MMAs", "TS elected + wait, fence, commit per 6 MMAs", "TS elected + wait, fence per 6 MMAs", "TS elected, accumulators alternate every MMA", "TS elected, accumulators alternate every 6 MMAs")[mode], N, cyc, N // 2, 100 * (N / 2) / cyc))
+
+out = torch.zeros(32, dtype=torch.int64, device="cuda")
+for it in range(2):
+    _lib.check(lib.desire_selftest_mma_rate(12, 128, 64, 148, C.c_void_p(out.data_ptr()), None), "rate")
+    torch.cuda.synchronize()
+print("cycles until the n-th MMA (N=128) was issued:", ", ".join("%d: %d" % (4 * k + 4, out[1 + k].item()) for k in range(16)))
