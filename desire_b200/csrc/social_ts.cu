@@ -53,7 +53,7 @@ __host__ __device__ inline Layout make_layout(int H, int Npad, int n_rad, int n_
   L.rowmap = off; off += TM * 8;
   off = (off + 15) / 16 * 16;
   L.tab = off; off += 24 * 4;                                   // 8 squared radial edges (+inf padded), 8 directions
-  L.bars = off; off += (2 * MAXNB + 10) * 8 + 32;
+  L.bars = off; off += (2 * MAXNB + 12) * 8 + 48;              // barriers, tensor-memory slot, existence bits, bin mask
   off = (off + 1023) / 1024 * 1024;
   L.slot_bytes = 2 * (size_t)4 * H * 16;                        // one packed block of 32 K values: hi + lo
   L.ring = off;
@@ -109,6 +109,13 @@ __device__ __forceinline__ int logpolar_bin_regs(float dx, float dy, const float
   return (rb < 0 || rb >= n_rad) ? -1 : rb * n_ang + ab;
 }
 
+// the tile's stage list: bins with at least one pair; a tile without any pair runs one stage on (empty) bin 0, which
+// leaves D = 0 for the epilogue
+__device__ __forceinline__ uint64_t active_bins(const uint32_t* binmask) {
+  const uint64_t m = (uint64_t)binmask[0] | ((uint64_t)binmask[1] << 32);
+  return m ? m : 1ull;
+}
+
 // 0x80 in every byte of w that equals the byte replicated in g4 (exact per byte, no cross-byte carries)
 __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t g4) {
   const uint32_t t = w ^ g4;
@@ -145,8 +152,10 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
   uint64_t* pfull = aempty + 2;                      // pool MMAs of a bin complete (commit)
   uint64_t* pempty = pfull + 1;                      // P read into registers (16 warps)
   uint64_t* tfull = pempty + 1;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* lready = tfull + 1;                      // the bin mask of the tile is complete (16 warps)
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(lready + 1);
   uint32_t* exist = tslot + 1;                       // bit l of word l/32: tile lane l is an existing agent
+  uint32_t* binmask = exist + 4;                     // bit g: some (row, neighbour) pair of the tile falls into bin g
   const int nb = L.nb;
   const bool tr = trace != nullptr && blockIdx.x == 0;
 #define TRACE(i) do { if (tr) trace[i] = clock64(); } while (0)
@@ -194,6 +203,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     mbar_init(pfull, 1);
     mbar_init(pempty, NPW);
     mbar_init(tfull, 1);
+    mbar_init(lready, NPW);
+    binmask[0] = binmask[1] = 0u;
     fence_barrier_init();
   }
   if (warp == NPW) tmem_alloc<TCOLS>(tslot);
@@ -204,16 +215,21 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     // ===================== weight loader
     if (lane == 0) {
       const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed);
-      for (int kb = 0; kb < nblk; ++kb) {
-        const int slot = kb % nb;
-        mbar_wait_idle(&bempty[slot], ((kb / nb) & 1) ^ 1);
-        if ((dbg & 2) && kb >= nb) {                             // timing experiment: no weight traffic after the first ring fill
-          mbar_arrive(&bfull[slot]);
-          continue;
+      mbar_wait_idle(lready, 0);                                 // which bins does the tile use at all?
+      uint64_t rem = active_bins(binmask);
+      for (int kb = 0; rem; rem &= rem - 1) {
+        const int g = __ffsll((long long)rem) - 1;
+        for (int c = 0; c < CPB; ++c, ++kb) {
+          const int slot = kb % nb;
+          mbar_wait_idle(&bempty[slot], ((kb / nb) & 1) ^ 1);
+          if ((dbg & 2) && kb >= nb) {                           // timing experiment: no weight traffic after the first ring fill
+            mbar_arrive(&bfull[slot]);
+            continue;
+          }
+          mbar_arrive_expect_tx(&bfull[slot], (uint32_t)L.slot_bytes);
+          bulk_g2s_hint(ring + (size_t)slot * L.slot_bytes, src + (size_t)(g * CPB + c) * L.slot_bytes,
+                        (uint32_t)L.slot_bytes, &bfull[slot], L2_EVICT_LAST);
         }
-        mbar_arrive_expect_tx(&bfull[slot], (uint32_t)L.slot_bytes);
-        bulk_g2s_hint(ring + (size_t)slot * L.slot_bytes, src + (size_t)kb * L.slot_bytes, (uint32_t)L.slot_bytes,
-                      &bfull[slot], L2_EVICT_LAST);
       }
     }
   } else if (warp == NPW) {
@@ -227,7 +243,9 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     constexpr uint32_t lbo_b = H * 16;
     const uint64_t d_ring = smem_desc(smem_u32(ring), lbo_b, 128);
     int kb = 0;
-    for (int g = 0; g < G; ++g) {
+    mbar_wait(lready, 0);
+    const int nst = __popcll(active_bins(binmask));              // stages = bins that hold at least one pair of the tile
+    for (int g = 0; g < nst; ++g) {                              // (g counts stages here; the weights follow the bin list)
       const int as = g & 1;
       mbar_wait(&afull[as], (g >> 1) & 1);
       tc_fence_after();
@@ -270,7 +288,9 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     const uint32_t t_p = tmem + H;
     const uint64_t d_s0 = smem_desc(smem_u32(sm), lbo_s, 128);
     const uint64_t d_hh = smem_desc(smem_u32(ht), lbo_b, 128), d_hl = desc_adv(d_hh, H * TM * 2);
-    for (int g = 0; g < G; ++g) {
+    mbar_wait(lready, 0);
+    const int nst = __popcll(active_bins(binmask));
+    for (int g = 0; g < nst; ++g) {                              // stages
       const int sb = g & 1;
       const uint64_t ds = desc_adv(d_s0, sb * (TM * TM * 2));
       mbar_wait(&sfull[sb], (g >> 1) & 1);
@@ -335,10 +355,20 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
 #pragma unroll
       for (int e = 0; e < 16; ++e) asm volatile("" : "+f"(dr[e]));
       uint8_t* brow = bins + (size_t)rl * L.bin_stride;
+      uint32_t m0 = 0u, m1 = 0u;                                 // bins seen by this thread
       for (int j = q; j < Npad; j += 4) {
         const bool on = valid && j < N && j != me && ((exist[(gbase + j) >> 5] >> ((gbase + j) & 31)) & 1u);
         const int g = logpolar_bin_regs(px[gbase + j] - xi, py[gbase + j] - yi, re, dr, a.n_rad, a.n_ang);
         brow[j] = (uint8_t)(on ? g : -1);                        // 255 = no bin (a masked row still pools its neighbours)
+        if (on && g >= 0) {
+          if (g < 32) m0 |= 1u << g; else m1 |= 1u << (g - 32);
+        }
+      }
+      m0 = __reduce_or_sync(0xffffffffu, m0);
+      m1 = __reduce_or_sync(0xffffffffu, m1);
+      if (lane == 0) {
+        if (m0) atomicOr(&binmask[0], m0);
+        if (m1) atomicOr(&binmask[1], m1);
       }
     }
     if (tid == 0) TRACE(9);
@@ -353,9 +383,14 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     }
     fence_proxy_async();
     asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+    if (lane == 0) mbar_arrive(lready);                          // the other warps may read the bin mask now
     tc_fence_after();
     const uint32_t tmem = *tslot;
     if (tid == 0) TRACE(1);
+    // Bins without a single pair in this tile are skipped altogether (their A operand would be zero): the stage list
+    // is the set bits of the mask, in ascending bin order, for every role alike.
+    const uint64_t act = active_bins(binmask);
+    const int nst = __popcll(act);
 
     // ---- S builder role: thread (row = tid % 128, part = tid / 128) owns JT consecutive neighbours of its row
     const int srow = tid & (TM - 1), part = tid >> 7;
@@ -364,8 +399,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     const uint8_t* sb_src = bins + (size_t)srow * L.bin_stride + part * JT;
     // K index of neighbour j of this row = its tile lane: group base + j
     const uint32_t s_dst = smem_u32(sm) + (uint32_t)(((srow / Npad) * Npad + part * JT) / 8) * (TM * 16) + srow * 16;
-    auto build = [&](int g) {                                    // selection matrix + partial counts of bin g
-      const uint32_t g4 = (uint32_t)g * 0x01010101u;
+    auto build = [&](int g, int bin) {                           // selection matrix + partial counts of stage g = bin `bin`
+      const uint32_t g4 = (uint32_t)bin * 0x01010101u;
       int cnt = 0;
       if (s_on && !(dbg & 32)) {                                 // (32: timing experiment, handshakes only)
         const uint32_t dst = s_dst + (uint32_t)(g & 1) * (TM * TM * 2);
@@ -391,12 +426,15 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     const uint32_t t_p = tmem + lane_f + H + cg * CW;
     const uint32_t t_a = tmem + lane_f + 2 * H + cg * (CW / 2);
 
-    build(0);
-    for (int g = 0; g < G; ++g) {
-      if (tid == 0) TRACE(16 + 8 * g);
-      if (g + 1 < G) {
+    uint64_t rem = act;
+    build(0, __ffsll((long long)rem) - 1);
+    rem &= rem - 1;
+    for (int g = 0; g < nst; ++g) {                              // stages
+      if (tid == 0 && g < 36) TRACE(16 + 8 * g);
+      if (g + 1 < nst) {
         if (g >= 1) mbar_wait(&sempty[(g + 1) & 1], ((g - 1) >> 1) & 1);     // pool(g-1) has read this buffer
-        build(g + 1);
+        build(g + 1, __ffsll((long long)rem) - 1);
+        rem &= rem - 1;
       }
       if (tid == 0) TRACE(16 + 8 * g + 1);
       mbar_wait(pfull, g & 1);                                   // pool(g) complete (=> every warp's build(g) is visible)

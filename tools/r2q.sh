@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_conv_util.py tests/test_gpu_parity.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py tests/test_gpu_social_fc.py tests/test_gpu_fullsize.py -m gpu -x -q -k "not cfg5 and not cfg3" 2>&1 | tail -2
 timeout 400 python bench.py --steps 10 --warmup 3 --no-train --no-cpu-baseline --breakdown gpurun_out/q_breakdown.json > gpurun_out/q_bench.json 2> gpurun_out/q_bench.err; echo "bench rc=$?"
 python - <<'PY'
 import json
