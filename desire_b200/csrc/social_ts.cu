@@ -89,24 +89,33 @@ __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
-// log-polar bin from tables held in registers (8 squared radial edges padded with +inf, 8 sector directions): the same
-// arithmetic and the same decisions as logpolar_bin() in common.cuh, branch-free.  n_rad <= 7, n_ang <= 8.
-__device__ __forceinline__ int logpolar_bin_regs(float dx, float dy, const float (&re)[8], const float (&dr)[16], int n_rad,
-                                                 int n_ang) {
+// Log-polar bins of BOTH directions of a pair from tables held in registers (8 squared radial edges padded with +inf,
+// 8 sector directions): d = pos_j - pos_i gives the bin of j as seen from i (fwd), -d the bin of i as seen from j (bwd).
+// The same arithmetic and the same decisions as logpolar_bin() in common.cuh, branch-free: r2 is the same for both
+// directions, and every cross product of -d is exactly the negated cross product of d (negation commutes with the
+// roundings), so "cross(-d) >= 0" is "cross(d) <= 0".  n_rad <= 7, n_ang <= 8.
+__device__ __forceinline__ void logpolar_bin_pair(float dx, float dy, const float (&re)[8], const float (&dr)[16], int n_rad,
+                                                  int n_ang, int& fwd, int& bwd) {
   const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
   int rb = -1;
-  uint32_t ge = 0;
+  uint32_t ge = 0, le = 0;
 #pragma unroll
   for (int e = 0; e < 8; ++e) rb += (r2 >= re[e]) ? 1 : 0;
 #pragma unroll
-  for (int s = 0; s < 8; ++s)
-    ge |= (__fsub_rn(__fmul_rn(dr[2 * s], dy), __fmul_rn(dr[2 * s + 1], dx)) >= 0.f ? 1u : 0u) << s;
-  ge &= (1u << n_ang) - 1u;
+  for (int s = 0; s < 8; ++s) {
+    const float c = __fsub_rn(__fmul_rn(dr[2 * s], dy), __fmul_rn(dr[2 * s + 1], dx));
+    ge |= (c >= 0.f ? 1u : 0u) << s;
+    le |= (c <= 0.f ? 1u : 0u) << s;
+  }
+  const uint32_t all = (1u << n_ang) - 1u;
+  ge &= all;
+  le &= all;
   // the first sector s with ge[s] and not ge[s+1] (cyclically), else the last one
-  const uint32_t nxt = (ge >> 1) | ((ge & 1u) << (n_ang - 1));
-  const uint32_t hit = ge & ~nxt;
-  const int ab = hit ? __ffs(hit) - 1 : n_ang - 1;
-  return (rb < 0 || rb >= n_rad) ? -1 : rb * n_ang + ab;
+  const uint32_t hf = ge & ~((ge >> 1) | ((ge & 1u) << (n_ang - 1)));
+  const uint32_t hb = le & ~((le >> 1) | ((le & 1u) << (n_ang - 1)));
+  const bool out = rb < 0 || rb >= n_rad;
+  fwd = out ? -1 : rb * n_ang + (hf ? __ffs(hf) - 1 : n_ang - 1);
+  bwd = out ? -1 : rb * n_ang + (hb ? __ffs(hb) - 1 : n_ang - 1);
 }
 
 // the tile's stage list: bins with at least one pair; a tile without any pair runs one stage on (empty) bin 0, which
@@ -332,18 +341,26 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const long r = rowmap[oct * 8 + e];
-        hv[it][e] = r >= 0 ? __ldg(a.h + r * (long)a.ld_h + c) : 0.f;
+        hv[it][e] = (r >= 0 && !(dbg & 64)) ? __ldg(a.h + r * (long)a.ld_h + c) : 0.f;   // (64: timing experiment)
       }
     }
+    {
+      uint4* b4 = reinterpret_cast<uint4*>(bins);                // 255 = no bin
+      for (int e = tid; e < (int)(TM * L.bin_stride / 16); e += PT) b4[e] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
     if (tid == 0) TRACE(7);
-    asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");          // the tables are complete
+    asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");          // the tables and the bin fill are complete
     if (tid == 0) TRACE(8);
-    // bins: thread (row = tid % 128, quarter = tid / 128) takes neighbours j = quarter, quarter + 4, ...
+    // bins: one evaluation per UNORDERED pair {i, j} of a group gives bins[i][j] and bins[j][i].  Row i takes the pairs
+    // {i, (i + k) mod N}, k = 1 .. (N-1)/2 (and k = N/2 for the first half of the rows when N is even): every pair once,
+    // the same number of pairs per row; thread (row = tid % 128, quarter = tid / 128) takes k = 1 + quarter, 5 + quarter, ..
+    // Entries no pair writes (self, padding, missing agents, rows of no group) keep the 255 of the fill above.
     {
       const int rl = tid & (TM - 1), q = tid >> 7;
-      const bool valid = rowmap[rl] >= 0;
-      const int gbase = (rl / Npad) * Npad, me = rl % Npad;
+      const int gbase = (rl / Npad) * Npad, i = rl % Npad;
+      const bool valid = rowmap[rl] >= 0;                        // => every row i' < N of this group is valid
       const float xi = px[rl], yi = py[rl];
+      const bool ex_i = (exist[rl >> 5] >> (rl & 31)) & 1u;
       float re[8], dr[16];
 #pragma unroll
       for (int e = 0; e < 8; e += 4) *reinterpret_cast<float4*>(re + e) = *reinterpret_cast<const float4*>(tab + e);
@@ -354,14 +371,25 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       for (int e = 0; e < 8; ++e) asm volatile("" : "+f"(re[e]));
 #pragma unroll
       for (int e = 0; e < 16; ++e) asm volatile("" : "+f"(dr[e]));
-      uint8_t* brow = bins + (size_t)rl * L.bin_stride;
+      uint8_t* bgrp = bins + (size_t)gbase * L.bin_stride;       // rows of this group
+      const int kmax = valid ? (N - 1) / 2 + ((N % 2 == 0 && i < N / 2) ? 1 : 0) : 0;
       uint32_t m0 = 0u, m1 = 0u;                                 // bins seen by this thread
-      for (int j = q; j < Npad; j += 4) {
-        const bool on = valid && j < N && j != me && ((exist[(gbase + j) >> 5] >> ((gbase + j) & 31)) & 1u);
-        const int g = logpolar_bin_regs(px[gbase + j] - xi, py[gbase + j] - yi, re, dr, a.n_rad, a.n_ang);
-        brow[j] = (uint8_t)(on ? g : -1);                        // 255 = no bin (a masked row still pools its neighbours)
-        if (on && g >= 0) {
-          if (g < 32) m0 |= 1u << g; else m1 |= 1u << (g - 32);
+      for (int k = 1 + q; k <= kmax; k += 4) {
+        int j = i + k;
+        if (j >= N) j -= N;
+        const bool ex_j = (exist[(gbase + j) >> 5] >> ((gbase + j) & 31)) & 1u;
+        int gf, gb;
+        logpolar_bin_pair(px[gbase + j] - xi, py[gbase + j] - yi, re, dr, a.n_rad, a.n_ang, gf, gb);
+        // a masked row still pools its existing neighbours: only the NEIGHBOUR has to exist
+        if (!ex_j) gf = -1;
+        if (!ex_i) gb = -1;
+        bgrp[(size_t)i * L.bin_stride + j] = (uint8_t)gf;
+        bgrp[(size_t)j * L.bin_stride + i] = (uint8_t)gb;
+        if (gf >= 0) {
+          if (gf < 32) m0 |= 1u << gf; else m1 |= 1u << (gf - 32);
+        }
+        if (gb >= 0) {
+          if (gb < 32) m0 |= 1u << gb; else m1 |= 1u << (gb - 32);
         }
       }
       m0 = __reduce_or_sync(0xffffffffu, m0);
