@@ -15,6 +15,7 @@
 // Full/empty mbarrier ring of `stages` stages; accumulator handed to the epilogue by tcgen05.commit.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -242,6 +243,39 @@ __global__ void pack_b_kernel(const float* __restrict__ W, int ldw, int trans, i
   stage[KC * BN + c * BN + n] = s.lo;
 }
 
+// Epilogue of one 32-column chunk held in registers: rank-2 term, bias, activation.  The bias and the rank-2 vectors are
+// read as float4 (16-byte aligned: n0 % 32 == 0, N % 4 == 0) before any arithmetic and the activation is selected ONCE per
+// chunk: with a per-element `if (bias) x += __ldg(..); x = act_apply(x, act)` the branches of act_apply kept every load
+// behind the previous element's — 32 serial L2 round trips, ~7 k cycles per chunk, which is what bounded the tall GEMMs
+// (the Decoder-2 input projection spent 21 us per 128 x 192 tile in it).
+__device__ __forceinline__ void chunk_epilogue(float (&acc)[32], const float* bias_c, const float* p0, int N, float s0,
+                                               float s1, int act) {
+  if (p0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p0 + j));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p0 + N + j));
+      acc[j] = fmaf(s0, a.x, fmaf(s1, b.x, acc[j]));
+      acc[j + 1] = fmaf(s0, a.y, fmaf(s1, b.y, acc[j + 1]));
+      acc[j + 2] = fmaf(s0, a.z, fmaf(s1, b.z, acc[j + 2]));
+      acc[j + 3] = fmaf(s0, a.w, fmaf(s1, b.w, acc[j + 3]));
+    }
+  }
+  if (bias_c) {
+    float4 bv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(bias_c) + j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[4 * j] += bv[j].x; acc[4 * j + 1] += bv[j].y; acc[4 * j + 2] += bv[j].z; acc[4 * j + 3] += bv[j].w;
+    }
+  }
+  if (act != DESIRE_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = act_apply(acc[j], act);
+  }
+}
+
 template <class ALoad>
 __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __restrict__ Bp,
                                                        const float* __restrict__ bias, float* __restrict__ C, int ldc,
@@ -316,6 +350,7 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
     tc_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const int n0 = jn * BN;
+    const bool bias_vec = bias && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && N % 4 == 0;
     if (tma_c) {
       // Output through shared memory + TMA tensor-map stores (SASS UTMASTG): the thread-per-row float4 stores below
       // touch 32 different 128-byte lines per instruction, which throttled the huge-M GEMMs (Decoder-2 input projection:
@@ -327,17 +362,27 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
         float acc[32];
         tmem_ld32(trow + c0, acc);
         tmem_ld_wait();
-        if (r2.P && m < M) {
-          const float s0 = __ldg(r2.s + 2 * (size_t)m), s1 = __ldg(r2.s + 2 * (size_t)m + 1);
-          const float* p0 = r2.P + (size_t)(m / r2.div) * 2 * N + n0 + c0;
+        {
+          float s0 = 0.f, s1 = 0.f;
+          const float* p0 = nullptr;
+          if (r2.P && m < M) {
+            s0 = __ldg(r2.s + 2 * (size_t)m);
+            s1 = __ldg(r2.s + 2 * (size_t)m + 1);
+            p0 = r2.P + (size_t)(m / r2.div) * 2 * N + n0 + c0;
+          }
+          const bool late_bias = bias && !bias_vec;            // unaligned bias: scalar loads, activation afterwards
+          chunk_epilogue(acc, bias_vec ? bias + n0 + c0 : nullptr, p0, N, s0, s1, late_bias ? DESIRE_ACT_NONE : act);
+          if (late_bias) {
+            float bv[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = fmaf(s0, __ldg(p0 + j), fmaf(s1, __ldg(p0 + N + j), acc[j]));
-        }
+            for (int j = 0; j < 32; ++j) bv[j] = __ldg(bias + n0 + c0 + j);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = acc[j];
-          if (bias) x += __ldg(bias + n0 + c0 + j);
-          acc[j] = act_apply(x, act);
+            for (int j = 0; j < 32; ++j) acc[j] += bv[j];
+            if (act != DESIRE_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = act_apply(acc[j], act);
+            }
+          }
         }
         const uint32_t box = obox + (ci & 1) * (TM * 128);
         if (ci >= 2) {                                   // the store that last read this box has finished reading it
@@ -378,34 +423,44 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
             if (j >= ncol || n0 + c0 + j >= N) break;
             atomicAdd(crow + j, acc[j]);
           }
-        } else if (vec_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j >= ncol) break;
-            float4 o;
-            float* po = reinterpret_cast<float*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = acc[j + e];
-              if (bias) x += __ldg(bias + n0 + c0 + j + e);
-              po[e] = x;
-            }
-            if (accumulate) {
-              float4 old = *reinterpret_cast<const float4*>(crow + j);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            o.x = act_apply(o.x, act); o.y = act_apply(o.y, act); o.z = act_apply(o.z, act); o.w = act_apply(o.w, act);
-            *reinterpret_cast<float4*>(crow + j) = o;
-          }
         } else {
+          // bias first, all loads before any arithmetic or branch (see chunk_epilogue), then (+C), activation, store
+          if (bias) {
+            float bv[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (j >= ncol || n >= N) break;
-            float x = acc[j];
-            if (bias) x += __ldg(bias + n);
-            if (accumulate) x += crow[j];
-            crow[j] = act_apply(x, act);
+            for (int j = 0; j < 32; ++j) bv[j] = (j < ncol && n0 + c0 + j < N) ? __ldg(bias + n0 + c0 + j) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += bv[j];
+          }
+          if (vec_ok) {
+            if (accumulate) {
+              float4 old[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                old[j] = 4 * j < ncol ? *reinterpret_cast<const float4*>(crow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                acc[4 * j] += old[j].x; acc[4 * j + 1] += old[j].y; acc[4 * j + 2] += old[j].z; acc[4 * j + 3] += old[j].w;
+              }
+            }
+            if (act != DESIRE_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = act_apply(acc[j], act);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j >= ncol) break;
+              *reinterpret_cast<float4*>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c0 + j;
+              if (j >= ncol || n >= N) break;
+              float x = acc[j];
+              if (accumulate) x += crow[j];
+              crow[j] = act_apply(x, act);
+            }
           }
         }
       }
@@ -530,6 +585,226 @@ int pack_for_plan(const Plan& p, const float* W, int ldw, bool trans_b, int K, i
   return DESIRE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent, weight-stationary variant for short-K / huge-M products (the Decoder-2 input projection: M = R*T_f =
+// 460 800 rows, K = 48, N = 3H = 384 at the bench workload, 708 MB of output per call).  With one output tile per CTA
+// (kernel above) 7 200 CTAs each pay barrier set-up, TMEM allocation, the weight fetch and a prologue / main loop /
+// epilogue that do not overlap: 0.62 ms per call where the HBM traffic needs 0.12.  Here
+//   * a CTA per SM loads the WHOLE packed weight image once (<= 96 KB) and walks over M tiles (stride gridDim.x);
+//   * warps 0-3 (thread = row) load + split the A rows of tile i+1 while tile i is multiplied and tile i-1 leaves;
+//   * warp 4 issues the MMAs of one (tile, n-tile) into one of TWO accumulators (2 x 256 TMEM columns);
+//   * warps 6-9 drain the other accumulator: bias / rank-2 term / activation, 128-byte-swizzled [128 x 32] boxes in
+//     shared memory, TMA tensor-map stores (two boxes in flight).
+// Requirements (gemm_persist_eligible): dense A, K % 8 == 0, K <= 64, N % 32 == 0, no accumulate, 16-byte aligned rows.
+constexpr int PN_A = 2;                 // A tiles in shared memory
+constexpr int PNTHR = 320;
+
+__global__ void __launch_bounds__(PNTHR, 1) gemm_tc_persist_kernel(DenseA8 A_, const uint4* __restrict__ Bp,
+                                                                   const float* __restrict__ bias, int M, int N, int BN,
+                                                                   int ntn, int nks, int act, int passes, Rank2 r2,
+                                                                   const __grid_constant__ CUtensorMap tm_c) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int a_half = KC * TM * 16;                      // bytes of A_hi (== A_lo) per K stage
+  const int a_tile = nks * 2 * a_half;                  // one A tile: nks stages of { hi, lo }
+  const int b_half = KC * BN * 16;
+  const int b_blk = 2 * b_half;                         // one packed (n-tile, K stage) block
+  const int b_bytes = ntn * nks * b_blk;
+  uint8_t* boxes = smem;                                // two [128 x 32] FP32 output boxes (1024-byte aligned)
+  uint8_t* a_s = smem + 2 * TM * 128;
+  uint8_t* b_s = a_s + PN_A * a_tile;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_s + b_bytes);
+  uint64_t* a_empty = a_full + PN_A;
+  uint64_t* acc_full = a_empty + PN_A;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* b_full = acc_empty + 2;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mtiles = (M + TM - 1) / TM;
+  const int my_tiles = ((int)blockIdx.x < mtiles) ? (mtiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < PN_A; ++s) {
+      mbar_init(&a_full[s], 4);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<512>(tslot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  if (warp < 4) {
+    // ===================== A producers: thread <-> row; the rows of the next tile are in registers while this one is written
+    DenseA8 A = A_;
+    float v[2][KC][8];
+    auto load = [&](int i) {
+      A.init(((int)blockIdx.x + i * (int)gridDim.x) * TM + tid);
+      A.load_stage(0, v[0]);
+      if (nks > 1) A.load_stage(1, v[1]);
+    };
+    if (my_tiles > 0) load(0);
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i % PN_A;
+      mbar_wait(&a_empty[buf], ((i / PN_A) & 1) ^ 1);
+      uint8_t* sa = a_s + (size_t)buf * a_tile;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks < nks) {
+#pragma unroll
+          for (int c = 0; c < KC; ++c) {
+            const Split8 sp = split8(v[ks][c]);
+            *reinterpret_cast<uint4*>(sa + ks * 2 * a_half + c * TM * 16 + tid * 16) = sp.hi;
+            *reinterpret_cast<uint4*>(sa + ks * 2 * a_half + a_half + c * TM * 16 + tid * 16) = sp.lo;
+          }
+        }
+      }
+      if (i + 1 < my_tiles) load(i + 1);                 // in flight while the other roles work on tile i
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[buf]);
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer (whole warp, elected lane, uniform descriptors)
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = idesc_bf16(TM, BN);
+    const uint32_t lbo_a = TM * 16, lbo_b = BN * 16;
+    const uint64_t d_a = smem_desc(smem_u32(a_s), lbo_a, 128), d_b = smem_desc(smem_u32(b_s), lbo_b, 128);
+    const int ksteps = (A_.K + 15) / 16;                 // 16-wide K steps that hold data
+    const bool p3 = passes == 3;
+    mbar_wait(b_full, 0);
+    uint32_t use = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i % PN_A;
+      mbar_wait(&a_full[buf], (i / PN_A) & 1);
+      tc_fence_after();
+      for (int jn = 0; jn < ntn; ++jn, ++use) {
+        const int slot = use & 1;
+        mbar_wait(&acc_empty[slot], ((use >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tm + slot * 256;
+        const uint64_t da = desc_adv(d_a, buf * (uint32_t)a_tile), db = desc_adv(d_b, (uint32_t)(jn * nks) * (uint32_t)b_blk);
+        if (elect_one()) {
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint32_t ao = (kk >> 1) * 2 * a_half + (kk & 1) * 2 * lbo_a;
+            const uint32_t bo = (kk >> 1) * b_blk + (kk & 1) * 2 * lbo_b;
+            mma_bf16(d, desc_adv(da, ao), desc_adv(db, bo), idesc, kk > 0);
+            if (p3) {
+              mma_bf16(d, desc_adv(da, ao + a_half), desc_adv(db, bo), idesc, 1);
+              mma_bf16(d, desc_adv(da, ao), desc_adv(db, bo + b_half), idesc, 1);
+            }
+          }
+          mma_commit(&acc_full[slot]);
+          if (jn == ntn - 1) mma_commit(&a_empty[buf]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== weight loader: the whole packed image, once
+    if (lane == 0) {
+      mbar_arrive_expect_tx(b_full, (uint32_t)b_bytes);
+      for (int o = 0; o < b_bytes; o += b_blk)
+        bulk_g2s(b_s + o, reinterpret_cast<const uint8_t*>(Bp) + o, (uint32_t)b_blk, b_full);
+    }
+  } else {
+    // ===================== epilogue warps 6-9: TMEM lanes 32*(warp%4) .. +31 == rows m0 + et
+    const int q = warp & 3, et = q * 32 + lane;          // row of the tile; also this thread's index among the 128
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const bool leader = warp == 6 && lane == 0;
+    const uint32_t obox = smem_u32(boxes);
+    uint32_t use = 0;
+    int ci = 0;                                          // boxes written so far (two alternate)
+    for (int i = 0; i < my_tiles; ++i) {
+      const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TM;
+      const int m = m0 + et;
+      float s0 = 0.f, s1 = 0.f;
+      const float* pr = nullptr;
+      if (r2.P && m < M) {
+        s0 = __ldg(r2.s + 2 * (size_t)m);
+        s1 = __ldg(r2.s + 2 * (size_t)m + 1);
+        pr = r2.P + (size_t)(m / r2.div) * 2 * N;
+      }
+      for (int jn = 0; jn < ntn; ++jn, ++use) {
+        const int slot = use & 1;
+        const int n0 = jn * BN;
+        mbar_wait(&acc_full[slot], (use >> 1) & 1);
+        tc_fence_after();
+        for (int c0 = 0; c0 < BN && n0 + c0 < N; c0 += 32, ++ci) {
+          float acc[32];
+          tmem_ld32(trow + slot * 256 + c0, acc);
+          tmem_ld_wait();
+          if (c0 + 32 >= BN || n0 + c0 + 32 >= N) {      // last chunk of the accumulator: the MMAs may refill it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[slot]);
+          }
+          chunk_epilogue(acc, bias ? bias + n0 + c0 : nullptr, pr ? pr + n0 + c0 : nullptr, N, s0, s1, act);
+          const uint32_t box = obox + (ci & 1) * (TM * 128);
+          if (ci >= 2) {                                 // the store that last read this box has finished reading it
+            if (leader) tma_store_wait_read1();
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+          }
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16)
+            sts128(swz128_abs(box, et, c16), make_float4(acc[4 * c16], acc[4 * c16 + 1], acc[4 * c16 + 2], acc[4 * c16 + 3]));
+          fence_proxy_async();
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (leader) {
+            tma_store_2d(&tm_c, boxes + (ci & 1) * (TM * 128), n0 + c0, m0);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+size_t persist_smem(const Plan& p) {
+  return 2 * (size_t)TM * 128 + (size_t)PN_A * p.nks * 2 * KC * TM * 16 + p.pack_bytes + (2 * PN_A + 5) * 8 + 16;
+}
+// Takes the problem when it is the short-K / huge-M kind this kernel is for; *rc receives the launch status.
+bool run_tc_persist(const DenseA8& A, const void* packed, const float* bias, float* C, int ldc, int M, int N, int K,
+                    int act, cudaStream_t st, const Rank2& r2, int* rc) {
+  static const bool off = [] {
+    const char* e = getenv("DESIRE_GEMM_NO_PERSIST");
+    return e && e[0] == '1';
+  }();
+  const Plan p = make_plan(N, K, M);
+  if (off || K > 2 * BK || K % 8 != 0 || !A.vec || N % 32 != 0 || p.BN % 32 != 0 || p.BN > 256 || M < 148 * 4 * TM ||
+      ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(C) & 15) != 0 || (reinterpret_cast<uintptr_t>(bias) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(r2.P) & 15) != 0 || persist_smem(p) > 227 * 1024)
+    return false;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (make_tmap_rows32(&tm, C, M, ldc) != DESIRE_OK) return false;
+  const size_t smem = persist_smem(p);
+  auto launch = [&]() -> int {
+    DESIRE_ENSURE_SMEM(gemm_tc_persist_kernel, smem);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int mtiles = (M + TM - 1) / TM;
+    const unsigned grid = (unsigned)std::min(sms, mtiles);
+    DESIRE_LAUNCH(st, (gemm_tc_persist_kernel<<<grid, PNTHR, smem, st>>>(A, (const uint4*)packed, bias, M, N, p.BN, p.ntn, p.nks,
+                                                                         act, g_gemm_mode == 1 ? 1 : 3, r2, tm)));
+    return DESIRE_OK;
+  };
+  *rc = launch();
+  return true;
+}
+
 template <class ALoad>
 int run_tc(const ALoad& A, const void* packed, const float* bias, float* C, int ldc, int M, int N, int K, int act,
            bool accumulate, cudaStream_t st, Rank2 r2 = Rank2()) {
@@ -633,6 +908,15 @@ bool gemm_tc_eligible(int M, int N, int K, const void* pack_ws, size_t pack_byte
 int gemm_tc(const float* A, int lda, const float* W, int ldw, bool trans_b, const float* bias, float* C, int ldc, int M,
             int N, int K, int act, bool accumulate, void* pack_ws, cudaStream_t st) {
   DenseA8 a{A, lda, M, K, (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0), nullptr};
+  if (!accumulate) {                                             // short-K / huge-M: the persistent, weight-stationary kernel
+    const Plan p = make_plan(N, K);
+    if (K <= 2 * BK && M >= 148 * 4 * TM) {
+      DESIRE_TRY(pack_for_plan(p, W, ldw, trans_b, K, N, pack_ws, st));
+      int rc = DESIRE_OK;
+      if (run_tc_persist(a, pack_ws, bias, C, ldc, M, N, K, act, st, Rank2(), &rc)) return rc;
+      return run_tc(a, pack_ws, bias, C, ldc, M, N, K, act, false, st);
+    }
+  }
   return launch_tc(a, W, ldw, trans_b, bias, C, ldc, M, N, K, act, accumulate, pack_ws, st);
 }
 
@@ -648,6 +932,8 @@ int gemm_packed(const float* A, int lda, const PackedW& w, const float* bias, fl
                 bool accumulate, cudaStream_t st) {
   if (w.packed && g_gemm_mode != 0 && M >= 64 && (M + TM - 1) / TM <= 65535) {
     DenseA8 a{A, lda, M, w.K, (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0), nullptr};
+    int rc = DESIRE_OK;
+    if (!accumulate && run_tc_persist(a, w.packed, bias, C, ldc, M, w.N, w.K, act, st, Rank2(), &rc)) return rc;
     return run_tc(a, w.packed, bias, C, ldc, M, w.N, w.K, act, accumulate, st);
   }
   return sgemm(A, lda, w.W, w.ldw, w.trans, bias, C, ldc, M, w.N, w.K, act, accumulate, st);
@@ -656,9 +942,11 @@ int gemm_packed(const float* A, int lda, const PackedW& w, const float* bias, fl
 // C = A @ W + bias + s[:,0] * P[g,0,:] + s[:,1] * P[g,1,:] on the tensor-core path (W packed); false = not eligible
 bool gemm_packed_r2(const float* A, int lda, const PackedW& w, const float* bias, float* C, int ldc, int M, int act,
                     const Rank2& r2, cudaStream_t st, int* rc) {
-  const bool ok = w.packed && g_gemm_mode != 0 && M >= 64 && (M + TM - 1) / TM <= 65535 && r2.P && r2.s && r2.div > 0;
+  const bool ok = w.packed && g_gemm_mode != 0 && M >= 64 && (M + TM - 1) / TM <= 65535 && r2.P && r2.s && r2.div > 0 &&
+                  (reinterpret_cast<uintptr_t>(r2.P) & 15) == 0 && w.N % 4 == 0;
   if (!ok) return false;
   DenseA8 a{A, lda, M, w.K, (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0), nullptr};
+  if (run_tc_persist(a, w.packed, bias, C, ldc, M, w.N, w.K, act, st, r2, rc)) return true;
   *rc = run_tc(a, w.packed, bias, C, ldc, M, w.N, w.K, act, false, st, r2);
   return true;
 }

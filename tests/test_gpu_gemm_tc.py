@@ -23,6 +23,10 @@ SHAPES = [  # M, N, K, trans_w, act, accumulate, bias
     (1536, 384, 248, 0, 0, 0, 1),        # decoder-2 input projection, K tail
     (640, 24, 128, 0, 0, 1, 1),          # regression refine: accumulate into C, N=24
     (513, 2048, 128, 1, 2, 0, 1),        # deconv1 shape + ELU
+    # short K, huge M: the persistent weight-stationary kernel (ragged last tile; one and two K stages; N = 3H of both sizes)
+    (100000 + 77, 384, 48, 0, 0, 0, 1),
+    (90000, 512, 64, 0, 1, 0, 1),
+    (76000, 96, 24, 1, 0, 0, 0),
 ]
 
 
