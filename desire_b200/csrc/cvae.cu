@@ -7,6 +7,7 @@
 // BN is the reference's batch-of-one statistics: per row and channel over the H*W positions
 // (DESIGN.md D5), two-pass variance, eps = 1e-3.
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace desire {
 namespace {
@@ -167,11 +168,17 @@ __global__ void __launch_bounds__(256) colbn_act_v4_kernel(const float* __restri
   for (int e = tid; e < Pout * C4; e += nthr) {
     const int oc = (e % C4) * 4;
     const float4 x = reinterpret_cast<const float4*>(tile)[e];
+    // all reads first, branch-free activation (tc.cuh: act_fast): a data-dependent branch per element (act_apply's ELU)
+    // keeps the next element's loads behind it
+    const float g0 = __ldg(gamma + oc), g1 = __ldg(gamma + oc + 1), g2 = __ldg(gamma + oc + 2), g3 = __ldg(gamma + oc + 3);
+    const float b0 = __ldg(beta + oc), b1 = __ldg(beta + oc + 1), b2 = __ldg(beta + oc + 2), b3 = __ldg(beta + oc + 3);
+    const float m0 = stat[oc], m1 = stat[oc + 1], m2 = stat[oc + 2], m3 = stat[oc + 3];
+    const float r0 = stat[Cout + oc], r1 = stat[Cout + oc + 1], r2 = stat[Cout + oc + 2], r3 = stat[Cout + oc + 3];
     float4 y;
-    y.x = act_apply(__ldg(gamma + oc) * ((x.x - stat[oc]) * stat[Cout + oc]) + __ldg(beta + oc), act);
-    y.y = act_apply(__ldg(gamma + oc + 1) * ((x.y - stat[oc + 1]) * stat[Cout + oc + 1]) + __ldg(beta + oc + 1), act);
-    y.z = act_apply(__ldg(gamma + oc + 2) * ((x.z - stat[oc + 2]) * stat[Cout + oc + 2]) + __ldg(beta + oc + 2), act);
-    y.w = act_apply(__ldg(gamma + oc + 3) * ((x.w - stat[oc + 3]) * stat[Cout + oc + 3]) + __ldg(beta + oc + 3), act);
+    y.x = tc::act_fast(g0 * ((x.x - m0) * r0) + b0, act);
+    y.y = tc::act_fast(g1 * ((x.y - m1) * r1) + b1, act);
+    y.z = tc::act_fast(g2 * ((x.z - m2) * r2) + b2, act);
+    y.w = tc::act_fast(g3 * ((x.w - m3) * r3) + b3, act);
     outr[e] = y;
   }
 }

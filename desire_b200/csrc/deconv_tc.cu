@@ -320,20 +320,36 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + cg * CG) + qd);
         const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + cg * CG) + qd);
         const float4 bb4 = __ldg(reinterpret_cast<const float4*>(a.bias + cg * CG) + qd);
-        for (int e4 = tid; e4 < ntile_el / 4; e4 += 256) {
-          const int pq = e4 >> 3;
-          const int q = pq % Pout, s2 = pq / Pout;
-          const long smp = samp0 + s2;
-          if (smp >= a.R) continue;
-          const int oy = q / HOUT, ox = q - oy * HOUT;
-          const float4 x = *reinterpret_cast<const float4*>(outt + ((size_t)s2 * Pout + q) * CG + ((qd + swz(oy, ox, sh)) & 7) * 4);
-          const float4 m4 = stat4[s2 * 8 + qd], r4 = stat4[units + s2 * 8 + qd];
-          float4 y;
-          y.x = act_apply(g4.x * ((x.x + bb4.x - m4.x) * r4.x) + be4.x, a.act);
-          y.y = act_apply(g4.y * ((x.y + bb4.y - m4.y) * r4.y) + be4.y, a.act);
-          y.z = act_apply(g4.z * ((x.z + bb4.z - m4.z) * r4.z) + be4.z, a.act);
-          y.w = act_apply(g4.w * ((x.w + bb4.w - m4.w) * r4.w) + be4.w, a.act);
-          *reinterpret_cast<float4*>(a.Y + ((size_t)smp * Pout + q) * a.Cout + cg * CG + qd * 4) = y;
+        // four quads per trip: their tile / statistics reads first, then the branch-free normalise + activation (tc.cuh:
+        // act_fast — with act_apply's data-dependent ELU branch and expf every element waited for the previous one: this
+        // phase was a third of the kernel), then the 16-byte stores
+        constexpr int NIT = ntile_el / 4 / 256;
+        static_assert(NIT % 4 == 0, "store loop batches");
+        const int act = a.act;
+#pragma unroll 1
+        for (int it0 = 0; it0 < NIT; it0 += 4) {
+          float4 x[4], m4[4], r4[4];
+          int qq[4], ss[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int pq = (tid + (it0 + u) * 256) >> 3;
+            qq[u] = pq % Pout;
+            ss[u] = pq / Pout;
+            const int oy = qq[u] / HOUT, ox = qq[u] - oy * HOUT;
+            x[u] = *reinterpret_cast<const float4*>(outt + ((size_t)ss[u] * Pout + qq[u]) * CG + ((qd + swz(oy, ox, sh)) & 7) * 4);
+            m4[u] = stat4[ss[u] * 8 + qd];
+            r4[u] = stat4[units + ss[u] * 8 + qd];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float4 y;
+            y.x = act_fast(g4.x * ((x[u].x + bb4.x - m4[u].x) * r4[u].x) + be4.x, act);
+            y.y = act_fast(g4.y * ((x[u].y + bb4.y - m4[u].y) * r4[u].y) + be4.y, act);
+            y.z = act_fast(g4.z * ((x[u].z + bb4.z - m4[u].z) * r4[u].z) + be4.z, act);
+            y.w = act_fast(g4.w * ((x[u].w + bb4.w - m4[u].w) * r4[u].w) + be4.w, act);
+            if (samp0 + ss[u] < a.R)
+              *reinterpret_cast<float4*>(a.Y + ((size_t)(samp0 + ss[u]) * Pout + qq[u]) * a.Cout + cg * CG + qd * 4) = y;
+          }
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");

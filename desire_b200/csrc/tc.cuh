@@ -285,6 +285,15 @@ __device__ __forceinline__ float rcpa(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// branch-free activation for store loops (a data-dependent branch per element keeps the next element's loads behind
+// it): ELU and sigmoid through ex2.approx (2 ulp), the others exact
+__device__ __forceinline__ float act_fast(float x, int act) {
+  const float e = ex2a(1.4426950408889634f * (act == 3 /*DESIRE_ACT_SIGMOID*/ ? -x : fminf(x, 0.f)));
+  const float elu = x > 0.f ? x : e - 1.f;
+  const float sig = rcpa(1.f + e);
+  const float relu = fmaxf(x, 0.f);
+  return act == 2 /*ELU*/ ? elu : (act == 3 ? sig : (act == 1 /*RELU*/ ? relu : x));
+}
 __device__ __forceinline__ float sigmoid_a(float x) { return rcpa(1.f + ex2a(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_a(float x) {     // 1 - 2/(1+e^{2x}); saturates to +-1 for large |x|
   return fmaf(-2.f, rcpa(1.f + ex2a(2.8853900817779268f * x)), 1.f);

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r_tests.log 2>&1; echo "tests rc $?"; tail -3 gpurun_out/r_tests.log
-python tools/bench_gemm.py | cut -c1-110; DESIRE_GEMM_NO_PERSIST=1 python tools/bench_gemm.py | cut -c1-110
 timeout 400 python bench.py --steps 20 --warmup 5 --breakdown gpurun_out/q_breakdown.json > gpurun_out/q_bench.json 2> gpurun_out/q_bench.err; echo "bench rc=$?"
 python - <<'PY'
 import json
