@@ -495,13 +495,16 @@ __global__ void __launch_bounds__(320) deconv1c_tc_kernel(Dc1Args a) {
     float v[32];
     tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + tile * 32, v);
     tmem_ld_wait();
-#pragma unroll
-    for (int t = 0; t < KS * KS; ++t) {
-      const int ky = t / KS, kx = t % KS;
+    // taps in conflict-free rounds (TapOrder: taps of different (ky, kx) parity never meet in a pixel): 9 lockstep
+    // barriers instead of 25, still deterministic and race-free
+    static_for<KS * KS>([&](auto sc) {
+      constexpr int slot = decltype(sc)::value;
+      constexpr int t = TapPlan<KS, 2, 8>::ORD.tap[slot];
+      constexpr int ky = t / KS, kx = t % KS;
       const int oy = iy * 2 + ky - PAD, ox = ix * 2 + kx - PAD;
       if (oy >= 0 && oy < HOUT && ox >= 0 && ox < HOUT) out_s[oy * HOUT + ox] += v[t];
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // taps in lockstep: deterministic, race-free
-    }
+      if constexpr (TapPlan<KS, 2, 8>::ORD.last[slot]) asm volatile("bar.sync 1, 256;" ::: "memory");
+    });
     // ---- bias + BN over the 1024 pixels + activation
     const float b0 = __ldg(a.bias);
     float vals[4], s = 0.f;
@@ -527,12 +530,14 @@ __global__ void __launch_bounds__(320) deconv1c_tc_kernel(Dc1Args a) {
     const float rstd = 1.f / sqrtf(block_sum(q) / (float)(HOUT * HOUT) + 1e-3f);
     const float g = __ldg(a.gamma), be = __ldg(a.beta);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a.Y[r * (size_t)(HOUT * HOUT) + tid + 256 * i] = act_apply(g * ((vals[i] - mean) * rstd) + be, a.act);
+    for (int i = 0; i < 4; ++i) a.Y[r * (size_t)(HOUT * HOUT) + tid + 256 * i] = act_fast(g * ((vals[i] - mean) * rstd) + be, a.act);
   } else if (warp == 8) {
-    if (lane == 0) {
-      mbar_wait(b_full, 0);
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
+    mbar_wait(b_full, 0);
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    if (elect_one()) {
+      const uint32_t tmem = tmem_u;
       const uint32_t idesc = idesc_bf16(128, 32);
       const uint32_t sb = smem_u32(B_s);
 #pragma unroll
