@@ -292,9 +292,16 @@ int gru_seq_tc3(const GruSeqArgs& a, void* pack_ws, cudaStream_t st);
 size_t deconv_tc_pack_bytes(int Cin, int Cout, int ks);
 bool deconv_tc_eligible(int R, int Hin, int Hout, int Cin, int Cout, int ks, int stride, const void* pack_ws,
                         size_t pack_bytes);
+// fuse4 (optional, only for the 8x8 -> 16x16 stride-2 layer with Cout == 32): the decoder's last layer (16x16x32 -> 32x32x1,
+// k5 s2 SAME, BN + activation) runs on the normalised tile while it is still in shared memory; Y is then not written.
+struct DeconvFuse4 {
+  const float *W, *bias, *gamma, *beta;   // W [5,5,1,32]
+  int act;
+  float* Y;                               // [R, 1024]
+};
 int deconv_tc(const float* X, int R, int Hin, int Hout, int Cin, int Cout, int ks, int stride, int pad, const float* W,
               const float* bias, const float* gamma, const float* beta, int act, float* Y, void* pack_ws,
-              cudaStream_t st);
+              cudaStream_t st, const DeconvFuse4* fuse4 = nullptr);
 
 bool deconv1c_tc_eligible();
 int deconv1c_tc(const float* X, int R, const float* W, const float* bias, const float* gamma, const float* beta, int act,

@@ -6,6 +6,8 @@
 // algorithmic MACs (no stride-2 zero taps), and the col2im kernel gathers each col element once.
 // BN is the reference's batch-of-one statistics: per row and channel over the H*W positions
 // (DESIGN.md D5), two-pass variance, eps = 1e-3.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -466,10 +468,18 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
       DESIRE_TRY(colbn_act(col, rc, 4, 8, 5, 1, 0, 64, w->d2.b, w->d2.gamma, w->d2.beta, DESIRE_ACT_ELU, a2, st));
     }
     // deconv5/2 SAME 8x8x64 -> 16x16x32 (full 19x19, keep [1,17))
+    static const bool no_fuse4 = [] {                          // DESIRE_NO_FUSE4=1: last layer as its own kernel (A/B timing)
+      const char* e = getenv("DESIRE_NO_FUSE4");
+      return e && e[0] == '1';
+    }();
+    bool fused4 = false;
     if (deconv_tc_eligible(rc, 8, 16, 64, 32, 5, 2, pw.p, pw.bytes)) {
       ProfScope ps_(DESIRE_PROF_DECONV3, st);
+      // the last layer (16x16x32 -> 32x32x1 + BN + sigmoid) rides on this kernel's normalised tile: a3 is never written
+      DeconvFuse4 f4{w->d4.w, w->d4.b, w->d4.gamma, w->d4.beta, DESIRE_ACT_SIGMOID, xr + (size_t)r0 * 1024};
+      fused4 = !no_fuse4 && deconv1c_tc_eligible() && pw.bytes >= align_up(deconv_tc_pack_bytes(64, 32, 5)) + 4096;
       DESIRE_TRY(deconv_tc(a2, rc, 8, 16, 64, 32, 5, 2, 1, w->d3.w, w->d3.b, w->d3.gamma, w->d3.beta, DESIRE_ACT_ELU, a3,
-                           pw.p, st));
+                           pw.p, st, fused4 ? &f4 : nullptr));
     } else {
       {
         ProfScope ps_(DESIRE_PROF_DECONV3, st);
@@ -480,7 +490,7 @@ extern "C" int desire_cvae_decode_fwd(const float* z, int R, int Z, const desire
     }
     // deconv5/2 SAME 16x16x32 -> 32x32x1, BN + sigmoid: tiny-N tcgen05 kernel with in-kernel col2im + BN
     // (CUDA-core direct kernel when tensor cores are off)
-    {
+    if (!fused4) {
       ProfScope ps_(DESIRE_PROF_COL2IM, st);
       if (deconv1c_tc_eligible()) {
         DESIRE_TRY(deconv1c_tc(a3, rc, w->d4.w, w->d4.b, w->d4.gamma, w->d4.beta, DESIRE_ACT_SIGMOID,

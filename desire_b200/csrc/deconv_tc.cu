@@ -38,10 +38,17 @@ struct DcArgs {
   int act;
   float* Y;
   int passes, nstg;
+  // Fused last decoder layer (model/model.py:468, 16x16x32 -> 32x32x1 k5 s2 SAME + BN + sigmoid) on the normalised tile of
+  // THIS layer while it is still in shared memory (only for the <8, 16, 2, 5> geometry with Cout == 32): Y4 != nullptr
+  // switches it on; then Y is not written at all.
+  const uint8_t* w4pack;   // { hi [4][32][8 bf16], lo } : [N = 25 taps (32), K = 32]
+  const float *b4, *g4, *be4;
+  int act4;
+  float* Y4;               // [R, 1024]
 };
 
 struct DcLayout {
-  size_t a_hi, a_lo, ring, out, red, stat, bars, total;
+  size_t a_hi, a_lo, ring, out, red, stat, bars, w4, total;
 };
 __host__ __device__ inline DcLayout dc_layout(int Cin, int nstg, int spt) {
   DcLayout L;
@@ -53,7 +60,9 @@ __host__ __device__ inline DcLayout dc_layout(int Cin, int nstg, int spt) {
   L.out = off; off += 64 * 1024;
   L.red = off; off += 256 * 16;     // float4 partial sums of the vectorised BN phase
   L.stat = off; off += (size_t)2 * spt * CG * 4;
-  L.bars = off; off += (2 * 4 + 4 + 1) * 8 + 16;
+  L.bars = off; off += (2 * 4 + 4 + 1 + 3) * 8 + 16;
+  off = (off + 127) / 128 * 128;
+  L.w4 = off; off += 4096;                                       // fused last layer: its packed weights
   L.total = off;
   return L;
 }
@@ -158,7 +167,11 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
   uint64_t* acc_full = empty + 4;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* a_ready = acc_empty + 2;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(a_ready + 1);
+  uint64_t* w4_full = a_ready + 1;      // fused last layer: weights landed / A operand written / accumulators complete
+  uint64_t* a4_ready = w4_full + 1;
+  uint64_t* acc4_full = a4_ready + 1;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(acc4_full + 1);
+  const bool fuse4 = a.Y4 != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int ntaps = KS * KS, nnt = (ntaps + TPT - 1) / TPT;
@@ -176,6 +189,9 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
       mbar_init(&acc_empty[s], 8);
     }
     mbar_init(a_ready, 8);
+    mbar_init(w4_full, 1);
+    mbar_init(a4_ready, 8);
+    mbar_init(acc4_full, 1);
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc_dyn(tslot, 512);
@@ -320,6 +336,102 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + cg * CG) + qd);
         const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + cg * CG) + qd);
         const float4 bb4 = __ldg(reinterpret_cast<const float4*>(a.bias + cg * CG) + qd);
+        if (fuse4) {
+          // normalised + activated quads go straight into the A operand of the last layer: M-tile = 128 positions of one
+          // sample, K = the 32 channels; byte(row, k) = (k/8)*2048 + row*16 + (k%8)*2 (hi image, then lo image)
+          uint8_t* a4 = ring;                                    // 4 M-tiles x 16 KB: the weight ring is idle by now
+#pragma unroll 1
+          for (int it0 = 0; it0 < ntile_el / 4 / 256; it0 += 4) {
+            float4 x[4], m4[4], r4[4];
+            int pqs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int pq = (tid + (it0 + u) * 256) >> 3;
+              pqs[u] = pq;
+              const int q = pq % Pout, s2 = pq / Pout;
+              const int oy = q / HOUT, ox = q - oy * HOUT;
+              x[u] = *reinterpret_cast<const float4*>(outt + ((size_t)s2 * Pout + q) * CG + ((qd + swz(oy, ox, sh)) & 7) * 4);
+              m4[u] = stat4[s2 * 8 + qd];
+              r4[u] = stat4[units + s2 * 8 + qd];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float y0 = act_fast(g4.x * ((x[u].x + bb4.x - m4[u].x) * r4[u].x) + be4.x, a.act);
+              const float y1 = act_fast(g4.y * ((x[u].y + bb4.y - m4[u].y) * r4[u].y) + be4.y, a.act);
+              const float y2 = act_fast(g4.z * ((x[u].z + bb4.z - m4[u].z) * r4[u].z) + be4.z, a.act);
+              const float y3 = act_fast(g4.w * ((x[u].w + bb4.w - m4[u].w) * r4[u].w) + be4.w, a.act);
+              uint2 hi, lo;
+              split2(y0, y1, hi.x, lo.x);
+              split2(y2, y3, hi.y, lo.y);
+              const int mt = pqs[u] >> 7, row = pqs[u] & 127;
+              uint8_t* dst = a4 + (size_t)mt * 16384 + (qd >> 1) * 2048 + row * 16 + (qd & 1) * 8;
+              *reinterpret_cast<uint2*>(dst) = hi;
+              *reinterpret_cast<uint2*>(dst + 8192) = lo;
+            }
+          }
+          // the 32x32 output tiles of the two samples live where this layer's A operand was
+          float* out2 = reinterpret_cast<float*>(A_hi);
+          for (int e = tid; e < 2 * 1024 / 4; e += 256) reinterpret_cast<float4*>(out2)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          fence_proxy_async();
+          tc_fence_before();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (lane == 0) mbar_arrive(a4_ready);
+          // ---- scatter: warp w reads TMEM lanes 32*(w%4).. of the two M-tiles of sample w/4
+          const int q4 = warp & 3, s2 = warp >> 2;
+          mbar_wait(acc4_full, 0);
+          tc_fence_after();
+          float v0[32], v1[32];
+          tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (2 * s2) * 32, v0);
+          tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (2 * s2 + 1) * 32, v1);
+          tmem_ld_wait();
+          {
+            const int p0 = q4 * 32 + lane;                       // position 0..127 of the sample; the second M-tile: +128
+            const int iy0 = p0 >> 4, ix0 = p0 & 15, iy1 = iy0 + 8;
+            float* o2 = out2 + s2 * 1024;
+            static_for<25>([&](auto sc) {
+              constexpr int slot = decltype(sc)::value;
+              constexpr int t = TapPlan<5, 2, 8>::ORD.tap[slot];
+              constexpr int ky = t / 5, kx = t % 5;
+              const int ox = ix0 * 2 + kx - 1;
+              const int oya = iy0 * 2 + ky - 1, oyb = iy1 * 2 + ky - 1;
+              if (ox >= 0 && ox < 32) {
+                if (oya >= 0 && oya < 32) o2[oya * 32 + ox] += v0[t];
+                if (oyb >= 0 && oyb < 32) o2[oyb * 32 + ox] += v1[t];
+              }
+              if constexpr (TapPlan<5, 2, 8>::ORD.last[slot]) asm volatile("bar.sync 1, 256;" ::: "memory");
+            });
+          }
+          // ---- bias + BN over the 1024 pixels of each sample + activation: 128 threads per sample, 8 pixels each
+          {
+            const int tl = tid & 127;
+            const float* o2 = out2 + s2 * 1024;
+            const float b0 = __ldg(a.b4);
+            float vals[8], ssum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              vals[i] = o2[tl + 128 * i] + b0;
+              ssum += vals[i];
+            }
+            auto half_sum = [&](float xx) {                      // sum over the four warps of this sample
+              xx = warp_sum(xx);
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (lane == 0) red[warp] = xx;
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              return red[4 * s2] + red[4 * s2 + 1] + red[4 * s2 + 2] + red[4 * s2 + 3];
+            };
+            const float mean = half_sum(ssum) * (1.f / 1024.f);
+            float qs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qs += (vals[i] - mean) * (vals[i] - mean);
+            const float rstd = 1.f / sqrtf(half_sum(qs) * (1.f / 1024.f) + 1e-3f);
+            const float g = __ldg(a.g4), be = __ldg(a.be4);
+            const long smp = samp0 + s2;
+            if (smp < a.R) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a.Y4[(size_t)smp * 1024 + tl + 128 * i] = act_fast(g * ((vals[i] - mean) * rstd) + be, a.act4);
+            }
+          }
+        } else {
         // four quads per trip: their tile / statistics reads first, then the branch-free normalise + activation (tc.cuh:
         // act_fast — with act_apply's data-dependent ELU branch and expf every element waited for the previous one: this
         // phase was a third of the kernel), then the 16-byte stores
@@ -350,6 +462,7 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
             if (samp0 + ss[u] < a.R)
               *reinterpret_cast<float4*>(a.Y + ((size_t)(samp0 + ss[u]) * Pout + qq[u]) * a.Cout + cg * CG + qd * 4) = y;
           }
+        }
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -399,10 +512,39 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
         }
       }
       __syncwarp();
+      if (fuse4) {
+        // last layer: four M-tiles (two samples x two halves of the 256 positions) x [K = 32] x [N = 32 taps]
+        mbar_wait(w4_full, 0);
+        mbar_wait(a4_ready, 0);
+        tc_fence_after();
+        const uint64_t d_a4 = smem_desc(ring_s, 2048, 128), d_b4 = smem_desc(smem_u32(smem + L.w4), 512, 128);
+        constexpr uint32_t idesc4 = idesc_bf16(128, 32);
+        if (elect_one()) {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t ahi = desc_adv(d_a4, mt * 16384 + j * 2 * 2048), alo = desc_adv(d_a4, mt * 16384 + 8192 + j * 2 * 2048);
+              const uint64_t bhi = desc_adv(d_b4, j * 2 * 512), blo = desc_adv(d_b4, 4 * 512 + j * 2 * 512);
+              mma_bf16(tm + mt * 32, ahi, bhi, idesc4, j > 0 ? 1u : 0u);
+              if (p3) {
+                mma_bf16(tm + mt * 32, alo, bhi, idesc4, 1);
+                mma_bf16(tm + mt * 32, ahi, blo, idesc4, 1);
+              }
+            }
+          }
+          mma_commit(acc4_full);
+        }
+        __syncwarp();
+      }
     }
   } else {
     // ===================== weight streamer
     if (lane == 0) {
+      if (fuse4) {
+        mbar_arrive_expect_tx(w4_full, 4096);
+        bulk_g2s(smem + L.w4, a.w4pack, 4096, w4_full);
+      }
       uint32_t it = 0;
       const uint8_t* src = a.wpack;
       for (int cg = 0; cg < ncg; ++cg) {
@@ -588,7 +730,7 @@ bool deconv_tc_eligible(int R, int Hin, int Hout, int Cin, int Cout, int ks, int
 
 int deconv_tc(const float* X, int R, int Hin, int Hout, int Cin, int Cout, int ks, int stride, int pad, const float* W,
               const float* bias, const float* gamma, const float* beta, int act, float* Y, void* pack_ws,
-              cudaStream_t st) {
+              cudaStream_t st, const DeconvFuse4* fuse4) {
   const int nks = Cin / 32, ncg = Cout / CG, ntaps = ks * ks;
   long items = 0;
   for (int nt = 0; nt * TPT < ntaps; ++nt) items += (long)nks * 4 * std::min(TPT, ntaps - nt * TPT) * CG;
@@ -607,6 +749,14 @@ int deconv_tc(const float* X, int R, int Hin, int Hout, int Cin, int Cout, int k
   a.X = X; a.R = R; a.Hin = Hin; a.Hout = Hout; a.Cin = Cin; a.Cout = Cout; a.ks = ks; a.stride = stride; a.pad = pad;
   a.wpack = (const uint8_t*)pack_ws; a.bias = bias; a.gamma = gamma; a.beta = beta; a.act = act; a.Y = Y;
   a.passes = gemm_mode() == 1 ? 1 : 3;
+  if (fuse4) {
+    DESIRE_CHECK_ARG(Hin == 8 && Hout == 16 && stride == 2 && ks == 5 && Cout == 32 && fuse4->Y && fuse4->W,
+                     "deconv_tc: the fused last layer needs the 8x8 -> 16x16 stride-2 geometry with 32 channels");
+    // its packed weights ([N = 25 taps, K = 32], one 4 KB block) follow this layer's in the pack scratch
+    uint8_t* w4 = (uint8_t*)pack_ws + align_up(deconv_tc_pack_bytes(Cin, Cout, ks));
+    DESIRE_TRY(tc_pack_b(fuse4->W, 32, true, 32, 25, 32, w4, st));
+    a.w4pack = w4; a.b4 = fuse4->bias; a.g4 = fuse4->gamma; a.be4 = fuse4->beta; a.act4 = fuse4->act; a.Y4 = fuse4->Y;
+  }
   const int spt = TM / (Hin * Hin);
   a.nstg = Cin > 64 ? 2 : 3;
   const DcLayout L = dc_layout(Cin, a.nstg, spt);
