@@ -445,6 +445,8 @@ int social_pool_launch(const float* pos, long pos_stride, const float* h, int ld
       return DESIRE_OK;
     }
   }
+  if (social_pool_mma_eligible(h, ld_h, N, H, n_rad, n_ang, pooled))
+    return social_pool_mma(pos, pos_stride, h, ld_h, obs, Tp, B, N, K, H, n_rad, n_ang, r2_edges, dirs, pooled, st);
   if (H % 32 == 0 && G <= 64 && ld_h % 4 == 0 && N < 65535 && (long)B * K > 0) {
     // large scenes: row-block kernel, widest column slice whose staging fits shared memory
     for (int W = 128; W >= 32; W >>= 1) {

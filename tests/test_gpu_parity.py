@@ -77,7 +77,8 @@ def _ptr(t):
 @pytest.mark.parametrize("B,N,K,H,missing", [(2, 7, 3, 8, 2), (3, 60, 4, 128, 5), (1, 33, 2, 256, 0), (2, 100, 2, 48, 3),
                                              # large scenes -> row-block kernel (128-, 64- and 32-column slices)
                                              (1, 300, 2, 256, 5), (1, 400, 2, 192, 0), (1, 1024, 1, 128, 7),
-                                             (2, 256, 3, 256, 1)])
+                                             # 129..256 agents -> selection-matrix MMA (one and two row blocks, ragged N)
+                                             (2, 256, 3, 256, 1), (1, 129, 2, 64, 3), (2, 200, 2, 128, 0)])
 def test_social_pool_exact_bins(lib, B, N, K, H, missing):
     """Identical inputs -> identical bin membership (the binning arithmetic is shared exactly)."""
     from oracle import desire_oracle as O
@@ -102,7 +103,12 @@ def test_social_pool_exact_bins(lib, B, N, K, H, missing):
     torch.cuda.synchronize()
     got = out.cpu().numpy()
     assert np.array_equal(got != 0, ref != 0)           # same bins occupied for every row
-    assert rel_l2(got, ref) < 1e-6
+    # 129..256 agents with H % 64 == 0 pool on the tensor core (social_pm.cu): sums of the BF16 hi + lo split of h,
+    # |error| <= 2^-17 per element; everything else adds the FP32 values themselves
+    mma = 128 < N <= 256 and H % 64 == 0
+    e = rel_l2(got, ref)
+    print("social pool B%d N%d K%d H%d: rel-L2 %.2e (%s)" % (B, N, K, H, e, "tensor core" if mma else "SIMT"))
+    assert e < (1e-5 if mma else 1e-6)
 
 
 def test_scene_gather_matches_oracle(lib):
