@@ -238,6 +238,9 @@ bool social_pool_mma_eligible(const float* h, int ld_h, int N, int H, int n_rad,
 int social_pool_mma(const float* pos, long pos_stride, const float* h, int ld_h, const float* obs, int Tp, int B, int N,
                     int K, int H, int n_rad, int n_ang, const float* r2_edges, const float* dirs, float* pooled,
                     cudaStream_t st);
+// fused pooling + fc for 129..256 agents per scene, H in {128, 256} (social_fm.cu); social_fc_tc() takes it when eligible
+bool social_fc_fm_eligible(const SocialFcArgs& a);
+int social_fc_fm(const SocialFcArgs& a, cudaStream_t st);
 bool social_fc_tc_eligible(const SocialFcArgs& a);
 int social_fc_tc(const SocialFcArgs& a, cudaStream_t st);
 // second design (social_ts.cu): pooled A operand in tensor memory; social_fc_tc() takes it whenever it is eligible

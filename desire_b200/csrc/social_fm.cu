@@ -1,0 +1,406 @@
+// Fused log-polar social pooling + fc for scenes of 129..256 agents (BASELINE configs[2]: N = 256, H = 256), the large-scene
+// sibling of social_ts.cu:   fsp[r, :] = relu( pool(h)[r, :] @ sp_w + sp_b )   without ever writing the [R, G*H] tensor
+// (12 GB per launch at cfg3, written by the pooling kernel and read back by the fc GEMM).
+//
+// One CTA = 128 rows (agents i0 .. i0+127) of one (scene, sample) group.  The pooled K dimension (G*H) is walked in stages
+// of 64 values = (64-column pass p of the hidden dimension, bin g), pass-major so that the pass's h^T slice (64 columns x
+// 256 neighbours, BF16 hi + lo, 64 KB) stays in shared memory as the B operand of the pool MMAs:
+//   builders    S_g [128 x 256] (0/1, BF16) straight into tensor memory (tcgen05.st, thread = row, one byte compare per pair)
+//   pool MMA    P [128 x 64]  = S_g @ h[:, 64p..]           (A from tensor memory, two passes: hi, lo)
+//   finishers   P -> registers, * 1/count, BF16 hi/lo split -> A [128 x 64] in tensor memory
+//   fc MMA      D [128 x H] += A @ sp_w[g*H + 64p .. +64, :]  (A from tensor memory, 3xBF16, weights streamed by bulk TMA)
+// TMEM columns: D [0,H) | S [H,H+128) | P [H+128,H+192) | A [H+192,H+256): with H = 256 that is all 512, so S, P and A are
+// single-buffered; what overlaps is pool(s+1) with the conversion and the fc MMAs of stage s.
+//   warps 0-15  prologue (bins), h^T slices, builders, finishers, epilogue;  warp 16 fc issuer;  warp 17 weight loader;
+//   warp 18     pool issuer
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "social_common.cuh"
+#include "tc.cuh"
+
+namespace desire {
+namespace {
+
+using namespace tc;
+using namespace social;
+
+constexpr int TM = 128;
+constexpr int NPW = 16;
+constexpr int PT = NPW * 32;
+constexpr int NTHR = (NPW + 3) * 32;
+constexpr int NC = 64;           // pooled K values per stage = columns of h per pass
+constexpr int NJ = 256;          // neighbours (padded)
+constexpr int MAXNB = 8;
+
+struct Layout {
+  size_t ht, bins, bin_stride, pc, patch, px, py, exb, tab, bars, ring, slot_bytes, total;
+  int nb;
+};
+__host__ __device__ inline Layout make_layout(int H) {
+  Layout L;
+  size_t off = 0;
+  L.ht = off; off += 2 * (size_t)NC * NJ * 2;                    // h^T slice, K-major [NC x NJ] BF16: hi, lo
+  L.bin_stride = NJ + 16;
+  L.bins = off; off += TM * L.bin_stride;
+  L.pc = off; off += 4 * 4 * TM * 4;                             // partial counts [4 buffers][4 parts][128 rows]
+  L.patch = off; off += (size_t)NPW * 32 * 20 * 4;               // epilogue: per warp a [32 x 16] block being transposed
+  L.px = off; off += NJ * 4;
+  L.py = off; off += NJ * 4;
+  L.exb = off; off += NJ;
+  L.tab = off; off += 24 * 4;
+  L.bars = off; off += (2 * MAXNB + 8) * 8 + 32;
+  off = (off + 1023) / 1024 * 1024;
+  L.slot_bytes = 2 * (size_t)4 * H * 16;                         // one packed block of 32 K values: hi + lo
+  L.ring = off;
+  const long room = 227L * 1024 - (long)off;
+  int nb = room > 0 ? (int)(room / (long)L.slot_bytes) : 0;
+  L.nb = nb > MAXNB ? MAXNB : nb;
+  L.total = off + (size_t)L.nb * L.slot_bytes;
+  return L;
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+template <int H, bool P3>
+__global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, int nrb) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Layout L = make_layout(H);
+  uint8_t* ht = smem + L.ht;
+  uint8_t* bins = smem + L.bins;
+  int* pc = reinterpret_cast<int*>(smem + L.pc);
+  float* patch = reinterpret_cast<float*>(smem + L.patch);
+  float* px = reinterpret_cast<float*>(smem + L.px);
+  float* py = reinterpret_cast<float*>(smem + L.py);
+  uint8_t* exb = smem + L.exb;
+  float* tab = reinterpret_cast<float*>(smem + L.tab);
+  uint8_t* ring = smem + L.ring;
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* bempty = bfull + MAXNB;
+  uint64_t* sfull = bempty + MAXNB;      // selection matrix written (16 warps)
+  uint64_t* pfull = sfull + 1;           // pool MMAs of a stage complete (commit)
+  uint64_t* pempty = pfull + 1;          // P read into registers (16 warps)
+  uint64_t* afull = pempty + 1;          // A operand written (16 warps)
+  uint64_t* aempty = afull + 1;          // ... read by its fc MMAs (commit)
+  uint64_t* tfull = aempty + 1;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const int nb = L.nb;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, K = a.K, G = a.n_rad * a.n_ang;
+  const long grp = blockIdx.x / nrb;
+  const int i0 = (int)(blockIdx.x % nrb) * TM;
+  const long b = grp / K;
+  const int k = (int)(grp % K);
+  constexpr int npass = H / NC;
+  const int total = G * npass;
+  constexpr uint32_t S_COL = H, P_COL = H + NJ / 2, A_COL = P_COL + NC;
+  static_assert(A_COL + NC <= 512, "tensor memory: D + S + P + A");
+  constexpr uint32_t b_blk = 4 * H * 16;
+
+  for (int j = tid; j < NJ; j += NTHR) {                          // positions / existence of the group's agents
+    float x = 0.f, y = 0.f;
+    bool ex = false;
+    if (j < N) {
+      const long rj = (b * N + j) * K + k;
+      ex = __ldg(a.obs + (size_t)(b * N + j) * a.Tp * 3) != 0.f;
+      x = __ldg(a.pos + rj * a.pos_stride);
+      y = __ldg(a.pos + rj * a.pos_stride + 1);
+    }
+    px[j] = x;
+    py[j] = y;
+    exb[j] = ex ? 1 : 0;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < nb; ++s) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+    }
+    mbar_init(sfull, NPW);
+    mbar_init(pfull, 1);
+    mbar_init(pempty, NPW);
+    mbar_init(afull, NPW);
+    mbar_init(aempty, 1);
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == NPW) tmem_alloc<512>(tslot);
+  tc_fence_before();
+  __syncthreads();
+
+  if (warp == NPW + 1) {
+    // ===================== weight loader: blocks in stage order (pass-major)
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed);
+      int kb = 0;
+      for (int p = 0; p < npass; ++p)
+        for (int g = 0; g < G; ++g)
+          for (int c = 0; c < NC / 32; ++c, ++kb) {
+            const int slot = kb % nb;
+            mbar_wait_idle(&bempty[slot], ((kb / nb) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bfull[slot], (uint32_t)L.slot_bytes);
+            bulk_g2s_hint(ring + (size_t)slot * L.slot_bytes, src + (size_t)((g * H + p * NC) / 32 + c) * L.slot_bytes,
+                          (uint32_t)L.slot_bytes, &bfull[slot], L2_EVICT_LAST);
+          }
+    }
+  } else if (warp == NPW) {
+    // ===================== fc MMA issuer (whole warp, elected lane, descriptors = base + constant offsets)
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);
+    constexpr uint32_t idesc = idesc_bf16(TM, H);
+    constexpr uint32_t lbo_b = H * 16;
+    const uint64_t d_ring = smem_desc(smem_u32(ring), lbo_b, 128);
+    const uint32_t a_hi = tmem + A_COL, a_lo = a_hi + NC / 2;
+    int kb = 0;
+    for (int sg = 0; sg < total; ++sg) {
+      mbar_wait(afull, sg & 1);
+      tc_fence_after();
+      const uint32_t acc0 = sg > 0;
+#pragma unroll
+      for (int c = 0; c < NC / 32; ++c, ++kb) {
+        const int slot = kb % nb;
+        const uint64_t dsl = desc_adv(d_ring, slot * (uint32_t)L.slot_bytes);
+        mbar_wait(&bfull[slot], (kb / nb) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * c + jj;                            // 16-wide K step inside the stage
+            const uint64_t bhi = desc_adv(dsl, jj * 2 * lbo_b), blo = desc_adv(dsl, b_blk + jj * 2 * lbo_b);
+            mma_bf16_ts(tmem, a_hi + 8 * j, bhi, idesc, j == 0 ? acc0 : 1u);
+            if (P3) {
+              mma_bf16_ts(tmem, a_lo + 8 * j, bhi, idesc, 1);
+              mma_bf16_ts(tmem, a_hi + 8 * j, blo, idesc, 1);
+            }
+          }
+          mma_commit(&bempty[slot]);
+          if (c == NC / 32 - 1) mma_commit(aempty);
+        }
+      }
+    }
+    if (elect_one()) mma_commit(tfull);
+    __syncwarp();
+  } else if (warp == NPW + 2) {
+    // ===================== pool MMA issuer: P = S_g @ h[:, pass] (hi, then lo), A from tensor memory
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);
+    constexpr uint32_t idesc = idesc_bf16(TM, NC);
+    constexpr uint32_t lbo_h = NC * 16;
+    const uint64_t d_hh = smem_desc(smem_u32(ht), lbo_h, 128), d_hl = desc_adv(d_hh, NC * NJ * 2);
+    const uint32_t t_s = tmem + S_COL, t_p = tmem + P_COL;
+    for (int sg = 0; sg < total; ++sg) {
+      mbar_wait(sfull, sg & 1);                                   // (=> this pass's h^T slice is in place as well)
+      if (sg >= 1) mbar_wait(pempty, (sg - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < NJ / 16; ++j) {
+          mma_bf16_ts(t_p, t_s + 8 * j, desc_adv(d_hh, j * 2 * lbo_h), idesc, j > 0);
+          if (P3) mma_bf16_ts(t_p, t_s + 8 * j, desc_adv(d_hl, j * 2 * lbo_h), idesc, 1);
+        }
+        mma_commit(pfull);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== prologue: tables, bins of the 128 x N pairs
+    if (tid < 8) tab[tid] = tid <= a.n_rad ? __ldg(a.r2_edges + tid) : __int_as_float(0x7f800000);
+    if (tid >= 32 && tid < 48) tab[8 + tid - 32] = tid - 32 < 2 * a.n_ang ? __ldg(a.dirs + tid - 32) : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+    {
+      const int rl = tid & (TM - 1), q = tid >> 7;
+      const int i = i0 + rl;
+      const bool valid = i < N;
+      const float xi = valid ? px[i] : 0.f, yi = valid ? py[i] : 0.f;
+      float re[8], dr[16];
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) *reinterpret_cast<float4*>(re + e) = *reinterpret_cast<const float4*>(tab + e);
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(dr + e) = *reinterpret_cast<const float4*>(tab + 8 + e);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) asm volatile("" : "+f"(re[e]));
+#pragma unroll
+      for (int e = 0; e < 16; ++e) asm volatile("" : "+f"(dr[e]));
+      uint8_t* brow = bins + (size_t)rl * L.bin_stride;
+      for (int j = q; j < NJ; j += 4) {
+        const bool on = valid && j < N && j != i && exb[j];       // a masked row still pools its existing neighbours
+        int gf, gb;
+        logpolar_bin_pair(px[j] - xi, py[j] - yi, re, dr, a.n_rad, a.n_ang, gf, gb);
+        brow[j] = (uint8_t)(on ? gf : -1);                        // 255 = no bin
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+
+    // thread = TMEM lane (row 32*(warp%4) + lane); part = warp/4: 64 neighbours (32 packed columns) of S, 16 columns of P
+    const int q4 = warp & 3, part = warp >> 2;
+    const int frow = 32 * q4 + lane;
+    const uint32_t lane_f = (uint32_t)(32 * q4) << 16;
+    const uint8_t* brow = bins + (size_t)frow * L.bin_stride + 64 * part;
+    auto build = [&](int sg, int bin) {                           // selection matrix + partial counts of stage sg; the caller
+      const uint32_t g4 = (uint32_t)bin * 0x01010101u;           // has seen pool(sg-1) complete: S is free
+      uint32_t sr[32];
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 w = *reinterpret_cast<const uint4*>(brow + 16 * c);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t z = eq_bytes(ww[e], g4);
+          cnt += __popc(z);
+          sr[8 * c + 2 * e] = ones_lo(z);
+          sr[8 * c + 2 * e + 1] = ones_hi(z);
+        }
+      }
+      pc[((sg & 3) * 4 + part) * TM + frow] = cnt;
+      tc_fence_after();
+      tmem_st32(tmem + lane_f + S_COL + part * 32, sr);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sfull);
+    };
+    // h^T slice of pass p (columns 64p .. 64p+63): byte(c, j) = (j/8) * NC*16 + c*16 + (j%8)*2
+    auto load_ht = [&](int p) {
+      constexpr int ITEMS = NC * (NJ / 8) / PT;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int item = it * PT + tid;
+        const int c = item % NC, oct = item / NC;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = oct * 8 + e;
+          v[e] = j < N ? __ldg(a.h + ((b * N + j) * K + k) * (long)a.ld_h + p * NC + c) : 0.f;
+        }
+        const Split8 s8 = split8(v);
+        const size_t o = (size_t)oct * NC * 16 + (size_t)c * 16;
+        *reinterpret_cast<uint4*>(ht + o) = s8.hi;
+        *reinterpret_cast<uint4*>(ht + (size_t)NC * NJ * 2 + o) = s8.lo;
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(PT) : "memory");
+    };
+
+    load_ht(0);
+    build(0, 0);
+    for (int sg = 0; sg < total; ++sg) {
+      const int p = sg / G, g = sg - p * G;
+      mbar_wait(pfull, sg & 1);                                   // pool(sg) complete: P is ready, S is free
+      tc_fence_after();
+      const int* pcg = pc + (size_t)(sg & 3) * 4 * TM + frow;
+      const int cnt = pcg[0] + pcg[TM] + pcg[2 * TM] + pcg[3 * TM];
+      float v[16];
+      tmem_ld16(tmem + lane_f + P_COL + part * 16, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pempty);
+      if (g + 1 < G) build(sg + 1, g + 1);                        // the next pool MMAs run while this stage is converted
+      if (cnt > 1) {
+        const float inv = __frcp_rn((float)cnt);                 // mean = sum * (1/count)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= inv;
+      }
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+      if (sg >= 1) mbar_wait(aempty, (sg - 1) & 1);               // fc(sg-1) has read the A operand
+      tc_fence_after();
+      tmem_st8(tmem + lane_f + A_COL + part * 8, reinterpret_cast<const float*>(hi));
+      tmem_st8(tmem + lane_f + A_COL + NC / 2 + part * 8, reinterpret_cast<const float*>(lo));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(afull);
+      if (g + 1 == G && p + 1 < npass) {                          // next pass: every pool MMA of this one is complete
+        load_ht(p + 1);
+        build(sg + 1, 0);
+      }
+    }
+
+    // ===================== epilogue: bias + ReLU; the warp transposes 16-column blocks of its 32 rows through a private
+    // patch and writes 64-byte row segments (four lanes per row, eight rows per instruction)
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    float* st = patch + (size_t)warp * 32 * 20;
+    constexpr int CPP = H / 4;                                    // columns per part
+#pragma unroll 1
+    for (int c0 = part * CPP; c0 < (part + 1) * CPP; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + lane_f + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + i));
+        *reinterpret_cast<float4*>(st + lane * 20 + i) =
+            make_float4(fmaxf(v[i] + bv.x, 0.f), fmaxf(v[i + 1] + bv.y, 0.f), fmaxf(v[i + 2] + bv.z, 0.f), fmaxf(v[i + 3] + bv.w, 0.f));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = 8 * it + (lane >> 2), c4 = lane & 3;
+        const int i = i0 + 32 * q4 + rr;
+        if (i < N) {
+          const long r = (b * N + i) * K + k;
+          *(reinterpret_cast<float4*>(a.out + r * (long)H + c0) + c4) = *reinterpret_cast<const float4*>(st + rr * 20 + c4 * 4);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NPW) tmem_dealloc(*tslot, 512);
+}
+
+}  // namespace
+
+// DESIRE_SOCIAL_NO_FM=1 keeps the materialising path (pool kernel + GEMM) for these shapes (A/B timing)
+bool social_fc_fm_eligible(const SocialFcArgs& a) {
+  static const bool off = [] {
+    const char* e = getenv("DESIRE_SOCIAL_NO_FM");
+    return e && e[0] == '1';
+  }();
+  const int G = a.n_rad * a.n_ang;
+  if (off || gemm_mode() == 0 || !a.packed) return false;
+  if ((a.H != 128 && a.H != 256) || a.N <= 128 || a.N > NJ) return false;
+  if (a.n_rad > 7 || a.n_ang > 8 || G > 64 || G < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(a.bias) & 15) || (reinterpret_cast<uintptr_t>(a.out) & 15)) return false;
+  return make_layout(a.H).nb >= 2;
+}
+
+int social_fc_fm(const SocialFcArgs& a, cudaStream_t st) {
+  const long ngroups = (long)a.B * a.K;
+  if (ngroups == 0) return DESIRE_OK;
+  const int nrb = (a.N + TM - 1) / TM;
+  const Layout L = make_layout(a.H);
+  const long grid = ngroups * nrb;
+  DESIRE_CHECK_ARG(grid < (1L << 31), "social_fc_fm: grid too large");
+  const bool p3 = gemm_mode() != 1;
+#define SOCIAL_FM_LAUNCH(HH, PP)                                                                       \
+  do {                                                                                                 \
+    DESIRE_ENSURE_SMEM((social_fc_fm_kernel<HH, PP>), L.total);                                        \
+    DESIRE_LAUNCH(st, (social_fc_fm_kernel<HH, PP><<<(unsigned)grid, NTHR, L.total, st>>>(a, nrb)));   \
+  } while (0)
+  if (a.H == 256) {
+    if (p3) SOCIAL_FM_LAUNCH(256, true); else SOCIAL_FM_LAUNCH(256, false);
+  } else {
+    if (p3) SOCIAL_FM_LAUNCH(128, true); else SOCIAL_FM_LAUNCH(128, false);
+  }
+#undef SOCIAL_FM_LAUNCH
+  return DESIRE_OK;
+}
+
+}  // namespace desire

@@ -327,7 +327,7 @@ static bool use_ts(const SocialFcArgs& a) {
 
 bool social_fc_tc_eligible(const SocialFcArgs& a) {
   const int G = a.n_rad * a.n_ang;
-  if (use_ts(a)) return true;
+  if (use_ts(a) || social_fc_fm_eligible(a)) return true;
   if (gemm_mode() == 0 || !a.packed) return false;
   if (a.H % 64 != 0 || a.H < 64 || a.H > 128 || a.ld_h % 4 != 0) return false;   // a 64-column stage never straddles bins
   if (a.N > 128 || a.N < 1 || G > MAXG || G < 1) return false;
@@ -337,6 +337,7 @@ bool social_fc_tc_eligible(const SocialFcArgs& a) {
 
 int social_fc_tc(const SocialFcArgs& a, cudaStream_t st) {
   if (use_ts(a)) return social_fc_ts(a, st);
+  if (social_fc_fm_eligible(a)) return social_fc_fm(a, st);
   const int Npad = npad_of(a.N), G = a.n_rad * a.n_ang;
   const Layout L = make_layout(a.H, Npad, G, a.n_rad, a.n_ang);
   const long ngroups = (long)a.B * a.K;

@@ -31,7 +31,9 @@ def social_fc_gpu(lib, pos, h, obs, W, b, cfg, r2, dirs):
 
 
 CASES = [(3, 60, 4, 128, 5), (2, 7, 3, 64, 2), (1, 128, 2, 128, 0), (2, 100, 3, 64, 3), (5, 33, 5, 128, 1), (1, 1, 3, 128, 0),
-         (2, 16, 9, 128, 0), (1, 65, 1, 128, 4)]
+         (2, 16, 9, 128, 0), (1, 65, 1, 128, 4),
+         # 129..256 agents per scene -> social_fm.cu (one and two row blocks per group, H = 128 and 256)
+         (1, 256, 2, 256, 3), (2, 200, 2, 128, 0), (1, 129, 3, 256, 0)]
 
 
 @pytest.mark.parametrize("B,N,K,H,missing", CASES)
@@ -54,7 +56,7 @@ def test_fused_social_fc_matches_oracle(lib, B, N, K, H, missing):
     got = social_fc_gpu(lib, pos, h, obs, W, b, cfg, r2, dirs)
     e = rel_l2(got, ref)
     print("fused social fc B%d N%d K%d H%d: rel-L2 %.3e" % (B, N, K, H, e))
-    assert e < 2e-5
+    assert e < (2e-5 if N <= 128 else 4e-5)      # (large scenes: sums over up to 255 neighbours, K = G*H up to 9216)
     # rows without any neighbour in range: exactly relu(bias)
     lonely = ~(pooled != 0).any(axis=1)
     if lonely.any():

@@ -1,9 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -s -k "social_pool" 2>&1 | grep "social pool\|passed\|failed\|Error" | tail -14
-timeout 900 python -m pytest tests/test_gpu_fullsize.py -x -q -k "cfg3" 2>&1 | tail -2
-timeout 400 python bench.py --config cfg3 --steps 5 --warmup 3 --no-train --no-cpu-baseline 2>/dev/null | python -c "
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/t_tests.log 2>&1; echo "tests rc $?"; tail -3 gpurun_out/t_tests.log
+for c in cfg3 cfg5; do
+timeout 400 python bench.py --config $c --steps 5 --warmup 3 --no-train --no-cpu-baseline --breakdown gpurun_out/r2_${c}_breakdown.json 2>gpurun_out/r2_${c}_bench.err > gpurun_out/r2_${c}_bench.json
+python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('cfg3 value %.0f ms %.3f'%(d['value'], d['ms_per_step']))
-for k in (d.get('kernels') or [])[:6]: print('   %-40s %8.3f ms frac %.3f' % (k['kernel'],k['ms_per_step'],k['frac']))"
+d=json.loads(open('gpurun_out/r2_${c}_bench.json').read().strip().splitlines()[-1])
+print('$c value %.0f ms %.3f e2e %.0f'%(d['value'], d['ms_per_step'], d['e2e']['value']))
+for k in (d.get('kernels') or [])[:5]: print('   %-40s %8.3f ms frac %.3f' % (k['kernel'],k['ms_per_step'],k['frac']))"
+done
