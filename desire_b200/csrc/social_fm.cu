@@ -31,27 +31,28 @@ constexpr int PT = NPW * 32;
 constexpr int NTHR = (NPW + 3) * 32;
 constexpr int NC = 64;           // pooled K values per stage = columns of h per pass
 constexpr int NJ = 256;          // neighbours (padded)
-constexpr int MAXNB = 8;
+constexpr int MAXNB = 12;
 
 struct Layout {
-  size_t ht, bins, bin_stride, pc, patch, px, py, exb, tab, bars, ring, slot_bytes, total;
+  size_t ht, bins, bin_stride, pc, px, py, exb, tab, bars, ring, slot_bytes, total;
   int nb;
 };
 __host__ __device__ inline Layout make_layout(int H) {
   Layout L;
   size_t off = 0;
-  L.ht = off; off += 2 * (size_t)NC * NJ * 2;                    // h^T slice, K-major [NC x NJ] BF16: hi, lo
+  L.ht = off; off += 2 * (size_t)NC * NJ * 2;                    // h^T slice, K-major [NC x NJ] BF16: hi, lo (64 KB; the
+                                                                 // epilogue's 40 KB of transpose patches reuse it)
   L.bin_stride = NJ + 16;
   L.bins = off; off += TM * L.bin_stride;
   L.pc = off; off += 4 * 4 * TM * 4;                             // partial counts [4 buffers][4 parts][128 rows]
-  L.patch = off; off += (size_t)NPW * 32 * 20 * 4;               // epilogue: per warp a [32 x 16] block being transposed
   L.px = off; off += NJ * 4;
   L.py = off; off += NJ * 4;
   L.exb = off; off += NJ;
   L.tab = off; off += 24 * 4;
   L.bars = off; off += (2 * MAXNB + 8) * 8 + 32;
   off = (off + 1023) / 1024 * 1024;
-  L.slot_bytes = 2 * (size_t)4 * H * 16;                         // one packed block of 32 K values: hi + lo
+  L.slot_bytes = 2 * (size_t)2 * H * 16;                         // 16 K values of the packed weights: hi + lo (8 KB each at
+                                                                 // H = 256): small slots = more stages of look-ahead
   L.ring = off;
   const long room = 227L * 1024 - (long)off;
   int nb = room > 0 ? (int)(room / (long)L.slot_bytes) : 0;
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
   uint8_t* ht = smem + L.ht;
   uint8_t* bins = smem + L.bins;
   int* pc = reinterpret_cast<int*>(smem + L.pc);
-  float* patch = reinterpret_cast<float*>(smem + L.patch);
+  float* patch = reinterpret_cast<float*>(smem + L.ht);          // epilogue only: the h^T slice is dead by then
   float* px = reinterpret_cast<float*>(smem + L.px);
   float* py = reinterpret_cast<float*>(smem + L.py);
   uint8_t* exb = smem + L.exb;
@@ -144,12 +145,14 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
       int kb = 0;
       for (int p = 0; p < npass; ++p)
         for (int g = 0; g < G; ++g)
-          for (int c = 0; c < NC / 32; ++c, ++kb) {
+          for (int c = 0; c < NC / 16; ++c, ++kb) {              // 16-wide K steps: half of a packed 32-K block each
             const int slot = kb % nb;
+            const uint8_t* blk = src + (size_t)((g * H + p * NC) / 32 + c / 2) * (2 * b_blk) + (c & 1) * (b_blk / 2);
+            uint8_t* dst = ring + (size_t)slot * L.slot_bytes;
             mbar_wait_idle(&bempty[slot], ((kb / nb) & 1) ^ 1);
             mbar_arrive_expect_tx(&bfull[slot], (uint32_t)L.slot_bytes);
-            bulk_g2s_hint(ring + (size_t)slot * L.slot_bytes, src + (size_t)((g * H + p * NC) / 32 + c) * L.slot_bytes,
-                          (uint32_t)L.slot_bytes, &bfull[slot], L2_EVICT_LAST);
+            bulk_g2s_hint(dst, blk, b_blk / 2, &bfull[slot], L2_EVICT_LAST);                      // hi: two K chunks
+            bulk_g2s_hint(dst + b_blk / 2, blk + b_blk, b_blk / 2, &bfull[slot], L2_EVICT_LAST);  // lo
           }
     }
   } else if (warp == NPW) {
@@ -166,24 +169,19 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
       tc_fence_after();
       const uint32_t acc0 = sg > 0;
 #pragma unroll
-      for (int c = 0; c < NC / 32; ++c, ++kb) {
+      for (int j = 0; j < NC / 16; ++j, ++kb) {                  // 16-wide K steps = weight slots
         const int slot = kb % nb;
-        const uint64_t dsl = desc_adv(d_ring, slot * (uint32_t)L.slot_bytes);
+        const uint64_t bhi = desc_adv(d_ring, slot * (uint32_t)L.slot_bytes), blo = desc_adv(bhi, b_blk / 2);
         mbar_wait(&bfull[slot], (kb / nb) & 1);
         tc_fence_after();
         if (elect_one()) {
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int j = 2 * c + jj;                            // 16-wide K step inside the stage
-            const uint64_t bhi = desc_adv(dsl, jj * 2 * lbo_b), blo = desc_adv(dsl, b_blk + jj * 2 * lbo_b);
-            mma_bf16_ts(tmem, a_hi + 8 * j, bhi, idesc, j == 0 ? acc0 : 1u);
-            if (P3) {
-              mma_bf16_ts(tmem, a_lo + 8 * j, bhi, idesc, 1);
-              mma_bf16_ts(tmem, a_hi + 8 * j, blo, idesc, 1);
-            }
+          mma_bf16_ts(tmem, a_hi + 8 * j, bhi, idesc, j == 0 ? acc0 : 1u);
+          if (P3) {
+            mma_bf16_ts(tmem, a_lo + 8 * j, bhi, idesc, 1);
+            mma_bf16_ts(tmem, a_hi + 8 * j, blo, idesc, 1);
           }
           mma_commit(&bempty[slot]);
-          if (c == NC / 32 - 1) mma_commit(aempty);
+          if (j == NC / 16 - 1) mma_commit(aempty);
         }
       }
     }
@@ -378,7 +376,7 @@ bool social_fc_fm_eligible(const SocialFcArgs& a) {
   if ((a.H != 128 && a.H != 256) || a.N <= 128 || a.N > NJ) return false;
   if (a.n_rad > 7 || a.n_ang > 8 || G > 64 || G < 1) return false;
   if ((reinterpret_cast<uintptr_t>(a.bias) & 15) || (reinterpret_cast<uintptr_t>(a.out) & 15)) return false;
-  return make_layout(a.H).nb >= 2;
+  return make_layout(a.H).nb >= 4;
 }
 
 int social_fc_fm(const SocialFcArgs& a, cudaStream_t st) {

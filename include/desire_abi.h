@@ -237,7 +237,8 @@ int desire_social_pool_fwd(const float* pos, long pos_stride, const float* h, in
                            desire_stream_t stream);
 /* One step of the social feature, fused (binning + pooling + fc on tensor cores; the [R, G*H] pooled tensor is never
  * written): fsp [R,H] = relu(pool(h) @ sp_w [G*H,H] + sp_b).  ws: scratch for the packed weights.  Returns
- * DESIRE_ERR_INVALID when the shape is outside the fused kernels (H in {64,128}, N <= 128) — no fallback here. */
+ * DESIRE_ERR_INVALID when the shape is outside the fused kernels (N <= 128 with H in {64, 128}; 129..256 agents with
+ * H in {128, 256}) — no fallback here. */
 size_t desire_social_fc_workspace_bytes(int H, int n_bins);
 int desire_social_fc_fwd(const float* pos, long pos_stride, const float* h, int ld_h, const float* obs, int Tp, int B,
                          int N, int K, int H, int n_rad, int n_ang, const float* r2_edges, const float* dirs,
