@@ -73,7 +73,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 }
 
 template <int H, bool P3>
-__global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, int nrb) {
+__global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, int nrb, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Layout L = make_layout(H);
   uint8_t* ht = smem + L.ht;
@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
   const int nb = L.nb;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool tr = trace != nullptr && blockIdx.x == 0;
+#define TRACE(i) do { if (tr && (i) < 1000) trace[i] = clock64(); } while (0)
+  if (tid == 0) TRACE(0);
   const int N = a.N, K = a.K, G = a.n_rad * a.n_ang;
   const long grp = blockIdx.x / nrb;
   const int i0 = (int)(blockIdx.x % nrb) * TM;
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
     for (int sg = 0; sg < total; ++sg) {
       mbar_wait(afull, sg & 1);
       tc_fence_after();
+      if (lane == 0 && sg < 60) TRACE(16 + 16 * sg + 8);
       const uint32_t acc0 = sg > 0;
 #pragma unroll
       for (int j = 0; j < NC / 16; ++j, ++kb) {                  // 16-wide K steps = weight slots
@@ -184,6 +188,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
           if (j == NC / 16 - 1) mma_commit(aempty);
         }
       }
+      if (lane == 0 && sg < 60) TRACE(16 + 16 * sg + 9);
     }
     if (elect_one()) mma_commit(tfull);
     __syncwarp();
@@ -199,6 +204,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
       mbar_wait(sfull, sg & 1);                                   // (=> this pass's h^T slice is in place as well)
       if (sg >= 1) mbar_wait(pempty, (sg - 1) & 1);
       tc_fence_after();
+      if (lane == 0 && sg < 60) TRACE(16 + 16 * sg + 10);
       if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < NJ / 16; ++j) {
@@ -207,6 +213,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
         }
         mma_commit(pfull);
       }
+      if (lane == 0 && sg < 60) TRACE(16 + 16 * sg + 11);
     }
     __syncwarp();
   } else {
@@ -245,9 +252,12 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
     const int frow = 32 * q4 + lane;
     const uint32_t lane_f = (uint32_t)(32 * q4) << 16;
     const uint8_t* brow = bins + (size_t)frow * L.bin_stride + 64 * part;
-    auto build = [&](int sg, int bin) {                           // selection matrix + partial counts of stage sg; the caller
-      const uint32_t g4 = (uint32_t)bin * 0x01010101u;           // has seen pool(sg-1) complete: S is free
-      uint32_t sr[32];
+    // The selection matrix of a stage is prepared in registers BEFORE the previous pool MMAs are known to be complete (its
+    // byte compares only need the bins) and stored when S is free: the store is all that is left on the chain
+    // pool(s) -> S(s+1) -> pool(s+1) of the single-buffered S.
+    uint32_t sr[32];
+    auto prep = [&](int sg, int bin) {
+      const uint32_t g4 = (uint32_t)bin * 0x01010101u;
       int cnt = 0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -262,6 +272,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
         }
       }
       pc[((sg & 3) * 4 + part) * TM + frow] = cnt;
+    };
+    auto put = [&]() {                                            // the caller has seen the previous pool MMAs complete
       tc_fence_after();
       tmem_st32(tmem + lane_f + S_COL + part * 32, sr);
       tmem_st_wait();
@@ -292,11 +304,15 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
     };
 
     load_ht(0);
-    build(0, 0);
+    prep(0, 0);
+    put();
     for (int sg = 0; sg < total; ++sg) {
       const int p = sg / G, g = sg - p * G;
+      if (sg + 1 < total) prep(sg + 1, g + 1 < G ? g + 1 : 0);
+      if (tid == 0 && sg < 60) TRACE(16 + 16 * sg);
       mbar_wait(pfull, sg & 1);                                   // pool(sg) complete: P is ready, S is free
       tc_fence_after();
+      if (tid == 0 && sg < 60) TRACE(16 + 16 * sg + 1);
       const int* pcg = pc + (size_t)(sg & 3) * 4 * TM + frow;
       const int cnt = pcg[0] + pcg[TM] + pcg[2 * TM] + pcg[3 * TM];
       float v[16];
@@ -305,7 +321,9 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pempty);
-      if (g + 1 < G) build(sg + 1, g + 1);                        // the next pool MMAs run while this stage is converted
+      if (tid == 0 && sg < 60) TRACE(16 + 16 * sg + 2);
+      if (g + 1 < G) put();                                       // the next pool MMAs run while this stage is converted
+      if (tid == 0 && sg < 60) TRACE(16 + 16 * sg + 3);
       if (cnt > 1) {
         const float inv = __frcp_rn((float)cnt);                 // mean = sum * (1/count)
 #pragma unroll
@@ -314,17 +332,20 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+      if (tid == 0 && sg < 60) TRACE(16 + 16 * sg + 4);
       if (sg >= 1) mbar_wait(aempty, (sg - 1) & 1);               // fc(sg-1) has read the A operand
       tc_fence_after();
+      if (tid == 0 && sg < 60) TRACE(16 + 16 * sg + 5);
       tmem_st8(tmem + lane_f + A_COL + part * 8, reinterpret_cast<const float*>(hi));
       tmem_st8(tmem + lane_f + A_COL + NC / 2 + part * 8, reinterpret_cast<const float*>(lo));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(afull);
+      if (tid == 0 && sg < 60) TRACE(16 + 16 * sg + 6);
       if (g + 1 == G && p + 1 < npass) {                          // next pass: every pool MMA of this one is complete
         load_ht(p + 1);
-        build(sg + 1, 0);
+        put();
       }
     }
 
@@ -358,6 +379,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
       __syncwarp();
     }
   }
+#undef TRACE
   tc_fence_before();
   __syncthreads();
   if (warp == NPW) tmem_dealloc(*tslot, 512);
@@ -387,10 +409,18 @@ int social_fc_fm(const SocialFcArgs& a, cudaStream_t st) {
   const long grid = ngroups * nrb;
   DESIRE_CHECK_ARG(grid < (1L << 31), "social_fc_fm: grid too large");
   const bool p3 = gemm_mode() != 1;
+  // DESIRE_SOCIAL_TRACE=1: block 0 records clock64() at its milestones; printed after the fifth launch (timing tool only)
+  static long long* trace = nullptr;
+  static const bool want_trace = [] {
+    const char* e = getenv("DESIRE_SOCIAL_TRACE");
+    return e && e[0] == '1';
+  }();
+  if (want_trace && !trace) DESIRE_CUDA(cudaMalloc(&trace, 1024 * sizeof(long long)));
+  if (want_trace) DESIRE_CUDA(cudaMemsetAsync(trace, 0, 1024 * sizeof(long long), st));
 #define SOCIAL_FM_LAUNCH(HH, PP)                                                                       \
   do {                                                                                                 \
     DESIRE_ENSURE_SMEM((social_fc_fm_kernel<HH, PP>), L.total);                                        \
-    DESIRE_LAUNCH(st, (social_fc_fm_kernel<HH, PP><<<(unsigned)grid, NTHR, L.total, st>>>(a, nrb)));   \
+    DESIRE_LAUNCH(st, (social_fc_fm_kernel<HH, PP><<<(unsigned)grid, NTHR, L.total, st>>>(a, nrb, trace))); \
   } while (0)
   if (a.H == 256) {
     if (p3) SOCIAL_FM_LAUNCH(256, true); else SOCIAL_FM_LAUNCH(256, false);
@@ -398,6 +428,20 @@ int social_fc_fm(const SocialFcArgs& a, cudaStream_t st) {
     if (p3) SOCIAL_FM_LAUNCH(128, true); else SOCIAL_FM_LAUNCH(128, false);
   }
 #undef SOCIAL_FM_LAUNCH
+  if (want_trace) {
+    static int printed = 0;
+    long long h[1024];
+    DESIRE_CUDA(cudaStreamSynchronize(st));
+    DESIRE_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    if (printed++ == 4) {
+      const long long t0 = h[0];
+      for (int sg = 0; sg < 12; ++sg) {
+        const long long* e = h + 16 + 16 * sg;
+        fprintf(stderr, "  fm stage %2d: start %7lld wait-pool %5lld ld %5lld build-next %5lld convert %5lld wait-fc %5lld st %5lld | fc: A at %7lld issue %5lld | pool: go at %7lld issue %5lld\n",
+                sg, e[0] - t0, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4], e[6] - e[5], e[8] - t0, e[9] - e[8], e[10] - t0, e[11] - e[10]);
+      }
+    }
+  }
   return DESIRE_OK;
 }
 
