@@ -11,14 +11,14 @@ from desire_b200 import _lib
 lib = _lib.load()
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
 for grid in (148,):
-    for mode in (5, 10, 11):
+    for mode in (5, 10, 11, 13):
         for N in (128,):
             for it in range(2):
                 _lib.check(lib.desire_selftest_mma_rate(mode, N, 4092, grid, C.c_void_p(out.data_ptr()), None), "rate")
                 torch.cuda.synchronize()
             cyc = out.item() / 4092
             print("grid %3d  %s  N=%3d: %.1f cycles per MMA (floor %d) -> %.0f%% of the tensor peak" % (
-                grid, ("SS", "TS", "SS two accumulators", "TS two accumulators", "TS two issuing threads (cycles per MMA of ONE thread)", "TS elected lane, uniform operands", "SS elected lane, uniform operands", "TS elected + commit per 6 MMAs", "TS elected + wait, fence, commit per 6 MMAs", "TS elected + wait, fence per 6 MMAs", "TS elected, accumulators alternate every MMA", "TS elected, accumulators alternate every 6 MMAs")[mode], N, cyc, N // 2, 100 * (N / 2) / cyc))
+                grid, ("SS", "TS", "SS two accumulators", "TS two accumulators", "TS two issuing threads (cycles per MMA of ONE thread)", "TS elected lane, uniform operands", "SS elected lane, uniform operands", "TS elected + commit per 6 MMAs", "TS elected + wait, fence, commit per 6 MMAs", "TS elected + wait, fence per 6 MMAs", "TS elected, accumulators alternate every MMA", "TS elected, accumulators alternate every 6 MMAs", "", "TS two issuing warps, elected lanes (cycles per MMA of ONE warp; 128 = the pipe is shared without loss)")[mode], N, cyc, N // 2, 100 * (N / 2) / cyc))
 
 out = torch.zeros(32, dtype=torch.int64, device="cuda")
 for it in range(2):
