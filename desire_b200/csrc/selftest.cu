@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (128 * 64 * 2 + 256 * 64 * 2) / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    mbar_init(&bar, (mode == 4 || mode == 13) ? 2 : 1);
+    mbar_init(&bar, (mode == 4 || mode == 13 || mode == 14) ? 2 : 1);
     mbar_init(&dummy, 1 << 20);
     mbar_init(&done0, 1);
     mbar_arrive(&done0);                                         // phase 0 of done0 is complete from the start
@@ -156,6 +156,39 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
   }
   // mode 5: the whole warp runs the issue loop with warp-uniform operands and one ELECTED lane issues (TS) — the
   // compiler then feeds UTCHMMA from uniform registers instead of wrapping every MMA in a lane-broadcast loop
+  // mode 14: the MMA mix of one stage of the fused social kernel, nothing else running: warp 1 issues 24 MMAs with A in
+  // tensor memory (the fc), warp 2 sixteen with both operands in shared memory (the pooling), per round; N = 128
+  if (mode == 14 && (warp == 1 || warp == 2)) {
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t sa = smem_u32(sm), sb = sa + 128 * 64 * 2;
+    uint64_t da[4], db[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      da[j] = smem_desc(sa + j * 2 * 128 * 16, 128 * 16, 128);
+      db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
+    }
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 40) {
+      if (warp == 1) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 24; ++j) mma_bf16_ts(tm, tm + 256 + (j & 3) * 8, db[j & 3], idesc, 1);
+        }
+      } else {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mma_bf16(tm + 128, da[j & 3], db[j & 3], idesc, 1);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && tid == 32) out[0] = t1 - t0;
+  }
   // mode 13: TWO warps issue concurrently (elected lanes, uniform operands), each into its own accumulator
   if (mode == 13 && (warp == 1 || warp == 2)) {
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
@@ -177,7 +210,7 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
     const long long t1 = clock64();
     if (blockIdx.x == 0 && tid == 32) out[0] = t1 - t0;
   }
-  if (mode >= 5 && mode != 13 && warp == 1) {
+  if (mode >= 5 && mode != 13 && mode != 14 && warp == 1) {
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc = idesc_bf16(128, N);
     const uint32_t sb = smem_u32(sm) + 128 * 64 * 2;
@@ -259,7 +292,7 @@ extern "C" int desire_selftest_tsmma(const float* A, const float* B, float* out_
 }
 
 extern "C" int desire_selftest_mma_rate(int mode, int N, int iters, int grid, long long* out_cycles, desire_stream_t stream) {
-  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 13 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
+  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 14 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
                    "desire_selftest_mma_rate: bad arguments");
   const size_t smem = 128 * 64 * 2 + 256 * 64 * 2;
   DESIRE_ENSURE_SMEM(desire::mma_rate_kernel, smem);

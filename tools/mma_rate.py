@@ -25,3 +25,8 @@ for it in range(2):
     _lib.check(lib.desire_selftest_mma_rate(12, 128, 64, 148, C.c_void_p(out.data_ptr()), None), "rate")
     torch.cuda.synchronize()
 print("cycles until the n-th MMA (N=128) was issued:", ", ".join("%d: %d" % (4 * k + 4, out[1 + k].item()) for k in range(16)))
+
+_lib.check(lib.desire_selftest_mma_rate(14, 128, 4000, 148, C.c_void_p(out.data_ptr()), None), "rate")
+_lib.check(lib.desire_selftest_mma_rate(14, 128, 4000, 148, C.c_void_p(out.data_ptr()), None), "rate")
+torch.cuda.synchronize()
+print("stage mix of the fused social kernel (24 TS + 16 SS MMAs, N=128, two issuing warps, nothing else running): %.0f cycles per stage (floor 2560)" % (out[0].item() / 100))
