@@ -109,14 +109,14 @@ __global__ void __launch_bounds__(160) tsmma_kernel(const float* __restrict__ A,
 
 // How fast does one thread's stream of tcgen05.mma (M = 128, K = 16, BF16) retire?  mode 0: both operands in shared
 // memory, 1: A in tensor memory.  Every CTA issues `iters` MMAs on the same operands; cycles of block 0 are returned.
-__global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iters, long long* __restrict__ out) {
+__global__ void __launch_bounds__(640) mma_rate_kernel(int mode, int N, int iters, long long* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t bar, dummy, done0;
   __shared__ uint32_t tslot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (128 * 64 * 2 + 256 * 64 * 2) / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (128 * 64 * 2 + 256 * 64 * 2) / 16; i += blockDim.x) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    mbar_init(&bar, (mode == 4 || mode == 13 || mode == 14) ? 2 : 1);
+    mbar_init(&bar, (mode == 4 || mode == 13 || mode >= 14) ? 2 : 1);
     mbar_init(&dummy, 1 << 20);
     mbar_init(&done0, 1);
     mbar_arrive(&done0);                                         // phase 0 of done0 is complete from the start
@@ -158,7 +158,152 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
   // compiler then feeds UTCHMMA from uniform registers instead of wrapping every MMA in a lane-broadcast loop
   // mode 14: the MMA mix of one stage of the fused social kernel, nothing else running: warp 1 issues 24 MMAs with A in
   // tensor memory (the fc), warp 2 sixteen with both operands in shared memory (the pooling), per round; N = 128
-  if (mode == 14 && (warp == 1 || warp == 2)) {
+  // modes 18-21: a miniature of the fused social kernel's stage protocol (TMEM D | P | A0 | A1): warp 1 issues the fc MMAs
+  // (24 TS) of stage g when A(g) is announced and commits aempty; warp 2 issues pool(g) (16 SS) when P is free and
+  // commits pfull; 16 finisher warps wait for pfull, tcgen05.ld P, release it, convert, wait for aempty(g-2),
+  // tcgen05.st A(g), announce it.  18: all of it, 19: handshakes only (no ld / st), 20: 18 with the fc MMAs issued in four
+  // elect blocks with a commit each (the weight ring), 21: 18 with P released only after the conversion
+  if (mode >= 18) {
+    __shared__ uint64_t pfull, pempty, afull[2], aempty[2];
+    if (tid == 0) {
+      mbar_init(&pfull, 1);
+      mbar_init(&pempty, 16);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&afull[i], 16);
+        mbar_init(&aempty[i], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncthreads();
+    const int nst = iters / 40;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t sa = smem_u32(sm), sb = sa + 128 * 64 * 2;
+    uint64_t da[4], db[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      da[j] = smem_desc(sa + j * 2 * 128 * 16, 128 * 16, 128);
+      db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
+    }
+    const long long t0 = clock64();
+    if (warp == 1) {
+      for (int g = 0; g < nst; ++g) {
+        mbar_wait(&afull[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t ta = tm + 256 + (g & 1) * 128;
+        if (mode == 20) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < 6; ++j) mma_bf16_ts(tm, ta + ((c * 6 + j) & 7) * 8, db[j & 3], idesc, 1);
+              mma_commit(&dummy);
+              if (c == 3) mma_commit(&aempty[g & 1]);
+            }
+            __syncwarp();
+          }
+        } else {
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) mma_bf16_ts(tm, ta + (j & 7) * 8, db[j & 3], idesc, 1);
+            mma_commit(&aempty[g & 1]);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) mma_commit(&bar);
+      __syncwarp();
+      mbar_wait(&bar, 0);
+      const long long t1 = clock64();
+      if (blockIdx.x == 0 && tid == 32) out[0] = t1 - t0;
+    } else if (warp == 2) {
+      for (int g = 0; g < nst; ++g) {
+        if (g > 0) mbar_wait(&pempty, (g - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mma_bf16(tm + 128, da[j & 3], db[j & 3], idesc, j > 0);
+          mma_commit(&pfull);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) mma_commit(&bar);
+      __syncwarp();
+    } else if (warp >= 3) {
+      const int w = warp - 3, q4 = warp & 3, cg = w >> 2;
+      const uint32_t lane_f = (uint32_t)(32 * q4) << 16;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      for (int g = 0; g < nst; ++g) {
+        mbar_wait(&pfull, g & 1);
+        tc_fence_after();
+        if (mode != 19) {
+          tmem_ld32(tm + lane_f + 128 + cg * 32, v);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        if (mode != 21) {
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&pempty);
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split2(v[2 * i] * 0.5f, v[2 * i + 1] * 0.5f, hi[i], lo[i]);
+        if (mode == 21) {
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&pempty);
+        }
+        if (mode >= 22) {                                        // 22: fence.proxy.async per thread and stage (what follows
+          if (mode == 23) {                                      // the selection-matrix stores), 23: with two 16-byte stores
+            uint4* q = reinterpret_cast<uint4*>(sm + 128 * 64 * 2 + 256 * 64 * 2) + (tid - 96);
+            q[0] = make_uint4(hi[0], hi[1], lo[0], lo[1]);
+            q[512] = make_uint4(hi[2], hi[3], lo[2], lo[3]);
+          }
+          fence_proxy_async();
+        }
+        if (g >= 2) mbar_wait(&aempty[g & 1], ((g - 2) >> 1) & 1);
+        tc_fence_after();
+        if (mode != 19) {
+          const uint32_t ta = tm + lane_f + 256 + (g & 1) * 128 + cg * 16;
+          tmem_st16(ta, reinterpret_cast<const float*>(hi));
+          tmem_st16(ta + 64, reinterpret_cast<const float*>(lo));
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&afull[g & 1]);
+      }
+    }
+  }
+  // modes 15-17: the same, with 16 more warps that 15: poll the final barrier (what waiting producer warps do),
+  // 16: stream 16-byte shared-memory stores and loads next to the operands, 17: issue tcgen05.ld of idle columns
+  if (mode >= 15 && mode <= 17 && warp >= 3) {
+    if (mode == 15) {
+      mbar_wait(&bar, 0);
+    } else if (mode == 16) {
+      uint4* q = reinterpret_cast<uint4*>(sm + 128 * 64 * 2 + 256 * 64 * 2) + (tid - 96);
+      uint4 v = make_uint4(tid, 0, 0, 0);
+      while (!mbar_try_wait(&bar, 0)) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          q[0] = v;
+          v.x += q[512 * (r & 1)].y;
+        }
+      }
+      if (v.x == 0x7fffffff) out[1] = 1;
+    } else {
+      const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 384 + 32 * ((warp - 3) >> 2 & 3);
+      float v[32], acc = 0.f;
+      while (!mbar_try_wait(&bar, 0)) {
+        tmem_ld32(ta, v);
+        tmem_ld_wait();
+        acc += v[0];
+      }
+      if (acc == 123.456f) out[1] = 1;
+    }
+  }
+  if (mode >= 14 && mode <= 17 && (warp == 1 || warp == 2)) {
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc = idesc_bf16(128, N);
     const uint32_t sa = smem_u32(sm), sb = sa + 128 * 64 * 2;
@@ -210,7 +355,7 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int mode, int N, int iter
     const long long t1 = clock64();
     if (blockIdx.x == 0 && tid == 32) out[0] = t1 - t0;
   }
-  if (mode >= 5 && mode != 13 && mode != 14 && warp == 1) {
+  if (mode >= 5 && mode != 13 && mode < 14 && warp == 1) {
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc = idesc_bf16(128, N);
     const uint32_t sb = smem_u32(sm) + 128 * 64 * 2;
@@ -292,11 +437,11 @@ extern "C" int desire_selftest_tsmma(const float* A, const float* B, float* out_
 }
 
 extern "C" int desire_selftest_mma_rate(int mode, int N, int iters, int grid, long long* out_cycles, desire_stream_t stream) {
-  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 14 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
+  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 23 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
                    "desire_selftest_mma_rate: bad arguments");
-  const size_t smem = 128 * 64 * 2 + 256 * 64 * 2;
+  const size_t smem = 128 * 64 * 2 + 256 * 64 * 2 + (mode == 16 || mode == 23 ? 1024 * 16 : 0);
   DESIRE_ENSURE_SMEM(desire::mma_rate_kernel, smem);
-  desire::mma_rate_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(mode, N, iters, out_cycles);
+  desire::mma_rate_kernel<<<grid, mode >= 15 ? 608 : 128, smem, (cudaStream_t)stream>>>(mode, N, iters, out_cycles);
   DESIRE_LAUNCH_CHECK();
   return DESIRE_OK;
 }

@@ -183,9 +183,14 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     constexpr uint32_t idesc = idesc_bf16(TM, H);
     constexpr uint32_t lbo_b = H * 16;
     const uint64_t d_ring = smem_desc(smem_u32(ring), lbo_b, 128);
-    int kb = 0;
     mbar_wait(lready, 0);
     const int nst = __popcll(active_bins(binmask));              // stages = bins that hold at least one pair of the tile
+    // The issuing warp must stay lean: every instruction between two blocks of MMAs is time in which the queue of the
+    // tensor pipe drains (ring slot and barrier phase are counted up, not divided out of a block counter: the division
+    // by the run-time ring length cost ~300 cycles per block and made this warp, not the tensor pipe, the bound).
+    uint32_t slot = 0, ph = 0;
+    uint64_t dsl = d_ring;
+    const uint32_t slot_adv = (uint32_t)L.slot_bytes >> 4;
     for (int g = 0; g < nst; ++g) {                              // (g counts stages here; the weights follow the bin list)
       const int as = g & 1;
       mbar_wait(&afull[as], (g >> 1) & 1);
@@ -194,10 +199,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       const uint32_t a_hi = tmem + 2 * H + as * H, a_lo = a_hi + H / 2;
       const uint32_t acc0 = g > 0;
 #pragma unroll
-      for (int c = 0; c < CPB; ++c, ++kb) {
-        const int slot = kb % nb;
-        const uint64_t dsl = desc_adv(d_ring, slot * (uint32_t)L.slot_bytes);
-        mbar_wait(&bfull[slot], (kb / nb) & 1);
+      for (int c = 0; c < CPB; ++c) {
+        mbar_wait(&bfull[slot], ph);
         tc_fence_after();
         if (elect_one()) {
           if (!(dbg & 4)) {
@@ -214,6 +217,12 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
           }
           mma_commit(&bempty[slot]);
           if (c == CPB - 1) mma_commit(&aempty[as]);
+        }
+        dsl += slot_adv;
+        if (++slot == (uint32_t)nb) {
+          slot = 0;
+          ph ^= 1;
+          dsl = d_ring;
         }
       }
       if (lane == 0) TRACE(16 + 8 * g + 6);
@@ -245,8 +254,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
             if (P3 && !(dbg & 16)) mma_bf16(t_p, desc_adv(ds, j * 2 * lbo_s), desc_adv(d_hl, j * 2 * lbo_b), idesc, 1);
           }
         }
-        mma_commit(pfull);
-        mma_commit(&sempty[sb]);
+        mma_commit(pfull);                                       // (also frees the selection matrix: see the builders)
       }
     }
     __syncwarp();
@@ -386,13 +394,20 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     const uint32_t t_p = tmem + lane_f + H + cg * CW;
     const uint32_t t_a = tmem + lane_f + 2 * H + cg * (CW / 2);
 
+    // The selection matrix of stage g + 2 is built inside stage g, in the time the finishers would otherwise spend
+    // waiting for the fc MMAs of stage g - 2: its buffer (g & 1) is free as soon as pool(g) is complete, which the
+    // pfull wait has just established — the pool issuer then never waits for a selection matrix.
     uint64_t rem = act;
     build(0, __ffsll((long long)rem) - 1);
     rem &= rem - 1;
+    if (nst > 1) {
+      build(1, __ffsll((long long)rem) - 1);
+      rem &= rem - 1;
+    }
+    const bool late_build = dbg & 512;                           // (timing experiment: build g + 2 at the top of stage g + 1)
     for (int g = 0; g < nst; ++g) {                              // stages
       if (tid == 0 && g < 36) TRACE(16 + 8 * g);
-      if (g + 1 < nst) {
-        if (g >= 1) mbar_wait(&sempty[(g + 1) & 1], ((g - 1) >> 1) & 1);     // pool(g-1) has read this buffer
+      if (late_build && g >= 1 && g + 1 < nst) {
         build(g + 1, __ffsll((long long)rem) - 1);
         rem &= rem - 1;
       }
@@ -421,6 +436,10 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       uint32_t hi[CW / 2], lo[CW / 2];
 #pragma unroll
       for (int i = 0; i < CW / 2; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+      if (!late_build && g + 2 < nst) {
+        build(g + 2, __ffsll((long long)rem) - 1);
+        rem &= rem - 1;
+      }
       if (tid == 0) TRACE(16 + 8 * g + 3);
       if (g >= 2) mbar_wait(&aempty[g & 1], ((g - 2) >> 1) & 1);             // fc(g-2) has read this stage
       tc_fence_after();

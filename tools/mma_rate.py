@@ -26,7 +26,18 @@ for it in range(2):
     torch.cuda.synchronize()
 print("cycles until the n-th MMA (N=128) was issued:", ", ".join("%d: %d" % (4 * k + 4, out[1 + k].item()) for k in range(16)))
 
-_lib.check(lib.desire_selftest_mma_rate(14, 128, 4000, 148, C.c_void_p(out.data_ptr()), None), "rate")
-_lib.check(lib.desire_selftest_mma_rate(14, 128, 4000, 148, C.c_void_p(out.data_ptr()), None), "rate")
-torch.cuda.synchronize()
-print("stage mix of the fused social kernel (24 TS + 16 SS MMAs, N=128, two issuing warps, nothing else running): %.0f cycles per stage (floor 2560)" % (out[0].item() / 100))
+for mode, what in ((14, "nothing else running"), (15, "16 more warps polling an mbarrier"),
+                   (16, "16 more warps streaming 16-byte shared-memory stores and loads"),
+                   (17, "16 more warps issuing tcgen05.ld on idle columns")):
+    for it in range(2):
+        _lib.check(lib.desire_selftest_mma_rate(mode, 128, 4000, 148, C.c_void_p(out.data_ptr()), None), "rate")
+    torch.cuda.synchronize()
+    print("stage mix of the fused social kernel (24 TS + 16 SS MMAs, N=128, two issuing warps, %s): %.0f cycles per stage (floor 2560)" % (what, out[0].item() / 100))
+
+for mode, what in ((18, "all of it"), (19, "handshakes only (no tcgen05.ld / st)"), (20, "fc MMAs in four blocks with a commit each"),
+                   (21, "P released after the conversion"), (22, "all of it + fence.proxy.async per thread and stage"),
+                   (23, "all of it + two 16-byte shared-memory stores and fence.proxy.async per thread and stage")):
+    for it in range(2):
+        _lib.check(lib.desire_selftest_mma_rate(mode, 128, 4000, 148, C.c_void_p(out.data_ptr()), None), "rate")
+    torch.cuda.synchronize()
+    print("stage protocol of the fused social kernel in miniature, %s: %.0f cycles per stage (floor 2560)" % (what, out[0].item() / 100))
