@@ -477,7 +477,8 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
       const bool p3 = a.passes == 3;
       mbar_wait(a_ready, 0);
       tc_fence_after();
-      uint32_t it = 0, use = 0;
+      uint32_t use = 0;
+      RingPos rp;
       for (int cg = 0; cg < ncg; ++cg) {
         for (int nt = 0; nt < nnt; ++nt, ++use) {
           const int ab = use & 1;
@@ -488,11 +489,11 @@ __global__ void __launch_bounds__(NTHR, 1) deconv_tc_kernel(DcArgs a) {
           const uint32_t d = tm + ab * 256;
           mbar_wait(&acc_empty[ab], ((use >> 1) & 1) ^ 1);
           tc_fence_after();
-          for (int ks = 0; ks < nks; ++ks, ++it) {
-            const int slot = it % a.nstg;
+          for (int ks = 0; ks < nks; ++ks, rp.next(a.nstg)) {
+            const uint32_t slot = rp.slot;
             const uint64_t db = desc_adv(d_b, slot * (uint32_t)SLOT);
             const uint64_t dah = desc_adv(d_ahi, ks * 4 * 2048), dal = desc_adv(d_alo, ks * 4 * 2048);
-            mbar_wait(&full[slot], (it / a.nstg) & 1);
+            mbar_wait(&full[slot], rp.ph);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll

@@ -321,9 +321,10 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
     float v0[KC][8], v1[KC][8];
     A.load_stage(ks_begin, v0);
     if (nks > 1) A.load_stage(ks_begin + 1, v1);
+    RingPos rp;                                                  // emit() is called for ks = 0, 1, 2, .. in order
     auto emit = [&](int ks, float (*v)[8]) {
-      const int slot = ks % stages;
-      const uint32_t ph = (ks / stages) & 1;
+      const uint32_t slot = rp.slot, ph = rp.ph;
+      rp.next(stages);
       mbar_wait(&empty[slot], ph ^ 1);
       uint8_t* sa = smem + (size_t)slot * stage_bytes;
 #pragma unroll
@@ -475,9 +476,9 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
       const uint64_t d_a = smem_desc(smem_u32(smem), lbo_a, 128), d_b = smem_desc(smem_u32(smem) + 2 * a_half, lbo_b, 128);
       const bool p3 = passes == 3;
       uint32_t acc_flag = 0;
-      for (int ks = 0; ks < nks; ++ks) {
-        const int slot = ks % stages;
-        const uint32_t ph = (ks / stages) & 1;
+      RingPos rp;
+      for (int ks = 0; ks < nks; ++ks, rp.next(stages)) {
+        const uint32_t slot = rp.slot, ph = rp.ph;
         const uint64_t da = desc_adv(d_a, slot * (uint32_t)stage_bytes), db = desc_adv(d_b, slot * (uint32_t)stage_bytes);
         mbar_wait(&full[slot], ph);
         tc_fence_after();
@@ -507,9 +508,9 @@ __global__ void __launch_bounds__(NTHR) gemm_tc_kernel(ALoad A_, const uint4* __
     // ===================== B loader: one bulk TMA copy per stage
     if (lane == 0) {
       const uint8_t* src = reinterpret_cast<const uint8_t*>(Bp) + ((size_t)jn * nks_total + ks_begin) * (2 * b_half);
-      for (int ks = 0; ks < nks; ++ks) {
-        const int slot = ks % stages;
-        const uint32_t ph = (ks / stages) & 1;
+      RingPos rp;
+      for (int ks = 0; ks < nks; ++ks, rp.next(stages)) {
+        const uint32_t slot = rp.slot, ph = rp.ph;
         mbar_wait(&empty[slot], ph ^ 1);
         mbar_arrive_expect_tx(&full[slot], 2 * b_half);
         bulk_g2s(smem + (size_t)slot * stage_bytes + 2 * a_half, src + (size_t)ks * (2 * b_half), 2 * b_half, &full[slot]);

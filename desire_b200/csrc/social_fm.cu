@@ -166,17 +166,17 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_fm_kernel(SocialFcArgs a, i
     constexpr uint32_t lbo_b = H * 16;
     const uint64_t d_ring = smem_desc(smem_u32(ring), lbo_b, 128);
     const uint32_t a_hi = tmem + A_COL, a_lo = a_hi + NC / 2;
-    int kb = 0;
+    RingPos rp;
     for (int sg = 0; sg < total; ++sg) {
       mbar_wait(afull, sg & 1);
       tc_fence_after();
       if (lane == 0 && sg < 60) TRACE(16 + 16 * sg + 8);
       const uint32_t acc0 = sg > 0;
 #pragma unroll
-      for (int j = 0; j < NC / 16; ++j, ++kb) {                  // 16-wide K steps = weight slots
-        const int slot = kb % nb;
+      for (int j = 0; j < NC / 16; ++j, rp.next(nb)) {           // 16-wide K steps = weight slots
+        const uint32_t slot = rp.slot;
         const uint64_t bhi = desc_adv(d_ring, slot * (uint32_t)L.slot_bytes), blo = desc_adv(bhi, b_blk / 2);
-        mbar_wait(&bfull[slot], (kb / nb) & 1);
+        mbar_wait(&bfull[slot], rp.ph);
         tc_fence_after();
         if (elect_one()) {
           mma_bf16_ts(tmem, a_hi + 8 * j, bhi, idesc, j == 0 ? acc0 : 1u);

@@ -55,7 +55,7 @@ __host__ __device__ inline Layout make_layout(int H, int Npad, int n_rad, int n_
   L.rowmap = off; off += TM * 8;
   off = (off + 15) / 16 * 16;
   L.tab = off; off += 24 * 4;                                   // 8 squared radial edges (+inf padded), 8 directions
-  L.bars = off; off += (2 * MAXNB + 12) * 8 + 48;              // barriers, tensor-memory slot, existence bits, bin mask
+  L.bars = off; off += (2 * MAXNB + 13) * 8 + 40;              // barriers, tensor-memory slot, existence bits, bin mask
   off = (off + 1023) / 1024 * 1024;
   L.slot_bytes = 2 * (size_t)4 * H * 16;                        // one packed block of 32 K values: hi + lo
   L.ring = off;
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
   uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* bempty = bfull + MAXNB;
   uint64_t* sfull = bempty + MAXNB;                  // [2] selection matrix written (16 warps)
-  uint64_t* sempty = sfull + 2;                      // [2] ... consumed by its pool MMAs (commit)
-  uint64_t* afull = sempty + 2;                      // [2] A stage written (16 warps)
+  uint64_t* pissued = sfull + 2;                     // [3] the pool MMAs of the next stage are in the queue (see the fc issuer)
+  uint64_t* afull = pissued + 3;                     // [2] A stage written (16 warps)
   uint64_t* aempty = afull + 2;                      // [2] ... consumed by its fc MMAs (commit)
   uint64_t* pfull = aempty + 2;                      // pool MMAs of a bin complete (commit)
   uint64_t* pempty = pfull + 1;                      // P read into registers (16 warps)
@@ -137,10 +137,10 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sfull[s], NPW);
-      mbar_init(&sempty[s], 1);
       mbar_init(&afull[s], NPW);
       mbar_init(&aempty[s], 1);
     }
+    for (int s = 0; s < 3; ++s) mbar_init(&pissued[s], 1);
     mbar_init(pfull, 1);
     mbar_init(pempty, NPW);
     mbar_init(tfull, 1);
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
         for (int c = 0; c < CPB; ++c, ++kb) {
           const int slot = kb % nb;
           mbar_wait_idle(&bempty[slot], ((kb / nb) & 1) ^ 1);
+          if (kb >= nb && kb - nb < 160) TRACE(400 + kb - nb);    // fc block kb - nb (6 MMAs) is complete
           if ((dbg & 2) && kb >= nb) {                           // timing experiment: no weight traffic after the first ring fill
             mbar_arrive(&bfull[slot]);
             continue;
@@ -188,12 +189,23 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     // The issuing warp must stay lean: every instruction between two blocks of MMAs is time in which the queue of the
     // tensor pipe drains (ring slot and barrier phase are counted up, not divided out of a block counter: the division
     // by the run-time ring length cost ~300 cycles per block and made this warp, not the tensor pipe, the bound).
-    uint32_t slot = 0, ph = 0;
+    uint32_t slot = 0, ph = 0, pi = 0, pph = 0;
     uint64_t dsl = d_ring;
+    const bool gate = !(dbg & 1024);                             // (1024: timing experiment, fc not held back)
     const uint32_t slot_adv = (uint32_t)L.slot_bytes >> 4;
     for (int g = 0; g < nst; ++g) {                              // (g counts stages here; the weights follow the bin list)
       const int as = g & 1;
       mbar_wait(&afull[as], (g >> 1) & 1);
+      // The queue of the tensor pipe is first-in first-out and a dozen MMAs deep.  pool(g+1) is on the critical chain
+      // (P is single-buffered: pool -> finishers' tcgen05.ld -> pool), fc(g) is not: fc(g) queues up behind pool(g+1)
+      // and runs while P(g+1) is handed over, instead of sitting in front of it.
+      // (three barriers in turn: the pool issuer can be two announcements ahead of this wait, not three — the third needs
+      // aempty of this very stage)
+      if (gate && g + 1 < nst) mbar_wait(&pissued[pi], pph);
+      if (++pi == 3) {
+        pi = 0;
+        pph ^= 1;
+      }
       tc_fence_after();
       if (lane == 0) TRACE(16 + 8 * g + 5);
       const uint32_t a_hi = tmem + 2 * H + as * H, a_lo = a_hi + H / 2;
@@ -240,6 +252,7 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     const uint64_t d_hh = smem_desc(smem_u32(ht), lbo_b, 128), d_hl = desc_adv(d_hh, H * TM * 2);
     mbar_wait(lready, 0);
     const int nst = __popcll(active_bins(binmask));
+    uint32_t pi = 0;
     for (int g = 0; g < nst; ++g) {                              // stages
       const int sb = g & 1;
       const uint64_t ds = desc_adv(d_s0, sb * (TM * TM * 2));
@@ -255,7 +268,9 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
           }
         }
         mma_commit(pfull);                                       // (also frees the selection matrix: see the builders)
+        if (g > 0) mbar_arrive(&pissued[pi]);
       }
+      if (g > 0 && ++pi == 3) pi = 0;
     }
     __syncwarp();
   } else {
@@ -394,20 +409,15 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
     const uint32_t t_p = tmem + lane_f + H + cg * CW;
     const uint32_t t_a = tmem + lane_f + 2 * H + cg * (CW / 2);
 
-    // The selection matrix of stage g + 2 is built inside stage g, in the time the finishers would otherwise spend
-    // waiting for the fc MMAs of stage g - 2: its buffer (g & 1) is free as soon as pool(g) is complete, which the
-    // pfull wait has just established — the pool issuer then never waits for a selection matrix.
+    // The selection matrix of stage g + 1 is built at the top of stage g: its buffer was read by pool(g-1), which the
+    // pfull wait of stage g - 1 has shown to be complete.  (Building it two stages ahead, in the time the finishers wait
+    // for the fc MMAs of stage g - 2, measured 2-4 % slower: the stores then coincide with the pool MMAs' operand reads.)
     uint64_t rem = act;
     build(0, __ffsll((long long)rem) - 1);
     rem &= rem - 1;
-    if (nst > 1) {
-      build(1, __ffsll((long long)rem) - 1);
-      rem &= rem - 1;
-    }
-    const bool late_build = dbg & 512;                           // (timing experiment: build g + 2 at the top of stage g + 1)
     for (int g = 0; g < nst; ++g) {                              // stages
       if (tid == 0 && g < 36) TRACE(16 + 8 * g);
-      if (late_build && g >= 1 && g + 1 < nst) {
+      if (g + 1 < nst) {
         build(g + 1, __ffsll((long long)rem) - 1);
         rem &= rem - 1;
       }
@@ -436,10 +446,6 @@ __global__ void __launch_bounds__(NTHR, 1) social_fc_ts_kernel(SocialFcArgs a, i
       uint32_t hi[CW / 2], lo[CW / 2];
 #pragma unroll
       for (int i = 0; i < CW / 2; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-      if (!late_build && g + 2 < nst) {
-        build(g + 2, __ffsll((long long)rem) - 1);
-        rem &= rem - 1;
-      }
       if (tid == 0) TRACE(16 + 8 * g + 3);
       if (g >= 2) mbar_wait(&aempty[g & 1], ((g - 2) >> 1) & 1);             // fc(g-2) has read this stage
       tc_fence_after();
@@ -571,6 +577,10 @@ int social_fc_ts(const SocialFcArgs& a, cudaStream_t st) {
         fprintf(stderr, "  stage %2d: start %7lld build-next %6lld wait-pool %5lld ld+convert %6lld wait+st+arrive %5lld | mma: afull at %7lld fc issue %5lld\n",
                 g, e[0] - t0, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - t0, e[6] - e[5]);
       }
+      fprintf(stderr, "  completion of the fc blocks (6 MMAs each; cycles from start), four per stage:\n");
+      for (int g = 0; g < G; ++g)
+        fprintf(stderr, "  stage %2d: %7lld %7lld %7lld %7lld | pool complete (seen by warp 0) %7lld\n", g, h[400 + 4 * g] - t0,
+                h[401 + 4 * g] - t0, h[402 + 4 * g] - t0, h[403 + 4 * g] - t0, h[16 + 8 * g + 2] - t0);
     }
   }
   return DESIRE_OK;

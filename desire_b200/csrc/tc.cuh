@@ -34,6 +34,19 @@ __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Position in a ring of n slots with the mbarrier phase of the current lap, counted up: `it % n` and `it / n` with a
+// run-time n are ~20 dependent integer instructions each, which an MMA-issuing warp cannot afford between two blocks of
+// MMAs (social_ts.cu: that division, not the tensor pipe, bounded the kernel).
+struct RingPos {
+  uint32_t slot = 0, ph = 0;
+  __device__ __forceinline__ void next(uint32_t n) {
+    if (++slot == n) {
+      slot = 0;
+      ph ^= 1;
+    }
+  }
+};
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
