@@ -1,1 +1,2 @@
-DESIRE_SOCIAL_DBG=512 DESIRE_SOCIAL_TRACE=1 timeout 60 python tools/bench_social.py > gpurun_out/ts_trace7.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r2_final_gputests.txt; cat gpurun_out/r2_final_gputests.txt
+bash tools/r2z.sh
