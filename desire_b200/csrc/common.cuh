@@ -155,6 +155,11 @@ int sgemm(const float* A, int lda, const float* B, int ldb, bool trans_b, const 
           int ldc, int M, int N, int K, int act, bool accumulate, cudaStream_t st, PackWs pw = PackWs());
 int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const float* bias, float* C,
                  int ldc, int M, int N, int K, int act, cudaStream_t st, PackWs pw = PackWs());
+// conv5_tc.cu: 5x5 / stride 1 / SAME convolution over NHWC as an implicit GEMM on tcgen05 (the input tile is staged once
+// as the A operand; a filter tap is a start-address shift).  X [B, H, W, Cin], w [(ky, kx, ci), n] (ldb), Y [B, H, W, ldc].
+bool conv5_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs& pw);
+int conv5_tc(const float* X, const Im2col& g, int B, const float* w, int ldb, const float* bias, float* Y, int ldc, int Cout,
+             int act, cudaStream_t st, PackWs pw);
 // train step (gemm_f32.cu): dW[Kd,N] (ldw) += A^T @ B over M rows, A dense or implicit im2col; column sums
 // wp: scratch for the packed BF16 image of B (wgrad_tc_pack_bytes(M, N)); with it (and gemm mode != 0, Kd >= 64,
 // N >= 16, M >= 2048) the product runs on tcgen05 (gemm_tc.cu, split-K + atomics), otherwise on FP32 CUDA cores.

@@ -1,0 +1,272 @@
+// 5x5, stride-1, SAME convolution (+ bias + ReLU) over NHWC FP32 maps as an IMPLICIT GEMM on tcgen05: the scene CNN's
+// second and third layer (DESIGN D13: the reference leaves stage 2 unbuilt, model/model.py:312-313).
+//
+// Why not im2col (gemm_tc.cu, Im2colA8): every output pixel re-reads its 25 x Cin receptive field, 3.2 KB per pixel at
+// Cin = 32 — 2.5 GB of L2 -> SM traffic for the two layers of a 32-image batch, and the A producers (thread = row, 32-byte
+// reads) are what the kernel waits for: 0.03 of the tensor peak.
+//
+// Here the input tile (TH + 4 rows x TW + 4 columns, zero halo) is staged ONCE in shared memory as the K-major A operand
+// itself: pixel p = row * WP + col of the padded tile is operand row p, its Cin channels are the K dimension (BF16 hi and
+// lo images, 8-channel chunks LBO apart, 16 bytes per row, SBO = 128: with SWIZZLE_NONE the operand's row address is LINEAR
+// in the row index).  The receptive-field shift of filter tap (ky, kx) is then nothing but a different START ADDRESS:
+//     D[p, :] += A[p + ky*WP + kx, :] @ W[ky, kx]        for all 25 taps, p = 128 consecutive padded positions per MMA
+// so the whole convolution is 25 x (Cin/16) x 3 MMAs per 128 positions with NO data movement between taps.  Positions in
+// the 4 halo columns of each row are computed and dropped (128/132 useful).  The accumulators of all MT = 8 position
+// tiles of a CTA live in tensor memory (MT x Cout columns), so each tap's weights (a 4 KB bulk-TMA slot) are used by all
+// eight tiles before the next tap is needed.
+//   warps 0-15  stage the tile (FP32 -> BF16 hi/lo), later the epilogue (tcgen05.ld, bias, ReLU, 128-byte pixel rows)
+//   warp 16     issues the MMAs (elected lane, warp-uniform operands), warp 17 streams the packed taps
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace desire {
+namespace {
+
+using namespace tc;
+
+constexpr int C5_TH = 7, C5_TW = 128, C5_WP = C5_TW + 4, C5_MT = 8;
+constexpr int C5_NPIX = (C5_TH + 4) * C5_WP;                    // 1452 staged pixels
+constexpr int C5_NPIXA = (C5_NPIX + 7) / 8 * 8;                 // rows per K chunk of the operand image
+constexpr int C5_LBO = C5_NPIXA * 16;
+constexpr int C5_PW = 16, C5_PT = C5_PW * 32;                   // staging / epilogue warps
+constexpr int C5_NTHR = (C5_PW + 2) * 32;
+constexpr int C5_NSLOT = 4;
+static_assert(C5_TH * C5_WP <= C5_MT * 128, "position tiles cover the tile");
+
+struct C5Args {
+  const float* X;
+  const uint8_t* packed;                 // [25][hi | lo][Cin/8][Cout][8] BF16
+  const float* bias;
+  float* Y;
+  int B, H, W, Cin, Cout, ldc, act, passes;
+};
+
+__global__ void c5_pack_kernel(const float* __restrict__ w, int ldb, int Cin, int Cout, uint8_t* __restrict__ packed) {
+  // w[(tap*Cin + ci)*ldb + n]  ->  packed[tap][half][ci/8][n][ci%8]
+  const int total = 25 * Cin * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i % Cout, t = i / Cout, ci = t % Cin, tap = t / Cin;
+    const float x = __ldg(w + (size_t)(tap * Cin + ci) * ldb + n);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    const size_t half = (size_t)Cin * Cout * 2;
+    const size_t o = (size_t)tap * 2 * half + (size_t)(ci >> 3) * Cout * 16 + (size_t)n * 16 + (ci & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(packed + o) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(packed + o + half) = lo;
+  }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
+  constexpr int CK = CIN / 8;                                    // 8-channel K chunks
+  constexpr int IMG = CK * C5_LBO;                               // bytes of one (hi or lo) operand image
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = smem + IMG;
+  const int Cout = a.Cout;
+  const uint32_t b_half = (uint32_t)CIN * Cout * 2, slot_bytes = 2 * b_half;
+  uint8_t* ring = smem + 2 * IMG;
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(ring + C5_NSLOT * slot_bytes);
+  uint64_t* wempty = wfull + C5_NSLOT;
+  uint64_t* a_ready = wempty + C5_NSLOT;
+  uint64_t* tfull = a_ready + 1;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = blockIdx.x * C5_TW, y0 = blockIdx.y * C5_TH, img = blockIdx.z;
+  const uint32_t tcols = (uint32_t)(C5_MT * Cout);              // 128, 256 or 512
+
+  if (tid == 0) {
+    for (int s = 0; s < C5_NSLOT; ++s) {
+      mbar_init(&wfull[s], 1);
+      mbar_init(&wempty[s], 1);
+    }
+    mbar_init(a_ready, C5_PW);
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == C5_PW) tmem_alloc_dyn(tslot, tcols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  if (warp == C5_PW + 1) {
+    // ===================== tap loader
+    if (lane == 0) {
+      RingPos rp;
+      for (int tap = 0; tap < 25; ++tap, rp.next(C5_NSLOT)) {
+        mbar_wait(&wempty[rp.slot], rp.ph ^ 1);
+        mbar_arrive_expect_tx(&wfull[rp.slot], slot_bytes);
+        bulk_g2s_hint(ring + (size_t)rp.slot * slot_bytes, a.packed + (size_t)tap * slot_bytes, slot_bytes, &wfull[rp.slot],
+                      L2_EVICT_LAST);
+      }
+    }
+  } else if (warp == C5_PW) {
+    // ===================== MMA issuer
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = idesc_bf16(128, Cout);
+    const uint32_t lbo_b = (uint32_t)Cout * 16;
+    const uint64_t d_ah = smem_desc(smem_u32(a_hi), C5_LBO, 128), d_al = smem_desc(smem_u32(a_lo), C5_LBO, 128);
+    const uint64_t d_ring = smem_desc(smem_u32(ring), lbo_b, 128);
+    const bool p3 = a.passes == 3;
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    RingPos rp;
+    int ky = 0, kx = 0;
+    for (int tap = 0; tap < 25; ++tap, rp.next(C5_NSLOT)) {
+      const uint64_t db = desc_adv(d_ring, rp.slot * slot_bytes);
+      const uint32_t shift = (uint32_t)(ky * C5_WP + kx) * 16;    // the tap: a start address, nothing else
+      const uint64_t dah = desc_adv(d_ah, shift), dal = desc_adv(d_al, shift);
+      mbar_wait(&wfull[rp.slot], rp.ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int mt = 0; mt < C5_MT; ++mt) {
+          const uint32_t d = tm + (uint32_t)(mt * Cout);
+#pragma unroll
+          for (int ks = 0; ks < CK / 2; ++ks) {
+            const uint64_t ah = desc_adv(dah, mt * 128 * 16 + ks * 2 * C5_LBO), al = desc_adv(dal, mt * 128 * 16 + ks * 2 * C5_LBO);
+            const uint64_t bh = desc_adv(db, ks * 2 * lbo_b), bl = desc_adv(db, b_half + ks * 2 * lbo_b);
+            mma_bf16(d, ah, bh, idesc, (tap > 0 || ks > 0) ? 1u : 0u);
+            if (p3) {
+              mma_bf16(d, al, bh, idesc, 1);
+              mma_bf16(d, ah, bl, idesc, 1);
+            }
+          }
+        }
+        mma_commit(&wempty[rp.slot]);
+        if (tap == 24) mma_commit(tfull);
+      }
+      if (++kx == 5) {
+        kx = 0;
+        ++ky;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== stage the tile: item = (pixel, 8-channel chunk); a warp reads 8 pixels x CIN*4 contiguous bytes
+    {
+      constexpr int ITEMS = C5_NPIX * CK;
+      const float* xin = a.X + (size_t)img * a.H * a.W * CIN;
+      constexpr int U = 4;
+      for (int i0 = tid; i0 < ITEMS; i0 += U * C5_PT) {
+        float v[U][8];
+        int pix[U], q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int item = i0 + u * C5_PT;
+          pix[u] = item / CK;
+          q[u] = item - pix[u] * CK;
+          const int r = pix[u] / C5_WP, c = pix[u] - r * C5_WP;
+          const int iy = y0 - 2 + r, ix = x0 - 2 + c;
+          const bool ok = item < ITEMS && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+          float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+          if (ok) {
+            const float4* p = reinterpret_cast<const float4*>(xin + ((size_t)iy * a.W + ix) * CIN + q[u] * 8);
+            f0 = __ldg(p);
+            f1 = __ldg(p + 1);
+          }
+          v[u][0] = f0.x; v[u][1] = f0.y; v[u][2] = f0.z; v[u][3] = f0.w;
+          v[u][4] = f1.x; v[u][5] = f1.y; v[u][6] = f1.z; v[u][7] = f1.w;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (i0 + u * C5_PT < ITEMS) {
+            const Split8 s = split8(v[u]);
+            const size_t o = (size_t)q[u] * C5_LBO + (size_t)pix[u] * 16;
+            *reinterpret_cast<uint4*>(a_hi + o) = s.hi;
+            *reinterpret_cast<uint4*>(a_lo + o) = s.lo;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    // ===================== epilogue: warp w reads TMEM lanes 32*(w%4).. of position tiles w/4 and w/4 + 4
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int q4 = warp & 3;
+#pragma unroll 1
+    for (int j = 0; j < C5_MT / 4; ++j) {
+      const int mt = (warp >> 2) + 4 * j;
+      const int p = mt * 128 + 32 * q4 + lane;
+      const int r = p / C5_WP, c = p - r * C5_WP;
+      const int oy = y0 + r, ox = x0 + c;
+      const bool ok = r < C5_TH && c < C5_TW && oy < a.H && ox < a.W;
+      float* dst = a.Y + (((size_t)img * a.H + oy) * a.W + ox) * a.ldc;
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(mt * Cout);
+#pragma unroll 1
+      for (int n0 = 0; n0 < Cout; n0 += 16) {
+        float acc[16];
+        tmem_ld16(taddr + n0, acc);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 y = make_float4(acc[e] + b4.x, acc[e + 1] + b4.y, acc[e + 2] + b4.z, acc[e + 3] + b4.w);
+            if (a.act == DESIRE_ACT_RELU) {
+              y.x = fmaxf(y.x, 0.f);
+              y.y = fmaxf(y.y, 0.f);
+              y.z = fmaxf(y.z, 0.f);
+              y.w = fmaxf(y.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(dst + n0 + e) = y;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C5_PW) tmem_dealloc(tmem, tcols);
+}
+
+size_t c5_smem(int Cin, int Cout) {
+  return (size_t)2 * (Cin / 8) * C5_LBO + (size_t)C5_NSLOT * 4 * Cin * Cout + (2 * C5_NSLOT + 2) * 8 + 16;
+}
+
+}  // namespace
+
+size_t conv5_tc_pack_bytes(int Cin, int Cout) { return (size_t)25 * 4 * Cin * Cout; }
+
+// 5x5 / stride 1 / SAME over NHWC, Cin in {16, 32}, Cout in {16, 32, 64}, bias 16-byte aligned, act NONE or RELU
+bool conv5_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs& pw) {
+  static const bool off = [] {
+    const char* e = getenv("DESIRE_NO_CONV5");
+    return e && e[0] == '1';
+  }();
+  if (off || gemm_mode() == 0) return false;
+  return g.kh == 5 && g.kw == 5 && g.stride == 1 && g.pad_t == 2 && g.pad_l == 2 && g.Hi == g.Ho && g.Wi == g.Wo &&
+         (g.Ci == 16 || g.Ci == 32) && (Cout == 16 || Cout == 32 || Cout == 64) && ldc % 4 == 0 &&
+         (act == DESIRE_ACT_NONE || act == DESIRE_ACT_RELU) && pw.p && pw.bytes >= conv5_tc_pack_bytes(g.Ci, Cout) &&
+         g.Ho <= 65535 * C5_TH;
+}
+
+int conv5_tc(const float* X, const Im2col& g, int B, const float* w, int ldb, const float* bias, float* Y, int ldc, int Cout,
+             int act, cudaStream_t st, PackWs pw) {
+  if (B <= 0) return DESIRE_OK;
+  DESIRE_CHECK_ARG(conv5_tc_eligible(g, Cout, ldc, act, pw) && B <= 65535, "conv5_tc: not eligible");
+  DESIRE_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
+                       (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+                   "conv5_tc: X, Y and bias must be 16-byte aligned");
+  uint8_t* packed = reinterpret_cast<uint8_t*>(pw.p);
+  DESIRE_LAUNCH(st, (c5_pack_kernel<<<std::min(148, (25 * g.Ci * Cout + 255) / 256), 256, 0, st>>>(w, ldb, g.Ci, Cout, packed)));
+  C5Args a{X, packed, bias, Y, B, g.Hi, g.Wi, g.Ci, Cout, ldc, act, gemm_mode() == 1 ? 1 : 3};
+  const dim3 grid((unsigned)((g.Wi + C5_TW - 1) / C5_TW), (unsigned)((g.Hi + C5_TH - 1) / C5_TH), (unsigned)B);
+  const size_t smem = c5_smem(g.Ci, Cout);
+  if (g.Ci == 16) {
+    DESIRE_ENSURE_SMEM(conv5_tc_kernel<16>, smem);
+    DESIRE_LAUNCH(st, (conv5_tc_kernel<16><<<grid, C5_NTHR, smem, st>>>(a)));
+  } else {
+    DESIRE_ENSURE_SMEM(conv5_tc_kernel<32>, smem);
+    DESIRE_LAUNCH(st, (conv5_tc_kernel<32><<<grid, C5_NTHR, smem, st>>>(a)));
+  }
+  return DESIRE_OK;
+}
+
+}  // namespace desire

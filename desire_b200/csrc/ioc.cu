@@ -505,12 +505,19 @@ extern "C" int desire_scene_cnn_fwd(const float* img, int B, int Hi, int Wi, int
     Im2col g1{Hi, Wi, 3, Ho, Wo, 5, 5, 2, pt1, pl1};
     DESIRE_TRY(sgemm_im2col(img + (size_t)b * Hi * Wi * 3, g1, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, M, 16, 75,
                             DESIRE_ACT_RELU, st, pw));
+    // layers 2 and 3: the tile-resident implicit GEMM (conv5_tc.cu) where it applies, im2col GEMM otherwise
     Im2col g2{Ho, Wo, 16, Ho, Wo, 5, 5, 1, 2, 2};
-    DESIRE_TRY(sgemm_im2col(f1 + b * px * 16, g2, w->c2_w, 32, w->c2_b, f2 + b * px * 32, 32, M, 32, 400, DESIRE_ACT_RELU,
-                            st, pw));
+    if (conv5_tc_eligible(g2, 32, 32, DESIRE_ACT_RELU, pw))
+      DESIRE_TRY(conv5_tc(f1 + b * px * 16, g2, nb, w->c2_w, 32, w->c2_b, f2 + b * px * 32, 32, 32, DESIRE_ACT_RELU, st, pw));
+    else
+      DESIRE_TRY(sgemm_im2col(f1 + b * px * 16, g2, w->c2_w, 32, w->c2_b, f2 + b * px * 32, 32, M, 32, 400, DESIRE_ACT_RELU,
+                              st, pw));
     Im2col g3{Ho, Wo, 32, Ho, Wo, 5, 5, 1, 2, 2};
-    DESIRE_TRY(sgemm_im2col(f2 + b * px * 32, g3, w->c3_w, Cs, w->c3_b, fmap + b * px * Cs, Cs, M, Cs, 800, DESIRE_ACT_RELU,
-                            st, pw));
+    if (conv5_tc_eligible(g3, Cs, Cs, DESIRE_ACT_RELU, pw))
+      DESIRE_TRY(conv5_tc(f2 + b * px * 32, g3, nb, w->c3_w, Cs, w->c3_b, fmap + b * px * Cs, Cs, Cs, DESIRE_ACT_RELU, st, pw));
+    else
+      DESIRE_TRY(sgemm_im2col(f2 + b * px * 32, g3, w->c3_w, Cs, w->c3_b, fmap + b * px * Cs, Cs, M, Cs, 800, DESIRE_ACT_RELU,
+                              st, pw));
   }
   return DESIRE_OK;
 }
