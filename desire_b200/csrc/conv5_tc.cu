@@ -10,10 +10,11 @@
 // lo images, 8-channel chunks LBO apart, 16 bytes per row, SBO = 128: with SWIZZLE_NONE the operand's row address is LINEAR
 // in the row index).  The receptive-field shift of filter tap (ky, kx) is then nothing but a different START ADDRESS:
 //     D[p, :] += A[p + ky*WP + kx, :] @ W[ky, kx]        for all 25 taps, p = 128 consecutive padded positions per MMA
-// so the whole convolution is 25 x (Cin/16) x 3 MMAs per 128 positions with NO data movement between taps.  Positions in
-// the 4 halo columns of each row are computed and dropped (128/132 useful).  The accumulators of all MT = 8 position
-// tiles of a CTA live in tensor memory (MT x Cout columns), so each tap's weights (a 4 KB bulk-TMA slot) are used by all
-// eight tiles before the next tap is needed.
+// so the whole convolution is 25 x (Cin/16) x 2 MMAs per 128 positions (3xBF16 with the weights' hi and lo images as ONE
+// B operand, see the issuer) with NO data movement between taps.  Positions in the 4 halo columns of each row are computed
+// and dropped (128/132 useful).  The accumulators of all MT = 8 position tiles of a CTA live in tensor memory
+// (MT x 2*Cout columns), so each tap's weights (a 4 KB bulk-TMA slot) are used by all eight tiles before the next tap is
+// needed.  (tools/mma_rate_n.py: a start address anywhere inside a core matrix costs nothing.)
 //   warps 0-15  stage the tile (FP32 -> BF16 hi/lo), later the epilogue (tcgen05.ld, bias, ReLU, 128-byte pixel rows)
 //   warp 16     issues the MMAs (elected lane, warp-uniform operands), warp 17 streams the packed taps
 #include <stdlib.h>
@@ -37,24 +38,25 @@ static_assert(C5_TH * C5_WP <= C5_MT * 128, "position tiles cover the tile");
 
 struct C5Args {
   const float* X;
-  const uint8_t* packed;                 // [25][hi | lo][Cin/8][Cout][8] BF16
+  const uint8_t* packed;                 // [25][Cin/8][hi rows | lo rows][8] BF16
   const float* bias;
   float* Y;
   int B, H, W, Cin, Cout, ldc, act, passes;
+  long long* trace;                      // DESIRE_CONV5_TRACE=1: clock64() milestones of block (0, 0, 0)
 };
 
 __global__ void c5_pack_kernel(const float* __restrict__ w, int ldb, int Cin, int Cout, uint8_t* __restrict__ packed) {
-  // w[(tap*Cin + ci)*ldb + n]  ->  packed[tap][half][ci/8][n][ci%8]
+  // w[(tap*Cin + ci)*ldb + n]  ->  packed[tap][ci/8][n' = n (hi) | Cout + n (lo)][ci%8]: one B operand of 2*Cout rows
   const int total = 25 * Cin * Cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i % Cout, t = i / Cout, ci = t % Cin, tap = t / Cin;
     const float x = __ldg(w + (size_t)(tap * Cin + ci) * ldb + n);
     const __nv_bfloat16 hi = __float2bfloat16_rn(x);
     const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-    const size_t half = (size_t)Cin * Cout * 2;
-    const size_t o = (size_t)tap * 2 * half + (size_t)(ci >> 3) * Cout * 16 + (size_t)n * 16 + (ci & 7) * 2;
+    const size_t slot = (size_t)4 * Cin * Cout;
+    const size_t o = (size_t)tap * slot + (size_t)(ci >> 3) * (2 * Cout * 16) + (size_t)n * 16 + (ci & 7) * 2;
     *reinterpret_cast<__nv_bfloat16*>(packed + o) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(packed + o + half) = lo;
+    *reinterpret_cast<__nv_bfloat16*>(packed + o + (size_t)Cout * 16) = lo;
   }
 }
 
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
   uint8_t* a_hi = smem;
   uint8_t* a_lo = smem + IMG;
   const int Cout = a.Cout;
-  const uint32_t b_half = (uint32_t)CIN * Cout * 2, slot_bytes = 2 * b_half;
+  const uint32_t slot_bytes = (uint32_t)4 * CIN * Cout;
   uint8_t* ring = smem + 2 * IMG;
   uint64_t* wfull = reinterpret_cast<uint64_t*>(ring + C5_NSLOT * slot_bytes);
   uint64_t* wempty = wfull + C5_NSLOT;
@@ -76,7 +78,13 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int x0 = blockIdx.x * C5_TW, y0 = blockIdx.y * C5_TH, img = blockIdx.z;
-  const uint32_t tcols = (uint32_t)(C5_MT * Cout);              // 128, 256 or 512
+  const uint32_t tcols = (uint32_t)(C5_MT * 2 * Cout);          // 256 or 512: [hi x (hi | lo)] per position tile
+  // the last row tile of a map may hold fewer rows: only the position tiles that contain one of its pixels are computed
+  const int rows = min(C5_TH, a.H - y0);
+  const int mt_used = (rows * C5_WP + 127) / 128;
+  const bool tr = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define TRACE(i) do { if (tr) a.trace[i] = clock64(); } while (0)
+  if (tid == 0) TRACE(0);
 
   if (tid == 0) {
     for (int s = 0; s < C5_NSLOT; ++s) {
@@ -92,6 +100,7 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
+  if (tid == 0) TRACE(1);
 
   if (warp == C5_PW + 1) {
     // ===================== tap loader
@@ -107,13 +116,18 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
   } else if (warp == C5_PW) {
     // ===================== MMA issuer
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t idesc = idesc_bf16(128, Cout);
-    const uint32_t lbo_b = (uint32_t)Cout * 16;
+    // 3xBF16 in TWO MMAs per K step: the weights' hi and lo images are one B operand of 2*Cout rows, so
+    //   D[:, 0:2C] += A_hi @ [B_hi | B_lo]   (N = 2C)      D[:, 0:C] += A_lo @ B_hi   (N = C)
+    // and the epilogue adds the two column halves.  With both operands in shared memory an MMA costs 32 + N/4 cycles
+    // (tools/mma_rate_n.py: the 4 KB A read dominates), so 48 + 40 cycles replace 3 x 40.
+    const uint32_t idesc2 = idesc_bf16(128, 2 * Cout), idesc1 = idesc_bf16(128, Cout);
+    const uint32_t lbo_b = (uint32_t)2 * Cout * 16;
     const uint64_t d_ah = smem_desc(smem_u32(a_hi), C5_LBO, 128), d_al = smem_desc(smem_u32(a_lo), C5_LBO, 128);
     const uint64_t d_ring = smem_desc(smem_u32(ring), lbo_b, 128);
     const bool p3 = a.passes == 3;
     mbar_wait(a_ready, 0);
     tc_fence_after();
+    if (lane == 0) TRACE(3);
     RingPos rp;
     int ky = 0, kx = 0;
     for (int tap = 0; tap < 25; ++tap, rp.next(C5_NSLOT)) {
@@ -125,33 +139,38 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
       if (elect_one()) {
 #pragma unroll
         for (int mt = 0; mt < C5_MT; ++mt) {
-          const uint32_t d = tm + (uint32_t)(mt * Cout);
+          if (mt >= mt_used) break;
+          const uint32_t d = tm + (uint32_t)(mt * 2 * Cout);
 #pragma unroll
           for (int ks = 0; ks < CK / 2; ++ks) {
             const uint64_t ah = desc_adv(dah, mt * 128 * 16 + ks * 2 * C5_LBO), al = desc_adv(dal, mt * 128 * 16 + ks * 2 * C5_LBO);
-            const uint64_t bh = desc_adv(db, ks * 2 * lbo_b), bl = desc_adv(db, b_half + ks * 2 * lbo_b);
-            mma_bf16(d, ah, bh, idesc, (tap > 0 || ks > 0) ? 1u : 0u);
+            const uint64_t b = desc_adv(db, ks * 2 * lbo_b);
+            const uint32_t acc = (tap > 0 || ks > 0) ? 1u : 0u;
             if (p3) {
-              mma_bf16(d, al, bh, idesc, 1);
-              mma_bf16(d, ah, bl, idesc, 1);
+              mma_bf16(d, ah, b, idesc2, acc);
+              mma_bf16(d, al, b, idesc1, 1);
+            } else {
+              mma_bf16(d, ah, b, idesc1, acc);
             }
           }
         }
         mma_commit(&wempty[rp.slot]);
         if (tap == 24) mma_commit(tfull);
       }
+      if (lane == 0 && tap == 0) TRACE(4);
       if (++kx == 5) {
         kx = 0;
         ++ky;
       }
     }
+    if (lane == 0) TRACE(5);
     __syncwarp();
   } else {
     // ===================== stage the tile: item = (pixel, 8-channel chunk); a warp reads 8 pixels x CIN*4 contiguous bytes
     {
-      constexpr int ITEMS = C5_NPIX * CK;
+      const int ITEMS = (rows + 4) * C5_WP * CK;
       const float* xin = a.X + (size_t)img * a.H * a.W * CIN;
-      constexpr int U = 4;
+      constexpr int U = 6;
       for (int i0 = tid; i0 < ITEMS; i0 += U * C5_PT) {
         float v[U][8];
         int pix[U], q[U];
@@ -185,45 +204,69 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
+      if (tid == 0) TRACE(2);
     }
     // ===================== epilogue: warp w reads TMEM lanes 32*(w%4).. of position tiles w/4 and w/4 + 4
     mbar_wait(tfull, 0);
     tc_fence_after();
+    if (tid == 0) TRACE(6);
+    // thread = position (TMEM lane): add the halves, bias, ReLU, park the 32 x Cout patch in shared memory (the operand
+    // images are dead; pitch Cout*4 + 16 bytes keeps the 16-byte accesses conflict-free), then write it out with lanes
+    // along the channels: 512 contiguous bytes per store instruction instead of 32 half-used sectors
     const int q4 = warp & 3;
+    const bool p3 = a.passes == 3;
+    const uint32_t pitch = (uint32_t)Cout * 4 + 16;
+    uint8_t* patch = smem + (size_t)warp * 32 * (32 * 4 + 16);   // 16 x 4.5 KB < the smaller operand image pair (91 KB)
+    const int cpr = Cout / 4, rpi = 32 / cpr;                    // 16-byte chunks per row, rows per store instruction
 #pragma unroll 1
     for (int j = 0; j < C5_MT / 4; ++j) {
       const int mt = (warp >> 2) + 4 * j;
-      const int p = mt * 128 + 32 * q4 + lane;
-      const int r = p / C5_WP, c = p - r * C5_WP;
-      const int oy = y0 + r, ox = x0 + c;
-      const bool ok = r < C5_TH && c < C5_TW && oy < a.H && ox < a.W;
-      float* dst = a.Y + (((size_t)img * a.H + oy) * a.W + ox) * a.ldc;
-      const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(mt * Cout);
+      if (mt >= mt_used) break;                                  // (warp-uniform)
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(mt * 2 * Cout);
 #pragma unroll 1
       for (int n0 = 0; n0 < Cout; n0 += 16) {
-        float acc[16];
+        float acc[16], acl[16];
         tmem_ld16(taddr + n0, acc);
+        if (p3) tmem_ld16(taddr + Cout + n0, acl);
         tmem_ld_wait();
-        if (ok) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 y = make_float4(acc[e] + b4.x, acc[e + 1] + b4.y, acc[e + 2] + b4.z, acc[e + 3] + b4.w);
-            if (a.act == DESIRE_ACT_RELU) {
-              y.x = fmaxf(y.x, 0.f);
-              y.y = fmaxf(y.y, 0.f);
-              y.z = fmaxf(y.z, 0.f);
-              y.w = fmaxf(y.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(dst + n0 + e) = y;
+        for (int e = 0; e < 16; e += 4) {
+          const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 y;
+          if (p3) y = make_float4(acc[e] + acl[e], acc[e + 1] + acl[e + 1], acc[e + 2] + acl[e + 2], acc[e + 3] + acl[e + 3]);
+          else y = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+          y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
+          if (a.act == DESIRE_ACT_RELU) {
+            y.x = fmaxf(y.x, 0.f);
+            y.y = fmaxf(y.y, 0.f);
+            y.z = fmaxf(y.z, 0.f);
+            y.w = fmaxf(y.w, 0.f);
           }
+          *reinterpret_cast<float4*>(patch + lane * pitch + (n0 + e) * 4) = y;
         }
       }
+      __syncwarp();
+      const int ch = lane % cpr, rsub = lane / cpr;
+#pragma unroll 1
+      for (int it = 0; it < 32; it += rpi) {
+        const int row = it + rsub;
+        const int p = mt * 128 + 32 * q4 + row;
+        const int r = p / C5_WP, c = p - r * C5_WP;
+        const int oy = y0 + r, ox = x0 + c;
+        if (r < C5_TH && c < C5_TW && oy < a.H && ox < a.W) {
+          const float4 y = *reinterpret_cast<const float4*>(patch + row * pitch + ch * 16);
+          *reinterpret_cast<float4*>(a.Y + (((size_t)img * a.H + oy) * a.W + ox) * a.ldc + ch * 4) = y;
+        }
+      }
+      __syncwarp();
     }
   }
+  if (tid == 0) TRACE(7);
   tc_fence_before();
   __syncthreads();
   if (warp == C5_PW) tmem_dealloc(tmem, tcols);
+  if (tid == 0) TRACE(8);
+#undef TRACE
 }
 
 size_t c5_smem(int Cin, int Cout) {
@@ -234,7 +277,7 @@ size_t c5_smem(int Cin, int Cout) {
 
 size_t conv5_tc_pack_bytes(int Cin, int Cout) { return (size_t)25 * 4 * Cin * Cout; }
 
-// 5x5 / stride 1 / SAME over NHWC, Cin in {16, 32}, Cout in {16, 32, 64}, bias 16-byte aligned, act NONE or RELU
+// 5x5 / stride 1 / SAME over NHWC, Cin in {16, 32}, Cout in {16, 32} (8 x 2*Cout accumulator columns), act NONE or RELU
 bool conv5_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs& pw) {
   static const bool off = [] {
     const char* e = getenv("DESIRE_NO_CONV5");
@@ -242,7 +285,7 @@ bool conv5_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs
   }();
   if (off || gemm_mode() == 0) return false;
   return g.kh == 5 && g.kw == 5 && g.stride == 1 && g.pad_t == 2 && g.pad_l == 2 && g.Hi == g.Ho && g.Wi == g.Wo &&
-         (g.Ci == 16 || g.Ci == 32) && (Cout == 16 || Cout == 32 || Cout == 64) && ldc % 4 == 0 &&
+         (g.Ci == 16 || g.Ci == 32) && (Cout == 16 || Cout == 32) && ldc % 4 == 0 &&
          (act == DESIRE_ACT_NONE || act == DESIRE_ACT_RELU) && pw.p && pw.bytes >= conv5_tc_pack_bytes(g.Ci, Cout) &&
          g.Ho <= 65535 * C5_TH;
 }
@@ -256,7 +299,13 @@ int conv5_tc(const float* X, const Im2col& g, int B, const float* w, int ldb, co
                    "conv5_tc: X, Y and bias must be 16-byte aligned");
   uint8_t* packed = reinterpret_cast<uint8_t*>(pw.p);
   DESIRE_LAUNCH(st, (c5_pack_kernel<<<std::min(148, (25 * g.Ci * Cout + 255) / 256), 256, 0, st>>>(w, ldb, g.Ci, Cout, packed)));
-  C5Args a{X, packed, bias, Y, B, g.Hi, g.Wi, g.Ci, Cout, ldc, act, gemm_mode() == 1 ? 1 : 3};
+  static long long* trace = nullptr;
+  static const bool want_trace = [] {
+    const char* e = getenv("DESIRE_CONV5_TRACE");
+    return e && e[0] == '1';
+  }();
+  if (want_trace && !trace) DESIRE_CUDA(cudaMalloc(&trace, 16 * sizeof(long long)));
+  C5Args a{X, packed, bias, Y, B, g.Hi, g.Wi, g.Ci, Cout, ldc, act, gemm_mode() == 1 ? 1 : 3, want_trace ? trace : nullptr};
   const dim3 grid((unsigned)((g.Wi + C5_TW - 1) / C5_TW), (unsigned)((g.Hi + C5_TH - 1) / C5_TH), (unsigned)B);
   const size_t smem = c5_smem(g.Ci, Cout);
   if (g.Ci == 16) {
@@ -265,6 +314,16 @@ int conv5_tc(const float* X, const Im2col& g, int B, const float* w, int ldb, co
   } else {
     DESIRE_ENSURE_SMEM(conv5_tc_kernel<32>, smem);
     DESIRE_LAUNCH(st, (conv5_tc_kernel<32><<<grid, C5_NTHR, smem, st>>>(a)));
+  }
+  if (want_trace) {
+    static int printed = 0;
+    long long h[16];
+    DESIRE_CUDA(cudaStreamSynchronize(st));
+    DESIRE_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    if (printed++ < 4)
+      fprintf(stderr, "conv5 trace Cin=%d (cycles from start): setup %lld staged %lld | mma: go %lld first tap issued %lld all issued %lld | "
+              "accumulators complete %lld epilogue done %lld end %lld\n", g.Ci, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0],
+              h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
   }
   return DESIRE_OK;
 }

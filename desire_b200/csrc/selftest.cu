@@ -109,7 +109,10 @@ __global__ void __launch_bounds__(160) tsmma_kernel(const float* __restrict__ A,
 
 // How fast does one thread's stream of tcgen05.mma (M = 128, K = 16, BF16) retire?  mode 0: both operands in shared
 // memory, 1: A in tensor memory.  Every CTA issues `iters` MMAs on the same operands; cycles of block 0 are returned.
-__global__ void __launch_bounds__(640) mma_rate_kernel(int mode, int N, int iters, long long* __restrict__ out) {
+__global__ void __launch_bounds__(640) mma_rate_kernel(int mode_, int N, int iters, long long* __restrict__ out) {
+  // mode = 100 * s + m: mode m with the A operand of the shared-memory descriptors starting s * 16 bytes into its first
+  // 8-row core matrix (conv5_tc.cu addresses filter taps this way)
+  const int mode = mode_ % 100, ashift = (mode_ / 100) * 16;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t bar, dummy, done0;
   __shared__ uint32_t tslot;
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(640) mma_rate_kernel(int mode, int N, int iter
     uint64_t da[4], db[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      da[j] = smem_desc(smem_u32(sm) + j * 2 * 128 * 16, 128 * 16, 128);
+      da[j] = smem_desc(smem_u32(sm) + ashift + j * 2 * 128 * 16, 128 * 16, 128);
       db[j] = smem_desc(sb + j * 2 * N * 16, N * 16, 128);
     }
     const long long t0 = clock64();
@@ -437,11 +440,11 @@ extern "C" int desire_selftest_tsmma(const float* A, const float* B, float* out_
 }
 
 extern "C" int desire_selftest_mma_rate(int mode, int N, int iters, int grid, long long* out_cycles, desire_stream_t stream) {
-  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode <= 23 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
+  DESIRE_CHECK_ARG(out_cycles && mode >= 0 && mode % 100 <= 23 && mode / 100 <= 7 && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && grid > 0,
                    "desire_selftest_mma_rate: bad arguments");
-  const size_t smem = 128 * 64 * 2 + 256 * 64 * 2 + (mode == 16 || mode == 23 ? 1024 * 16 : 0);
+  const size_t smem = 128 * 64 * 2 + 256 * 64 * 2 + (mode % 100 == 16 || mode % 100 == 23 ? 1024 * 16 : 0);
   DESIRE_ENSURE_SMEM(desire::mma_rate_kernel, smem);
-  desire::mma_rate_kernel<<<grid, mode >= 15 ? 608 : 128, smem, (cudaStream_t)stream>>>(mode, N, iters, out_cycles);
+  desire::mma_rate_kernel<<<grid, mode % 100 >= 15 ? 608 : 128, smem, (cudaStream_t)stream>>>(mode, N, iters, out_cycles);
   DESIRE_LAUNCH_CHECK();
   return DESIRE_OK;
 }
