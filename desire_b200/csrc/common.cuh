@@ -158,6 +158,9 @@ int sgemm_im2col(const float* X, const Im2col& g, const float* B, int ldb, const
 // conv5_tc.cu: 5x5 / stride 1 / SAME convolution over NHWC as an implicit GEMM on tcgen05 (the input tile is staged once
 // as the A operand; a filter tap is a start-address shift).  X [B, H, W, Cin], w [(ky, kx, ci), n] (ldb), Y [B, H, W, ldc].
 bool conv5_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs& pw);
+// the same kernel for 5x5 / stride 2 / SAME over a 3-channel image with even sides, staged space-to-depth (conv5_tc()
+// takes either geometry)
+bool conv5s2_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs& pw);
 int conv5_tc(const float* X, const Im2col& g, int B, const float* w, int ldb, const float* bias, float* Y, int ldc, int Cout,
              int act, cudaStream_t st, PackWs pw);
 // train step (gemm_f32.cu): dW[Kd,N] (ldw) += A^T @ B over M rows, A dense or implicit im2col; column sums

@@ -60,8 +60,36 @@ __global__ void c5_pack_kernel(const float* __restrict__ w, int ldb, int Cin, in
   }
 }
 
-template <int CIN>
+// Space-to-depth form of the 5x5 / stride-2 / SAME convolution of a 3-channel image with even sides (TF pads 1 before):
+//   out[oy, ox] = sum img[2 oy + ky - 1, 2 ox + kx - 1, c] w[ky, kx, c];   2 oy + ky - 1 = 2 (oy + a) + py,
+//   (a, py) = (-1, 1), (0, 0), (0, 1), (1, 0), (1, 1) for ky = 0..4
+// = a 3x3 / stride-1 convolution over S[Y, X, (py, px, c)] = img[2Y + py, 2X + px, c] (12 channels, padded to 16) with
+// w3[a, b, (py, px, c)] = w[2a + py + 1, 2b + px + 1, c] (zero where that tap does not exist).
+__global__ void c5_pack_s2d_kernel(const float* __restrict__ w, int ldb, int Cout, uint8_t* __restrict__ packed) {
+  const int total = 9 * 16 * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i % Cout, t = i / Cout, ci = t % 16, tap = t / 16;
+    const int a = tap / 3 - 1, b = tap % 3 - 1;
+    float x = 0.f;
+    if (ci < 12) {
+      const int py = ci / 6, px = (ci / 3) & 1, c = ci % 3;
+      const int ky = 2 * a + py + 1, kx = 2 * b + px + 1;
+      if (ky >= 0 && ky < 5 && kx >= 0 && kx < 5) x = __ldg(w + (size_t)((ky * 5 + kx) * 3 + c) * ldb + n);
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    const size_t slot = (size_t)4 * 16 * Cout;
+    const size_t o = (size_t)tap * slot + (size_t)(ci >> 3) * (2 * Cout * 16) + (size_t)n * 16 + (ci & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(packed + o) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(packed + o + (size_t)Cout * 16) = lo;
+  }
+}
+
+// S2D = false: X is the NHWC map [B, H, W, CIN], 25 taps.  S2D = true (CIN = 16): X is the 3-channel image
+// [B, 2H, 2W, 3], staged space-to-depth, 9 taps centred in the same (TH + 4) x (TW + 4) window.
+template <int CIN, bool S2D>
 __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
+  constexpr int KS = S2D ? 3 : 5, NT = KS * KS, OFF = S2D ? 1 : 0;
   constexpr int CK = CIN / 8;                                    // 8-channel K chunks
   constexpr int IMG = CK * C5_LBO;                               // bytes of one (hi or lo) operand image
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -106,7 +134,7 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
     // ===================== tap loader
     if (lane == 0) {
       RingPos rp;
-      for (int tap = 0; tap < 25; ++tap, rp.next(C5_NSLOT)) {
+      for (int tap = 0; tap < NT; ++tap, rp.next(C5_NSLOT)) {
         mbar_wait(&wempty[rp.slot], rp.ph ^ 1);
         mbar_arrive_expect_tx(&wfull[rp.slot], slot_bytes);
         bulk_g2s_hint(ring + (size_t)rp.slot * slot_bytes, a.packed + (size_t)tap * slot_bytes, slot_bytes, &wfull[rp.slot],
@@ -130,9 +158,9 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
     if (lane == 0) TRACE(3);
     RingPos rp;
     int ky = 0, kx = 0;
-    for (int tap = 0; tap < 25; ++tap, rp.next(C5_NSLOT)) {
+    for (int tap = 0; tap < NT; ++tap, rp.next(C5_NSLOT)) {
       const uint64_t db = desc_adv(d_ring, rp.slot * slot_bytes);
-      const uint32_t shift = (uint32_t)(ky * C5_WP + kx) * 16;    // the tap: a start address, nothing else
+      const uint32_t shift = (uint32_t)((ky + OFF) * C5_WP + kx + OFF) * 16;   // the tap: a start address, nothing else
       const uint64_t dah = desc_adv(d_ah, shift), dal = desc_adv(d_al, shift);
       mbar_wait(&wfull[rp.slot], rp.ph);
       tc_fence_after();
@@ -155,10 +183,10 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
           }
         }
         mma_commit(&wempty[rp.slot]);
-        if (tap == 24) mma_commit(tfull);
+        if (tap == NT - 1) mma_commit(tfull);
       }
       if (lane == 0 && tap == 0) TRACE(4);
-      if (++kx == 5) {
+      if (++kx == KS) {
         kx = 0;
         ++ky;
       }
@@ -167,7 +195,53 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
     __syncwarp();
   } else {
     // ===================== stage the tile: item = (pixel, 8-channel chunk); a warp reads 8 pixels x CIN*4 contiguous bytes
-    {
+    if constexpr (S2D) {
+      // item = one space-to-depth pixel: two 24-byte runs of the image (rows 2Y and 2Y + 1, pixels 2X and 2X + 1)
+      const int NP = (rows + 4) * C5_WP;
+      const int Hi = 2 * a.H, Wi = 2 * a.W;
+      const float* xin = a.X + (size_t)img * Hi * Wi * 3;
+      constexpr int U = 3;
+      for (int i0 = tid; i0 < NP; i0 += U * C5_PT) {
+        float v[U][16];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int pix = i0 + u * C5_PT;
+          const int r = pix / C5_WP, c = pix - r * C5_WP;
+          const int Y = y0 - 2 + r, X = x0 - 2 + c;
+          const bool ok = pix < NP && Y >= 0 && Y < a.H && X >= 0 && X < a.W;
+          float2 f[6];
+#pragma unroll
+          for (int e = 0; e < 6; ++e) f[e] = make_float2(0.f, 0.f);
+          if (ok) {
+            const float2* p0 = reinterpret_cast<const float2*>(xin + ((size_t)(2 * Y) * Wi + 2 * X) * 3);
+            const float2* p1 = reinterpret_cast<const float2*>(xin + ((size_t)(2 * Y + 1) * Wi + 2 * X) * 3);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+              f[e] = __ldg(p0 + e);
+              f[3 + e] = __ldg(p1 + e);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 6; ++e) {
+            v[u][2 * e] = f[e].x;
+            v[u][2 * e + 1] = f[e].y;
+          }
+          v[u][12] = v[u][13] = v[u][14] = v[u][15] = 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int pix = i0 + u * C5_PT;
+          if (pix < NP) {
+            const Split8 s0 = split8(v[u]), s1 = split8(v[u] + 8);
+            const size_t o = (size_t)pix * 16;
+            *reinterpret_cast<uint4*>(a_hi + o) = s0.hi;
+            *reinterpret_cast<uint4*>(a_lo + o) = s0.lo;
+            *reinterpret_cast<uint4*>(a_hi + C5_LBO + o) = s1.hi;
+            *reinterpret_cast<uint4*>(a_lo + C5_LBO + o) = s1.lo;
+          }
+        }
+      }
+    } else {
       const int ITEMS = (rows + 4) * C5_WP * CK;
       const float* xin = a.X + (size_t)img * a.H * a.W * CIN;
       constexpr int U = 6;
@@ -201,11 +275,11 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
           }
         }
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
-      if (tid == 0) TRACE(2);
     }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready);
+    if (tid == 0) TRACE(2);
     // ===================== epilogue: warp w reads TMEM lanes 32*(w%4).. of position tiles w/4 and w/4 + 4
     mbar_wait(tfull, 0);
     tc_fence_after();
@@ -277,55 +351,79 @@ size_t c5_smem(int Cin, int Cout) {
 
 size_t conv5_tc_pack_bytes(int Cin, int Cout) { return (size_t)25 * 4 * Cin * Cout; }
 
-// 5x5 / stride 1 / SAME over NHWC, Cin in {16, 32}, Cout in {16, 32} (8 x 2*Cout accumulator columns), act NONE or RELU
-bool conv5_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs& pw) {
+namespace {
+bool c5_off() {
   static const bool off = [] {
     const char* e = getenv("DESIRE_NO_CONV5");
     return e && e[0] == '1';
   }();
-  if (off || gemm_mode() == 0) return false;
-  return g.kh == 5 && g.kw == 5 && g.stride == 1 && g.pad_t == 2 && g.pad_l == 2 && g.Hi == g.Ho && g.Wi == g.Wo &&
-         (g.Ci == 16 || g.Ci == 32) && (Cout == 16 || Cout == 32) && ldc % 4 == 0 &&
-         (act == DESIRE_ACT_NONE || act == DESIRE_ACT_RELU) && pw.p && pw.bytes >= conv5_tc_pack_bytes(g.Ci, Cout) &&
-         g.Ho <= 65535 * C5_TH;
+  return off || gemm_mode() == 0;
 }
 
-int conv5_tc(const float* X, const Im2col& g, int B, const float* w, int ldb, const float* bias, float* Y, int ldc, int Cout,
-             int act, cudaStream_t st, PackWs pw) {
-  if (B <= 0) return DESIRE_OK;
-  DESIRE_CHECK_ARG(conv5_tc_eligible(g, Cout, ldc, act, pw) && B <= 65535, "conv5_tc: not eligible");
-  DESIRE_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
-                       (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
-                   "conv5_tc: X, Y and bias must be 16-byte aligned");
-  uint8_t* packed = reinterpret_cast<uint8_t*>(pw.p);
-  DESIRE_LAUNCH(st, (c5_pack_kernel<<<std::min(148, (25 * g.Ci * Cout + 255) / 256), 256, 0, st>>>(w, ldb, g.Ci, Cout, packed)));
+template <int CIN, bool S2D>
+int c5_launch(const C5Args& a0, int taps_ci, cudaStream_t st) {
   static long long* trace = nullptr;
   static const bool want_trace = [] {
     const char* e = getenv("DESIRE_CONV5_TRACE");
     return e && e[0] == '1';
   }();
   if (want_trace && !trace) DESIRE_CUDA(cudaMalloc(&trace, 16 * sizeof(long long)));
-  C5Args a{X, packed, bias, Y, B, g.Hi, g.Wi, g.Ci, Cout, ldc, act, gemm_mode() == 1 ? 1 : 3, want_trace ? trace : nullptr};
-  const dim3 grid((unsigned)((g.Wi + C5_TW - 1) / C5_TW), (unsigned)((g.Hi + C5_TH - 1) / C5_TH), (unsigned)B);
-  const size_t smem = c5_smem(g.Ci, Cout);
-  if (g.Ci == 16) {
-    DESIRE_ENSURE_SMEM(conv5_tc_kernel<16>, smem);
-    DESIRE_LAUNCH(st, (conv5_tc_kernel<16><<<grid, C5_NTHR, smem, st>>>(a)));
-  } else {
-    DESIRE_ENSURE_SMEM(conv5_tc_kernel<32>, smem);
-    DESIRE_LAUNCH(st, (conv5_tc_kernel<32><<<grid, C5_NTHR, smem, st>>>(a)));
-  }
+  C5Args a = a0;
+  a.trace = want_trace ? trace : nullptr;
+  const dim3 grid((unsigned)((a.W + C5_TW - 1) / C5_TW), (unsigned)((a.H + C5_TH - 1) / C5_TH), (unsigned)a.B);
+  const size_t smem = c5_smem(CIN, a.Cout);
+  DESIRE_ENSURE_SMEM((conv5_tc_kernel<CIN, S2D>), smem);
+  DESIRE_LAUNCH(st, (conv5_tc_kernel<CIN, S2D><<<grid, C5_NTHR, smem, st>>>(a)));
   if (want_trace) {
     static int printed = 0;
     long long h[16];
     DESIRE_CUDA(cudaStreamSynchronize(st));
     DESIRE_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
-    if (printed++ < 4)
-      fprintf(stderr, "conv5 trace Cin=%d (cycles from start): setup %lld staged %lld | mma: go %lld first tap issued %lld all issued %lld | "
-              "accumulators complete %lld epilogue done %lld end %lld\n", g.Ci, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0],
-              h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
+    if (printed++ < 2)
+      fprintf(stderr, "conv5 trace Cin=%d%s (cycles from start): setup %lld staged %lld | mma: go %lld first tap issued %lld all issued %lld | "
+              "accumulators complete %lld epilogue done %lld end %lld\n", taps_ci, S2D ? " space-to-depth" : "", h[1] - h[0], h[2] - h[0],
+              h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
   }
   return DESIRE_OK;
+}
+}  // namespace
+
+// 5x5 / stride 1 / SAME over NHWC, Cin in {16, 32}, Cout in {16, 32} (8 x 2*Cout accumulator columns), act NONE or RELU
+bool conv5_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs& pw) {
+  if (c5_off()) return false;
+  return g.kh == 5 && g.kw == 5 && g.stride == 1 && g.pad_t == 2 && g.pad_l == 2 && g.Hi == g.Ho && g.Wi == g.Wo &&
+         (g.Ci == 16 || g.Ci == 32) && (Cout == 16 || Cout == 32) && ldc % 4 == 0 &&
+         (act == DESIRE_ACT_NONE || act == DESIRE_ACT_RELU) && pw.p && pw.bytes >= conv5_tc_pack_bytes(g.Ci, Cout) &&
+         g.Ho <= 65535 * C5_TH;
+}
+
+// 5x5 / stride 2 / SAME over a 3-channel image with even sides (TF: one pixel of padding before): the space-to-depth form
+bool conv5s2_tc_eligible(const Im2col& g, int Cout, int ldc, int act, const PackWs& pw) {
+  if (c5_off()) return false;
+  return g.kh == 5 && g.kw == 5 && g.stride == 2 && g.pad_t == 1 && g.pad_l == 1 && g.Ci == 3 && g.Hi % 2 == 0 &&
+         g.Wi % 2 == 0 && g.Ho == g.Hi / 2 && g.Wo == g.Wi / 2 && (Cout == 16 || Cout == 32) && ldc % 4 == 0 &&
+         (act == DESIRE_ACT_NONE || act == DESIRE_ACT_RELU) && pw.p && pw.bytes >= conv5_tc_pack_bytes(16, Cout) &&
+         g.Ho <= 65535 * C5_TH;
+}
+
+int conv5_tc(const float* X, const Im2col& g, int B, const float* w, int ldb, const float* bias, float* Y, int ldc, int Cout,
+             int act, cudaStream_t st, PackWs pw) {
+  if (B <= 0) return DESIRE_OK;
+  const bool s2d = g.stride == 2;
+  DESIRE_CHECK_ARG((s2d ? conv5s2_tc_eligible(g, Cout, ldc, act, pw) : conv5_tc_eligible(g, Cout, ldc, act, pw)) && B <= 65535,
+                   "conv5_tc: not eligible");
+  DESIRE_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
+                       (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+                   "conv5_tc: X, Y and bias must be 16-byte aligned");
+  uint8_t* packed = reinterpret_cast<uint8_t*>(pw.p);
+  C5Args a{X, packed, bias, Y, B, g.Ho, g.Wo, s2d ? 16 : g.Ci, Cout, ldc, act, gemm_mode() == 1 ? 1 : 3, nullptr};
+  if (s2d) {
+    DESIRE_LAUNCH(st, (c5_pack_s2d_kernel<<<std::min(148, (9 * 16 * Cout + 255) / 256), 256, 0, st>>>(w, ldb, Cout, packed)));
+    return c5_launch<16, true>(a, 3, st);
+  }
+  DESIRE_LAUNCH(st, (c5_pack_kernel<<<std::min(148, (25 * g.Ci * Cout + 255) / 256), 256, 0, st>>>(w, ldb, g.Ci, Cout, packed)));
+  if (g.Ci == 16) return c5_launch<16, false>(a, 16, st);
+  return c5_launch<32, false>(a, 32, st);
 }
 
 }  // namespace desire

@@ -503,8 +503,12 @@ extern "C" int desire_scene_cnn_fwd(const float* img, int B, int Hi, int Wi, int
     const int M = (int)(nb * px);
     ProfScope ps_(DESIRE_PROF_SCENE_CNN, st);
     Im2col g1{Hi, Wi, 3, Ho, Wo, 5, 5, 2, pt1, pl1};
-    DESIRE_TRY(sgemm_im2col(img + (size_t)b * Hi * Wi * 3, g1, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, M, 16, 75,
-                            DESIRE_ACT_RELU, st, pw));
+    if (conv5s2_tc_eligible(g1, 16, 16, DESIRE_ACT_RELU, pw))
+      DESIRE_TRY(conv5_tc(img + (size_t)b * Hi * Wi * 3, g1, nb, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, 16, DESIRE_ACT_RELU, st,
+                          pw));
+    else
+      DESIRE_TRY(sgemm_im2col(img + (size_t)b * Hi * Wi * 3, g1, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, M, 16, 75,
+                              DESIRE_ACT_RELU, st, pw));
     // layers 2 and 3: the tile-resident implicit GEMM (conv5_tc.cu) where it applies, im2col GEMM otherwise
     Im2col g2{Ho, Wo, 16, Ho, Wo, 5, 5, 1, 2, 2};
     if (conv5_tc_eligible(g2, 32, 32, DESIRE_ACT_RELU, pw))

@@ -1,5 +1,5 @@
 """-m gpu: the scene CNN (desire_scene_cnn_fwd) against the oracle's float64 convolutions at map sizes that exercise the
-tile-resident implicit-GEMM kernel of layers 2 and 3 (conv5_tc.cu): several row tiles with a partial last one, a map narrower
+tile-resident implicit-GEMM kernel (conv5_tc.cu: layers 2 and 3, and layer 1 in its space-to-depth form): several row tiles with a partial last one, a map narrower
 than a tile, two column tiles with a partial second one, odd sizes; and that kernel against the im2col GEMM it replaces."""
 import ctypes as C
 import os
@@ -52,7 +52,8 @@ def oracle64(img, P):
     return O.scene_cnn(img.astype(np.float64), P64)
 
 
-CASES = [(2, 64, 64, 32), (2, 256, 256, 32), (1, 300, 300, 32), (3, 30, 50, 32), (1, 14, 530, 16), (1, 2, 2, 64)]
+# (odd image sides: layer 1 keeps the im2col GEMM; Cs = 64: layer 3 does)
+CASES = [(2, 64, 64, 32), (2, 256, 256, 32), (1, 300, 300, 32), (3, 30, 50, 32), (1, 14, 530, 16), (1, 2, 2, 64), (2, 31, 45, 32)]
 
 
 @pytest.mark.parametrize("B,Hi,Wi,Cs", CASES)
@@ -69,7 +70,7 @@ def test_scene_cnn_matches_oracle(lib, B, Hi, Wi, Cs):
 
 
 def test_implicit_gemm_agrees_with_im2col_path():
-    """DESIRE_NO_CONV5=1 routes layers 2 and 3 through the im2col GEMM (gemm_tc.cu); both paths multiply the same BF16 hi/lo
+    """DESIRE_NO_CONV5=1 routes all three layers through the im2col GEMM (gemm_tc.cu); both paths multiply the same BF16 hi/lo
     splits and accumulate in FP32, in a different order."""
     code = (
         "import sys, numpy as np\n"

@@ -35,4 +35,4 @@ ms = e0.elapsed_time(e1) / 20
 px = B * (S // 2) ** 2
 flop = 2.0 * px * (75 * 16 + 400 * 32 + 800 * Cs)
 print("scene CNN B%d %dx%d: %.3f ms per call, %.1f TFLOP/s algorithmic (%s)" % (
-    B, S, S, ms, flop / (ms * 1e-3) / 1e12, "im2col" if os.environ.get("DESIRE_NO_CONV5") == "1" else "implicit GEMM layers 2, 3"))
+    B, S, S, ms, flop / (ms * 1e-3) / 1e12, "im2col GEMMs" if os.environ.get("DESIRE_NO_CONV5") == "1" else "tile-resident implicit GEMM"))
