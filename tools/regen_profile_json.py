@@ -21,6 +21,7 @@ MAP = {
     "cvae_deconv3_gemm": ("r2_deconv3", "cvae_deconv3_gemm"),
     "scene_gather": ("r2_gather", "scene_gather"),
     "readout_feature_pool": ("r2_readout", "readout_feature_pool"),
+    "scene_cnn_conv3_tile_resident": ("r2_conv5_l3", None),
 }
 UNITS = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
