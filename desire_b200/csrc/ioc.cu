@@ -474,6 +474,33 @@ int social_pool_launch(const float* pos, long pos_stride, const float* h, int ld
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ scene CNN
+// The three convolutions of the scene CNN over `nb` images: the tile-resident implicit GEMM (conv5_tc.cu) where it applies
+// (even image sides for layer 1, C_s in {16, 32} for layer 3), the im2col GEMM otherwise.  Forward pass and the backward
+// pass's recompute share it, so the ReLU masks of the backward are those of the forward.
+static int scene_cnn_layers(const float* img, int nb, int Hi, int Wi, int Cs, const desire_scene_cnn_t* w, float* f1, float* f2,
+                            float* f3, cudaStream_t st, PackWs pw) {
+  const int Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
+  const int M = (int)((size_t)nb * Ho * Wo);
+  // TF SAME: total pad = max((out-1)*s + k - in, 0), before = total/2
+  const int pt1 = max((Ho - 1) * 2 + 5 - Hi, 0) / 2, pl1 = max((Wo - 1) * 2 + 5 - Wi, 0) / 2;
+  Im2col g1{Hi, Wi, 3, Ho, Wo, 5, 5, 2, pt1, pl1};
+  if (conv5s2_tc_eligible(g1, 16, 16, DESIRE_ACT_RELU, pw))
+    DESIRE_TRY(conv5_tc(img, g1, nb, w->c1_w, 16, w->c1_b, f1, 16, 16, DESIRE_ACT_RELU, st, pw));
+  else
+    DESIRE_TRY(sgemm_im2col(img, g1, w->c1_w, 16, w->c1_b, f1, 16, M, 16, 75, DESIRE_ACT_RELU, st, pw));
+  Im2col g2{Ho, Wo, 16, Ho, Wo, 5, 5, 1, 2, 2};
+  if (conv5_tc_eligible(g2, 32, 32, DESIRE_ACT_RELU, pw))
+    DESIRE_TRY(conv5_tc(f1, g2, nb, w->c2_w, 32, w->c2_b, f2, 32, 32, DESIRE_ACT_RELU, st, pw));
+  else
+    DESIRE_TRY(sgemm_im2col(f1, g2, w->c2_w, 32, w->c2_b, f2, 32, M, 32, 400, DESIRE_ACT_RELU, st, pw));
+  Im2col g3{Ho, Wo, 32, Ho, Wo, 5, 5, 1, 2, 2};
+  if (conv5_tc_eligible(g3, Cs, Cs, DESIRE_ACT_RELU, pw))
+    DESIRE_TRY(conv5_tc(f2, g3, nb, w->c3_w, Cs, w->c3_b, f3, Cs, Cs, DESIRE_ACT_RELU, st, pw));
+  else
+    DESIRE_TRY(sgemm_im2col(f2, g3, w->c3_w, Cs, w->c3_b, f3, Cs, M, Cs, 800, DESIRE_ACT_RELU, st, pw));
+  return DESIRE_OK;
+}
+
 extern "C" size_t desire_scene_cnn_workspace_bytes(int B, int Hi, int Wi) {
   size_t Ho = (Hi + 1) / 2, Wo = (Wi + 1) / 2;
   return align_up((size_t)B * Ho * Wo * 16 * 4) + align_up((size_t)B * Ho * Wo * 32 * 4) + PACK_WS_BYTES;
@@ -492,36 +519,15 @@ extern "C" int desire_scene_cnn_fwd(const float* img, int B, int Hi, int Wi, int
   float* f1 = W.take<float>((size_t)B * Ho * Wo * 16);
   float* f2 = W.take<float>((size_t)B * Ho * Wo * 32);
   PackWs pw{W.take<char>(PACK_WS_BYTES), PACK_WS_BYTES};
-  // TF SAME: total pad = max((out-1)*s + k - in, 0), before = total/2
-  const int pt1 = max((Ho - 1) * 2 + 5 - Hi, 0) / 2, pl1 = max((Wo - 1) * 2 + 5 - Wi, 0) / 2;
   // all images of a chunk in one launch (a single 128x128 map is only 128 tiles — less than one wave);
   // chunks keep gridDim.y <= 65535 for any map size
   const size_t px = (size_t)Ho * Wo;
   const int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (size_t)65535 * 128 / px));
   for (int b = 0; b < B; b += per) {
     const int nb = std::min(per, B - b);
-    const int M = (int)(nb * px);
     ProfScope ps_(DESIRE_PROF_SCENE_CNN, st);
-    Im2col g1{Hi, Wi, 3, Ho, Wo, 5, 5, 2, pt1, pl1};
-    if (conv5s2_tc_eligible(g1, 16, 16, DESIRE_ACT_RELU, pw))
-      DESIRE_TRY(conv5_tc(img + (size_t)b * Hi * Wi * 3, g1, nb, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, 16, DESIRE_ACT_RELU, st,
-                          pw));
-    else
-      DESIRE_TRY(sgemm_im2col(img + (size_t)b * Hi * Wi * 3, g1, w->c1_w, 16, w->c1_b, f1 + b * px * 16, 16, M, 16, 75,
-                              DESIRE_ACT_RELU, st, pw));
-    // layers 2 and 3: the tile-resident implicit GEMM (conv5_tc.cu) where it applies, im2col GEMM otherwise
-    Im2col g2{Ho, Wo, 16, Ho, Wo, 5, 5, 1, 2, 2};
-    if (conv5_tc_eligible(g2, 32, 32, DESIRE_ACT_RELU, pw))
-      DESIRE_TRY(conv5_tc(f1 + b * px * 16, g2, nb, w->c2_w, 32, w->c2_b, f2 + b * px * 32, 32, 32, DESIRE_ACT_RELU, st, pw));
-    else
-      DESIRE_TRY(sgemm_im2col(f1 + b * px * 16, g2, w->c2_w, 32, w->c2_b, f2 + b * px * 32, 32, M, 32, 400, DESIRE_ACT_RELU,
-                              st, pw));
-    Im2col g3{Ho, Wo, 32, Ho, Wo, 5, 5, 1, 2, 2};
-    if (conv5_tc_eligible(g3, Cs, Cs, DESIRE_ACT_RELU, pw))
-      DESIRE_TRY(conv5_tc(f2 + b * px * 32, g3, nb, w->c3_w, Cs, w->c3_b, fmap + b * px * Cs, Cs, Cs, DESIRE_ACT_RELU, st, pw));
-    else
-      DESIRE_TRY(sgemm_im2col(f2 + b * px * 32, g3, w->c3_w, Cs, w->c3_b, fmap + b * px * Cs, Cs, M, Cs, 800, DESIRE_ACT_RELU,
-                              st, pw));
+    DESIRE_TRY(scene_cnn_layers(img + (size_t)b * Hi * Wi * 3, nb, Hi, Wi, Cs, w, f1 + b * px * 16, f2 + b * px * 32,
+                                fmap + b * px * Cs, st, pw));
   }
   return DESIRE_OK;
 }
@@ -1411,9 +1417,7 @@ extern "C" int desire_scene_cnn_bwd(const float* img, int B, int Hi, int Wi, int
     Im2col g2{Ho, Wo, 16, Ho, Wo, 5, 5, 1, 2, 2};
     Im2col g3{Ho, Wo, 32, Ho, Wo, 5, 5, 1, 2, 2};
     // forward recompute (the forward keeps only the final map)
-    DESIRE_TRY(sgemm_im2col(im, g1, w->c1_w, 16, w->c1_b, F1, 16, Mr, 16, 75, DESIRE_ACT_RELU, st, pw));
-    DESIRE_TRY(sgemm_im2col(F1, g2, w->c2_w, 32, w->c2_b, F2, 32, Mr, 32, 400, DESIRE_ACT_RELU, st, pw));
-    DESIRE_TRY(sgemm_im2col(F2, g3, w->c3_w, Cs, w->c3_b, F3, Cs, Mr, Cs, 800, DESIRE_ACT_RELU, st, pw));
+    DESIRE_TRY(scene_cnn_layers(im, nb, Hi, Wi, Cs, w, F1, F2, F3, st, pw));
     // conv3
     DESIRE_TRY(act_bwd_post(F3, Cs, DF3, Cs, (size_t)Mr, Cs, DESIRE_ACT_RELU, st));
     DESIRE_TRY(wgrad_tn_im2col(F2, g3, DF3, Cs, g->c3_w, Cs, Mr, 800, Cs, st));
