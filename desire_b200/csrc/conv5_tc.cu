@@ -283,6 +283,9 @@ __global__ void __launch_bounds__(C5_NTHR, 1) conv5_tc_kernel(C5Args a) {
     // ===================== epilogue: warp w reads TMEM lanes 32*(w%4).. of position tiles w/4 and w/4 + 4
     mbar_wait(tfull, 0);
     tc_fence_after();
+    // (the patches below alias the operand images other warps staged; tfull already orders them — every staging store
+    // precedes a_ready, the MMAs and their commit — and this barrier states the same among the 16 warps themselves)
+    asm volatile("bar.sync 1, %0;" ::"n"(C5_PT) : "memory");
     if (tid == 0) TRACE(6);
     // thread = position (TMEM lane): add the halves, bias, ReLU, park the 32 x Cout patch in shared memory (the operand
     // images are dead; pitch Cout*4 + 16 bytes keeps the 16-byte accesses conflict-free), then write it out with lanes
